@@ -1,0 +1,188 @@
+/*
+ * swegl_b200.h — C ABI of the B200-native replacement for swegl's per-frame
+ * rendering hot path.
+ *
+ * The reference (gbizzotto/swegl) has no FFI; its boundary is one C++ call,
+ *     swegl::render(scene_t&, viewport_t&...)          swegl/render/renderer.hpp:27-34
+ * which runs vertex_shader_t::original_to_world once (vertex_shaders.hpp:16-33)
+ * and then swegl::_render(scene, viewport) per viewport (src/render/renderer.cpp:77-235).
+ * This header is what a maintainer binds from the body of those two functions
+ * (see INTEGRATION.md and swegl_b200/host/swegl_b200_adapter.hpp): plain
+ * pointers and sizes only, `int` status returns (0 = ok), no C++ or torch
+ * types.  There is no CPU fallback: every entry point fails with
+ * SWEGL_B200_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Data layout conventions (all little-endian, tightly packed):
+ *   - matrices are row-major float[16] exactly like swegl::matrix44_t
+ *     (freon::Matrix<float,4,4>, m[row][col]),
+ *   - colours are 32-bit words with bytes b,g,r,a (swegl/render/colors.hpp:9-18),
+ *   - vertex attributes are SoA copies of mesh_vertex_t::{v, normal, tex_coords}
+ *     (swegl/data/model.hpp:20-29) flattened over nodes -> primitives in
+ *     scene.nodes order, which is also the draw order of renderer.cpp:83-231.
+ */
+#ifndef SWEGL_B200_H
+#define SWEGL_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWEGL_B200_ABI_VERSION 1
+
+/* ---- status codes (reference has none: void + assert, renderer.cpp:98-100) ---- */
+enum {
+    SWEGL_B200_OK              = 0,
+    SWEGL_B200_ERR_ARG         = 1,  /* null pointer / bad size / bad enum               */
+    SWEGL_B200_ERR_CUDA        = 2,  /* CUDA runtime error, see swegl_b200_last_error()   */
+    SWEGL_B200_ERR_UNSUPPORTED = 3,  /* shader / transparency combination not on device   */
+    SWEGL_B200_ERR_CAPACITY    = 4,  /* internal span/chunk pool exhausted even after grow*/
+    SWEGL_B200_ERR_STATE       = 5   /* call order (render before upload, ...)            */
+};
+
+/* primitive_t::index_mode_t, swegl/data/model.hpp:33-42 (glTF mode codes) */
+enum {
+    SWEGL_B200_MODE_TRIANGLES      = 4,
+    SWEGL_B200_MODE_TRIANGLE_STRIP = 5,
+    SWEGL_B200_MODE_TRIANGLE_FAN   = 6
+};
+
+/* which pixel_shader_t the viewport carries (swegl/render/pixel_shaders.hpp:15-179).
+ * COMBINED = pixel_shader_light_and_texture<L,T> (:121-179): texture colour scaled by light. */
+enum { SWEGL_B200_LIGHT_NONE = 0, SWEGL_B200_LIGHT_FLAT = 1, SWEGL_B200_LIGHT_PHONG = 2 };
+enum { SWEGL_B200_TEX_PLAIN = 0, SWEGL_B200_TEX_NEAREST = 1, SWEGL_B200_TEX_BILINEAR = 2 };
+/* post_shader_t (null / copy, post_shaders.hpp:15-48) or post_shader_depth_box (:51-132, as
+ * repaired: "DoF-R") */
+enum { SWEGL_B200_POST_NULL = 0, SWEGL_B200_POST_DOF = 1 };
+
+typedef struct swegl_b200_primitive {
+    int32_t  node;          /* index of the owning node_t in scene.nodes                 */
+    int32_t  mode;          /* SWEGL_B200_MODE_*                                         */
+    int32_t  material_id;   /* primitive_t::material_id, -1 = scene.default_material     */
+    uint32_t first_vertex;  /* offset into the SoA vertex arrays                         */
+    uint32_t n_vertices;    /* real vertices (the 2 spare clip slots are NOT uploaded)   */
+    uint32_t first_index;   /* offset into indices[]                                     */
+    uint32_t n_indices;     /* indices are relative to first_vertex, as in primitive_t   */
+} swegl_b200_primitive;
+
+/* material_t, swegl/data/model.hpp:80-87 */
+typedef struct swegl_b200_material {
+    uint8_t  b, g, r, a;    /* material_t::color                                         */
+    float    metallic, roughness;
+    int32_t  texture_idx;   /* -1 = none: a 1x1 bitmap of `color` is sampled instead     */
+    int32_t  double_sided;
+} swegl_b200_material;
+
+/* texture_t level 0 only (pixel_shaders.cpp:298-300), row-major BGRA words */
+typedef struct swegl_b200_texture {
+    const uint32_t *texels;
+    int32_t width, height;
+} swegl_b200_texture;
+
+/* everything that is static after load_scene() */
+typedef struct swegl_b200_scene_desc {
+    uint32_t n_nodes, n_primitives, n_vertices, n_indices, n_materials, n_textures;
+    const swegl_b200_primitive *primitives;   /* in draw order                             */
+    const float    *positions;                /* 3*n_vertices, mesh_vertex_t::v            */
+    const float    *normals;                  /* 3*n_vertices, mesh_vertex_t::normal       */
+    const float    *texcoords;                /* 2*n_vertices, tex_coords.x(), .y()        */
+    const uint32_t *indices;                  /* n_indices                                  */
+    const swegl_b200_material *materials;     /* n_materials                                */
+    swegl_b200_material default_material;     /* scene_t::default_material                  */
+    const swegl_b200_texture *textures;       /* n_textures, scene_t::images                */
+} swegl_b200_scene_desc;
+
+/* what may change every frame: node transforms and lights (test_1.cpp:288-303,378).
+ * The node-hierarchy product (freon::operator*, vertex_shaders.hpp:18) stays on the
+ * host; the device only does matrix x vertex. */
+typedef struct swegl_b200_frame_desc {
+    const float *node_world;   /* n_nodes*16: node_t::original_to_world_matrix            */
+    const float *node_normal;  /* n_nodes*9 : upper 3x3 of scale(node.rotation,node.scale) */
+    float    ambient;          /* scene_t::ambient_light_intensity                         */
+    float    sun_dir[3];       /* scene_t::sun_direction (already normalised)              */
+    float    sun_intensity;
+    uint32_t n_point_lights;
+    const float *point_lights; /* n*4: position xyz, intensity (point_source_light)        */
+} swegl_b200_frame_desc;
+
+/* viewport_t + camera_t + shader selection, swegl/render/viewport.hpp:27-62 */
+typedef struct swegl_b200_viewport_desc {
+    int32_t x, y, w, h;            /* m_x, m_y, m_w, m_h                                   */
+    float   view[16];              /* camera_t::m_viewmatrix                               */
+    float   proj[16];              /* camera_t::m_projectionmatrix                         */
+    float   cam_pos[3];            /* camera_t::m_center                                   */
+    float   vp_m00, vp_m03;        /* m_viewportmatrix[0][0], [0][3]  (viewport.cpp:30-35) */
+    float   vp_m11, vp_m13;        /* m_viewportmatrix[1][1], [1][3]                       */
+    int32_t light_mode;            /* SWEGL_B200_LIGHT_*                                   */
+    int32_t tex_mode;              /* SWEGL_B200_TEX_*                                     */
+    int32_t post_mode;             /* SWEGL_B200_POST_*                                    */
+    float   focal_distance;        /* post_shader_depth_box::focal_distance                */
+    float   focal_depth;           /* post_shader_depth_box::focal_depth                   */
+    int32_t transparency_layers;   /* ctor argument; >0 only supported for opaque scenes   */
+    int32_t band_y0, band_y1;      /* sort-first scissor, viewport-relative rows
+                                      [band_y0, band_y1); (0,0) = whole viewport           */
+} swegl_b200_viewport_desc;
+
+/* per-frame counters, filled by the render calls when non-null */
+typedef struct swegl_b200_stats {
+    uint32_t n_setup_triangles;    /* triangles that reached fill_triangle_2               */
+    uint32_t n_spans;              /* scanline spans walked                                */
+    uint32_t n_chunks;             /* <=32-pixel span pieces binned                        */
+    uint32_t n_covered;            /* pixels whose depth != 0x7F7F7F7F after the frame     */
+    uint32_t n_launches;           /* kernels launched by the call                         */
+    uint32_t pool_grows;           /* times the span/chunk pools had to be enlarged        */
+    float    ms_vertex, ms_setup, ms_raster, ms_fragment, ms_post, ms_total;
+                                   /* CUDA-event times, only when timing is enabled        */
+} swegl_b200_stats;
+
+typedef struct swegl_b200_ctx swegl_b200_ctx;
+
+/* ---- lifetime ---- */
+int  swegl_b200_abi_version(void);
+int  swegl_b200_create(int device, swegl_b200_ctx **out);
+void swegl_b200_destroy(swegl_b200_ctx *ctx);
+const char *swegl_b200_last_error(const swegl_b200_ctx *ctx);
+/* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the ctx's own */
+int  swegl_b200_set_stream(swegl_b200_ctx *ctx, void *cuda_stream);
+/* enable CUDA-event stage timing into swegl_b200_stats (adds synchronisation) */
+int  swegl_b200_set_timing(swegl_b200_ctx *ctx, int enabled);
+
+/* ---- scene ---- */
+/* replaces nothing in the reference (its scene lives in host vectors); uploads the static part */
+int  swegl_b200_upload_scene(swegl_b200_ctx *ctx, const swegl_b200_scene_desc *scene);
+/* the screen (SDL_Surface w,h) the viewports draw into; device copy is cleared to 0 */
+int  swegl_b200_set_screen(swegl_b200_ctx *ctx, int32_t screen_w, int32_t screen_h);
+
+/* ---- frame ---- */
+/* replaces vertex_shader_t::original_to_world's per-vertex loop (vertex_shaders.hpp:20-24):
+ * uploads node matrices + lights and computes v_world for every vertex. Once per frame. */
+int  swegl_b200_begin_frame(swegl_b200_ctx *ctx, const swegl_b200_frame_desc *frame);
+
+/* replaces swegl::_render(scene, viewport) (renderer.cpp:77-235), result left in HBM. */
+int  swegl_b200_render_viewport_device(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *vp,
+                                       swegl_b200_stats *stats);
+/* same + copies the viewport rectangle into host `pixels` (SDL_Surface::pixels, rows
+ * `pitch_bytes` apart, absolute screen coordinates) and, if non-null, the viewport's
+ * depth buffer into host `zbuffer` (w*h floats, viewport_t::m_zbuffer). Synchronous. */
+int  swegl_b200_render_viewport(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *vp,
+                                void *pixels, int32_t pitch_bytes, float *zbuffer,
+                                swegl_b200_stats *stats);
+
+/* ---- read-back of device state (parity tests, multi-GPU gather) ---- */
+/* device pointers of the screen (screen_w*screen_h words) and of the last viewport's depth */
+int  swegl_b200_device_buffers(swegl_b200_ctx *ctx, void **screen_dev, void **depth_dev);
+/* copy rows [y0,y1) of the device screen to host */
+int  swegl_b200_read_screen(swegl_b200_ctx *ctx, int32_t y0, int32_t y1, void *pixels, int32_t pitch_bytes);
+int  swegl_b200_read_depth(swegl_b200_ctx *ctx, float *zbuffer);
+/* post-render vertex state of the last viewport, as the reference leaves it in
+ * mesh_vertex_t: any pointer may be null. v_viewport holds pixel coordinates
+ * for yes-vertices and NDC for the others (vertex_shaders.hpp:72-84). */
+int  swegl_b200_read_vertices(swegl_b200_ctx *ctx, float *v_world, float *v_viewport,
+                              float *normal_world, uint8_t *yes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWEGL_B200_H */

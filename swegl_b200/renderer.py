@@ -1,0 +1,106 @@
+"""Python front end of the C ABI (include/swegl_b200.h), mirroring the reference's call sequence
+
+    swegl::render(scene, viewport...)          swegl/render/renderer.hpp:27-34
+      -> original_to_world(scene)              Renderer.begin_frame(scene)
+      -> _render(scene, viewport) each         Renderer.render(viewport, pixels)
+
+There is no CPU path behind these calls: they fail loudly when the CUDA library or device is missing.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+
+
+class SweglB200Error(RuntimeError):
+    pass
+
+
+class Renderer:
+    def __init__(self, device=0, stream=None):
+        self.lib = _abi.load()
+        if self.lib.swegl_b200_abi_version() != 1:
+            raise SweglB200Error("ABI version mismatch between swegl_b200/_abi.py and libswegl_b200.so")
+        self.ctx = C.c_void_p()
+        rc = self.lib.swegl_b200_create(int(device), C.byref(self.ctx))
+        if rc != _abi.OK:
+            raise SweglB200Error(f"swegl_b200_create(device={device}) failed with status {rc} "
+                                 "(no CUDA device? swegl_b200 has no CPU fallback)")
+        if stream is not None:
+            self._check(self.lib.swegl_b200_set_stream(self.ctx, C.c_void_p(int(stream))))
+        self.scene = None
+        self.screen_wh = None
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.swegl_b200_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != _abi.OK:
+            msg = self.lib.swegl_b200_last_error(self.ctx)
+            raise SweglB200Error(f"swegl_b200 status {rc}: {msg.decode() if msg else ''}")
+
+    def set_timing(self, enabled=True):
+        self._check(self.lib.swegl_b200_set_timing(self.ctx, int(enabled)))
+
+    def upload_scene(self, scene):
+        self.scene = scene
+        sd = scene.scene_desc()
+        self._check(self.lib.swegl_b200_upload_scene(self.ctx, C.byref(sd)))
+
+    def set_screen(self, w, h):
+        self.screen_wh = (int(w), int(h))
+        self._check(self.lib.swegl_b200_set_screen(self.ctx, int(w), int(h)))
+
+    def begin_frame(self, scene=None, node_mats=None):
+        scene = scene or self.scene
+        fd = scene.frame_desc(*(node_mats or (None, None)))
+        self._check(self.lib.swegl_b200_begin_frame(self.ctx, C.byref(fd)))
+
+    def render_device(self, viewport, stats=True):
+        """_render() with the result left in HBM."""
+        vd = viewport.desc() if not isinstance(viewport, _abi.ViewportDesc) else viewport
+        st = _abi.Stats()
+        self._check(self.lib.swegl_b200_render_viewport_device(self.ctx, C.byref(vd), C.byref(st) if stats else None))
+        return st
+
+    def render(self, viewport, pixels, zbuffer=None, stats=True):
+        """_render() into host memory: `pixels` is the (screen_h, screen_w) uint32 surface."""
+        vd = viewport.desc() if not isinstance(viewport, _abi.ViewportDesc) else viewport
+        st = _abi.Stats()
+        zptr = zbuffer.ctypes.data if zbuffer is not None else None
+        self._check(self.lib.swegl_b200_render_viewport(self.ctx, C.byref(vd), pixels.ctypes.data, pixels.strides[0],
+                                                        zptr, C.byref(st) if stats else None))
+        return st
+
+    def read_screen(self, y0=0, y1=None):
+        w, h = self.screen_wh
+        y1 = h if y1 is None else y1
+        out = np.empty((y1 - y0, w), dtype=np.uint32)
+        self._check(self.lib.swegl_b200_read_screen(self.ctx, y0, y1, out.ctypes.data, w * 4))
+        return out
+
+    def read_depth(self, w, h):
+        out = np.empty((h, w), dtype=np.float32)
+        self._check(self.lib.swegl_b200_read_depth(self.ctx, out.ctypes.data))
+        return out
+
+    def read_vertices(self):
+        nv = self.scene.n_vertices
+        vw, vv, nw = (np.zeros((nv, 3), np.float32) for _ in range(3))
+        yes = np.zeros(nv, np.uint8)
+        self._check(self.lib.swegl_b200_read_vertices(self.ctx, vw.ctypes.data, vv.ctypes.data, nw.ctypes.data, yes.ctypes.data))
+        return dict(v_world=vw, v_viewport=vv, normal_world=nw, yes=yes)
+
+    def device_buffers(self):
+        s, d = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.swegl_b200_device_buffers(self.ctx, C.byref(s), C.byref(d)))
+        return s.value, d.value

@@ -1,0 +1,407 @@
+"""Host-side scene containers for the Python harness (tests, bench).
+
+The C++ drop-in (swegl_b200/host/swegl_b200_adapter.hpp) reads swegl's own scene_t/viewport_t;
+this module is the same thing for Python callers: a flattened scene in the layout
+include/swegl_b200.h wants, plus bit-exact restatements of the tiny pieces of host math the
+reference does per frame on the CPU and that stay on the host in this design:
+
+  * camera_t                     swegl/projection/camera.hpp:10-24, src/projection/camera.cpp:8-58
+  * matrix44_t::rotate_{x,y,z}   src/projection/matrix44.cpp:11-66
+  * viewport matrix              src/render/viewport.cpp:30-35
+  * node_t::get_local_world_matrix + hierarchy product   swegl/data/model.hpp:56-61,
+                                 swegl/render/vertex_shaders.hpp:16-33 (freon::operator*, see
+                                 oracle/shims/freon/Matrix.hpp for the product order used)
+
+All arithmetic is done on numpy float32 scalars so every operation rounds like the C++ code.
+"""
+import io
+import json
+import math
+import zipfile
+
+import numpy as np
+
+from . import _abi
+
+f32 = np.float32
+
+
+def _cosf(a):
+    return f32(math.cos(float(f32(a))))
+
+
+def _sinf(a):
+    return f32(math.sin(float(f32(a))))
+
+
+def identity44():
+    return np.eye(4, dtype=np.float32)
+
+
+def _rotate_rows(m, a, r0, r1):
+    """matrix44_t::rotate_*: new_r0 = cos*old_r0 + sin*old_r1 ; new_r1 = -sin*old_r0 + cos*old_r1."""
+    c, s = _cosf(a), _sinf(a)
+    old0 = m[r0].copy()
+    old1 = m[r1].copy()
+    for j in range(4):
+        m[r0, j] = f32(c * old0[j]) + f32(s * old1[j])
+        m[r1, j] = f32(f32(-s) * old0[j]) + f32(c * old1[j])
+
+
+def rotate_x(m, a):
+    _rotate_rows(m, a, 1, 2)
+
+
+def rotate_y(m, a):
+    _rotate_rows(m, a, 0, 2)
+
+
+def rotate_z(m, a):
+    _rotate_rows(m, a, 0, 1)
+
+
+def matmul44(a, b):
+    """freon::operator* as defined by oracle/shims/freon/Matrix.hpp: s = 0; s += a[i][k]*b[k][j]."""
+    out = np.zeros((4, 4), dtype=np.float32)
+    for i in range(4):
+        for j in range(4):
+            s = f32(0)
+            for k in range(4):
+                s = f32(s + f32(a[i, k] * b[k, j]))
+            out[i, j] = s
+    return out
+
+
+def from_quaternion(q0, q1, q2, q3):
+    """matrix44_t::from_quaternion, swegl/projection/matrix44.hpp:34-43 (argument order as written)."""
+    q0, q1, q2, q3 = f32(q0), f32(q1), f32(q2), f32(q3)
+    two, one = f32(2), f32(1)
+    m = np.zeros((4, 4), dtype=np.float32)
+    m[0, 0] = two * (q0 * q0 + q1 * q1) - one
+    m[0, 1] = two * (q1 * q2 - q0 * q3)
+    m[0, 2] = two * (q1 * q3 + q0 * q2)
+    m[1, 0] = two * (q1 * q2 + q0 * q3)
+    m[1, 1] = two * (q0 * q0 + q2 * q2) - one
+    m[1, 2] = two * (q2 * q3 - q0 * q1)
+    m[2, 0] = two * (q1 * q3 - q0 * q2)
+    m[2, 1] = two * (q2 * q3 + q0 * q1)
+    m[2, 2] = two * (q0 * q0 + q3 * q3) - one
+    m[3, 3] = one
+    return m
+
+
+class Camera:
+    """camera_t: view matrix, projection matrix and position (m_center)."""
+
+    def __init__(self, aspect_ratio):
+        aspect = f32(aspect_ratio)
+        self.center = np.zeros(3, dtype=np.float32)
+        self.view = identity44()
+        self.proj = identity44()
+        self.view[2, 2] = f32(-1)
+        n, f, w, h = f32(0.5), f32(10.0), f32(1.0), f32(1.0)
+        two = f32(2)
+        if aspect > 1:
+            self.proj[0, 0] = f32(two * n) / w
+            self.proj[1, 1] = f32(f32(aspect * two) * n) / h
+        else:
+            self.proj[0, 0] = f32(f32(f32(f32(1.0) / aspect) * two) * n) / w
+            self.proj[1, 1] = f32(two * n) / h
+        self.proj[2, 2] = f / f32(f - n)
+        self.proj[2, 3] = f32(f32(-f) * n) / f32(f - n)
+        self.proj[3, 2] = f32(1)
+
+    def rotate_x(self, a):
+        rotate_x(self.view, -f32(a))
+
+    def rotate_y(self, a):
+        rotate_y(self.view, -f32(a))
+
+    def rotate_z(self, a):
+        rotate_z(self.view, -f32(a))
+
+    def translate(self, x, y, z):
+        x, y, z = f32(x), f32(y), f32(z)
+        m = self.view
+        m[0, 3] = f32(m[0, 3] + f32(-x))
+        m[1, 3] = f32(m[1, 3] + f32(-y))
+        m[2, 3] = f32(m[2, 3] + f32(-z))
+        for c in range(3):
+            self.center[c] = f32(self.center[c] + f32(f32(f32(x * m[0, c]) + f32(y * m[1, c])) + f32(z * m[2, c])))
+
+    def apply(self, ops):
+        """ops: sequence of ("translate", x, y, z) / ("rotate_x", a) / ("rotate_y", a) / ("rotate_z", a)."""
+        for op in ops:
+            getattr(self, op[0])(*op[1:])
+        return self
+
+
+class Viewport:
+    """viewport_t: rectangle, camera, shader selection and post pass (swegl/render/viewport.hpp:27-62)."""
+
+    def __init__(self, x, y, w, h, light_mode=_abi.LIGHT_PHONG, tex_mode=_abi.TEX_BILINEAR,
+                 transparency_layers=0, post_mode=_abi.POST_NULL, focal_distance=5.0, focal_depth=5.0):
+        self.x, self.y, self.w, self.h = int(x), int(y), int(w), int(h)
+        self.camera = Camera(1.0 * w / h)          # viewport.cpp:25: m_camera(1.0*w/h)
+        self.light_mode, self.tex_mode = light_mode, tex_mode
+        self.transparency_layers = transparency_layers
+        self.post_mode, self.focal_distance, self.focal_depth = post_mode, focal_distance, focal_depth
+        self.band = (0, 0)
+
+    def desc(self):
+        d = _abi.ViewportDesc()
+        d.x, d.y, d.w, d.h = self.x, self.y, self.w, self.h
+        d.view[:] = [float(v) for v in self.camera.view.reshape(-1)]
+        d.proj[:] = [float(v) for v in self.camera.proj.reshape(-1)]
+        d.cam_pos[:] = [float(v) for v in self.camera.center]
+        half = f32(2.0)
+        d.vp_m00 = float(f32(self.w) / half)                       # viewport.cpp:30-35
+        d.vp_m03 = float(f32(f32(self.x) + f32(self.w) / half))
+        d.vp_m11 = float(-(f32(self.h) / half))
+        d.vp_m13 = float(f32(f32(self.y) + f32(self.h) / half))
+        d.light_mode, d.tex_mode, d.post_mode = self.light_mode, self.tex_mode, self.post_mode
+        d.focal_distance, d.focal_depth = self.focal_distance, self.focal_depth
+        d.transparency_layers = self.transparency_layers
+        d.band_y0, d.band_y1 = self.band
+        return d
+
+
+def normalized3(x, y, z):
+    """normal_t(x,y,z): vector_t::normalize, swegl/projection/points.hpp:71-90,139-142."""
+    x, y, z = f32(x), f32(y), f32(z)
+    l = f32(math.sqrt(float(f32(f32(f32(x * x) + f32(y * y)) + f32(z * z)))))
+    if l != 0:
+        x, y, z = f32(x / l), f32(y / l), f32(z / l)
+    return np.array([x, y, z], dtype=np.float32)
+
+
+class Scene:
+    """Flattened scene_t (swegl/data/model.hpp:128-145): static geometry + per-frame node/light state."""
+
+    ARRAYS = ["node_scale", "node_rotation", "node_translation", "node_parent",
+              "prim_node", "prim_mode", "prim_material", "prim_first_vertex", "prim_n_vertices",
+              "prim_first_index", "prim_n_indices", "positions", "normals", "texcoords", "indices",
+              "mat_bgra", "mat_metal_rough", "mat_tex_ds"]
+
+    def __init__(self):
+        self.node_scale = np.zeros((0, 3), np.float32)
+        self.node_rotation = np.zeros((0, 4, 4), np.float32)
+        self.node_translation = np.zeros((0, 3), np.float32)
+        self.node_parent = np.zeros(0, np.int32)
+        for n in ["prim_node", "prim_mode", "prim_material"]:
+            setattr(self, n, np.zeros(0, np.int32))
+        for n in ["prim_first_vertex", "prim_n_vertices", "prim_first_index", "prim_n_indices", "indices"]:
+            setattr(self, n, np.zeros(0, np.uint32))
+        self.positions = np.zeros((0, 3), np.float32)
+        self.normals = np.zeros((0, 3), np.float32)
+        self.texcoords = np.zeros((0, 2), np.float32)
+        self.mat_bgra = np.zeros((0, 4), np.uint8)
+        self.mat_metal_rough = np.zeros((0, 2), np.float32)
+        self.mat_tex_ds = np.zeros((0, 2), np.int32)
+        self.textures = []                          # list of (h, w) uint32 BGRA arrays
+        self.default_material = (255, 255, 255, 255, 1.0, 1.0, -1, 0)   # material_t defaults, model.hpp:80-87
+        # lights: test_1.cpp:334-336 defaults
+        self.ambient = 0.3
+        self.sun_raw = (1.0, -2.0, -1.0)
+        self.sun_dir = normalized3(*self.sun_raw)
+        self.sun_intensity = 0.7
+        self.point_lights = np.zeros((0, 4), np.float32)
+        self.name = "scene"
+        self._keep = []
+
+    # ---- counts ----
+    @property
+    def n_nodes(self):
+        return len(self.node_parent)
+
+    @property
+    def n_primitives(self):
+        return len(self.prim_node)
+
+    @property
+    def n_vertices(self):
+        return len(self.positions)
+
+    def n_triangles(self):
+        t = 0
+        for mode, n in zip(self.prim_mode, self.prim_n_indices):
+            n = int(n)
+            if mode == _abi.MODE_TRIANGLES:
+                t += n // 3
+            elif n >= 3:
+                t += n - 2
+        return t
+
+    def set_lights(self, ambient, sun_xyz, sun_intensity, point_lights=()):
+        self.ambient = ambient
+        self.sun_raw = tuple(float(v) for v in sun_xyz)
+        self.sun_dir = normalized3(*sun_xyz)
+        self.sun_intensity = sun_intensity
+        self.point_lights = np.array(point_lights, dtype=np.float32).reshape(-1, 4)
+        return self
+
+    # ---- per-frame host math ----
+    def node_matrices(self):
+        """original_to_world_matrix (n,4,4) and the 3x3 of scale(rotation, scale) (n,3,3) per node."""
+        n = self.n_nodes
+        local = np.zeros((n, 4, 4), np.float32)
+        for i in range(n):
+            m = self.node_rotation[i].astype(np.float32).copy()
+            for c in range(3):                       # scale(): columns 0..2 of all four rows, points.cpp:14-30
+                m[:, c] = (m[:, c] * self.node_scale[i, c]).astype(np.float32)
+            for r in range(3):                       # translate(): model.hpp:59
+                m[r, 3] = f32(m[r, 3] + self.node_translation[i, r])
+            local[i] = m
+        world = np.zeros((n, 4, 4), np.float32)
+        done = np.zeros(n, bool)
+
+        def resolve(i):
+            if done[i]:
+                return
+            p = int(self.node_parent[i])
+            if p < 0:
+                world[i] = matmul44(identity44(), local[i])
+            else:
+                resolve(p)
+                world[i] = matmul44(world[p], local[i])
+            done[i] = True
+
+        for i in range(n):
+            resolve(i)
+        normal = np.ascontiguousarray(local[:, :3, :3])
+        # the translation is not part of the 3x3, so `local` before translate == after for these entries
+        return world, normal
+
+    # ---- ABI descriptors (keep numpy buffers alive in self._keep) ----
+    def scene_desc(self):
+        import ctypes as C
+        d = _abi.SceneDesc()
+        keep = []
+        prims = (_abi.Primitive * max(1, self.n_primitives))()
+        for i in range(self.n_primitives):
+            prims[i] = _abi.Primitive(int(self.prim_node[i]), int(self.prim_mode[i]), int(self.prim_material[i]),
+                                      int(self.prim_first_vertex[i]), int(self.prim_n_vertices[i]),
+                                      int(self.prim_first_index[i]), int(self.prim_n_indices[i]))
+        mats = (_abi.Material * max(1, len(self.mat_bgra)))()
+        for i in range(len(self.mat_bgra)):
+            b, g, r, a = (int(v) for v in self.mat_bgra[i])
+            mats[i] = _abi.Material(b, g, r, a, float(self.mat_metal_rough[i, 0]), float(self.mat_metal_rough[i, 1]),
+                                    int(self.mat_tex_ds[i, 0]), int(self.mat_tex_ds[i, 1]))
+        texs = (_abi.Texture * max(1, len(self.textures)))()
+        for i, t in enumerate(self.textures):
+            t = np.ascontiguousarray(t, dtype=np.uint32)
+            keep.append(t)
+            texs[i] = _abi.Texture(t.ctypes.data_as(C.POINTER(C.c_uint32)), t.shape[1], t.shape[0])
+
+        def fptr(a, dt, ct):
+            a = np.ascontiguousarray(a, dtype=dt)
+            keep.append(a)
+            return a.ctypes.data_as(C.POINTER(ct))
+
+        d.n_nodes, d.n_primitives, d.n_vertices = self.n_nodes, self.n_primitives, self.n_vertices
+        d.n_indices, d.n_materials, d.n_textures = len(self.indices), len(self.mat_bgra), len(self.textures)
+        d.primitives = prims
+        d.positions = fptr(self.positions, np.float32, C.c_float)
+        d.normals = fptr(self.normals, np.float32, C.c_float)
+        d.texcoords = fptr(self.texcoords, np.float32, C.c_float)
+        d.indices = fptr(self.indices, np.uint32, C.c_uint32)
+        d.materials = mats
+        dm = self.default_material
+        d.default_material = _abi.Material(dm[0], dm[1], dm[2], dm[3], dm[4], dm[5], dm[6], dm[7])
+        d.textures = texs
+        keep += [prims, mats, texs]
+        self._keep = keep
+        return d
+
+    def frame_desc(self, node_world=None, node_normal=None):
+        import ctypes as C
+        if node_world is None:
+            node_world, node_normal = self.node_matrices()
+        d = _abi.FrameDesc()
+        self._nw = np.ascontiguousarray(node_world, dtype=np.float32).reshape(-1)
+        self._nn = np.ascontiguousarray(node_normal, dtype=np.float32).reshape(-1)
+        self._pl = np.ascontiguousarray(self.point_lights, dtype=np.float32).reshape(-1)
+        d.node_world = self._nw.ctypes.data_as(C.POINTER(C.c_float))
+        d.node_normal = self._nn.ctypes.data_as(C.POINTER(C.c_float))
+        d.ambient = float(f32(self.ambient))
+        d.sun_dir[:] = [float(v) for v in self.sun_dir]
+        d.sun_intensity = float(f32(self.sun_intensity))
+        d.n_point_lights = len(self.point_lights)
+        d.point_lights = self._pl.ctypes.data_as(C.POINTER(C.c_float))
+        return d
+
+    # ---- scene packs (assets/*.scenepack): npz-style zip of the arrays + encoded images ----
+    def save_pack(self, path, encoded_images=None):
+        """encoded_images: list of original PNG/JPEG byte strings (kept small); else raw texels are stored."""
+        with zipfile.ZipFile(path, "w", zipfile.ZIP_DEFLATED) as z:
+            meta = {"format": "swegl_b200.scenepack.v1", "name": self.name,
+                    "default_material": list(self.default_material),
+                    "textures": []}
+            for name in self.ARRAYS:
+                buf = io.BytesIO()
+                np.save(buf, getattr(self, name))
+                z.writestr(name + ".npy", buf.getvalue())
+            for i, t in enumerate(self.textures):
+                entry = {"w": int(t.shape[1]), "h": int(t.shape[0]), "sha256": texel_digest(t)}
+                if encoded_images is not None and encoded_images[i] is not None:
+                    z.writestr(f"image_{i}.bin", encoded_images[i])
+                    entry["encoding"] = "image"
+                else:
+                    buf = io.BytesIO()
+                    np.save(buf, np.ascontiguousarray(t, dtype=np.uint32))
+                    z.writestr(f"image_{i}.npy", buf.getvalue())
+                    entry["encoding"] = "raw"
+                meta["textures"].append(entry)
+            z.writestr("meta.json", json.dumps(meta, indent=1))
+
+    @classmethod
+    def load_pack(cls, path):
+        s = cls()
+        with zipfile.ZipFile(path) as z:
+            meta = json.loads(z.read("meta.json"))
+            if meta.get("format") != "swegl_b200.scenepack.v1":
+                raise ValueError(f"{path}: not a swegl_b200 scene pack")
+            s.name = meta["name"]
+            s.default_material = tuple(meta["default_material"])
+            for name in cls.ARRAYS:
+                setattr(s, name, np.load(io.BytesIO(z.read(name + ".npy"))))
+            for i, entry in enumerate(meta["textures"]):
+                if entry["encoding"] == "raw":
+                    t = np.load(io.BytesIO(z.read(f"image_{i}.npy")))
+                else:
+                    t = decode_image_bgra(z.read(f"image_{i}.bin"))
+                if texel_digest(t) != entry["sha256"]:
+                    raise ValueError(f"{path}: image {i} decodes to different texels than when the pack was made "
+                                     "(image decoder drift); golden frames would not match")
+                s.textures.append(t)
+        return s
+
+
+def decode_image_bgra(data):
+    """PNG/JPEG bytes -> (h, w) uint32 array with bytes b,g,r,a; rows top-down; alpha 255 when absent
+    (the layout src/misc/image.cpp:93-258 produces)."""
+    from PIL import Image
+    im = Image.open(io.BytesIO(data))
+    has_alpha = im.mode in ("RGBA", "LA") or "transparency" in im.info
+    rgba = np.asarray(im.convert("RGBA"), dtype=np.uint8)
+    out = np.empty(rgba.shape, np.uint8)
+    out[..., 0], out[..., 1], out[..., 2] = rgba[..., 2], rgba[..., 1], rgba[..., 0]
+    out[..., 3] = rgba[..., 3] if has_alpha else 255
+    return np.ascontiguousarray(out).view(np.uint32).reshape(rgba.shape[0], rgba.shape[1])
+
+
+def texel_digest(a):
+    """sha256 of the texel bytes: guards scene packs against image-decoder drift."""
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a, dtype=np.uint32).tobytes()).hexdigest()
+
+
+def lcg_texture(size=1024, seed=12345):
+    """The seeded synthetic texture of SURVEY §8c: s = s*1664525 + 1013904223 (mod 2^32);
+    texel = 0xFF000000 | (s >> 8)."""
+    s, a, c, m32 = seed, 1664525, 1013904223, (1 << 32) - 1
+    vals = []
+    for _ in range(size * size):
+        s = (s * a + c) & m32
+        vals.append(0xFF000000 | (s >> 8))
+    return np.array(vals, dtype=np.uint64).astype(np.uint32).reshape(size, size)
