@@ -1,0 +1,152 @@
+"""The workloads of BASELINE.json / SURVEY.md §8(d), made concrete once for tests, bench and golden
+generation: scene + lights + viewport(s) + camera pose(s).
+
+Camera poses are lists of camera_t calls replayed on swegl_b200.scene.Camera (and, in the pinning tests,
+on the reference's own camera_t).
+"""
+import os
+
+import numpy as np
+
+from . import _abi
+from .scene import Scene, Viewport, f32, identity44, rotate_y, rotate_z, lcg_texture
+
+ASSETS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "assets")
+
+POSE_TEST1 = [("translate", 1, 2, -5), ("rotate_y", -0.2), ("rotate_x", -0.3)]        # src/test_1.cpp:359-361
+POSE_CLOSE = [("translate", 1, 2, -1.5), ("rotate_y", -0.2), ("rotate_x", -0.3)]
+POSE_BRAIN_CLOSE = [("translate", 1, 2, -1), ("rotate_y", -0.2), ("rotate_x", -0.3)]
+POSE_SPHERE = [("translate", 0, 0, -4.5)]                                             # SURVEY §8c synthetic
+POINT_LIGHTS = [(0.0, 3.0, 0.0, 0.6), (0.5, 2.0, 0.0, 100.0)]                         # src/test_1.cpp:74-75
+
+
+def make_sphere_scene(precision, radius=2.0, texture_size=1024):
+    """swegl::make_sphere(precision, radius, material 0) (swegl/data/model.hpp:393-464) as a flattened
+    Scene with the seeded LCG texture; arithmetic order follows matrix44_t::rotate_* and transform()."""
+    P = precision
+    angle = f32(f32(2 * f32(3.141592653589)) / f32(P))
+    half = f32(angle / f32(2))
+    # `small` after k rotate_z(angle/2) calls, `big` after k rotate_y(angle) calls
+    smalls = np.zeros((P + 1, 4, 4), np.float32)
+    m = identity44()
+    for k in range(P + 1):
+        smalls[k] = m
+        rotate_z(m, half)
+    bigs = np.zeros((P + 2, 4, 4), np.float32)
+    m = identity44()
+    for k in range(P + 2):
+        bigs[k] = m
+        rotate_y(m, angle)
+
+    def xform(M, v):            # transform(vertex_t, matrix44_t), points.cpp:8-13, vectorised in fp32
+        x, y, z = v[..., 0], v[..., 1], v[..., 2]
+        out = np.empty(np.broadcast(M[..., 0, 0], x).shape + (3,), np.float32)
+        for r in range(3):
+            out[..., r] = ((M[..., r, 0] * x + M[..., r, 1] * y) + M[..., r, 2] * z) + M[..., r, 3]
+        return out
+
+    base = xform(smalls, np.array([0.0, radius, 0.0], np.float32)[None, :])          # (P+1, 3)
+    rows = xform(bigs[:, None], base[None, :, :])                                    # (P+2, P+1, 3)
+    l = np.sqrt((rows[..., 0] * rows[..., 0] + rows[..., 1] * rows[..., 1]) + rows[..., 2] * rows[..., 2])
+    safe = np.where(l != 0, l, f32(1))
+    nrm = np.where((l != 0)[..., None], rows / safe[..., None], rows).astype(np.float32)
+    u = (np.arange(P + 1) / P).astype(np.float32)                                     # 1.0*sm/precision
+    vrow = (np.arange(P + 2) / P).astype(np.float32)                                  # 1.0*bg/precision
+
+    nprim, nvp = P + 1, 2 * (P + 1)
+    s = Scene()
+    s.name = f"sphere{P}"
+    s.node_scale = np.ones((1, 3), np.float32)
+    s.node_rotation = identity44()[None]
+    s.node_translation = np.zeros((1, 3), np.float32)
+    s.node_parent = np.array([-1], np.int32)
+    s.positions = np.concatenate([rows[:-1], rows[1:]], axis=1).reshape(-1, 3).astype(np.float32)
+    s.normals = np.concatenate([nrm[:-1], nrm[1:]], axis=1).reshape(-1, 3).astype(np.float32)
+    tc = np.empty((nprim, nvp, 2), np.float32)
+    tc[:, :P + 1, 0] = u[None]; tc[:, P + 1:, 0] = u[None]
+    tc[:, :P + 1, 1] = vrow[:-1, None]; tc[:, P + 1:, 1] = vrow[1:, None]
+    s.texcoords = tc.reshape(-1, 2)
+    idx = np.empty((P + 1, 2), np.uint32)
+    idx[:, 0] = P + 1 + np.arange(P + 1); idx[:, 1] = np.arange(P + 1)
+    s.indices = np.tile(idx.reshape(-1), nprim).astype(np.uint32)
+    s.prim_node = np.zeros(nprim, np.int32)
+    s.prim_mode = np.full(nprim, _abi.MODE_TRIANGLE_STRIP, np.int32)
+    s.prim_material = np.zeros(nprim, np.int32)
+    s.prim_first_vertex = (np.arange(nprim) * nvp).astype(np.uint32)
+    s.prim_n_vertices = np.full(nprim, nvp, np.uint32)
+    s.prim_first_index = (np.arange(nprim) * nvp).astype(np.uint32)
+    s.prim_n_indices = np.full(nprim, nvp, np.uint32)
+    s.mat_bgra = np.array([[128, 128, 128, 255]], np.uint8)
+    s.mat_metal_rough = np.ones((1, 2), np.float32)
+    s.mat_tex_ds = np.array([[0, 0]], np.int32)
+    s.textures = [lcg_texture(texture_size)]
+    return s
+
+
+_SCENE_CACHE = {}
+
+
+def load_scene(name):
+    if name not in _SCENE_CACHE:
+        if name.startswith("sphere"):
+            _SCENE_CACHE[name] = make_sphere_scene(int(name[len("sphere"):]))
+        else:
+            _SCENE_CACHE[name] = Scene.load_pack(os.path.join(ASSETS, name + ".scenepack"))
+    return _SCENE_CACHE[name]
+
+
+def _lights_test1(s, points=False):
+    return s.set_lights(0.3, (1.0, -2.0, -1.0), 0.7, POINT_LIGHTS if points else ())   # test_1.cpp:334-336
+
+
+def _lights_synth(s):
+    return s.set_lights(0.2, (1.0, -1.0, -1.0), 0.3, POINT_LIGHTS)                     # SURVEY §8c synthetic
+
+
+# name -> (scene, screen (w,h), lights fn, [viewport kwargs + pose], description)
+CONFIGS = {
+    "box_640": dict(scene="BoxTextured", screen=(640, 480), lights="test1", views=[dict(rect=(0, 0, 640, 480), pose=POSE_TEST1, layers=3)],
+                    desc="config 1: BoxTextured 640x480, Phong+bilinear, sun, 3 layers, test_1 pose"),
+    "box_640_close": dict(scene="BoxTextured", screen=(640, 480), lights="test1", views=[dict(rect=(0, 0, 640, 480), pose=POSE_CLOSE, layers=3)],
+                          desc="config 1 close pose (8.3% coverage)"),
+    "truck_1080": dict(scene="CesiumMilkTruck", screen=(1920, 1080), lights="test1+points", views=[dict(rect=(0, 0, 1920, 1080), pose=POSE_TEST1, layers=3)],
+                       desc="config 2: CesiumMilkTruck 1920x1080, Phong+bilinear, sun + 2 point lights (no bump map: none in the reference)"),
+    "truck_1080_sun": dict(scene="CesiumMilkTruck", screen=(1920, 1080), lights="test1", views=[dict(rect=(0, 0, 1920, 1080), pose=POSE_TEST1, layers=3)],
+                           desc="CesiumMilkTruck 1920x1080, sun only (survey hash 0418ee20dd2b64e1)"),
+    "truck_4k_dof": dict(scene="CesiumMilkTruck", screen=(3840, 2160), lights="test1+points",
+                         views=[dict(rect=(0, 0, 3840, 2160), pose=POSE_TEST1, layers=0, post=_abi.POST_DOF)],
+                         desc="north-star target: CesiumMilkTruck 3840x2160, Phong+bilinear, sun + 2 point lights, DoF-R(5,5)"),
+    "truck_4k": dict(scene="CesiumMilkTruck", screen=(3840, 2160), lights="test1", views=[dict(rect=(0, 0, 3840, 2160), pose=POSE_TEST1, layers=3)],
+                     desc="CesiumMilkTruck 3840x2160, sun only (survey hash a8310584d693ad8c)"),
+    "brainstem_4k": dict(scene="BrainStem", screen=(3840, 2160), lights="test1", views=[dict(rect=(0, 0, 3840, 2160), pose=POSE_TEST1, layers=3)],
+                         desc="BrainStem 3840x2160, test_1 pose (survey hash 8cea197b1c69d6f1)"),
+    "brainstem_4k_dof": dict(scene="BrainStem", screen=(3840, 2160), lights="test1",
+                             views=[dict(rect=(0, 0, 3840, 2160), pose=POSE_BRAIN_CLOSE, layers=0, post=_abi.POST_DOF)],
+                             desc="config 3: BrainStem 3840x2160 close pose, Phong+bilinear+DoF-R"),
+    "multiview_1080": dict(scene="CesiumMilkTruck", screen=(1920, 1080), lights="test1",
+                           views=[dict(rect=(0, 0, 960, 540), pose=POSE_TEST1, layers=0),
+                                  dict(rect=(960, 0, 960, 540), pose=[("translate", -1, 2, -5), ("rotate_y", 0.2), ("rotate_x", -0.3)], layers=0),
+                                  dict(rect=(0, 540, 960, 540), pose=[("translate", 0, 4, -4), ("rotate_x", -0.7)], layers=0),
+                                  dict(rect=(960, 540, 960, 540), pose=[("translate", 3, 1, -3), ("rotate_y", -0.7), ("rotate_x", -0.1)], layers=0)],
+                           desc="config 4: 2x2 split screen, 4 cameras (CesiumMilkTruck substituted for the missing BarramundiFish.glb)"),
+    "sphere100_1080": dict(scene="sphere100", screen=(1920, 1080), lights="synth", views=[dict(rect=(0, 0, 1920, 1080), pose=POSE_SPHERE, layers=0)],
+                           desc="make_sphere(100) 20 200 triangles, LCG texture, 1920x1080 (survey hash 72b4fc66d972867b)"),
+    "sphere1000_8k": dict(scene="sphere1000", screen=(7680, 4320), lights="synth", views=[dict(rect=(0, 0, 7680, 4320), pose=POSE_SPHERE, layers=0)],
+                          desc="config 5: make_sphere(1000) 2 002 000 triangles, LCG texture, 7680x4320 (survey hash 729fb9ef5c41fa64)"),
+}
+
+
+def build(name, light_mode=_abi.LIGHT_PHONG, tex_mode=_abi.TEX_BILINEAR):
+    """-> (scene, [Viewport...], (screen_w, screen_h), config dict)"""
+    cfg = CONFIGS[name]
+    s = load_scene(cfg["scene"])
+    {"test1": lambda: _lights_test1(s), "test1+points": lambda: _lights_test1(s, True), "synth": lambda: _lights_synth(s)}[cfg["lights"]]()
+    vps = []
+    for v in cfg["views"]:
+        x, y, w, h = v["rect"]
+        vp = Viewport(x, y, w, h, light_mode=light_mode, tex_mode=tex_mode, transparency_layers=v.get("layers", 0),
+                      post_mode=v.get("post", _abi.POST_NULL))
+        vp.camera.apply(v["pose"])
+        vp.pose = v["pose"]
+        vps.append(vp)
+    return s, vps, cfg["screen"], cfg

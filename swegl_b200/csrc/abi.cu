@@ -1,0 +1,480 @@
+// abi.cu — the C ABI of include/swegl_b200.h: context, HBM pools, scene upload and the per-frame
+// kernel sequence that replaces swegl::render / swegl::_render (renderer.hpp:27-34, renderer.cpp:77-235).
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace sb;
+
+struct swegl_b200_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    bool timing = false;
+    std::string err;
+
+    // scene (static)
+    bool have_scene = false, have_frame = false;
+    DeviceScene ds{};
+    uint32_t n_nodes = 0;
+    float *d_pos = nullptr, *d_nrm = nullptr, *d_uv = nullptr;
+    uint32_t *d_vert_node = nullptr, *d_texels = nullptr;
+    Tri *d_tris = nullptr; Prim *d_prims = nullptr;
+    float *d_node_world = nullptr, *d_node_normal = nullptr;
+    float *d_v_world = nullptr, *d_v_ndc = nullptr, *d_n_world = nullptr; uint8_t *d_yes = nullptr;
+    float4 *d_lights = nullptr; uint32_t lights_cap = 0;
+    bool opaque = true;            // every material and texel has alpha 255
+    FrameParams fp{};
+
+    // pools
+    Pools pools{};
+    uint32_t slots_cap = 0; size_t bins_cap = 0;
+    Counters *h_counters = nullptr;     // pinned
+
+    // screen
+    int sw = 0, sh = 0;
+    uint32_t *d_screen = nullptr; float *d_depth = nullptr; uint32_t *d_tmp_color = nullptr;
+    size_t depth_cap = 0;
+
+    ViewParams last_vp{}; bool have_vp = false;
+    cudaEvent_t ev[8]{};
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return SWEGL_B200_ERR_CUDA; } } while (0)
+
+static int fail(swegl_b200_ctx *ctx, int code, const char *msg) { if (ctx) ctx->err = msg; return code; }
+
+template <typename T> static cudaError_t dalloc(T *&p, size_t n)
+{
+    if (p) { cudaFree(p); p = nullptr; }
+    return cudaMalloc((void **)&p, (n ? n : 1) * sizeof(T));
+}
+
+extern "C" {
+
+int swegl_b200_abi_version(void) { return SWEGL_B200_ABI_VERSION; }
+
+int swegl_b200_create(int device, swegl_b200_ctx **out)
+{
+    if (!out) return SWEGL_B200_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return SWEGL_B200_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SWEGL_B200_ERR_CUDA;
+    if (prop.major != 10) return SWEGL_B200_ERR_CUDA;          // sm_100a code only, no fallback
+    if (cudaSetDevice(device) != cudaSuccess) return SWEGL_B200_ERR_CUDA;
+    swegl_b200_ctx *ctx = new (std::nothrow) swegl_b200_ctx;
+    if (!ctx) return SWEGL_B200_ERR_ARG;
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SWEGL_B200_ERR_CUDA; }
+    ctx->stream = ctx->own_stream;
+    for (auto &e : ctx->ev) cudaEventCreate(&e);
+    cudaMallocHost((void **)&ctx->h_counters, sizeof(Counters));
+    cudaMalloc((void **)&ctx->pools.counters, sizeof(Counters));
+    *out = ctx;
+    return SWEGL_B200_OK;
+}
+
+void swegl_b200_destroy(swegl_b200_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    void *ptrs[] = { ctx->d_pos, ctx->d_nrm, ctx->d_uv, ctx->d_vert_node, ctx->d_texels, ctx->d_tris, ctx->d_prims,
+                     ctx->d_node_world, ctx->d_node_normal, ctx->d_v_world, ctx->d_v_ndc, ctx->d_n_world, ctx->d_yes,
+                     ctx->d_lights, ctx->pools.edges, ctx->pools.shades, ctx->pools.live, ctx->pools.rows,
+                     ctx->pools.chunks, ctx->pools.bin_head, ctx->pools.counters, ctx->d_screen, ctx->d_depth,
+                     ctx->d_tmp_color };
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char *swegl_b200_last_error(const swegl_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int swegl_b200_set_stream(swegl_b200_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return SWEGL_B200_ERR_ARG;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_set_timing(swegl_b200_ctx *ctx, int enabled)
+{
+    if (!ctx) return SWEGL_B200_ERR_ARG;
+    ctx->timing = enabled != 0;
+    return SWEGL_B200_OK;
+}
+
+static int ensure_pools(swegl_b200_ctx *ctx, uint32_t rows_cap, uint32_t chunks_cap)
+{
+    if (rows_cap > ctx->pools.rows_cap) {
+        CK(dalloc(ctx->pools.rows, (size_t)rows_cap));
+        ctx->pools.rows_cap = rows_cap;
+    }
+    if (chunks_cap > ctx->pools.chunks_cap) {
+        CK(dalloc(ctx->pools.chunks, (size_t)chunks_cap));
+        ctx->pools.chunks_cap = chunks_cap;
+    }
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_upload_scene(swegl_b200_ctx *ctx, const swegl_b200_scene_desc *sc)
+{
+    if (!ctx || !sc) return SWEGL_B200_ERR_ARG;
+    if ((sc->n_vertices && (!sc->positions || !sc->normals || !sc->texcoords)) || (sc->n_primitives && !sc->primitives)
+        || (sc->n_indices && !sc->indices) || (sc->n_materials && !sc->materials) || (sc->n_textures && !sc->textures))
+        return fail(ctx, SWEGL_B200_ERR_ARG, "upload_scene: null array");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+
+    // texel pool: [textures..., one 1x1 colour per material, the default material's colour]
+    std::vector<uint32_t> tex_off(sc->n_textures);
+    size_t n_texels = 0;
+    bool opaque = true;
+    for (uint32_t t = 0; t < sc->n_textures; t++) {
+        const auto &tx = sc->textures[t];
+        if (!tx.texels || tx.width <= 0 || tx.height <= 0) return fail(ctx, SWEGL_B200_ERR_ARG, "upload_scene: bad texture");
+        tex_off[t] = (uint32_t)n_texels;
+        n_texels += (size_t)tx.width * tx.height;
+    }
+    std::vector<uint32_t> texels(n_texels + sc->n_materials + 1);
+    for (uint32_t t = 0; t < sc->n_textures; t++) {
+        const auto &tx = sc->textures[t];
+        size_t n = (size_t)tx.width * tx.height;
+        memcpy(&texels[tex_off[t]], tx.texels, n * 4);
+        for (size_t i = 0; i < n && opaque; i++) if ((tx.texels[i] >> 24) != 255) opaque = false;
+    }
+    auto mat_color = [](const swegl_b200_material &m) {
+        return (uint32_t)m.b | ((uint32_t)m.g << 8) | ((uint32_t)m.r << 16) | ((uint32_t)m.a << 24);
+    };
+    for (uint32_t m = 0; m < sc->n_materials; m++) {
+        texels[n_texels + m] = mat_color(sc->materials[m]);
+        if (sc->materials[m].a != 255) opaque = false;
+        if (sc->materials[m].texture_idx >= (int32_t)sc->n_textures) return fail(ctx, SWEGL_B200_ERR_ARG, "upload_scene: texture_idx out of range");
+    }
+    texels[n_texels + sc->n_materials] = mat_color(sc->default_material);
+
+    // primitives and the expanded triangle list (renderer.cpp:197-229 argument order)
+    std::vector<Prim> prims(sc->n_primitives);
+    std::vector<uint32_t> vert_node(sc->n_vertices, 0);
+    std::vector<Tri> tris;
+    for (uint32_t p = 0; p < sc->n_primitives; p++) {
+        const auto &sp = sc->primitives[p];
+        if (sp.node < 0 || (uint32_t)sp.node >= sc->n_nodes || sp.material_id < -1 || sp.material_id >= (int32_t)sc->n_materials
+            || (uint64_t)sp.first_vertex + sp.n_vertices > sc->n_vertices || (uint64_t)sp.first_index + sp.n_indices > sc->n_indices)
+            return fail(ctx, SWEGL_B200_ERR_ARG, "upload_scene: primitive out of range");
+        Prim &d = prims[p];
+        const swegl_b200_material &m = sp.material_id >= 0 ? sc->materials[sp.material_id] : sc->default_material;
+        if (sp.material_id == -1 && sc->default_material.a != 255) opaque = false;
+        d.color = mat_color(m);
+        d.node = sp.node;
+        d.double_sided = (sp.material_id != -1 && m.double_sided) ? 1 : 0;          // renderer.cpp:90
+        if (sp.material_id == -1 || m.texture_idx == -1) {                           // pixel_shaders.cpp:288-294
+            d.tex_off = (uint32_t)(n_texels + (sp.material_id >= 0 ? (uint32_t)sp.material_id : sc->n_materials));
+            d.tw = 1; d.th = 1;
+        } else {
+            d.tex_off = tex_off[m.texture_idx];
+            d.tw = sc->textures[m.texture_idx].width; d.th = sc->textures[m.texture_idx].height;
+        }
+        d.pad0 = d.pad1 = 0;
+        for (uint32_t k = 0; k < sp.n_vertices; k++) vert_node[sp.first_vertex + k] = (uint32_t)sp.node;
+        const uint32_t *I = sc->indices + sp.first_index;
+        auto idx = [&](uint32_t i) -> uint32_t { return sp.first_vertex + I[i]; };
+        for (uint32_t i = 0; i < sp.n_indices; i++)
+            if (I[i] >= sp.n_vertices) return fail(ctx, SWEGL_B200_ERR_ARG, "upload_scene: index out of range");
+        if (sp.mode == SWEGL_B200_MODE_TRIANGLE_STRIP)
+            for (uint32_t i = 2; i < sp.n_indices; i++) tris.push_back(Tri{ idx(i - 2), idx(i - 1 + (i & 1)), idx(i - (i & 1)), p });
+        else if (sp.mode == SWEGL_B200_MODE_TRIANGLE_FAN)
+            for (uint32_t i = 2; i < sp.n_indices; i++) tris.push_back(Tri{ idx(0), idx(i - 1), idx(i), p });
+        else if (sp.mode == SWEGL_B200_MODE_TRIANGLES)
+            for (uint32_t i = 2; i < sp.n_indices; i += 3) tris.push_back(Tri{ idx(i - 2), idx(i - 1), idx(i), p });
+        // other modes (points, lines) draw nothing in the reference either
+    }
+    if (tris.size() >= (1u << 29)) return fail(ctx, SWEGL_B200_ERR_UNSUPPORTED, "upload_scene: more than 2^29 triangles");
+
+    const uint32_t nv = sc->n_vertices, nt = (uint32_t)tris.size();
+    CK(dalloc(ctx->d_pos, (size_t)3 * nv)); CK(dalloc(ctx->d_nrm, (size_t)3 * nv)); CK(dalloc(ctx->d_uv, (size_t)2 * nv));
+    CK(dalloc(ctx->d_vert_node, (size_t)nv)); CK(dalloc(ctx->d_texels, texels.size()));
+    CK(dalloc(ctx->d_tris, (size_t)nt)); CK(dalloc(ctx->d_prims, (size_t)sc->n_primitives));
+    CK(dalloc(ctx->d_node_world, (size_t)16 * sc->n_nodes)); CK(dalloc(ctx->d_node_normal, (size_t)9 * sc->n_nodes));
+    CK(dalloc(ctx->d_v_world, (size_t)3 * nv)); CK(dalloc(ctx->d_v_ndc, (size_t)3 * nv)); CK(dalloc(ctx->d_n_world, (size_t)3 * nv));
+    CK(dalloc(ctx->d_yes, (size_t)nv));
+    CK(cudaMemcpy(ctx->d_pos, sc->positions, (size_t)12 * nv, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_nrm, sc->normals, (size_t)12 * nv, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_uv, sc->texcoords, (size_t)8 * nv, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_vert_node, vert_node.data(), (size_t)4 * nv, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_texels, texels.data(), texels.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_tris, tris.data(), (size_t)nt * sizeof(Tri), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_prims, prims.data(), prims.size() * sizeof(Prim), cudaMemcpyHostToDevice));
+    CK(cudaMemset(ctx->d_yes, 0, nv ? nv : 1));
+
+    // per-slot records: 2 slots per triangle, addressed by slot id (sparse; only live slots are touched)
+    ctx->slots_cap = 2 * nt;
+    CK(dalloc(ctx->pools.edges, (size_t)ctx->slots_cap)); CK(dalloc(ctx->pools.shades, (size_t)ctx->slots_cap));
+    CK(dalloc(ctx->pools.live, (size_t)ctx->slots_cap));
+    uint32_t rows0 = nt * 8u < (1u << 20) ? (1u << 20) : nt * 8u;
+    int rc = ensure_pools(ctx, rows0, rows0 * 2);
+    if (rc) return rc;
+
+    DeviceScene &ds = ctx->ds;
+    ds.n_vertices = nv; ds.n_tris = nt; ds.n_prims = sc->n_primitives; ds.n_nodes = sc->n_nodes;
+    ds.pos = ctx->d_pos; ds.nrm = ctx->d_nrm; ds.uv = ctx->d_uv; ds.vert_node = ctx->d_vert_node;
+    ds.tris = ctx->d_tris; ds.prims = ctx->d_prims; ds.texels = ctx->d_texels;
+    ds.node_world = ctx->d_node_world; ds.node_normal = ctx->d_node_normal;
+    ds.v_world = ctx->d_v_world; ds.v_ndc = ctx->d_v_ndc; ds.n_world = ctx->d_n_world; ds.yes = ctx->d_yes;
+    ctx->n_nodes = sc->n_nodes;
+    ctx->opaque = opaque;
+    ctx->have_scene = true; ctx->have_frame = false; ctx->have_vp = false;
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_set_screen(swegl_b200_ctx *ctx, int32_t w, int32_t h)
+{
+    if (!ctx || w <= 0 || h <= 0 || w > 65535 || h > 65535) return fail(ctx, SWEGL_B200_ERR_ARG, "set_screen: bad size");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    size_t n = (size_t)w * h;
+    CK(dalloc(ctx->d_screen, n)); CK(dalloc(ctx->d_depth, n)); CK(dalloc(ctx->d_tmp_color, n));
+    CK(cudaMemset(ctx->d_screen, 0, n * 4));
+    CK(cudaMemset(ctx->d_depth, 0x7F, n * 4));
+    size_t bins = (size_t)((w + 31) / 32 + 1) * h;
+    CK(dalloc(ctx->pools.bin_head, bins));
+    CK(cudaMemset(ctx->pools.bin_head, 0xFF, bins * 4));
+    ctx->bins_cap = bins; ctx->depth_cap = n;
+    ctx->sw = w; ctx->sh = h;
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_begin_frame(swegl_b200_ctx *ctx, const swegl_b200_frame_desc *fr)
+{
+    if (!ctx || !fr) return SWEGL_B200_ERR_ARG;
+    if (!ctx->have_scene) return fail(ctx, SWEGL_B200_ERR_STATE, "begin_frame before upload_scene");
+    if ((ctx->n_nodes && (!fr->node_world || !fr->node_normal)) || (fr->n_point_lights && !fr->point_lights))
+        return fail(ctx, SWEGL_B200_ERR_ARG, "begin_frame: null array");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->d_node_world, fr->node_world, (size_t)64 * ctx->n_nodes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_node_normal, fr->node_normal, (size_t)36 * ctx->n_nodes, cudaMemcpyHostToDevice, st));
+    if (fr->n_point_lights > ctx->lights_cap) {
+        CK(cudaStreamSynchronize(st));
+        CK(dalloc(ctx->d_lights, (size_t)fr->n_point_lights));
+        ctx->lights_cap = fr->n_point_lights;
+    }
+    if (fr->n_point_lights)
+        CK(cudaMemcpyAsync(ctx->d_lights, fr->point_lights, (size_t)16 * fr->n_point_lights, cudaMemcpyHostToDevice, st));
+    ctx->fp.ambient = fr->ambient;
+    ctx->fp.sun[0] = fr->sun_dir[0]; ctx->fp.sun[1] = fr->sun_dir[1]; ctx->fp.sun[2] = fr->sun_dir[2];
+    ctx->fp.sun_intensity = fr->sun_intensity;
+    ctx->fp.n_lights = fr->n_point_lights;
+    ctx->fp.lights = ctx->d_lights;
+    launch_vertex_world(ctx->ds, st);
+    CK(cudaGetLastError());
+    // host buffers of the caller may be reused as soon as we return
+    CK(cudaStreamSynchronize(st));
+    ctx->have_frame = true;
+    return SWEGL_B200_OK;
+}
+
+static int build_view(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v, ViewParams &vp)
+{
+    if (v->w <= 0 || v->h <= 0 || v->x < 0 || v->y < 0 || v->x + v->w > ctx->sw || v->y + v->h > ctx->sh)
+        return fail(ctx, SWEGL_B200_ERR_ARG, "viewport rectangle outside the screen (call set_screen first)");
+    if (v->light_mode < 0 || v->light_mode > 2 || v->tex_mode < 0 || v->tex_mode > 2 || v->post_mode < 0 || v->post_mode > 1)
+        return fail(ctx, SWEGL_B200_ERR_ARG, "bad shader / post mode");
+    if (v->transparency_layers > 0 && !ctx->opaque)
+        return fail(ctx, SWEGL_B200_ERR_UNSUPPORTED,
+                    "transparency layers with non-opaque materials/texels are not on the device yet (SURVEY §8f N1)");
+    memcpy(vp.view, v->view, sizeof vp.view);
+    memcpy(vp.proj, v->proj, sizeof vp.proj);
+    memcpy(vp.cam, v->cam_pos, sizeof vp.cam);
+    vp.vp_m00 = v->vp_m00; vp.vp_m03 = v->vp_m03; vp.vp_m11 = v->vp_m11; vp.vp_m13 = v->vp_m13;
+    vp.vx = v->x; vp.vy = v->y; vp.vw = v->w; vp.vh = v->h;
+    vp.band0 = v->y; vp.band1 = v->y + v->h;
+    if (v->band_y0 != 0 || v->band_y1 != 0) {
+        if (v->band_y0 < 0 || v->band_y1 > v->h || v->band_y0 >= v->band_y1) return fail(ctx, SWEGL_B200_ERR_ARG, "bad band");
+        vp.band0 = v->y + v->band_y0; vp.band1 = v->y + v->band_y1;
+    }
+    vp.nbx = (v->w + 31) / 32;
+    vp.screen_w = ctx->sw;
+    vp.light_mode = v->light_mode; vp.tex_mode = v->tex_mode;
+    return SWEGL_B200_OK;
+}
+
+// one pass of the kernel sequence; returns ERR_CAPACITY when a pool overflowed (caller grows and retries)
+static int run_frame(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v, const ViewParams &vp_draw,
+                     bool sync_counters, swegl_b200_stats *stats)
+{
+    cudaStream_t st = ctx->stream;
+    const bool dof = v->post_mode == SWEGL_B200_POST_DOF;
+    const bool timing = ctx->timing && stats;
+    ViewParams vp = vp_draw;
+    // DoF needs colour+depth of a 5-row halo around the band: render it redundantly
+    const int out0 = vp.band0, out1 = vp.band1;
+    if (dof) { vp.band0 = max(vp.vy, vp.band0 - 5); vp.band1 = min(vp.vy + vp.vh, vp.band1 + 5); }
+
+    uint32_t launches = 0;
+    if (timing) cudaEventRecord(ctx->ev[0], st);
+    CK(cudaMemsetAsync(ctx->pools.counters, 0, sizeof(Counters), st));
+    launch_vertex_view(ctx->ds, vp, st); launches++;
+    launch_mark(ctx->ds, st); launches++;
+    if (timing) cudaEventRecord(ctx->ev[1], st);
+    launch_setup(ctx->ds, vp, ctx->fp, ctx->pools, st); launches++;
+    if (timing) cudaEventRecord(ctx->ev[2], st);
+    launch_edgewalk(vp, ctx->pools, ctx->slots_cap, st); launches++;
+    launch_spans(vp, ctx->pools, st); launches++;
+    if (timing) cudaEventRecord(ctx->ev[3], st);
+    uint32_t *color = dof ? ctx->d_tmp_color - ((size_t)vp.vy * vp.vw + vp.vx) : ctx->d_screen;
+    int color_pitch = dof ? vp.vw : ctx->sw;
+    launch_fragments(ctx->ds, vp, ctx->fp, ctx->pools, color, color_pitch, ctx->d_depth, stats != nullptr, st); launches++;
+    if (timing) cudaEventRecord(ctx->ev[4], st);
+    if (dof) {
+        launch_dof(ctx->d_tmp_color, vp.vw, ctx->d_depth, ctx->d_screen + (size_t)vp.vy * ctx->sw + vp.vx, ctx->sw,
+                   vp.vw, vp.vh, out0 - vp.vy, out1 - vp.vy, v->focal_distance, v->focal_depth, st);
+        launches++;
+    }
+    if (timing) cudaEventRecord(ctx->ev[5], st);
+    CK(cudaGetLastError());
+
+    if (sync_counters) {
+        CK(cudaMemcpyAsync(ctx->h_counters, ctx->pools.counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const Counters &c = *ctx->h_counters;
+        if (c.overflow) return SWEGL_B200_ERR_CAPACITY;
+        if (stats) {
+            stats->n_setup_triangles = c.n_live; stats->n_spans = c.n_rows; stats->n_chunks = c.n_chunks;
+            stats->n_covered = c.n_covered; stats->n_launches = launches;
+            if (timing) {
+                cudaEventElapsedTime(&stats->ms_vertex, ctx->ev[0], ctx->ev[1]);
+                cudaEventElapsedTime(&stats->ms_setup, ctx->ev[1], ctx->ev[2]);
+                cudaEventElapsedTime(&stats->ms_raster, ctx->ev[2], ctx->ev[3]);
+                cudaEventElapsedTime(&stats->ms_fragment, ctx->ev[3], ctx->ev[4]);
+                cudaEventElapsedTime(&stats->ms_post, ctx->ev[4], ctx->ev[5]);
+                cudaEventElapsedTime(&stats->ms_total, ctx->ev[0], ctx->ev[5]);
+            }
+        }
+    } else if (stats) {
+        stats->n_launches = launches;
+    }
+    return SWEGL_B200_OK;
+}
+
+static int render_common(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v, bool sync, swegl_b200_stats *stats)
+{
+    if (!ctx || !v) return SWEGL_B200_ERR_ARG;
+    if (!ctx->have_scene || !ctx->have_frame || !ctx->d_screen)
+        return fail(ctx, SWEGL_B200_ERR_STATE, "render before upload_scene / set_screen / begin_frame");
+    CK(cudaSetDevice(ctx->device));
+    ViewParams vp;
+    int rc = build_view(ctx, v, vp);
+    if (rc) return rc;
+    if (stats) memset(stats, 0, sizeof *stats);
+    uint32_t grows = 0;
+    for (;;) {
+        rc = run_frame(ctx, v, vp, sync || stats, stats);
+        if (rc != SWEGL_B200_ERR_CAPACITY) break;
+        // grow the pools to what the frame asked for (+25 %) and redo it; bin lists were consumed/reset by
+        // k_fragments, except for chunks that never got linked -- reset them all to be safe
+        const Counters c = *ctx->h_counters;
+        if (++grows > 8) return fail(ctx, SWEGL_B200_ERR_CAPACITY, "span/chunk pools keep overflowing");
+        uint64_t want_rows = (uint64_t)c.n_rows + c.n_rows / 4 + 1024, want_chunks = (uint64_t)c.n_chunks + c.n_chunks / 4 + 1024;
+        if (c.overflow & 1u) want_chunks = want_chunks > 2 * want_rows ? want_chunks : 2 * want_rows;
+        if (want_rows > 0xFFFFFFF0ull || want_chunks > 0x7FFFFFF0ull) return fail(ctx, SWEGL_B200_ERR_CAPACITY, "frame needs more than 2^31 chunks");
+        CK(cudaMemsetAsync(ctx->pools.bin_head, 0xFF, ctx->bins_cap * 4, ctx->stream));
+        rc = ensure_pools(ctx, (uint32_t)want_rows, (uint32_t)want_chunks);
+        if (rc) return rc;
+    }
+    if (rc == SWEGL_B200_OK) { ctx->last_vp = vp; ctx->have_vp = true; if (stats) stats->pool_grows = grows; }
+    return rc;
+}
+
+int swegl_b200_render_viewport_device(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *vp, swegl_b200_stats *stats)
+{
+    return render_common(ctx, vp, false, stats);
+}
+
+int swegl_b200_render_viewport(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v, void *pixels, int32_t pitch_bytes,
+                               float *zbuffer, swegl_b200_stats *stats)
+{
+    if (!pixels || pitch_bytes < 4) return fail(ctx, SWEGL_B200_ERR_ARG, "render_viewport: null pixels");
+    int rc = render_common(ctx, v, true, stats);
+    if (rc) return rc;
+    const ViewParams &vp = ctx->last_vp;
+    cudaStream_t st = ctx->stream;
+    const int rows = vp.band1 - vp.band0;
+    CK(cudaMemcpy2DAsync((char *)pixels + (size_t)vp.band0 * pitch_bytes + (size_t)vp.vx * 4, (size_t)pitch_bytes,
+                         ctx->d_screen + (size_t)vp.band0 * ctx->sw + vp.vx, (size_t)ctx->sw * 4,
+                         (size_t)vp.vw * 4, (size_t)rows, cudaMemcpyDeviceToHost, st));
+    if (zbuffer)
+        CK(cudaMemcpyAsync(zbuffer + (size_t)(vp.band0 - vp.vy) * vp.vw, ctx->d_depth + (size_t)(vp.band0 - vp.vy) * vp.vw,
+                           (size_t)rows * vp.vw * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_device_buffers(swegl_b200_ctx *ctx, void **screen_dev, void **depth_dev)
+{
+    if (!ctx) return SWEGL_B200_ERR_ARG;
+    if (screen_dev) *screen_dev = ctx->d_screen;
+    if (depth_dev) *depth_dev = ctx->d_depth;
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_read_screen(swegl_b200_ctx *ctx, int32_t y0, int32_t y1, void *pixels, int32_t pitch_bytes)
+{
+    if (!ctx || !pixels || !ctx->d_screen || y0 < 0 || y1 > ctx->sh || y0 > y1 || pitch_bytes < ctx->sw * 4)
+        return fail(ctx, SWEGL_B200_ERR_ARG, "read_screen: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy2DAsync(pixels, (size_t)pitch_bytes, ctx->d_screen + (size_t)y0 * ctx->sw, (size_t)ctx->sw * 4,
+                         (size_t)ctx->sw * 4, (size_t)(y1 - y0), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_read_depth(swegl_b200_ctx *ctx, float *zbuffer)
+{
+    if (!ctx || !zbuffer || !ctx->have_vp) return fail(ctx, SWEGL_B200_ERR_ARG, "read_depth: nothing rendered");
+    CK(cudaSetDevice(ctx->device));
+    const ViewParams &vp = ctx->last_vp;
+    CK(cudaMemcpyAsync(zbuffer, ctx->d_depth, (size_t)vp.vw * vp.vh * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_read_vertices(swegl_b200_ctx *ctx, float *v_world, float *v_viewport, float *normal_world, uint8_t *yes)
+{
+    if (!ctx || !ctx->have_vp) return fail(ctx, SWEGL_B200_ERR_STATE, "read_vertices: nothing rendered");
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t nv = ctx->ds.n_vertices;
+    cudaStream_t st = ctx->stream;
+    std::vector<uint8_t> y(nv);
+    if (v_world) CK(cudaMemcpyAsync(v_world, ctx->d_v_world, (size_t)12 * nv, cudaMemcpyDeviceToHost, st));
+    if (v_viewport) CK(cudaMemcpyAsync(v_viewport, ctx->d_v_ndc, (size_t)12 * nv, cudaMemcpyDeviceToHost, st));
+    if (normal_world) CK(cudaMemcpyAsync(normal_world, ctx->d_n_world, (size_t)12 * nv, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(y.data(), ctx->d_yes, nv, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (v_viewport) {
+        // the device keeps NDC and applies frustum_to_viewport on the fly in k_setup; reproduce the
+        // reference's in-place state (vertex_shaders.hpp:72-84) for marked vertices.  Same two fp32 ops
+        // (this TU is built with -ffp-contract=off on the host side).
+        const ViewParams &vp = ctx->last_vp;
+        for (uint32_t i = 0; i < nv; i++)
+            if (y[i]) {
+                volatile float mx = vp.vp_m00 * v_viewport[3 * i];
+                volatile float my = vp.vp_m11 * v_viewport[3 * i + 1];
+                v_viewport[3 * i] = mx + vp.vp_m03;
+                v_viewport[3 * i + 1] = my + vp.vp_m13;
+            }
+    }
+    if (yes) memcpy(yes, y.data(), nv);
+    return SWEGL_B200_OK;
+}
+
+} // extern "C"
