@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py — fps / shaded Mpixels/s of the swegl hot path on B200, beside swegl's own CPU renderer.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+A step = one frame of the workload: swegl::render(scene, viewport) = vertex stage + cull/mark + setup +
+scan rasterisation with z test + Phong/bilinear shading + DoF-R.  Default workload = the north-star
+target of BASELINE.json (CesiumMilkTruck 3840x2160, Phong + bilinear, sun + 2 point lights, DoF-R);
+the 1080p configs[1] frame is measured in the same run and reported under "also".
+
+  value     : frames/s with the scene resident in HBM, CUDA events around each frame on the launching
+              stream, a 256 MiB L2 flush between frames (outside the events); max over ranks.
+  e2e       : the same frames through the public host API (Renderer.begin_frame + Renderer.render):
+              node matrices/lights H2D and the finished frame D2H into pinned memory every step.
+  roofline  : the dominant kernel's algorithmic bytes / its CUDA-event duration.
+  cpu_baseline : the unmodified reference (oracle/_ref) timed on this box's host cores (rank 0, N=1).
+N>1 (torchrun): frame-parallel, scene replicated, frame i on GPU i mod N, no collective ("weak").
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "fps"
+UNIT = "frames/s"
+DEFAULT_WORKLOAD = "truck_4k_dof"
+ALSO_WORKLOAD = "truck_1080"
+
+
+def workload_config(name, cfg, scene, screen, extra=None):
+    c = {"workload": name, "description": cfg["desc"], "resolution": f"{screen[0]}x{screen[1]}",
+         "triangles": scene.n_triangles(), "vertices": scene.n_vertices,
+         "shader": "phong+bilinear", "data": "bundled glTF scene pack" if not name.startswith("sphere") else "synthetic make_sphere + seeded LCG texture",
+         "l2": "256 MiB memset between timed frames, outside the CUDA events"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the CPU reference arm
+# ------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _ref_worker_init(name):
+    """one process = one copy of the single-threaded reference renderer (scene imported once)"""
+    from oracle.binding import Ref, Oracle, REF_LIB
+    from swegl_b200 import configs
+    scene, vps, screen, cfg = configs.build(name)
+    _W.update(scene=scene, vp=vps[0], screen=screen, orc=Oracle(), use_ref=os.path.exists(REF_LIB))
+    if _W["use_ref"]:
+        ref = Ref()
+        h = ref.import_scene(scene)
+        scr = ref.lib.ref_screen_new(*screen)
+        _W.update(ref=ref, h=h, scr=scr, rv=ref.make_viewport(scr, vps[0], vps[0].pose))
+
+
+def _ref_worker_frames(frames):
+    """render `frames` frames; returns (seconds per frame list, kind)"""
+    from swegl_b200 import _abi
+    vp, screen, orc = _W["vp"], _W["screen"], _W["orc"]
+    times = []
+    for _ in range(frames):
+        t0 = time.perf_counter()
+        if _W["use_ref"]:
+            px, z = _W["ref"].render(_W["h"], _W["rv"], _W["scr"], screen[0], screen[1], vp.w, vp.h)
+            if vp.post_mode == _abi.POST_DOF:       # the reference's DoF is broken at HEAD: DoF-R from the C oracle
+                orc.dof_r(px, z, vp.focal_distance, vp.focal_depth)
+        else:
+            orc.render(_W["scene"], vp, screen_wh=screen)
+        times.append(time.perf_counter() - t0)
+    return times, ("reference" if _W["use_ref"] else "port")
+
+
+def cpu_reference_single(name, frames, warmup):
+    """the reference as shipped: one process, one raster thread. -> (frames/s, kind, per-frame seconds)"""
+    _ref_worker_init(name)
+    _ref_worker_frames(warmup)
+    times, kind = _ref_worker_frames(frames)
+    return frames / sum(times), kind, times
+
+
+def run_reference_arm(args, rank, world):
+    """bench.py --impl reference: every host core renders its own frames with the (single-threaded)
+    reference; a step = one frame per process; value = aggregate frames/s (median over steps)."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from swegl_b200 import configs
+    name = args.workload
+    scene, vps, screen, cfg = configs.build(name)
+    procs = max(1, min(os.cpu_count() or 1, 64))
+    vals, kind = [], "reference"
+    t_start = time.perf_counter()
+    with mp.get_context("spawn").Pool(procs, initializer=_ref_worker_init, initargs=(name,)) as pool:
+        for _ in range(max(args.warmup, 0)):
+            pool.map(_ref_worker_frames, [1] * procs, chunksize=1)
+            if time.perf_counter() - t_start > 60:
+                break
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            res = pool.map(_ref_worker_frames, [1] * procs, chunksize=1)
+            wall = time.perf_counter() - t0
+            kind = res[0][1]
+            vals.append(procs / wall)
+            if time.perf_counter() - t_start > 200:
+                break
+    value = statistics.median(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+            "warmup": args.warmup, "ms_per_step": 1e3 * procs / value, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic" if name.startswith("sphere") else "bundled scene",
+            "config": workload_config(name, cfg, scene, screen),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind,
+                             "sample": f"{procs} independent single-threaded renderer processes, 1 frame each per step, "
+                                       f"{len(vals)} steps (swegl has one raster thread, so frame-parallel processes are all the "
+                                       f"host threads it can use); DoF-R by the C oracle because the reference's DoF is broken at HEAD"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# the GPU arm
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(scene, vp, covered):
+    """B_frag = 8*W*H + T_unique ; B_dof = 12*W*H"""
+    wh = vp.w * vp.h
+    tex_bytes = sum(int(t.size) * 4 for t in scene.textures)
+    t_unique = min(tex_bytes, 16 * covered)
+    return {"fragment": 8 * wh + t_unique, "dof": 12 * wh}
+
+
+def measure_gpu(r, torch, scene, vps, screen, steps, warmup, flush):
+    """-> (seconds for `steps` frames measured with per-frame CUDA events, stats of the last frame)"""
+    for _ in range(warmup):
+        r.begin_frame(scene)
+        for vp in vps:
+            r.render_device(vp, stats=False)
+    torch.cuda.synchronize()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    descs = [vp.desc() for vp in vps]
+    fd_nodes = scene.node_matrices()
+    for i in range(steps):
+        flush.zero_()
+        ev0[i].record()
+        r.begin_frame(scene, fd_nodes)
+        for d in descs:
+            r.render_device(d, stats=False)
+        ev1[i].record()
+    torch.cuda.synchronize()
+    ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+    return sum(ms) / 1e3, ms
+
+
+def measure_e2e(r, torch, scene, vps, screen, steps, warmup, pixels):
+    fd_nodes = scene.node_matrices()
+    descs = [vp.desc() for vp in vps]
+    for _ in range(max(1, warmup)):
+        r.begin_frame(scene, fd_nodes)
+        for d in descs:
+            r.render(d, pixels, stats=False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r.begin_frame(scene, fd_nodes)
+        for d in descs:
+            r.render(d, pixels, stats=False)
+    torch.cuda.synchronize()
+    return time.perf_counter() - t0
+
+
+def measure_kernels(r, scene, vps, steps):
+    """per-stage CUDA-event times (context timing mode), averaged over `steps` frames"""
+    r.set_timing(True)
+    acc = {"ms_vertex": 0.0, "ms_setup": 0.0, "ms_raster": 0.0, "ms_fragment": 0.0, "ms_post": 0.0, "ms_total": 0.0}
+    last = None
+    n = 0
+    for i in range(steps + 2):
+        r.begin_frame(scene)
+        for vp in vps:
+            st = r.render_device(vp, stats=True)
+            if i >= 2:
+                for k in acc:
+                    acc[k] += getattr(st, k)
+                n += 1
+            last = st
+    r.set_timing(False)
+    return {k: v / max(n, 1) for k, v in acc.items()}, last
+
+
+def gpu_workload(r, torch, name, steps, warmup, flush, world, dist, do_e2e=True):
+    from swegl_b200 import configs
+    scene, vps, screen, cfg = configs.build(name)
+    r.upload_scene(scene)
+    r.set_screen(*screen)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    secs, ms = measure_gpu(r, torch, scene, vps, screen, steps, warmup, flush)
+    if world > 1:
+        t = torch.tensor([secs], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t.item())
+        dist.barrier()
+    out = {"scene": scene, "vps": vps, "screen": screen, "cfg": cfg, "secs": secs, "ms": ms}
+    if do_e2e:
+        pixels = r.alloc_host((screen[1], screen[0]), np.uint32)
+        e2e_secs = measure_e2e(r, torch, scene, vps, screen, steps, warmup, pixels)
+        if world > 1:
+            t = torch.tensor([e2e_secs], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_secs = float(t.item())
+        out["e2e_secs"] = e2e_secs
+        nodes = scene.n_nodes
+        out["h2d"] = nodes * (64 + 36) + 16 * len(scene.point_lights)
+        out["d2h"] = sum(vp.w * vp.h * 4 for vp in vps) + 32
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — swegl_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from swegl_b200 import Renderer
+    r = Renderer(local_rank, stream=torch.cuda.current_stream().cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    main_res = gpu_workload(r, torch, args.workload, args.steps, args.warmup, flush, world, dist)
+    clocks = sampler.stop() if rank == 0 else None
+
+    scene, vps, screen, cfg = main_res["scene"], main_res["vps"], main_res["screen"], main_res["cfg"]
+    kern, last = measure_kernels(r, scene, vps, min(args.steps, 20))
+    covered = int(last.n_covered)
+    fps = world * args.steps / main_res["secs"]
+    e2e_fps = world * args.steps / main_res["e2e_secs"]
+
+    also = None
+    if not args.no_also and args.workload == DEFAULT_WORKLOAD and world == 1:
+        a = gpu_workload(r, torch, ALSO_WORKLOAD, args.steps, args.warmup, flush, world, dist)
+        ak, al = measure_kernels(r, a["scene"], a["vps"], min(args.steps, 20))
+        also = {"workload": ALSO_WORKLOAD, "description": a["cfg"]["desc"], "fps": args.steps / a["secs"],
+                "e2e_fps": args.steps / a["e2e_secs"], "shaded_mpix_per_s": al.n_covered * args.steps / a["secs"] / 1e6,
+                "ms_per_stage": ak}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak = 6650.0; peak_src = "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+    ab = algorithmic_bytes(scene, vps[0], covered)
+    per_kernel = {"k_fragments": (ab["fragment"], kern["ms_fragment"])}
+    if kern["ms_post"] > 0:
+        per_kernel["k_dof"] = (ab["dof"], kern["ms_post"])
+    dom = max(per_kernel, key=lambda k: per_kernel[k][1])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload, {}).get(dom)
+
+    def roof(k):
+        b, ms_ = per_kernel[k]
+        ach = b / (ms_ * 1e-3) / 1e9 if ms_ > 0 else 0.0
+        return {"kernel": k, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "algorithmic_bytes": b, "ms": ms_, "peak_source": peak_src}
+    roofline = roof(dom)
+    roofline["traffic"] = traffic
+    roofline["all_kernels"] = [roof(k) for k in per_kernel]
+
+    # ---- CPU baseline (bounded sample of the same workload) ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, kind, times = cpu_reference_single(args.workload, 3, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": f"3 frames of {args.workload} after 1 warm-up, swegl::render as shipped (1 raster thread) "
+                         f"via oracle/_ref + DoF-R by the C oracle; {1e3 / v:.1f} ms/frame"}
+
+    line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * main_res["secs"] / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic" if args.workload.startswith("sphere") else "bundled scene",
+            "config": workload_config(args.workload, cfg, scene, screen,
+                                      {"parallelism": "single GPU" if world == 1 else
+                                       f"frame-parallel x{world}: scene replicated, frame i on GPU i mod N, no collective"}),
+            "shaded_mpix_per_s": covered * fps / 1e6, "viewport_mpix_per_s": sum(v.w * v.h for v in vps) * fps / 1e6,
+            "covered_pixels": covered,
+            "frame_stats": {"setup_triangles": int(last.n_setup_triangles), "spans": int(last.n_spans), "chunks": int(last.n_chunks)},
+            "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": main_res["h2d"], "d2h_bytes_per_step": main_res["d2h"]},
+            "gpu_launches": (int(last.n_launches) * len(vps) + 1) * args.steps,
+            "ms_per_stage": kern, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
+    if also:
+        line["also"] = also
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -146,6 +146,12 @@ void swegl_b200_destroy(swegl_b200_ctx *ctx);
 const char *swegl_b200_last_error(const swegl_b200_ctx *ctx);
 /* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the ctx's own */
 int  swegl_b200_set_stream(swegl_b200_ctx *ctx, void *cuda_stream);
+/* block until everything queued on the context's stream has finished */
+int  swegl_b200_synchronize(swegl_b200_ctx *ctx);
+/* page-locked host memory for `pixels` / `zbuffer` (what SDL_Surface::pixels should live in for
+ * full-speed read-back); plain malloc'ed memory works too, just slower */
+int  swegl_b200_alloc_host(size_t bytes, void **out);
+int  swegl_b200_free_host(void *p);
 /* enable CUDA-event stage timing into swegl_b200_stats (adds synchronisation) */
 int  swegl_b200_set_timing(swegl_b200_ctx *ctx, int enabled);
 

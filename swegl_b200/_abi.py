@@ -71,6 +71,9 @@ SYMBOLS = [
     ("swegl_b200_destroy", None, [C.c_void_p]),
     ("swegl_b200_last_error", C.c_char_p, [C.c_void_p]),
     ("swegl_b200_set_stream", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("swegl_b200_synchronize", C.c_int, [C.c_void_p]),
+    ("swegl_b200_alloc_host", C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    ("swegl_b200_free_host", C.c_int, [C.c_void_p]),
     ("swegl_b200_set_timing", C.c_int, [C.c_void_p, C.c_int]),
     ("swegl_b200_upload_scene", C.c_int, [C.c_void_p, C.POINTER(SceneDesc)]),
     ("swegl_b200_set_screen", C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),

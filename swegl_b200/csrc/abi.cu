@@ -26,6 +26,8 @@ struct swegl_b200_ctx {
     float *d_node_world = nullptr, *d_node_normal = nullptr;
     float *d_v_world = nullptr, *d_v_ndc = nullptr, *d_n_world = nullptr; uint8_t *d_yes = nullptr;
     float4 *d_lights = nullptr; uint32_t lights_cap = 0;
+    float *h_stage = nullptr; size_t stage_cap = 0;   // pinned staging for the per-frame uploads
+    cudaEvent_t stage_free = nullptr;                 // the previous frame's H2D copies are done
     bool opaque = true;            // every material and texel has alpha 255
     FrameParams fp{};
 
@@ -74,6 +76,7 @@ int swegl_b200_create(int device, swegl_b200_ctx **out)
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SWEGL_B200_ERR_CUDA; }
     ctx->stream = ctx->own_stream;
     for (auto &e : ctx->ev) cudaEventCreate(&e);
+    cudaEventCreateWithFlags(&ctx->stage_free, cudaEventDisableTiming);
     cudaMallocHost((void **)&ctx->h_counters, sizeof(Counters));
     cudaMalloc((void **)&ctx->pools.counters, sizeof(Counters));
     *out = ctx;
@@ -87,11 +90,13 @@ void swegl_b200_destroy(swegl_b200_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     void *ptrs[] = { ctx->d_pos, ctx->d_nrm, ctx->d_uv, ctx->d_vert_node, ctx->d_texels, ctx->d_tris, ctx->d_prims,
                      ctx->d_node_world, ctx->d_node_normal, ctx->d_v_world, ctx->d_v_ndc, ctx->d_n_world, ctx->d_yes,
-                     ctx->d_lights, ctx->pools.edges, ctx->pools.shades, ctx->pools.live, ctx->pools.rows,
+                     ctx->d_lights, ctx->pools.edges, ctx->pools.shades, ctx->pools.spans, ctx->pools.row_slot,
                      ctx->pools.chunks, ctx->pools.bin_head, ctx->pools.counters, ctx->d_screen, ctx->d_depth,
                      ctx->d_tmp_color };
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->stage_free) cudaEventDestroy(ctx->stage_free);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -106,6 +111,24 @@ int swegl_b200_set_stream(swegl_b200_ctx *ctx, void *cuda_stream)
     return SWEGL_B200_OK;
 }
 
+int swegl_b200_alloc_host(size_t bytes, void **out)
+{
+    if (!out) return SWEGL_B200_ERR_ARG;
+    return cudaMallocHost(out, bytes ? bytes : 1) == cudaSuccess ? SWEGL_B200_OK : SWEGL_B200_ERR_CUDA;
+}
+
+int swegl_b200_free_host(void *p)
+{
+    return cudaFreeHost(p) == cudaSuccess ? SWEGL_B200_OK : SWEGL_B200_ERR_CUDA;
+}
+
+int swegl_b200_synchronize(swegl_b200_ctx *ctx)
+{
+    if (!ctx) return SWEGL_B200_ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SWEGL_B200_OK;
+}
+
 int swegl_b200_set_timing(swegl_b200_ctx *ctx, int enabled)
 {
     if (!ctx) return SWEGL_B200_ERR_ARG;
@@ -116,7 +139,8 @@ int swegl_b200_set_timing(swegl_b200_ctx *ctx, int enabled)
 static int ensure_pools(swegl_b200_ctx *ctx, uint32_t rows_cap, uint32_t chunks_cap)
 {
     if (rows_cap > ctx->pools.rows_cap) {
-        CK(dalloc(ctx->pools.rows, (size_t)rows_cap));
+        CK(dalloc(ctx->pools.spans, (size_t)rows_cap));
+        CK(dalloc(ctx->pools.row_slot, (size_t)rows_cap));
         ctx->pools.rows_cap = rows_cap;
     }
     if (chunks_cap > ctx->pools.chunks_cap) {
@@ -219,7 +243,6 @@ int swegl_b200_upload_scene(swegl_b200_ctx *ctx, const swegl_b200_scene_desc *sc
     // per-slot records: 2 slots per triangle, addressed by slot id (sparse; only live slots are touched)
     ctx->slots_cap = 2 * nt;
     CK(dalloc(ctx->pools.edges, (size_t)ctx->slots_cap)); CK(dalloc(ctx->pools.shades, (size_t)ctx->slots_cap));
-    CK(dalloc(ctx->pools.live, (size_t)ctx->slots_cap));
     uint32_t rows0 = nt * 8u < (1u << 20) ? (1u << 20) : nt * 8u;
     int rc = ensure_pools(ctx, rows0, rows0 * 2);
     if (rc) return rc;
@@ -261,15 +284,29 @@ int swegl_b200_begin_frame(swegl_b200_ctx *ctx, const swegl_b200_frame_desc *fr)
         return fail(ctx, SWEGL_B200_ERR_ARG, "begin_frame: null array");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    CK(cudaMemcpyAsync(ctx->d_node_world, fr->node_world, (size_t)64 * ctx->n_nodes, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_node_normal, fr->node_normal, (size_t)36 * ctx->n_nodes, cudaMemcpyHostToDevice, st));
+    // stage the caller's arrays in pinned memory so the call returns without a device sync and the
+    // caller may reuse its buffers immediately
+    const size_t nw = (size_t)16 * ctx->n_nodes, nn = (size_t)9 * ctx->n_nodes, nl = (size_t)4 * fr->n_point_lights;
+    if (nw + nn + nl > ctx->stage_cap) {
+        CK(cudaStreamSynchronize(st));
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->stage_cap = (nw + nn + nl) * 2 + 64;
+        CK(cudaMallocHost((void **)&ctx->h_stage, ctx->stage_cap * sizeof(float)));
+    } else {
+        CK(cudaEventSynchronize(ctx->stage_free));
+    }
     if (fr->n_point_lights > ctx->lights_cap) {
         CK(cudaStreamSynchronize(st));
         CK(dalloc(ctx->d_lights, (size_t)fr->n_point_lights));
         ctx->lights_cap = fr->n_point_lights;
     }
-    if (fr->n_point_lights)
-        CK(cudaMemcpyAsync(ctx->d_lights, fr->point_lights, (size_t)16 * fr->n_point_lights, cudaMemcpyHostToDevice, st));
+    memcpy(ctx->h_stage, fr->node_world, nw * 4);
+    memcpy(ctx->h_stage + nw, fr->node_normal, nn * 4);
+    if (nl) memcpy(ctx->h_stage + nw + nn, fr->point_lights, nl * 4);
+    CK(cudaMemcpyAsync(ctx->d_node_world, ctx->h_stage, nw * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_node_normal, ctx->h_stage + nw, nn * 4, cudaMemcpyHostToDevice, st));
+    if (nl) CK(cudaMemcpyAsync(ctx->d_lights, ctx->h_stage + nw + nn, nl * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->stage_free, st));
     ctx->fp.ambient = fr->ambient;
     ctx->fp.sun[0] = fr->sun_dir[0]; ctx->fp.sun[1] = fr->sun_dir[1]; ctx->fp.sun[2] = fr->sun_dir[2];
     ctx->fp.sun_intensity = fr->sun_intensity;
@@ -277,8 +314,6 @@ int swegl_b200_begin_frame(swegl_b200_ctx *ctx, const swegl_b200_frame_desc *fr)
     ctx->fp.lights = ctx->d_lights;
     launch_vertex_world(ctx->ds, st);
     CK(cudaGetLastError());
-    // host buffers of the caller may be reused as soon as we return
-    CK(cudaStreamSynchronize(st));
     ctx->have_frame = true;
     return SWEGL_B200_OK;
 }
@@ -328,7 +363,6 @@ static int run_frame(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v, con
     if (timing) cudaEventRecord(ctx->ev[1], st);
     launch_setup(ctx->ds, vp, ctx->fp, ctx->pools, st); launches++;
     if (timing) cudaEventRecord(ctx->ev[2], st);
-    launch_edgewalk(vp, ctx->pools, ctx->slots_cap, st); launches++;
     launch_spans(vp, ctx->pools, st); launches++;
     if (timing) cudaEventRecord(ctx->ev[3], st);
     uint32_t *color = dof ? ctx->d_tmp_color - ((size_t)vp.vy * vp.vw + vp.vx) : ctx->d_screen;
@@ -349,7 +383,7 @@ static int run_frame(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v, con
         const Counters &c = *ctx->h_counters;
         if (c.overflow) return SWEGL_B200_ERR_CAPACITY;
         if (stats) {
-            stats->n_setup_triangles = c.n_live; stats->n_spans = c.n_rows; stats->n_chunks = c.n_chunks;
+            stats->n_setup_triangles = c.n_slots; stats->n_spans = c.n_rows; stats->n_chunks = c.n_chunks;
             stats->n_covered = c.n_covered; stats->n_launches = launches;
             if (timing) {
                 cudaEventElapsedTime(&stats->ms_vertex, ctx->ev[0], ctx->ev[1]);

@@ -122,7 +122,13 @@ SB_DEV uint32_t shade(const SlotShade *sh, const Prim &pr, const uint32_t *texel
 }
 
 static constexpr int FRAG_TPB = 256;
+static constexpr int FRAG_ROWS = FRAG_TPB / 32;     // one warp per row of the CTA's 8-row group
+static constexpr int FRAG_STRETCH = 8;              // bins (of 32 pixels) one warp owns along its row
 
+// One warp owns a stretch of FRAG_STRETCH bins (256 pixels) of one scanline:
+//   1. one load fetches the bin heads (and resets them for the next frame),
+//   2. empty bins are cleared in bulk with 128-bit stores (colour 0, depth 0x7F7F7F7F: viewport.cpp:88-113),
+//   3. each non-empty bin is resolved with lane = pixel as described at the top of this file.
 template <int LIGHT, int TEX>
 __global__ void __launch_bounds__(FRAG_TPB) k_fragments(DeviceScene s, const __grid_constant__ ViewParams vp,
                                                         const __grid_constant__ FrameParams fp, Pools pl,
@@ -130,19 +136,46 @@ __global__ void __launch_bounds__(FRAG_TPB) k_fragments(DeviceScene s, const __g
                                                         float *__restrict__ depth, int count_covered)
 {
     const int lane = threadIdx.x & 31;
-    const uint32_t n_bins = (uint32_t)vp.nbx * (uint32_t)(vp.band1 - vp.band0);
-    const uint32_t warps = (gridDim.x * FRAG_TPB) >> 5;
-    const Span *spans = reinterpret_cast<const Span *>(pl.rows);
+    const int row = (vp.band0 - vp.vy) + blockIdx.y * FRAG_ROWS + (threadIdx.x >> 5);   // viewport-relative
+    if (row >= vp.band1 - vp.vy) return;
+    const int y = vp.vy + row;
+    const int bx0 = blockIdx.x * FRAG_STRETCH;
+    const int nb = min(FRAG_STRETCH, vp.nbx - bx0);
+    const Span *spans = pl.spans;
     const uint64_t KEY_INIT = (uint64_t)MAXZ_BITS << 32;
 
-    for (uint32_t bin = (blockIdx.x * FRAG_TPB + threadIdx.x) >> 5; bin < n_bins; bin += warps) {
-        const int row = (int)(bin / (uint32_t)vp.nbx) + (vp.band0 - vp.vy);      // viewport-relative row
-        const int bx = (int)(bin % (uint32_t)vp.nbx);
-        const int binx0 = vp.vx + (bx << 5);
-        const int x = binx0 + lane, y = vp.vy + row;
-        int32_t *headp = pl.bin_head + (size_t)row * vp.nbx + bx;
-        int32_t c = *headp;
-        if (c >= 0 && lane == 0) *headp = -1;                               // ready for the next frame
+    int32_t *headp = pl.bin_head + (size_t)row * vp.nbx + bx0 + lane;
+    int32_t head = -1;
+    if (lane < nb) { head = *headp; if (head >= 0) *headp = -1; }
+    unsigned mask = __ballot_sync(0xFFFFFFFFu, head >= 0);
+
+    uint32_t *crow = color + (size_t)y * color_pitch + vp.vx + (bx0 << 5);
+    float *drow = depth + (size_t)row * vp.vw + (bx0 << 5);
+    const int px_left = vp.vw - (bx0 << 5);                                 // pixels from the stretch start to the row end
+    const bool aligned = ((reinterpret_cast<uintptr_t>(crow) | reinterpret_cast<uintptr_t>(drow)) & 15) == 0;
+    // ---- empty bins ----
+    if (mask != 0xFFFFFFFFu) {
+        const float maxz = __uint_as_float(MAXZ_BITS);
+        for (int i = lane; i < nb * 8; i += 32) {
+            const int b = i >> 3, px = (b << 5) + ((i & 7) << 2);
+            if ((mask >> b) & 1u) continue;
+            if (aligned && px + 4 <= px_left) {
+                *reinterpret_cast<uint4 *>(crow + px) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<float4 *>(drow + px) = make_float4(maxz, maxz, maxz, maxz);
+            } else {
+                for (int k = 0; k < 4; k++)
+                    if (px + k < px_left) { crow[px + k] = 0; drow[px + k] = maxz; }
+            }
+        }
+    }
+    // ---- non-empty bins ----
+    uint32_t covered = 0;
+    while (mask) {
+        const int b = __ffs(mask) - 1;
+        mask &= mask - 1;
+        int32_t c = __shfl_sync(0xFFFFFFFFu, head, b);
+        const int binx0 = vp.vx + ((bx0 + b) << 5);
+        const int x = binx0 + lane;
 
         uint64_t best = KEY_INIT;
         float best_u = 0.f;
@@ -154,7 +187,15 @@ __global__ void __launch_bounds__(FRAG_TPB) k_fragments(DeviceScene s, const __g
             const int xs = max(x1, binx0), xe = min(x2, binx0 + 32);
             const int k = x - xs, n = xe - xs;
             float top = ch.top, bot = ch.bottom;
-            for (int j = 0; j < n - 1; j++)                                 // qpixel.Step() x (x - xs)
+            // qpixel.Step() x (x - xs): the same fp32 additions the CPU performs, in the same order
+            int j = 0;
+            for (; j + 4 <= n - 1; j += 4) {
+                if (j + 0 < k) { top = fadd(top, sp.topstep); bot = fadd(bot, sp.bottomstep); }
+                if (j + 1 < k) { top = fadd(top, sp.topstep); bot = fadd(bot, sp.bottomstep); }
+                if (j + 2 < k) { top = fadd(top, sp.topstep); bot = fadd(bot, sp.bottomstep); }
+                if (j + 3 < k) { top = fadd(top, sp.topstep); bot = fadd(bot, sp.bottomstep); }
+            }
+            for (; j < n - 1; j++)
                 if (j < k) { top = fadd(top, sp.topstep); bot = fadd(bot, sp.bottomstep); }
             const float u = fdiv(top, bot);                                 // interpolator.hpp:98
             const float z = fadd(sp.v0, fmul(sp.v1, u));                    // value(0)
@@ -177,23 +218,33 @@ __global__ void __launch_bounds__(FRAG_TPB) k_fragments(DeviceScene s, const __g
             out = shade<LIGHT, TEX>(sh, pr, s.texels, vp, fp, lower, lor, sp.pl, sp.pr, best_u);
         }
         if (inside) {
-            color[(size_t)y * color_pitch + x] = out;
-            depth[(size_t)row * vp.vw + (x - vp.vx)] = __uint_as_float((uint32_t)(best >> 32));
+            crow[(b << 5) + lane] = out;
+            drow[(b << 5) + lane] = __uint_as_float((uint32_t)(best >> 32));
         }
-        if (count_covered) {
-            unsigned m = __ballot_sync(0xFFFFFFFFu, hit && inside);
-            if (lane == 0 && m) atomicAdd(&pl.counters->n_covered, (uint32_t)__popc(m));
-        }
+        if (count_covered) covered += __popc(__ballot_sync(0xFFFFFFFFu, hit && inside));
     }
+    if (count_covered && lane == 0 && covered) atomicAdd(&pl.counters->n_covered, covered);
 }
 
 // ----------------------------------------------------------------------------------------
 // DoF-R: the repaired post_shader_depth_box (post_shaders.hpp:63-111).
-// 32x8 output tile per CTA, (32+10)x(8+10) source tile staged in shared memory as
-// colour | (blur != 0) << 24 so a tap costs one LDS.
+//
+// out(x,y) = src(x,y)                                   if r == 0 or no tap counts
+//          = (sum b / n, sum g / n, sum r / n, 255)      over taps (i,j) in [x-r,x+r) x [y-r,y+r), clipped
+//                                                        to the viewport, whose blur factor is != 0
+// with r = (int)blur(depth(x,y)) in 0..5.  All integer arithmetic -> pixel-identical.
+//
+// One CTA produces a 64x32 tile.  It stages the (64+9)x(32+9) source window in shared memory as
+// packed per-pixel contributions (b | g<<21 | r<<42 in a u64, the tap count in a u32), turns
+// them into a summed-area table with two short serial scans (rows, then columns), and every
+// output pixel is then 4 corner lookups instead of up to 100 taps.  HBM traffic is the
+// algorithmic 12 B/pixel; the 46 % halo over-fetch is served by L2.
 // ----------------------------------------------------------------------------------------
-static constexpr int DOF_TX = 32, DOF_TY = 8, DOF_R = 5;
-static constexpr int DOF_SW = DOF_TX + 2 * DOF_R, DOF_SH = DOF_TY + 2 * DOF_R;
+static constexpr int DOF_OW = 64, DOF_OH = 32, DOF_LO = 5, DOF_HI = 4;
+static constexpr int DOF_SW = DOF_OW + DOF_LO + DOF_HI;      // 73 source columns
+static constexpr int DOF_SH = DOF_OH + DOF_LO + DOF_HI;      // 41 source rows
+static constexpr int DOF_PW = 75;                            // SAT row stride in entries (col 0 = zero border; odd -> no bank conflicts)
+static constexpr int DOF_THREADS = 256;
 
 SB_DEV float blur_factor(float depth, float focal_distance, float focal_depth)
 {
@@ -206,43 +257,131 @@ SB_DEV float blur_factor(float depth, float focal_distance, float focal_depth)
     return r;
 }
 
-__global__ void __launch_bounds__(DOF_TX * DOF_TY) k_dof(const uint32_t *__restrict__ src, int src_pitch,
-                                                         const float *__restrict__ depth, uint32_t *__restrict__ dst,
-                                                         int dst_pitch, int w, int h, int row0, int row1,
-                                                         float focal_distance, float focal_depth)
+__global__ void __launch_bounds__(DOF_THREADS) k_dof(const uint32_t *__restrict__ src, int src_pitch,
+                                                     const float *__restrict__ depth, uint32_t *__restrict__ dst,
+                                                     int dst_pitch, int w, int h, int row0, int row1,
+                                                     float focal_distance, float focal_depth)
 {
-    __shared__ uint32_t tile[DOF_SH][DOF_SW];
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int ox = blockIdx.x * DOF_TX, oy = row0 + blockIdx.y * DOF_TY;
-    for (int i = ty * DOF_TX + tx; i < DOF_SW * DOF_SH; i += DOF_TX * DOF_TY) {
-        int sy = i / DOF_SW, sx = i % DOF_SW;
-        int gx = ox + sx - DOF_R, gy = oy + sy - DOF_R;
-        uint32_t v = 0;
-        if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
-            uint32_t c = src[(size_t)gy * src_pitch + gx];
-            float bf = blur_factor(depth[(size_t)gy * w + gx], focal_distance, focal_depth);
-            v = (c & 0x00FFFFFFu) | (bf != 0.0f ? 0x01000000u : 0u);
+    __shared__ unsigned long long s64[(DOF_SH + 1) * DOF_PW];
+    __shared__ uint32_t s32[(DOF_SH + 1) * DOF_PW];
+    __shared__ uint32_t magic[128];                          // ceil(2^28 / n): exact b / n for b < 2^15, n <= 100
+    const int tid = threadIdx.x;
+    const int ox = blockIdx.x * DOF_OW, oy = row0 + blockIdx.y * DOF_OH;
+
+    if (tid < 128) magic[tid] = tid ? (uint32_t)(((1u << 28) + tid - 1) / tid) : 0u;
+    for (int i = tid; i < DOF_PW; i += DOF_THREADS) { s64[i] = 0; s32[i] = 0; }                 // zero row 0
+    for (int i = tid; i <= DOF_SH; i += DOF_THREADS) { s64[i * DOF_PW] = 0; s32[i * DOF_PW] = 0; } // zero column 0
+    // stage the source window: loads are issued in batches of DOF_BATCH per thread (all independent) so the
+    // L2/HBM latency is paid once per batch instead of once per element
+    constexpr int DOF_ITEMS = (DOF_SW * DOF_SH + DOF_THREADS - 1) / DOF_THREADS;      // 12
+    constexpr int DOF_BATCH = 6;
+    static_assert(DOF_ITEMS % DOF_BATCH == 0, "batching assumes an exact split");
+    #pragma unroll
+    for (int it0 = 0; it0 < DOF_ITEMS; it0 += DOF_BATCH) {
+        float dz[DOF_BATCH]; uint32_t cc[DOF_BATCH];
+        uint32_t inmask = 0;
+        #pragma unroll
+        for (int u = 0; u < DOF_BATCH; u++) {
+            const int i = tid + (it0 + u) * DOF_THREADS;
+            const int sy = i / DOF_SW, sx = i - sy * DOF_SW;
+            const int gx = ox + sx - DOF_LO, gy = oy + sy - DOF_LO;
+            const bool in = i < DOF_SW * DOF_SH && gx >= 0 && gx < w && gy >= 0 && gy < h;
+            dz[u] = in ? __ldg(&depth[(size_t)gy * w + gx]) : 0.0f;
+            cc[u] = in ? __ldg(&src[(size_t)gy * src_pitch + gx]) : 0u;
+            inmask |= (in ? 1u : 0u) << u;
         }
-        tile[sy][sx] = v;
+        #pragma unroll
+        for (int u = 0; u < DOF_BATCH; u++) {
+            const int i = tid + (it0 + u) * DOF_THREADS;
+            if (i >= DOF_SW * DOF_SH) continue;
+            const int sy = i / DOF_SW, sx = i - sy * DOF_SW;
+            unsigned long long v = 0; uint32_t n = 0;
+            if (((inmask >> u) & 1u) && blur_factor(dz[u], focal_distance, focal_depth) != 0.0f) {
+                const uint32_t c = cc[u];
+                v = (unsigned long long)(c & 0xFF) | ((unsigned long long)((c >> 8) & 0xFF) << 21)
+                  | ((unsigned long long)((c >> 16) & 0xFF) << 42);
+                n = 1;
+            }
+            s64[(sy + 1) * DOF_PW + sx + 1] = v;
+            s32[(sy + 1) * DOF_PW + sx + 1] = n;
+        }
     }
     __syncthreads();
-    const int x = ox + tx, y = oy + ty;
-    if (x >= w || y >= row1 || y >= h) return;
-    const uint32_t own = src[(size_t)y * src_pitch + x];
-    const int radius = f2i(blur_factor(depth[(size_t)y * w + x], focal_distance, focal_depth));
-    uint32_t out = own;
-    if (radius != 0) {
-        int b = 0, g = 0, r = 0, count = 0;
-        const int j0 = max(0, y - radius), j1 = min(h, y + radius);
-        const int i0 = max(0, x - radius), i1 = min(w, x + radius);
-        for (int j = j0; j < j1; j++)
-            for (int i = i0; i < i1; i++) {
-                uint32_t p = tile[j - oy + DOF_R][i - ox + DOF_R];
-                if (p >> 24) { count++; b += p & 0xFF; g += (p >> 8) & 0xFF; r += (p >> 16) & 0xFF; }
-            }
-        if (count) out = (uint32_t)(b / count) | ((uint32_t)(g / count) << 8) | ((uint32_t)(r / count) << 16) | 0xFF000000u;
+    if (tid < DOF_SH) {                                      // inclusive scan along each row
+        unsigned long long a = 0; uint32_t n = 0;
+        const int base = (tid + 1) * DOF_PW;
+        #pragma unroll 8
+        for (int sx = 1; sx <= DOF_SW; sx++) {
+            a += s64[base + sx]; n += s32[base + sx];
+            s64[base + sx] = a; s32[base + sx] = n;
+        }
     }
-    dst[(size_t)y * dst_pitch + x] = out;
+    __syncthreads();
+    if (tid < DOF_SW) {                                      // then down each column
+        unsigned long long a = 0; uint32_t n = 0;
+        const int col = tid + 1;
+        #pragma unroll 8
+        for (int sy = 1; sy <= DOF_SH; sy++) {
+            a += s64[sy * DOF_PW + col]; n += s32[sy * DOF_PW + col];
+            s64[sy * DOF_PW + col] = a; s32[sy * DOF_PW + col] = n;
+        }
+    }
+    __syncthreads();
+
+    // each thread: 2 groups of 4 consecutive pixels (one 128-bit load of colour and depth, one 128-bit store)
+    #pragma unroll
+    for (int g = 0; g < (DOF_OW * DOF_OH) / (4 * DOF_THREADS); g++) {
+        const int q = tid + g * DOF_THREADS;                 // quad index in the tile
+        const int ty = q / (DOF_OW / 4), tx = (q % (DOF_OW / 4)) * 4;
+        const int x0 = ox + tx, y = oy + ty;
+        if (y >= row1 || y >= h || x0 >= w) continue;
+        uint32_t own[4]; float dz[4];
+        const bool vec = (x0 + 3 < w) && ((src_pitch & 3) == 0) && ((w & 3) == 0) && ((dst_pitch & 3) == 0)
+                      && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(depth) & 15) == 0)
+                      && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+        if (vec) {
+            const uint4 c4 = *reinterpret_cast<const uint4 *>(src + (size_t)y * src_pitch + x0);
+            const float4 d4 = *reinterpret_cast<const float4 *>(depth + (size_t)y * w + x0);
+            own[0] = c4.x; own[1] = c4.y; own[2] = c4.z; own[3] = c4.w;
+            dz[0] = d4.x; dz[1] = d4.y; dz[2] = d4.z; dz[3] = d4.w;
+        } else {
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const bool in = x0 + k < w;
+                own[k] = in ? src[(size_t)y * src_pitch + x0 + k] : 0u;
+                dz[k] = in ? depth[(size_t)y * w + x0 + k] : 0.f;
+            }
+        }
+        uint32_t out[4];
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int radius = f2i(blur_factor(dz[k], focal_distance, focal_depth));
+            out[k] = own[k];
+            if (radius != 0) {
+                // SAT index of source pixel (gx, gy) is (gx - ox + 6, gy - oy + 6); the zero border and the
+                // zeros stored for out-of-viewport pixels implement the max(0,..)/min(w|h,..) clipping
+                const int J0 = ty + DOF_LO - radius, J1 = ty + DOF_LO + radius;
+                const int I0 = tx + k + DOF_LO - radius, I1 = tx + k + DOF_LO + radius;
+                const unsigned long long sum = (s64[J1 * DOF_PW + I1] + s64[J0 * DOF_PW + I0])
+                                             - (s64[J0 * DOF_PW + I1] + s64[J1 * DOF_PW + I0]);
+                const uint32_t count = (s32[J1 * DOF_PW + I1] + s32[J0 * DOF_PW + I0])
+                                     - (s32[J0 * DOF_PW + I1] + s32[J1 * DOF_PW + I0]);
+                if (count) {
+                    const unsigned long long m = magic[count];
+                    const uint32_t b = (uint32_t)(((sum & 0x1FFFFFull) * m) >> 28);
+                    const uint32_t gg = (uint32_t)((((sum >> 21) & 0x1FFFFFull) * m) >> 28);
+                    const uint32_t r = (uint32_t)((((sum >> 42) & 0x1FFFFFull) * m) >> 28);
+                    out[k] = b | (gg << 8) | (r << 16) | 0xFF000000u;
+                }
+            }
+        }
+        if (vec) {
+            *reinterpret_cast<uint4 *>(dst + (size_t)y * dst_pitch + x0) = make_uint4(out[0], out[1], out[2], out[3]);
+        } else {
+            #pragma unroll
+            for (int k = 0; k < 4; k++) if (x0 + k < w) dst[(size_t)y * dst_pitch + x0 + k] = out[k];
+        }
+    }
 }
 
 // ----------------------------------------------------------------------------------------
@@ -252,10 +391,9 @@ template <int LIGHT, int TEX>
 static void launch_frag_t(const DeviceScene &s, const ViewParams &vp, const FrameParams &fp, const Pools &p,
                           uint32_t *color, int color_pitch, float *depth, bool count_covered, cudaStream_t st)
 {
-    uint32_t n_bins = (uint32_t)vp.nbx * (uint32_t)(vp.band1 - vp.band0);
-    uint32_t blocks = (n_bins + (FRAG_TPB / 32) - 1) / (FRAG_TPB / 32);
-    if (!blocks) return;
-    k_fragments<LIGHT, TEX><<<blocks, FRAG_TPB, 0, st>>>(s, vp, fp, p, color, color_pitch, depth, count_covered ? 1 : 0);
+    dim3 grid((vp.nbx + FRAG_STRETCH - 1) / FRAG_STRETCH, (vp.band1 - vp.band0 + FRAG_ROWS - 1) / FRAG_ROWS);
+    if (!grid.x || !grid.y) return;
+    k_fragments<LIGHT, TEX><<<grid, FRAG_TPB, 0, st>>>(s, vp, fp, p, color, color_pitch, depth, count_covered ? 1 : 0);
 }
 
 void launch_fragments(const DeviceScene &s, const ViewParams &vp, const FrameParams &fp, const Pools &p,
@@ -271,10 +409,9 @@ void launch_fragments(const DeviceScene &s, const ViewParams &vp, const FramePar
 void launch_dof(const uint32_t *src, int src_pitch, const float *depth, uint32_t *dst, int dst_pitch,
                 int w, int h, int row0, int row1, float focal_distance, float focal_depth, cudaStream_t st)
 {
-    dim3 block(DOF_TX, DOF_TY);
-    dim3 grid((w + DOF_TX - 1) / DOF_TX, (row1 - row0 + DOF_TY - 1) / DOF_TY);
+    dim3 grid((w + DOF_OW - 1) / DOF_OW, (row1 - row0 + DOF_OH - 1) / DOF_OH);
     if (grid.x && grid.y)
-        k_dof<<<grid, block, 0, st>>>(src, src_pitch, depth, dst, dst_pitch, w, h, row0, row1, focal_distance, focal_depth);
+        k_dof<<<grid, DOF_THREADS, 0, st>>>(src, src_pitch, depth, dst, dst_pitch, w, h, row0, row1, focal_distance, focal_depth);
 }
 
 } // namespace sb

@@ -4,12 +4,11 @@
 //   k_vertex_world  vertex_shader_t::original_to_world            vertex_shaders.hpp:16-33
 //   k_vertex_view   world_to_camera_or_frustum / camera_to_frustum vertex_shaders.hpp:35-52,61-71
 //   k_mark          the mark pass of _render                      renderer.cpp:86-185
-//   k_setup         fill_triangle + the head of fill_triangle_2   renderer.cpp:240-394
-//   k_edgewalk      fill_triangle_2 + the y loop of fill_half_triangle   renderer.cpp:396-460,467,553-556
-//   k_spans         the per-scanline part of fill_half_triangle   renderer.cpp:469-480
-// The fp32 recurrences (edge x += ratio, topalpha += topstep ...) are replayed step by step so
-// coverage and depth are bit-identical to the CPU renderer; everything that is not a recurrence
-// runs one thread per vertex / triangle / scanline.
+//   k_setup         fill_triangle + fill_triangle_2 (edge set-up)  renderer.cpp:240-460
+//   k_spans         the y loop and per-scanline part of fill_half_triangle   renderer.cpp:467-480,553-556
+// The fp32 recurrences (edge x += ratio, topalpha += topstep ...) must see the same additions as the
+// CPU renderer for coverage and depth to be bit-identical; radd() (radd.h) performs k of them in
+// O(1), so there is no serial edge walk: one thread per vertex / triangle / scanline everywhere.
 #include "common.cuh"
 
 namespace sb {
@@ -138,12 +137,49 @@ SB_DEV void emit_slot(const DeviceScene &s, const ViewParams &vp, const FramePar
     uint32_t base = atomicAdd(&pl.counters->n_rows, (uint32_t)n);
     if (base + (uint32_t)n > pl.rows_cap) { atomicOr(&pl.counters->overflow, 1u); return; }
 
+    // fill_triangle_2's edge set-up (renderer.cpp:396-459): every side's state at the first scanline it is
+    // walked on.  k_spans jumps from here to any scanline with radd().
     SlotEdge e;
-    e.x0 = a.s.x; e.y0 = a.s.y; e.z0 = a.s.z;
-    e.x1 = b.s.x; e.y1 = b.s.y; e.z1 = b.s.z;
-    e.x2 = c.s.x; e.y2 = c.s.y; e.z2 = c.s.z;
-    e.span_base = (int32_t)base; e.pad0 = 0; e.pad1 = 0;
+    const float x0 = a.s.x, yy0 = a.s.y, z0 = a.s.z, x1 = b.s.x, yy1 = b.s.y, z1 = b.s.z, x2 = c.s.x, yy2 = c.s.y, z2 = c.s.z;
+    {
+        Interp ip;
+        e.lng.ratio = fdiv(fsub(x2, x0), fsub(yy2, yy0));                   // :400-409
+        interp_init_self(ip, fsub(yy2, yy0), z0, z2);
+        const float move = (y0 < vp.vy) ? fsub((float)vp.vy, yy0) : fsub((float)y0, yy0);
+        interp_displace(ip, move);
+        e.lng.x = fadd(x0, fmul(e.lng.ratio, move));
+        e.lng.top = ip.top; e.lng.topstep = ip.topstep; e.lng.bottom = ip.bottom; e.lng.bottomstep = ip.bottomstep;
+    }
+    e.y_long = max(y0, vp.vy);
+    e.flags = 0;
+    e.ya_u = e.yb_u = e.ya_l = e.yb_l = 0;
+    e.su = e.lng; e.sl = e.lng;
+    if (y1 >= vp.vy) {                                                      // upper half, :416-436
+        Interp ip;
+        e.su.ratio = fdiv(fsub(x1, x0), fsub(yy1, yy0));
+        interp_init_self(ip, fsub(yy1, yy0), z0, z1);
+        e.ya_u = max(y0, vp.vy); e.yb_u = min(y1, vp.vy + vp.vh);
+        const float move = fsub((float)e.ya_u, yy0);
+        interp_displace(ip, move);
+        e.su.x = fadd(x0, fmul(e.su.ratio, move));
+        e.su.top = ip.top; e.su.topstep = ip.topstep; e.su.bottom = ip.bottom; e.su.bottomstep = ip.bottomstep;
+        if (e.lng.ratio > e.su.ratio) e.flags |= 1u;
+    }
+    if (y1 < vp.vy + vp.vh) {                                               // lower half, :439-459
+        Interp ip;
+        e.sl.ratio = fdiv(fsub(x2, x1), fsub(yy2, yy1));
+        interp_init_self(ip, fsub(yy2, yy1), z1, z2);
+        e.ya_l = max(y1, vp.vy); e.yb_l = min(y2, vp.vy + vp.vh);
+        const float move = fsub((float)e.ya_l, yy1);
+        interp_displace(ip, move);
+        e.sl.x = fadd(x1, fmul(e.sl.ratio, move));
+        e.sl.top = ip.top; e.sl.topstep = ip.topstep; e.sl.bottom = ip.bottom; e.sl.bottomstep = ip.bottomstep;
+        if (e.lng.ratio < e.sl.ratio) e.flags |= 2u;
+    }
+    e.z0 = z0; e.z1 = z1; e.z2 = z2;
+    e.span_base = (int32_t)base; e.pad = 0;
     pl.edges[slot] = e;
+    for (int k = 0; k < n; k++) pl.row_slot[base + k] = slot;               // scanline record -> owning slot
 
     SlotShade sh;
     sh.w0[0] = a.w.x; sh.w0[1] = a.w.y; sh.w0[2] = a.w.z;
@@ -175,7 +211,7 @@ SB_DEV void emit_slot(const DeviceScene &s, const ViewParams &vp, const FramePar
     for (int k = 0; k < 6; k++) sh.pad[k] = 0;
     pl.shades[slot] = sh;
 
-    pl.live[atomicAdd(&pl.counters->n_live, 1u)] = slot;
+    atomicAdd(&pl.counters->n_slots, 1u);
 }
 
 __global__ void __launch_bounds__(128) k_setup(DeviceScene s, const __grid_constant__ ViewParams vp,
@@ -222,107 +258,57 @@ __global__ void __launch_bounds__(128) k_setup(DeviceScene s, const __grid_const
 }
 
 // ----------------------------------------------------------------------------------------
-// edge walk: one thread per live slot replays the per-scanline recurrences of both edges
-// ----------------------------------------------------------------------------------------
-struct Side { Interp ip; float ratio, x; };
-
-SB_DEV void walk_half(const ViewParams &vp, Row *rows, uint32_t &k, uint32_t slot, int lower,
-                      int y, int y_end, bool lor, Side &lng, Side &sht)
-{
-    uint32_t flags = (slot << 2) | ((uint32_t)lower << 1) | (lor ? 1u : 0u);
-    for (; y < y_end; y++) {
-        if (y >= vp.band0 && y < vp.band1) {
-            Row r;
-            const Side &L = lor ? sht : lng;
-            const Side &R = lor ? lng : sht;
-            r.lx = L.x; r.rx = R.x;
-            r.ltop = L.ip.top; r.lbot = L.ip.bottom; r.rtop = R.ip.top; r.rbot = R.ip.bottom;
-            r.slot_flags = flags; r.y = y;
-            rows[k++] = r;
-        }
-        lng.x = fadd(lng.x, lng.ratio);                     // renderer.cpp:553-556
-        sht.x = fadd(sht.x, sht.ratio);
-        interp_step(lng.ip);
-        interp_step(sht.ip);
-    }
-}
-
-__global__ void __launch_bounds__(128) k_edgewalk(const __grid_constant__ ViewParams vp, Pools pl)
-{
-    uint32_t n_live = pl.counters->n_live;
-    for (uint32_t li = blockIdx.x * 128 + threadIdx.x; li < n_live; li += gridDim.x * 128) {
-        uint32_t slot = pl.live[li];
-        SlotEdge e = pl.edges[slot];
-        int y0 = ceil_i(e.y0), y1 = ceil_i(e.y1), y2 = ceil_i(e.y2);
-        uint32_t k = (uint32_t)e.span_base;
-
-        Side lng, sht;
-        lng.ratio = fdiv(fsub(e.x2, e.x0), fsub(e.y2, e.y0));              // renderer.cpp:400-409
-        interp_init_self(lng.ip, fsub(e.y2, e.y0), e.z0, e.z2);
-        {
-            float move = (y0 < vp.vy) ? fsub((float)vp.vy, e.y0) : fsub((float)y0, e.y0);
-            interp_displace(lng.ip, move);
-            lng.x = fadd(e.x0, fmul(lng.ratio, move));
-        }
-        if (y1 >= vp.vy) {                                                  // upper half, :416-436
-            sht.ratio = fdiv(fsub(e.x1, e.x0), fsub(e.y1, e.y0));
-            interp_init_self(sht.ip, fsub(e.y1, e.y0), e.z0, e.z1);
-            int y = max(y0, vp.vy), y_end = min(y1, vp.vy + vp.vh);
-            float move = fsub((float)y, e.y0);
-            interp_displace(sht.ip, move);
-            sht.x = fadd(e.x0, fmul(sht.ratio, move));
-            bool lor = lng.ratio > sht.ratio;
-            walk_half(vp, pl.rows, k, slot, 0, y, y_end, lor, lng, sht);
-        }
-        if (y1 < vp.vy + vp.vh) {                                           // lower half, :439-459
-            sht.ratio = fdiv(fsub(e.x2, e.x1), fsub(e.y2, e.y1));
-            interp_init_self(sht.ip, fsub(e.y2, e.y1), e.z1, e.z2);
-            int y = max(y1, vp.vy), y_end = min(y2, vp.vy + vp.vh);
-            float move = fsub((float)y, e.y1);
-            interp_displace(sht.ip, move);
-            sht.x = fadd(e.x1, fmul(sht.ratio, move));
-            bool lor = lng.ratio < sht.ratio;
-            walk_half(vp, pl.rows, k, slot, 1, y, y_end, lor, lng, sht);
-        }
-    }
-}
-
-// ----------------------------------------------------------------------------------------
-// spans: one thread per scanline record turns the edge state into the per-pixel interpolator,
-// replays it along x and drops a checkpoint ("chunk") at every 32-column bin it crosses
+// spans: one thread per scanline record.  The edges' state on this scanline is the state stored by
+// k_setup advanced by (y - first row) steps of `x += ratio; topalpha += topstep; bottomalpha += bottomstep`
+// (renderer.cpp:553-556) -- radd() does those steps exactly.  The thread then sets up the per-pixel
+// interpolator (renderer.cpp:469-480), replays it along x and drops a checkpoint ("chunk") at every
+// 32-column bin the span crosses.
 // ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB) k_spans(const __grid_constant__ ViewParams vp, Pools pl)
 {
-    if (pl.counters->overflow & 1u) return;      // some rows were never written: the host grows the pool and redoes the frame
-    uint32_t n_rows = min(pl.counters->n_rows, pl.rows_cap);
-    Span *spans = reinterpret_cast<Span *>(pl.rows);
+    if (pl.counters->overflow & 1u) return;      // some rows were never allocated: the host grows the pool and redoes the frame
+    const uint32_t n_rows = min(pl.counters->n_rows, pl.rows_cap);
+    Span *spans = pl.spans;
     for (uint32_t i = blockIdx.x * TPB + threadIdx.x; i < n_rows; i += gridDim.x * TPB) {
-        Row r = pl.rows[i];
+        const uint32_t slot = pl.row_slot[i];
+        const SlotEdge &e = pl.edges[slot];
+        const int j = (int)i - e.span_base;
+        // in-band scanlines of the upper half come first, then the lower half's
+        const int ua = max(e.ya_u, vp.band0), ub = min(e.yb_u, vp.band1);
+        const int nu = max(0, ub - ua);
+        const bool lower = j >= nu;
+        const int y = lower ? max(e.ya_l, vp.band0) + (j - nu) : ua + j;
+        const bool lor = lower ? ((e.flags >> 1) & 1u) : (e.flags & 1u);
+        const SideRec S = lower ? e.sl : e.su;
+        const SideRec G = e.lng;
+        const uint32_t kl = (uint32_t)(y - e.y_long), ks = (uint32_t)(y - (lower ? e.ya_l : e.ya_u));
+        const float gx = radd(G.x, G.ratio, kl), gtop = radd(G.top, G.topstep, kl), gbot = radd(G.bottom, G.bottomstep, kl);
+        const float sx = radd(S.x, S.ratio, ks), stop = radd(S.top, S.topstep, ks), sbot = radd(S.bottom, S.bottomstep, ks);
+        const float lx = lor ? sx : gx, rx = lor ? gx : sx;
+        const float ltop = lor ? stop : gtop, lbot = lor ? sbot : gbot, rtop = lor ? gtop : stop, rbot = lor ? gbot : sbot;
+
         Span sp;
-        sp.slot_flags = r.slot_flags;
-        int x1 = max(ceil_i(r.lx), vp.vx);                                  // renderer.cpp:469-470
-        int x2 = min(ceil_i(r.rx), vp.vx + vp.vw);
+        sp.slot_flags = (slot << 2) | ((uint32_t)lower << 1) | (lor ? 1u : 0u);
+        int x1 = max(ceil_i(lx), vp.vx);                                    // renderer.cpp:469-470
+        int x2 = min(ceil_i(rx), vp.vx + vp.vw);
         if (!(x1 < x2)) {
             sp.topstep = sp.bottomstep = sp.v0 = sp.v1 = sp.pl = sp.pr = 0.f; sp.x1x2 = 0;
             spans[i] = sp;
             continue;
         }
-        uint32_t slot = r.slot_flags >> 2;
-        bool lower = (r.slot_flags >> 1) & 1u, lor = r.slot_flags & 1u;
-        const SlotEdge &e = pl.edges[slot];
-        float z0 = e.z0, z1 = e.z1, z2 = e.z2;
+        const float z0 = e.z0, z1 = e.z1, z2 = e.z2;
         // edge interpolators' v[0]: long (z0, z2-z0); short (z0, z1-z0) upper / (z1, z2-z1) lower
-        float la = lor ? (lower ? z1 : z0) : z0;
-        float lb = lor ? (lower ? z2 : z1) : z2;
-        float ra = lor ? z0 : (lower ? z1 : z0);
-        float rb = lor ? z2 : (lower ? z2 : z1);
-        sp.pl = fdiv(r.ltop, r.lbot);                                       // interpolator progress()
-        sp.pr = fdiv(r.rtop, r.rbot);
-        float zl = fadd(la, fmul(fsub(lb, la), sp.pl));                     // value(0), interpolator.hpp:103
-        float zr = fadd(ra, fmul(fsub(rb, ra), sp.pr));
+        const float la = lor ? (lower ? z1 : z0) : z0;
+        const float lb = lor ? (lower ? z2 : z1) : z2;
+        const float ra = lor ? z0 : (lower ? z1 : z0);
+        const float rb = lor ? z2 : (lower ? z2 : z1);
+        sp.pl = fdiv(ltop, lbot);                                           // interpolator progress()
+        sp.pr = fdiv(rtop, rbot);
+        const float zl = fadd(la, fmul(fsub(lb, la), sp.pl));               // value(0), interpolator.hpp:103
+        const float zr = fadd(ra, fmul(fsub(rb, ra), sp.pr));
         Interp q;
-        interp_init_self(q, fsub(r.rx, r.lx), zl, zr);                      // renderer.cpp:476-480
-        interp_displace(q, fsub((float)x1, r.lx));
+        interp_init_self(q, fsub(rx, lx), zl, zr);                          // renderer.cpp:476-480
+        interp_displace(q, fsub((float)x1, lx));
         sp.topstep = q.topstep; sp.bottomstep = q.bottomstep; sp.v0 = q.v0; sp.v1 = q.v1;
         sp.x1x2 = (uint32_t)x1 | ((uint32_t)x2 << 16);
         spans[i] = sp;
@@ -331,17 +317,24 @@ __global__ void __launch_bounds__(TPB) k_spans(const __grid_constant__ ViewParam
         uint32_t nchunks = (uint32_t)(b1 - b0 + 1);
         uint32_t cbase = atomicAdd(&pl.counters->n_chunks, nchunks);
         if (cbase + nchunks > pl.chunks_cap) { atomicOr(&pl.counters->overflow, 2u); continue; }
-        int32_t *heads = pl.bin_head + (size_t)(r.y - vp.vy) * vp.nbx;
-        int b = b0;
-        for (int x = x1;;) {
+        int32_t *heads = pl.bin_head + (size_t)(y - vp.vy) * vp.nbx;
+        // the atomicExch that links a chunk into its bin has ~1 us latency: issue it, replay the
+        // interpolator across the bin while it is in flight, and only then write the chunk record
+        int b = b0, x = x1;
+        float ctop = q.top, cbot = q.bottom;
+        int32_t cnext = atomicExch(&heads[b], (int32_t)cbase);
+        for (;;) {
+            const int xn = min(vp.vx + ((b + 1) << 5), x2);                 // first column of the next bin
+            const bool last = xn >= x2;
+            if (!last)
+                for (; x < xn; x++) interp_step(q);                         // renderer.cpp:486 (Step per pixel)
             Chunk ch;
-            ch.top = q.top; ch.bottom = q.bottom; ch.span = i;
-            ch.next = atomicExch(&heads[b], (int32_t)cbase);
+            ch.top = ctop; ch.bottom = cbot; ch.span = i; ch.next = cnext;
             pl.chunks[cbase] = ch;
-            cbase++; b++;
-            int xn = min(vp.vx + (b << 5), x2);                             // first column of the next bin
-            if (xn >= x2) break;
-            for (; x < xn; x++) interp_step(q);                             // renderer.cpp:486 (Step per pixel)
+            if (last) break;
+            b++; cbase++;
+            ctop = q.top; cbot = q.bottom;
+            cnext = atomicExch(&heads[b], (int32_t)cbase);
         }
     }
 }
@@ -366,12 +359,6 @@ void launch_mark(const DeviceScene &s, cudaStream_t st)
 void launch_setup(const DeviceScene &s, const ViewParams &vp, const FrameParams &fp, const Pools &p, cudaStream_t st)
 {
     if (s.n_tris) k_setup<<<cdiv(s.n_tris, 128), 128, 0, st>>>(s, vp, fp, p);
-}
-void launch_edgewalk(const ViewParams &vp, const Pools &p, uint32_t max_live, cudaStream_t st)
-{
-    if (!max_live) return;
-    unsigned blocks = min(cdiv(max_live, 128u), 148u * 16u);
-    k_edgewalk<<<blocks, 128, 0, st>>>(vp, p);
 }
 void launch_spans(const ViewParams &vp, const Pools &p, cudaStream_t st)
 {

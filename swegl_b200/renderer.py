@@ -48,6 +48,20 @@ class Renderer:
             msg = self.lib.swegl_b200_last_error(self.ctx)
             raise SweglB200Error(f"swegl_b200 status {rc}: {msg.decode() if msg else ''}")
 
+    def synchronize(self):
+        self._check(self.lib.swegl_b200_synchronize(self.ctx))
+
+    def alloc_host(self, shape, dtype):
+        """numpy array backed by page-locked memory (for `pixels` / `zbuffer` of render())."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        if self.lib.swegl_b200_alloc_host(n, C.byref(p)) != _abi.OK:
+            raise SweglB200Error("swegl_b200_alloc_host failed")
+        buf = (C.c_uint8 * n).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+        self._pinned = getattr(self, "_pinned", []) + [p]
+        return arr
+
     def set_timing(self, enabled=True):
         self._check(self.lib.swegl_b200_set_timing(self.ctx, int(enabled)))
 
