@@ -208,7 +208,8 @@ int swegl_b200_upload_scene(swegl_b200_ctx *ctx, const swegl_b200_scene_desc *sc
             d.tex_off = tex_off[m.texture_idx];
             d.tw = sc->textures[m.texture_idx].width; d.th = sc->textures[m.texture_idx].height;
         }
-        d.pad0 = d.pad1 = 0;
+        d.tw_mask = (d.tw & (d.tw - 1)) == 0 ? d.tw - 1 : -1;
+        d.th_mask = (d.th & (d.th - 1)) == 0 ? d.th - 1 : -1;
         for (uint32_t k = 0; k < sp.n_vertices; k++) vert_node[sp.first_vertex + k] = (uint32_t)sp.node;
         const uint32_t *I = sc->indices + sp.first_index;
         auto idx = [&](uint32_t i) -> uint32_t { return sp.first_vertex + I[i]; };

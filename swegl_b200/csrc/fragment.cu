@@ -15,6 +15,23 @@ namespace sb {
 
 SB_DEV V3 ld3(const float *p) { return v3(p[0], p[1], p[2]); }
 
+// (unsigned char)round(x), colors.cpp:19-25 (round half away from zero), for the common case 0 <= x < 2^23
+// as trunc + exact fraction test; anything else takes roundf
+SB_DEV uint32_t round_to_byte(float a)
+{
+    if (!(a >= 0.0f && a < 8388608.0f)) return (uint32_t)f2i(roundf(a)) & 0xFFu;
+    const int i = __float2int_rz(a);
+    const float fr = fsub(a, (float)i);                                     // exact
+    return (uint32_t)(i + (fr >= 0.5f ? 1 : 0)) & 0xFFu;
+}
+// a mod n as the reference computes texel rows/columns, with the negative (UB in the reference) case wrapped
+SB_DEV int wrap_index(int a, int n, int mask)
+{
+    if (mask >= 0) return a & mask;                                         // power-of-two size
+    int r = a % n; if (r < 0) r += n;
+    return r;
+}
+
 template <int TEX>
 SB_DEV uint32_t shade_texture(const SlotShade *sh, const Prim &pr, const uint32_t *texels,
                               bool lower, bool lor, float pl, float pr_, float u)
@@ -39,7 +56,8 @@ SB_DEV uint32_t shade_texture(const SlotShade *sh, const Prim &pr, const uint32_
     if (TEX == SWEGL_B200_TEX_NEAREST) {
         // pixel_shader_texture::shade, pixel_shaders.cpp:275-281 (unsigned modulo)
         unsigned tw = (unsigned)pr.tw, th = (unsigned)pr.th;
-        unsigned uu = (unsigned)f2i(tx) % tw, vv = (unsigned)f2i(ty) % th;
+        unsigned uu = pr.tw_mask >= 0 ? ((unsigned)f2i(tx) & (unsigned)pr.tw_mask) : (unsigned)f2i(tx) % tw;
+        unsigned vv = pr.th_mask >= 0 ? ((unsigned)f2i(ty) & (unsigned)pr.th_mask) : (unsigned)f2i(ty) % th;
         return __ldg(&bm[vv * tw + uu]);
     }
     // pixel_shader_texture_bilinear::shade, pixel_shaders.cpp:348-384: t.x picks the ROW, t.y the COLUMN
@@ -47,10 +65,10 @@ SB_DEV uint32_t shade_texture(const SlotShade *sh, const Prim &pr, const uint32_
     float u1 = fsub(uq, 0.5f), u2 = fadd(uq, 0.5f), v1 = fsub(v, 0.5f), v2 = fadd(v, 0.5f);
     uq = floorf(u2); v = floorf(v2);
     int tw = pr.tw, th = pr.th;
-    int v1m = (f2i(v1) + th) % th; if (v1m < 0) { v1m %= th; if (v1m < 0) v1m += th; }   // UB guard
+    int v1m = wrap_index(f2i(v1) + th, th, pr.th_mask);                     // ((int)v1 + theight) % theight; UB guard
     int v2m = v1m + 1; if (v2m == th) v2m = 0;
     v1m *= tw; v2m *= tw;
-    int u1m = (f2i(u1) + tw) % tw; if (u1m < 0) { u1m %= tw; if (u1m < 0) u1m += tw; }
+    int u1m = wrap_index(f2i(u1) + tw, tw, pr.tw_mask);
     int u2m = u1m + 1; if (u2m == tw) u2m = 0;
     uint32_t p00 = __ldg(&bm[v1m + u1m]), p10 = __ldg(&bm[v2m + u1m]);
     uint32_t p01 = __ldg(&bm[v1m + u2m]), p11 = __ldg(&bm[v2m + u2m]);
@@ -64,7 +82,7 @@ SB_DEV uint32_t shade_texture(const SlotShade *sh, const Prim &pr, const uint32_
         acc = fadd(acc, fmul((float)((p10 >> sft) & 0xFF), w10));           // _mm_add_ps, left to right
         acc = fadd(acc, fmul((float)((p01 >> sft) & 0xFF), w01));
         acc = fadd(acc, fmul((float)((p11 >> sft) & 0xFF), w11));
-        out |= ((uint32_t)f2i(roundf(acc)) & 0xFFu) << sft;                 // (unsigned char)round(), colors.cpp:19-25
+        out |= round_to_byte(acc) << sft;                                   // (unsigned char)round(), colors.cpp:19-25
     }
     return out;
 }
@@ -109,14 +127,15 @@ SB_DEV uint32_t shade(const SlotShade *sh, const Prim &pr, const uint32_t *texel
     float light = fmul(__int2float_rn(li), 1.0f / 65536.0f);               // (float)(li / 65536.0)
     uint32_t b = c & 0xFF, g = (c >> 8) & 0xFF, r = (c >> 16) & 0xFF;
     if (light < 1.0f) {
-        b = (uint32_t)f2i(fmul((float)b, light)) & 0xFF;
-        g = (uint32_t)f2i(fmul((float)g, light)) & 0xFF;
-        r = (uint32_t)f2i(fmul((float)r, light)) & 0xFF;
+        // |light| <= 32768 and c <= 255, so the product is always inside int range: plain truncation
+        b = (uint32_t)__float2int_rz(fmul((float)b, light)) & 0xFF;
+        g = (uint32_t)__float2int_rz(fmul((float)g, light)) & 0xFF;
+        r = (uint32_t)__float2int_rz(fmul((float)r, light)) & 0xFF;
     } else {
         light = __fsqrt_rn(__fsqrt_rn(light));
-        b = (255u - ((uint32_t)f2i(fdiv((float)(255 - (int)b), light)) & 0xFF)) & 0xFF;
-        g = (255u - ((uint32_t)f2i(fdiv((float)(255 - (int)g), light)) & 0xFF)) & 0xFF;
-        r = (255u - ((uint32_t)f2i(fdiv((float)(255 - (int)r), light)) & 0xFF)) & 0xFF;
+        b = (255u - ((uint32_t)__float2int_rz(fdiv((float)(255 - (int)b), light)) & 0xFF)) & 0xFF;   // light >= 1
+        g = (255u - ((uint32_t)__float2int_rz(fdiv((float)(255 - (int)g), light)) & 0xFF)) & 0xFF;
+        r = (255u - ((uint32_t)__float2int_rz(fdiv((float)(255 - (int)r), light)) & 0xFF)) & 0xFF;
     }
     return (c & 0xFF000000u) | (r << 16) | (g << 8) | b;
 }
@@ -264,46 +283,74 @@ __global__ void __launch_bounds__(DOF_THREADS) k_dof(const uint32_t *__restrict_
 {
     __shared__ unsigned long long s64[(DOF_SH + 1) * DOF_PW];
     __shared__ uint32_t s32[(DOF_SH + 1) * DOF_PW];
-    __shared__ uint32_t magic[128];                          // ceil(2^28 / n): exact b / n for b < 2^15, n <= 100
-    const int tid = threadIdx.x;
+    __shared__ uint8_t srad[DOF_SH * DOF_SW];               // blur radius (0..5) of every staged pixel
+    __shared__ uint32_t magic[128];                          // ceil(2^28 / n): exact v / n for v < 2^15, n <= 100
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ox = blockIdx.x * DOF_OW, oy = row0 + blockIdx.y * DOF_OH;
+
+    // ---- stage the source window: warp `warp` loads rows warp, warp+8, ...; lanes sweep the 73 columns.
+    //      All global loads of a thread are issued before any is consumed (memory-level parallelism).
+    constexpr int ROWS_PER_WARP = (DOF_SH + 7) / 8;         // 6
+    constexpr int COLS_PER_LANE = (DOF_SW + 31) / 32;       // 3
+    float dz[ROWS_PER_WARP][COLS_PER_LANE]; uint32_t cc[ROWS_PER_WARP][COLS_PER_LANE];
+    const float maxz = __uint_as_float(MAXZ_BITS);
+    #pragma unroll
+    for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
+        const int sy = warp + rr * 8, gy = oy + sy - DOF_LO;
+        #pragma unroll
+        for (int cq = 0; cq < COLS_PER_LANE; cq++) {
+            const int sx = lane + cq * 32, gx = ox + sx - DOF_LO;
+            const bool in = sy < DOF_SH && sx < DOF_SW && gx >= 0 && gx < w && gy >= 0 && gy < h;
+            dz[rr][cq] = in ? __ldg(&depth[(size_t)gy * w + gx]) : __int_as_float(0x7FC00000);   // NaN = not a pixel
+            cc[rr][cq] = in ? __ldg(&src[(size_t)gy * src_pitch + gx]) : 0u;
+        }
+    }
+    // a window that only sees untouched background (colour 0, depth 0x7F7F7F7F) blurs to a constant
+    bool all_bg = true;
+    #pragma unroll
+    for (int rr = 0; rr < ROWS_PER_WARP; rr++)
+        #pragma unroll
+        for (int cq = 0; cq < COLS_PER_LANE; cq++) {
+            const bool pixel = dz[rr][cq] == dz[rr][cq];
+            all_bg = all_bg && (!pixel || (cc[rr][cq] == 0u && __float_as_uint(dz[rr][cq]) == MAXZ_BITS));
+        }
+    if (__syncthreads_and(all_bg)) {
+        const float bf = blur_factor(maxz, focal_distance, focal_depth);
+        const int radius = f2i(bf);
+        // r == 0: copy (0); else every tap counts iff bf != 0 -> average of zeros with alpha 255, or no taps -> copy
+        const uint32_t v = (radius != 0 && bf != 0.0f) ? 0xFF000000u : 0u;
+        for (int p = tid; p < DOF_OW * DOF_OH; p += DOF_THREADS) {
+            const int ty = p / DOF_OW, tx = p % DOF_OW;
+            const int x = ox + tx, y = oy + ty;
+            if (y < row1 && y < h && x < w) dst[(size_t)y * dst_pitch + x] = v;
+        }
+        return;
+    }
 
     if (tid < 128) magic[tid] = tid ? (uint32_t)(((1u << 28) + tid - 1) / tid) : 0u;
     for (int i = tid; i < DOF_PW; i += DOF_THREADS) { s64[i] = 0; s32[i] = 0; }                 // zero row 0
     for (int i = tid; i <= DOF_SH; i += DOF_THREADS) { s64[i * DOF_PW] = 0; s32[i * DOF_PW] = 0; } // zero column 0
-    // stage the source window: loads are issued in batches of DOF_BATCH per thread (all independent) so the
-    // L2/HBM latency is paid once per batch instead of once per element
-    constexpr int DOF_ITEMS = (DOF_SW * DOF_SH + DOF_THREADS - 1) / DOF_THREADS;      // 12
-    constexpr int DOF_BATCH = 6;
-    static_assert(DOF_ITEMS % DOF_BATCH == 0, "batching assumes an exact split");
     #pragma unroll
-    for (int it0 = 0; it0 < DOF_ITEMS; it0 += DOF_BATCH) {
-        float dz[DOF_BATCH]; uint32_t cc[DOF_BATCH];
-        uint32_t inmask = 0;
+    for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
+        const int sy = warp + rr * 8;
         #pragma unroll
-        for (int u = 0; u < DOF_BATCH; u++) {
-            const int i = tid + (it0 + u) * DOF_THREADS;
-            const int sy = i / DOF_SW, sx = i - sy * DOF_SW;
-            const int gx = ox + sx - DOF_LO, gy = oy + sy - DOF_LO;
-            const bool in = i < DOF_SW * DOF_SH && gx >= 0 && gx < w && gy >= 0 && gy < h;
-            dz[u] = in ? __ldg(&depth[(size_t)gy * w + gx]) : 0.0f;
-            cc[u] = in ? __ldg(&src[(size_t)gy * src_pitch + gx]) : 0u;
-            inmask |= (in ? 1u : 0u) << u;
-        }
-        #pragma unroll
-        for (int u = 0; u < DOF_BATCH; u++) {
-            const int i = tid + (it0 + u) * DOF_THREADS;
-            if (i >= DOF_SW * DOF_SH) continue;
-            const int sy = i / DOF_SW, sx = i - sy * DOF_SW;
-            unsigned long long v = 0; uint32_t n = 0;
-            if (((inmask >> u) & 1u) && blur_factor(dz[u], focal_distance, focal_depth) != 0.0f) {
-                const uint32_t c = cc[u];
-                v = (unsigned long long)(c & 0xFF) | ((unsigned long long)((c >> 8) & 0xFF) << 21)
-                  | ((unsigned long long)((c >> 16) & 0xFF) << 42);
-                n = 1;
+        for (int cq = 0; cq < COLS_PER_LANE; cq++) {
+            const int sx = lane + cq * 32;
+            if (sy >= DOF_SH || sx >= DOF_SW) continue;
+            unsigned long long v = 0; uint32_t n = 0; uint32_t rad = 0;
+            if (dz[rr][cq] == dz[rr][cq]) {
+                const float bf = blur_factor(dz[rr][cq], focal_distance, focal_depth);
+                rad = (uint32_t)f2i(bf);
+                if (bf != 0.0f) {
+                    const uint32_t c = cc[rr][cq];
+                    v = (unsigned long long)(c & 0xFF) | ((unsigned long long)((c >> 8) & 0xFF) << 21)
+                      | ((unsigned long long)((c >> 16) & 0xFF) << 42);
+                    n = 1;
+                }
             }
             s64[(sy + 1) * DOF_PW + sx + 1] = v;
             s32[(sy + 1) * DOF_PW + sx + 1] = n;
+            srad[sy * DOF_SW + sx] = (uint8_t)rad;
         }
     }
     __syncthreads();
@@ -328,59 +375,37 @@ __global__ void __launch_bounds__(DOF_THREADS) k_dof(const uint32_t *__restrict_
     }
     __syncthreads();
 
-    // each thread: 2 groups of 4 consecutive pixels (one 128-bit load of colour and depth, one 128-bit store)
-    #pragma unroll
-    for (int g = 0; g < (DOF_OW * DOF_OH) / (4 * DOF_THREADS); g++) {
-        const int q = tid + g * DOF_THREADS;                 // quad index in the tile
-        const int ty = q / (DOF_OW / 4), tx = (q % (DOF_OW / 4)) * 4;
-        const int x0 = ox + tx, y = oy + ty;
-        if (y >= row1 || y >= h || x0 >= w) continue;
-        uint32_t own[4]; float dz[4];
-        const bool vec = (x0 + 3 < w) && ((src_pitch & 3) == 0) && ((w & 3) == 0) && ((dst_pitch & 3) == 0)
-                      && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(depth) & 15) == 0)
-                      && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-        if (vec) {
-            const uint4 c4 = *reinterpret_cast<const uint4 *>(src + (size_t)y * src_pitch + x0);
-            const float4 d4 = *reinterpret_cast<const float4 *>(depth + (size_t)y * w + x0);
-            own[0] = c4.x; own[1] = c4.y; own[2] = c4.z; own[3] = c4.w;
-            dz[0] = d4.x; dz[1] = d4.y; dz[2] = d4.z; dz[3] = d4.w;
-        } else {
-            #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const bool in = x0 + k < w;
-                own[k] = in ? src[(size_t)y * src_pitch + x0 + k] : 0u;
-                dz[k] = in ? depth[(size_t)y * w + x0 + k] : 0.f;
-            }
-        }
-        uint32_t out[4];
-        #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int radius = f2i(blur_factor(dz[k], focal_distance, focal_depth));
-            out[k] = own[k];
-            if (radius != 0) {
-                // SAT index of source pixel (gx, gy) is (gx - ox + 6, gy - oy + 6); the zero border and the
-                // zeros stored for out-of-viewport pixels implement the max(0,..)/min(w|h,..) clipping
-                const int J0 = ty + DOF_LO - radius, J1 = ty + DOF_LO + radius;
-                const int I0 = tx + k + DOF_LO - radius, I1 = tx + k + DOF_LO + radius;
+    // ---- outputs: consecutive lanes take consecutive pixels (conflict-free SAT reads, coalesced stores)
+    #pragma unroll 2
+    for (int p = tid; p < DOF_OW * DOF_OH; p += DOF_THREADS) {
+        const int ty = p / DOF_OW, tx = p % DOF_OW;
+        const int x = ox + tx, y = oy + ty;
+        if (y >= row1 || y >= h || x >= w) continue;
+        const int radius = srad[(ty + DOF_LO) * DOF_SW + tx + DOF_LO];
+        uint32_t out;
+        bool have = false;
+        if (radius != 0) {
+            // SAT index of source pixel (gx, gy) is (gx - ox + 6, gy - oy + 6); the zero border and the
+            // zeros stored for out-of-viewport pixels implement the max(0,..)/min(w|h,..) clipping
+            const int J0 = ty + DOF_LO - radius, J1 = ty + DOF_LO + radius;
+            const int I0 = tx + DOF_LO - radius, I1 = tx + DOF_LO + radius;
+            const uint32_t count = (s32[J1 * DOF_PW + I1] + s32[J0 * DOF_PW + I0])
+                                 - (s32[J0 * DOF_PW + I1] + s32[J1 * DOF_PW + I0]);
+            if (count) {
                 const unsigned long long sum = (s64[J1 * DOF_PW + I1] + s64[J0 * DOF_PW + I0])
                                              - (s64[J0 * DOF_PW + I1] + s64[J1 * DOF_PW + I0]);
-                const uint32_t count = (s32[J1 * DOF_PW + I1] + s32[J0 * DOF_PW + I0])
-                                     - (s32[J0 * DOF_PW + I1] + s32[J1 * DOF_PW + I0]);
-                if (count) {
-                    const unsigned long long m = magic[count];
-                    const uint32_t b = (uint32_t)(((sum & 0x1FFFFFull) * m) >> 28);
-                    const uint32_t gg = (uint32_t)((((sum >> 21) & 0x1FFFFFull) * m) >> 28);
-                    const uint32_t r = (uint32_t)((((sum >> 42) & 0x1FFFFFull) * m) >> 28);
-                    out[k] = b | (gg << 8) | (r << 16) | 0xFF000000u;
-                }
+                // exact floor(v / count) for v < 2^15, count <= 100: (v * ceil(2^28 / count)) >> 28, as one IMAD.HI
+                const uint32_t m = magic[count];
+                const uint32_t lo = (uint32_t)sum, hi = (uint32_t)(sum >> 32);
+                const uint32_t b = __umulhi((lo & 0x1FFFFFu) << 4, m);
+                const uint32_t g = __umulhi((((lo >> 21) | (hi << 11)) & 0x1FFFFFu) << 4, m);
+                const uint32_t r = __umulhi(((hi >> 10) & 0x1FFFFFu) << 4, m);
+                out = b | (g << 8) | (r << 16) | 0xFF000000u;
+                have = true;
             }
         }
-        if (vec) {
-            *reinterpret_cast<uint4 *>(dst + (size_t)y * dst_pitch + x0) = make_uint4(out[0], out[1], out[2], out[3]);
-        } else {
-            #pragma unroll
-            for (int k = 0; k < 4; k++) if (x0 + k < w) dst[(size_t)y * dst_pitch + x0 + k] = out[k];
-        }
+        if (!have) out = __ldg(&src[(size_t)y * src_pitch + x]);
+        dst[(size_t)y * dst_pitch + x] = out;
     }
 }
 

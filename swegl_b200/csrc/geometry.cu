@@ -14,6 +14,7 @@
 namespace sb {
 
 static constexpr int TPB = 256;
+static constexpr uint32_t SPAN_SEG = 8;      // 32-column bins per span segment (one lane walks one segment)
 
 // ----------------------------------------------------------------------------------------
 // vertex stage
@@ -113,15 +114,18 @@ SB_DEV SV make_clip_vertex(const DeviceScene &s, const ViewParams &vp, const flo
 }
 
 // fill_triangle_2 up to the row count: y sort, ceil limits, and the records the later stages need
-SB_DEV void emit_slot(const DeviceScene &s, const ViewParams &vp, const FrameParams &fp, const Pools &pl,
-                      uint32_t slot, uint32_t prim_id, const Prim &pr, SV a, SV b, SV c, bool front_face_visible)
+struct RowRange { uint32_t base, n; };     // scanline records a slot allocated (n == 0: nothing to draw)
+
+SB_DEV RowRange emit_slot(const DeviceScene &s, const ViewParams &vp, const FrameParams &fp, const Pools &pl,
+                          uint32_t slot, uint32_t prim_id, const Prim &pr, SV a, SV b, SV c, bool front_face_visible)
 {
+    const RowRange none = { 0u, 0u };
     bool inverted = !front_face_visible;
     if (b.s.y < a.s.y) swap_sv(a, b);                       // renderer.cpp:375-387
     if (c.s.y < b.s.y) swap_sv(b, c);
     if (b.s.y < a.s.y) swap_sv(a, b);
     int y0 = ceil_i(a.s.y), y1 = ceil_i(b.s.y), y2 = ceil_i(c.s.y);
-    if (y0 == y2) return;                                   // renderer.cpp:394
+    if (y0 == y2) return none;                              // renderer.cpp:394
 
     // scanlines this slot will walk inside the band (upper half :416-421, lower half :439-444)
     int n = 0;
@@ -133,9 +137,9 @@ SB_DEV void emit_slot(const DeviceScene &s, const ViewParams &vp, const FramePar
         int ya = max(max(y1, vp.vy), vp.band0), yb = min(min(y2, vp.vy + vp.vh), vp.band1);
         n += max(0, yb - ya);
     }
-    if (n == 0) return;
+    if (n == 0) return none;
     uint32_t base = atomicAdd(&pl.counters->n_rows, (uint32_t)n);
-    if (base + (uint32_t)n > pl.rows_cap) { atomicOr(&pl.counters->overflow, 1u); return; }
+    if (base + (uint32_t)n > pl.rows_cap) { atomicOr(&pl.counters->overflow, 1u); return none; }
 
     // fill_triangle_2's edge set-up (renderer.cpp:396-459): every side's state at the first scanline it is
     // walked on.  k_spans jumps from here to any scanline with radd().
@@ -179,7 +183,6 @@ SB_DEV void emit_slot(const DeviceScene &s, const ViewParams &vp, const FramePar
     e.z0 = z0; e.z1 = z1; e.z2 = z2;
     e.span_base = (int32_t)base; e.pad = 0;
     pl.edges[slot] = e;
-    for (int k = 0; k < n; k++) pl.row_slot[base + k] = slot;               // scanline record -> owning slot
 
     SlotShade sh;
     sh.w0[0] = a.w.x; sh.w0[1] = a.w.y; sh.w0[2] = a.w.z;
@@ -212,49 +215,76 @@ SB_DEV void emit_slot(const DeviceScene &s, const ViewParams &vp, const FramePar
     pl.shades[slot] = sh;
 
     atomicAdd(&pl.counters->n_slots, 1u);
+    const RowRange rr = { base, (uint32_t)n };
+    return rr;
+}
+
+// row_slot[base .. base+n) = slot (scanline record -> owning slot).  Short ranges are written by their
+// own thread; tall triangles are written by the whole warp so no lane runs a thousand-iteration loop.
+SB_DEV void fill_row_slots(const Pools &pl, RowRange rr, uint32_t slot)
+{
+    const int lane = threadIdx.x & 31;
+    const bool big = rr.n > 8;
+    if (!big) for (uint32_t k = 0; k < rr.n; k++) pl.row_slot[rr.base + k] = slot;
+    unsigned m = __ballot_sync(0xFFFFFFFFu, big);
+    while (m) {
+        const int l = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t b = __shfl_sync(0xFFFFFFFFu, rr.base, l), n = __shfl_sync(0xFFFFFFFFu, rr.n, l);
+        const uint32_t sl = __shfl_sync(0xFFFFFFFFu, slot, l);
+        for (uint32_t k = lane; k < n; k += 32) pl.row_slot[b + k] = sl;
+    }
 }
 
 __global__ void __launch_bounds__(128) k_setup(DeviceScene s, const __grid_constant__ ViewParams vp,
                                                const __grid_constant__ FrameParams fp, Pools pl)
 {
-    uint32_t t = blockIdx.x * 128 + threadIdx.x;
-    if (t >= s.n_tris) return;
-    Tri tr = s.tris[t];
-    if (!s.yes[tr.i0] || !s.yes[tr.i1] || !s.yes[tr.i2]) return;        // renderer.cpp:248-253
-    Prim pr = s.prims[tr.prim];
-    SV a = load_sv(s, vp, tr.i0), b = load_sv(s, vp, tr.i1), c = load_sv(s, vp, tr.i2);
-
-    bool ffv = cross_n(sub(b.s, a.s), sub(c.s, a.s)).z < 0.0f;          // renderer.cpp:258
-    bool inverted_order = false;
-    if (b.s.z > a.s.z) { swap_sv(a, b); inverted_order = !inverted_order; }   // sort by z DESC, :264-279
-    if (c.s.z > b.s.z) { swap_sv(b, c); inverted_order = !inverted_order; }
-    if (b.s.z > a.s.z) { swap_sv(a, b); inverted_order = !inverted_order; }
-
-    const float *m9 = s.node_normal + 9 * pr.node;
-    if (c.s.z >= NEAR_Z) {
-        emit_slot(s, vp, fp, pl, 2 * t, tr.prim, pr, a, b, c, ffv);
-    } else if (b.s.z < NEAR_Z) {
-        // only a in front of the camera, renderer.cpp:286-317
-        float cut_1 = fdiv(fsub(a.s.z, 0.001f), fsub(a.s.z, b.s.z));
-        SV n1 = make_clip_vertex(s, vp, m9, a, b, cut_1);
-        float cut_2 = fdiv(fsub(a.s.z, 0.001f), fsub(a.s.z, c.s.z));
-        SV n2 = make_clip_vertex(s, vp, m9, a, c, cut_2);
-        ffv = cross_n(sub(n1.s, a.s), sub(n2.s, a.s)).z < 0.0f;
-        if (inverted_order) ffv = !ffv;
-        emit_slot(s, vp, fp, pl, 2 * t, tr.prim, pr, a, n1, n2, ffv);
-    } else if (c.s.z < NEAR_Z) {
-        // only c behind the camera: two triangles, renderer.cpp:318-356
-        float cut_0 = fdiv(fsub(a.s.z, 0.001f), fsub(a.s.z, c.s.z));
-        SV n1 = make_clip_vertex(s, vp, m9, a, c, cut_0);
-        float cut_1 = fdiv(fsub(b.s.z, 0.001f), fsub(b.s.z, c.s.z));
-        SV n2 = make_clip_vertex(s, vp, m9, b, c, cut_1);
-        ffv = cross_n(sub(b.s, a.s), sub(n2.s, a.s)).z < 0.0f;
-        if (inverted_order) ffv = !ffv;
-        emit_slot(s, vp, fp, pl, 2 * t, tr.prim, pr, a, b, n2, ffv);
-        ffv = cross_n(sub(n2.s, a.s), sub(n1.s, a.s)).z < 0.0f;
-        if (inverted_order) ffv = !ffv;
-        emit_slot(s, vp, fp, pl, 2 * t + 1, tr.prim, pr, a, n2, n1, ffv);
+    const uint32_t t = blockIdx.x * 128 + threadIdx.x;
+    RowRange r0 = { 0u, 0u }, r1 = { 0u, 0u };
+    Tri tr = { 0u, 0u, 0u, 0u };
+    bool go = t < s.n_tris;
+    if (go) {
+        tr = s.tris[t];
+        go = s.yes[tr.i0] && s.yes[tr.i1] && s.yes[tr.i2];                  // renderer.cpp:248-253
     }
+    if (go) {
+        Prim pr = s.prims[tr.prim];
+        SV a = load_sv(s, vp, tr.i0), b = load_sv(s, vp, tr.i1), c = load_sv(s, vp, tr.i2);
+
+        bool ffv = cross_n(sub(b.s, a.s), sub(c.s, a.s)).z < 0.0f;          // renderer.cpp:258
+        bool inverted_order = false;
+        if (b.s.z > a.s.z) { swap_sv(a, b); inverted_order = !inverted_order; }   // sort by z DESC, :264-279
+        if (c.s.z > b.s.z) { swap_sv(b, c); inverted_order = !inverted_order; }
+        if (b.s.z > a.s.z) { swap_sv(a, b); inverted_order = !inverted_order; }
+
+        const float *m9 = s.node_normal + 9 * pr.node;
+        if (c.s.z >= NEAR_Z) {
+            r0 = emit_slot(s, vp, fp, pl, 2 * t, tr.prim, pr, a, b, c, ffv);
+        } else if (b.s.z < NEAR_Z) {
+            // only a in front of the camera, renderer.cpp:286-317
+            float cut_1 = fdiv(fsub(a.s.z, 0.001f), fsub(a.s.z, b.s.z));
+            SV n1 = make_clip_vertex(s, vp, m9, a, b, cut_1);
+            float cut_2 = fdiv(fsub(a.s.z, 0.001f), fsub(a.s.z, c.s.z));
+            SV n2 = make_clip_vertex(s, vp, m9, a, c, cut_2);
+            ffv = cross_n(sub(n1.s, a.s), sub(n2.s, a.s)).z < 0.0f;
+            if (inverted_order) ffv = !ffv;
+            r0 = emit_slot(s, vp, fp, pl, 2 * t, tr.prim, pr, a, n1, n2, ffv);
+        } else if (c.s.z < NEAR_Z) {
+            // only c behind the camera: two triangles, renderer.cpp:318-356
+            float cut_0 = fdiv(fsub(a.s.z, 0.001f), fsub(a.s.z, c.s.z));
+            SV n1 = make_clip_vertex(s, vp, m9, a, c, cut_0);
+            float cut_1 = fdiv(fsub(b.s.z, 0.001f), fsub(b.s.z, c.s.z));
+            SV n2 = make_clip_vertex(s, vp, m9, b, c, cut_1);
+            ffv = cross_n(sub(b.s, a.s), sub(n2.s, a.s)).z < 0.0f;
+            if (inverted_order) ffv = !ffv;
+            r0 = emit_slot(s, vp, fp, pl, 2 * t, tr.prim, pr, a, b, n2, ffv);
+            ffv = cross_n(sub(n2.s, a.s), sub(n1.s, a.s)).z < 0.0f;
+            if (inverted_order) ffv = !ffv;
+            r1 = emit_slot(s, vp, fp, pl, 2 * t + 1, tr.prim, pr, a, n2, n1, ffv);
+        }
+    }
+    fill_row_slots(pl, r0, 2 * t);
+    if (__any_sync(0xFFFFFFFFu, r1.n != 0)) fill_row_slots(pl, r1, 2 * t + 1);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -268,73 +298,127 @@ __global__ void __launch_bounds__(TPB) k_spans(const __grid_constant__ ViewParam
 {
     if (pl.counters->overflow & 1u) return;      // some rows were never allocated: the host grows the pool and redoes the frame
     const uint32_t n_rows = min(pl.counters->n_rows, pl.rows_cap);
+    const int lane = threadIdx.x & 31;
+    const int grp = lane >> 3, rec = lane & 7;   // 4 scanlines per warp, 8 lanes each; lane `rec` < 6 owns one recurrence
+    const int lead = grp << 3;                   // the group's leader lane
+    const uint32_t warp_id = (blockIdx.x * TPB + threadIdx.x) >> 5, n_warps = (gridDim.x * TPB) >> 5;
     Span *spans = pl.spans;
-    for (uint32_t i = blockIdx.x * TPB + threadIdx.x; i < n_rows; i += gridDim.x * TPB) {
-        const uint32_t slot = pl.row_slot[i];
-        const SlotEdge &e = pl.edges[slot];
-        const int j = (int)i - e.span_base;
-        // in-band scanlines of the upper half come first, then the lower half's
-        const int ua = max(e.ya_u, vp.band0), ub = min(e.yb_u, vp.band1);
-        const int nu = max(0, ub - ua);
-        const bool lower = j >= nu;
-        const int y = lower ? max(e.ya_l, vp.band0) + (j - nu) : ua + j;
-        const bool lor = lower ? ((e.flags >> 1) & 1u) : (e.flags & 1u);
-        const SideRec S = lower ? e.sl : e.su;
-        const SideRec G = e.lng;
-        const uint32_t kl = (uint32_t)(y - e.y_long), ks = (uint32_t)(y - (lower ? e.ya_l : e.ya_u));
-        const float gx = radd(G.x, G.ratio, kl), gtop = radd(G.top, G.topstep, kl), gbot = radd(G.bottom, G.bottomstep, kl);
-        const float sx = radd(S.x, S.ratio, ks), stop = radd(S.top, S.topstep, ks), sbot = radd(S.bottom, S.bottomstep, ks);
-        const float lx = lor ? sx : gx, rx = lor ? gx : sx;
-        const float ltop = lor ? stop : gtop, lbot = lor ? sbot : gbot, rtop = lor ? gtop : stop, rbot = lor ? gbot : sbot;
-
-        Span sp;
-        sp.slot_flags = (slot << 2) | ((uint32_t)lower << 1) | (lor ? 1u : 0u);
-        int x1 = max(ceil_i(lx), vp.vx);                                    // renderer.cpp:469-470
-        int x2 = min(ceil_i(rx), vp.vx + vp.vw);
-        if (!(x1 < x2)) {
-            sp.topstep = sp.bottomstep = sp.v0 = sp.v1 = sp.pl = sp.pr = 0.f; sp.x1x2 = 0;
-            spans[i] = sp;
-            continue;
+    for (uint32_t r0 = warp_id * 4; r0 < n_rows; r0 += n_warps * 4) {       // warp-uniform
+        const uint32_t i = r0 + grp;
+        const bool valid = i < n_rows;
+        // ---- 6 lanes per scanline: each advances one of the edge recurrences to this scanline with radd() ----
+        uint32_t slot = 0; int y = 0; bool lower = false, lor = false;
+        float val = 0.f, z0 = 0.f, z1 = 0.f, z2 = 0.f;
+        if (valid) {
+            slot = pl.row_slot[i];
+            const SlotEdge &e = pl.edges[slot];
+            const int j = (int)i - e.span_base;
+            // in-band scanlines of the upper half come first, then the lower half's
+            const int ua = max(e.ya_u, vp.band0), ub = min(e.yb_u, vp.band1);
+            const int nu = max(0, ub - ua);
+            lower = j >= nu;
+            y = lower ? max(e.ya_l, vp.band0) + (j - nu) : ua + j;
+            lor = lower ? ((e.flags >> 1) & 1u) : (e.flags & 1u);
+            if (rec < 6) {
+                // rec 0..2: long side x / topalpha / bottomalpha; rec 3..5: the half's short side
+                const SideRec &S = rec < 3 ? e.lng : (lower ? e.sl : e.su);
+                const uint32_t k = rec < 3 ? (uint32_t)(y - e.y_long) : (uint32_t)(y - (lower ? e.ya_l : e.ya_u));
+                const int f = rec % 3;
+                const float start = f == 0 ? S.x : (f == 1 ? S.top : S.bottom);
+                const float step = f == 0 ? S.ratio : (f == 1 ? S.topstep : S.bottomstep);
+                val = radd(start, step, k);                                 // renderer.cpp:553-556, k times
+            }
+            if (rec == 0) { z0 = e.z0; z1 = e.z1; z2 = e.z2; }
         }
-        const float z0 = e.z0, z1 = e.z1, z2 = e.z2;
-        // edge interpolators' v[0]: long (z0, z2-z0); short (z0, z1-z0) upper / (z1, z2-z1) lower
-        const float la = lor ? (lower ? z1 : z0) : z0;
-        const float lb = lor ? (lower ? z2 : z1) : z2;
-        const float ra = lor ? z0 : (lower ? z1 : z0);
-        const float rb = lor ? z2 : (lower ? z2 : z1);
-        sp.pl = fdiv(ltop, lbot);                                           // interpolator progress()
-        sp.pr = fdiv(rtop, rbot);
-        const float zl = fadd(la, fmul(fsub(lb, la), sp.pl));               // value(0), interpolator.hpp:103
-        const float zr = fadd(ra, fmul(fsub(rb, ra), sp.pr));
-        Interp q;
-        interp_init_self(q, fsub(rx, lx), zl, zr);                          // renderer.cpp:476-480
-        interp_displace(q, fsub((float)x1, lx));
-        sp.topstep = q.topstep; sp.bottomstep = q.bottomstep; sp.v0 = q.v0; sp.v1 = q.v1;
-        sp.x1x2 = (uint32_t)x1 | ((uint32_t)x2 << 16);
-        spans[i] = sp;
+        const float gx = __shfl_sync(0xFFFFFFFFu, val, lead + 0), gtop = __shfl_sync(0xFFFFFFFFu, val, lead + 1);
+        const float gbot = __shfl_sync(0xFFFFFFFFu, val, lead + 2), sx = __shfl_sync(0xFFFFFFFFu, val, lead + 3);
+        const float stop = __shfl_sync(0xFFFFFFFFu, val, lead + 4), sbot = __shfl_sync(0xFFFFFFFFu, val, lead + 5);
 
-        int b0 = (x1 - vp.vx) >> 5, b1 = (x2 - 1 - vp.vx) >> 5;
-        uint32_t nchunks = (uint32_t)(b1 - b0 + 1);
-        uint32_t cbase = atomicAdd(&pl.counters->n_chunks, nchunks);
-        if (cbase + nchunks > pl.chunks_cap) { atomicOr(&pl.counters->overflow, 2u); continue; }
-        int32_t *heads = pl.bin_head + (size_t)(y - vp.vy) * vp.nbx;
-        // the atomicExch that links a chunk into its bin has ~1 us latency: issue it, replay the
-        // interpolator across the bin while it is in flight, and only then write the chunk record
-        int b = b0, x = x1;
-        float ctop = q.top, cbot = q.bottom;
-        int32_t cnext = atomicExch(&heads[b], (int32_t)cbase);
-        for (;;) {
-            const int xn = min(vp.vx + ((b + 1) << 5), x2);                 // first column of the next bin
-            const bool last = xn >= x2;
-            if (!last)
-                for (; x < xn; x++) interp_step(q);                         // renderer.cpp:486 (Step per pixel)
-            Chunk ch;
-            ch.top = ctop; ch.bottom = cbot; ch.span = i; ch.next = cnext;
-            pl.chunks[cbase] = ch;
-            if (last) break;
-            b++; cbase++;
-            ctop = q.top; cbot = q.bottom;
-            cnext = atomicExch(&heads[b], (int32_t)cbase);
+        // ---- leader lane: the scanline's span (renderer.cpp:469-480) ----
+        uint32_t nchunks = 0;
+        int x1 = 0, x2 = 0;
+        Interp q; q.top = q.topstep = q.bottom = q.bottomstep = q.v0 = q.v1 = 0.f;
+        Span sp;
+        if (valid && rec == 0) {
+            const float lx = lor ? sx : gx, rx = lor ? gx : sx;
+            const float ltop = lor ? stop : gtop, lbot = lor ? sbot : gbot, rtop = lor ? gtop : stop, rbot = lor ? gbot : sbot;
+            sp.slot_flags = (slot << 2) | ((uint32_t)lower << 1) | (lor ? 1u : 0u);
+            x1 = max(ceil_i(lx), vp.vx);
+            x2 = min(ceil_i(rx), vp.vx + vp.vw);
+            if (x1 < x2) {
+                // edge interpolators' v[0]: long (z0, z2-z0); short (z0, z1-z0) upper / (z1, z2-z1) lower
+                const float la = lor ? (lower ? z1 : z0) : z0;
+                const float lb = lor ? (lower ? z2 : z1) : z2;
+                const float ra = lor ? z0 : (lower ? z1 : z0);
+                const float rb = lor ? z2 : (lower ? z2 : z1);
+                sp.pl = fdiv(ltop, lbot);                                   // interpolator progress()
+                sp.pr = fdiv(rtop, rbot);
+                const float zl = fadd(la, fmul(fsub(lb, la), sp.pl));       // value(0), interpolator.hpp:103
+                const float zr = fadd(ra, fmul(fsub(rb, ra), sp.pr));
+                interp_init_self(q, fsub(rx, lx), zl, zr);
+                interp_displace(q, fsub((float)x1, lx));
+                sp.topstep = q.topstep; sp.bottomstep = q.bottomstep; sp.v0 = q.v0; sp.v1 = q.v1;
+                sp.x1x2 = (uint32_t)x1 | ((uint32_t)x2 << 16);
+                nchunks = (uint32_t)(((x2 - 1 - vp.vx) >> 5) - ((x1 - vp.vx) >> 5) + 1);
+            } else {
+                sp.topstep = sp.bottomstep = sp.v0 = sp.v1 = sp.pl = sp.pr = 0.f; sp.x1x2 = 0;
+            }
+        }
+        // one chunk allocation per warp instead of one same-address atomic per scanline
+        const uint32_t n0 = __shfl_sync(0xFFFFFFFFu, nchunks, 0), n1 = __shfl_sync(0xFFFFFFFFu, nchunks, 8);
+        const uint32_t n2 = __shfl_sync(0xFFFFFFFFu, nchunks, 16), n3 = __shfl_sync(0xFFFFFFFFu, nchunks, 24);
+        uint32_t wbase = 0;
+        if (lane == 0 && n0 + n1 + n2 + n3) wbase = atomicAdd(&pl.counters->n_chunks, n0 + n1 + n2 + n3);
+        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+        const bool room = wbase + n0 + n1 + n2 + n3 <= pl.chunks_cap;
+        if (!room && lane == 0) atomicOr(&pl.counters->overflow, 2u);
+        if (valid && rec == 0) spans[i] = sp;
+        if (!room) continue;
+        // ---- whole warp: one lane per SEGMENT (SPAN_SEG bins = 256 pixels) of the warp's 4 spans, so a
+        //      screen-wide span is walked by several lanes.  A lane jumps to its segment's first column
+        //      with radd() (free for the first segment) and then replays qpixel.Step() pixel by pixel
+        //      (renderer.cpp:486), dropping a chunk at every 32-column bin. ----
+        const uint32_t s0 = (n0 + SPAN_SEG - 1) / SPAN_SEG, s1 = s0 + (n1 + SPAN_SEG - 1) / SPAN_SEG;
+        const uint32_t s2 = s1 + (n2 + SPAN_SEG - 1) / SPAN_SEG, total = s2 + (n3 + SPAN_SEG - 1) / SPAN_SEG;
+        for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+            const uint32_t t = t0 + lane;
+            const int og = t < s0 ? 0 : (t < s1 ? 1 : (t < s2 ? 2 : 3));    // owning group
+            const int ol = og << 3;
+            const uint32_t o_first = og == 0 ? 0u : (og == 1 ? s0 : (og == 2 ? s1 : s2));
+            const uint32_t o_nch = og == 0 ? n0 : (og == 1 ? n1 : (og == 2 ? n2 : n3));
+            const uint32_t o_cbase = wbase + (og == 0 ? 0u : (og == 1 ? n0 : (og == 2 ? n0 + n1 : n0 + n1 + n2)));
+            const int o_x1 = __shfl_sync(0xFFFFFFFFu, x1, ol), o_y = __shfl_sync(0xFFFFFFFFu, y, ol);
+            Interp w;
+            w.top = __shfl_sync(0xFFFFFFFFu, q.top, ol); w.topstep = __shfl_sync(0xFFFFFFFFu, q.topstep, ol);
+            w.bottom = __shfl_sync(0xFFFFFFFFu, q.bottom, ol); w.bottomstep = __shfl_sync(0xFFFFFFFFu, q.bottomstep, ol);
+            if (t >= total) continue;
+            const uint32_t sg = t - o_first;                                // segment index inside its span
+            const uint32_t c0 = sg * SPAN_SEG, c1 = min(o_nch, c0 + SPAN_SEG);   // chunks [c0, c1) of the span
+            int b = ((o_x1 - vp.vx) >> 5) + (int)c0;
+            int x = c0 == 0 ? o_x1 : vp.vx + (b << 5);                      // first column of the segment
+            const uint32_t steps = (uint32_t)(x - o_x1);
+            w.top = radd(w.top, w.topstep, steps);
+            w.bottom = radd(w.bottom, w.bottomstep, steps);
+            int32_t *heads = pl.bin_head + (size_t)(o_y - vp.vy) * vp.nbx;
+            // the atomicExch that links a chunk into its bin has ~1 us latency: issue it, replay the
+            // interpolator across the bin while it is in flight, and only then write the chunk record
+            uint32_t cid = o_cbase + c0;
+            float ctop = w.top, cbot = w.bottom;
+            int32_t cnext = atomicExch(&heads[b], (int32_t)cid);
+            for (uint32_t c = c0;;) {
+                const bool last = c + 1 >= c1;
+                if (!last) {
+                    const int xn = vp.vx + ((b + 1) << 5);                  // first column of the next bin (< x2)
+                    for (; x < xn; x++) interp_step(w);
+                }
+                Chunk ch;
+                ch.top = ctop; ch.bottom = cbot; ch.span = r0 + (uint32_t)og; ch.next = cnext;
+                pl.chunks[cid] = ch;
+                if (last) break;
+                c++; b++; cid++;
+                ctop = w.top; cbot = w.bottom;
+                cnext = atomicExch(&heads[b], (int32_t)cid);
+            }
         }
     }
 }

@@ -3,7 +3,7 @@
 // swegl's rasteriser is built on serial fp32 recurrences (side.x += ratio, renderer.cpp:553-554;
 // topalpha += topstep / bottomalpha += bottomstep, interpolator.hpp:96-100).  x_k != x_0 + k*ratio in
 // floating point, so pixel-identical coverage needs the SAME additions -- but not one at a time:
-// radd() jumps k steps in O(#binades crossed), which turns every scanline and every chunk into an
+// radd() jumps k steps in O(#binades crossed), which turns every scanline and every span segment into an
 // independent work item.  Compiles as C (tests/radd_bruteforce.c checks it against the k-step loop on
 // millions of adversarial inputs) and as CUDA device code.
 #pragma once
@@ -14,6 +14,8 @@
 #define RADD_ADD(a, b) __fadd_rn(a, b)
 #define RADD_BITS(f) __float_as_uint(f)
 #define RADD_FLOAT(u) __uint_as_float(u)
+static __device__ __forceinline__ float radd_rcp_approx_(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#define RADD_RCP(x) radd_rcp_approx_(x)     // MUFU.RCP, <= 1 ulp: covered by the 2^-19 safety factor below
 #else
 #define RADD_FN static inline
 static inline float radd_add_(float a, float b) { volatile float r = a + b; return r; }
@@ -22,6 +24,7 @@ static inline float radd_float_(uint32_t u) { float f; memcpy(&f, &u, 4); return
 #define RADD_ADD(a, b) radd_add_(a, b)
 #define RADD_BITS(f) radd_bits_(f)
 #define RADD_FLOAT(u) radd_float_(u)
+#define RADD_RCP(x) (1.0f / (x))
 #endif
 
 // Within one binade (fixed sign and exponent) the grid spacing u is constant, so RN(s + c) moves the
@@ -31,6 +34,15 @@ static inline float radd_float_(uint32_t u) { float f; memcpy(&f, &u, 4); return
 // D = |r3 - r2| off the bit patterns, jump as many steps as keep the mantissa strictly inside the binade
 // (so every skipped step's exact sum stayed in the binade too), and fall back to real additions to cross
 // the boundary.  A step that does not change the value is a fixed point and ends the recurrence.
+// a lower bound of floor(num / den) for num, den < 2^24 that is never more than ~num/den * 2^-19 + 1 short:
+// one float multiply by a reciprocal instead of a ~100-cycle integer division.  Jumping fewer steps than
+// allowed is always safe (the loop just takes real steps / another jump for the rest).
+RADD_FN uint32_t radd_div_floor_lb(uint32_t num, uint32_t den)
+{
+    const float q = (float)num * RADD_RCP((float)den) * 0.99999809265136719f;   // * (1 - 2^-19)
+    return (uint32_t)q;
+}
+
 RADD_FN float radd(float s, float c, uint32_t k)
 {
     while (k) {
@@ -47,15 +59,15 @@ RADD_FN float radd(float s, float c, uint32_t k)
             uint32_t m3 = b3 & 0x7FFFFFu;
             if (b3 > b2) {                                  // magnitude grows
                 uint32_t D = b3 - b2;
-                if (b2 - b1 > 0 && b2 > b1) {
-                    uint32_t n = (0x7FFFFFu - m3) / D;
+                if (b2 > b1) {
+                    uint32_t n = radd_div_floor_lb(0x7FFFFFu - m3, D);
                     if (n > k) n = k;
                     b3 += n * D; k -= n;
                 }
             } else {                                        // magnitude shrinks
                 uint32_t D = b2 - b3;
                 if (b1 > b2 && m3 >= 1) {
-                    uint32_t n = (m3 - 1) / D;
+                    uint32_t n = radd_div_floor_lb(m3 - 1, D);
                     if (n > k) n = k;
                     b3 -= n * D; k -= n;
                 }
