@@ -90,7 +90,7 @@ void swegl_b200_destroy(swegl_b200_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     void *ptrs[] = { ctx->d_pos, ctx->d_nrm, ctx->d_uv, ctx->d_vert_node, ctx->d_texels, ctx->d_tris, ctx->d_prims,
                      ctx->d_node_world, ctx->d_node_normal, ctx->d_v_world, ctx->d_v_ndc, ctx->d_n_world, ctx->d_yes,
-                     ctx->d_lights, ctx->pools.edges, ctx->pools.shades, ctx->pools.spans, ctx->pools.row_slot,
+                     ctx->d_lights, ctx->pools.edges, ctx->pools.shades, ctx->pools.spans, ctx->pools.span_shades, ctx->pools.frag_tb, ctx->pools.row_slot,
                      ctx->pools.chunks, ctx->pools.bin_head, ctx->pools.counters, ctx->d_screen, ctx->d_depth,
                      ctx->d_tmp_color };
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -136,10 +136,15 @@ int swegl_b200_set_timing(swegl_b200_ctx *ctx, int enabled)
     return SWEGL_B200_OK;
 }
 
-static int ensure_pools(swegl_b200_ctx *ctx, uint32_t rows_cap, uint32_t chunks_cap)
+static int ensure_pools(swegl_b200_ctx *ctx, uint32_t rows_cap, uint32_t chunks_cap, uint32_t frags_cap)
 {
+    if (frags_cap > ctx->pools.frags_cap) {
+        CK(dalloc(ctx->pools.frag_tb, (size_t)frags_cap));
+        ctx->pools.frags_cap = frags_cap;
+    }
     if (rows_cap > ctx->pools.rows_cap) {
         CK(dalloc(ctx->pools.spans, (size_t)rows_cap));
+        CK(dalloc(ctx->pools.span_shades, (size_t)rows_cap));
         CK(dalloc(ctx->pools.row_slot, (size_t)rows_cap));
         ctx->pools.rows_cap = rows_cap;
     }
@@ -245,7 +250,7 @@ int swegl_b200_upload_scene(swegl_b200_ctx *ctx, const swegl_b200_scene_desc *sc
     ctx->slots_cap = 2 * nt;
     CK(dalloc(ctx->pools.edges, (size_t)ctx->slots_cap)); CK(dalloc(ctx->pools.shades, (size_t)ctx->slots_cap));
     uint32_t rows0 = nt * 8u < (1u << 20) ? (1u << 20) : nt * 8u;
-    int rc = ensure_pools(ctx, rows0, rows0 * 2);
+    int rc = ensure_pools(ctx, rows0, rows0 * 2, 1u << 24);
     if (rc) return rc;
 
     DeviceScene &ds = ctx->ds;
@@ -420,10 +425,13 @@ static int render_common(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v,
         const Counters c = *ctx->h_counters;
         if (++grows > 8) return fail(ctx, SWEGL_B200_ERR_CAPACITY, "span/chunk pools keep overflowing");
         uint64_t want_rows = (uint64_t)c.n_rows + c.n_rows / 4 + 1024, want_chunks = (uint64_t)c.n_chunks + c.n_chunks / 4 + 1024;
+        uint64_t want_frags = (uint64_t)c.n_frags + c.n_frags / 4 + 1024;
         if (c.overflow & 1u) want_chunks = want_chunks > 2 * want_rows ? want_chunks : 2 * want_rows;
-        if (want_rows > 0xFFFFFFF0ull || want_chunks > 0x7FFFFFF0ull) return fail(ctx, SWEGL_B200_ERR_CAPACITY, "frame needs more than 2^31 chunks");
+        if (c.overflow & 3u) want_frags = want_frags > 2 * (uint64_t)ctx->pools.frags_cap ? want_frags : 2 * (uint64_t)ctx->pools.frags_cap;
+        if (want_rows > 0xFFFFFFF0ull || want_chunks > 0x7FFFFFF0ull || want_frags > 0xFFFFFFF0ull)
+            return fail(ctx, SWEGL_B200_ERR_CAPACITY, "frame needs more than 2^32 fragments / 2^31 chunks");
         CK(cudaMemsetAsync(ctx->pools.bin_head, 0xFF, ctx->bins_cap * 4, ctx->stream));
-        rc = ensure_pools(ctx, (uint32_t)want_rows, (uint32_t)want_chunks);
+        rc = ensure_pools(ctx, (uint32_t)want_rows, (uint32_t)want_chunks, (uint32_t)want_frags);
         if (rc) return rc;
     }
     if (rc == SWEGL_B200_OK) { ctx->last_vp = vp; ctx->have_vp = true; if (stats) stats->pool_grows = grows; }

@@ -2,8 +2,8 @@
 // shaders (swegl/render/pixel_shaders.hpp, src/render/pixel_shaders.cpp), plus the DoF-R post pass.
 //
 // k_fragments: one warp owns one 32-pixel, 1-row bin of the viewport; lane = pixel.  The warp walks the
-// bin's chunk list, each lane replays the span interpolator from the chunk checkpoint to its own
-// column (<=31 fp32 add pairs, the same additions the CPU does), and keeps the nearest fragment
+// bin's chunk list, each lane reads its pixel's interpolator progress from the fragment stream k_spans
+// wrote (the same fp32 additions and division the CPU does), and keeps the nearest fragment
 // in registers: key = depth bits << 32 | slot id, so equal depths resolve to the earlier draw,
 // exactly like the serial `if (z >= *zb) continue;` (renderer.cpp:491).  Only the winner is shaded
 // (deferred), and the bin is written once as a 128-byte colour segment and a 128-byte depth
@@ -33,25 +33,11 @@ SB_DEV int wrap_index(int a, int n, int mask)
 }
 
 template <int TEX>
-SB_DEV uint32_t shade_texture(const SlotShade *sh, const Prim &pr, const uint32_t *texels,
-                              bool lower, bool lor, float pl, float pr_, float u)
+SB_DEV uint32_t shade_texture(const SpanShade *ss, const Prim &pr, const uint32_t *texels, float u)
 {
     if (TEX == SWEGL_B200_TEX_PLAIN) return pr.color;                       // pixel_shaders.hpp:28
-    // long side: t0 + (t2-t0)*p ; short side: upper t0 + (t1-t0)*p, lower t1 + (t2-t1)*p
-    float t0x = sh->t0[0], t0y = sh->t0[1], t1x = sh->t1[0], t1y = sh->t1[1], t2x = sh->t2[0], t2y = sh->t2[1];
-    float ldx = fsub(t2x, t0x), ldy = fsub(t2y, t0y);                       // side_long_t_dir
-    float sbx = lower ? t1x : t0x, sby = lower ? t1y : t0y;                 // side_short_t
-    float sdx = lower ? fsub(t2x, t1x) : fsub(t1x, t0x);                    // side_short_t_dir
-    float sdy = lower ? fsub(t2y, t1y) : fsub(t1y, t0y);
-    float tlx, tly, tdx, tdy;                                               // pixel_shaders.cpp:334-346
-    if (lor) {
-        tlx = fadd(sbx, fmul(sdx, pl)); tly = fadd(sby, fmul(sdy, pl));
-        tdx = fsub(fadd(t0x, fmul(ldx, pr_)), tlx); tdy = fsub(fadd(t0y, fmul(ldy, pr_)), tly);
-    } else {
-        tlx = fadd(t0x, fmul(ldx, pl)); tly = fadd(t0y, fmul(ldy, pl));
-        tdx = fsub(fadd(sbx, fmul(sdx, pr_)), tlx); tdy = fsub(fadd(sby, fmul(sdy, pr_)), tly);
-    }
-    float tx = fadd(tlx, fmul(tdx, u)), ty = fadd(tly, fmul(tdy, u));
+    // t = t_left + t_dir * progress   (pixel_shaders.cpp:277, 352)
+    float tx = fadd(ss->t_left[0], fmul(ss->t_dir[0], u)), ty = fadd(ss->t_left[1], fmul(ss->t_dir[1], u));
     const uint32_t *bm = texels + pr.tex_off;
     if (TEX == SWEGL_B200_TEX_NEAREST) {
         // pixel_shader_texture::shade, pixel_shaders.cpp:275-281 (unsigned modulo)
@@ -88,24 +74,11 @@ SB_DEV uint32_t shade_texture(const SlotShade *sh, const Prim &pr, const uint32_
 }
 
 template <int LIGHT>
-SB_DEV int shade_light(const SlotShade *sh, const ViewParams &vp, const FrameParams &fp,
-                       bool lower, bool lor, float pl, float pr_, float u)
+SB_DEV int shade_light(const SpanShade *ss, float flat_light, const ViewParams &vp, const FrameParams &fp, float u)
 {
-    if (LIGHT == SWEGL_B200_LIGHT_FLAT) return f2i(sh->flat_light);         // pixel_shaders.hpp:36-39
-    // pixel_shader_lights_phong: prepare_for_{upper,lower}_triangle (pixel_shaders.cpp:106-151),
-    // prepare_for_scanline (:152-158), shade (:159-205)
-    V3 w0 = ld3(sh->w0), w1 = ld3(sh->w1), w2 = ld3(sh->w2);
-    V3 n0 = ld3(sh->n0), n1 = ld3(sh->n1), n2 = ld3(sh->n2);
-    V3 lgb = w0, lgd = sub(w2, w0);                                         // long side
-    V3 shb = lower ? w1 : w0, shd = lower ? sub(w2, w1) : sub(w1, w0);      // short side
-    V3 nlgb = n0, nlgd = sub(n2, n0);
-    V3 nshb = lower ? n1 : n0, nshd = lower ? sub(n2, n1) : sub(n1, n0);
-    V3 vl = lor ? shb : lgb, vld = lor ? shd : lgd, vr = lor ? lgb : shb, vrd = lor ? lgd : shd;
-    V3 nl = lor ? nshb : nlgb, nld = lor ? nshd : nlgd, nr = lor ? nlgb : nshb, nrd = lor ? nlgd : nshd;
-    V3 v = add(vl, mul(vld, pl));
-    V3 vdir = sub(add(vr, mul(vrd, pr_)), v);
-    V3 n = add(nl, mul(nld, pl));
-    V3 ndir = sub(add(nr, mul(nrd, pr_)), n);
+    if (LIGHT == SWEGL_B200_LIGHT_FLAT) return f2i(flat_light);             // pixel_shaders.hpp:36-39
+    // pixel_shader_lights_phong::shade (pixel_shaders.cpp:159-205) on the span constants of prepare_for_scanline
+    const V3 v = ld3(ss->v), vdir = ld3(ss->vdir), n = ld3(ss->n), ndir = ld3(ss->ndir);
 
     V3 center = add(v, mul(vdir, u));
     V3 normal = normalize(add(n, mul(ndir, u)));
@@ -117,13 +90,13 @@ SB_DEV int shade_light(const SlotShade *sh, const ViewParams &vp, const FramePar
 }
 
 template <int LIGHT, int TEX>
-SB_DEV uint32_t shade(const SlotShade *sh, const Prim &pr, const uint32_t *texels, const ViewParams &vp,
-                      const FrameParams &fp, bool lower, bool lor, float pl, float pr_, float u)
+SB_DEV uint32_t shade(const SpanShade *ss, float flat_light, const Prim &pr, const uint32_t *texels, const ViewParams &vp,
+                      const FrameParams &fp, float u)
 {
-    uint32_t c = shade_texture<TEX>(sh, pr, texels, lower, lor, pl, pr_, u);
+    uint32_t c = shade_texture<TEX>(ss, pr, texels, u);
     if (LIGHT == SWEGL_B200_LIGHT_NONE) return c;
     // pixel_shader_light_and_texture::shade, pixel_shaders.hpp:159-178
-    int li = shade_light<LIGHT>(sh, vp, fp, lower, lor, pl, pr_, u);
+    int li = shade_light<LIGHT>(ss, flat_light, vp, fp, u);
     float light = fmul(__int2float_rn(li), 1.0f / 65536.0f);               // (float)(li / 65536.0)
     uint32_t b = c & 0xFF, g = (c >> 8) & 0xFF, r = (c >> 16) & 0xFF;
     if (light < 1.0f) {
@@ -203,24 +176,14 @@ __global__ void __launch_bounds__(FRAG_TPB) k_fragments(DeviceScene s, const __g
             const Chunk ch = pl.chunks[c];
             const Span sp = spans[ch.span];
             const int x1 = (int)(sp.x1x2 & 0xFFFFu), x2 = (int)(sp.x1x2 >> 16);
-            const int xs = max(x1, binx0), xe = min(x2, binx0 + 32);
-            const int k = x - xs, n = xe - xs;
-            float top = ch.top, bot = ch.bottom;
-            // qpixel.Step() x (x - xs): the same fp32 additions the CPU performs, in the same order
-            int j = 0;
-            for (; j + 4 <= n - 1; j += 4) {
-                if (j + 0 < k) { top = fadd(top, sp.topstep); bot = fadd(bot, sp.bottomstep); }
-                if (j + 1 < k) { top = fadd(top, sp.topstep); bot = fadd(bot, sp.bottomstep); }
-                if (j + 2 < k) { top = fadd(top, sp.topstep); bot = fadd(bot, sp.bottomstep); }
-                if (j + 3 < k) { top = fadd(top, sp.topstep); bot = fadd(bot, sp.bottomstep); }
-            }
-            for (; j < n - 1; j++)
-                if (j < k) { top = fadd(top, sp.topstep); bot = fadd(bot, sp.bottomstep); }
-            const float u = fdiv(top, bot);                                 // interpolator.hpp:98
-            const float z = fadd(sp.v0, fmul(sp.v1, u));                    // value(0)
-            if (k >= 0 && k < n && z >= NEAR_Z) {                           // renderer.cpp:488-492
-                uint64_t key = ((uint64_t)__float_as_uint(z) << 32) | (sp.slot_flags >> 2);
-                if (key < best) { best = key; best_u = u; best_span = ch.span; }
+            if (x >= x1 && x < x2) {
+                const float2 tb = pl.frag_tb[sp.frag_base + (uint32_t)(x - x1)];   // qpixel state, replayed by k_spans
+                const float u = fdiv(tb.x, tb.y);                               // progress(), interpolator.hpp:98
+                const float z = fadd(sp.v0, fmul(sp.v1, u));                    // value(0), renderer.cpp:488
+                if (z >= NEAR_Z) {                                              // renderer.cpp:489-492
+                    uint64_t key = ((uint64_t)__float_as_uint(z) << 32) | (sp.slot_flags >> 2);
+                    if (key < best) { best = key; best_u = u; best_span = ch.span; }
+                }
             }
             c = ch.next;
         }
@@ -229,12 +192,10 @@ __global__ void __launch_bounds__(FRAG_TPB) k_fragments(DeviceScene s, const __g
         const bool hit = best != KEY_INIT;
         uint32_t out = 0;                                                   // background, viewport.cpp:95-103
         if (hit) {
-            const Span sp = spans[best_span];
-            const uint32_t slot = sp.slot_flags >> 2;
-            const bool lower = (sp.slot_flags >> 1) & 1u, lor = sp.slot_flags & 1u;
+            const uint32_t slot = spans[best_span].slot_flags >> 2;
             const SlotShade *sh = &pl.shades[slot];
             const Prim pr = s.prims[sh->prim];
-            out = shade<LIGHT, TEX>(sh, pr, s.texels, vp, fp, lower, lor, sp.pl, sp.pr, best_u);
+            out = shade<LIGHT, TEX>(&pl.span_shades[best_span], sh->flat_light, pr, s.texels, vp, fp, best_u);
         }
         if (inside) {
             crow[(b << 5) + lane] = out;

@@ -14,7 +14,7 @@
 namespace sb {
 
 static constexpr int TPB = 256;
-static constexpr uint32_t SPAN_SEG = 8;      // 32-column bins per span segment (one lane walks one segment)
+static constexpr uint32_t SPAN_SEG = 4;      // 32-column bins per span segment (one lane walks one segment)
 
 // ----------------------------------------------------------------------------------------
 // vertex stage
@@ -294,132 +294,181 @@ __global__ void __launch_bounds__(128) k_setup(DeviceScene s, const __grid_const
 // interpolator (renderer.cpp:469-480), replays it along x and drops a checkpoint ("chunk") at every
 // 32-column bin the span crosses.
 // ----------------------------------------------------------------------------------------
+SB_DEV uint32_t warp_incl_scan(uint32_t v, int lane)
+{
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= d) v += t; }
+    return v;
+}
+
+// shared state of one CTA pass over 32 scanline records
+struct SpanCta {
+    float val[6][32];                   // phase A: long x/top/bottom, short x/top/bottom on each scanline
+    int x1[32], x2[32], y[32];          // phase B: the spans ...
+    float top[32], topstep[32], bottom[32], bottomstep[32];   // ... their qpixel at x1 ...
+    uint32_t nchunks[32], cbase[32], fbase[32], seg_incl[32]; // ... and their allocations / segment prefix
+};
+
 __global__ void __launch_bounds__(TPB) k_spans(const __grid_constant__ ViewParams vp, Pools pl)
 {
+    __shared__ SpanCta sh;
     if (pl.counters->overflow & 1u) return;      // some rows were never allocated: the host grows the pool and redoes the frame
     const uint32_t n_rows = min(pl.counters->n_rows, pl.rows_cap);
-    const int lane = threadIdx.x & 31;
-    const int grp = lane >> 3, rec = lane & 7;   // 4 scanlines per warp, 8 lanes each; lane `rec` < 6 owns one recurrence
-    const int lead = grp << 3;                   // the group's leader lane
-    const uint32_t warp_id = (blockIdx.x * TPB + threadIdx.x) >> 5, n_warps = (gridDim.x * TPB) >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     Span *spans = pl.spans;
-    for (uint32_t r0 = warp_id * 4; r0 < n_rows; r0 += n_warps * 4) {       // warp-uniform
-        const uint32_t i = r0 + grp;
-        const bool valid = i < n_rows;
-        // ---- 6 lanes per scanline: each advances one of the edge recurrences to this scanline with radd() ----
-        uint32_t slot = 0; int y = 0; bool lower = false, lor = false;
-        float val = 0.f, z0 = 0.f, z1 = 0.f, z2 = 0.f;
-        if (valid) {
-            slot = pl.row_slot[i];
-            const SlotEdge &e = pl.edges[slot];
-            const int j = (int)i - e.span_base;
-            // in-band scanlines of the upper half come first, then the lower half's
-            const int ua = max(e.ya_u, vp.band0), ub = min(e.yb_u, vp.band1);
-            const int nu = max(0, ub - ua);
-            lower = j >= nu;
-            y = lower ? max(e.ya_l, vp.band0) + (j - nu) : ua + j;
-            lor = lower ? ((e.flags >> 1) & 1u) : (e.flags & 1u);
-            if (rec < 6) {
-                // rec 0..2: long side x / topalpha / bottomalpha; rec 3..5: the half's short side
-                const SideRec &S = rec < 3 ? e.lng : (lower ? e.sl : e.su);
-                const uint32_t k = rec < 3 ? (uint32_t)(y - e.y_long) : (uint32_t)(y - (lower ? e.ya_l : e.ya_u));
-                const int f = rec % 3;
+    for (uint32_t i0 = blockIdx.x * 32; i0 < n_rows; i0 += gridDim.x * 32) {                    // CTA-uniform
+        const uint32_t i = i0 + lane;
+        // ---- phase A: warp r < 6 advances recurrence r of the 32 scanlines to their row with radd()
+        //      (renderer.cpp:553-556 applied (y - first walked row) times); same cost profile across a warp ----
+        if (warp < 6) {
+            float val = 0.f;
+            if (i < n_rows) {
+                const uint32_t slot = pl.row_slot[i];
+                const SlotEdge &e = pl.edges[slot];
+                const int j = (int)i - e.span_base;
+                const int ua = max(e.ya_u, vp.band0), ub = min(e.yb_u, vp.band1);
+                const int nu = max(0, ub - ua);
+                const bool lower = j >= nu;                                 // in-band rows of the upper half come first
+                const int y = lower ? max(e.ya_l, vp.band0) + (j - nu) : ua + j;
+                const SideRec &S = warp < 3 ? e.lng : (lower ? e.sl : e.su);
+                const uint32_t k = warp < 3 ? (uint32_t)(y - e.y_long) : (uint32_t)(y - (lower ? e.ya_l : e.ya_u));
+                const int f = warp % 3;
                 const float start = f == 0 ? S.x : (f == 1 ? S.top : S.bottom);
                 const float step = f == 0 ? S.ratio : (f == 1 ? S.topstep : S.bottomstep);
-                val = radd(start, step, k);                                 // renderer.cpp:553-556, k times
+                val = radd(start, step, k);
             }
-            if (rec == 0) { z0 = e.z0; z1 = e.z1; z2 = e.z2; }
+            sh.val[warp][lane] = val;
         }
-        const float gx = __shfl_sync(0xFFFFFFFFu, val, lead + 0), gtop = __shfl_sync(0xFFFFFFFFu, val, lead + 1);
-        const float gbot = __shfl_sync(0xFFFFFFFFu, val, lead + 2), sx = __shfl_sync(0xFFFFFFFFu, val, lead + 3);
-        const float stop = __shfl_sync(0xFFFFFFFFu, val, lead + 4), sbot = __shfl_sync(0xFFFFFFFFu, val, lead + 5);
+        __syncthreads();
+        // ---- phase B: warp 0, lane = scanline: the span (renderer.cpp:469-480), its shading constants, and one
+        //      chunk / fragment-stream allocation for the whole group ----
+        if (warp == 0) {
+            uint32_t nchunks = 0, npix = 0;
+            int x1 = 0, x2 = 0, y = 0;
+            Interp q; q.top = q.topstep = q.bottom = q.bottomstep = q.v0 = q.v1 = 0.f;
+            Span sp; sp.frag_base = 0; sp.pad0 = 0; sp.v0 = sp.v1 = sp.pl = sp.pr = 0.f; sp.x1x2 = 0; sp.slot_flags = 0;
+            if (i < n_rows) {
+                const uint32_t slot = pl.row_slot[i];
+                const SlotEdge &e = pl.edges[slot];
+                const int j = (int)i - e.span_base;
+                const int ua = max(e.ya_u, vp.band0), ub = min(e.yb_u, vp.band1);
+                const int nu = max(0, ub - ua);
+                const bool lower = j >= nu;
+                y = lower ? max(e.ya_l, vp.band0) + (j - nu) : ua + j;
+                const bool lor = lower ? ((e.flags >> 1) & 1u) : (e.flags & 1u);
+                const float gx = sh.val[0][lane], gtop = sh.val[1][lane], gbot = sh.val[2][lane];
+                const float sx = sh.val[3][lane], stop = sh.val[4][lane], sbot = sh.val[5][lane];
+                const float lx = lor ? sx : gx, rx = lor ? gx : sx;
+                const float ltop = lor ? stop : gtop, lbot = lor ? sbot : gbot, rtop = lor ? gtop : stop, rbot = lor ? gbot : sbot;
 
-        // ---- leader lane: the scanline's span (renderer.cpp:469-480) ----
-        uint32_t nchunks = 0;
-        int x1 = 0, x2 = 0;
-        Interp q; q.top = q.topstep = q.bottom = q.bottomstep = q.v0 = q.v1 = 0.f;
-        Span sp;
-        if (valid && rec == 0) {
-            const float lx = lor ? sx : gx, rx = lor ? gx : sx;
-            const float ltop = lor ? stop : gtop, lbot = lor ? sbot : gbot, rtop = lor ? gtop : stop, rbot = lor ? gbot : sbot;
-            sp.slot_flags = (slot << 2) | ((uint32_t)lower << 1) | (lor ? 1u : 0u);
-            x1 = max(ceil_i(lx), vp.vx);
-            x2 = min(ceil_i(rx), vp.vx + vp.vw);
-            if (x1 < x2) {
-                // edge interpolators' v[0]: long (z0, z2-z0); short (z0, z1-z0) upper / (z1, z2-z1) lower
-                const float la = lor ? (lower ? z1 : z0) : z0;
-                const float lb = lor ? (lower ? z2 : z1) : z2;
-                const float ra = lor ? z0 : (lower ? z1 : z0);
-                const float rb = lor ? z2 : (lower ? z2 : z1);
-                sp.pl = fdiv(ltop, lbot);                                   // interpolator progress()
-                sp.pr = fdiv(rtop, rbot);
-                const float zl = fadd(la, fmul(fsub(lb, la), sp.pl));       // value(0), interpolator.hpp:103
-                const float zr = fadd(ra, fmul(fsub(rb, ra), sp.pr));
-                interp_init_self(q, fsub(rx, lx), zl, zr);
-                interp_displace(q, fsub((float)x1, lx));
-                sp.topstep = q.topstep; sp.bottomstep = q.bottomstep; sp.v0 = q.v0; sp.v1 = q.v1;
-                sp.x1x2 = (uint32_t)x1 | ((uint32_t)x2 << 16);
-                nchunks = (uint32_t)(((x2 - 1 - vp.vx) >> 5) - ((x1 - vp.vx) >> 5) + 1);
-            } else {
-                sp.topstep = sp.bottomstep = sp.v0 = sp.v1 = sp.pl = sp.pr = 0.f; sp.x1x2 = 0;
+                sp.slot_flags = (slot << 2) | ((uint32_t)lower << 1) | (lor ? 1u : 0u);
+                x1 = max(ceil_i(lx), vp.vx);
+                x2 = min(ceil_i(rx), vp.vx + vp.vw);
+                if (x1 < x2) {
+                    const float z0 = e.z0, z1 = e.z1, z2 = e.z2;
+                    // edge interpolators' v[0]: long (z0, z2-z0); short (z0, z1-z0) upper / (z1, z2-z1) lower
+                    const float la = lor ? (lower ? z1 : z0) : z0;
+                    const float lb = lor ? (lower ? z2 : z1) : z2;
+                    const float ra = lor ? z0 : (lower ? z1 : z0);
+                    const float rb = lor ? z2 : (lower ? z2 : z1);
+                    sp.pl = fdiv(ltop, lbot);                               // interpolator progress()
+                    sp.pr = fdiv(rtop, rbot);
+                    const float zl = fadd(la, fmul(fsub(lb, la), sp.pl));   // value(0), interpolator.hpp:103
+                    const float zr = fadd(ra, fmul(fsub(rb, ra), sp.pr));
+                    interp_init_self(q, fsub(rx, lx), zl, zr);
+                    interp_displace(q, fsub((float)x1, lx));
+                    sp.v0 = q.v0; sp.v1 = q.v1;
+                    sp.x1x2 = (uint32_t)x1 | ((uint32_t)x2 << 16);
+                    nchunks = (uint32_t)(((x2 - 1 - vp.vx) >> 5) - ((x1 - vp.vx) >> 5) + 1);
+                    npix = (uint32_t)(x2 - x1);
+                    // prepare_for_{upper,lower}_triangle + prepare_for_scanline of the pixel shaders
+                    // (pixel_shaders.cpp:106-158, 320-346), once per span instead of once per pixel.
+                    // long side: base v0, dir v2-v0; short side: upper (v0, v1-v0) / lower (v1, v2-v1)
+                    const SlotShade &ssh = pl.shades[slot];
+                    SpanShade ss;
+                    #pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const float w0 = ssh.w0[c], w1 = ssh.w1[c], w2 = ssh.w2[c], m0 = ssh.n0[c], m1 = ssh.n1[c], m2 = ssh.n2[c];
+                        const float lgd = fsub(w2, w0), shb = lower ? w1 : w0, shd = lower ? fsub(w2, w1) : fsub(w1, w0);
+                        const float nlgd = fsub(m2, m0), nshb = lower ? m1 : m0, nshd = lower ? fsub(m2, m1) : fsub(m1, m0);
+                        const float vl = lor ? shb : w0, vld = lor ? shd : lgd, vr = lor ? w0 : shb, vrd = lor ? lgd : shd;
+                        const float nl = lor ? nshb : m0, nld = lor ? nshd : nlgd, nr = lor ? m0 : nshb, nrd = lor ? nlgd : nshd;
+                        ss.v[c] = fadd(vl, fmul(vld, sp.pl));
+                        ss.vdir[c] = fsub(fadd(vr, fmul(vrd, sp.pr)), ss.v[c]);
+                        ss.n[c] = fadd(nl, fmul(nld, sp.pl));
+                        ss.ndir[c] = fsub(fadd(nr, fmul(nrd, sp.pr)), ss.n[c]);
+                    }
+                    #pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        const float a0 = ssh.t0[c], a1 = ssh.t1[c], a2 = ssh.t2[c];
+                        const float lgd = fsub(a2, a0), shb = lower ? a1 : a0, shd = lower ? fsub(a2, a1) : fsub(a1, a0);
+                        const float tl = lor ? shb : a0, tld = lor ? shd : lgd, tr = lor ? a0 : shb, trd = lor ? lgd : shd;
+                        ss.t_left[c] = fadd(tl, fmul(tld, sp.pl));
+                        ss.t_dir[c] = fsub(fadd(tr, fmul(trd, sp.pr)), ss.t_left[c]);
+                    }
+                    pl.span_shades[i] = ss;
+                }
             }
+            const uint32_t c_incl = warp_incl_scan(nchunks, lane), p_incl = warp_incl_scan(npix, lane);
+            const uint32_t c_tot = __shfl_sync(0xFFFFFFFFu, c_incl, 31), p_tot = __shfl_sync(0xFFFFFFFFu, p_incl, 31);
+            uint32_t wbase = 0, fbase = 0;
+            if (lane == 0 && c_tot) {
+                wbase = atomicAdd(&pl.counters->n_chunks, c_tot);
+                fbase = atomicAdd(&pl.counters->n_frags, p_tot);
+            }
+            wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+            fbase = __shfl_sync(0xFFFFFFFFu, fbase, 0);
+            const bool room = wbase + c_tot <= pl.chunks_cap && fbase + p_tot <= pl.frags_cap;
+            if (!room && lane == 0)
+                atomicOr(&pl.counters->overflow, (wbase + c_tot > pl.chunks_cap ? 2u : 0u) | (fbase + p_tot > pl.frags_cap ? 4u : 0u));
+            sp.frag_base = fbase + p_incl - npix;
+            if (i < n_rows) spans[i] = sp;
+            if (!room) nchunks = 0;                                         // nothing is walked; the host redoes the frame
+            const uint32_t nseg = (nchunks + SPAN_SEG - 1) / SPAN_SEG;
+            sh.x1[lane] = x1; sh.x2[lane] = x2; sh.y[lane] = y;
+            sh.top[lane] = q.top; sh.topstep[lane] = q.topstep; sh.bottom[lane] = q.bottom; sh.bottomstep[lane] = q.bottomstep;
+            sh.nchunks[lane] = nchunks; sh.cbase[lane] = wbase + c_incl - (room ? nchunks : 0u); sh.fbase[lane] = sp.frag_base;
+            sh.seg_incl[lane] = warp_incl_scan(nseg, lane);
         }
-        // one chunk allocation per warp instead of one same-address atomic per scanline
-        const uint32_t n0 = __shfl_sync(0xFFFFFFFFu, nchunks, 0), n1 = __shfl_sync(0xFFFFFFFFu, nchunks, 8);
-        const uint32_t n2 = __shfl_sync(0xFFFFFFFFu, nchunks, 16), n3 = __shfl_sync(0xFFFFFFFFu, nchunks, 24);
-        uint32_t wbase = 0;
-        if (lane == 0 && n0 + n1 + n2 + n3) wbase = atomicAdd(&pl.counters->n_chunks, n0 + n1 + n2 + n3);
-        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-        const bool room = wbase + n0 + n1 + n2 + n3 <= pl.chunks_cap;
-        if (!room && lane == 0) atomicOr(&pl.counters->overflow, 2u);
-        if (valid && rec == 0) spans[i] = sp;
-        if (!room) continue;
-        // ---- whole warp: one lane per SEGMENT (SPAN_SEG bins = 256 pixels) of the warp's 4 spans, so a
-        //      screen-wide span is walked by several lanes.  A lane jumps to its segment's first column
-        //      with radd() (free for the first segment) and then replays qpixel.Step() pixel by pixel
-        //      (renderer.cpp:486), dropping a chunk at every 32-column bin. ----
-        const uint32_t s0 = (n0 + SPAN_SEG - 1) / SPAN_SEG, s1 = s0 + (n1 + SPAN_SEG - 1) / SPAN_SEG;
-        const uint32_t s2 = s1 + (n2 + SPAN_SEG - 1) / SPAN_SEG, total = s2 + (n3 + SPAN_SEG - 1) / SPAN_SEG;
-        for (uint32_t t0 = 0; t0 < total; t0 += 32) {
-            const uint32_t t = t0 + lane;
-            const int og = t < s0 ? 0 : (t < s1 ? 1 : (t < s2 ? 2 : 3));    // owning group
-            const int ol = og << 3;
-            const uint32_t o_first = og == 0 ? 0u : (og == 1 ? s0 : (og == 2 ? s1 : s2));
-            const uint32_t o_nch = og == 0 ? n0 : (og == 1 ? n1 : (og == 2 ? n2 : n3));
-            const uint32_t o_cbase = wbase + (og == 0 ? 0u : (og == 1 ? n0 : (og == 2 ? n0 + n1 : n0 + n1 + n2)));
-            const int o_x1 = __shfl_sync(0xFFFFFFFFu, x1, ol), o_y = __shfl_sync(0xFFFFFFFFu, y, ol);
-            Interp w;
-            w.top = __shfl_sync(0xFFFFFFFFu, q.top, ol); w.topstep = __shfl_sync(0xFFFFFFFFu, q.topstep, ol);
-            w.bottom = __shfl_sync(0xFFFFFFFFu, q.bottom, ol); w.bottomstep = __shfl_sync(0xFFFFFFFFu, q.bottomstep, ol);
-            if (t >= total) continue;
-            const uint32_t sg = t - o_first;                                // segment index inside its span
-            const uint32_t c0 = sg * SPAN_SEG, c1 = min(o_nch, c0 + SPAN_SEG);   // chunks [c0, c1) of the span
+        __syncthreads();
+        // ---- phase C: thread = SEGMENT (SPAN_SEG bins = 128 pixels) of the group's spans, so a screen-wide span
+        //      is walked by many threads.  A thread jumps to its segment's first column with radd() (free for a
+        //      span's first segment), then replays qpixel.Step() pixel by pixel (renderer.cpp:486), streaming the
+        //      interpolator state of every pixel and linking one chunk into every 32-column bin it crosses. ----
+        const uint32_t total = sh.seg_incl[31];
+        for (uint32_t t = tid; t < total; t += TPB) {
+            int owner = 0;                                                  // first row whose inclusive prefix exceeds t
+            #pragma unroll
+            for (int stp = 16; stp >= 1; stp >>= 1)
+                if (sh.seg_incl[owner + stp - 1] <= t) owner += stp;
+            const uint32_t o_nch = sh.nchunks[owner];
+            const uint32_t sg = t - (sh.seg_incl[owner] - (o_nch + SPAN_SEG - 1) / SPAN_SEG);   // segment index inside its span
+            const uint32_t c0 = sg * SPAN_SEG, c1 = min(o_nch, c0 + SPAN_SEG);                  // chunks [c0, c1) of the span
+            const int o_x1 = sh.x1[owner], o_x2 = sh.x2[owner];
             int b = ((o_x1 - vp.vx) >> 5) + (int)c0;
             int x = c0 == 0 ? o_x1 : vp.vx + (b << 5);                      // first column of the segment
             const uint32_t steps = (uint32_t)(x - o_x1);
-            w.top = radd(w.top, w.topstep, steps);
-            w.bottom = radd(w.bottom, w.bottomstep, steps);
-            int32_t *heads = pl.bin_head + (size_t)(o_y - vp.vy) * vp.nbx;
-            // the atomicExch that links a chunk into its bin has ~1 us latency: issue it, replay the
-            // interpolator across the bin while it is in flight, and only then write the chunk record
-            uint32_t cid = o_cbase + c0;
-            float ctop = w.top, cbot = w.bottom;
-            int32_t cnext = atomicExch(&heads[b], (int32_t)cid);
-            for (uint32_t c = c0;;) {
-                const bool last = c + 1 >= c1;
-                if (!last) {
-                    const int xn = vp.vx + ((b + 1) << 5);                  // first column of the next bin (< x2)
-                    for (; x < xn; x++) interp_step(w);
-                }
+            Interp w;
+            w.topstep = sh.topstep[owner]; w.bottomstep = sh.bottomstep[owner];
+            w.top = radd(sh.top[owner], w.topstep, steps);
+            w.bottom = radd(sh.bottom[owner], w.bottomstep, steps);
+            int32_t *heads = pl.bin_head + (size_t)(sh.y[owner] - vp.vy) * vp.nbx;
+            float2 *ftb = pl.frag_tb + sh.fbase[owner] - o_x1;              // ftb[x] = qpixel (topalpha, bottomalpha) at column x
+            const uint32_t span_id = i0 + (uint32_t)owner;
+            uint32_t cid = sh.cbase[owner] + c0;
+            for (uint32_t c = c0; c < c1; c++, b++, cid++) {
                 Chunk ch;
-                ch.top = ctop; ch.bottom = cbot; ch.span = r0 + (uint32_t)og; ch.next = cnext;
+                ch.span = span_id;
+                ch.next = atomicExch(&heads[b], (int32_t)cid);              // latency hidden behind the pixel loop below
+                const int xn = min(vp.vx + ((b + 1) << 5), o_x2);           // end of this bin's piece of the span
+                for (; x < xn; x++) {
+                    ftb[x] = make_float2(w.top, w.bottom);                  // k_fragments divides: ualpha, interpolator.hpp:98
+                    interp_step(w);
+                }
                 pl.chunks[cid] = ch;
-                if (last) break;
-                c++; b++; cid++;
-                ctop = w.top; cbot = w.bottom;
-                cnext = atomicExch(&heads[b], (int32_t)cid);
             }
         }
+        __syncthreads();                                                    // sh is reused by the next group
     }
 }
 
@@ -446,7 +495,7 @@ void launch_setup(const DeviceScene &s, const ViewParams &vp, const FrameParams 
 }
 void launch_spans(const ViewParams &vp, const Pools &p, cudaStream_t st)
 {
-    k_spans<<<148 * 8, TPB, 0, st>>>(vp, p);
+    k_spans<<<148 * 16, TPB, 0, st>>>(vp, p);      // persistent CTAs, 32 scanline records per pass
 }
 
 } // namespace sb
