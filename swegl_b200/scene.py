@@ -26,12 +26,23 @@ from . import _abi
 f32 = np.float32
 
 
+# matrix44_t::rotate_* call cos(a)/sin(a) on a float: C++ overload resolution picks the float versions, and
+# g++ -O3 merges them into glibc's sincosf (src/projection/matrix44.cpp:13-14).  glibc's float functions are
+# not correctly rounded (sinf(2.9f) is 1 ulp off), so the same libm entry points are called here.
+import ctypes as _C
+import ctypes.util as _Cu
+
+_libm = _C.CDLL(_Cu.find_library("m") or "libm.so.6")
+_libm.cosf.restype = _libm.sinf.restype = _C.c_float
+_libm.cosf.argtypes = _libm.sinf.argtypes = [_C.c_float]
+
+
 def _cosf(a):
-    return f32(math.cos(float(f32(a))))
+    return f32(_libm.cosf(float(f32(a))))
 
 
 def _sinf(a):
-    return f32(math.sin(float(f32(a))))
+    return f32(_libm.sinf(float(f32(a))))
 
 
 def identity44():
