@@ -19,6 +19,8 @@ from swegl_b200.scene import Scene, decode_image_bgra
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_LIB = os.path.join(HERE, "liboracle.so")
 REF_LIB = os.path.join(HERE, "_ref", "libswegl_ref.so")
+# the same driver + unmodified reference sources, with swegl::_render supplied by swegl_b200/host/renderer_b200.cpp
+DROPIN_LIB = os.path.join(HERE, "_ref", "libswegl_dropin.so")
 
 
 def build(ref=True):
@@ -92,10 +94,10 @@ _DECODE_CB = C.CFUNCTYPE(C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POI
 class Ref:
     """The unmodified reference renderer (swegl::render) behind oracle/ref_driver.cpp."""
 
-    def __init__(self):
-        if not os.path.exists(REF_LIB):
-            raise FileNotFoundError(REF_LIB)
-        L = self.lib = C.CDLL(REF_LIB)
+    def __init__(self, lib_path=REF_LIB):
+        if not os.path.exists(lib_path):
+            raise FileNotFoundError(lib_path)
+        L = self.lib = C.CDLL(lib_path)
         vp = C.c_void_p
         fp, ip, up = C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_uint)
         sig = {
