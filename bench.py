@@ -184,10 +184,10 @@ def algorithmic_bytes(scene, vp, covered):
 
 def measure_gpu(r, torch, scene, vps, screen, steps, warmup, flush):
     """-> (seconds for `steps` frames measured with per-frame CUDA events, stats of the last frame)"""
-    for _ in range(warmup):
+    for w in range(warmup):
         r.begin_frame(scene)
         for vp in vps:
-            r.render_device(vp, stats=False)
+            r.render_device(vp, stats=(w == 0))        # the first frame sizes the span/chunk/fragment pools
     torch.cuda.synchronize()
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
@@ -200,6 +200,7 @@ def measure_gpu(r, torch, scene, vps, screen, steps, warmup, flush):
         for d in descs:
             r.render_device(d, stats=False)
         ev1[i].record()
+    r.synchronize()                                     # raises if any timed frame overflowed a pool (incomplete work)
     torch.cuda.synchronize()
     ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
     return sum(ms) / 1e3, ms
@@ -270,6 +271,61 @@ def gpu_workload(r, torch, name, steps, warmup, flush, world, dist, do_e2e=True)
     return out
 
 
+class _DevArray:
+    """torch.as_tensor() view of a raw device pointer (the context's screen buffer) for the NCCL gather"""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
+
+
+def sharded_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
+    """sort-first: ONE frame split in row bands over the ranks (scene replicated), bands gathered to rank 0 with
+    NCCL over NVLink.  Strong scaling of a single frame; returns ms per frame (max over ranks)."""
+    from swegl_b200 import configs, sharding
+    scene, vps, screen, cfg = configs.build(name)
+    vp = vps[0]
+    r.upload_scene(scene)
+    r.set_screen(*screen)
+    y0, y1 = sharding.band_rows(vp.h, world, rank)
+    vp.band = (y0, y1) if world > 1 else (0, 0)
+    desc = vp.desc()
+    nodes = scene.node_matrices()
+    screen_ptr, _ = r.device_buffers()
+    full = torch.as_tensor(_DevArray(screen_ptr, (screen[1], screen[0])), device="cuda")
+
+    def one():
+        r.begin_frame(scene, nodes)
+        r.render_device(desc, stats=False)
+        if world > 1:
+            return sharding.gather_bands(full[vp.y + y0: vp.y + y1, vp.x: vp.x + vp.w], vp.h, vp.w, dist, dst=0)
+        return full
+    r.begin_frame(scene, nodes)
+    r.render_device(desc, stats=True)                   # sizes the pools for this workload
+    for _ in range(max(warmup, 3)):
+        one()
+    r.synchronize()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = []
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        one()
+        e1.record()
+        r.synchronize()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    t = torch.tensor([sum(ms) / len(ms)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    st = r.render_device(desc, stats=True)
+    return {"workload": name, "description": cfg["desc"], "ms_per_frame": float(t.item()), "fps": 1e3 / float(t.item()),
+            "n_gpus": world, "partition": "contiguous row bands of the full viewport + NCCL gather to rank 0" if world > 1 else "single GPU",
+            "rank0_band_covered_pixels": int(st.n_covered), "scaling": "strong"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -279,6 +335,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true")
+    ap.add_argument("--sharded", default="sphere1000_8k", help="workload of the band-sharded single-frame measurement ('' = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -297,7 +354,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from swegl_b200 import Renderer
-    r = Renderer(local_rank, stream=torch.cuda.current_stream().cuda_stream)
+    # an explicit stream: torch's default stream is the legacy stream (handle 0), which the ABI reads as "use the
+    # context's own stream" -- events recorded by torch would then not bracket the kernels
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    r = Renderer(local_rank, stream=stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     sampler = ClockSampler(local_rank)
@@ -319,6 +381,10 @@ def main():
         also = {"workload": ALSO_WORKLOAD, "description": a["cfg"]["desc"], "fps": args.steps / a["secs"],
                 "e2e_fps": args.steps / a["e2e_secs"], "shaded_mpix_per_s": al.n_covered * args.steps / a["secs"] / 1e6,
                 "ms_per_stage": ak}
+
+    sharded = None
+    if args.sharded and not args.no_also:
+        sharded = sharded_frame(r, torch, dist, args.sharded, min(args.steps, 10), args.warmup, flush, world, rank)
 
     if rank != 0:
         if world > 1:
@@ -372,6 +438,8 @@ def main():
             "ms_per_stage": kern, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
     if also:
         line["also"] = also
+    if sharded:
+        line["sharded_frame"] = sharded
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

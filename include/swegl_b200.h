@@ -146,7 +146,9 @@ void swegl_b200_destroy(swegl_b200_ctx *ctx);
 const char *swegl_b200_last_error(const swegl_b200_ctx *ctx);
 /* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the ctx's own */
 int  swegl_b200_set_stream(swegl_b200_ctx *ctx, void *cuda_stream);
-/* block until everything queued on the context's stream has finished */
+/* block until everything queued on the context's stream has finished.  Returns SWEGL_B200_ERR_CAPACITY when
+ * the last render_viewport_device() frame ran out of internal pool space (the pools are enlarged by this call;
+ * re-issue the frame).  render_viewport() and calls with stats != NULL handle that case themselves. */
 int  swegl_b200_synchronize(swegl_b200_ctx *ctx);
 /* page-locked host memory for `pixels` / `zbuffer` (what SDL_Surface::pixels should live in for
  * full-speed read-back); plain malloc'ed memory works too, just slower */
@@ -166,7 +168,9 @@ int  swegl_b200_set_screen(swegl_b200_ctx *ctx, int32_t screen_w, int32_t screen
  * uploads node matrices + lights and computes v_world for every vertex. Once per frame. */
 int  swegl_b200_begin_frame(swegl_b200_ctx *ctx, const swegl_b200_frame_desc *frame);
 
-/* replaces swegl::_render(scene, viewport) (renderer.cpp:77-235), result left in HBM. */
+/* replaces swegl::_render(scene, viewport) (renderer.cpp:77-235), result left in HBM.  Asynchronous when
+ * stats == NULL (see swegl_b200_synchronize for the pool-overflow contract); with stats it synchronises,
+ * grows the pools if needed and redoes the frame. */
 int  swegl_b200_render_viewport_device(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *vp,
                                        swegl_b200_stats *stats);
 /* same + copies the viewport rectangle into host `pixels` (SDL_Surface::pixels, rows

@@ -26,8 +26,21 @@ struct swegl_b200_ctx {
     float *d_node_world = nullptr, *d_node_normal = nullptr;
     float *d_v_world = nullptr, *d_v_ndc = nullptr, *d_n_world = nullptr; uint8_t *d_yes = nullptr;
     float4 *d_lights = nullptr; uint32_t lights_cap = 0;
-    float *h_stage = nullptr; size_t stage_cap = 0;   // pinned staging for the per-frame uploads
-    cudaEvent_t stage_free = nullptr;                 // the previous frame's H2D copies are done
+    // per-frame / per-viewport constants in device memory, fed from double-buffered pinned staging so that a
+    // frame's launch sequence has no per-frame kernel arguments and replays as a CUDA graph
+    ViewParams *d_vp = nullptr; FrameParams *d_fp = nullptr;
+    struct Slot {
+        float *stage = nullptr;                       // node_world | node_normal | lights
+        FrameParams *fp = nullptr; ViewParams *vp = nullptr; Counters *counters = nullptr;   // pinned
+        cudaEvent_t done = nullptr; bool pending = false;       // last viewport launch that used this slot
+        cudaEvent_t bdone = nullptr; bool bpending = false;     // last begin_frame launch that used this slot
+        cudaGraphExec_t begin_exec = nullptr;
+    } slots[2];
+    size_t stage_cap = 0;                             // floats per slot
+    int begin_slot = 0, view_slot = 0;
+    struct ViewGraph { int32_t key[11]; cudaGraphExec_t exec[2]; };
+    std::vector<ViewGraph> view_graphs;
+    bool graphs_enabled = true;
     bool opaque = true;            // every material and texel has alpha 255
     FrameParams fp{};
 
@@ -35,6 +48,7 @@ struct swegl_b200_ctx {
     Pools pools{};
     uint32_t slots_cap = 0; size_t bins_cap = 0;
     Counters *h_counters = nullptr;     // pinned
+
 
     // screen
     int sw = 0, sh = 0;
@@ -49,6 +63,14 @@ struct swegl_b200_ctx {
     ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return SWEGL_B200_ERR_CUDA; } } while (0)
 
 static int fail(swegl_b200_ctx *ctx, int code, const char *msg) { if (ctx) ctx->err = msg; return code; }
+
+// every captured graph bakes in device pointers, grid sizes and the stream: drop them whenever one of those changes
+static void drop_graphs(swegl_b200_ctx *ctx)
+{
+    for (auto &g : ctx->view_graphs) for (auto &e : g.exec) if (e) cudaGraphExecDestroy(e);
+    ctx->view_graphs.clear();
+    for (auto &sl : ctx->slots) if (sl.begin_exec) { cudaGraphExecDestroy(sl.begin_exec); sl.begin_exec = nullptr; }
+}
 
 template <typename T> static cudaError_t dalloc(T *&p, size_t n)
 {
@@ -76,8 +98,17 @@ int swegl_b200_create(int device, swegl_b200_ctx **out)
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SWEGL_B200_ERR_CUDA; }
     ctx->stream = ctx->own_stream;
     for (auto &e : ctx->ev) cudaEventCreate(&e);
-    cudaEventCreateWithFlags(&ctx->stage_free, cudaEventDisableTiming);
     cudaMallocHost((void **)&ctx->h_counters, sizeof(Counters));
+    cudaMalloc((void **)&ctx->d_vp, sizeof(ViewParams));
+    cudaMalloc((void **)&ctx->d_fp, sizeof(FrameParams));
+    for (auto &sl : ctx->slots) {
+        cudaMallocHost((void **)&sl.fp, sizeof(FrameParams));
+        cudaMallocHost((void **)&sl.vp, sizeof(ViewParams));
+        cudaMallocHost((void **)&sl.counters, sizeof(Counters));
+        memset(sl.counters, 0, sizeof(Counters));
+        cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&sl.bdone, cudaEventDisableTiming);
+    }
     cudaMalloc((void **)&ctx->pools.counters, sizeof(Counters));
     *out = ctx;
     return SWEGL_B200_OK;
@@ -95,8 +126,17 @@ void swegl_b200_destroy(swegl_b200_ctx *ctx)
                      ctx->d_tmp_color };
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
-    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-    if (ctx->stage_free) cudaEventDestroy(ctx->stage_free);
+    drop_graphs(ctx);
+    if (ctx->d_vp) cudaFree(ctx->d_vp);
+    if (ctx->d_fp) cudaFree(ctx->d_fp);
+    for (auto &sl : ctx->slots) {
+        if (sl.stage) cudaFreeHost(sl.stage);
+        if (sl.fp) cudaFreeHost(sl.fp);
+        if (sl.vp) cudaFreeHost(sl.vp);
+        if (sl.counters) cudaFreeHost(sl.counters);
+        if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.bdone) cudaEventDestroy(sl.bdone);
+    }
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -107,6 +147,8 @@ const char *swegl_b200_last_error(const swegl_b200_ctx *ctx) { return ctx ? ctx-
 int swegl_b200_set_stream(swegl_b200_ctx *ctx, void *cuda_stream)
 {
     if (!ctx) return SWEGL_B200_ERR_ARG;
+    cudaStreamSynchronize(ctx->stream);
+    drop_graphs(ctx);
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return SWEGL_B200_OK;
 }
@@ -122,11 +164,28 @@ int swegl_b200_free_host(void *p)
     return cudaFreeHost(p) == cudaSuccess ? SWEGL_B200_OK : SWEGL_B200_ERR_CUDA;
 }
 
+static int grow_pools_for(swegl_b200_ctx *ctx, const Counters &c);
+
+// an asynchronous frame that ran out of pool space is incomplete: enlarge the pools so re-issuing it succeeds
+static int check_slot_overflow(swegl_b200_ctx *ctx, swegl_b200_ctx::Slot &sl)
+{
+    if (!sl.pending) return SWEGL_B200_OK;
+    sl.pending = false;
+    if (!sl.counters->overflow) return SWEGL_B200_OK;
+    Counters c = *sl.counters;
+    sl.counters->overflow = 0;
+    int rc = grow_pools_for(ctx, c);
+    if (rc) return rc;
+    return fail(ctx, SWEGL_B200_ERR_CAPACITY, "an asynchronous frame overflowed the span/chunk/fragment pools (now enlarged): render it again");
+}
+
 int swegl_b200_synchronize(swegl_b200_ctx *ctx)
 {
     if (!ctx) return SWEGL_B200_ERR_ARG;
     CK(cudaStreamSynchronize(ctx->stream));
-    return SWEGL_B200_OK;
+    int rc = SWEGL_B200_OK;
+    for (auto &sl : ctx->slots) { int r = check_slot_overflow(ctx, sl); if (r) rc = r; }
+    return rc;
 }
 
 int swegl_b200_set_timing(swegl_b200_ctx *ctx, int enabled)
@@ -138,6 +197,10 @@ int swegl_b200_set_timing(swegl_b200_ctx *ctx, int enabled)
 
 static int ensure_pools(swegl_b200_ctx *ctx, uint32_t rows_cap, uint32_t chunks_cap, uint32_t frags_cap)
 {
+    if (frags_cap > ctx->pools.frags_cap || rows_cap > ctx->pools.rows_cap || chunks_cap > ctx->pools.chunks_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        drop_graphs(ctx);
+    }
     if (frags_cap > ctx->pools.frags_cap) {
         CK(dalloc(ctx->pools.frag_tb, (size_t)frags_cap));
         ctx->pools.frags_cap = frags_cap;
@@ -163,6 +226,7 @@ int swegl_b200_upload_scene(swegl_b200_ctx *ctx, const swegl_b200_scene_desc *sc
         return fail(ctx, SWEGL_B200_ERR_ARG, "upload_scene: null array");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
+    drop_graphs(ctx);
 
     // texel pool: [textures..., one 1x1 colour per material, the default material's colour]
     std::vector<uint32_t> tex_off(sc->n_textures);
@@ -270,6 +334,7 @@ int swegl_b200_set_screen(swegl_b200_ctx *ctx, int32_t w, int32_t h)
     if (!ctx || w <= 0 || h <= 0 || w > 65535 || h > 65535) return fail(ctx, SWEGL_B200_ERR_ARG, "set_screen: bad size");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
+    drop_graphs(ctx);
     size_t n = (size_t)w * h;
     CK(dalloc(ctx->d_screen, n)); CK(dalloc(ctx->d_depth, n)); CK(dalloc(ctx->d_tmp_color, n));
     CK(cudaMemset(ctx->d_screen, 0, n * 4));
@@ -282,6 +347,18 @@ int swegl_b200_set_screen(swegl_b200_ctx *ctx, int32_t w, int32_t h)
     return SWEGL_B200_OK;
 }
 
+// wait until the launch that last used this staging slot has finished, and act on its pool overflow
+static int acquire_slot(swegl_b200_ctx *ctx, swegl_b200_ctx::Slot &sl)
+{
+    if (sl.pending) {
+        CK(cudaEventSynchronize(sl.done));
+        int rc = check_slot_overflow(ctx, sl);
+        if (rc == SWEGL_B200_ERR_CAPACITY) ctx->err.clear();     // pools were enlarged; later frames are fine
+        else if (rc) return rc;
+    }
+    return SWEGL_B200_OK;
+}
+
 int swegl_b200_begin_frame(swegl_b200_ctx *ctx, const swegl_b200_frame_desc *fr)
 {
     if (!ctx || !fr) return SWEGL_B200_ERR_ARG;
@@ -290,36 +367,62 @@ int swegl_b200_begin_frame(swegl_b200_ctx *ctx, const swegl_b200_frame_desc *fr)
         return fail(ctx, SWEGL_B200_ERR_ARG, "begin_frame: null array");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    // stage the caller's arrays in pinned memory so the call returns without a device sync and the
-    // caller may reuse its buffers immediately
-    const size_t nw = (size_t)16 * ctx->n_nodes, nn = (size_t)9 * ctx->n_nodes, nl = (size_t)4 * fr->n_point_lights;
-    if (nw + nn + nl > ctx->stage_cap) {
-        CK(cudaStreamSynchronize(st));
-        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-        ctx->stage_cap = (nw + nn + nl) * 2 + 64;
-        CK(cudaMallocHost((void **)&ctx->h_stage, ctx->stage_cap * sizeof(float)));
-    } else {
-        CK(cudaEventSynchronize(ctx->stage_free));
-    }
+    const size_t nw = (size_t)16 * ctx->n_nodes, nn = (size_t)9 * ctx->n_nodes;
     if (fr->n_point_lights > ctx->lights_cap) {
         CK(cudaStreamSynchronize(st));
-        CK(dalloc(ctx->d_lights, (size_t)fr->n_point_lights));
-        ctx->lights_cap = fr->n_point_lights;
+        drop_graphs(ctx);
+        CK(dalloc(ctx->d_lights, (size_t)fr->n_point_lights + 8));
+        ctx->lights_cap = fr->n_point_lights + 8;
     }
-    memcpy(ctx->h_stage, fr->node_world, nw * 4);
-    memcpy(ctx->h_stage + nw, fr->node_normal, nn * 4);
-    if (nl) memcpy(ctx->h_stage + nw + nn, fr->point_lights, nl * 4);
-    CK(cudaMemcpyAsync(ctx->d_node_world, ctx->h_stage, nw * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_node_normal, ctx->h_stage + nw, nn * 4, cudaMemcpyHostToDevice, st));
-    if (nl) CK(cudaMemcpyAsync(ctx->d_lights, ctx->h_stage + nw + nn, nl * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaEventRecord(ctx->stage_free, st));
+    const size_t nl = (size_t)4 * ctx->lights_cap;
+    if (nw + nn + nl > ctx->stage_cap) {
+        CK(cudaStreamSynchronize(st));
+        drop_graphs(ctx);
+        ctx->stage_cap = nw + nn + nl + 64;
+        for (auto &sl : ctx->slots) {
+            if (sl.stage) cudaFreeHost(sl.stage);
+            CK(cudaMallocHost((void **)&sl.stage, ctx->stage_cap * sizeof(float)));
+        }
+    }
+    // stage the caller's arrays in pinned memory: the call returns without a device sync and the caller may
+    // reuse its buffers immediately; two slots let the host prepare frame i+1 while frame i runs
+    auto &sl = ctx->slots[ctx->begin_slot];
+    ctx->begin_slot ^= 1;
+    if (sl.bpending) { CK(cudaEventSynchronize(sl.bdone)); sl.bpending = false; }
+    memcpy(sl.stage, fr->node_world, nw * 4);
+    memcpy(sl.stage + nw, fr->node_normal, nn * 4);
+    if (fr->n_point_lights) memcpy(sl.stage + nw + nn, fr->point_lights, (size_t)16 * fr->n_point_lights);
     ctx->fp.ambient = fr->ambient;
     ctx->fp.sun[0] = fr->sun_dir[0]; ctx->fp.sun[1] = fr->sun_dir[1]; ctx->fp.sun[2] = fr->sun_dir[2];
     ctx->fp.sun_intensity = fr->sun_intensity;
     ctx->fp.n_lights = fr->n_point_lights;
     ctx->fp.lights = ctx->d_lights;
-    launch_vertex_world(ctx->ds, st);
+    *sl.fp = ctx->fp;
+
+    auto issue = [&]() {
+        cudaMemcpyAsync(ctx->d_node_world, sl.stage, nw * 4, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(ctx->d_node_normal, sl.stage + nw, nn * 4, cudaMemcpyHostToDevice, st);
+        if (nl) cudaMemcpyAsync(ctx->d_lights, sl.stage + nw + nn, nl * 4, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(ctx->d_fp, sl.fp, sizeof(FrameParams), cudaMemcpyHostToDevice, st);
+        launch_vertex_world(ctx->ds, st);
+    };
+    if (ctx->graphs_enabled && !ctx->timing) {
+        if (!sl.begin_exec) {
+            cudaGraph_t g = nullptr;
+            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+            issue();
+            CK(cudaStreamEndCapture(st, &g));
+            cudaError_t e = cudaGraphInstantiate(&sl.begin_exec, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) { ctx->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e); return SWEGL_B200_ERR_CUDA; }
+        }
+        CK(cudaGraphLaunch(sl.begin_exec, st));
+    } else {
+        issue();
+    }
     CK(cudaGetLastError());
+    CK(cudaEventRecord(sl.bdone, st));
+    sl.bpending = true;
     ctx->have_frame = true;
     return SWEGL_B200_OK;
 }
@@ -333,6 +436,7 @@ static int build_view(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v, Vi
     if (v->transparency_layers > 0 && !ctx->opaque)
         return fail(ctx, SWEGL_B200_ERR_UNSUPPORTED,
                     "transparency layers with non-opaque materials/texels are not on the device yet (SURVEY §8f N1)");
+    memset(&vp, 0, sizeof vp);
     memcpy(vp.view, v->view, sizeof vp.view);
     memcpy(vp.proj, v->proj, sizeof vp.proj);
     memcpy(vp.cam, v->cam_pos, sizeof vp.cam);
@@ -346,64 +450,103 @@ static int build_view(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v, Vi
     vp.nbx = (v->w + 31) / 32;
     vp.screen_w = ctx->sw;
     vp.light_mode = v->light_mode; vp.tex_mode = v->tex_mode;
+    vp.focal_distance = v->focal_distance; vp.focal_depth = v->focal_depth;
     return SWEGL_B200_OK;
 }
 
-// one pass of the kernel sequence; returns ERR_CAPACITY when a pool overflowed (caller grows and retries)
-static int run_frame(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v, const ViewParams &vp_draw,
-                     bool sync_counters, swegl_b200_stats *stats)
+// the rows the kernels draw: DoF needs colour + depth of a 5-row halo around the band, rendered redundantly
+static ViewParams draw_params(const ViewParams &vp, bool dof)
+{
+    ViewParams d = vp;
+    if (dof) { d.band0 = max(vp.vy, vp.band0 - 5); d.band1 = min(vp.vy + vp.vh, vp.band1 + 5); }
+    return d;
+}
+
+// enqueue one viewport's kernel sequence on the stream (no synchronisation: usable under stream capture).
+// `src_vp` is the pinned staging copy of draw_params() that is uploaded to ctx->d_vp first.
+static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const ViewParams &vp, const ViewParams *src_vp, bool dof,
+                           bool count_covered, bool timing, Counters *counters_out)
 {
     cudaStream_t st = ctx->stream;
-    const bool dof = v->post_mode == SWEGL_B200_POST_DOF;
-    const bool timing = ctx->timing && stats;
-    ViewParams vp = vp_draw;
-    // DoF needs colour+depth of a 5-row halo around the band: render it redundantly
-    const int out0 = vp.band0, out1 = vp.band1;
-    if (dof) { vp.band0 = max(vp.vy, vp.band0 - 5); vp.band1 = min(vp.vy + vp.vh, vp.band1 + 5); }
-
     uint32_t launches = 0;
     if (timing) cudaEventRecord(ctx->ev[0], st);
-    CK(cudaMemsetAsync(ctx->pools.counters, 0, sizeof(Counters), st));
-    launch_vertex_view(ctx->ds, vp, st); launches++;
+    cudaMemcpyAsync(ctx->d_vp, src_vp, sizeof(ViewParams), cudaMemcpyHostToDevice, st);
+    cudaMemsetAsync(ctx->pools.counters, 0, sizeof(Counters), st);
+    launch_vertex_view(ctx->ds, ctx->d_vp, st); launches++;
     launch_mark(ctx->ds, st); launches++;
     if (timing) cudaEventRecord(ctx->ev[1], st);
-    launch_setup(ctx->ds, vp, ctx->fp, ctx->pools, st); launches++;
+    launch_setup(ctx->ds, ctx->d_vp, ctx->d_fp, ctx->pools, st); launches++;
     if (timing) cudaEventRecord(ctx->ev[2], st);
-    launch_spans(vp, ctx->pools, st); launches++;
+    launch_spans(ctx->d_vp, ctx->pools, st); launches++;
     if (timing) cudaEventRecord(ctx->ev[3], st);
     uint32_t *color = dof ? ctx->d_tmp_color - ((size_t)vp.vy * vp.vw + vp.vx) : ctx->d_screen;
-    int color_pitch = dof ? vp.vw : ctx->sw;
-    launch_fragments(ctx->ds, vp, ctx->fp, ctx->pools, color, color_pitch, ctx->d_depth, stats != nullptr, st); launches++;
+    const int color_pitch = dof ? vp.vw : ctx->sw;
+    launch_fragments(ctx->ds, vp, ctx->d_vp, ctx->d_fp, ctx->pools, color, color_pitch, ctx->d_depth, count_covered, st); launches++;
     if (timing) cudaEventRecord(ctx->ev[4], st);
     if (dof) {
-        launch_dof(ctx->d_tmp_color, vp.vw, ctx->d_depth, ctx->d_screen + (size_t)vp.vy * ctx->sw + vp.vx, ctx->sw,
-                   vp.vw, vp.vh, out0 - vp.vy, out1 - vp.vy, v->focal_distance, v->focal_depth, st);
+        launch_dof(ctx->d_vp, ctx->d_tmp_color, vp.vw, ctx->d_depth, ctx->d_screen + (size_t)vp.vy * ctx->sw + vp.vx, ctx->sw,
+                   vp.vw, vp.vh, out.band0 - vp.vy, out.band1 - vp.vy, st);
         launches++;
     }
     if (timing) cudaEventRecord(ctx->ev[5], st);
-    CK(cudaGetLastError());
+    cudaMemcpyAsync(counters_out, ctx->pools.counters, sizeof(Counters), cudaMemcpyDeviceToHost, st);
+    return launches;
+}
 
-    if (sync_counters) {
-        CK(cudaMemcpyAsync(ctx->h_counters, ctx->pools.counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        const Counters &c = *ctx->h_counters;
-        if (c.overflow) return SWEGL_B200_ERR_CAPACITY;
-        if (stats) {
-            stats->n_setup_triangles = c.n_slots; stats->n_spans = c.n_rows; stats->n_chunks = c.n_chunks;
-            stats->n_covered = c.n_covered; stats->n_launches = launches;
-            if (timing) {
-                cudaEventElapsedTime(&stats->ms_vertex, ctx->ev[0], ctx->ev[1]);
-                cudaEventElapsedTime(&stats->ms_setup, ctx->ev[1], ctx->ev[2]);
-                cudaEventElapsedTime(&stats->ms_raster, ctx->ev[2], ctx->ev[3]);
-                cudaEventElapsedTime(&stats->ms_fragment, ctx->ev[3], ctx->ev[4]);
-                cudaEventElapsedTime(&stats->ms_post, ctx->ev[4], ctx->ev[5]);
-                cudaEventElapsedTime(&stats->ms_total, ctx->ev[0], ctx->ev[5]);
-            }
+// asynchronous frame: replay (or first capture) the CUDA graph of this viewport configuration
+static int render_async(swegl_b200_ctx *ctx, const ViewParams &out, bool dof)
+{
+    cudaStream_t st = ctx->stream;
+    const int si = ctx->view_slot;
+    ctx->view_slot ^= 1;
+    auto &sl = ctx->slots[si];
+    int rc = acquire_slot(ctx, sl);
+    if (rc) return rc;
+    const ViewParams vp = draw_params(out, dof);
+    *sl.vp = vp;
+    if (!ctx->graphs_enabled) {
+        issue_view(ctx, out, vp, sl.vp, dof, false, false, sl.counters);
+    } else {
+        const int32_t key[11] = { out.vx, out.vy, out.vw, out.vh, out.band0, out.band1, out.light_mode, out.tex_mode, dof ? 1 : 0, ctx->sw, ctx->sh };
+        swegl_b200_ctx::ViewGraph *vg = nullptr;
+        for (auto &g : ctx->view_graphs) if (memcmp(g.key, key, sizeof key) == 0) { vg = &g; break; }
+        if (!vg) {
+            if (ctx->view_graphs.size() >= 64) { CK(cudaStreamSynchronize(st)); for (auto &g : ctx->view_graphs) for (auto &e : g.exec) if (e) cudaGraphExecDestroy(e); ctx->view_graphs.clear(); }
+            swegl_b200_ctx::ViewGraph ng{};
+            memcpy(ng.key, key, sizeof key);
+            ctx->view_graphs.push_back(ng);
+            vg = &ctx->view_graphs.back();
         }
-    } else if (stats) {
-        stats->n_launches = launches;
+        if (!vg->exec[si]) {
+            cudaGraph_t g = nullptr;
+            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+            issue_view(ctx, out, vp, sl.vp, dof, false, false, sl.counters);
+            CK(cudaStreamEndCapture(st, &g));
+            cudaError_t e = cudaGraphInstantiate(&vg->exec[si], g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) { ctx->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e); return SWEGL_B200_ERR_CUDA; }
+        }
+        CK(cudaGraphLaunch(vg->exec[si], st));
     }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(sl.done, st));
+    sl.pending = true;
     return SWEGL_B200_OK;
+}
+
+static int grow_pools_for(swegl_b200_ctx *ctx, const Counters &c)
+{
+    uint64_t want_rows = (uint64_t)c.n_rows + c.n_rows / 4 + 1024, want_chunks = (uint64_t)c.n_chunks + c.n_chunks / 4 + 1024;
+    uint64_t want_frags = (uint64_t)c.n_frags + c.n_frags / 4 + 1024;
+    // when rows overflowed, k_spans did not run: chunk / fragment demand is unknown, so at least double them
+    if (c.overflow & 1u) want_chunks = want_chunks > 2 * want_rows ? want_chunks : 2 * want_rows;
+    if (c.overflow & 3u) want_frags = want_frags > 2 * (uint64_t)ctx->pools.frags_cap ? want_frags : 2 * (uint64_t)ctx->pools.frags_cap;
+    if (want_rows > 0xFFFFFFF0ull || want_chunks > 0x7FFFFFF0ull || want_frags > 0xFFFFFFF0ull)
+        return fail(ctx, SWEGL_B200_ERR_CAPACITY, "frame needs more than 2^32 fragments / 2^31 chunks");
+    // bin lists were consumed by k_fragments except for chunks that never got linked: reset them all
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemsetAsync(ctx->pools.bin_head, 0xFF, ctx->bins_cap * 4, ctx->stream));
+    return ensure_pools(ctx, (uint32_t)want_rows, (uint32_t)want_chunks, (uint32_t)want_frags);
 }
 
 static int render_common(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v, bool sync, swegl_b200_stats *stats)
@@ -412,30 +555,49 @@ static int render_common(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v,
     if (!ctx->have_scene || !ctx->have_frame || !ctx->d_screen)
         return fail(ctx, SWEGL_B200_ERR_STATE, "render before upload_scene / set_screen / begin_frame");
     CK(cudaSetDevice(ctx->device));
-    ViewParams vp;
-    int rc = build_view(ctx, v, vp);
+    ViewParams out;
+    int rc = build_view(ctx, v, out);
     if (rc) return rc;
+    const bool dof = v->post_mode == SWEGL_B200_POST_DOF;
     if (stats) memset(stats, 0, sizeof *stats);
-    uint32_t grows = 0;
+
+    if (!sync && !stats) {                                   // fire and forget
+        rc = render_async(ctx, out, dof);
+        if (rc == SWEGL_B200_OK) { ctx->last_vp = out; ctx->have_vp = true; }
+        return rc;
+    }
+    // synchronous frame: direct launches, counters checked, pools grown and the frame redone if needed
+    const bool timing = ctx->timing && stats;
+    const ViewParams vp = draw_params(out, dof);
+    auto &sl = ctx->slots[ctx->view_slot];
+    uint32_t grows = 0, launches = 0;
     for (;;) {
-        rc = run_frame(ctx, v, vp, sync || stats, stats);
-        if (rc != SWEGL_B200_ERR_CAPACITY) break;
-        // grow the pools to what the frame asked for (+25 %) and redo it; bin lists were consumed/reset by
-        // k_fragments, except for chunks that never got linked -- reset them all to be safe
-        const Counters c = *ctx->h_counters;
-        if (++grows > 8) return fail(ctx, SWEGL_B200_ERR_CAPACITY, "span/chunk pools keep overflowing");
-        uint64_t want_rows = (uint64_t)c.n_rows + c.n_rows / 4 + 1024, want_chunks = (uint64_t)c.n_chunks + c.n_chunks / 4 + 1024;
-        uint64_t want_frags = (uint64_t)c.n_frags + c.n_frags / 4 + 1024;
-        if (c.overflow & 1u) want_chunks = want_chunks > 2 * want_rows ? want_chunks : 2 * want_rows;
-        if (c.overflow & 3u) want_frags = want_frags > 2 * (uint64_t)ctx->pools.frags_cap ? want_frags : 2 * (uint64_t)ctx->pools.frags_cap;
-        if (want_rows > 0xFFFFFFF0ull || want_chunks > 0x7FFFFFF0ull || want_frags > 0xFFFFFFF0ull)
-            return fail(ctx, SWEGL_B200_ERR_CAPACITY, "frame needs more than 2^32 fragments / 2^31 chunks");
-        CK(cudaMemsetAsync(ctx->pools.bin_head, 0xFF, ctx->bins_cap * 4, ctx->stream));
-        rc = ensure_pools(ctx, (uint32_t)want_rows, (uint32_t)want_chunks, (uint32_t)want_frags);
+        rc = acquire_slot(ctx, sl);
+        if (rc) return rc;
+        *sl.vp = vp;
+        launches = issue_view(ctx, out, vp, sl.vp, dof, stats != nullptr, timing, ctx->h_counters);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (!ctx->h_counters->overflow) break;
+        if (++grows > 8) return fail(ctx, SWEGL_B200_ERR_CAPACITY, "span/chunk/fragment pools keep overflowing");
+        rc = grow_pools_for(ctx, *ctx->h_counters);
         if (rc) return rc;
     }
-    if (rc == SWEGL_B200_OK) { ctx->last_vp = vp; ctx->have_vp = true; if (stats) stats->pool_grows = grows; }
-    return rc;
+    if (stats) {
+        const Counters &c = *ctx->h_counters;
+        stats->n_setup_triangles = c.n_slots; stats->n_spans = c.n_rows; stats->n_chunks = c.n_chunks;
+        stats->n_covered = c.n_covered; stats->n_launches = launches; stats->pool_grows = grows;
+        if (timing) {
+            cudaEventElapsedTime(&stats->ms_vertex, ctx->ev[0], ctx->ev[1]);
+            cudaEventElapsedTime(&stats->ms_setup, ctx->ev[1], ctx->ev[2]);
+            cudaEventElapsedTime(&stats->ms_raster, ctx->ev[2], ctx->ev[3]);
+            cudaEventElapsedTime(&stats->ms_fragment, ctx->ev[3], ctx->ev[4]);
+            cudaEventElapsedTime(&stats->ms_post, ctx->ev[4], ctx->ev[5]);
+            cudaEventElapsedTime(&stats->ms_total, ctx->ev[0], ctx->ev[5]);
+        }
+    }
+    ctx->last_vp = out; ctx->have_vp = true;
+    return SWEGL_B200_OK;
 }
 
 int swegl_b200_render_viewport_device(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *vp, swegl_b200_stats *stats)
@@ -447,19 +609,27 @@ int swegl_b200_render_viewport(swegl_b200_ctx *ctx, const swegl_b200_viewport_de
                                float *zbuffer, swegl_b200_stats *stats)
 {
     if (!pixels || pitch_bytes < 4) return fail(ctx, SWEGL_B200_ERR_ARG, "render_viewport: null pixels");
-    int rc = render_common(ctx, v, true, stats);
+    // the frame and its read-back are queued back to back; one synchronisation at the end.  If the frame
+    // overflowed a pool (first frames of a new scene) it is redone through the synchronous path.
+    int rc = render_common(ctx, v, false, stats);
     if (rc) return rc;
     const ViewParams &vp = ctx->last_vp;
     cudaStream_t st = ctx->stream;
     const int rows = vp.band1 - vp.band0;
-    CK(cudaMemcpy2DAsync((char *)pixels + (size_t)vp.band0 * pitch_bytes + (size_t)vp.vx * 4, (size_t)pitch_bytes,
-                         ctx->d_screen + (size_t)vp.band0 * ctx->sw + vp.vx, (size_t)ctx->sw * 4,
-                         (size_t)vp.vw * 4, (size_t)rows, cudaMemcpyDeviceToHost, st));
-    if (zbuffer)
-        CK(cudaMemcpyAsync(zbuffer + (size_t)(vp.band0 - vp.vy) * vp.vw, ctx->d_depth + (size_t)(vp.band0 - vp.vy) * vp.vw,
-                           (size_t)rows * vp.vw * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    return SWEGL_B200_OK;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CK(cudaMemcpy2DAsync((char *)pixels + (size_t)vp.band0 * pitch_bytes + (size_t)vp.vx * 4, (size_t)pitch_bytes,
+                             ctx->d_screen + (size_t)vp.band0 * ctx->sw + vp.vx, (size_t)ctx->sw * 4,
+                             (size_t)vp.vw * 4, (size_t)rows, cudaMemcpyDeviceToHost, st));
+        if (zbuffer)
+            CK(cudaMemcpyAsync(zbuffer + (size_t)(vp.band0 - vp.vy) * vp.vw, ctx->d_depth + (size_t)(vp.band0 - vp.vy) * vp.vw,
+                               (size_t)rows * vp.vw * 4, cudaMemcpyDeviceToHost, st));
+        rc = swegl_b200_synchronize(ctx);
+        if (rc != SWEGL_B200_ERR_CAPACITY || attempt) break;
+        ctx->err.clear();
+        rc = render_common(ctx, v, true, stats);             // pools are larger now: redo synchronously
+        if (rc) return rc;
+    }
+    return rc;
 }
 
 int swegl_b200_device_buffers(swegl_b200_ctx *ctx, void **screen_dev, void **depth_dev)

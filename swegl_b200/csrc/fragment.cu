@@ -122,11 +122,16 @@ static constexpr int FRAG_STRETCH = 8;              // bins (of 32 pixels) one w
 //   2. empty bins are cleared in bulk with 128-bit stores (colour 0, depth 0x7F7F7F7F: viewport.cpp:88-113),
 //   3. each non-empty bin is resolved with lane = pixel as described at the top of this file.
 template <int LIGHT, int TEX>
-__global__ void __launch_bounds__(FRAG_TPB) k_fragments(DeviceScene s, const __grid_constant__ ViewParams vp,
-                                                        const __grid_constant__ FrameParams fp, Pools pl,
+__global__ void __launch_bounds__(FRAG_TPB) k_fragments(DeviceScene s, const ViewParams *__restrict__ vpp,
+                                                        const FrameParams *__restrict__ fpp, Pools pl,
                                                         uint32_t *__restrict__ color, int color_pitch,
                                                         float *__restrict__ depth, int count_covered)
 {
+    __shared__ ViewParams vp;                   // per-frame constants staged once per CTA
+    __shared__ FrameParams fp;
+    for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += FRAG_TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
+    for (int w = threadIdx.x; w < (int)(sizeof(FrameParams) / 4); w += FRAG_TPB) reinterpret_cast<uint32_t *>(&fp)[w] = reinterpret_cast<const uint32_t *>(fpp)[w];
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int row = (vp.band0 - vp.vy) + blockIdx.y * FRAG_ROWS + (threadIdx.x >> 5);   // viewport-relative
     if (row >= vp.band1 - vp.vy) return;
@@ -237,11 +242,11 @@ SB_DEV float blur_factor(float depth, float focal_distance, float focal_depth)
     return r;
 }
 
-__global__ void __launch_bounds__(DOF_THREADS) k_dof(const uint32_t *__restrict__ src, int src_pitch,
+__global__ void __launch_bounds__(DOF_THREADS) k_dof(const ViewParams *__restrict__ vpp, const uint32_t *__restrict__ src, int src_pitch,
                                                      const float *__restrict__ depth, uint32_t *__restrict__ dst,
-                                                     int dst_pitch, int w, int h, int row0, int row1,
-                                                     float focal_distance, float focal_depth)
+                                                     int dst_pitch, int w, int h, int row0, int row1)
 {
+    const float focal_distance = vpp->focal_distance, focal_depth = vpp->focal_depth;
     __shared__ unsigned long long s64[(DOF_SH + 1) * DOF_PW];
     __shared__ uint32_t s32[(DOF_SH + 1) * DOF_PW];
     __shared__ uint8_t srad[DOF_SH * DOF_SW];               // blur radius (0..5) of every staged pixel
@@ -374,30 +379,30 @@ __global__ void __launch_bounds__(DOF_THREADS) k_dof(const uint32_t *__restrict_
 // launchers
 // ----------------------------------------------------------------------------------------
 template <int LIGHT, int TEX>
-static void launch_frag_t(const DeviceScene &s, const ViewParams &vp, const FrameParams &fp, const Pools &p,
+static void launch_frag_t(const DeviceScene &s, const ViewParams &vp, const ViewParams *d_vp, const FrameParams *d_fp, const Pools &p,
                           uint32_t *color, int color_pitch, float *depth, bool count_covered, cudaStream_t st)
 {
     dim3 grid((vp.nbx + FRAG_STRETCH - 1) / FRAG_STRETCH, (vp.band1 - vp.band0 + FRAG_ROWS - 1) / FRAG_ROWS);
     if (!grid.x || !grid.y) return;
-    k_fragments<LIGHT, TEX><<<grid, FRAG_TPB, 0, st>>>(s, vp, fp, p, color, color_pitch, depth, count_covered ? 1 : 0);
+    k_fragments<LIGHT, TEX><<<grid, FRAG_TPB, 0, st>>>(s, d_vp, d_fp, p, color, color_pitch, depth, count_covered ? 1 : 0);
 }
 
-void launch_fragments(const DeviceScene &s, const ViewParams &vp, const FrameParams &fp, const Pools &p,
+void launch_fragments(const DeviceScene &s, const ViewParams &vp, const ViewParams *d_vp, const FrameParams *d_fp, const Pools &p,
                       uint32_t *color, int color_pitch, float *depth, bool count_covered, cudaStream_t st)
 {
-#define SB_CASE(L, T) if (vp.light_mode == L && vp.tex_mode == T) { launch_frag_t<L, T>(s, vp, fp, p, color, color_pitch, depth, count_covered, st); return; }
+#define SB_CASE(L, T) if (vp.light_mode == L && vp.tex_mode == T) { launch_frag_t<L, T>(s, vp, d_vp, d_fp, p, color, color_pitch, depth, count_covered, st); return; }
     SB_CASE(0, 0) SB_CASE(0, 1) SB_CASE(0, 2)
     SB_CASE(1, 0) SB_CASE(1, 1) SB_CASE(1, 2)
     SB_CASE(2, 0) SB_CASE(2, 1) SB_CASE(2, 2)
 #undef SB_CASE
 }
 
-void launch_dof(const uint32_t *src, int src_pitch, const float *depth, uint32_t *dst, int dst_pitch,
-                int w, int h, int row0, int row1, float focal_distance, float focal_depth, cudaStream_t st)
+void launch_dof(const ViewParams *d_vp, const uint32_t *src, int src_pitch, const float *depth, uint32_t *dst, int dst_pitch,
+                int w, int h, int row0, int row1, cudaStream_t st)
 {
     dim3 grid((w + DOF_OW - 1) / DOF_OW, (row1 - row0 + DOF_OH - 1) / DOF_OH);
     if (grid.x && grid.y)
-        k_dof<<<grid, DOF_THREADS, 0, st>>>(src, src_pitch, depth, dst, dst_pitch, w, h, row0, row1, focal_distance, focal_depth);
+        k_dof<<<grid, DOF_THREADS, 0, st>>>(d_vp, src, src_pitch, depth, dst, dst_pitch, w, h, row0, row1);
 }
 
 } // namespace sb

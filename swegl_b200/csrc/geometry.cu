@@ -28,8 +28,9 @@ __global__ void __launch_bounds__(TPB) k_vertex_world(DeviceScene s)
     s.v_world[3 * i] = w.x; s.v_world[3 * i + 1] = w.y; s.v_world[3 * i + 2] = w.z;
 }
 
-__global__ void __launch_bounds__(TPB) k_vertex_view(DeviceScene s, const __grid_constant__ ViewParams vp)
+__global__ void __launch_bounds__(TPB) k_vertex_view(DeviceScene s, const ViewParams *__restrict__ vpp)
 {
+    const ViewParams &vp = *vpp;
     uint32_t i = blockIdx.x * TPB + threadIdx.x;
     if (i >= s.n_vertices) return;
     V3 w = v3(s.v_world[3 * i], s.v_world[3 * i + 1], s.v_world[3 * i + 2]);
@@ -236,9 +237,14 @@ SB_DEV void fill_row_slots(const Pools &pl, RowRange rr, uint32_t slot)
     }
 }
 
-__global__ void __launch_bounds__(128) k_setup(DeviceScene s, const __grid_constant__ ViewParams vp,
-                                               const __grid_constant__ FrameParams fp, Pools pl)
+__global__ void __launch_bounds__(128) k_setup(DeviceScene s, const ViewParams *__restrict__ vpp,
+                                               const FrameParams *__restrict__ fpp, Pools pl)
 {
+    __shared__ ViewParams vp;                   // staged once per CTA: used all over the set-up code
+    __shared__ FrameParams fp;
+    for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += 128) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
+    for (int w = threadIdx.x; w < (int)(sizeof(FrameParams) / 4); w += 128) reinterpret_cast<uint32_t *>(&fp)[w] = reinterpret_cast<const uint32_t *>(fpp)[w];
+    __syncthreads();
     const uint32_t t = blockIdx.x * 128 + threadIdx.x;
     RowRange r0 = { 0u, 0u }, r1 = { 0u, 0u };
     Tri tr = { 0u, 0u, 0u, 0u };
@@ -309,9 +315,12 @@ struct SpanCta {
     uint32_t nchunks[32], cbase[32], fbase[32], seg_incl[32]; // ... and their allocations / segment prefix
 };
 
-__global__ void __launch_bounds__(TPB) k_spans(const __grid_constant__ ViewParams vp, Pools pl)
+__global__ void __launch_bounds__(TPB) k_spans(const ViewParams *__restrict__ vpp, Pools pl)
 {
     __shared__ SpanCta sh;
+    __shared__ ViewParams vp;
+    for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
+    __syncthreads();
     if (pl.counters->overflow & 1u) return;      // some rows were never allocated: the host grows the pool and redoes the frame
     const uint32_t n_rows = min(pl.counters->n_rows, pl.rows_cap);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -481,21 +490,21 @@ void launch_vertex_world(const DeviceScene &s, cudaStream_t st)
 {
     if (s.n_vertices) k_vertex_world<<<cdiv(s.n_vertices, TPB), TPB, 0, st>>>(s);
 }
-void launch_vertex_view(const DeviceScene &s, const ViewParams &vp, cudaStream_t st)
+void launch_vertex_view(const DeviceScene &s, const ViewParams *d_vp, cudaStream_t st)
 {
-    if (s.n_vertices) k_vertex_view<<<cdiv(s.n_vertices, TPB), TPB, 0, st>>>(s, vp);
+    if (s.n_vertices) k_vertex_view<<<cdiv(s.n_vertices, TPB), TPB, 0, st>>>(s, d_vp);
 }
 void launch_mark(const DeviceScene &s, cudaStream_t st)
 {
     if (s.n_tris) k_mark<<<cdiv(s.n_tris, TPB), TPB, 0, st>>>(s);
 }
-void launch_setup(const DeviceScene &s, const ViewParams &vp, const FrameParams &fp, const Pools &p, cudaStream_t st)
+void launch_setup(const DeviceScene &s, const ViewParams *d_vp, const FrameParams *d_fp, const Pools &p, cudaStream_t st)
 {
-    if (s.n_tris) k_setup<<<cdiv(s.n_tris, 128), 128, 0, st>>>(s, vp, fp, p);
+    if (s.n_tris) k_setup<<<cdiv(s.n_tris, 128), 128, 0, st>>>(s, d_vp, d_fp, p);
 }
-void launch_spans(const ViewParams &vp, const Pools &p, cudaStream_t st)
+void launch_spans(const ViewParams *d_vp, const Pools &p, cudaStream_t st)
 {
-    k_spans<<<148 * 16, TPB, 0, st>>>(vp, p);      // persistent CTAs, 32 scanline records per pass
+    k_spans<<<148 * 16, TPB, 0, st>>>(d_vp, p);      // persistent CTAs, 32 scanline records per pass
 }
 
 } // namespace sb
