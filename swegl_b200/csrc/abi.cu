@@ -400,10 +400,8 @@ int swegl_b200_begin_frame(swegl_b200_ctx *ctx, const swegl_b200_frame_desc *fr)
     *sl.fp = ctx->fp;
 
     auto issue = [&]() {
-        cudaMemcpyAsync(ctx->d_node_world, sl.stage, nw * 4, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(ctx->d_node_normal, sl.stage + nw, nn * 4, cudaMemcpyHostToDevice, st);
-        if (nl) cudaMemcpyAsync(ctx->d_lights, sl.stage + nw + nn, nl * 4, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(ctx->d_fp, sl.fp, sizeof(FrameParams), cudaMemcpyHostToDevice, st);
+        launch_stage_in(sl.stage, ctx->d_node_world, (uint32_t)nw, ctx->d_node_normal, (uint32_t)nn,
+                        reinterpret_cast<float *>(ctx->d_lights), (uint32_t)nl, sl.fp, ctx->d_fp, st);
         launch_vertex_world(ctx->ds, st);
     };
     if (ctx->graphs_enabled && !ctx->timing) {
@@ -465,14 +463,12 @@ static ViewParams draw_params(const ViewParams &vp, bool dof)
 // enqueue one viewport's kernel sequence on the stream (no synchronisation: usable under stream capture).
 // `src_vp` is the pinned staging copy of draw_params() that is uploaded to ctx->d_vp first.
 static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const ViewParams &vp, const ViewParams *src_vp, bool dof,
-                           bool count_covered, bool timing, Counters *counters_out)
+                           bool count_covered, bool timing, bool sync_counters, Counters *counters_out)
 {
     cudaStream_t st = ctx->stream;
     uint32_t launches = 0;
     if (timing) cudaEventRecord(ctx->ev[0], st);
-    cudaMemcpyAsync(ctx->d_vp, src_vp, sizeof(ViewParams), cudaMemcpyHostToDevice, st);
-    cudaMemsetAsync(ctx->pools.counters, 0, sizeof(Counters), st);
-    launch_vertex_view(ctx->ds, ctx->d_vp, st); launches++;
+    launch_vertex_view(ctx->ds, src_vp, ctx->d_vp, ctx->pools.counters, st); launches++;
     launch_mark(ctx->ds, st); launches++;
     if (timing) cudaEventRecord(ctx->ev[1], st);
     launch_setup(ctx->ds, ctx->d_vp, ctx->d_fp, ctx->pools, st); launches++;
@@ -481,7 +477,9 @@ static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const Vie
     if (timing) cudaEventRecord(ctx->ev[3], st);
     uint32_t *color = dof ? ctx->d_tmp_color - ((size_t)vp.vy * vp.vw + vp.vx) : ctx->d_screen;
     const int color_pitch = dof ? vp.vw : ctx->sw;
-    launch_fragments(ctx->ds, vp, ctx->d_vp, ctx->d_fp, ctx->pools, color, color_pitch, ctx->d_depth, count_covered, st); launches++;
+    // asynchronous frames publish their counters from inside k_fragments; synchronous ones copy them at the end
+    launch_fragments(ctx->ds, vp, ctx->d_vp, ctx->d_fp, ctx->pools, color, color_pitch, ctx->d_depth, count_covered,
+                     sync_counters ? nullptr : counters_out, st); launches++;
     if (timing) cudaEventRecord(ctx->ev[4], st);
     if (dof) {
         launch_dof(ctx->d_vp, ctx->d_tmp_color, vp.vw, ctx->d_depth, ctx->d_screen + (size_t)vp.vy * ctx->sw + vp.vx, ctx->sw,
@@ -489,7 +487,7 @@ static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const Vie
         launches++;
     }
     if (timing) cudaEventRecord(ctx->ev[5], st);
-    cudaMemcpyAsync(counters_out, ctx->pools.counters, sizeof(Counters), cudaMemcpyDeviceToHost, st);
+    if (sync_counters) cudaMemcpyAsync(counters_out, ctx->pools.counters, sizeof(Counters), cudaMemcpyDeviceToHost, st);
     return launches;
 }
 
@@ -505,7 +503,7 @@ static int render_async(swegl_b200_ctx *ctx, const ViewParams &out, bool dof)
     const ViewParams vp = draw_params(out, dof);
     *sl.vp = vp;
     if (!ctx->graphs_enabled) {
-        issue_view(ctx, out, vp, sl.vp, dof, false, false, sl.counters);
+        issue_view(ctx, out, vp, sl.vp, dof, false, false, false, sl.counters);
     } else {
         const int32_t key[11] = { out.vx, out.vy, out.vw, out.vh, out.band0, out.band1, out.light_mode, out.tex_mode, dof ? 1 : 0, ctx->sw, ctx->sh };
         swegl_b200_ctx::ViewGraph *vg = nullptr;
@@ -520,7 +518,7 @@ static int render_async(swegl_b200_ctx *ctx, const ViewParams &out, bool dof)
         if (!vg->exec[si]) {
             cudaGraph_t g = nullptr;
             CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-            issue_view(ctx, out, vp, sl.vp, dof, false, false, sl.counters);
+            issue_view(ctx, out, vp, sl.vp, dof, false, false, false, sl.counters);
             CK(cudaStreamEndCapture(st, &g));
             cudaError_t e = cudaGraphInstantiate(&vg->exec[si], g, 0);
             cudaGraphDestroy(g);
@@ -575,7 +573,7 @@ static int render_common(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v,
         rc = acquire_slot(ctx, sl);
         if (rc) return rc;
         *sl.vp = vp;
-        launches = issue_view(ctx, out, vp, sl.vp, dof, stats != nullptr, timing, ctx->h_counters);
+        launches = issue_view(ctx, out, vp, sl.vp, dof, stats != nullptr, timing, true, ctx->h_counters);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(ctx->stream));
         if (!ctx->h_counters->overflow) break;

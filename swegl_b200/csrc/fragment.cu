@@ -125,8 +125,14 @@ template <int LIGHT, int TEX>
 __global__ void __launch_bounds__(FRAG_TPB) k_fragments(DeviceScene s, const ViewParams *__restrict__ vpp,
                                                         const FrameParams *__restrict__ fpp, Pools pl,
                                                         uint32_t *__restrict__ color, int color_pitch,
-                                                        float *__restrict__ depth, int count_covered)
+                                                        float *__restrict__ depth, int count_covered,
+                                                        Counters *__restrict__ h_counters_out)
 {
+    // k_setup / k_spans are done: publish their counters (pool demand, overflow flags) to the pinned slot the host
+    // polls, instead of a D2H copy node at the end of the graph.  (n_covered is only final after this kernel; the
+    // synchronous stats path copies the counters itself.)
+    if (h_counters_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < sizeof(Counters) / 4)
+        reinterpret_cast<uint32_t *>(h_counters_out)[threadIdx.x] = reinterpret_cast<const uint32_t *>(pl.counters)[threadIdx.x];
     __shared__ ViewParams vp;                   // per-frame constants staged once per CTA
     __shared__ FrameParams fp;
     for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += FRAG_TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
@@ -380,17 +386,17 @@ __global__ void __launch_bounds__(DOF_THREADS) k_dof(const ViewParams *__restric
 // ----------------------------------------------------------------------------------------
 template <int LIGHT, int TEX>
 static void launch_frag_t(const DeviceScene &s, const ViewParams &vp, const ViewParams *d_vp, const FrameParams *d_fp, const Pools &p,
-                          uint32_t *color, int color_pitch, float *depth, bool count_covered, cudaStream_t st)
+                          uint32_t *color, int color_pitch, float *depth, bool count_covered, Counters *h_counters_out, cudaStream_t st)
 {
     dim3 grid((vp.nbx + FRAG_STRETCH - 1) / FRAG_STRETCH, (vp.band1 - vp.band0 + FRAG_ROWS - 1) / FRAG_ROWS);
     if (!grid.x || !grid.y) return;
-    k_fragments<LIGHT, TEX><<<grid, FRAG_TPB, 0, st>>>(s, d_vp, d_fp, p, color, color_pitch, depth, count_covered ? 1 : 0);
+    k_fragments<LIGHT, TEX><<<grid, FRAG_TPB, 0, st>>>(s, d_vp, d_fp, p, color, color_pitch, depth, count_covered ? 1 : 0, h_counters_out);
 }
 
 void launch_fragments(const DeviceScene &s, const ViewParams &vp, const ViewParams *d_vp, const FrameParams *d_fp, const Pools &p,
-                      uint32_t *color, int color_pitch, float *depth, bool count_covered, cudaStream_t st)
+                      uint32_t *color, int color_pitch, float *depth, bool count_covered, Counters *h_counters_out, cudaStream_t st)
 {
-#define SB_CASE(L, T) if (vp.light_mode == L && vp.tex_mode == T) { launch_frag_t<L, T>(s, vp, d_vp, d_fp, p, color, color_pitch, depth, count_covered, st); return; }
+#define SB_CASE(L, T) if (vp.light_mode == L && vp.tex_mode == T) { launch_frag_t<L, T>(s, vp, d_vp, d_fp, p, color, color_pitch, depth, count_covered, h_counters_out, st); return; }
     SB_CASE(0, 0) SB_CASE(0, 1) SB_CASE(0, 2)
     SB_CASE(1, 0) SB_CASE(1, 1) SB_CASE(1, 2)
     SB_CASE(2, 0) SB_CASE(2, 1) SB_CASE(2, 2)

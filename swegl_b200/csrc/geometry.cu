@@ -19,6 +19,20 @@ static constexpr uint32_t SPAN_SEG = 4;      // 32-column bins per span segment 
 // ----------------------------------------------------------------------------------------
 // vertex stage
 // ----------------------------------------------------------------------------------------
+// begin_frame's uploads without DMA nodes: one CTA reads the caller's arrays from the pinned staging slot
+// (zero-copy over PCIe) and writes the device copies every later kernel uses
+__global__ void __launch_bounds__(256) k_stage_in(const float *__restrict__ stage, float *__restrict__ node_world, uint32_t n_world,
+                                                   float *__restrict__ node_normal, uint32_t n_normal,
+                                                   float *__restrict__ lights, uint32_t n_lights_f,
+                                                   const FrameParams *__restrict__ h_fp, FrameParams *__restrict__ d_fp)
+{
+    for (uint32_t i = threadIdx.x; i < n_world; i += 256) node_world[i] = stage[i];
+    for (uint32_t i = threadIdx.x; i < n_normal; i += 256) node_normal[i] = stage[n_world + i];
+    for (uint32_t i = threadIdx.x; i < n_lights_f; i += 256) lights[i] = stage[n_world + n_normal + i];
+    for (uint32_t i = threadIdx.x; i < sizeof(FrameParams) / 4; i += 256)
+        reinterpret_cast<uint32_t *>(d_fp)[i] = reinterpret_cast<const uint32_t *>(h_fp)[i];
+}
+
 __global__ void __launch_bounds__(TPB) k_vertex_world(DeviceScene s)
 {
     uint32_t i = blockIdx.x * TPB + threadIdx.x;
@@ -28,9 +42,19 @@ __global__ void __launch_bounds__(TPB) k_vertex_world(DeviceScene s)
     s.v_world[3 * i] = w.x; s.v_world[3 * i + 1] = w.y; s.v_world[3 * i + 2] = w.z;
 }
 
-__global__ void __launch_bounds__(TPB) k_vertex_view(DeviceScene s, const ViewParams *__restrict__ vpp)
+// first kernel of a viewport: reads the ViewParams from the pinned staging slot (zero-copy), publishes the
+// device copy the later kernels use and clears the frame counters -- no memcpy / memset nodes in the graph
+__global__ void __launch_bounds__(TPB) k_vertex_view(DeviceScene s, const ViewParams *__restrict__ h_vp,
+                                                     ViewParams *__restrict__ d_vp, Counters *__restrict__ counters)
 {
-    const ViewParams &vp = *vpp;
+    __shared__ ViewParams vp;
+    for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += TPB) {
+        const uint32_t v = reinterpret_cast<const uint32_t *>(h_vp)[w];
+        reinterpret_cast<uint32_t *>(&vp)[w] = v;
+        if (blockIdx.x == 0) reinterpret_cast<uint32_t *>(d_vp)[w] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < sizeof(Counters) / 4) reinterpret_cast<uint32_t *>(counters)[threadIdx.x] = 0;
+    __syncthreads();
     uint32_t i = blockIdx.x * TPB + threadIdx.x;
     if (i >= s.n_vertices) return;
     V3 w = v3(s.v_world[3 * i], s.v_world[3 * i + 1], s.v_world[3 * i + 2]);
@@ -490,9 +514,14 @@ void launch_vertex_world(const DeviceScene &s, cudaStream_t st)
 {
     if (s.n_vertices) k_vertex_world<<<cdiv(s.n_vertices, TPB), TPB, 0, st>>>(s);
 }
-void launch_vertex_view(const DeviceScene &s, const ViewParams *d_vp, cudaStream_t st)
+void launch_stage_in(const float *stage, float *node_world, uint32_t n_world, float *node_normal, uint32_t n_normal,
+                     float *lights, uint32_t n_lights_f, const FrameParams *h_fp, FrameParams *d_fp, cudaStream_t st)
 {
-    if (s.n_vertices) k_vertex_view<<<cdiv(s.n_vertices, TPB), TPB, 0, st>>>(s, d_vp);
+    k_stage_in<<<1, 256, 0, st>>>(stage, node_world, n_world, node_normal, n_normal, lights, n_lights_f, h_fp, d_fp);
+}
+void launch_vertex_view(const DeviceScene &s, const ViewParams *h_vp, ViewParams *d_vp, Counters *counters, cudaStream_t st)
+{
+    k_vertex_view<<<max(1u, cdiv(s.n_vertices, TPB)), TPB, 0, st>>>(s, h_vp, d_vp, counters);
 }
 void launch_mark(const DeviceScene &s, cudaStream_t st)
 {
