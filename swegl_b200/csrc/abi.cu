@@ -56,6 +56,7 @@ struct swegl_b200_ctx {
     size_t depth_cap = 0;
 
     ViewParams last_vp{}; bool have_vp = false;
+    ViewParams dof_cache{}; float dof_cache_depth = 0.f; bool dof_cache_valid = false;   // DoF thresholds per focal_depth
     cudaEvent_t ev[8]{};
 };
 
@@ -122,7 +123,7 @@ void swegl_b200_destroy(swegl_b200_ctx *ctx)
     void *ptrs[] = { ctx->d_pos, ctx->d_nrm, ctx->d_uv, ctx->d_vert_node, ctx->d_texels, ctx->d_tris, ctx->d_prims,
                      ctx->d_node_world, ctx->d_node_normal, ctx->d_v_world, ctx->d_v_ndc, ctx->d_n_world, ctx->d_yes,
                      ctx->d_lights, ctx->pools.edges, ctx->pools.shades, ctx->pools.spans, ctx->pools.span_shades, ctx->pools.frag_tb, ctx->pools.row_slot,
-                     ctx->pools.chunks, ctx->pools.bin_head, ctx->pools.counters, ctx->d_screen, ctx->d_depth,
+                     ctx->pools.chunks, ctx->pools.bin_head, ctx->pools.bin_used, ctx->pools.counters, ctx->d_screen, ctx->d_depth,
                      ctx->d_tmp_color };
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -342,6 +343,8 @@ int swegl_b200_set_screen(swegl_b200_ctx *ctx, int32_t w, int32_t h)
     size_t bins = (size_t)((w + 31) / 32 + 1) * h;
     CK(dalloc(ctx->pools.bin_head, bins));
     CK(cudaMemset(ctx->pools.bin_head, 0xFF, bins * 4));
+    CK(dalloc(ctx->pools.bin_used, bins));
+    CK(cudaMemset(ctx->pools.bin_used, 0, bins));
     ctx->bins_cap = bins; ctx->depth_cap = n;
     ctx->sw = w; ctx->sh = h;
     return SWEGL_B200_OK;
@@ -425,6 +428,54 @@ int swegl_b200_begin_frame(swegl_b200_ctx *ctx, const swegl_b200_frame_desc *fr)
     return SWEGL_B200_OK;
 }
 
+// remap_clipped(1.0f, focal_depth, 0.0f, 5.0f, t) (lerp.hpp:24-43) in IEEE fp32 on the host (this TU is built with
+// -ffp-contract=off; volatile keeps every intermediate in fp32)
+static float dof_blur_of_t(float t, float focal_depth)
+{
+    const float a = 1.0f, b = focal_depth;
+    volatile float xq;
+    if (a == b) xq = 0.5f; else if (t <= a) xq = 0.0f; else if (t >= b) xq = 1.0f;
+    else { volatile float num = t - a; volatile float den = b - a; xq = num / den; }
+    if (xq <= 0.0f) return 0.0f;
+    if (xq >= 5.0f) return 5.0f;
+    volatile float m = 5.0f * xq; volatile float r = 0.0f + m;
+    return r;
+}
+
+// DoF-R's radius (int)blur(t) is a monotone step function of t = |focal_distance - z| >= 0: find, for k = 1..5, the
+// smallest float t with radius(t) >= k by bisection over the (monotone) bit patterns of non-negative floats, and the
+// largest t whose blur is exactly 0.  The kernel then classifies a pixel with 6 comparisons instead of a division.
+static void dof_thresholds(float focal_depth, ViewParams &vp)
+{
+    auto f = [](uint32_t bits) { float x; memcpy(&x, &bits, 4); return x; };
+    vp.dof_const_radius = -1;
+    if (focal_depth == 1.0f) { vp.dof_const_radius = (int32_t)dof_blur_of_t(2.0f, focal_depth); }   // a == b: blur 2.5 everywhere
+    const uint32_t top = 0x7F800000u;                         // +inf: radius(inf) is the maximum
+    for (int k = 1; k <= 5; k++) {
+        uint32_t lo = 0, hi = top;                            // invariant: radius(lo) < k (or lo == 0), radius(hi) >= k or hi == top
+        if ((int)dof_blur_of_t(f(top), focal_depth) < k) { vp.dof_t[k - 1] = f(0x7FC00000u); continue; }   // never reached: NaN compares false
+        if ((int)dof_blur_of_t(0.0f, focal_depth) >= k) { vp.dof_t[k - 1] = 0.0f; continue; }
+        while (hi - lo > 1) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            if ((int)dof_blur_of_t(f(mid), focal_depth) >= k) hi = mid; else lo = mid;
+        }
+        vp.dof_t[k - 1] = f(hi);
+    }
+    // taps count iff blur != 0: largest t with blur == 0 (blur is monotone too)
+    {
+        uint32_t lo = 0, hi = top;
+        if (dof_blur_of_t(f(top), focal_depth) == 0.0f) vp.dof_on = f(top);
+        else if (dof_blur_of_t(0.0f, focal_depth) != 0.0f) vp.dof_on = -1.0f;
+        else {
+            while (hi - lo > 1) {
+                const uint32_t mid = lo + (hi - lo) / 2;
+                if (dof_blur_of_t(f(mid), focal_depth) != 0.0f) hi = mid; else lo = mid;
+            }
+            vp.dof_on = f(lo);
+        }
+    }
+}
+
 static int build_view(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v, ViewParams &vp)
 {
     if (v->w <= 0 || v->h <= 0 || v->x < 0 || v->y < 0 || v->x + v->w > ctx->sw || v->y + v->h > ctx->sh)
@@ -449,6 +500,17 @@ static int build_view(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v, Vi
     vp.screen_w = ctx->sw;
     vp.light_mode = v->light_mode; vp.tex_mode = v->tex_mode;
     vp.focal_distance = v->focal_distance; vp.focal_depth = v->focal_depth;
+    vp.dof_const_radius = -1;
+    if (v->post_mode == SWEGL_B200_POST_DOF) {
+        if (!(v->focal_depth == v->focal_depth) || !(v->focal_distance == v->focal_distance))
+            return fail(ctx, SWEGL_B200_ERR_ARG, "DoF focal parameters are NaN");
+        if (v->focal_depth != ctx->dof_cache_depth || !ctx->dof_cache_valid) {
+            dof_thresholds(v->focal_depth, ctx->dof_cache);
+            ctx->dof_cache_depth = v->focal_depth; ctx->dof_cache_valid = true;
+        }
+        memcpy(vp.dof_t, ctx->dof_cache.dof_t, sizeof vp.dof_t);
+        vp.dof_on = ctx->dof_cache.dof_on; vp.dof_const_radius = ctx->dof_cache.dof_const_radius;
+    }
     return SWEGL_B200_OK;
 }
 
@@ -482,7 +544,7 @@ static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const Vie
                      sync_counters ? nullptr : counters_out, st); launches++;
     if (timing) cudaEventRecord(ctx->ev[4], st);
     if (dof) {
-        launch_dof(ctx->d_vp, ctx->d_tmp_color, vp.vw, ctx->d_depth, ctx->d_screen + (size_t)vp.vy * ctx->sw + vp.vx, ctx->sw,
+        launch_dof(ctx->d_vp, ctx->pools.bin_used, vp.nbx, ctx->d_tmp_color, vp.vw, ctx->d_depth, ctx->d_screen + (size_t)vp.vy * ctx->sw + vp.vx, ctx->sw,
                    vp.vw, vp.vh, out.band0 - vp.vy, out.band1 - vp.vy, st);
         launches++;
     }

@@ -117,6 +117,14 @@ static constexpr int FRAG_TPB = 256;
 static constexpr int FRAG_ROWS = FRAG_TPB / 32;     // one warp per row of the CTA's 8-row group
 static constexpr int FRAG_STRETCH = 8;              // bins (of 32 pixels) one warp owns along its row
 
+// per-warp queue of the stretch's winning fragments (pass 1 -> pass 2 -> pass 3 of k_fragments)
+struct FragWarp {
+    float u[FRAG_STRETCH * 32];         // interpolator progress of the winner; overwritten by its colour in pass 2
+    uint32_t span[FRAG_STRETCH * 32];   // winning span, 0xFFFFFFFF = background
+    uint32_t slot[FRAG_STRETCH * 32];   // winning slot (-> SlotShade)
+    uint8_t idx[FRAG_STRETCH * 32];     // compacted list of covered pixels
+};
+
 // One warp owns a stretch of FRAG_STRETCH bins (256 pixels) of one scanline:
 //   1. one load fetches the bin heads (and resets them for the next frame),
 //   2. empty bins are cleared in bulk with 128-bit stores (colour 0, depth 0x7F7F7F7F: viewport.cpp:88-113),
@@ -135,6 +143,7 @@ __global__ void __launch_bounds__(FRAG_TPB) k_fragments(DeviceScene s, const Vie
         reinterpret_cast<uint32_t *>(h_counters_out)[threadIdx.x] = reinterpret_cast<const uint32_t *>(pl.counters)[threadIdx.x];
     __shared__ ViewParams vp;                   // per-frame constants staged once per CTA
     __shared__ FrameParams fp;
+    __shared__ FragWarp fwarp[FRAG_ROWS];
     for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += FRAG_TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
     for (int w = threadIdx.x; w < (int)(sizeof(FrameParams) / 4); w += FRAG_TPB) reinterpret_cast<uint32_t *>(&fp)[w] = reinterpret_cast<const uint32_t *>(fpp)[w];
     __syncthreads();
@@ -144,12 +153,15 @@ __global__ void __launch_bounds__(FRAG_TPB) k_fragments(DeviceScene s, const Vie
     const int y = vp.vy + row;
     const int bx0 = blockIdx.x * FRAG_STRETCH;
     const int nb = min(FRAG_STRETCH, vp.nbx - bx0);
-    const Span *spans = pl.spans;
     const uint64_t KEY_INIT = (uint64_t)MAXZ_BITS << 32;
 
     int32_t *headp = pl.bin_head + (size_t)row * vp.nbx + bx0 + lane;
     int32_t head = -1;
-    if (lane < nb) { head = *headp; if (head >= 0) *headp = -1; }
+    if (lane < nb) {
+        head = *headp;
+        if (head >= 0) *headp = -1;
+        pl.bin_used[(size_t)row * vp.nbx + bx0 + lane] = head >= 0;           // occupancy map for the DoF pass
+    }
     unsigned mask = __ballot_sync(0xFFFFFFFFu, head >= 0);
 
     uint32_t *crow = color + (size_t)y * color_pitch + vp.vx + (bx0 << 5);
@@ -171,50 +183,67 @@ __global__ void __launch_bounds__(FRAG_TPB) k_fragments(DeviceScene s, const Vie
             }
         }
     }
-    // ---- non-empty bins ----
-    uint32_t covered = 0;
+    // ---- non-empty bins, pass 1: depth resolve.  lane = pixel; the nearest fragment of every pixel is kept in
+    //      registers, depth is written at once, and the winners of the whole 256-pixel stretch are queued in shared
+    //      memory so that shading (pass 2) runs on dense batches of 32 covered pixels instead of on partly
+    //      covered bins ----
+    FragWarp &fw = fwarp[threadIdx.x >> 5];
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t n_hit = 0;
+    const unsigned used = mask;
     while (mask) {
         const int b = __ffs(mask) - 1;
         mask &= mask - 1;
         int32_t c = __shfl_sync(0xFFFFFFFFu, head, b);
-        const int binx0 = vp.vx + ((bx0 + b) << 5);
-        const int x = binx0 + lane;
-
         uint64_t best = KEY_INIT;
         float best_u = 0.f;
-        uint32_t best_span = 0;
+        uint32_t best_span = 0xFFFFFFFFu;
+        Chunk ch = pl.chunks[c];
         while (c >= 0) {
-            const Chunk ch = pl.chunks[c];
-            const Span sp = spans[ch.span];
-            const int x1 = (int)(sp.x1x2 & 0xFFFFu), x2 = (int)(sp.x1x2 >> 16);
-            if (x >= x1 && x < x2) {
-                const float2 tb = pl.frag_tb[sp.frag_base + (uint32_t)(x - x1)];   // qpixel state, replayed by k_spans
+            c = ch.next;
+            Chunk nxt = ch;
+            if (c >= 0) nxt = pl.chunks[c];                                     // pointer chase overlapped with this chunk's work
+            const int xs = (int)(ch.xs_xe & 0xFFu), xe = (int)(ch.xs_xe >> 8);
+            if (lane >= xs && lane < xe) {
+                const float2 tb = pl.frag_tb[ch.frag0 + (uint32_t)lane];        // qpixel state, replayed by k_spans
                 const float u = fdiv(tb.x, tb.y);                               // progress(), interpolator.hpp:98
-                const float z = fadd(sp.v0, fmul(sp.v1, u));                    // value(0), renderer.cpp:488
+                const float z = fadd(ch.v0, fmul(ch.v1, u));                    // value(0), renderer.cpp:488
                 if (z >= NEAR_Z) {                                              // renderer.cpp:489-492
-                    uint64_t key = ((uint64_t)__float_as_uint(z) << 32) | (sp.slot_flags >> 2);
+                    uint64_t key = ((uint64_t)__float_as_uint(z) << 32) | ch.slot;
                     if (key < best) { best = key; best_u = u; best_span = ch.span; }
                 }
             }
-            c = ch.next;
+            ch = nxt;
         }
-
-        const bool inside = x < vp.vx + vp.vw;
-        const bool hit = best != KEY_INIT;
-        uint32_t out = 0;                                                   // background, viewport.cpp:95-103
-        if (hit) {
-            const uint32_t slot = spans[best_span].slot_flags >> 2;
-            const SlotShade *sh = &pl.shades[slot];
-            const Prim pr = s.prims[sh->prim];
-            out = shade<LIGHT, TEX>(&pl.span_shades[best_span], sh->flat_light, pr, s.texels, vp, fp, best_u);
-        }
-        if (inside) {
-            crow[(b << 5) + lane] = out;
-            drow[(b << 5) + lane] = __uint_as_float((uint32_t)(best >> 32));
-        }
-        if (count_covered) covered += __popc(__ballot_sync(0xFFFFFFFFu, hit && inside));
+        const int px = (b << 5) + lane;
+        const bool inside = px < px_left;
+        const bool hit = best_span != 0xFFFFFFFFu && inside;
+        if (inside) drow[px] = __uint_as_float((uint32_t)(best >> 32));
+        fw.u[px] = best_u; fw.span[px] = hit ? best_span : 0xFFFFFFFFu; fw.slot[px] = (uint32_t)best;
+        const unsigned hm = __ballot_sync(0xFFFFFFFFu, hit);
+        if (hit) fw.idx[n_hit + __popc(hm & lt)] = (uint8_t)px;
+        n_hit += __popc(hm);
     }
-    if (count_covered && lane == 0 && covered) atomicAdd(&pl.counters->n_covered, covered);
+    __syncwarp();
+    // ---- pass 2: shade the queued winners, 32 at a time (deferred: only the visible fragment of a pixel is shaded) ----
+    for (uint32_t k = lane; k < n_hit; k += 32) {
+        const int px = fw.idx[k];
+        const uint32_t span = fw.span[px];
+        const SlotShade *sh = &pl.shades[fw.slot[px]];
+        const Prim pr = s.prims[sh->prim];
+        const uint32_t out = shade<LIGHT, TEX>(&pl.span_shades[span], sh->flat_light, pr, s.texels, vp, fp, fw.u[px]);
+        fw.u[px] = __uint_as_float(out);
+    }
+    __syncwarp();
+    // ---- pass 3: colour write-back, one 128-byte segment per bin (background pixels of a used bin get 0) ----
+    mask = used;
+    while (mask) {
+        const int b = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int px = (b << 5) + lane;
+        if (px < px_left) crow[px] = fw.span[px] != 0xFFFFFFFFu ? __float_as_uint(fw.u[px]) : 0u;
+    }
+    if (count_covered && lane == 0 && n_hit) atomicAdd(&pl.counters->n_covered, n_hit);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -229,73 +258,126 @@ __global__ void __launch_bounds__(FRAG_TPB) k_fragments(DeviceScene s, const Vie
 // packed per-pixel contributions (b | g<<21 | r<<42 in a u64, the tap count in a u32), turns
 // them into a summed-area table with two short serial scans (rows, then columns), and every
 // output pixel is then 4 corner lookups instead of up to 100 taps.  HBM traffic is the
-// algorithmic 12 B/pixel; the 46 % halo over-fetch is served by L2.
+// algorithmic 12 B/pixel; the halo over-fetch (80x41 staged for 64x32 outputs) is served by L2.
+// The blur radius needs no per-pixel division: r(t) is a monotone step function of
+// t = |focal_distance - z|, so the host finds its 5 step positions by exact bisection over the
+// float bit patterns (abi.cu dof_thresholds) and the kernel just compares.
 // ----------------------------------------------------------------------------------------
 static constexpr int DOF_OW = 64, DOF_OH = 32, DOF_LO = 5, DOF_HI = 4;
-static constexpr int DOF_SW = DOF_OW + DOF_LO + DOF_HI;      // 73 source columns
 static constexpr int DOF_SH = DOF_OH + DOF_LO + DOF_HI;      // 41 source rows
-static constexpr int DOF_PW = 75;                            // SAT row stride in entries (col 0 = zero border; odd -> no bank conflicts)
+static constexpr int DOF_X0 = 8;                             // the staged window starts 8 columns left of the tile (16-byte aligned)
+static constexpr int DOF_WW = DOF_OW + 16;                   // 80 staged columns = 20 x 128-bit loads per row
+static constexpr int DOF_PW = DOF_WW + 1;                    // SAT row stride in entries (col 0 = zero border; odd -> no bank conflicts)
 static constexpr int DOF_THREADS = 256;
 
-SB_DEV float blur_factor(float depth, float focal_distance, float focal_depth)
+struct DofClass { uint32_t radius; bool counts; };
+// blur radius and "this pixel is a tap" for depth z, from the host-derived thresholds (common.cuh ViewParams)
+SB_DEV DofClass dof_classify(const ViewParams &vp, float z)
 {
-    // remap_clipped(1.0f, focal_depth, 0.0f, 5.0f, |focal_distance - z|), lerp.hpp:24-43
-    float t = fabsf(fsub(focal_distance, depth));
-    float a = 1.0f, b = focal_depth, xq;
-    if (a == b) xq = 0.5f; else if (t <= a) xq = 0.0f; else if (t >= b) xq = 1.0f; else xq = fdiv(fsub(t, a), fsub(b, a));
-    float r;
-    if (xq <= 0.0f) r = 0.0f; else if (xq >= 5.0f) r = 5.0f; else r = fadd(0.0f, fmul(5.0f, xq));
-    return r;
+    const float t = fabsf(fsub(vp.focal_distance, z));
+    DofClass c;
+    if (vp.dof_const_radius >= 0) { c.radius = (uint32_t)vp.dof_const_radius; c.counts = true; return c; }   // focal_depth == 1
+    c.radius = (t >= vp.dof_t[0]) + (t >= vp.dof_t[1]) + (t >= vp.dof_t[2]) + (t >= vp.dof_t[3]) + (t >= vp.dof_t[4]);
+    c.counts = t > vp.dof_on;
+    return c;
 }
 
-__global__ void __launch_bounds__(DOF_THREADS) k_dof(const ViewParams *__restrict__ vpp, const uint32_t *__restrict__ src, int src_pitch,
-                                                     const float *__restrict__ depth, uint32_t *__restrict__ dst,
-                                                     int dst_pitch, int w, int h, int row0, int row1)
+// constant fill of a tile whose whole window is untouched background (colour 0, depth 0x7F7F7F7F)
+SB_DEV void dof_fill_background(const ViewParams &vp, uint32_t *__restrict__ dst, int dst_pitch, int ox, int oy, int w, int h, int row1, int tid)
 {
-    const float focal_distance = vpp->focal_distance, focal_depth = vpp->focal_depth;
-    __shared__ unsigned long long s64[(DOF_SH + 1) * DOF_PW];
-    __shared__ uint32_t s32[(DOF_SH + 1) * DOF_PW];
-    __shared__ uint8_t srad[DOF_SH * DOF_SW];               // blur radius (0..5) of every staged pixel
-    __shared__ uint32_t magic[128];                          // ceil(2^28 / n): exact v / n for v < 2^15, n <= 100
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ox = blockIdx.x * DOF_OW, oy = row0 + blockIdx.y * DOF_OH;
-
-    // ---- stage the source window: warp `warp` loads rows warp, warp+8, ...; lanes sweep the 73 columns.
-    //      All global loads of a thread are issued before any is consumed (memory-level parallelism).
-    constexpr int ROWS_PER_WARP = (DOF_SH + 7) / 8;         // 6
-    constexpr int COLS_PER_LANE = (DOF_SW + 31) / 32;       // 3
-    float dz[ROWS_PER_WARP][COLS_PER_LANE]; uint32_t cc[ROWS_PER_WARP][COLS_PER_LANE];
-    const float maxz = __uint_as_float(MAXZ_BITS);
-    #pragma unroll
-    for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
-        const int sy = warp + rr * 8, gy = oy + sy - DOF_LO;
-        #pragma unroll
-        for (int cq = 0; cq < COLS_PER_LANE; cq++) {
-            const int sx = lane + cq * 32, gx = ox + sx - DOF_LO;
-            const bool in = sy < DOF_SH && sx < DOF_SW && gx >= 0 && gx < w && gy >= 0 && gy < h;
-            dz[rr][cq] = in ? __ldg(&depth[(size_t)gy * w + gx]) : __int_as_float(0x7FC00000);   // NaN = not a pixel
-            cc[rr][cq] = in ? __ldg(&src[(size_t)gy * src_pitch + gx]) : 0u;
+    const DofClass bgc = dof_classify(vp, __uint_as_float(MAXZ_BITS));
+    // radius 0: copy (0); else every tap counts iff its blur != 0 -> average of zeros with alpha 255, or no taps -> copy
+    const uint32_t v = (bgc.radius != 0 && bgc.counts) ? 0xFF000000u : 0u;
+    const bool vst = ((dst_pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ox + DOF_OW <= w;
+    if (vst) {
+        for (int q = tid; q < DOF_OW * DOF_OH / 4; q += DOF_THREADS) {
+            const int ty = q / (DOF_OW / 4), tx = (q % (DOF_OW / 4)) * 4;
+            const int y = oy + ty;
+            if (y < row1 && y < h) *reinterpret_cast<uint4 *>(dst + (size_t)y * dst_pitch + ox + tx) = make_uint4(v, v, v, v);
         }
-    }
-    // a window that only sees untouched background (colour 0, depth 0x7F7F7F7F) blurs to a constant
-    bool all_bg = true;
-    #pragma unroll
-    for (int rr = 0; rr < ROWS_PER_WARP; rr++)
-        #pragma unroll
-        for (int cq = 0; cq < COLS_PER_LANE; cq++) {
-            const bool pixel = dz[rr][cq] == dz[rr][cq];
-            all_bg = all_bg && (!pixel || (cc[rr][cq] == 0u && __float_as_uint(dz[rr][cq]) == MAXZ_BITS));
-        }
-    if (__syncthreads_and(all_bg)) {
-        const float bf = blur_factor(maxz, focal_distance, focal_depth);
-        const int radius = f2i(bf);
-        // r == 0: copy (0); else every tap counts iff bf != 0 -> average of zeros with alpha 255, or no taps -> copy
-        const uint32_t v = (radius != 0 && bf != 0.0f) ? 0xFF000000u : 0u;
+    } else {
         for (int p = tid; p < DOF_OW * DOF_OH; p += DOF_THREADS) {
             const int ty = p / DOF_OW, tx = p % DOF_OW;
             const int x = ox + tx, y = oy + ty;
             if (y < row1 && y < h && x < w) dst[(size_t)y * dst_pitch + x] = v;
         }
+    }
+}
+
+__global__ void __launch_bounds__(DOF_THREADS) k_dof(const ViewParams *__restrict__ vpp, const uint8_t *__restrict__ bin_used, int nbx,
+                                                     const uint32_t *__restrict__ src, int src_pitch,
+                                                     const float *__restrict__ depth, uint32_t *__restrict__ dst,
+                                                     int dst_pitch, int w, int h, int row0, int row1)
+{
+    __shared__ unsigned long long s64[(DOF_SH + 1) * DOF_PW];
+    __shared__ uint32_t s32[(DOF_SH + 1) * DOF_PW];
+    __shared__ uint8_t srad[DOF_SH * DOF_WW];               // blur radius (0..5) of every staged pixel
+    __shared__ uint32_t magic[128];                          // ceil(2^28 / n): exact v / n for v < 2^15, n <= 100
+    __shared__ ViewParams vp;
+    const int tid = threadIdx.x;
+    const int ox = blockIdx.x * DOF_OW, oy = row0 + blockIdx.y * DOF_OH;
+    for (int k = tid; k < (int)(sizeof(ViewParams) / 4); k += DOF_THREADS) reinterpret_cast<uint32_t *>(&vp)[k] = reinterpret_cast<const uint32_t *>(vpp)[k];
+
+    // ---- k_fragments left one byte per 32-column bin saying whether it drew anything there this frame.  If no bin
+    //      under the window [ox-8, ox+72) x [oy-5, oy+36) did, the window is pure background: no loads at all. ----
+    {
+        const int b0 = max(0, (ox - DOF_X0) >> 5), b1 = min(nbx - 1, (ox - DOF_X0 + DOF_WW - 1) >> 5);
+        const int nbw = b1 - b0 + 1;                         // <= 4
+        bool used = false;
+        for (int i = tid; i < nbw * DOF_SH; i += DOF_THREADS) {
+            const int sy = i / nbw, gy = oy + sy - DOF_LO;
+            if (gy >= 0 && gy < h) used = used || bin_used[(size_t)gy * nbx + b0 + (i - sy * nbw)];
+        }
+        if (!__syncthreads_or(used)) {                       // (the barrier also makes `vp` visible)
+            dof_fill_background(vp, dst, dst_pitch, ox, oy, w, h, row1, tid);
+            return;
+        }
+    }
+
+    // ---- stage the source window [ox-8, ox+72) x [oy-5, oy+36): 20 x 41 quads of 4 pixels, 128-bit loads, all of a
+    //      thread's loads issued before any is consumed.  Needs 16-byte aligned rows (w, pitches multiples of 4). ----
+    constexpr int QPR = DOF_WW / 4, NQ = QPR * DOF_SH;       // 20 quads per row, 820 quads
+    constexpr int QPT = (NQ + DOF_THREADS - 1) / DOF_THREADS;   // 4 per thread
+    const bool vec_ok = ((w | src_pitch | dst_pitch) & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(depth)) & 15) == 0;
+    float4 dz[QPT]; uint4 cc[QPT];
+    uint32_t inmask = 0;                                     // 4 bits per quad: which of its pixels exist
+    #pragma unroll
+    for (int k = 0; k < QPT; k++) {
+        const int qi = tid + k * DOF_THREADS;
+        const int sy = qi / QPR, sxq = qi - sy * QPR;
+        const int gy = oy + sy - DOF_LO, gx = ox - DOF_X0 + 4 * sxq;
+        dz[k] = make_float4(0.f, 0.f, 0.f, 0.f); cc[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (qi < NQ && gy >= 0 && gy < h) {
+            if (vec_ok) {
+                if (gx >= 0 && gx < w) {
+                    dz[k] = __ldg(reinterpret_cast<const float4 *>(depth + (size_t)gy * w + gx));
+                    cc[k] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)gy * src_pitch + gx));
+                    inmask |= 0xFu << (4 * k);
+                }
+            } else {
+                float d4[4] = { 0.f, 0.f, 0.f, 0.f }; uint32_t c4[4] = { 0u, 0u, 0u, 0u };
+                #pragma unroll
+                for (int e = 0; e < 4; e++)
+                    if (gx + e >= 0 && gx + e < w) {
+                        d4[e] = __ldg(&depth[(size_t)gy * w + gx + e]); c4[e] = __ldg(&src[(size_t)gy * src_pitch + gx + e]);
+                        inmask |= 1u << (4 * k + e);
+                    }
+                dz[k] = make_float4(d4[0], d4[1], d4[2], d4[3]); cc[k] = make_uint4(c4[0], c4[1], c4[2], c4[3]);
+            }
+        }
+    }
+    // a window that only sees untouched background (colour 0, depth 0x7F7F7F7F) blurs to a constant
+    bool all_bg = true;
+    #pragma unroll
+    for (int k = 0; k < QPT; k++) {
+        const uint32_t m = (inmask >> (4 * k)) & 0xFu;
+        const bool bg = (cc[k].x | cc[k].y | cc[k].z | cc[k].w) == 0u
+                     && __float_as_uint(dz[k].x) == MAXZ_BITS && __float_as_uint(dz[k].y) == MAXZ_BITS
+                     && __float_as_uint(dz[k].z) == MAXZ_BITS && __float_as_uint(dz[k].w) == MAXZ_BITS;
+        all_bg = all_bg && (m == 0u || (m == 0xFu && bg));
+    }
+    if (__syncthreads_and(all_bg)) {                         // bins were touched, but only by background-coloured pixels
+        dof_fill_background(vp, dst, dst_pitch, ox, oy, w, h, row1, tid);
         return;
     }
 
@@ -303,26 +385,28 @@ __global__ void __launch_bounds__(DOF_THREADS) k_dof(const ViewParams *__restric
     for (int i = tid; i < DOF_PW; i += DOF_THREADS) { s64[i] = 0; s32[i] = 0; }                 // zero row 0
     for (int i = tid; i <= DOF_SH; i += DOF_THREADS) { s64[i * DOF_PW] = 0; s32[i * DOF_PW] = 0; } // zero column 0
     #pragma unroll
-    for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
-        const int sy = warp + rr * 8;
+    for (int k = 0; k < QPT; k++) {
+        const int qi = tid + k * DOF_THREADS;
+        if (qi >= NQ) continue;
+        const int sy = qi / QPR, sx0 = 4 * (qi - sy * QPR);
+        const float d4[4] = { dz[k].x, dz[k].y, dz[k].z, dz[k].w };
+        const uint32_t c4[4] = { cc[k].x, cc[k].y, cc[k].z, cc[k].w };
         #pragma unroll
-        for (int cq = 0; cq < COLS_PER_LANE; cq++) {
-            const int sx = lane + cq * 32;
-            if (sy >= DOF_SH || sx >= DOF_SW) continue;
-            unsigned long long v = 0; uint32_t n = 0; uint32_t rad = 0;
-            if (dz[rr][cq] == dz[rr][cq]) {
-                const float bf = blur_factor(dz[rr][cq], focal_distance, focal_depth);
-                rad = (uint32_t)f2i(bf);
-                if (bf != 0.0f) {
-                    const uint32_t c = cc[rr][cq];
+        for (int e = 0; e < 4; e++) {
+            unsigned long long v = 0; uint32_t n = 0, rad = 0;
+            if ((inmask >> (4 * k + e)) & 1u) {
+                const DofClass dc = dof_classify(vp, d4[e]);
+                rad = dc.radius;
+                if (dc.counts) {
+                    const uint32_t c = c4[e];
                     v = (unsigned long long)(c & 0xFF) | ((unsigned long long)((c >> 8) & 0xFF) << 21)
                       | ((unsigned long long)((c >> 16) & 0xFF) << 42);
                     n = 1;
                 }
             }
-            s64[(sy + 1) * DOF_PW + sx + 1] = v;
-            s32[(sy + 1) * DOF_PW + sx + 1] = n;
-            srad[sy * DOF_SW + sx] = (uint8_t)rad;
+            s64[(sy + 1) * DOF_PW + sx0 + e + 1] = v;
+            s32[(sy + 1) * DOF_PW + sx0 + e + 1] = n;
+            srad[sy * DOF_WW + sx0 + e] = (uint8_t)rad;
         }
     }
     __syncthreads();
@@ -330,13 +414,13 @@ __global__ void __launch_bounds__(DOF_THREADS) k_dof(const ViewParams *__restric
         unsigned long long a = 0; uint32_t n = 0;
         const int base = (tid + 1) * DOF_PW;
         #pragma unroll 8
-        for (int sx = 1; sx <= DOF_SW; sx++) {
+        for (int sx = 1; sx <= DOF_WW; sx++) {
             a += s64[base + sx]; n += s32[base + sx];
             s64[base + sx] = a; s32[base + sx] = n;
         }
     }
     __syncthreads();
-    if (tid < DOF_SW) {                                      // then down each column
+    if (tid < DOF_WW) {                                      // then down each column
         unsigned long long a = 0; uint32_t n = 0;
         const int col = tid + 1;
         #pragma unroll 8
@@ -347,20 +431,21 @@ __global__ void __launch_bounds__(DOF_THREADS) k_dof(const ViewParams *__restric
     }
     __syncthreads();
 
-    // ---- outputs: consecutive lanes take consecutive pixels (conflict-free SAT reads, coalesced stores)
+    // ---- outputs: consecutive lanes take consecutive pixels (conflict-free SAT reads, coalesced stores).
+    //      Staged column of output pixel tx is tx + DOF_X0; its SAT column index is that + 1. ----
     #pragma unroll 2
     for (int p = tid; p < DOF_OW * DOF_OH; p += DOF_THREADS) {
         const int ty = p / DOF_OW, tx = p % DOF_OW;
         const int x = ox + tx, y = oy + ty;
         if (y >= row1 || y >= h || x >= w) continue;
-        const int radius = srad[(ty + DOF_LO) * DOF_SW + tx + DOF_LO];
+        const int radius = srad[(ty + DOF_LO) * DOF_WW + tx + DOF_X0];
         uint32_t out;
         bool have = false;
         if (radius != 0) {
-            // SAT index of source pixel (gx, gy) is (gx - ox + 6, gy - oy + 6); the zero border and the
-            // zeros stored for out-of-viewport pixels implement the max(0,..)/min(w|h,..) clipping
+            // window rows [y-r, y+r) -> SAT rows (ty+5-r, ty+5+r]; columns likewise with the +8 staging offset; the zero
+            // border and the zeros stored for out-of-viewport pixels implement the max(0,..)/min(w|h,..) clipping
             const int J0 = ty + DOF_LO - radius, J1 = ty + DOF_LO + radius;
-            const int I0 = tx + DOF_LO - radius, I1 = tx + DOF_LO + radius;
+            const int I0 = tx + DOF_X0 - radius, I1 = tx + DOF_X0 + radius;
             const uint32_t count = (s32[J1 * DOF_PW + I1] + s32[J0 * DOF_PW + I0])
                                  - (s32[J0 * DOF_PW + I1] + s32[J1 * DOF_PW + I0]);
             if (count) {
@@ -403,12 +488,12 @@ void launch_fragments(const DeviceScene &s, const ViewParams &vp, const ViewPara
 #undef SB_CASE
 }
 
-void launch_dof(const ViewParams *d_vp, const uint32_t *src, int src_pitch, const float *depth, uint32_t *dst, int dst_pitch,
-                int w, int h, int row0, int row1, cudaStream_t st)
+void launch_dof(const ViewParams *d_vp, const uint8_t *bin_used, int nbx, const uint32_t *src, int src_pitch, const float *depth,
+                uint32_t *dst, int dst_pitch, int w, int h, int row0, int row1, cudaStream_t st)
 {
     dim3 grid((w + DOF_OW - 1) / DOF_OW, (row1 - row0 + DOF_OH - 1) / DOF_OH);
     if (grid.x && grid.y)
-        k_dof<<<grid, DOF_THREADS, 0, st>>>(d_vp, src, src_pitch, depth, dst, dst_pitch, w, h, row0, row1);
+        k_dof<<<grid, DOF_THREADS, 0, st>>>(d_vp, bin_used, nbx, src, src_pitch, depth, dst, dst_pitch, w, h, row0, row1);
 }
 
 } // namespace sb

@@ -336,6 +336,7 @@ struct SpanCta {
     float val[6][32];                   // phase A: long x/top/bottom, short x/top/bottom on each scanline
     int x1[32], x2[32], y[32];          // phase B: the spans ...
     float top[32], topstep[32], bottom[32], bottomstep[32];   // ... their qpixel at x1 ...
+    float v0[32], v1[32]; uint32_t slot[32];                  // ... depth plane and draw-order key ...
     uint32_t nchunks[32], cbase[32], fbase[32], seg_incl[32]; // ... and their allocations / segment prefix
 };
 
@@ -460,6 +461,7 @@ __global__ void __launch_bounds__(TPB) k_spans(const ViewParams *__restrict__ vp
             const uint32_t nseg = (nchunks + SPAN_SEG - 1) / SPAN_SEG;
             sh.x1[lane] = x1; sh.x2[lane] = x2; sh.y[lane] = y;
             sh.top[lane] = q.top; sh.topstep[lane] = q.topstep; sh.bottom[lane] = q.bottom; sh.bottomstep[lane] = q.bottomstep;
+            sh.v0[lane] = sp.v0; sh.v1[lane] = sp.v1; sh.slot[lane] = sp.slot_flags >> 2;
             sh.nchunks[lane] = nchunks; sh.cbase[lane] = wbase + c_incl - (room ? nchunks : 0u); sh.fbase[lane] = sp.frag_base;
             sh.seg_incl[lane] = warp_incl_scan(nseg, lane);
         }
@@ -489,11 +491,16 @@ __global__ void __launch_bounds__(TPB) k_spans(const ViewParams *__restrict__ vp
             float2 *ftb = pl.frag_tb + sh.fbase[owner] - o_x1;              // ftb[x] = qpixel (topalpha, bottomalpha) at column x
             const uint32_t span_id = i0 + (uint32_t)owner;
             uint32_t cid = sh.cbase[owner] + c0;
+            const float o_v0 = sh.v0[owner], o_v1 = sh.v1[owner];
+            const uint32_t o_slot = sh.slot[owner], o_fb = sh.fbase[owner];
             for (uint32_t c = c0; c < c1; c++, b++, cid++) {
                 Chunk ch;
-                ch.span = span_id;
+                ch.span = span_id; ch.v0 = o_v0; ch.v1 = o_v1; ch.slot = o_slot; ch.pad = 0;
                 ch.next = atomicExch(&heads[b], (int32_t)cid);              // latency hidden behind the pixel loop below
-                const int xn = min(vp.vx + ((b + 1) << 5), o_x2);           // end of this bin's piece of the span
+                const int binx0 = vp.vx + (b << 5);
+                const int xn = min(binx0 + 32, o_x2);                       // end of this bin's piece of the span
+                ch.frag0 = o_fb + (uint32_t)(binx0 - o_x1);                 // wraps for the span's first bin; lanes < xs never read
+                ch.xs_xe = (uint32_t)(x - binx0) | ((uint32_t)(xn - binx0) << 8);
                 for (; x < xn; x++) {
                     ftb[x] = make_float2(w.top, w.bottom);                  // k_fragments divides: ualpha, interpolator.hpp:98
                     interp_step(w);
