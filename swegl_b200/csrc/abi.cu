@@ -1,5 +1,13 @@
 // abi.cu — the C ABI of include/swegl_b200.h: context, HBM pools, scene upload and the per-frame
 // kernel sequence that replaces swegl::render / swegl::_render (renderer.hpp:27-34, renderer.cpp:77-235).
+//
+// Frame protocol.  Everything that changes per frame or per viewport lives in ONE device block
+//     [ FrameParams | ViewParams | node_world 16/node | node_normal 9/node | lights 4/light ]
+// mirrored by two pinned staging blocks.  begin_frame() only fills the frame part of a staging block;
+// the first render_viewport*() of the frame uploads the whole block with one copy and runs the
+// vertex stage with the world transform, later viewports of the same frame upload just their
+// ViewParams.  The launch sequence therefore has no per-frame kernel arguments and is replayed as a
+// CUDA graph (one per viewport configuration, staging slot and with/without frame upload).
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -23,41 +31,36 @@ struct swegl_b200_ctx {
     float *d_pos = nullptr, *d_nrm = nullptr, *d_uv = nullptr;
     uint32_t *d_vert_node = nullptr, *d_texels = nullptr;
     Tri *d_tris = nullptr; Prim *d_prims = nullptr;
-    float *d_node_world = nullptr, *d_node_normal = nullptr;
     float *d_v_world = nullptr, *d_v_ndc = nullptr, *d_n_world = nullptr; uint8_t *d_yes = nullptr;
-    float4 *d_lights = nullptr; uint32_t lights_cap = 0;
-    // per-frame / per-viewport constants in device memory, fed from double-buffered pinned staging so that a
-    // frame's launch sequence has no per-frame kernel arguments and replays as a CUDA graph
-    ViewParams *d_vp = nullptr; FrameParams *d_fp = nullptr;
+    bool opaque = true;            // every material and texel has alpha 255
+
+    // the frame block
+    uint8_t *d_block = nullptr; size_t block_bytes = 0;
+    size_t off_vp = 0, off_nw = 0, off_nn = 0, off_lights = 0; uint32_t lights_cap = 0;
     struct Slot {
-        float *stage = nullptr;                       // node_world | node_normal | lights
-        FrameParams *fp = nullptr; ViewParams *vp = nullptr; Counters *counters = nullptr;   // pinned
-        cudaEvent_t done = nullptr; bool pending = false;       // last viewport launch that used this slot
-        cudaEvent_t bdone = nullptr; bool bpending = false;     // last begin_frame launch that used this slot
-        cudaGraphExec_t begin_exec = nullptr;
+        uint8_t *block = nullptr; Counters *counters = nullptr;     // pinned
+        cudaEvent_t done = nullptr; bool pending = false;           // last launch that read this slot
     } slots[2];
-    size_t stage_cap = 0;                             // floats per slot
-    int begin_slot = 0, view_slot = 0;
-    struct ViewGraph { int32_t key[11]; cudaGraphExec_t exec[2]; };
+    int next_slot = 0, frame_slot = 0; bool frame_dirty = false;
+    struct ViewGraph { int32_t key[12]; cudaGraphExec_t exec[2]; };
     std::vector<ViewGraph> view_graphs;
     bool graphs_enabled = true;
-    bool opaque = true;            // every material and texel has alpha 255
-    FrameParams fp{};
 
     // pools
     Pools pools{};
     uint32_t slots_cap = 0; size_t bins_cap = 0;
     Counters *h_counters = nullptr;     // pinned
 
-
     // screen
     int sw = 0, sh = 0;
     uint32_t *d_screen = nullptr; float *d_depth = nullptr; uint32_t *d_tmp_color = nullptr;
-    size_t depth_cap = 0;
 
     ViewParams last_vp{}; bool have_vp = false;
     ViewParams dof_cache{}; float dof_cache_depth = 0.f; bool dof_cache_valid = false;   // DoF thresholds per focal_depth
     cudaEvent_t ev[8]{};
+
+    ViewParams *d_vp() const { return reinterpret_cast<ViewParams *>(d_block + off_vp); }
+    FrameParams *d_fp() const { return reinterpret_cast<FrameParams *>(d_block); }
 };
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
@@ -70,13 +73,40 @@ static void drop_graphs(swegl_b200_ctx *ctx)
 {
     for (auto &g : ctx->view_graphs) for (auto &e : g.exec) if (e) cudaGraphExecDestroy(e);
     ctx->view_graphs.clear();
-    for (auto &sl : ctx->slots) if (sl.begin_exec) { cudaGraphExecDestroy(sl.begin_exec); sl.begin_exec = nullptr; }
 }
 
 template <typename T> static cudaError_t dalloc(T *&p, size_t n)
 {
     if (p) { cudaFree(p); p = nullptr; }
     return cudaMalloc((void **)&p, (n ? n : 1) * sizeof(T));
+}
+
+static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// (re)allocate the frame block for the current node count and `lights_cap` point lights
+static int layout_block(swegl_b200_ctx *ctx, uint32_t lights_cap)
+{
+    CK(cudaStreamSynchronize(ctx->stream));
+    drop_graphs(ctx);
+    ctx->lights_cap = lights_cap;
+    ctx->off_vp = align16(sizeof(FrameParams));
+    ctx->off_nw = ctx->off_vp + align16(sizeof(ViewParams));
+    ctx->off_nn = ctx->off_nw + (size_t)64 * ctx->n_nodes;
+    ctx->off_lights = align16(ctx->off_nn + (size_t)36 * ctx->n_nodes);
+    ctx->block_bytes = align16(ctx->off_lights + (size_t)16 * lights_cap);
+    if (ctx->d_block) { cudaFree(ctx->d_block); ctx->d_block = nullptr; }
+    CK(cudaMalloc((void **)&ctx->d_block, ctx->block_bytes));
+    CK(cudaMemset(ctx->d_block, 0, ctx->block_bytes));
+    for (auto &sl : ctx->slots) {
+        if (sl.block) cudaFreeHost(sl.block);
+        sl.block = nullptr; sl.pending = false;
+        CK(cudaMallocHost((void **)&sl.block, ctx->block_bytes));
+        memset(sl.block, 0, ctx->block_bytes);
+    }
+    ctx->ds.node_world = reinterpret_cast<const float *>(ctx->d_block + ctx->off_nw);
+    ctx->ds.node_normal = reinterpret_cast<const float *>(ctx->d_block + ctx->off_nn);
+    ctx->have_frame = false; ctx->frame_dirty = false;
+    return SWEGL_B200_OK;
 }
 
 extern "C" {
@@ -100,15 +130,10 @@ int swegl_b200_create(int device, swegl_b200_ctx **out)
     ctx->stream = ctx->own_stream;
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     cudaMallocHost((void **)&ctx->h_counters, sizeof(Counters));
-    cudaMalloc((void **)&ctx->d_vp, sizeof(ViewParams));
-    cudaMalloc((void **)&ctx->d_fp, sizeof(FrameParams));
     for (auto &sl : ctx->slots) {
-        cudaMallocHost((void **)&sl.fp, sizeof(FrameParams));
-        cudaMallocHost((void **)&sl.vp, sizeof(ViewParams));
         cudaMallocHost((void **)&sl.counters, sizeof(Counters));
         memset(sl.counters, 0, sizeof(Counters));
         cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&sl.bdone, cudaEventDisableTiming);
     }
     cudaMalloc((void **)&ctx->pools.counters, sizeof(Counters));
     *out = ctx;
@@ -120,23 +145,18 @@ void swegl_b200_destroy(swegl_b200_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    drop_graphs(ctx);
     void *ptrs[] = { ctx->d_pos, ctx->d_nrm, ctx->d_uv, ctx->d_vert_node, ctx->d_texels, ctx->d_tris, ctx->d_prims,
-                     ctx->d_node_world, ctx->d_node_normal, ctx->d_v_world, ctx->d_v_ndc, ctx->d_n_world, ctx->d_yes,
-                     ctx->d_lights, ctx->pools.edges, ctx->pools.shades, ctx->pools.spans, ctx->pools.span_shades, ctx->pools.frag_tb, ctx->pools.row_slot,
+                     ctx->d_v_world, ctx->d_v_ndc, ctx->d_n_world, ctx->d_yes, ctx->d_block,
+                     ctx->pools.edges, ctx->pools.shades, ctx->pools.spans, ctx->pools.span_shades, ctx->pools.frag_tb, ctx->pools.row_slot,
                      ctx->pools.chunks, ctx->pools.bin_head, ctx->pools.bin_used, ctx->pools.counters, ctx->d_screen, ctx->d_depth,
                      ctx->d_tmp_color };
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
-    drop_graphs(ctx);
-    if (ctx->d_vp) cudaFree(ctx->d_vp);
-    if (ctx->d_fp) cudaFree(ctx->d_fp);
     for (auto &sl : ctx->slots) {
-        if (sl.stage) cudaFreeHost(sl.stage);
-        if (sl.fp) cudaFreeHost(sl.fp);
-        if (sl.vp) cudaFreeHost(sl.vp);
+        if (sl.block) cudaFreeHost(sl.block);
         if (sl.counters) cudaFreeHost(sl.counters);
         if (sl.done) cudaEventDestroy(sl.done);
-        if (sl.bdone) cudaEventDestroy(sl.bdone);
     }
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -165,30 +185,6 @@ int swegl_b200_free_host(void *p)
     return cudaFreeHost(p) == cudaSuccess ? SWEGL_B200_OK : SWEGL_B200_ERR_CUDA;
 }
 
-static int grow_pools_for(swegl_b200_ctx *ctx, const Counters &c);
-
-// an asynchronous frame that ran out of pool space is incomplete: enlarge the pools so re-issuing it succeeds
-static int check_slot_overflow(swegl_b200_ctx *ctx, swegl_b200_ctx::Slot &sl)
-{
-    if (!sl.pending) return SWEGL_B200_OK;
-    sl.pending = false;
-    if (!sl.counters->overflow) return SWEGL_B200_OK;
-    Counters c = *sl.counters;
-    sl.counters->overflow = 0;
-    int rc = grow_pools_for(ctx, c);
-    if (rc) return rc;
-    return fail(ctx, SWEGL_B200_ERR_CAPACITY, "an asynchronous frame overflowed the span/chunk/fragment pools (now enlarged): render it again");
-}
-
-int swegl_b200_synchronize(swegl_b200_ctx *ctx)
-{
-    if (!ctx) return SWEGL_B200_ERR_ARG;
-    CK(cudaStreamSynchronize(ctx->stream));
-    int rc = SWEGL_B200_OK;
-    for (auto &sl : ctx->slots) { int r = check_slot_overflow(ctx, sl); if (r) rc = r; }
-    return rc;
-}
-
 int swegl_b200_set_timing(swegl_b200_ctx *ctx, int enabled)
 {
     if (!ctx) return SWEGL_B200_ERR_ARG;
@@ -215,6 +211,55 @@ static int ensure_pools(swegl_b200_ctx *ctx, uint32_t rows_cap, uint32_t chunks_
     if (chunks_cap > ctx->pools.chunks_cap) {
         CK(dalloc(ctx->pools.chunks, (size_t)chunks_cap));
         ctx->pools.chunks_cap = chunks_cap;
+    }
+    return SWEGL_B200_OK;
+}
+
+static int grow_pools_for(swegl_b200_ctx *ctx, const Counters &c)
+{
+    uint64_t want_rows = (uint64_t)c.n_rows + c.n_rows / 4 + 1024, want_chunks = (uint64_t)c.n_chunks + c.n_chunks / 4 + 1024;
+    uint64_t want_frags = (uint64_t)c.n_frags + c.n_frags / 4 + 1024;
+    // when rows overflowed, k_spans did not run: chunk / fragment demand is unknown, so at least double them
+    if (c.overflow & 1u) want_chunks = want_chunks > 2 * want_rows ? want_chunks : 2 * want_rows;
+    if (c.overflow & 3u) want_frags = want_frags > 2 * (uint64_t)ctx->pools.frags_cap ? want_frags : 2 * (uint64_t)ctx->pools.frags_cap;
+    if (want_rows > 0xFFFFFFF0ull || want_chunks > 0x7FFFFFF0ull || want_frags > 0xFFFFFFF0ull)
+        return fail(ctx, SWEGL_B200_ERR_CAPACITY, "frame needs more than 2^32 fragments / 2^31 chunks");
+    // bin lists were consumed by k_fragments except for chunks that never got linked: reset them all
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemsetAsync(ctx->pools.bin_head, 0xFF, ctx->bins_cap * 4, ctx->stream));
+    return ensure_pools(ctx, (uint32_t)want_rows, (uint32_t)want_chunks, (uint32_t)want_frags);
+}
+
+// an asynchronous frame that ran out of pool space is incomplete: enlarge the pools so re-issuing it succeeds
+static int check_slot_overflow(swegl_b200_ctx *ctx, swegl_b200_ctx::Slot &sl)
+{
+    if (!sl.pending) return SWEGL_B200_OK;
+    sl.pending = false;
+    if (!sl.counters->overflow) return SWEGL_B200_OK;
+    Counters c = *sl.counters;
+    sl.counters->overflow = 0;
+    int rc = grow_pools_for(ctx, c);
+    if (rc) return rc;
+    return fail(ctx, SWEGL_B200_ERR_CAPACITY, "an asynchronous frame overflowed the span/chunk/fragment pools (now enlarged): render it again");
+}
+
+int swegl_b200_synchronize(swegl_b200_ctx *ctx)
+{
+    if (!ctx) return SWEGL_B200_ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    int rc = SWEGL_B200_OK;
+    for (auto &sl : ctx->slots) { int r = check_slot_overflow(ctx, sl); if (r) rc = r; }
+    return rc;
+}
+
+// wait until the launch that last read this staging slot has finished, and act on its pool overflow
+static int acquire_slot(swegl_b200_ctx *ctx, swegl_b200_ctx::Slot &sl)
+{
+    if (sl.pending) {
+        CK(cudaEventSynchronize(sl.done));
+        int rc = check_slot_overflow(ctx, sl);
+        if (rc == SWEGL_B200_ERR_CAPACITY) ctx->err.clear();     // pools were enlarged; later frames are fine
+        else if (rc) return rc;
     }
     return SWEGL_B200_OK;
 }
@@ -299,7 +344,6 @@ int swegl_b200_upload_scene(swegl_b200_ctx *ctx, const swegl_b200_scene_desc *sc
     CK(dalloc(ctx->d_pos, (size_t)3 * nv)); CK(dalloc(ctx->d_nrm, (size_t)3 * nv)); CK(dalloc(ctx->d_uv, (size_t)2 * nv));
     CK(dalloc(ctx->d_vert_node, (size_t)nv)); CK(dalloc(ctx->d_texels, texels.size()));
     CK(dalloc(ctx->d_tris, (size_t)nt)); CK(dalloc(ctx->d_prims, (size_t)sc->n_primitives));
-    CK(dalloc(ctx->d_node_world, (size_t)16 * sc->n_nodes)); CK(dalloc(ctx->d_node_normal, (size_t)9 * sc->n_nodes));
     CK(dalloc(ctx->d_v_world, (size_t)3 * nv)); CK(dalloc(ctx->d_v_ndc, (size_t)3 * nv)); CK(dalloc(ctx->d_n_world, (size_t)3 * nv));
     CK(dalloc(ctx->d_yes, (size_t)nv));
     CK(cudaMemcpy(ctx->d_pos, sc->positions, (size_t)12 * nv, cudaMemcpyHostToDevice));
@@ -322,9 +366,10 @@ int swegl_b200_upload_scene(swegl_b200_ctx *ctx, const swegl_b200_scene_desc *sc
     ds.n_vertices = nv; ds.n_tris = nt; ds.n_prims = sc->n_primitives; ds.n_nodes = sc->n_nodes;
     ds.pos = ctx->d_pos; ds.nrm = ctx->d_nrm; ds.uv = ctx->d_uv; ds.vert_node = ctx->d_vert_node;
     ds.tris = ctx->d_tris; ds.prims = ctx->d_prims; ds.texels = ctx->d_texels;
-    ds.node_world = ctx->d_node_world; ds.node_normal = ctx->d_node_normal;
     ds.v_world = ctx->d_v_world; ds.v_ndc = ctx->d_v_ndc; ds.n_world = ctx->d_n_world; ds.yes = ctx->d_yes;
     ctx->n_nodes = sc->n_nodes;
+    rc = layout_block(ctx, ctx->lights_cap ? ctx->lights_cap : 8);
+    if (rc) return rc;
     ctx->opaque = opaque;
     ctx->have_scene = true; ctx->have_frame = false; ctx->have_vp = false;
     return SWEGL_B200_OK;
@@ -345,20 +390,8 @@ int swegl_b200_set_screen(swegl_b200_ctx *ctx, int32_t w, int32_t h)
     CK(cudaMemset(ctx->pools.bin_head, 0xFF, bins * 4));
     CK(dalloc(ctx->pools.bin_used, bins));
     CK(cudaMemset(ctx->pools.bin_used, 0, bins));
-    ctx->bins_cap = bins; ctx->depth_cap = n;
+    ctx->bins_cap = bins;
     ctx->sw = w; ctx->sh = h;
-    return SWEGL_B200_OK;
-}
-
-// wait until the launch that last used this staging slot has finished, and act on its pool overflow
-static int acquire_slot(swegl_b200_ctx *ctx, swegl_b200_ctx::Slot &sl)
-{
-    if (sl.pending) {
-        CK(cudaEventSynchronize(sl.done));
-        int rc = check_slot_overflow(ctx, sl);
-        if (rc == SWEGL_B200_ERR_CAPACITY) ctx->err.clear();     // pools were enlarged; later frames are fine
-        else if (rc) return rc;
-    }
     return SWEGL_B200_OK;
 }
 
@@ -369,62 +402,27 @@ int swegl_b200_begin_frame(swegl_b200_ctx *ctx, const swegl_b200_frame_desc *fr)
     if ((ctx->n_nodes && (!fr->node_world || !fr->node_normal)) || (fr->n_point_lights && !fr->point_lights))
         return fail(ctx, SWEGL_B200_ERR_ARG, "begin_frame: null array");
     CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    const size_t nw = (size_t)16 * ctx->n_nodes, nn = (size_t)9 * ctx->n_nodes;
     if (fr->n_point_lights > ctx->lights_cap) {
-        CK(cudaStreamSynchronize(st));
-        drop_graphs(ctx);
-        CK(dalloc(ctx->d_lights, (size_t)fr->n_point_lights + 8));
-        ctx->lights_cap = fr->n_point_lights + 8;
+        int rc = layout_block(ctx, fr->n_point_lights + 8);
+        if (rc) return rc;
     }
-    const size_t nl = (size_t)4 * ctx->lights_cap;
-    if (nw + nn + nl > ctx->stage_cap) {
-        CK(cudaStreamSynchronize(st));
-        drop_graphs(ctx);
-        ctx->stage_cap = nw + nn + nl + 64;
-        for (auto &sl : ctx->slots) {
-            if (sl.stage) cudaFreeHost(sl.stage);
-            CK(cudaMallocHost((void **)&sl.stage, ctx->stage_cap * sizeof(float)));
-        }
-    }
-    // stage the caller's arrays in pinned memory: the call returns without a device sync and the caller may
-    // reuse its buffers immediately; two slots let the host prepare frame i+1 while frame i runs
-    auto &sl = ctx->slots[ctx->begin_slot];
-    ctx->begin_slot ^= 1;
-    if (sl.bpending) { CK(cudaEventSynchronize(sl.bdone)); sl.bpending = false; }
-    memcpy(sl.stage, fr->node_world, nw * 4);
-    memcpy(sl.stage + nw, fr->node_normal, nn * 4);
-    if (fr->n_point_lights) memcpy(sl.stage + nw + nn, fr->point_lights, (size_t)16 * fr->n_point_lights);
-    ctx->fp.ambient = fr->ambient;
-    ctx->fp.sun[0] = fr->sun_dir[0]; ctx->fp.sun[1] = fr->sun_dir[1]; ctx->fp.sun[2] = fr->sun_dir[2];
-    ctx->fp.sun_intensity = fr->sun_intensity;
-    ctx->fp.n_lights = fr->n_point_lights;
-    ctx->fp.lights = ctx->d_lights;
-    *sl.fp = ctx->fp;
-
-    auto issue = [&]() {
-        launch_stage_in(sl.stage, ctx->d_node_world, (uint32_t)nw, ctx->d_node_normal, (uint32_t)nn,
-                        reinterpret_cast<float *>(ctx->d_lights), (uint32_t)nl, sl.fp, ctx->d_fp, st);
-        launch_vertex_world(ctx->ds, st);
-    };
-    if (ctx->graphs_enabled && !ctx->timing) {
-        if (!sl.begin_exec) {
-            cudaGraph_t g = nullptr;
-            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-            issue();
-            CK(cudaStreamEndCapture(st, &g));
-            cudaError_t e = cudaGraphInstantiate(&sl.begin_exec, g, 0);
-            cudaGraphDestroy(g);
-            if (e != cudaSuccess) { ctx->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e); return SWEGL_B200_ERR_CUDA; }
-        }
-        CK(cudaGraphLaunch(sl.begin_exec, st));
-    } else {
-        issue();
-    }
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(sl.bdone, st));
-    sl.bpending = true;
-    ctx->have_frame = true;
+    // stage the caller's arrays in a pinned block: no device work here, the caller may reuse its buffers at once,
+    // and the first render_viewport of the frame uploads the block and computes v_world
+    const int si = ctx->frame_dirty ? ctx->frame_slot : ctx->next_slot;
+    auto &sl = ctx->slots[si];
+    int rc = acquire_slot(ctx, sl);
+    if (rc) return rc;
+    FrameParams fp{};
+    fp.ambient = fr->ambient;
+    fp.sun[0] = fr->sun_dir[0]; fp.sun[1] = fr->sun_dir[1]; fp.sun[2] = fr->sun_dir[2];
+    fp.sun_intensity = fr->sun_intensity;
+    fp.n_lights = fr->n_point_lights;
+    fp.lights = reinterpret_cast<const float4 *>(ctx->d_block + ctx->off_lights);
+    memcpy(sl.block, &fp, sizeof fp);
+    memcpy(sl.block + ctx->off_nw, fr->node_world, (size_t)64 * ctx->n_nodes);
+    memcpy(sl.block + ctx->off_nn, fr->node_normal, (size_t)36 * ctx->n_nodes);
+    if (fr->n_point_lights) memcpy(sl.block + ctx->off_lights, fr->point_lights, (size_t)16 * fr->n_point_lights);
+    ctx->frame_slot = si; ctx->frame_dirty = true; ctx->have_frame = true;
     return SWEGL_B200_OK;
 }
 
@@ -522,30 +520,32 @@ static ViewParams draw_params(const ViewParams &vp, bool dof)
     return d;
 }
 
-// enqueue one viewport's kernel sequence on the stream (no synchronisation: usable under stream capture).
-// `src_vp` is the pinned staging copy of draw_params() that is uploaded to ctx->d_vp first.
-static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const ViewParams &vp, const ViewParams *src_vp, bool dof,
-                           bool count_covered, bool timing, bool sync_counters, Counters *counters_out)
+// enqueue one viewport's work on the stream (no synchronisation: usable under stream capture): upload of the staging
+// slot (whole block when the frame data is new, else just the ViewParams), then the kernel sequence.
+static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const ViewParams &vp, swegl_b200_ctx::Slot &sl, bool with_frame,
+                           bool dof, bool count_covered, bool timing, bool sync_counters, Counters *counters_out)
 {
     cudaStream_t st = ctx->stream;
     uint32_t launches = 0;
     if (timing) cudaEventRecord(ctx->ev[0], st);
-    launch_vertex_view(ctx->ds, src_vp, ctx->d_vp, ctx->pools.counters, st); launches++;
+    if (with_frame) cudaMemcpyAsync(ctx->d_block, sl.block, ctx->block_bytes, cudaMemcpyHostToDevice, st);
+    else cudaMemcpyAsync(ctx->d_block + ctx->off_vp, sl.block + ctx->off_vp, sizeof(ViewParams), cudaMemcpyHostToDevice, st);
+    launch_vertex(ctx->ds, ctx->d_vp(), ctx->pools.counters, with_frame, st); launches++;
     launch_mark(ctx->ds, st); launches++;
     if (timing) cudaEventRecord(ctx->ev[1], st);
-    launch_setup(ctx->ds, ctx->d_vp, ctx->d_fp, ctx->pools, st); launches++;
+    launch_setup(ctx->ds, ctx->d_vp(), ctx->d_fp(), ctx->pools, st); launches++;
     if (timing) cudaEventRecord(ctx->ev[2], st);
-    launch_spans(ctx->d_vp, ctx->pools, st); launches++;
+    launch_spans(ctx->d_vp(), ctx->pools, st); launches++;
     if (timing) cudaEventRecord(ctx->ev[3], st);
     uint32_t *color = dof ? ctx->d_tmp_color - ((size_t)vp.vy * vp.vw + vp.vx) : ctx->d_screen;
     const int color_pitch = dof ? vp.vw : ctx->sw;
     // asynchronous frames publish their counters from inside k_fragments; synchronous ones copy them at the end
-    launch_fragments(ctx->ds, vp, ctx->d_vp, ctx->d_fp, ctx->pools, color, color_pitch, ctx->d_depth, count_covered,
+    launch_fragments(ctx->ds, vp, ctx->d_vp(), ctx->d_fp(), ctx->pools, color, color_pitch, ctx->d_depth, count_covered,
                      sync_counters ? nullptr : counters_out, st); launches++;
     if (timing) cudaEventRecord(ctx->ev[4], st);
     if (dof) {
-        launch_dof(ctx->d_vp, ctx->pools.bin_used, vp.nbx, ctx->d_tmp_color, vp.vw, ctx->d_depth, ctx->d_screen + (size_t)vp.vy * ctx->sw + vp.vx, ctx->sw,
-                   vp.vw, vp.vh, out.band0 - vp.vy, out.band1 - vp.vy, st);
+        launch_dof(ctx->d_vp(), ctx->pools.bin_used, vp.nbx, ctx->d_tmp_color, vp.vw, ctx->d_depth,
+                   ctx->d_screen + (size_t)vp.vy * ctx->sw + vp.vx, ctx->sw, vp.vw, vp.vh, out.band0 - vp.vy, out.band1 - vp.vy, st);
         launches++;
     }
     if (timing) cudaEventRecord(ctx->ev[5], st);
@@ -553,25 +553,46 @@ static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const Vie
     return launches;
 }
 
+// pick the staging slot of this render call and put the ViewParams into it
+static int stage_view(swegl_b200_ctx *ctx, const ViewParams &vp, int &si, bool &with_frame)
+{
+    with_frame = ctx->frame_dirty;
+    si = with_frame ? ctx->frame_slot : ctx->next_slot;
+    auto &sl = ctx->slots[si];
+    int rc = acquire_slot(ctx, sl);          // no-op right after begin_frame acquired it
+    if (rc) return rc;
+    memcpy(sl.block + ctx->off_vp, &vp, sizeof(ViewParams));
+    return SWEGL_B200_OK;
+}
+
+static int finish_view(swegl_b200_ctx *ctx, int si)
+{
+    auto &sl = ctx->slots[si];
+    CK(cudaEventRecord(sl.done, ctx->stream));
+    sl.pending = true;
+    ctx->next_slot = si ^ 1;
+    ctx->frame_dirty = false;
+    return SWEGL_B200_OK;
+}
+
 // asynchronous frame: replay (or first capture) the CUDA graph of this viewport configuration
 static int render_async(swegl_b200_ctx *ctx, const ViewParams &out, bool dof)
 {
     cudaStream_t st = ctx->stream;
-    const int si = ctx->view_slot;
-    ctx->view_slot ^= 1;
-    auto &sl = ctx->slots[si];
-    int rc = acquire_slot(ctx, sl);
-    if (rc) return rc;
     const ViewParams vp = draw_params(out, dof);
-    *sl.vp = vp;
+    int si; bool with_frame;
+    int rc = stage_view(ctx, vp, si, with_frame);
+    if (rc) return rc;
+    auto &sl = ctx->slots[si];
     if (!ctx->graphs_enabled) {
-        issue_view(ctx, out, vp, sl.vp, dof, false, false, false, sl.counters);
+        issue_view(ctx, out, vp, sl, with_frame, dof, false, false, false, sl.counters);
     } else {
-        const int32_t key[11] = { out.vx, out.vy, out.vw, out.vh, out.band0, out.band1, out.light_mode, out.tex_mode, dof ? 1 : 0, ctx->sw, ctx->sh };
+        const int32_t key[12] = { out.vx, out.vy, out.vw, out.vh, out.band0, out.band1, out.light_mode, out.tex_mode, dof ? 1 : 0,
+                                  ctx->sw, ctx->sh, with_frame ? 1 : 0 };
         swegl_b200_ctx::ViewGraph *vg = nullptr;
         for (auto &g : ctx->view_graphs) if (memcmp(g.key, key, sizeof key) == 0) { vg = &g; break; }
         if (!vg) {
-            if (ctx->view_graphs.size() >= 64) { CK(cudaStreamSynchronize(st)); for (auto &g : ctx->view_graphs) for (auto &e : g.exec) if (e) cudaGraphExecDestroy(e); ctx->view_graphs.clear(); }
+            if (ctx->view_graphs.size() >= 64) { CK(cudaStreamSynchronize(st)); drop_graphs(ctx); }
             swegl_b200_ctx::ViewGraph ng{};
             memcpy(ng.key, key, sizeof key);
             ctx->view_graphs.push_back(ng);
@@ -580,7 +601,7 @@ static int render_async(swegl_b200_ctx *ctx, const ViewParams &out, bool dof)
         if (!vg->exec[si]) {
             cudaGraph_t g = nullptr;
             CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-            issue_view(ctx, out, vp, sl.vp, dof, false, false, false, sl.counters);
+            issue_view(ctx, out, vp, sl, with_frame, dof, false, false, false, sl.counters);
             CK(cudaStreamEndCapture(st, &g));
             cudaError_t e = cudaGraphInstantiate(&vg->exec[si], g, 0);
             cudaGraphDestroy(g);
@@ -589,24 +610,7 @@ static int render_async(swegl_b200_ctx *ctx, const ViewParams &out, bool dof)
         CK(cudaGraphLaunch(vg->exec[si], st));
     }
     CK(cudaGetLastError());
-    CK(cudaEventRecord(sl.done, st));
-    sl.pending = true;
-    return SWEGL_B200_OK;
-}
-
-static int grow_pools_for(swegl_b200_ctx *ctx, const Counters &c)
-{
-    uint64_t want_rows = (uint64_t)c.n_rows + c.n_rows / 4 + 1024, want_chunks = (uint64_t)c.n_chunks + c.n_chunks / 4 + 1024;
-    uint64_t want_frags = (uint64_t)c.n_frags + c.n_frags / 4 + 1024;
-    // when rows overflowed, k_spans did not run: chunk / fragment demand is unknown, so at least double them
-    if (c.overflow & 1u) want_chunks = want_chunks > 2 * want_rows ? want_chunks : 2 * want_rows;
-    if (c.overflow & 3u) want_frags = want_frags > 2 * (uint64_t)ctx->pools.frags_cap ? want_frags : 2 * (uint64_t)ctx->pools.frags_cap;
-    if (want_rows > 0xFFFFFFF0ull || want_chunks > 0x7FFFFFF0ull || want_frags > 0xFFFFFFF0ull)
-        return fail(ctx, SWEGL_B200_ERR_CAPACITY, "frame needs more than 2^32 fragments / 2^31 chunks");
-    // bin lists were consumed by k_fragments except for chunks that never got linked: reset them all
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaMemsetAsync(ctx->pools.bin_head, 0xFF, ctx->bins_cap * 4, ctx->stream));
-    return ensure_pools(ctx, (uint32_t)want_rows, (uint32_t)want_chunks, (uint32_t)want_frags);
+    return finish_view(ctx, si);
 }
 
 static int render_common(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v, bool sync, swegl_b200_stats *stats)
@@ -629,18 +633,20 @@ static int render_common(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v,
     // synchronous frame: direct launches, counters checked, pools grown and the frame redone if needed
     const bool timing = ctx->timing && stats;
     const ViewParams vp = draw_params(out, dof);
-    auto &sl = ctx->slots[ctx->view_slot];
     uint32_t grows = 0, launches = 0;
     for (;;) {
-        rc = acquire_slot(ctx, sl);
+        int si; bool with_frame;
+        rc = stage_view(ctx, vp, si, with_frame);
         if (rc) return rc;
-        *sl.vp = vp;
-        launches = issue_view(ctx, out, vp, sl.vp, dof, stats != nullptr, timing, true, ctx->h_counters);
+        launches = issue_view(ctx, out, vp, ctx->slots[si], with_frame, dof, stats != nullptr, timing, true, ctx->h_counters);
         CK(cudaGetLastError());
+        rc = finish_view(ctx, si);
+        if (rc) return rc;
         CK(cudaStreamSynchronize(ctx->stream));
+        ctx->slots[si].pending = false;
         if (!ctx->h_counters->overflow) break;
         if (++grows > 8) return fail(ctx, SWEGL_B200_ERR_CAPACITY, "span/chunk/fragment pools keep overflowing");
-        rc = grow_pools_for(ctx, *ctx->h_counters);
+        rc = grow_pools_for(ctx, *ctx->h_counters);          // the frame data is already on the device: the redo is view-only
         if (rc) return rc;
     }
     if (stats) {

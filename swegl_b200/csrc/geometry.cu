@@ -1,8 +1,8 @@
 // geometry.cu — vertex stage, cull/mark, near clip + triangle setup, edge walk, span setup.
 //
 // Stage map against the reference (paths relative to the swegl checkout):
-//   k_vertex_world  vertex_shader_t::original_to_world            vertex_shaders.hpp:16-33
-//   k_vertex_view   world_to_camera_or_frustum / camera_to_frustum vertex_shaders.hpp:35-52,61-71
+//   k_vertex<W>     vertex_shader_t::original_to_world (W) +      vertex_shaders.hpp:16-33
+//                   world_to_camera_or_frustum / camera_to_frustum vertex_shaders.hpp:35-52,61-71
 //   k_mark          the mark pass of _render                      renderer.cpp:86-185
 //   k_setup         fill_triangle + fill_triangle_2 (edge set-up)  renderer.cpp:240-460
 //   k_spans         the y loop and per-scanline part of fill_half_triangle   renderer.cpp:467-480,553-556
@@ -19,47 +19,28 @@ static constexpr uint32_t SPAN_SEG = 4;      // 32-column bins per span segment 
 // ----------------------------------------------------------------------------------------
 // vertex stage
 // ----------------------------------------------------------------------------------------
-// begin_frame's uploads without DMA nodes: one CTA reads the caller's arrays from the pinned staging slot
-// (zero-copy over PCIe) and writes the device copies every later kernel uses
-__global__ void __launch_bounds__(256) k_stage_in(const float *__restrict__ stage, float *__restrict__ node_world, uint32_t n_world,
-                                                   float *__restrict__ node_normal, uint32_t n_normal,
-                                                   float *__restrict__ lights, uint32_t n_lights_f,
-                                                   const FrameParams *__restrict__ h_fp, FrameParams *__restrict__ d_fp)
-{
-    for (uint32_t i = threadIdx.x; i < n_world; i += 256) node_world[i] = stage[i];
-    for (uint32_t i = threadIdx.x; i < n_normal; i += 256) node_normal[i] = stage[n_world + i];
-    for (uint32_t i = threadIdx.x; i < n_lights_f; i += 256) lights[i] = stage[n_world + n_normal + i];
-    for (uint32_t i = threadIdx.x; i < sizeof(FrameParams) / 4; i += 256)
-        reinterpret_cast<uint32_t *>(d_fp)[i] = reinterpret_cast<const uint32_t *>(h_fp)[i];
-}
-
-__global__ void __launch_bounds__(TPB) k_vertex_world(DeviceScene s)
-{
-    uint32_t i = blockIdx.x * TPB + threadIdx.x;
-    if (i >= s.n_vertices) return;
-    const float *M = s.node_world + 16 * s.vert_node[i];
-    V3 w = xform(M, v3(s.pos[3 * i], s.pos[3 * i + 1], s.pos[3 * i + 2]));
-    s.v_world[3 * i] = w.x; s.v_world[3 * i + 1] = w.y; s.v_world[3 * i + 2] = w.z;
-}
-
-// first kernel of a viewport: reads the ViewParams from the pinned staging slot (zero-copy), publishes the
-// device copy the later kernels use and clears the frame counters -- no memcpy / memset nodes in the graph
-__global__ void __launch_bounds__(TPB) k_vertex_view(DeviceScene s, const ViewParams *__restrict__ h_vp,
-                                                     ViewParams *__restrict__ d_vp, Counters *__restrict__ counters)
+// v_world = M_node * v (A1, once per frame) and, per viewport, camera/projection transform, world normal and the
+// yes reset (A2).  WORLD selects whether this launch is the first of the frame and also has to produce v_world.
+// Block 0 clears the frame counters (no memset node in the graph).
+template <bool WORLD>
+__global__ void __launch_bounds__(TPB) k_vertex(DeviceScene s, const ViewParams *__restrict__ vpp, Counters *__restrict__ counters)
 {
     __shared__ ViewParams vp;
-    for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += TPB) {
-        const uint32_t v = reinterpret_cast<const uint32_t *>(h_vp)[w];
-        reinterpret_cast<uint32_t *>(&vp)[w] = v;
-        if (blockIdx.x == 0) reinterpret_cast<uint32_t *>(d_vp)[w] = v;
-    }
+    for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
     if (blockIdx.x == 0 && threadIdx.x < sizeof(Counters) / 4) reinterpret_cast<uint32_t *>(counters)[threadIdx.x] = 0;
     __syncthreads();
     uint32_t i = blockIdx.x * TPB + threadIdx.x;
     if (i >= s.n_vertices) return;
-    V3 w = v3(s.v_world[3 * i], s.v_world[3 * i + 1], s.v_world[3 * i + 2]);
+    const uint32_t node = s.vert_node[i];
+    V3 w;
+    if (WORLD) {
+        w = xform(s.node_world + 16 * node, v3(s.pos[3 * i], s.pos[3 * i + 1], s.pos[3 * i + 2]));     // vertex_shaders.hpp:20-24
+        s.v_world[3 * i] = w.x; s.v_world[3 * i + 1] = w.y; s.v_world[3 * i + 2] = w.z;
+    } else {
+        w = v3(s.v_world[3 * i], s.v_world[3 * i + 1], s.v_world[3 * i + 2]);
+    }
     V3 p = project(vp.proj, xform(vp.view, w));
-    V3 n = normal_to_world(s.node_normal + 9 * s.vert_node[i], v3(s.nrm[3 * i], s.nrm[3 * i + 1], s.nrm[3 * i + 2]));
+    V3 n = normal_to_world(s.node_normal + 9 * node, v3(s.nrm[3 * i], s.nrm[3 * i + 1], s.nrm[3 * i + 2]));
     s.v_ndc[3 * i] = p.x; s.v_ndc[3 * i + 1] = p.y; s.v_ndc[3 * i + 2] = p.z;
     s.n_world[3 * i] = n.x; s.n_world[3 * i + 1] = n.y; s.n_world[3 * i + 2] = n.z;
     s.yes[i] = 0;
@@ -517,18 +498,11 @@ __global__ void __launch_bounds__(TPB) k_spans(const ViewParams *__restrict__ vp
 // ----------------------------------------------------------------------------------------
 static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
-void launch_vertex_world(const DeviceScene &s, cudaStream_t st)
+void launch_vertex(const DeviceScene &s, const ViewParams *d_vp, Counters *counters, bool with_world, cudaStream_t st)
 {
-    if (s.n_vertices) k_vertex_world<<<cdiv(s.n_vertices, TPB), TPB, 0, st>>>(s);
-}
-void launch_stage_in(const float *stage, float *node_world, uint32_t n_world, float *node_normal, uint32_t n_normal,
-                     float *lights, uint32_t n_lights_f, const FrameParams *h_fp, FrameParams *d_fp, cudaStream_t st)
-{
-    k_stage_in<<<1, 256, 0, st>>>(stage, node_world, n_world, node_normal, n_normal, lights, n_lights_f, h_fp, d_fp);
-}
-void launch_vertex_view(const DeviceScene &s, const ViewParams *h_vp, ViewParams *d_vp, Counters *counters, cudaStream_t st)
-{
-    k_vertex_view<<<max(1u, cdiv(s.n_vertices, TPB)), TPB, 0, st>>>(s, h_vp, d_vp, counters);
+    const unsigned blocks = max(1u, cdiv(s.n_vertices, TPB));
+    if (with_world) k_vertex<true><<<blocks, TPB, 0, st>>>(s, d_vp, counters);
+    else k_vertex<false><<<blocks, TPB, 0, st>>>(s, d_vp, counters);
 }
 void launch_mark(const DeviceScene &s, cudaStream_t st)
 {
