@@ -9,6 +9,7 @@
 // ViewParams.  The launch sequence therefore has no per-frame kernel arguments and is replayed as a
 // CUDA graph (one per viewport configuration, staging slot and with/without frame upload).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -42,9 +43,11 @@ struct swegl_b200_ctx {
         cudaEvent_t done = nullptr; bool pending = false;           // last launch that read this slot
     } slots[2];
     int next_slot = 0, frame_slot = 0; bool frame_dirty = false;
-    struct ViewGraph { int32_t key[12]; cudaGraphExec_t exec[2]; };
+    struct ViewGraph { int32_t key[13]; cudaGraphExec_t exec[2]; };
     std::vector<ViewGraph> view_graphs;
     bool graphs_enabled = true;
+    bool dense_spans = false;           // which span kernel the next frames use (see choose_span_kernel)
+    int span_policy = -1;               // -1 automatic, 0 always k_spans, 1 always k_spans_dense
 
     // pools
     Pools pools{};
@@ -136,6 +139,10 @@ int swegl_b200_create(int device, swegl_b200_ctx **out)
         cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
     }
     cudaMalloc((void **)&ctx->pools.counters, sizeof(Counters));
+    if (const char *e = getenv("SWEGL_B200_SPANS")) {          // "dense" / "coop" pin the span kernel, default: automatic
+        ctx->span_policy = !strcmp(e, "dense") ? 1 : (!strcmp(e, "coop") ? 0 : -1);
+        ctx->dense_spans = ctx->span_policy == 1;
+    }
     *out = ctx;
     return SWEGL_B200_OK;
 }
@@ -230,11 +237,22 @@ static int grow_pools_for(swegl_b200_ctx *ctx, const Counters &c)
     return ensure_pools(ctx, (uint32_t)want_rows, (uint32_t)want_chunks, (uint32_t)want_frags);
 }
 
+// k_spans (6 warps x 32 rows) has the shorter critical path when a few big triangles need long radd() chains;
+// k_spans_dense (thread = row) has ~10x the throughput when there are very many scanlines.  Decide from the
+// scanline count of the most recent frame whose counters are known.
+static void choose_span_kernel(swegl_b200_ctx *ctx, const Counters &c)
+{
+    if (ctx->span_policy >= 0) return;
+    const bool dense = c.n_rows >= 150000u;
+    if (dense != ctx->dense_spans) ctx->dense_spans = dense;      // (the graph key carries the choice)
+}
+
 // an asynchronous frame that ran out of pool space is incomplete: enlarge the pools so re-issuing it succeeds
 static int check_slot_overflow(swegl_b200_ctx *ctx, swegl_b200_ctx::Slot &sl)
 {
     if (!sl.pending) return SWEGL_B200_OK;
     sl.pending = false;
+    choose_span_kernel(ctx, *sl.counters);
     if (!sl.counters->overflow) return SWEGL_B200_OK;
     Counters c = *sl.counters;
     sl.counters->overflow = 0;
@@ -535,7 +553,7 @@ static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const Vie
     if (timing) cudaEventRecord(ctx->ev[1], st);
     launch_setup(ctx->ds, ctx->d_vp(), ctx->d_fp(), ctx->pools, st); launches++;
     if (timing) cudaEventRecord(ctx->ev[2], st);
-    launch_spans(ctx->d_vp(), ctx->pools, st); launches++;
+    launch_spans(ctx->d_vp(), ctx->pools, ctx->dense_spans, st); launches++;
     if (timing) cudaEventRecord(ctx->ev[3], st);
     uint32_t *color = dof ? ctx->d_tmp_color - ((size_t)vp.vy * vp.vw + vp.vx) : ctx->d_screen;
     const int color_pitch = dof ? vp.vw : ctx->sw;
@@ -587,8 +605,8 @@ static int render_async(swegl_b200_ctx *ctx, const ViewParams &out, bool dof)
     if (!ctx->graphs_enabled) {
         issue_view(ctx, out, vp, sl, with_frame, dof, false, false, false, sl.counters);
     } else {
-        const int32_t key[12] = { out.vx, out.vy, out.vw, out.vh, out.band0, out.band1, out.light_mode, out.tex_mode, dof ? 1 : 0,
-                                  ctx->sw, ctx->sh, with_frame ? 1 : 0 };
+        const int32_t key[13] = { out.vx, out.vy, out.vw, out.vh, out.band0, out.band1, out.light_mode, out.tex_mode, dof ? 1 : 0,
+                                  ctx->sw, ctx->sh, with_frame ? 1 : 0, ctx->dense_spans ? 1 : 0 };
         swegl_b200_ctx::ViewGraph *vg = nullptr;
         for (auto &g : ctx->view_graphs) if (memcmp(g.key, key, sizeof key) == 0) { vg = &g; break; }
         if (!vg) {
@@ -644,6 +662,7 @@ static int render_common(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v,
         if (rc) return rc;
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->slots[si].pending = false;
+        choose_span_kernel(ctx, *ctx->h_counters);
         if (!ctx->h_counters->overflow) break;
         if (++grows > 8) return fail(ctx, SWEGL_B200_ERR_CAPACITY, "span/chunk/fragment pools keep overflowing");
         rc = grow_pools_for(ctx, *ctx->h_counters);          // the frame data is already on the device: the redo is view-only

@@ -494,6 +494,172 @@ __global__ void __launch_bounds__(TPB) k_spans(const ViewParams *__restrict__ vp
 }
 
 // ----------------------------------------------------------------------------------------
+// k_spans_dense: the same work with thread = scanline record and 256 records per CTA pass.  Every thread does its
+// six radd() jumps itself (cheap when triangles are small: a handful of real additions), the span set-up runs on all
+// 256 threads, there is one allocation per CTA pass, and the segment phase again gives long spans to many threads.
+// Preferred when scanlines vastly outnumber SMs x warps (small triangles); k_spans (6 warps per 32 rows) keeps the
+// critical path short when a few big triangles have long radd() chains.
+// ----------------------------------------------------------------------------------------
+struct SpanCtaDense {
+    int x1[TPB], x2[TPB], y[TPB];
+    float top[TPB], topstep[TPB], bottom[TPB], bottomstep[TPB];
+    float v0[TPB], v1[TPB]; uint32_t slot[TPB];
+    uint32_t nchunks[TPB], cbase[TPB], fbase[TPB], seg_incl[TPB];
+    uint32_t wsum[3][TPB / 32];          // per-warp totals of the three block scans
+    uint32_t base[2];                    // chunk / fragment-stream allocation of this pass
+    uint32_t room;
+};
+
+__global__ void __launch_bounds__(TPB) k_spans_dense(const ViewParams *__restrict__ vpp, Pools pl)
+{
+    __shared__ SpanCtaDense sh;
+    __shared__ ViewParams vp;
+    for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
+    __syncthreads();
+    if (pl.counters->overflow & 1u) return;
+    const uint32_t n_rows = min(pl.counters->n_rows, pl.rows_cap);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    Span *spans = pl.spans;
+    for (uint32_t i0 = blockIdx.x * TPB; i0 < n_rows; i0 += gridDim.x * TPB) {                  // CTA-uniform
+        const uint32_t i = i0 + tid;
+        uint32_t nchunks = 0, npix = 0;
+        int x1 = 0, x2 = 0, y = 0;
+        Interp q; q.top = q.topstep = q.bottom = q.bottomstep = q.v0 = q.v1 = 0.f;
+        Span sp; sp.frag_base = 0; sp.pad0 = 0; sp.v0 = sp.v1 = sp.pl = sp.pr = 0.f; sp.x1x2 = 0; sp.slot_flags = 0;
+        if (i < n_rows) {
+            const uint32_t slot = pl.row_slot[i];
+            const SlotEdge &e = pl.edges[slot];
+            const int j = (int)i - e.span_base;
+            const int ua = max(e.ya_u, vp.band0), ub = min(e.yb_u, vp.band1);
+            const int nu = max(0, ub - ua);
+            const bool lower = j >= nu;                                     // in-band rows of the upper half come first
+            y = lower ? max(e.ya_l, vp.band0) + (j - nu) : ua + j;
+            const bool lor = lower ? ((e.flags >> 1) & 1u) : (e.flags & 1u);
+            const SideRec S = lower ? e.sl : e.su;
+            const SideRec G = e.lng;
+            // renderer.cpp:553-556 applied (y - first walked row) times
+            const uint32_t kl = (uint32_t)(y - e.y_long), ks = (uint32_t)(y - (lower ? e.ya_l : e.ya_u));
+            const float gx = radd(G.x, G.ratio, kl), gtop = radd(G.top, G.topstep, kl), gbot = radd(G.bottom, G.bottomstep, kl);
+            const float sx = radd(S.x, S.ratio, ks), stop = radd(S.top, S.topstep, ks), sbot = radd(S.bottom, S.bottomstep, ks);
+            const float lx = lor ? sx : gx, rx = lor ? gx : sx;
+            const float ltop = lor ? stop : gtop, lbot = lor ? sbot : gbot, rtop = lor ? gtop : stop, rbot = lor ? gbot : sbot;
+            sp.slot_flags = (slot << 2) | ((uint32_t)lower << 1) | (lor ? 1u : 0u);
+            x1 = max(ceil_i(lx), vp.vx);                                    // renderer.cpp:469-470
+            x2 = min(ceil_i(rx), vp.vx + vp.vw);
+            if (x1 < x2) {
+                const float z0 = e.z0, z1 = e.z1, z2 = e.z2;
+                const float la = lor ? (lower ? z1 : z0) : z0;
+                const float lb = lor ? (lower ? z2 : z1) : z2;
+                const float ra = lor ? z0 : (lower ? z1 : z0);
+                const float rb = lor ? z2 : (lower ? z2 : z1);
+                sp.pl = fdiv(ltop, lbot);
+                sp.pr = fdiv(rtop, rbot);
+                const float zl = fadd(la, fmul(fsub(lb, la), sp.pl));
+                const float zr = fadd(ra, fmul(fsub(rb, ra), sp.pr));
+                interp_init_self(q, fsub(rx, lx), zl, zr);                  // renderer.cpp:476-480
+                interp_displace(q, fsub((float)x1, lx));
+                sp.v0 = q.v0; sp.v1 = q.v1;
+                sp.x1x2 = (uint32_t)x1 | ((uint32_t)x2 << 16);
+                nchunks = (uint32_t)(((x2 - 1 - vp.vx) >> 5) - ((x1 - vp.vx) >> 5) + 1);
+                npix = (uint32_t)(x2 - x1);
+                const SlotShade &ssh = pl.shades[slot];                     // prepare_for_scanline, once per span
+                SpanShade ss;
+                #pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const float w0 = ssh.w0[c], w1 = ssh.w1[c], w2 = ssh.w2[c], m0 = ssh.n0[c], m1 = ssh.n1[c], m2 = ssh.n2[c];
+                    const float lgd = fsub(w2, w0), shb = lower ? w1 : w0, shd = lower ? fsub(w2, w1) : fsub(w1, w0);
+                    const float nlgd = fsub(m2, m0), nshb = lower ? m1 : m0, nshd = lower ? fsub(m2, m1) : fsub(m1, m0);
+                    const float vl = lor ? shb : w0, vld = lor ? shd : lgd, vr = lor ? w0 : shb, vrd = lor ? lgd : shd;
+                    const float nl = lor ? nshb : m0, nld = lor ? nshd : nlgd, nr = lor ? m0 : nshb, nrd = lor ? nlgd : nshd;
+                    ss.v[c] = fadd(vl, fmul(vld, sp.pl));
+                    ss.vdir[c] = fsub(fadd(vr, fmul(vrd, sp.pr)), ss.v[c]);
+                    ss.n[c] = fadd(nl, fmul(nld, sp.pl));
+                    ss.ndir[c] = fsub(fadd(nr, fmul(nrd, sp.pr)), ss.n[c]);
+                }
+                #pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    const float a0 = ssh.t0[c], a1 = ssh.t1[c], a2 = ssh.t2[c];
+                    const float lgd = fsub(a2, a0), shb = lower ? a1 : a0, shd = lower ? fsub(a2, a1) : fsub(a1, a0);
+                    const float tl = lor ? shb : a0, tld = lor ? shd : lgd, tr = lor ? a0 : shb, trd = lor ? lgd : shd;
+                    ss.t_left[c] = fadd(tl, fmul(tld, sp.pl));
+                    ss.t_dir[c] = fsub(fadd(tr, fmul(trd, sp.pr)), ss.t_left[c]);
+                }
+                pl.span_shades[i] = ss;
+            }
+        }
+        // ---- block-wide exclusive scans of chunks / pixels / segments; one allocation per pass ----
+        const uint32_t nseg = (nchunks + SPAN_SEG - 1) / SPAN_SEG;
+        const uint32_t c_incl = warp_incl_scan(nchunks, lane), p_incl = warp_incl_scan(npix, lane), s_incl = warp_incl_scan(nseg, lane);
+        if (lane == 31) { sh.wsum[0][warp] = c_incl; sh.wsum[1][warp] = p_incl; sh.wsum[2][warp] = s_incl; }
+        __syncthreads();
+        uint32_t c_off = 0, p_off = 0, s_off = 0, c_tot = 0, p_tot = 0;
+        #pragma unroll
+        for (int w = 0; w < TPB / 32; w++) {
+            const uint32_t a = sh.wsum[0][w], b = sh.wsum[1][w], c = sh.wsum[2][w];
+            if (w < warp) { c_off += a; p_off += b; s_off += c; }
+            c_tot += a; p_tot += b;
+        }
+        if (tid == 0) {
+            uint32_t wb = 0, fb = 0;
+            if (c_tot) { wb = atomicAdd(&pl.counters->n_chunks, c_tot); fb = atomicAdd(&pl.counters->n_frags, p_tot); }
+            const bool room = wb + c_tot <= pl.chunks_cap && fb + p_tot <= pl.frags_cap;
+            if (!room) atomicOr(&pl.counters->overflow, (wb + c_tot > pl.chunks_cap ? 2u : 0u) | (fb + p_tot > pl.frags_cap ? 4u : 0u));
+            sh.base[0] = wb; sh.base[1] = fb; sh.room = room ? 1u : 0u;
+        }
+        __syncthreads();
+        const bool room = sh.room != 0;
+        sp.frag_base = sh.base[1] + p_off + p_incl - npix;
+        if (i < n_rows) spans[i] = sp;
+        sh.x1[tid] = x1; sh.x2[tid] = x2; sh.y[tid] = y;
+        sh.top[tid] = q.top; sh.topstep[tid] = q.topstep; sh.bottom[tid] = q.bottom; sh.bottomstep[tid] = q.bottomstep;
+        sh.v0[tid] = sp.v0; sh.v1[tid] = sp.v1; sh.slot[tid] = sp.slot_flags >> 2;
+        sh.nchunks[tid] = room ? nchunks : 0u; sh.cbase[tid] = sh.base[0] + c_off + c_incl - nchunks; sh.fbase[tid] = sp.frag_base;
+        sh.seg_incl[tid] = room ? s_off + s_incl : 0u;
+        __syncthreads();
+        // ---- thread = segment of SPAN_SEG bins, as in k_spans ----
+        const uint32_t total = sh.seg_incl[TPB - 1];
+        for (uint32_t t = tid; t < total; t += TPB) {
+            int owner = 0;                                                  // first row whose inclusive prefix exceeds t
+            #pragma unroll
+            for (int stp = TPB / 2; stp >= 1; stp >>= 1)
+                if (sh.seg_incl[owner + stp - 1] <= t) owner += stp;
+            const uint32_t o_nch = sh.nchunks[owner];
+            const uint32_t sg = t - (sh.seg_incl[owner] - (o_nch + SPAN_SEG - 1) / SPAN_SEG);
+            const uint32_t c0 = sg * SPAN_SEG, c1 = min(o_nch, c0 + SPAN_SEG);
+            const int o_x1 = sh.x1[owner], o_x2 = sh.x2[owner];
+            int b = ((o_x1 - vp.vx) >> 5) + (int)c0;
+            int x = c0 == 0 ? o_x1 : vp.vx + (b << 5);
+            const uint32_t steps = (uint32_t)(x - o_x1);
+            Interp w;
+            w.topstep = sh.topstep[owner]; w.bottomstep = sh.bottomstep[owner];
+            w.top = radd(sh.top[owner], w.topstep, steps);
+            w.bottom = radd(sh.bottom[owner], w.bottomstep, steps);
+            int32_t *heads = pl.bin_head + (size_t)(sh.y[owner] - vp.vy) * vp.nbx;
+            float2 *ftb = pl.frag_tb + sh.fbase[owner] - o_x1;
+            const uint32_t span_id = i0 + (uint32_t)owner;
+            uint32_t cid = sh.cbase[owner] + c0;
+            const float o_v0 = sh.v0[owner], o_v1 = sh.v1[owner];
+            const uint32_t o_slot = sh.slot[owner], o_fb = sh.fbase[owner];
+            for (uint32_t c = c0; c < c1; c++, b++, cid++) {
+                Chunk ch;
+                ch.span = span_id; ch.v0 = o_v0; ch.v1 = o_v1; ch.slot = o_slot; ch.pad = 0;
+                ch.next = atomicExch(&heads[b], (int32_t)cid);
+                const int binx0 = vp.vx + (b << 5);
+                const int xn = min(binx0 + 32, o_x2);
+                ch.frag0 = o_fb + (uint32_t)(binx0 - o_x1);
+                ch.xs_xe = (uint32_t)(x - binx0) | ((uint32_t)(xn - binx0) << 8);
+                for (; x < xn; x++) {
+                    ftb[x] = make_float2(w.top, w.bottom);
+                    interp_step(w);
+                }
+                pl.chunks[cid] = ch;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ----------------------------------------------------------------------------------------
 // launchers
 // ----------------------------------------------------------------------------------------
 static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
@@ -512,9 +678,10 @@ void launch_setup(const DeviceScene &s, const ViewParams *d_vp, const FrameParam
 {
     if (s.n_tris) k_setup<<<cdiv(s.n_tris, 128), 128, 0, st>>>(s, d_vp, d_fp, p);
 }
-void launch_spans(const ViewParams *d_vp, const Pools &p, cudaStream_t st)
+void launch_spans(const ViewParams *d_vp, const Pools &p, bool dense, cudaStream_t st)
 {
-    k_spans<<<148 * 16, TPB, 0, st>>>(d_vp, p);      // persistent CTAs, 32 scanline records per pass
+    if (dense) k_spans_dense<<<148 * 8, TPB, 0, st>>>(d_vp, p);      // persistent CTAs, 256 scanline records per pass
+    else k_spans<<<148 * 16, TPB, 0, st>>>(d_vp, p);                 // persistent CTAs, 32 scanline records per pass
 }
 
 } // namespace sb
