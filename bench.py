@@ -297,7 +297,7 @@ def sharded_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
         r.begin_frame(scene, nodes)
         r.render_device(desc, stats=False)
         if world > 1:
-            return sharding.gather_bands(full[vp.y + y0: vp.y + y1, vp.x: vp.x + vp.w], vp.h, vp.w, dist, dst=0)
+            return sharding.gather_bands_inplace(full, vp.h, dist, dst=0)      # bands land in place in rank 0's screen
         return full
     r.begin_frame(scene, nodes)
     r.render_device(desc, stats=True)                   # sizes the pools for this workload
@@ -351,6 +351,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — swegl_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    # stdout carries exactly one JSON line: NCCL's version banner / debug output goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from swegl_b200 import Renderer

@@ -216,8 +216,10 @@ SB_DEV RowRange emit_slot(const DeviceScene &s, const ViewParams &vp, const Fram
         sh.flat_light = fmul(fadd(fadd(fp.ambient, sun), dyn), 65536.0f);
     }
     sh.prim = prim_id;
+    // plain colour shaders never sample the texture: alpha is the material's (pixel_shaders.hpp:28)
+    sh.alpha_class = vp.tex_mode == SWEGL_B200_TEX_PLAIN ? ((pr.color >> 24) == 255u ? ALPHA_OPAQUE : ALPHA_UNIFORM) : pr.alpha_class;
     #pragma unroll
-    for (int k = 0; k < 6; k++) sh.pad[k] = 0;
+    for (int k = 0; k < 5; k++) sh.pad[k] = 0;
     pl.shades[slot] = sh;
 
     atomicAdd(&pl.counters->n_slots, 1u);
@@ -317,7 +319,7 @@ struct SpanCta {
     float val[6][32];                   // phase A: long x/top/bottom, short x/top/bottom on each scanline
     int x1[32], x2[32], y[32];          // phase B: the spans ...
     float top[32], topstep[32], bottom[32], bottomstep[32];   // ... their qpixel at x1 ...
-    float v0[32], v1[32]; uint32_t slot[32];                  // ... depth plane and draw-order key ...
+    float v0[32], v1[32]; uint32_t slot[32], aclass[32];      // ... depth plane, draw-order key, alpha class ...
     uint32_t nchunks[32], cbase[32], fbase[32], seg_incl[32]; // ... and their allocations / segment prefix
 };
 
@@ -443,6 +445,7 @@ __global__ void __launch_bounds__(TPB) k_spans(const ViewParams *__restrict__ vp
             sh.x1[lane] = x1; sh.x2[lane] = x2; sh.y[lane] = y;
             sh.top[lane] = q.top; sh.topstep[lane] = q.topstep; sh.bottom[lane] = q.bottom; sh.bottomstep[lane] = q.bottomstep;
             sh.v0[lane] = sp.v0; sh.v1[lane] = sp.v1; sh.slot[lane] = sp.slot_flags >> 2;
+            sh.aclass[lane] = (i < n_rows && nchunks) ? pl.shades[sp.slot_flags >> 2].alpha_class : 0u;
             sh.nchunks[lane] = nchunks; sh.cbase[lane] = wbase + c_incl - (room ? nchunks : 0u); sh.fbase[lane] = sp.frag_base;
             sh.seg_incl[lane] = warp_incl_scan(nseg, lane);
         }
@@ -473,10 +476,10 @@ __global__ void __launch_bounds__(TPB) k_spans(const ViewParams *__restrict__ vp
             const uint32_t span_id = i0 + (uint32_t)owner;
             uint32_t cid = sh.cbase[owner] + c0;
             const float o_v0 = sh.v0[owner], o_v1 = sh.v1[owner];
-            const uint32_t o_slot = sh.slot[owner], o_fb = sh.fbase[owner];
+            const uint32_t o_slot = sh.slot[owner], o_fb = sh.fbase[owner], o_ac = sh.aclass[owner];
             for (uint32_t c = c0; c < c1; c++, b++, cid++) {
                 Chunk ch;
-                ch.span = span_id; ch.v0 = o_v0; ch.v1 = o_v1; ch.slot = o_slot; ch.pad = 0;
+                ch.span = span_id; ch.v0 = o_v0; ch.v1 = o_v1; ch.slot = o_slot; ch.alpha_class = o_ac;
                 ch.next = atomicExch(&heads[b], (int32_t)cid);              // latency hidden behind the pixel loop below
                 const int binx0 = vp.vx + (b << 5);
                 const int xn = min(binx0 + 32, o_x2);                       // end of this bin's piece of the span
@@ -503,7 +506,7 @@ __global__ void __launch_bounds__(TPB) k_spans(const ViewParams *__restrict__ vp
 struct SpanCtaDense {
     int x1[TPB], x2[TPB], y[TPB];
     float top[TPB], topstep[TPB], bottom[TPB], bottomstep[TPB];
-    float v0[TPB], v1[TPB]; uint32_t slot[TPB];
+    float v0[TPB], v1[TPB]; uint32_t slot[TPB], aclass[TPB];
     uint32_t nchunks[TPB], cbase[TPB], fbase[TPB], seg_incl[TPB];
     uint32_t wsum[3][TPB / 32];          // per-warp totals of the three block scans
     uint32_t base[2];                    // chunk / fragment-stream allocation of this pass
@@ -613,6 +616,7 @@ __global__ void __launch_bounds__(TPB) k_spans_dense(const ViewParams *__restric
         sh.x1[tid] = x1; sh.x2[tid] = x2; sh.y[tid] = y;
         sh.top[tid] = q.top; sh.topstep[tid] = q.topstep; sh.bottom[tid] = q.bottom; sh.bottomstep[tid] = q.bottomstep;
         sh.v0[tid] = sp.v0; sh.v1[tid] = sp.v1; sh.slot[tid] = sp.slot_flags >> 2;
+        sh.aclass[tid] = (i < n_rows && nchunks) ? pl.shades[sp.slot_flags >> 2].alpha_class : 0u;
         sh.nchunks[tid] = room ? nchunks : 0u; sh.cbase[tid] = sh.base[0] + c_off + c_incl - nchunks; sh.fbase[tid] = sp.frag_base;
         sh.seg_incl[tid] = room ? s_off + s_incl : 0u;
         __syncthreads();
@@ -639,10 +643,10 @@ __global__ void __launch_bounds__(TPB) k_spans_dense(const ViewParams *__restric
             const uint32_t span_id = i0 + (uint32_t)owner;
             uint32_t cid = sh.cbase[owner] + c0;
             const float o_v0 = sh.v0[owner], o_v1 = sh.v1[owner];
-            const uint32_t o_slot = sh.slot[owner], o_fb = sh.fbase[owner];
+            const uint32_t o_slot = sh.slot[owner], o_fb = sh.fbase[owner], o_ac = sh.aclass[owner];
             for (uint32_t c = c0; c < c1; c++, b++, cid++) {
                 Chunk ch;
-                ch.span = span_id; ch.v0 = o_v0; ch.v1 = o_v1; ch.slot = o_slot; ch.pad = 0;
+                ch.span = span_id; ch.v0 = o_v0; ch.v1 = o_v1; ch.slot = o_slot; ch.alpha_class = o_ac;
                 ch.next = atomicExch(&heads[b], (int32_t)cid);
                 const int binx0 = vp.vx + (b << 5);
                 const int xn = min(binx0 + 32, o_x2);

@@ -29,10 +29,32 @@ def frames_for_rank(n_frames, world, rank):
     return list(range(rank, n_frames, world))
 
 
+def gather_bands_inplace(frame, height, dist, dst=0):
+    """Copy-free gather for the common case: `frame` is every rank's full (height, width) screen tensor (contiguous),
+    rank r has rendered rows band_rows(height, world, r) of it.  On return rank `dst`'s tensor holds the whole frame:
+    each peer's band is received straight into its place (one NCCL send/recv pair per peer, batched)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if world == 1:
+        return frame
+    ops = []
+    if rank == dst:
+        for r in range(world):
+            if r != dst:
+                y0, y1 = band_rows(height, world, r)
+                ops.append(dist.P2POp(dist.irecv, frame[y0:y1], r))
+    else:
+        y0, y1 = band_rows(height, world, rank)
+        ops.append(dist.P2POp(dist.isend, frame[y0:y1], dst))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    return frame if rank == dst else None
+
+
 def gather_bands(local_rows, height, width, dist, dst=0):
     """Gather every rank's band (a (rows, width) uint32/int32 tensor for band_rows(height, world, rank)) to `dst`.
     Returns the assembled (height, width) frame on dst, None elsewhere.  Bands may differ by one row, so the
-    payload is padded to the largest band and trimmed on arrival."""
+    payload is padded to the largest band and trimmed on arrival.  (General form; gather_bands_inplace avoids
+    the staging copies when every rank holds a full-size frame buffer.)"""
     import torch
     world, rank = dist.get_world_size(), dist.get_rank()
     max_rows = -(-height // world)

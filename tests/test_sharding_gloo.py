@@ -26,6 +26,12 @@ def _worker(rank, world, port, out_path):
     o = Oracle().render(scene, vp, screen_wh=screen)
     band = torch.from_numpy(o["pixels"][y0:y1].view(np.int32).copy())
     frame = sharding.gather_bands(band, vp.h, vp.w, dist, dst=0)
+    # the copy-free variant: every rank holds a full-size frame with only its band rendered
+    mine = torch.zeros((vp.h, vp.w), dtype=torch.int32)
+    mine[y0:y1] = band
+    inplace = sharding.gather_bands_inplace(mine, vp.h, dist, dst=0)
+    if rank == 0:
+        assert torch.equal(inplace, frame)
     frames = sharding.frames_for_rank(7, world, rank)
     counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(counts, torch.tensor([len(frames)], dtype=torch.int64))
