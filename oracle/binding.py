@@ -223,6 +223,29 @@ class Ref:
             s.textures.append(tex)
         return s
 
+    def procedural_scene(self) -> Scene:
+        """test_1.cpp's build_scene() flavour from the reference's own mesh builders (src/data/model.cpp):
+        torus (triangle strips), cube (fans, node scale.x = 2), textured sphere, three stacked triangles whose
+        materials tests make transparent.  All materials opaque here; see configs.with_transparency."""
+        from swegl_b200.scene import lcg_texture
+        h = self.new_scene()
+        tex = lcg_texture(64, seed=99)
+        self.lib.ref_scene_add_texture(h, tex.ctypes.data, 64, 64)
+        mats = [(128, 128, 128, 255, 0), (128, 128, 255, 255, -1), (255, 128, 255, 255, -1),
+                (128, 128, 255, 255, -1), (128, 255, 128, 255, -1), (255, 128, 128, 255, -1)]
+        for b, g, r, a, t in mats:
+            self.lib.ref_scene_add_material(h, b, g, r, a, 1.0, 1.0, t, 0)
+        f3 = lambda *v: (C.c_float * 3)(*v)
+        self.lib.ref_scene_add_builtin(h, 2, 24, 1.0, 0, None, f3(0, 0, 0.5), f3(0, 0, -2.5))      # tore
+        self.lib.ref_scene_add_builtin(h, 1, 0, 1.0, 0, f3(2, 1, 1), None, f3(0, 0, 0))             # cube, scale.x = 2
+        self.lib.ref_scene_add_builtin(h, 3, 16, 2.0, 2, None, None, f3(3, 0, -1))                  # sphere
+        self.lib.ref_scene_add_builtin(h, 0, 0, 1.0, 3, None, None, f3(1, 0.5, 2.1))                # tri
+        self.lib.ref_scene_add_builtin(h, 0, 0, 1.0, 4, None, None, f3(1, 0.5, 2.0))
+        self.lib.ref_scene_add_builtin(h, 0, 0, 1.0, 5, None, None, f3(1, 0.5, 2.2))
+        s = self.export(h, "procedural")
+        self.lib.ref_scene_free(h)
+        return s
+
     def node_matrices(self, h, n_nodes):
         w = np.zeros((n_nodes, 4, 4), np.float32)
         n = np.zeros((n_nodes, 3, 3), np.float32)

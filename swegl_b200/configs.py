@@ -150,3 +150,29 @@ def build(name, light_mode=_abi.LIGHT_PHONG, tex_mode=_abi.TEX_BILINEAR):
         vp.pose = v["pose"]
         vps.append(vp)
     return s, vps, cfg["screen"], cfg
+
+
+POSE_PROCEDURAL = [("translate", 1, 2, 6), ("rotate_y", 3.0), ("rotate_x", -0.3)]      # torus / cube / sphere, strips and fans
+# the three stacked (transparent) triangles in front of the cube: 1, 2 and 3 layers deep per pixel
+POSE_LAYERS = [("translate", 1.3, 1.2, -4), ("rotate_y", 0.1), ("rotate_x", -0.1)]
+POSE_LAYERS_CLOSE = [("translate", 1.5, 1, -3)]
+
+
+def procedural(alpha=255, tex_alpha=False):
+    """a fresh (uncached) copy of assets/procedural.scenepack with transparency applied"""
+    return with_transparency(Scene.load_pack(os.path.join(ASSETS, "procedural.scenepack")), alpha, tex_alpha)
+
+
+def with_transparency(scene, alpha, tex_alpha=False):
+    """the `procedural` scene with its three stacked triangles' materials (3..5) at `alpha`, and optionally a
+    texture whose texels alternate alpha 255 / 90 in 8x8 blocks (per-fragment opaque/transparent decision)."""
+    scene.mat_bgra = scene.mat_bgra.copy()
+    scene.mat_bgra[3:6, 3] = alpha
+    if tex_alpha:
+        t = scene.textures[0]
+        yy, xx = np.mgrid[0:t.shape[0], 0:t.shape[1]]
+        a = np.where(((xx // 8 + yy // 8) & 1) == 1, 255, 90).astype(np.uint32)
+        scene.textures[0] = ((t & np.uint32(0x00FFFFFF)) | (a << np.uint32(24))).astype(np.uint32)
+        scene.mat_bgra[0, 3] = 200                  # the textured material itself is not what decides: the texel is
+    scene.set_lights(0.2, (1.0, -1.0, -1.0), 0.3, POINT_LIGHTS)
+    return scene

@@ -303,11 +303,12 @@ int swegl_b200_upload_scene(swegl_b200_ctx *ctx, const swegl_b200_scene_desc *sc
         n_texels += (size_t)tx.width * tx.height;
     }
     std::vector<uint32_t> texels(n_texels + sc->n_materials + 1);
+    std::vector<uint8_t> tex_opaque(sc->n_textures, 1);
     for (uint32_t t = 0; t < sc->n_textures; t++) {
         const auto &tx = sc->textures[t];
         size_t n = (size_t)tx.width * tx.height;
         memcpy(&texels[tex_off[t]], tx.texels, n * 4);
-        for (size_t i = 0; i < n && opaque; i++) if ((tx.texels[i] >> 24) != 255) opaque = false;
+        for (size_t i = 0; i < n; i++) if ((tx.texels[i] >> 24) != 255) { tex_opaque[t] = 0; opaque = false; break; }
     }
     auto mat_color = [](const swegl_b200_material &m) {
         return (uint32_t)m.b | ((uint32_t)m.g << 8) | ((uint32_t)m.r << 16) | ((uint32_t)m.a << 24);
@@ -337,9 +338,11 @@ int swegl_b200_upload_scene(swegl_b200_ctx *ctx, const swegl_b200_scene_desc *sc
         if (sp.material_id == -1 || m.texture_idx == -1) {                           // pixel_shaders.cpp:288-294
             d.tex_off = (uint32_t)(n_texels + (sp.material_id >= 0 ? (uint32_t)sp.material_id : sc->n_materials));
             d.tw = 1; d.th = 1;
+            d.alpha_class = m.a == 255 ? ALPHA_OPAQUE : ALPHA_UNIFORM;               // a filtered 1x1 texel keeps alpha 255 / < 255
         } else {
             d.tex_off = tex_off[m.texture_idx];
             d.tw = sc->textures[m.texture_idx].width; d.th = sc->textures[m.texture_idx].height;
+            d.alpha_class = tex_opaque[m.texture_idx] ? ALPHA_OPAQUE : ALPHA_PER_FRAGMENT;
         }
         d.tw_mask = (d.tw & (d.tw - 1)) == 0 ? d.tw - 1 : -1;
         d.th_mask = (d.th & (d.th - 1)) == 0 ? d.th - 1 : -1;
@@ -498,10 +501,16 @@ static int build_view(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v, Vi
         return fail(ctx, SWEGL_B200_ERR_ARG, "viewport rectangle outside the screen (call set_screen first)");
     if (v->light_mode < 0 || v->light_mode > 2 || v->tex_mode < 0 || v->tex_mode > 2 || v->post_mode < 0 || v->post_mode > 1)
         return fail(ctx, SWEGL_B200_ERR_ARG, "bad shader / post mode");
-    if (v->transparency_layers > 0 && !ctx->opaque)
+    // transparency layers only change the frame when something can be non-opaque (renderer.cpp:505)
+    const int n_layers = (v->transparency_layers > 0 && !ctx->opaque) ? v->transparency_layers : 0;
+    if (n_layers > 8)
+        return fail(ctx, SWEGL_B200_ERR_UNSUPPORTED, "more than 8 transparency layers");
+    if (n_layers > 0 && (v->x != 0 || v->y != 0))
         return fail(ctx, SWEGL_B200_ERR_UNSUPPORTED,
-                    "transparency layers with non-opaque materials/texels are not on the device yet (SURVEY §8f N1)");
+                    "transparency layers on a viewport that is not at the screen origin: viewport_t::flatten (viewport.cpp:62) "
+                    "blends against screen rows/columns counted from 0, i.e. against another viewport's pixels");
     memset(&vp, 0, sizeof vp);
+    vp.n_layers = n_layers;
     memcpy(vp.view, v->view, sizeof vp.view);
     memcpy(vp.proj, v->proj, sizeof vp.proj);
     memcpy(vp.cam, v->cam_pos, sizeof vp.cam);
@@ -558,8 +567,9 @@ static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const Vie
     uint32_t *color = dof ? ctx->d_tmp_color - ((size_t)vp.vy * vp.vw + vp.vx) : ctx->d_screen;
     const int color_pitch = dof ? vp.vw : ctx->sw;
     // asynchronous frames publish their counters from inside k_fragments; synchronous ones copy them at the end
-    launch_fragments(ctx->ds, vp, ctx->d_vp(), ctx->d_fp(), ctx->pools, color, color_pitch, ctx->d_depth, count_covered,
-                     sync_counters ? nullptr : counters_out, st); launches++;
+    (vp.n_layers > 0 ? launch_fragments_layers : launch_fragments)(ctx->ds, vp, ctx->d_vp(), ctx->d_fp(), ctx->pools, color, color_pitch,
+                                                                    ctx->d_depth, count_covered, sync_counters ? nullptr : counters_out, st);
+    launches++;
     if (timing) cudaEventRecord(ctx->ev[4], st);
     if (dof) {
         launch_dof(ctx->d_vp(), ctx->pools.bin_used, vp.nbx, ctx->d_tmp_color, vp.vw, ctx->d_depth,
@@ -605,7 +615,7 @@ static int render_async(swegl_b200_ctx *ctx, const ViewParams &out, bool dof)
     if (!ctx->graphs_enabled) {
         issue_view(ctx, out, vp, sl, with_frame, dof, false, false, false, sl.counters);
     } else {
-        const int32_t key[13] = { out.vx, out.vy, out.vw, out.vh, out.band0, out.band1, out.light_mode, out.tex_mode, dof ? 1 : 0,
+        const int32_t key[13] = { out.vx, out.vy, out.vw, out.vh, out.band0, out.band1, out.light_mode, out.tex_mode, (dof ? 1 : 0) | (out.n_layers << 1),
                                   ctx->sw, ctx->sh, with_frame ? 1 : 0, ctx->dense_spans ? 1 : 0 };
         swegl_b200_ctx::ViewGraph *vg = nullptr;
         for (auto &g : ctx->view_graphs) if (memcmp(g.key, key, sizeof key) == 0) { vg = &g; break; }

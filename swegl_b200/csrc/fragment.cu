@@ -247,6 +247,148 @@ __global__ void __launch_bounds__(FRAG_TPB) k_fragments(DeviceScene s, const Vie
 }
 
 // ----------------------------------------------------------------------------------------
+// Transparency layers (viewport_t::m_got_transparency; renderer.cpp:500-550, viewport.cpp:43-86).
+//
+// The reference keeps, per pixel, the opaque colour/z and up to L transparent fragments sorted
+// far -> near, updated fragment by fragment in draw order:
+//   * a fragment must pass `z < zbuffer` (the OPAQUE depth so far) to be looked at all,
+//   * an opaque one (shaded alpha == 255) replaces the base and drops every layer with layer_z >= z,
+//   * a transparent one is inserted by depth (equal depth: the later draw is nearer); when all L layers
+//     are used the farthest is discarded.
+// The end state does not depend on the draw order except through ties, so it has a closed form that a
+// parallel resolve can evaluate: base = min (z, slot) over opaque fragments; layers = the L nearest
+// transparent fragments under the order (z ascending, slot descending) among those with z < base z.
+// (A fragment discarded for capacity is farther than every kept one, so it would also fall to any later
+// opaque fragment that removes a kept one; and a transparent fragment that failed the z test at its
+// time has z >= the final base z.)  flatten() then blends layer[1..] onto layer[0] and the result onto
+// the screen with colors.cpp:39-57's blend(), which is exact integer arithmetic.
+//
+// lane = pixel, as in k_fragments, without the shading queue (every kept layer is shaded as well).
+// ----------------------------------------------------------------------------------------
+static constexpr int MAX_LAYERS = 8;
+
+SB_DEV uint32_t blend_px(uint32_t back, uint32_t front)                    // colors.cpp:39-57
+{
+    const int alpha = (int)(front >> 24), back_a = (int)(back >> 24);
+    const uint32_t new_alpha = (uint32_t)(255 - ((255 - alpha) * (255 - back_a) / 255));
+    if (alpha == 255) return (front & 0x00FFFFFFu) | (new_alpha << 24);
+    if (alpha == 0) return (back & 0x00FFFFFFu) | (new_alpha << 24);
+    uint32_t out = new_alpha << 24;
+    #pragma unroll
+    for (int c = 0; c < 3; c++) {
+        // (unsigned char)(back * ((256 - alpha) / 256.0) + front * (alpha / 256.0)): every term is a multiple of
+        // 1/256 below 2^16, so the double expression is exact and the truncation is a shift
+        const uint32_t bk = (back >> (8 * c)) & 0xFFu, fr = (front >> (8 * c)) & 0xFFu;
+        out |= (((bk * (uint32_t)(256 - alpha) + fr * (uint32_t)alpha) >> 8) & 0xFFu) << (8 * c);
+    }
+    return out;
+}
+
+template <int LIGHT, int TEX>
+__global__ void __launch_bounds__(FRAG_TPB) k_fragments_layers(DeviceScene s, const ViewParams *__restrict__ vpp,
+                                                               const FrameParams *__restrict__ fpp, Pools pl,
+                                                               uint32_t *__restrict__ color, int color_pitch,
+                                                               float *__restrict__ depth, int count_covered,
+                                                               Counters *__restrict__ h_counters_out)
+{
+    if (h_counters_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < sizeof(Counters) / 4)
+        reinterpret_cast<uint32_t *>(h_counters_out)[threadIdx.x] = reinterpret_cast<const uint32_t *>(pl.counters)[threadIdx.x];
+    __shared__ ViewParams vp;
+    __shared__ FrameParams fp;
+    for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += FRAG_TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
+    for (int w = threadIdx.x; w < (int)(sizeof(FrameParams) / 4); w += FRAG_TPB) reinterpret_cast<uint32_t *>(&fp)[w] = reinterpret_cast<const uint32_t *>(fpp)[w];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int row = (vp.band0 - vp.vy) + blockIdx.y * FRAG_ROWS + (threadIdx.x >> 5);
+    if (row >= vp.band1 - vp.vy) return;
+    const int y = vp.vy + row;
+    const int bx0 = blockIdx.x * FRAG_STRETCH;
+    const int nb = min(FRAG_STRETCH, vp.nbx - bx0);
+    const int L = vp.n_layers;
+    const uint64_t KEY_INIT = (uint64_t)MAXZ_BITS << 32;
+
+    int32_t *headp = pl.bin_head + (size_t)row * vp.nbx + bx0 + lane;
+    int32_t head = -1;
+    if (lane < nb) {
+        head = *headp;
+        if (head >= 0) *headp = -1;
+        pl.bin_used[(size_t)row * vp.nbx + bx0 + lane] = head >= 0;
+    }
+    unsigned mask = __ballot_sync(0xFFFFFFFFu, head >= 0);
+    uint32_t *crow = color + (size_t)y * color_pitch + vp.vx + (bx0 << 5);
+    float *drow = depth + (size_t)row * vp.vw + (bx0 << 5);
+    const int px_left = vp.vw - (bx0 << 5);
+    const float maxz = __uint_as_float(MAXZ_BITS);
+    for (int b = 0; b < nb; b++) {
+        const int px = (b << 5) + lane;
+        if (!((mask >> b) & 1u)) {                                          // empty bin: clear values (viewport.cpp:88-113)
+            if (px < px_left) { crow[px] = 0; drow[px] = maxz; }
+            continue;
+        }
+        int32_t c = __shfl_sync(0xFFFFFFFFu, head, b);
+        uint64_t best = KEY_INIT;                                           // opaque base: z bits << 32 | slot
+        float best_u = 0.f;
+        uint32_t best_span = 0xFFFFFFFFu;
+        // kept transparent fragments, nearest first: key = z bits << 32 | ~slot (a later draw at equal depth is nearer)
+        uint64_t tkey[MAX_LAYERS]; float tu[MAX_LAYERS]; uint32_t tspan[MAX_LAYERS];
+        int tn = 0;
+        while (c >= 0) {
+            const Chunk ch = pl.chunks[c];
+            c = ch.next;
+            const int xs = (int)(ch.xs_xe & 0xFFu), xe = (int)(ch.xs_xe >> 8);
+            if (lane < xs || lane >= xe) continue;
+            const float2 tb = pl.frag_tb[ch.frag0 + (uint32_t)lane];
+            const float u = fdiv(tb.x, tb.y);
+            const float z = fadd(ch.v0, fmul(ch.v1, u));
+            if (!(z >= NEAR_Z)) continue;                                   // renderer.cpp:489
+            bool opaque = ch.alpha_class == ALPHA_OPAQUE;
+            if (ch.alpha_class == ALPHA_PER_FRAGMENT) {                     // the texel decides (renderer.cpp:505)
+                const Prim pr = s.prims[pl.shades[ch.slot].prim];
+                opaque = (shade_texture<TEX>(&pl.span_shades[ch.span], pr, s.texels, u) >> 24) == 255u;
+            }
+            if (opaque) {
+                const uint64_t key = ((uint64_t)__float_as_uint(z) << 32) | ch.slot;
+                if (key < best) { best = key; best_u = u; best_span = ch.span; }
+                continue;
+            }
+            const uint64_t key = ((uint64_t)__float_as_uint(z) << 32) | (0xFFFFFFFFu - ch.slot);
+            if (tn == L && key > tkey[L - 1]) continue;                     // farther than all L kept ones
+            int i = tn < L ? tn : L - 1;                                    // insertion sort; the farthest falls off
+            for (; i > 0 && tkey[i - 1] > key; i--) { tkey[i] = tkey[i - 1]; tu[i] = tu[i - 1]; tspan[i] = tspan[i - 1]; }
+            tkey[i] = key; tu[i] = u; tspan[i] = ch.span;
+            if (tn < L) tn++;
+        }
+        const bool inside = px < px_left;
+        const bool hit = best_span != 0xFFFFFFFFu && inside;
+        const uint32_t zb = (uint32_t)(best >> 32);
+        uint32_t out = 0;                                                   // cleared screen
+        if (hit) {
+            const SlotShade *sh = &pl.shades[(uint32_t)best];
+            out = shade<LIGHT, TEX>(&pl.span_shades[best_span], sh->flat_light, s.prims[sh->prim], s.texels, vp, fp, best_u);
+        }
+        if (inside) {
+            int m = 0;                                                      // layers strictly in front of the base
+            while (m < tn && (uint32_t)(tkey[m] >> 32) < zb) m++;
+            uint32_t layer0 = 0;
+            for (int i = m - 1; i >= 0; i--) {                              // far -> near: viewport.cpp:45-58
+                const uint32_t slot = 0xFFFFFFFFu - (uint32_t)tkey[i];
+                const SlotShade *sh = &pl.shades[slot];
+                const uint32_t cl = shade<LIGHT, TEX>(&pl.span_shades[tspan[i]], sh->flat_light, s.prims[sh->prim], s.texels, vp, fp, tu[i]);
+                if (i == m - 1) layer0 = cl;
+                else if ((cl >> 24) != 0) layer0 = blend_px(layer0, cl);
+            }
+            if ((layer0 >> 24) != 0) out = blend_px(out, layer0);          // viewport.cpp:60-84
+            crow[px] = out;
+            drow[px] = __uint_as_float(zb);
+        }
+        if (count_covered) {
+            const unsigned hm = __ballot_sync(0xFFFFFFFFu, hit);
+            if (lane == 0 && hm) atomicAdd(&pl.counters->n_covered, (uint32_t)__popc(hm));
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
 // DoF-R: the repaired post_shader_depth_box (post_shaders.hpp:63-111).
 //
 // out(x,y) = src(x,y)                                   if r == 0 or no tap counts
@@ -486,6 +628,21 @@ void launch_fragments(const DeviceScene &s, const ViewParams &vp, const ViewPara
     SB_CASE(1, 0) SB_CASE(1, 1) SB_CASE(1, 2)
     SB_CASE(2, 0) SB_CASE(2, 1) SB_CASE(2, 2)
 #undef SB_CASE
+}
+
+template <int LIGHT, int TEX>
+static void launch_frag_layers_t(const DeviceScene &s, const ViewParams &vp, const ViewParams *d_vp, const FrameParams *d_fp, const Pools &p,
+                                 uint32_t *color, int color_pitch, float *depth, bool count_covered, Counters *h_counters_out, cudaStream_t st)
+{
+    dim3 grid((vp.nbx + FRAG_STRETCH - 1) / FRAG_STRETCH, (vp.band1 - vp.band0 + FRAG_ROWS - 1) / FRAG_ROWS);
+    k_fragments_layers<LIGHT, TEX><<<grid, FRAG_TPB, 0, st>>>(s, d_vp, d_fp, p, color, color_pitch, depth, count_covered ? 1 : 0, h_counters_out);
+}
+void launch_fragments_layers(const DeviceScene &s, const ViewParams &vp, const ViewParams *d_vp, const FrameParams *d_fp, const Pools &p,
+                             uint32_t *color, int color_pitch, float *depth, bool count_covered, Counters *h_counters_out, cudaStream_t st)
+{
+#define SB_LCASE(L, T) if (vp.light_mode == L && vp.tex_mode == T) { launch_frag_layers_t<L, T>(s, vp, d_vp, d_fp, p, color, color_pitch, depth, count_covered, h_counters_out, st); return; }
+    SB_LCASE(0, 0) SB_LCASE(0, 1) SB_LCASE(0, 2) SB_LCASE(1, 0) SB_LCASE(1, 1) SB_LCASE(1, 2) SB_LCASE(2, 0) SB_LCASE(2, 1) SB_LCASE(2, 2)
+#undef SB_LCASE
 }
 
 void launch_dof(const ViewParams *d_vp, const uint8_t *bin_used, int nbx, const uint32_t *src, int src_pitch, const float *depth,

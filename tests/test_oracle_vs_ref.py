@@ -57,39 +57,25 @@ def test_near_clip_and_odd_poses(ref, oracle, pose):
     assert (rvs["yes"] == o["yes"]).all()
 
 
-def procedural_scene(ref, alpha):
-    """test_1.cpp's build_scene() flavour: torus (strips), cube (fans, scaled), sphere, triangles; optional
-    transparent materials (the transparency-layer path, renderer.cpp:500-550)."""
-    from swegl_b200.scene import lcg_texture
-    h = ref.new_scene()
-    tex = lcg_texture(64, seed=99)
-    ref.lib.ref_scene_add_texture(h, tex.ctypes.data, 64, 64)
-    mats = [(128, 128, 128, 255, 0), (128, 128, 255, 255, -1), (255, 128, 255, 255, -1),
-            (128, 128, 255, alpha, -1), (128, 255, 128, alpha, -1), (255, 128, 128, alpha, -1)]
-    for b, g, r, a, t in mats:
-        ref.lib.ref_scene_add_material(h, b, g, r, a, 1.0, 1.0, t, 0)
-    import ctypes as C
-    f3 = lambda *v: (C.c_float * 3)(*v)
-    ref.lib.ref_scene_add_builtin(h, 2, 24, 1.0, 0, None, f3(0, 0, 0.5), f3(0, 0, -2.5))       # tore
-    ref.lib.ref_scene_add_builtin(h, 1, 0, 1.0, 0, f3(2, 1, 1), None, f3(0, 0, 0))              # cube, scale.x = 2
-    ref.lib.ref_scene_add_builtin(h, 3, 16, 2.0, 2, None, None, f3(3, 0, -1))                   # sphere
-    ref.lib.ref_scene_add_builtin(h, 0, 0, 1.0, 3, None, None, f3(1, 0.5, 2.1))                 # tri
-    ref.lib.ref_scene_add_builtin(h, 0, 0, 1.0, 4, None, None, f3(1, 0.5, 2.0))
-    ref.lib.ref_scene_add_builtin(h, 0, 0, 1.0, 5, None, None, f3(1, 0.5, 2.2))
-    s = ref.export(h, "procedural")
-    ref.lib.ref_scene_free(h)
-    s.set_lights(0.2, (1.0, -1.0, -1.0), 0.3, configs.POINT_LIGHTS)
-    return s
+def procedural_scene(ref, alpha, tex_alpha=False):
+    s = ref.procedural_scene()                      # oracle/binding.py: test_1.cpp build_scene() flavour, via the reference's builtins
+    return configs.with_transparency(s, alpha, tex_alpha)
 
 
-@pytest.mark.parametrize("alpha,layers", [(255, 0), (255, 3), (100, 3), (100, 1), (30, 2)])
-def test_procedural_scene_and_transparency_layers(ref, oracle, alpha, layers):
-    """strips + fans + node scale + (for alpha < 255) the sorted transparency-layer insertion, flatten and blend"""
-    scene = procedural_scene(ref, alpha)
-    pose = [("translate", 1, 2, 6), ("rotate_y", 3.0), ("rotate_x", -0.3)]
+@pytest.mark.parametrize("alpha,layers,tex_alpha", [(255, 0, False), (255, 3, False), (100, 3, False), (100, 1, False), (30, 2, False),
+                                                    (100, 2, True), (0, 3, True)])
+@pytest.mark.parametrize("pose", ["POSE_PROCEDURAL", "POSE_LAYERS", "POSE_LAYERS_CLOSE"])
+def test_procedural_scene_and_transparency_layers(ref, oracle, alpha, layers, tex_alpha, pose):
+    """strips + fans + node scale + (for alpha < 255) the sorted transparency-layer insertion, flatten and blend;
+    tex_alpha: texels decide per fragment whether the fragment is opaque (renderer.cpp:505)"""
+    scene = procedural_scene(ref, alpha, tex_alpha)
+    pose = getattr(configs, pose)
     vp = Viewport(0, 0, 400, 300, transparency_layers=layers)
     vp.camera.apply(pose)
     rpx, rz, rvs, o = both(ref, oracle, scene, vp, (400, 300), pose)
     assert (rz.view(np.uint32) == o["z"].view(np.uint32)).all()
     assert (rpx == o["pixels"]).all()
     assert o["n_covered"] > 1000
+    if pose is not configs.POSE_PROCEDURAL and layers > 0 and (alpha not in (0, 255) or tex_alpha):
+        a = rpx >> 24
+        assert ((a != 0) & (a != 255)).sum() > 500          # blended pixels are really in the frame

@@ -37,6 +37,9 @@ def main():
         print(f"{name}: nodes={s.n_nodes} prims={s.n_primitives} verts={s.n_vertices} tris={s.n_triangles()} "
               f"textures={[t.shape for t in s.textures]} -> {os.path.getsize(path)} bytes")
         ref.lib.ref_scene_free(h)
+    s = ref.procedural_scene()                      # built with the reference's own mesh builders, not a glTF
+    s.save_pack(os.path.join(out, "procedural.scenepack"), None)
+    print(f"procedural: prims={s.n_primitives} verts={s.n_vertices} tris={s.n_triangles()}")
 
 
 if __name__ == "__main__":
