@@ -180,6 +180,18 @@ int  swegl_b200_render_viewport(swegl_b200_ctx *ctx, const swegl_b200_viewport_d
                                 void *pixels, int32_t pitch_bytes, float *zbuffer,
                                 swegl_b200_stats *stats);
 
+/* Pipelined variant of render_viewport ("async readback / double-buffered frames"): queues the
+ * frame, a device-side copy of the finished rectangle into one of two staging images, and the copy of that
+ * image to host `pixels` / `zbuffer` on a second stream -- then returns.  The next frame renders while this one
+ * crosses PCIe.  `*ticket` identifies the frame; its host data is complete after swegl_b200_wait(ticket).
+ * At most two frames are in flight (a third submit waits for the oldest), so callers alternate between two
+ * host images; these should be page-locked (swegl_b200_alloc_host), otherwise the copy blocks the submit.
+ * swegl_b200_wait returns SWEGL_B200_ERR_CAPACITY when that frame ran out of pool space (the pools are then
+ * enlarged: submit it again), like swegl_b200_synchronize. */
+int  swegl_b200_render_viewport_async(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *vp,
+                                      void *pixels, int32_t pitch_bytes, float *zbuffer, uint64_t *ticket);
+int  swegl_b200_wait(swegl_b200_ctx *ctx, uint64_t ticket);
+
 /* ---- read-back of device state (parity tests, multi-GPU gather) ---- */
 /* device pointers of the screen (screen_w*screen_h words) and of the last viewport's depth */
 int  swegl_b200_device_buffers(swegl_b200_ctx *ctx, void **screen_dev, void **depth_dev);

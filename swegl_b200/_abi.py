@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libswegl_b200.so")
+LIB_PATH = os.environ.get("SWEGL_B200_LIB") or os.path.join(_HERE, "libswegl_b200.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_CAPACITY, ERR_STATE = range(6)
 MODE_TRIANGLES, MODE_TRIANGLE_STRIP, MODE_TRIANGLE_FAN = 4, 5, 6
@@ -81,6 +81,9 @@ SYMBOLS = [
     ("swegl_b200_render_viewport_device", C.c_int, [C.c_void_p, C.POINTER(ViewportDesc), C.POINTER(Stats)]),
     ("swegl_b200_render_viewport", C.c_int, [C.c_void_p, C.POINTER(ViewportDesc), C.c_void_p, C.c_int32,
                                              C.c_void_p, C.POINTER(Stats)]),
+    ("swegl_b200_render_viewport_async", C.c_int, [C.c_void_p, C.POINTER(ViewportDesc), C.c_void_p, C.c_int32,
+                                                   C.c_void_p, C.POINTER(C.c_uint64)]),
+    ("swegl_b200_wait", C.c_int, [C.c_void_p, C.c_uint64]),
     ("swegl_b200_device_buffers", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     ("swegl_b200_read_screen", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     ("swegl_b200_read_depth", C.c_int, [C.c_void_p, C.c_void_p]),

@@ -34,6 +34,7 @@ struct swegl_b200_ctx {
     Tri *d_tris = nullptr; Prim *d_prims = nullptr;
     float *d_v_world = nullptr, *d_v_ndc = nullptr, *d_n_world = nullptr; uint8_t *d_yes = nullptr;
     bool opaque = true;            // every material and texel has alpha 255
+    uint32_t stamp = 0;            // ViewParams::stamp of the last staged view
 
     // the frame block
     uint8_t *d_block = nullptr; size_t block_bytes = 0;
@@ -41,8 +42,19 @@ struct swegl_b200_ctx {
     struct Slot {
         uint8_t *block = nullptr; Counters *counters = nullptr;     // pinned
         cudaEvent_t done = nullptr; bool pending = false;           // last launch that read this slot
+        uint64_t ticket = 0;                                        // of that launch, when it came through render_viewport_async
     } slots[2];
+    std::vector<uint64_t> failed_tickets;                           // async frames found to have overflowed a pool
     int next_slot = 0, frame_slot = 0; bool frame_dirty = false;
+    int last_slot = 0;                  // staging slot of the most recently issued view
+    // pipelined read-back (render_viewport_async): two device staging images, filled on `stream`, drained on `copy_stream`
+    struct OutBuf {
+        uint32_t *color = nullptr; float *depth = nullptr; size_t cap = 0;
+        cudaEvent_t ready = nullptr, copied = nullptr;
+        uint64_t ticket = 0; int slot = 0; bool in_flight = false;
+    } out[2];
+    cudaStream_t copy_stream = nullptr;
+    uint64_t ticket_seq = 0;
     struct ViewGraph { int32_t key[13]; cudaGraphExec_t exec[2]; };
     std::vector<ViewGraph> view_graphs;
     bool graphs_enabled = true;
@@ -156,7 +168,8 @@ void swegl_b200_destroy(swegl_b200_ctx *ctx)
     void *ptrs[] = { ctx->d_pos, ctx->d_nrm, ctx->d_uv, ctx->d_vert_node, ctx->d_texels, ctx->d_tris, ctx->d_prims,
                      ctx->d_v_world, ctx->d_v_ndc, ctx->d_n_world, ctx->d_yes, ctx->d_block,
                      ctx->pools.edges, ctx->pools.shades, ctx->pools.spans, ctx->pools.span_shades, ctx->pools.frag_tb, ctx->pools.row_slot,
-                     ctx->pools.chunks, ctx->pools.bin_head, ctx->pools.bin_used, ctx->pools.counters, ctx->d_screen, ctx->d_depth,
+                     ctx->pools.chunks, ctx->pools.bin_head, ctx->pools.bin_used, ctx->pools.tile_stamp, ctx->pools.busy_list,
+                     ctx->pools.counters, ctx->d_screen, ctx->d_depth,
                      ctx->d_tmp_color };
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -166,6 +179,13 @@ void swegl_b200_destroy(swegl_b200_ctx *ctx)
         if (sl.done) cudaEventDestroy(sl.done);
     }
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto &ob : ctx->out) {
+        if (ob.color) cudaFree(ob.color);
+        if (ob.depth) cudaFree(ob.depth);
+        if (ob.ready) cudaEventDestroy(ob.ready);
+        if (ob.copied) cudaEventDestroy(ob.copied);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -256,6 +276,7 @@ static int check_slot_overflow(swegl_b200_ctx *ctx, swegl_b200_ctx::Slot &sl)
     if (!sl.counters->overflow) return SWEGL_B200_OK;
     Counters c = *sl.counters;
     sl.counters->overflow = 0;
+    if (sl.ticket) { if (ctx->failed_tickets.size() >= 16) ctx->failed_tickets.erase(ctx->failed_tickets.begin()); ctx->failed_tickets.push_back(sl.ticket); }
     int rc = grow_pools_for(ctx, c);
     if (rc) return rc;
     return fail(ctx, SWEGL_B200_ERR_CAPACITY, "an asynchronous frame overflowed the span/chunk/fragment pools (now enlarged): render it again");
@@ -411,6 +432,9 @@ int swegl_b200_set_screen(swegl_b200_ctx *ctx, int32_t w, int32_t h)
     CK(cudaMemset(ctx->pools.bin_head, 0xFF, bins * 4));
     CK(dalloc(ctx->pools.bin_used, bins));
     CK(cudaMemset(ctx->pools.bin_used, 0, bins));
+    CK(dalloc(ctx->pools.tile_stamp, bins));            // (a tile is at least one bin)
+    CK(cudaMemset(ctx->pools.tile_stamp, 0, bins * 4));
+    CK(dalloc(ctx->pools.busy_list, bins));
     ctx->bins_cap = bins;
     ctx->sw = w; ctx->sh = h;
     return SWEGL_B200_OK;
@@ -522,6 +546,7 @@ static int build_view(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v, Vi
         vp.band0 = v->y + v->band_y0; vp.band1 = v->y + v->band_y1;
     }
     vp.nbx = (v->w + 31) / 32;
+    vp.ntx = (vp.nbx + FRAG_STRETCH - 1) / FRAG_STRETCH;
     vp.screen_w = ctx->sw;
     vp.light_mode = v->light_mode; vp.tex_mode = v->tex_mode;
     vp.focal_distance = v->focal_distance; vp.focal_depth = v->focal_depth;
@@ -590,6 +615,9 @@ static int stage_view(swegl_b200_ctx *ctx, const ViewParams &vp, int &si, bool &
     int rc = acquire_slot(ctx, sl);          // no-op right after begin_frame acquired it
     if (rc) return rc;
     memcpy(sl.block + ctx->off_vp, &vp, sizeof(ViewParams));
+    // every rendered view gets a stamp no earlier view had (0 = the initial tile_stamp contents, skipped on wrap-around)
+    if (++ctx->stamp == 0) ctx->stamp = 1;
+    reinterpret_cast<ViewParams *>(sl.block + ctx->off_vp)->stamp = ctx->stamp;
     return SWEGL_B200_OK;
 }
 
@@ -599,6 +627,8 @@ static int finish_view(swegl_b200_ctx *ctx, int si)
     CK(cudaEventRecord(sl.done, ctx->stream));
     sl.pending = true;
     ctx->next_slot = si ^ 1;
+    ctx->last_slot = si;
+    sl.ticket = 0;
     ctx->frame_dirty = false;
     return SWEGL_B200_OK;
 }
@@ -725,6 +755,67 @@ int swegl_b200_render_viewport(swegl_b200_ctx *ctx, const swegl_b200_viewport_de
         if (rc) return rc;
     }
     return rc;
+}
+
+int swegl_b200_render_viewport_async(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v, void *pixels, int32_t pitch_bytes,
+                                     float *zbuffer, uint64_t *ticket)
+{
+    if (!ctx || !pixels || pitch_bytes < 4 || !ticket) return fail(ctx, SWEGL_B200_ERR_ARG, "render_viewport_async: null argument");
+    int rc = render_common(ctx, v, false, nullptr);
+    if (rc) return rc;
+    const ViewParams &vp = ctx->last_vp;
+    const int rows = vp.band1 - vp.band0;
+    const size_t need = (size_t)vp.vw * rows;
+    if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    auto &ob = ctx->out[ctx->ticket_seq & 1];
+    if (!ob.ready) { CK(cudaEventCreateWithFlags(&ob.ready, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ob.copied, cudaEventDisableTiming)); }
+    if (ob.cap < need) {
+        if (ob.in_flight) CK(cudaEventSynchronize(ob.copied));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(dalloc(ob.color, need)); CK(dalloc(ob.depth, need));
+        ob.cap = need;
+    }
+    cudaStream_t st = ctx->stream;
+    if (ob.in_flight) CK(cudaStreamWaitEvent(st, ob.copied, 0));        // the frame before last has left this image
+    CK(cudaMemcpy2DAsync(ob.color, (size_t)vp.vw * 4, ctx->d_screen + (size_t)vp.band0 * ctx->sw + vp.vx, (size_t)ctx->sw * 4,
+                         (size_t)vp.vw * 4, (size_t)rows, cudaMemcpyDeviceToDevice, st));
+    if (zbuffer)
+        CK(cudaMemcpyAsync(ob.depth, ctx->d_depth + (size_t)(vp.band0 - vp.vy) * vp.vw, need * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaEventRecord(ob.ready, st));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ob.ready, 0));
+    CK(cudaMemcpy2DAsync((char *)pixels + (size_t)vp.band0 * pitch_bytes + (size_t)vp.vx * 4, (size_t)pitch_bytes,
+                         ob.color, (size_t)vp.vw * 4, (size_t)vp.vw * 4, (size_t)rows, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (zbuffer)
+        CK(cudaMemcpyAsync(zbuffer + (size_t)(vp.band0 - vp.vy) * vp.vw, ob.depth, need * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CK(cudaEventRecord(ob.copied, ctx->copy_stream));
+    ob.in_flight = true;
+    ob.slot = ctx->last_slot;
+    ob.ticket = ++ctx->ticket_seq;
+    ctx->slots[ob.slot].ticket = ob.ticket;
+    *ticket = ob.ticket;
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_wait(swegl_b200_ctx *ctx, uint64_t ticket)
+{
+    if (!ctx || ticket == 0 || ticket > ctx->ticket_seq) return fail(ctx, SWEGL_B200_ERR_ARG, "wait: unknown ticket");
+    CK(cudaSetDevice(ctx->device));
+    auto &ob = ctx->out[(ticket - 1) & 1];
+    // a later frame through the same staging image implies this one is done (same stream order)
+    if (ob.in_flight) { CK(cudaEventSynchronize(ob.copied)); ob.in_flight = false; }
+    // the frame's kernels are complete.  If its staging slot was not reused since, its pool counters are still
+    // unexamined: do that now; if it was, acquire_slot() already did and noted a failure
+    if (ob.ticket == ticket && ctx->slots[ob.slot].ticket == ticket) {
+        int rc = check_slot_overflow(ctx, ctx->slots[ob.slot]);
+        if (rc && rc != SWEGL_B200_ERR_CAPACITY) return rc;
+    }
+    for (size_t i = 0; i < ctx->failed_tickets.size(); i++)
+        if (ctx->failed_tickets[i] == ticket) {
+            ctx->failed_tickets.erase(ctx->failed_tickets.begin() + i);
+            return fail(ctx, SWEGL_B200_ERR_CAPACITY, "the frame overflowed the span/chunk/fragment pools (now enlarged): submit it again");
+        }
+    ctx->err.clear();
+    return SWEGL_B200_OK;
 }
 
 int swegl_b200_device_buffers(swegl_b200_ctx *ctx, void **screen_dev, void **depth_dev)

@@ -113,15 +113,20 @@ SB_DEV uint32_t shade(const SpanShade *ss, float flat_light, const Prim &pr, con
     return (c & 0xFF000000u) | (r << 16) | (g << 8) | b;
 }
 
-static constexpr int FRAG_TPB = 256;
-static constexpr int FRAG_ROWS = FRAG_TPB / 32;     // one warp per row of the CTA's 8-row group
-static constexpr int FRAG_STRETCH = 8;              // bins (of 32 pixels) one warp owns along its row
 
-// per-warp queue of the stretch's winning fragments (pass 1 -> pass 2 -> pass 3 of k_fragments)
+// chunks of a bin whose records are fetched up front, all bins of the stretch at once; longer lists continue serially
+#ifndef FRAG_LIST_CAP_V
+#define FRAG_LIST_CAP_V 12
+#endif
+static constexpr int FRAG_LIST_CAP = FRAG_LIST_CAP_V;
+
+// per-warp staging: the stretch's chunk records (pass 1) and the queue of winning fragments (pass 1 -> 2 -> 3)
 struct FragWarp {
     float u[FRAG_STRETCH * 32];         // interpolator progress of the winner; overwritten by its colour in pass 2
     uint32_t span[FRAG_STRETCH * 32];   // winning span, 0xFFFFFFFF = background
     uint32_t slot[FRAG_STRETCH * 32];   // winning slot (-> SlotShade)
+    uint4 rec[FRAG_STRETCH * FRAG_LIST_CAP * 2];    // Chunk records of bin b at [b * FRAG_LIST_CAP ..], 2 x 16 B each
+    int32_t cnt[FRAG_STRETCH], cursor[FRAG_STRETCH];   // staged list lengths, continuation of longer lists
     uint8_t idx[FRAG_STRETCH * 32];     // compacted list of covered pixels
 };
 
@@ -129,44 +134,102 @@ struct FragWarp {
 //   1. one load fetches the bin heads (and resets them for the next frame),
 //   2. empty bins are cleared in bulk with 128-bit stores (colour 0, depth 0x7F7F7F7F: viewport.cpp:88-113),
 //   3. each non-empty bin is resolved with lane = pixel as described at the top of this file.
+// the part of ViewParams that is fixed for a captured frame graph (rectangle, band), passed by value so that the
+// first loads of the kernel do not wait for the parameter block
+struct FragGeom { int32_t vx, vy, vw, band0, band1, nbx, ntx, n_tiles; };
+
+// clear values (viewport.cpp:88-113) for one row of a tile: colour 0, depth 0x7F7F7F7F
+SB_DEV void clear_tile_row(uint32_t *crow, float *drow, int px_left, int lane)
+{
+    const float maxz = __uint_as_float(MAXZ_BITS);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(crow) | reinterpret_cast<uintptr_t>(drow)) & 15) == 0;
+    #pragma unroll
+    for (int px = lane << 2; px < FRAG_STRETCH * 32; px += 128) {
+        if (aligned && px + 4 <= px_left) {
+            *reinterpret_cast<uint4 *>(crow + px) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<float4 *>(drow + px) = make_float4(maxz, maxz, maxz, maxz);
+        } else {
+            #pragma unroll 1
+            for (int k = 0; k < 4; k++)
+                if (px + k < px_left) { crow[px + k] = 0; drow[px + k] = maxz; }
+        }
+    }
+}
+
+// Grid: n_tiles "busy" CTAs followed by ceil(n_tiles / FRAG_ROWS) "clear" CTAs.
+//  * busy CTA i works on busy_list[i] (the tiles k_spans put chunks into, so all the expensive tiles start at once
+//    at the head of the grid instead of wherever the scene happens to sit on the screen); i >= n_busy exits;
+//  * clear CTA j: warp w takes tile j * FRAG_ROWS + w and, unless it was busy, fills it with the clear values
+//    (16 independent 128-bit stores per lane; no bin heads are read for tiles nothing was drawn into).
 template <int LIGHT, int TEX>
 __global__ void __launch_bounds__(FRAG_TPB) k_fragments(DeviceScene s, const ViewParams *__restrict__ vpp,
-                                                        const FrameParams *__restrict__ fpp, Pools pl,
+                                                        const FrameParams *__restrict__ fpp, Pools pl, FragGeom g,
                                                         uint32_t *__restrict__ color, int color_pitch,
                                                         float *__restrict__ depth, int count_covered,
                                                         Counters *__restrict__ h_counters_out)
 {
+    static_assert(FRAG_ROWS * FRAG_STRETCH <= 32, "one warp-wide load fetches the bin heads of the whole CTA tile");
+    __shared__ ViewParams vp;                   // per-frame constants, staged only by tiles that shade something
+    __shared__ FrameParams fp;
+    __shared__ FragWarp fwarp[FRAG_ROWS];
+    __shared__ int32_t s_head[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int band_rows = g.band1 - g.band0;
+    if ((int)blockIdx.x >= g.n_tiles) {
+        // ---- clear CTA ----
+        const int t = ((int)blockIdx.x - g.n_tiles) * FRAG_ROWS + warp;
+        if (t >= g.n_tiles) return;
+        if (pl.tile_stamp[t] == vpp->stamp) return;                         // a busy CTA owns this tile
+        const int ty = t / g.ntx, tx = t - ty * g.ntx;
+        const int row0 = (g.band0 - g.vy) + ty * FRAG_ROWS, bx0 = tx * FRAG_STRETCH;
+        const int rows_here = min(FRAG_ROWS, band_rows - ty * FRAG_ROWS);
+        const int px_left = g.vw - (bx0 << 5);
+        for (int r = 0; r < rows_here; r++)
+            clear_tile_row(color + (size_t)(g.vy + row0 + r) * color_pitch + g.vx + (bx0 << 5),
+                           depth + (size_t)(row0 + r) * g.vw + (bx0 << 5), px_left, lane);
+        {   // occupancy map for the DoF pass
+            const int r = lane / FRAG_STRETCH, b = lane % FRAG_STRETCH;
+            if (r < rows_here && bx0 + b < g.nbx) pl.bin_used[(size_t)(row0 + r) * g.nbx + bx0 + b] = 0;
+        }
+        return;
+    }
+    // ---- busy CTA ----
     // k_setup / k_spans are done: publish their counters (pool demand, overflow flags) to the pinned slot the host
     // polls, instead of a D2H copy node at the end of the graph.  (n_covered is only final after this kernel; the
     // synchronous stats path copies the counters itself.)
-    if (h_counters_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < sizeof(Counters) / 4)
+    if (h_counters_out && blockIdx.x == 0 && threadIdx.x < sizeof(Counters) / 4)
         reinterpret_cast<uint32_t *>(h_counters_out)[threadIdx.x] = reinterpret_cast<const uint32_t *>(pl.counters)[threadIdx.x];
-    __shared__ ViewParams vp;                   // per-frame constants staged once per CTA
-    __shared__ FrameParams fp;
-    __shared__ FragWarp fwarp[FRAG_ROWS];
+    if (blockIdx.x >= pl.counters->n_busy) return;
+    const int t = (int)pl.busy_list[blockIdx.x];
+    const int ty = t / g.ntx, tx = t - ty * g.ntx;
+    const int row0 = (g.band0 - g.vy) + ty * FRAG_ROWS;                     // viewport-relative first row of the tile
+    const int rows_here = min(FRAG_ROWS, band_rows - ty * FRAG_ROWS);
+    const int bx0 = tx * FRAG_STRETCH;
+    const int nb = min(FRAG_STRETCH, g.nbx - bx0);
+    const int px_left = g.vw - (bx0 << 5);                                  // pixels from the stretch start to the row end
+    const uint64_t KEY_INIT = (uint64_t)MAXZ_BITS << 32;
+    if (warp == 0) {        // lane -> (row, bin) of the tile: fetch and reset the heads, leave the occupancy map for the DoF pass
+        const int r = lane / FRAG_STRETCH, b = lane % FRAG_STRETCH;
+        int32_t h = -1;
+        if (r < rows_here && b < nb) {
+            const size_t bi = (size_t)(row0 + r) * g.nbx + bx0 + b;
+            h = pl.bin_head[bi];
+            if (h >= 0) pl.bin_head[bi] = -1;
+            pl.bin_used[bi] = h >= 0;
+        }
+        s_head[lane] = h;
+    }
     for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += FRAG_TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
     for (int w = threadIdx.x; w < (int)(sizeof(FrameParams) / 4); w += FRAG_TPB) reinterpret_cast<uint32_t *>(&fp)[w] = reinterpret_cast<const uint32_t *>(fpp)[w];
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int row = (vp.band0 - vp.vy) + blockIdx.y * FRAG_ROWS + (threadIdx.x >> 5);   // viewport-relative
-    if (row >= vp.band1 - vp.vy) return;
-    const int y = vp.vy + row;
-    const int bx0 = blockIdx.x * FRAG_STRETCH;
-    const int nb = min(FRAG_STRETCH, vp.nbx - bx0);
-    const uint64_t KEY_INIT = (uint64_t)MAXZ_BITS << 32;
-
-    int32_t *headp = pl.bin_head + (size_t)row * vp.nbx + bx0 + lane;
-    int32_t head = -1;
-    if (lane < nb) {
-        head = *headp;
-        if (head >= 0) *headp = -1;
-        pl.bin_used[(size_t)row * vp.nbx + bx0 + lane] = head >= 0;           // occupancy map for the DoF pass
-    }
+    if (warp >= rows_here) return;
+    const int row = row0 + warp;
+    const int y = g.vy + row;
+    const int32_t head = lane < FRAG_STRETCH ? s_head[warp * FRAG_STRETCH + lane] : -1;
     unsigned mask = __ballot_sync(0xFFFFFFFFu, head >= 0);
 
-    uint32_t *crow = color + (size_t)y * color_pitch + vp.vx + (bx0 << 5);
-    float *drow = depth + (size_t)row * vp.vw + (bx0 << 5);
-    const int px_left = vp.vw - (bx0 << 5);                                 // pixels from the stretch start to the row end
+    uint32_t *crow = color + (size_t)y * color_pitch + g.vx + (bx0 << 5);
+    float *drow = depth + (size_t)row * g.vw + (bx0 << 5);
     const bool aligned = ((reinterpret_cast<uintptr_t>(crow) | reinterpret_cast<uintptr_t>(drow)) & 15) == 0;
     // ---- empty bins ----
     if (mask != 0xFFFFFFFFu) {
@@ -183,37 +246,65 @@ __global__ void __launch_bounds__(FRAG_TPB) k_fragments(DeviceScene s, const Vie
             }
         }
     }
-    // ---- non-empty bins, pass 1: depth resolve.  lane = pixel; the nearest fragment of every pixel is kept in
-    //      registers, depth is written at once, and the winners of the whole 256-pixel stretch are queued in shared
-    //      memory so that shading (pass 2) runs on dense batches of 32 covered pixels instead of on partly
-    //      covered bins ----
+    // ---- non-empty bins, pass 1: depth resolve.
+    //  a. the first lanes walk one bin list each (FRAG_STRETCH pointer chases side by side instead of one after the
+    //     other) and leave the chunk records in shared memory;
+    //  b. lane = pixel: per bin, the nearest fragment of every pixel is kept in registers.  Depth is written at once,
+    //     and the winners of the whole stretch are queued in shared memory so that shading (pass 2) runs on dense
+    //     batches of 32 covered pixels. ----
     FragWarp &fw = fwarp[threadIdx.x >> 5];
+    if (lane < FRAG_STRETCH) {
+        int n = 0;
+        int32_t c = head;
+        while (c >= 0 && n < FRAG_LIST_CAP) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(&pl.chunks[c]);
+            const uint4 r0 = src[0], r1 = src[1];
+            fw.rec[2 * (lane * FRAG_LIST_CAP + n)] = r0; fw.rec[2 * (lane * FRAG_LIST_CAP + n) + 1] = r1;
+            n++;
+            c = (int32_t)r1.z;                                                  // Chunk::next
+        }
+        fw.cnt[lane] = n; fw.cursor[lane] = c;
+    }
+    __syncwarp();
     const unsigned lt = (1u << lane) - 1u;
     uint32_t n_hit = 0;
     const unsigned used = mask;
     while (mask) {
         const int b = __ffs(mask) - 1;
         mask &= mask - 1;
-        int32_t c = __shfl_sync(0xFFFFFFFFu, head, b);
         uint64_t best = KEY_INIT;
         float best_u = 0.f;
         uint32_t best_span = 0xFFFFFFFFu;
-        Chunk ch = pl.chunks[c];
-        while (c >= 0) {
+        const int n = fw.cnt[b];
+        const uint4 *rec = &fw.rec[2 * b * FRAG_LIST_CAP];
+        #pragma unroll 2
+        for (int k = 0; k < n; k++) {
+            const uint4 r0 = rec[2 * k];                                        // frag0, xs_xe, v0, v1
+            const unsigned xs = r0.y & 0xFFu, wd = (r0.y >> 8) - xs;
+            if ((unsigned)lane - xs < wd) {
+                const float2 tb = pl.frag_tb[r0.x + (uint32_t)lane];            // qpixel state, replayed by k_spans
+                const float u = fdiv(tb.x, tb.y);                               // progress(), interpolator.hpp:98
+                const float z = fadd(__uint_as_float(r0.z), fmul(__uint_as_float(r0.w), u));   // value(0), renderer.cpp:488
+                if (z >= NEAR_Z) {                                              // renderer.cpp:489-492
+                    const uint2 r1 = *reinterpret_cast<const uint2 *>(&rec[2 * k + 1]);       // slot, span
+                    const uint64_t key = ((uint64_t)__float_as_uint(z) << 32) | r1.x;
+                    if (key < best) { best = key; best_u = u; best_span = r1.y; }
+                }
+            }
+        }
+        for (int32_t c = fw.cursor[b]; c >= 0;) {                               // a list longer than FRAG_LIST_CAP: the rest, serially
+            const Chunk ch = pl.chunks[c];
             c = ch.next;
-            Chunk nxt = ch;
-            if (c >= 0) nxt = pl.chunks[c];                                     // pointer chase overlapped with this chunk's work
             const int xs = (int)(ch.xs_xe & 0xFFu), xe = (int)(ch.xs_xe >> 8);
             if (lane >= xs && lane < xe) {
-                const float2 tb = pl.frag_tb[ch.frag0 + (uint32_t)lane];        // qpixel state, replayed by k_spans
-                const float u = fdiv(tb.x, tb.y);                               // progress(), interpolator.hpp:98
-                const float z = fadd(ch.v0, fmul(ch.v1, u));                    // value(0), renderer.cpp:488
-                if (z >= NEAR_Z) {                                              // renderer.cpp:489-492
-                    uint64_t key = ((uint64_t)__float_as_uint(z) << 32) | ch.slot;
+                const float2 tb = pl.frag_tb[ch.frag0 + (uint32_t)lane];
+                const float u = fdiv(tb.x, tb.y);
+                const float z = fadd(ch.v0, fmul(ch.v1, u));
+                if (z >= NEAR_Z) {
+                    const uint64_t key = ((uint64_t)__float_as_uint(z) << 32) | ch.slot;
                     if (key < best) { best = key; best_u = u; best_span = ch.span; }
                 }
             }
-            ch = nxt;
         }
         const int px = (b << 5) + lane;
         const bool inside = px < px_left;
@@ -230,7 +321,11 @@ __global__ void __launch_bounds__(FRAG_TPB) k_fragments(DeviceScene s, const Vie
         const int px = fw.idx[k];
         const uint32_t span = fw.span[px];
         const SlotShade *sh = &pl.shades[fw.slot[px]];
-        const Prim pr = s.prims[sh->prim];
+        const uint4 bind = *reinterpret_cast<const uint4 *>(&sh->color);       // colour, tex_off, tw, th
+        Prim pr;
+        pr.color = bind.x; pr.tex_off = bind.y; pr.tw = (int32_t)bind.z; pr.th = (int32_t)bind.w;
+        pr.tw_mask = (pr.tw & (pr.tw - 1)) == 0 ? pr.tw - 1 : -1;
+        pr.th_mask = (pr.th & (pr.th - 1)) == 0 ? pr.th - 1 : -1;
         const uint32_t out = shade<LIGHT, TEX>(&pl.span_shades[span], sh->flat_light, pr, s.texels, vp, fp, fw.u[px]);
         fw.u[px] = __uint_as_float(out);
     }
@@ -615,9 +710,11 @@ template <int LIGHT, int TEX>
 static void launch_frag_t(const DeviceScene &s, const ViewParams &vp, const ViewParams *d_vp, const FrameParams *d_fp, const Pools &p,
                           uint32_t *color, int color_pitch, float *depth, bool count_covered, Counters *h_counters_out, cudaStream_t st)
 {
-    dim3 grid((vp.nbx + FRAG_STRETCH - 1) / FRAG_STRETCH, (vp.band1 - vp.band0 + FRAG_ROWS - 1) / FRAG_ROWS);
-    if (!grid.x || !grid.y) return;
-    k_fragments<LIGHT, TEX><<<grid, FRAG_TPB, 0, st>>>(s, d_vp, d_fp, p, color, color_pitch, depth, count_covered ? 1 : 0, h_counters_out);
+    const int nty = (vp.band1 - vp.band0 + FRAG_ROWS - 1) / FRAG_ROWS, n_tiles = vp.ntx * nty;
+    if (n_tiles <= 0) return;
+    const FragGeom g = { vp.vx, vp.vy, vp.vw, vp.band0, vp.band1, vp.nbx, vp.ntx, n_tiles };
+    const unsigned grid = (unsigned)n_tiles + (unsigned)((n_tiles + FRAG_ROWS - 1) / FRAG_ROWS);
+    k_fragments<LIGHT, TEX><<<grid, FRAG_TPB, 0, st>>>(s, d_vp, d_fp, p, g, color, color_pitch, depth, count_covered ? 1 : 0, h_counters_out);
 }
 
 void launch_fragments(const DeviceScene &s, const ViewParams &vp, const ViewParams *d_vp, const FrameParams *d_fp, const Pools &p,

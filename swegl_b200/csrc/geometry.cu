@@ -218,8 +218,8 @@ SB_DEV RowRange emit_slot(const DeviceScene &s, const ViewParams &vp, const Fram
     sh.prim = prim_id;
     // plain colour shaders never sample the texture: alpha is the material's (pixel_shaders.hpp:28)
     sh.alpha_class = vp.tex_mode == SWEGL_B200_TEX_PLAIN ? ((pr.color >> 24) == 255u ? ALPHA_OPAQUE : ALPHA_UNIFORM) : pr.alpha_class;
-    #pragma unroll
-    for (int k = 0; k < 5; k++) sh.pad[k] = 0;
+    sh.pad0 = 0;
+    sh.color = pr.color; sh.tex_off = pr.tex_off; sh.tw = pr.tw; sh.th = pr.th;
     pl.shades[slot] = sh;
 
     atomicAdd(&pl.counters->n_slots, 1u);
@@ -490,6 +490,7 @@ __global__ void __launch_bounds__(TPB) k_spans(const ViewParams *__restrict__ vp
                     interp_step(w);
                 }
                 pl.chunks[cid] = ch;
+                if (ch.next < 0) note_busy_tile(pl, vp, sh.y[owner] - vp.vy, b);    // first chunk of the bin this frame
             }
         }
         __syncthreads();                                                    // sh is reused by the next group
@@ -657,6 +658,7 @@ __global__ void __launch_bounds__(TPB) k_spans_dense(const ViewParams *__restric
                     interp_step(w);
                 }
                 pl.chunks[cid] = ch;
+                if (ch.next < 0) note_busy_tile(pl, vp, sh.y[owner] - vp.vy, b);    // first chunk of the bin this frame
             }
         }
         __syncthreads();

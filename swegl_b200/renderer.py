@@ -14,7 +14,9 @@ from . import _abi
 
 
 class SweglB200Error(RuntimeError):
-    pass
+    def __init__(self, msg, status=None):
+        super().__init__(msg)
+        self.status = status
 
 
 class Renderer:
@@ -46,7 +48,7 @@ class Renderer:
     def _check(self, rc):
         if rc != _abi.OK:
             msg = self.lib.swegl_b200_last_error(self.ctx)
-            raise SweglB200Error(f"swegl_b200 status {rc}: {msg.decode() if msg else ''}")
+            raise SweglB200Error(f"swegl_b200 status {rc}: {msg.decode() if msg else ''}", rc)
 
     def synchronize(self):
         self._check(self.lib.swegl_b200_synchronize(self.ctx))
@@ -94,6 +96,21 @@ class Renderer:
         self._check(self.lib.swegl_b200_render_viewport(self.ctx, C.byref(vd), pixels.ctypes.data, pixels.strides[0],
                                                         zptr, C.byref(st) if stats else None))
         return st
+
+    def render_async(self, viewport, pixels, zbuffer=None):
+        """Pipelined render(): queues the frame and its copy into `pixels` (page-locked: alloc_host) and returns a
+        ticket; the image is complete after wait(ticket).  Alternate between two host images."""
+        vd = viewport.desc() if not isinstance(viewport, _abi.ViewportDesc) else viewport
+        zptr = zbuffer.ctypes.data if zbuffer is not None else None
+        ticket = C.c_uint64(0)
+        self._check(self.lib.swegl_b200_render_viewport_async(self.ctx, C.byref(vd), pixels.ctypes.data, pixels.strides[0],
+                                                              zptr, C.byref(ticket)))
+        return ticket.value
+
+    def wait(self, ticket):
+        """Blocks until the frame of `ticket` is in host memory.  Raises SweglB200Error(ERR_CAPACITY) if that frame must
+        be submitted again (its pools were too small and have been enlarged)."""
+        self._check(self.lib.swegl_b200_wait(self.ctx, C.c_uint64(ticket)))
 
     def read_screen(self, y0=0, y1=None):
         w, h = self.screen_wh

@@ -179,6 +179,38 @@ def test_transparency_layers_limits(renderer):
         renderer.render(Viewport(8, 0, 392, 300, transparency_layers=2), px)        # flatten() quirk: origin viewports only
 
 
+def test_pipelined_readback_matches_blocking_render(renderer):
+    """render_async/wait (two frames in flight, two pinned host images) delivers the frames render() delivers"""
+    from swegl_b200.scene import Viewport
+    scene, vps, screen, cfg = configs.build("truck_1080")
+    renderer.upload_scene(scene)
+    renderer.set_screen(*screen)
+    views = []
+    for pose in (configs.POSE_TEST1, configs.POSE_CLOSE):
+        v = Viewport(0, 0, screen[0], screen[1], transparency_layers=0)
+        v.camera.apply(pose)
+        views.append(v)
+    want = []
+    for v in views:
+        px = np.zeros((screen[1], screen[0]), np.uint32); z = np.empty((v.h, v.w), np.float32)
+        renderer.begin_frame(scene); renderer.render(v, px, z)
+        want.append((px, z))
+    assert (want[0][0] != want[1][0]).any()
+    images = [renderer.alloc_host((screen[1], screen[0]), np.uint32) for _ in range(2)]
+    depths = [renderer.alloc_host((screen[1], screen[0]), np.float32) for _ in range(2)]
+    tickets = []
+    for i in range(5):
+        renderer.begin_frame(scene)
+        tickets.append(renderer.render_async(views[i & 1], images[i & 1], depths[i & 1]))
+        if i >= 1:
+            renderer.wait(tickets[i - 1])
+            k = (i - 1) & 1
+            assert (images[k] == want[k][0]).all() and (depths[k].view(np.uint32) == want[k][1].view(np.uint32)).all(), f"frame {i - 1}"
+            images[k][:] = 0                                    # the next frame through this image must really arrive
+    renderer.wait(tickets[-1])
+    assert (images[0] == want[0][0]).all()
+
+
 def test_band_scissor_equals_full_frame(renderer, oracle):
     """sort-first row bands: rendering [0,h) as 3 uneven bands gives the full frame"""
     scene, vps, screen, cfg = configs.build("truck_1080")
