@@ -167,7 +167,7 @@ void swegl_b200_destroy(swegl_b200_ctx *ctx)
     drop_graphs(ctx);
     void *ptrs[] = { ctx->d_pos, ctx->d_nrm, ctx->d_uv, ctx->d_vert_node, ctx->d_texels, ctx->d_tris, ctx->d_prims,
                      ctx->d_v_world, ctx->d_v_ndc, ctx->d_n_world, ctx->d_yes, ctx->d_block,
-                     ctx->pools.edges, ctx->pools.shades, ctx->pools.spans, ctx->pools.span_shades, ctx->pools.frag_tb, ctx->pools.row_slot,
+                     ctx->pools.edges, ctx->pools.shades, ctx->pools.spans, ctx->pools.span_shades, ctx->pools.frag_u, ctx->pools.row_slot,
                      ctx->pools.chunks, ctx->pools.bin_head, ctx->pools.bin_used, ctx->pools.tile_stamp, ctx->pools.busy_list,
                      ctx->pools.counters, ctx->d_screen, ctx->d_depth,
                      ctx->d_tmp_color };
@@ -226,7 +226,7 @@ static int ensure_pools(swegl_b200_ctx *ctx, uint32_t rows_cap, uint32_t chunks_
         drop_graphs(ctx);
     }
     if (frags_cap > ctx->pools.frags_cap) {
-        CK(dalloc(ctx->pools.frag_tb, (size_t)frags_cap));
+        CK(dalloc(ctx->pools.frag_u, (size_t)frags_cap));
         ctx->pools.frags_cap = frags_cap;
     }
     if (rows_cap > ctx->pools.rows_cap) {

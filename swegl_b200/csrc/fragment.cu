@@ -1,7 +1,7 @@
 // fragment.cu — the per-pixel half of fill_half_triangle (renderer.cpp:486-499) and the pixel
 // shaders (swegl/render/pixel_shaders.hpp, src/render/pixel_shaders.cpp), plus the DoF-R post pass.
 //
-// k_fragments: one warp owns one 32-pixel, 1-row bin of the viewport; lane = pixel.  The warp walks the
+// k_fragments: a warp owns a stretch of 32-pixel, 1-row bins of the viewport; lane = pixel.  The warp walks a
 // bin's chunk list, each lane reads its pixel's interpolator progress from the fragment stream k_spans
 // wrote (the same fp32 additions and division the CPU does), and keeps the nearest fragment
 // in registers: key = depth bits << 32 | slot id, so equal depths resolve to the earlier draw,
@@ -282,8 +282,7 @@ __global__ void __launch_bounds__(FRAG_TPB) k_fragments(DeviceScene s, const Vie
             const uint4 r0 = rec[2 * k];                                        // frag0, xs_xe, v0, v1
             const unsigned xs = r0.y & 0xFFu, wd = (r0.y >> 8) - xs;
             if ((unsigned)lane - xs < wd) {
-                const float2 tb = pl.frag_tb[r0.x + (uint32_t)lane];            // qpixel state, replayed by k_spans
-                const float u = fdiv(tb.x, tb.y);                               // progress(), interpolator.hpp:98
+                const float u = pl.frag_u[r0.x + (uint32_t)lane];               // qpixel.ualpha, replayed by k_spans
                 const float z = fadd(__uint_as_float(r0.z), fmul(__uint_as_float(r0.w), u));   // value(0), renderer.cpp:488
                 if (z >= NEAR_Z) {                                              // renderer.cpp:489-492
                     const uint2 r1 = *reinterpret_cast<const uint2 *>(&rec[2 * k + 1]);       // slot, span
@@ -297,8 +296,7 @@ __global__ void __launch_bounds__(FRAG_TPB) k_fragments(DeviceScene s, const Vie
             c = ch.next;
             const int xs = (int)(ch.xs_xe & 0xFFu), xe = (int)(ch.xs_xe >> 8);
             if (lane >= xs && lane < xe) {
-                const float2 tb = pl.frag_tb[ch.frag0 + (uint32_t)lane];
-                const float u = fdiv(tb.x, tb.y);
+                const float u = pl.frag_u[ch.frag0 + (uint32_t)lane];
                 const float z = fadd(ch.v0, fmul(ch.v1, u));
                 if (z >= NEAR_Z) {
                     const uint64_t key = ((uint64_t)__float_as_uint(z) << 32) | ch.slot;
@@ -432,8 +430,7 @@ __global__ void __launch_bounds__(FRAG_TPB) k_fragments_layers(DeviceScene s, co
             c = ch.next;
             const int xs = (int)(ch.xs_xe & 0xFFu), xe = (int)(ch.xs_xe >> 8);
             if (lane < xs || lane >= xe) continue;
-            const float2 tb = pl.frag_tb[ch.frag0 + (uint32_t)lane];
-            const float u = fdiv(tb.x, tb.y);
+            const float u = pl.frag_u[ch.frag0 + (uint32_t)lane];
             const float z = fadd(ch.v0, fmul(ch.v1, u));
             if (!(z >= NEAR_Z)) continue;                                   // renderer.cpp:489
             bool opaque = ch.alpha_class == ALPHA_OPAQUE;

@@ -314,30 +314,121 @@ SB_DEV uint32_t warp_incl_scan(uint32_t v, int lane)
     return v;
 }
 
-// shared state of one CTA pass over 32 scanline records
+// One SEGMENT (up to SPAN_SEG bins = 128 pixels) of a span per thread.
+//  * The thread jumps to its segment's first column with radd() (free for a span's first segment) and replays
+//    qpixel.Step() pixel by pixel (renderer.cpp:486); the recurrence is serial in x.  It writes ualpha = topalpha /
+//    bottomalpha (progress(), interpolator.hpp:98) of every pixel to the fragment stream, four pixels per 128-bit
+//    store: the four divisions are independent (they pipeline), and a warp whose 32 threads write 32 different
+//    streams issues a quarter of the memory transactions it would with one store per pixel.  Stream indices are
+//    congruent to the column (relative to the viewport) modulo 4, see the allocation in phase B.
+//  * One chunk is linked into every 32-column bin crossed.  The atomics that return something (previous bin head,
+//    previous tile stamp) are issued side by side, around the pixel walk, so their round trips to L2 overlap.
+template <typename SH>
+SB_DEV void walk_segment(const Pools &pl, const ViewParams &vp, const SH &sh, int owner, uint32_t sg, uint32_t span_id)
+{
+    const uint32_t o_nch = sh.nchunks[owner];
+    const uint32_t c0 = sg * SPAN_SEG, c1 = min(o_nch, c0 + SPAN_SEG);                          // chunks [c0, c1) of the span
+    const int n = (int)(c1 - c0);
+    const int o_x1 = sh.x1[owner], o_x2 = sh.x2[owner];
+    const int b0 = ((o_x1 - vp.vx) >> 5) + (int)c0;
+    int x = c0 == 0 ? o_x1 : vp.vx + (b0 << 5);                             // first column of the segment
+    const int xend = min(vp.vx + ((b0 + n) << 5), o_x2);                    // one past its last column
+    const int row_rel = sh.y[owner] - vp.vy;
+    int32_t *heads = pl.bin_head + (size_t)row_rel * vp.nbx + b0;
+    const uint32_t cid0 = sh.cbase[owner] + c0;
+    int32_t nxt[SPAN_SEG];
+    #pragma unroll
+    for (int j = 0; j < (int)SPAN_SEG; j++) nxt[j] = j < n ? atomicExch(&heads[j], (int32_t)(cid0 + j)) : 0;
+    const uint32_t steps = (uint32_t)(x - o_x1);
+    Interp w;
+    w.topstep = sh.topstep[owner]; w.bottomstep = sh.bottomstep[owner];
+    w.top = radd(sh.top[owner], w.topstep, steps);
+    w.bottom = radd(sh.bottom[owner], w.bottomstep, steps);
+    const uint32_t o_fb = sh.fbase[owner];
+    // ---- the pixel walk ----
+    {
+        float *fu = pl.frag_u + o_fb - o_x1;                                // fu[x] = ualpha at column x; (&fu[x] - pool) % 4 == (x - vx) % 4
+        for (; x < xend && ((x - vp.vx) & 3); x++) { fu[x] = fdiv(w.top, w.bottom); interp_step(w); }
+        for (; x + 4 <= xend; x += 4) {
+            const float t0 = w.top, d0 = w.bottom; interp_step(w);
+            const float t1 = w.top, d1 = w.bottom; interp_step(w);
+            const float t2 = w.top, d2 = w.bottom; interp_step(w);
+            const float t3 = w.top, d3 = w.bottom; interp_step(w);
+            *reinterpret_cast<float4 *>(&fu[x]) = make_float4(fdiv(t0, d0), fdiv(t1, d1), fdiv(t2, d2), fdiv(t3, d3));
+        }
+        for (; x < xend; x++) { fu[x] = fdiv(w.top, w.bottom); interp_step(w); }
+    }
+    // ---- chunk records ----
+    Chunk ch;
+    ch.span = span_id; ch.v0 = sh.v0[owner]; ch.v1 = sh.v1[owner]; ch.slot = sh.slot[owner]; ch.alpha_class = sh.aclass[owner];
+    int xc = sg == 0 ? o_x1 : vp.vx + (b0 << 5);
+    #pragma unroll
+    for (int j = 0; j < (int)SPAN_SEG; j++) {
+        if (j >= n) break;
+        const int binx0 = vp.vx + ((b0 + j) << 5);
+        const int xn = min(binx0 + 32, o_x2);                               // end of this bin's piece of the span
+        ch.frag0 = o_fb + (uint32_t)(binx0 - o_x1);                         // wraps for the span's first bin; lanes < xs never read
+        ch.xs_xe = (uint32_t)(xc - binx0) | ((uint32_t)(xn - binx0) << 8);
+        ch.next = nxt[j];
+        pl.chunks[cid0 + j] = ch;
+        xc = xn;
+    }
+    // first chunk of a bin this frame: note the bin's tile once per frame (Pools::busy_list)
+    uint32_t tl[SPAN_SEG], old[SPAN_SEG];
+    #pragma unroll
+    for (int j = 0; j < (int)SPAN_SEG; j++) {
+        tl[j] = 0xFFFFFFFFu; old[j] = 0;
+        if (j < n && nxt[j] < 0) {
+            const uint32_t t = (uint32_t)((row_rel - (vp.band0 - vp.vy)) / FRAG_ROWS) * (uint32_t)vp.ntx + (uint32_t)((b0 + j) / FRAG_STRETCH);
+            bool dup = false;
+            #pragma unroll
+            for (int q = 0; q < j; q++) dup = dup || tl[q] == t;
+            if (!dup) { tl[j] = t; old[j] = atomicExch(&pl.tile_stamp[t], vp.stamp); }
+        }
+    }
+    #pragma unroll
+    for (int j = 0; j < (int)SPAN_SEG; j++)
+        if (tl[j] != 0xFFFFFFFFu && old[j] != vp.stamp) pl.busy_list[atomicAdd(&pl.counters->n_busy, 1u)] = tl[j];
+}
+
+// shared state of one CTA pass over SPAN_ROWS scanline records
+#ifndef SPAN_ROWS_V
+#define SPAN_ROWS_V 32
+#endif
+static constexpr int SPAN_ROWS = SPAN_ROWS_V;                 // scanline records per CTA pass (a multiple of 32, <= TPB)
 struct SpanCta {
-    float val[6][32];                   // phase A: long x/top/bottom, short x/top/bottom on each scanline
-    int x1[32], x2[32], y[32];          // phase B: the spans ...
-    float top[32], topstep[32], bottom[32], bottomstep[32];   // ... their qpixel at x1 ...
-    float v0[32], v1[32]; uint32_t slot[32], aclass[32];      // ... depth plane, draw-order key, alpha class ...
-    uint32_t nchunks[32], cbase[32], fbase[32], seg_incl[32]; // ... and their allocations / segment prefix
+    float val[6][SPAN_ROWS];            // phase A: long x/top/bottom, short x/top/bottom on each scanline
+    int x1[SPAN_ROWS], x2[SPAN_ROWS], y[SPAN_ROWS];          // phase B: the spans ...
+    float top[SPAN_ROWS], topstep[SPAN_ROWS], bottom[SPAN_ROWS], bottomstep[SPAN_ROWS];   // ... their qpixel at x1 ...
+    float v0[SPAN_ROWS], v1[SPAN_ROWS]; uint32_t slot[SPAN_ROWS], aclass[SPAN_ROWS];      // ... depth plane, draw-order key, alpha class ...
+    uint32_t nchunks[SPAN_ROWS], cbase[SPAN_ROWS], fbase[SPAN_ROWS], seg_incl[SPAN_ROWS]; // ... and their allocations / segment prefix
+    uint32_t warp_segs[(SPAN_ROWS + 31) / 32]; // segments of each 32-row group (phase B warp)
 };
 
-__global__ void __launch_bounds__(TPB) k_spans(const ViewParams *__restrict__ vpp, Pools pl)
+#ifndef SPAN_MINB
+#define SPAN_MINB 6
+#endif
+#ifndef SPAN_TPB_V
+#define SPAN_TPB_V 256
+#endif
+static constexpr int SPAN_TPB = SPAN_TPB_V;
+__global__ void __launch_bounds__(SPAN_TPB, SPAN_MINB) k_spans(const ViewParams *__restrict__ vpp, Pools pl)
 {
     __shared__ SpanCta sh;
     __shared__ ViewParams vp;
-    for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
+    for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += SPAN_TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
     __syncthreads();
     if (pl.counters->overflow & 1u) return;      // some rows were never allocated: the host grows the pool and redoes the frame
     const uint32_t n_rows = min(pl.counters->n_rows, pl.rows_cap);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     Span *spans = pl.spans;
-    for (uint32_t i0 = blockIdx.x * 32; i0 < n_rows; i0 += gridDim.x * 32) {                    // CTA-uniform
-        const uint32_t i = i0 + lane;
-        // ---- phase A: warp r < 6 advances recurrence r of the 32 scanlines to their row with radd()
-        //      (renderer.cpp:553-556 applied (y - first walked row) times); same cost profile across a warp ----
-        if (warp < 6) {
+    for (uint32_t i0 = blockIdx.x * SPAN_ROWS; i0 < n_rows; i0 += gridDim.x * SPAN_ROWS) {      // CTA-uniform
+        // ---- phase A: 6 recurrences x SPAN_ROWS scanlines, one (recurrence, scanline) task per thread and round:
+        //      advance it to its row with radd() (renderer.cpp:553-556 applied (y - first walked row) times);
+        //      a warp works on one recurrence, so its lanes share the cost profile ----
+        for (int task = tid; task < 6 * SPAN_ROWS; task += SPAN_TPB) {
+            const int rec = task / SPAN_ROWS, r = task - rec * SPAN_ROWS;
+            const uint32_t i = i0 + (uint32_t)r;
             float val = 0.f;
             if (i < n_rows) {
                 const uint32_t slot = pl.row_slot[i];
@@ -347,20 +438,22 @@ __global__ void __launch_bounds__(TPB) k_spans(const ViewParams *__restrict__ vp
                 const int nu = max(0, ub - ua);
                 const bool lower = j >= nu;                                 // in-band rows of the upper half come first
                 const int y = lower ? max(e.ya_l, vp.band0) + (j - nu) : ua + j;
-                const SideRec &S = warp < 3 ? e.lng : (lower ? e.sl : e.su);
-                const uint32_t k = warp < 3 ? (uint32_t)(y - e.y_long) : (uint32_t)(y - (lower ? e.ya_l : e.ya_u));
-                const int f = warp % 3;
+                const SideRec &S = rec < 3 ? e.lng : (lower ? e.sl : e.su);
+                const uint32_t k = rec < 3 ? (uint32_t)(y - e.y_long) : (uint32_t)(y - (lower ? e.ya_l : e.ya_u));
+                const int f = rec % 3;
                 const float start = f == 0 ? S.x : (f == 1 ? S.top : S.bottom);
                 const float step = f == 0 ? S.ratio : (f == 1 ? S.topstep : S.bottomstep);
                 val = radd(start, step, k);
             }
-            sh.val[warp][lane] = val;
+            sh.val[rec][r] = val;
         }
         __syncthreads();
-        // ---- phase B: warp 0, lane = scanline: the span (renderer.cpp:469-480), its shading constants, and one
-        //      chunk / fragment-stream allocation for the whole group ----
-        if (warp == 0) {
-            uint32_t nchunks = 0, npix = 0;
+        // ---- phase B: warps 0 .. SPAN_ROWS/32-1, lane = scanline: the span (renderer.cpp:469-480), its shading
+        //      constants, and one chunk / fragment-stream allocation per warp ----
+        if (warp < (SPAN_ROWS + 31) / 32) {
+            const int r = warp * 32 + lane;
+            const uint32_t i = r < SPAN_ROWS ? i0 + (uint32_t)r : 0xFFFFFFFFu;
+            uint32_t nchunks = 0, npix = 0, lead = 0;
             int x1 = 0, x2 = 0, y = 0;
             Interp q; q.top = q.topstep = q.bottom = q.bottomstep = q.v0 = q.v1 = 0.f;
             Span sp; sp.frag_base = 0; sp.pad0 = 0; sp.v0 = sp.v1 = sp.pl = sp.pr = 0.f; sp.x1x2 = 0; sp.slot_flags = 0;
@@ -373,8 +466,8 @@ __global__ void __launch_bounds__(TPB) k_spans(const ViewParams *__restrict__ vp
                 const bool lower = j >= nu;
                 y = lower ? max(e.ya_l, vp.band0) + (j - nu) : ua + j;
                 const bool lor = lower ? ((e.flags >> 1) & 1u) : (e.flags & 1u);
-                const float gx = sh.val[0][lane], gtop = sh.val[1][lane], gbot = sh.val[2][lane];
-                const float sx = sh.val[3][lane], stop = sh.val[4][lane], sbot = sh.val[5][lane];
+                const float gx = sh.val[0][r], gtop = sh.val[1][r], gbot = sh.val[2][r];
+                const float sx = sh.val[3][r], stop = sh.val[4][r], sbot = sh.val[5][r];
                 const float lx = lor ? sx : gx, rx = lor ? gx : sx;
                 const float ltop = lor ? stop : gtop, lbot = lor ? sbot : gbot, rtop = lor ? gtop : stop, rbot = lor ? gbot : sbot;
 
@@ -397,7 +490,9 @@ __global__ void __launch_bounds__(TPB) k_spans(const ViewParams *__restrict__ vp
                     sp.v0 = q.v0; sp.v1 = q.v1;
                     sp.x1x2 = (uint32_t)x1 | ((uint32_t)x2 << 16);
                     nchunks = (uint32_t)(((x2 - 1 - vp.vx) >> 5) - ((x1 - vp.vx) >> 5) + 1);
-                    npix = (uint32_t)(x2 - x1);
+                    // stream entries: index % 4 == (column - vx) % 4 so that walk_segment can store four at a time
+                    lead = (uint32_t)(x1 - vp.vx) & 3u;
+                    npix = (lead + (uint32_t)(x2 - x1) + 3u) & ~3u;
                     // prepare_for_{upper,lower}_triangle + prepare_for_scanline of the pixel shaders
                     // (pixel_shaders.cpp:106-158, 320-346), once per span instead of once per pixel.
                     // long side: base v0, dir v2-v0; short side: upper (v0, v1-v0) / lower (v1, v2-v1)
@@ -438,60 +533,38 @@ __global__ void __launch_bounds__(TPB) k_spans(const ViewParams *__restrict__ vp
             const bool room = wbase + c_tot <= pl.chunks_cap && fbase + p_tot <= pl.frags_cap;
             if (!room && lane == 0)
                 atomicOr(&pl.counters->overflow, (wbase + c_tot > pl.chunks_cap ? 2u : 0u) | (fbase + p_tot > pl.frags_cap ? 4u : 0u));
-            sp.frag_base = fbase + p_incl - npix;
+            sp.frag_base = fbase + p_incl - npix + lead;                    // entry of column x1
             if (i < n_rows) spans[i] = sp;
             if (!room) nchunks = 0;                                         // nothing is walked; the host redoes the frame
             const uint32_t nseg = (nchunks + SPAN_SEG - 1) / SPAN_SEG;
-            sh.x1[lane] = x1; sh.x2[lane] = x2; sh.y[lane] = y;
-            sh.top[lane] = q.top; sh.topstep[lane] = q.topstep; sh.bottom[lane] = q.bottom; sh.bottomstep[lane] = q.bottomstep;
-            sh.v0[lane] = sp.v0; sh.v1[lane] = sp.v1; sh.slot[lane] = sp.slot_flags >> 2;
-            sh.aclass[lane] = (i < n_rows && nchunks) ? pl.shades[sp.slot_flags >> 2].alpha_class : 0u;
-            sh.nchunks[lane] = nchunks; sh.cbase[lane] = wbase + c_incl - (room ? nchunks : 0u); sh.fbase[lane] = sp.frag_base;
-            sh.seg_incl[lane] = warp_incl_scan(nseg, lane);
+            if (r < SPAN_ROWS) {
+            sh.x1[r] = x1; sh.x2[r] = x2; sh.y[r] = y;
+            sh.top[r] = q.top; sh.topstep[r] = q.topstep; sh.bottom[r] = q.bottom; sh.bottomstep[r] = q.bottomstep;
+            sh.v0[r] = sp.v0; sh.v1[r] = sp.v1; sh.slot[r] = sp.slot_flags >> 2;
+            sh.aclass[r] = (i < n_rows && nchunks) ? pl.shades[sp.slot_flags >> 2].alpha_class : 0u;
+            sh.nchunks[r] = nchunks; sh.cbase[r] = wbase + c_incl - (room ? nchunks : 0u); sh.fbase[r] = sp.frag_base;
+            }
+            const uint32_t s_incl = warp_incl_scan(nseg, lane);
+            if (r < SPAN_ROWS) sh.seg_incl[r] = s_incl;                      // warp-local; made CTA-wide below
+            if (lane == 31) sh.warp_segs[warp] = s_incl;
         }
         __syncthreads();
+        if (SPAN_ROWS > 32 && tid >= 32 && tid < SPAN_ROWS) {               // add the segment totals of the warps before
+            uint32_t before = 0;
+            for (int w = 0; w < warp; w++) before += sh.warp_segs[w];
+            sh.seg_incl[tid] += before;
+        }
+        if (SPAN_ROWS > 32) __syncthreads();
         // ---- phase C: thread = SEGMENT (SPAN_SEG bins = 128 pixels) of the group's spans, so a screen-wide span
-        //      is walked by many threads.  A thread jumps to its segment's first column with radd() (free for a
-        //      span's first segment), then replays qpixel.Step() pixel by pixel (renderer.cpp:486), streaming the
-        //      interpolator state of every pixel and linking one chunk into every 32-column bin it crosses. ----
-        const uint32_t total = sh.seg_incl[31];
-        for (uint32_t t = tid; t < total; t += TPB) {
+        //      is walked by many threads (walk_segment) ----
+        const uint32_t total = sh.seg_incl[SPAN_ROWS - 1];
+        for (uint32_t t = tid; t < total; t += SPAN_TPB) {
             int owner = 0;                                                  // first row whose inclusive prefix exceeds t
             #pragma unroll
-            for (int stp = 16; stp >= 1; stp >>= 1)
+            for (int stp = SPAN_ROWS / 2; stp >= 1; stp >>= 1)
                 if (sh.seg_incl[owner + stp - 1] <= t) owner += stp;
-            const uint32_t o_nch = sh.nchunks[owner];
-            const uint32_t sg = t - (sh.seg_incl[owner] - (o_nch + SPAN_SEG - 1) / SPAN_SEG);   // segment index inside its span
-            const uint32_t c0 = sg * SPAN_SEG, c1 = min(o_nch, c0 + SPAN_SEG);                  // chunks [c0, c1) of the span
-            const int o_x1 = sh.x1[owner], o_x2 = sh.x2[owner];
-            int b = ((o_x1 - vp.vx) >> 5) + (int)c0;
-            int x = c0 == 0 ? o_x1 : vp.vx + (b << 5);                      // first column of the segment
-            const uint32_t steps = (uint32_t)(x - o_x1);
-            Interp w;
-            w.topstep = sh.topstep[owner]; w.bottomstep = sh.bottomstep[owner];
-            w.top = radd(sh.top[owner], w.topstep, steps);
-            w.bottom = radd(sh.bottom[owner], w.bottomstep, steps);
-            int32_t *heads = pl.bin_head + (size_t)(sh.y[owner] - vp.vy) * vp.nbx;
-            float2 *ftb = pl.frag_tb + sh.fbase[owner] - o_x1;              // ftb[x] = qpixel (topalpha, bottomalpha) at column x
-            const uint32_t span_id = i0 + (uint32_t)owner;
-            uint32_t cid = sh.cbase[owner] + c0;
-            const float o_v0 = sh.v0[owner], o_v1 = sh.v1[owner];
-            const uint32_t o_slot = sh.slot[owner], o_fb = sh.fbase[owner], o_ac = sh.aclass[owner];
-            for (uint32_t c = c0; c < c1; c++, b++, cid++) {
-                Chunk ch;
-                ch.span = span_id; ch.v0 = o_v0; ch.v1 = o_v1; ch.slot = o_slot; ch.alpha_class = o_ac;
-                ch.next = atomicExch(&heads[b], (int32_t)cid);              // latency hidden behind the pixel loop below
-                const int binx0 = vp.vx + (b << 5);
-                const int xn = min(binx0 + 32, o_x2);                       // end of this bin's piece of the span
-                ch.frag0 = o_fb + (uint32_t)(binx0 - o_x1);                 // wraps for the span's first bin; lanes < xs never read
-                ch.xs_xe = (uint32_t)(x - binx0) | ((uint32_t)(xn - binx0) << 8);
-                for (; x < xn; x++) {
-                    ftb[x] = make_float2(w.top, w.bottom);                  // k_fragments divides: ualpha, interpolator.hpp:98
-                    interp_step(w);
-                }
-                pl.chunks[cid] = ch;
-                if (ch.next < 0) note_busy_tile(pl, vp, sh.y[owner] - vp.vy, b);    // first chunk of the bin this frame
-            }
+            const uint32_t sg = t - (sh.seg_incl[owner] - (sh.nchunks[owner] + SPAN_SEG - 1) / SPAN_SEG);   // segment index inside its span
+            walk_segment(pl, vp, sh, owner, sg, i0 + (uint32_t)owner);
         }
         __syncthreads();                                                    // sh is reused by the next group
     }
@@ -526,7 +599,7 @@ __global__ void __launch_bounds__(TPB) k_spans_dense(const ViewParams *__restric
     Span *spans = pl.spans;
     for (uint32_t i0 = blockIdx.x * TPB; i0 < n_rows; i0 += gridDim.x * TPB) {                  // CTA-uniform
         const uint32_t i = i0 + tid;
-        uint32_t nchunks = 0, npix = 0;
+        uint32_t nchunks = 0, npix = 0, lead = 0;
         int x1 = 0, x2 = 0, y = 0;
         Interp q; q.top = q.topstep = q.bottom = q.bottomstep = q.v0 = q.v1 = 0.f;
         Span sp; sp.frag_base = 0; sp.pad0 = 0; sp.v0 = sp.v1 = sp.pl = sp.pr = 0.f; sp.x1x2 = 0; sp.slot_flags = 0;
@@ -565,7 +638,8 @@ __global__ void __launch_bounds__(TPB) k_spans_dense(const ViewParams *__restric
                 sp.v0 = q.v0; sp.v1 = q.v1;
                 sp.x1x2 = (uint32_t)x1 | ((uint32_t)x2 << 16);
                 nchunks = (uint32_t)(((x2 - 1 - vp.vx) >> 5) - ((x1 - vp.vx) >> 5) + 1);
-                npix = (uint32_t)(x2 - x1);
+                lead = (uint32_t)(x1 - vp.vx) & 3u;                         // stream index % 4 == (column - vx) % 4, as in k_spans
+                npix = (lead + (uint32_t)(x2 - x1) + 3u) & ~3u;
                 const SlotShade &ssh = pl.shades[slot];                     // prepare_for_scanline, once per span
                 SpanShade ss;
                 #pragma unroll
@@ -612,7 +686,7 @@ __global__ void __launch_bounds__(TPB) k_spans_dense(const ViewParams *__restric
         }
         __syncthreads();
         const bool room = sh.room != 0;
-        sp.frag_base = sh.base[1] + p_off + p_incl - npix;
+        sp.frag_base = sh.base[1] + p_off + p_incl - npix + lead;
         if (i < n_rows) spans[i] = sp;
         sh.x1[tid] = x1; sh.x2[tid] = x2; sh.y[tid] = y;
         sh.top[tid] = q.top; sh.topstep[tid] = q.topstep; sh.bottom[tid] = q.bottom; sh.bottomstep[tid] = q.bottomstep;
@@ -628,38 +702,8 @@ __global__ void __launch_bounds__(TPB) k_spans_dense(const ViewParams *__restric
             #pragma unroll
             for (int stp = TPB / 2; stp >= 1; stp >>= 1)
                 if (sh.seg_incl[owner + stp - 1] <= t) owner += stp;
-            const uint32_t o_nch = sh.nchunks[owner];
-            const uint32_t sg = t - (sh.seg_incl[owner] - (o_nch + SPAN_SEG - 1) / SPAN_SEG);
-            const uint32_t c0 = sg * SPAN_SEG, c1 = min(o_nch, c0 + SPAN_SEG);
-            const int o_x1 = sh.x1[owner], o_x2 = sh.x2[owner];
-            int b = ((o_x1 - vp.vx) >> 5) + (int)c0;
-            int x = c0 == 0 ? o_x1 : vp.vx + (b << 5);
-            const uint32_t steps = (uint32_t)(x - o_x1);
-            Interp w;
-            w.topstep = sh.topstep[owner]; w.bottomstep = sh.bottomstep[owner];
-            w.top = radd(sh.top[owner], w.topstep, steps);
-            w.bottom = radd(sh.bottom[owner], w.bottomstep, steps);
-            int32_t *heads = pl.bin_head + (size_t)(sh.y[owner] - vp.vy) * vp.nbx;
-            float2 *ftb = pl.frag_tb + sh.fbase[owner] - o_x1;
-            const uint32_t span_id = i0 + (uint32_t)owner;
-            uint32_t cid = sh.cbase[owner] + c0;
-            const float o_v0 = sh.v0[owner], o_v1 = sh.v1[owner];
-            const uint32_t o_slot = sh.slot[owner], o_fb = sh.fbase[owner], o_ac = sh.aclass[owner];
-            for (uint32_t c = c0; c < c1; c++, b++, cid++) {
-                Chunk ch;
-                ch.span = span_id; ch.v0 = o_v0; ch.v1 = o_v1; ch.slot = o_slot; ch.alpha_class = o_ac;
-                ch.next = atomicExch(&heads[b], (int32_t)cid);
-                const int binx0 = vp.vx + (b << 5);
-                const int xn = min(binx0 + 32, o_x2);
-                ch.frag0 = o_fb + (uint32_t)(binx0 - o_x1);
-                ch.xs_xe = (uint32_t)(x - binx0) | ((uint32_t)(xn - binx0) << 8);
-                for (; x < xn; x++) {
-                    ftb[x] = make_float2(w.top, w.bottom);
-                    interp_step(w);
-                }
-                pl.chunks[cid] = ch;
-                if (ch.next < 0) note_busy_tile(pl, vp, sh.y[owner] - vp.vy, b);    // first chunk of the bin this frame
-            }
+            const uint32_t sg = t - (sh.seg_incl[owner] - (sh.nchunks[owner] + SPAN_SEG - 1) / SPAN_SEG);
+            walk_segment(pl, vp, sh, owner, sg, i0 + (uint32_t)owner);
         }
         __syncthreads();
     }
@@ -687,7 +731,7 @@ void launch_setup(const DeviceScene &s, const ViewParams *d_vp, const FrameParam
 void launch_spans(const ViewParams *d_vp, const Pools &p, bool dense, cudaStream_t st)
 {
     if (dense) k_spans_dense<<<148 * 8, TPB, 0, st>>>(d_vp, p);      // persistent CTAs, 256 scanline records per pass
-    else k_spans<<<148 * 16, TPB, 0, st>>>(d_vp, p);                 // persistent CTAs, 32 scanline records per pass
+    else k_spans<<<148 * 16 * (256 / SPAN_TPB), SPAN_TPB, 0, st>>>(d_vp, p);                 // persistent CTAs, SPAN_ROWS scanline records per pass
 }
 
 } // namespace sb
