@@ -314,43 +314,91 @@ def sharded_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
     vp = vps[0]
     r.upload_scene(scene)
     r.set_screen(*screen)
-    y0, y1 = sharding.band_rows(vp.h, world, rank)
-    vp.band = (y0, y1) if world > 1 else (0, 0)
-    desc = vp.desc()
+    bands = [sharding.band_rows(vp.h, world, k) for k in range(world)]
     nodes = scene.node_matrices()
     screen_ptr, _ = r.device_buffers()
     full = torch.as_tensor(_DevArray(screen_ptr, (screen[1], screen[0])), device="cuda")
+    state = {}
+
+    def set_bands(b):
+        state["bands"] = b
+        vp.band = b[rank] if world > 1 else (0, 0)
+        state["desc"] = vp.desc()
+
+    token = torch.zeros(1, device="cuda")
 
     def one():
         r.begin_frame(scene, nodes)
-        r.render_device(desc, stats=False)
+        r.render_device(state["desc"], stats=False)
         if world > 1:
-            return sharding.gather_bands_inplace(full, vp.h, dist, dst=0)      # bands land in place in rank 0's screen
+            if state.get("peer"):
+                sharding.frame_barrier(dist, token)     # the bands were written into rank 0's screen by the kernels
+            else:
+                sharding.gather_bands_inplace(full, vp.h, dist, dst=0, bands=state["bands"])   # NCCL send/recv into place
         return full
+    set_bands(bands)
     r.begin_frame(scene, nodes)
-    r.render_device(desc, stats=True)                   # sizes the pools for this workload
-    for _ in range(max(warmup, 3)):
-        one()
-    r.synchronize()
-    torch.cuda.synchronize()
+    r.render_device(state["desc"], stats=True)          # sizes the pools for this workload
+    one()
     if world > 1:
-        dist.barrier()
-    ms = []
-    for _ in range(steps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        one()
-        e1.record()
+        # temporal coherence: rebalance the bands on the coverage of the frame just gathered (covered pixels per row
+        # + a share for the per-row fixed work), computed on rank 0 and broadcast
+        cuts = torch.zeros(world + 1, dtype=torch.int64, device="cuda")
+        if rank == 0:
+            r.synchronize(); torch.cuda.synchronize()
+            cov = ((full >> 24) != 0).sum(dim=1).to(torch.float64) + 0.05 * screen[0]
+            b = sharding.balanced_bands(cov.cpu().tolist(), world)
+            cuts = torch.tensor([b[0][0]] + [y1 for _, y1 in b], dtype=torch.int64, device="cuda")
+        dist.broadcast(cuts, src=0)
+        c = [int(v) for v in cuts.cpu().tolist()]
+        set_bands([(c[k], c[k + 1]) for k in range(world)])
+        r.begin_frame(scene, nodes)
+        r.render_device(state["desc"], stats=True)      # pools for the new band
+    def timed():
+        for _ in range(max(warmup, 3)):
+            one()
         r.synchronize()
         torch.cuda.synchronize()
-        ms.append(e0.elapsed_time(e1))
-    t = torch.tensor([sum(ms) / len(ms)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.barrier()
+        ms = []
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            one()
+            e1.record()
+            r.synchronize()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        t = torch.tensor([sum(ms) / len(ms)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    ms_gather = timed()                                 # bands sent to rank 0 after rendering (NCCL send/recv)
+    ms_peer, peer_ok = None, None
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    st = r.render_device(desc, stats=True)
-    return {"workload": name, "description": cfg["desc"], "ms_per_frame": float(t.item()), "fps": 1e3 / float(t.item()),
-            "n_gpus": world, "partition": "contiguous row bands of the full viewport + NCCL gather to rank 0" if world > 1 else "single GPU",
+        # the fused form: every rank's last kernel stores its band into rank 0's screen over NVLink (CUDA IPC mapping)
+        checksum = int(full.to(torch.int64).sum().item()) if rank == 0 else 0
+        sharding.share_screen(r, dist, dst=0, device="cuda")
+        state["peer"] = True
+        if rank == 0:
+            full.zero_()
+        ms_peer = timed()
+        if rank == 0:
+            peer_ok = int(full.to(torch.int64).sum().item()) == checksum        # same frame as the gathered one
+        r.set_color_target(None)
+        state["peer"] = False
+    st = r.render_device(state["desc"], stats=True)
+    best = ms_gather if ms_peer is None else min(ms_gather, ms_peer)
+    return {"workload": name, "description": cfg["desc"], "ms_per_frame": best, "fps": 1e3 / best,
+            "ms_per_frame_nccl_gather": ms_gather if world > 1 else None,
+            "ms_per_frame_peer_write": ms_peer, "peer_write_frame_matches_gather": peer_ok,
+            "n_gpus": world,
+            "partition": ("contiguous row bands of the full viewport, balanced on the previous frame's coverage per row; "
+                          "output either sent to rank 0 with NCCL send/recv after rendering, or stored into rank 0's screen "
+                          "by the frame's last kernel over NVLink peer memory + a one-element all-reduce") if world > 1 else "single GPU",
+            "bands": [list(b) for b in state["bands"]],
             "rank0_band_covered_pixels": int(st.n_covered), "scaling": "strong"}
 
 
@@ -379,8 +427,11 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — swegl_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
-    # stdout carries exactly one JSON line: NCCL's version banner / debug output goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner) goes to stderr.
+    # The original stdout is kept aside for that line.
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from swegl_b200 import Renderer
@@ -475,7 +526,8 @@ def main():
         line["also"] = also
     if sharded:
         line["sharded_frame"] = sharded
-    print(json.dumps(line))
+    json_out.write(json.dumps(line) + "\n")
+    json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 

@@ -192,6 +192,19 @@ int  swegl_b200_render_viewport_async(swegl_b200_ctx *ctx, const swegl_b200_view
                                       void *pixels, int32_t pitch_bytes, float *zbuffer, uint64_t *ticket);
 int  swegl_b200_wait(swegl_b200_ctx *ctx, uint64_t ticket);
 
+/* ---- multi-GPU single-frame output over peer memory ----
+ * Sort-first sharding gives every GPU a row band of the viewport (viewport_desc.band_y0/y1).  Instead of rendering
+ * into its own screen and sending the band afterwards, a GPU can write its finished pixels straight into the screen
+ * of the GPU that assembles the frame: that GPU exports its screen (a 64-byte CUDA IPC handle, to be shipped to the
+ * other processes by any means, e.g. a torch.distributed broadcast), the others import it and select it as their
+ * colour target.  The stores of the last kernel of the frame (k_fragments, or k_dof with the DoF pass) then travel
+ * over NVLink while the kernel is still computing; what is left of the "gather" is a barrier.
+ * set_color_target(NULL) restores the context's own screen; the target must have the context's screen size.
+ * Within one process a target can simply be another context's screen pointer (swegl_b200_device_buffers). */
+int  swegl_b200_export_screen(swegl_b200_ctx *ctx, void *handle64);
+int  swegl_b200_import_screen(swegl_b200_ctx *ctx, const void *handle64, void **peer_screen);
+int  swegl_b200_set_color_target(swegl_b200_ctx *ctx, void *device_screen);
+
 /* ---- read-back of device state (parity tests, multi-GPU gather) ---- */
 /* device pointers of the screen (screen_w*screen_h words) and of the last viewport's depth */
 int  swegl_b200_device_buffers(swegl_b200_ctx *ctx, void **screen_dev, void **depth_dev);

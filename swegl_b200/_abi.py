@@ -84,6 +84,9 @@ SYMBOLS = [
     ("swegl_b200_render_viewport_async", C.c_int, [C.c_void_p, C.POINTER(ViewportDesc), C.c_void_p, C.c_int32,
                                                    C.c_void_p, C.POINTER(C.c_uint64)]),
     ("swegl_b200_wait", C.c_int, [C.c_void_p, C.c_uint64]),
+    ("swegl_b200_export_screen", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("swegl_b200_import_screen", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    ("swegl_b200_set_color_target", C.c_int, [C.c_void_p, C.c_void_p]),
     ("swegl_b200_device_buffers", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     ("swegl_b200_read_screen", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     ("swegl_b200_read_depth", C.c_int, [C.c_void_p, C.c_void_p]),

@@ -55,7 +55,7 @@ struct swegl_b200_ctx {
     } out[2];
     cudaStream_t copy_stream = nullptr;
     uint64_t ticket_seq = 0;
-    struct ViewGraph { int32_t key[13]; cudaGraphExec_t exec[2]; };
+    struct ViewGraph { int32_t key[15]; cudaGraphExec_t exec[2]; };
     std::vector<ViewGraph> view_graphs;
     bool graphs_enabled = true;
     bool dense_spans = false;           // which span kernel the next frames use (see choose_span_kernel)
@@ -69,6 +69,8 @@ struct swegl_b200_ctx {
     // screen
     int sw = 0, sh = 0;
     uint32_t *d_screen = nullptr; float *d_depth = nullptr; uint32_t *d_tmp_color = nullptr;
+    uint32_t *color_target = nullptr;   // where finished colour goes instead of d_screen (another context's / GPU's screen)
+    std::vector<void *> imported;       // cudaIpcOpenMemHandle mappings to close
 
     ViewParams last_vp{}; bool have_vp = false;
     ViewParams dof_cache{}; float dof_cache_depth = 0.f; bool dof_cache_valid = false;   // DoF thresholds per focal_depth
@@ -179,6 +181,7 @@ void swegl_b200_destroy(swegl_b200_ctx *ctx)
         if (sl.done) cudaEventDestroy(sl.done);
     }
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (void *m : ctx->imported) cudaIpcCloseMemHandle(m);
     for (auto &ob : ctx->out) {
         if (ob.color) cudaFree(ob.color);
         if (ob.depth) cudaFree(ob.depth);
@@ -437,6 +440,7 @@ int swegl_b200_set_screen(swegl_b200_ctx *ctx, int32_t w, int32_t h)
     CK(dalloc(ctx->pools.busy_list, bins));
     ctx->bins_cap = bins;
     ctx->sw = w; ctx->sh = h;
+    ctx->color_target = nullptr;
     return SWEGL_B200_OK;
 }
 
@@ -589,7 +593,8 @@ static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const Vie
     if (timing) cudaEventRecord(ctx->ev[2], st);
     launch_spans(ctx->d_vp(), ctx->pools, ctx->dense_spans, st); launches++;
     if (timing) cudaEventRecord(ctx->ev[3], st);
-    uint32_t *color = dof ? ctx->d_tmp_color - ((size_t)vp.vy * vp.vw + vp.vx) : ctx->d_screen;
+    uint32_t *screen_out = ctx->color_target ? ctx->color_target : ctx->d_screen;
+    uint32_t *color = dof ? ctx->d_tmp_color - ((size_t)vp.vy * vp.vw + vp.vx) : screen_out;
     const int color_pitch = dof ? vp.vw : ctx->sw;
     // asynchronous frames publish their counters from inside k_fragments; synchronous ones copy them at the end
     (vp.n_layers > 0 ? launch_fragments_layers : launch_fragments)(ctx->ds, vp, ctx->d_vp(), ctx->d_fp(), ctx->pools, color, color_pitch,
@@ -598,7 +603,7 @@ static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const Vie
     if (timing) cudaEventRecord(ctx->ev[4], st);
     if (dof) {
         launch_dof(ctx->d_vp(), ctx->pools.bin_used, vp.nbx, ctx->d_tmp_color, vp.vw, ctx->d_depth,
-                   ctx->d_screen + (size_t)vp.vy * ctx->sw + vp.vx, ctx->sw, vp.vw, vp.vh, out.band0 - vp.vy, out.band1 - vp.vy, st);
+                   screen_out + (size_t)vp.vy * ctx->sw + vp.vx, ctx->sw, vp.vw, vp.vh, out.band0 - vp.vy, out.band1 - vp.vy, st);
         launches++;
     }
     if (timing) cudaEventRecord(ctx->ev[5], st);
@@ -645,8 +650,9 @@ static int render_async(swegl_b200_ctx *ctx, const ViewParams &out, bool dof)
     if (!ctx->graphs_enabled) {
         issue_view(ctx, out, vp, sl, with_frame, dof, false, false, false, sl.counters);
     } else {
-        const int32_t key[13] = { out.vx, out.vy, out.vw, out.vh, out.band0, out.band1, out.light_mode, out.tex_mode, (dof ? 1 : 0) | (out.n_layers << 1),
-                                  ctx->sw, ctx->sh, with_frame ? 1 : 0, ctx->dense_spans ? 1 : 0 };
+        const uint64_t tgt = (uint64_t)reinterpret_cast<uintptr_t>(ctx->color_target);
+        const int32_t key[15] = { out.vx, out.vy, out.vw, out.vh, out.band0, out.band1, out.light_mode, out.tex_mode, (dof ? 1 : 0) | (out.n_layers << 1),
+                                  ctx->sw, ctx->sh, with_frame ? 1 : 0, ctx->dense_spans ? 1 : 0, (int32_t)(tgt & 0xFFFFFFFFu), (int32_t)(tgt >> 32) };
         swegl_b200_ctx::ViewGraph *vg = nullptr;
         for (auto &g : ctx->view_graphs) if (memcmp(g.key, key, sizeof key) == 0) { vg = &g; break; }
         if (!vg) {
@@ -815,6 +821,37 @@ int swegl_b200_wait(swegl_b200_ctx *ctx, uint64_t ticket)
             return fail(ctx, SWEGL_B200_ERR_CAPACITY, "the frame overflowed the span/chunk/fragment pools (now enlarged): submit it again");
         }
     ctx->err.clear();
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_set_color_target(swegl_b200_ctx *ctx, void *device_screen)
+{
+    if (!ctx || !ctx->d_screen) return fail(ctx, SWEGL_B200_ERR_STATE, "set_color_target before set_screen");
+    ctx->color_target = static_cast<uint32_t *>(device_screen);
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_export_screen(swegl_b200_ctx *ctx, void *handle64)
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI promises a 64-byte handle");
+    if (!ctx || !handle64 || !ctx->d_screen) return fail(ctx, SWEGL_B200_ERR_STATE, "export_screen before set_screen");
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->d_screen));
+    memcpy(handle64, &h, sizeof h);
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_import_screen(swegl_b200_ctx *ctx, const void *handle64, void **peer_screen)
+{
+    if (!ctx || !handle64 || !peer_screen) return fail(ctx, SWEGL_B200_ERR_ARG, "import_screen: null argument");
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof h);
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->imported.push_back(p);
+    *peer_screen = p;
     return SWEGL_B200_OK;
 }
 

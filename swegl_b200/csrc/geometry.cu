@@ -260,6 +260,18 @@ __global__ void __launch_bounds__(128) k_setup(DeviceScene s, const ViewParams *
         tr = s.tris[t];
         go = s.yes[tr.i0] && s.yes[tr.i1] && s.yes[tr.i2];                  // renderer.cpp:248-253
     }
+    if (go && (vp.band0 > vp.vy || vp.band1 < vp.vy + vp.vh)) {
+        // a row band of the viewport (sort-first sharding): a triangle that is not near-clipped walks scanlines
+        // [ceil(min y), ceil(max y)) only (renderer.cpp:375-394), so one that misses the band is dropped here,
+        // before its world positions, normals and texture coordinates are fetched
+        const float za = s.v_ndc[3 * tr.i0 + 2], zb = s.v_ndc[3 * tr.i1 + 2], zc = s.v_ndc[3 * tr.i2 + 2];
+        if (za >= NEAR_Z && zb >= NEAR_Z && zc >= NEAR_Z) {
+            const int ya = ceil_i(fadd(fmul(vp.vp_m11, s.v_ndc[3 * tr.i0 + 1]), vp.vp_m13));   // frustum_to_viewport, as load_sv
+            const int yb = ceil_i(fadd(fmul(vp.vp_m11, s.v_ndc[3 * tr.i1 + 1]), vp.vp_m13));
+            const int yc = ceil_i(fadd(fmul(vp.vp_m11, s.v_ndc[3 * tr.i2 + 1]), vp.vp_m13));
+            if (max(ya, max(yb, yc)) <= vp.band0 || min(ya, min(yb, yc)) >= vp.band1) go = false;
+        }
+    }
     if (go) {
         Prim pr = s.prims[tr.prim];
         SV a = load_sv(s, vp, tr.i0), b = load_sv(s, vp, tr.i1), c = load_sv(s, vp, tr.i2);

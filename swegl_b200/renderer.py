@@ -112,6 +112,23 @@ class Renderer:
         be submitted again (its pools were too small and have been enlarged)."""
         self._check(self.lib.swegl_b200_wait(self.ctx, C.c_uint64(ticket)))
 
+    def export_screen(self):
+        """64-byte CUDA IPC handle of this context's device screen (ship it to the other ranks)"""
+        buf = (C.c_uint8 * 64)()
+        self._check(self.lib.swegl_b200_export_screen(self.ctx, buf))
+        return bytes(buf)
+
+    def import_screen(self, handle):
+        """map another process's exported screen; returns its device pointer in this process"""
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        self._check(self.lib.swegl_b200_import_screen(self.ctx, buf, C.byref(p)))
+        return p.value
+
+    def set_color_target(self, device_ptr):
+        """finished colour goes to `device_ptr` (another context's / GPU's screen) instead of the own screen; None resets"""
+        self._check(self.lib.swegl_b200_set_color_target(self.ctx, C.c_void_p(device_ptr) if device_ptr else None))
+
     def read_screen(self, y0=0, y1=None):
         w, h = self.screen_wh
         y1 = h if y1 is None else y1

@@ -15,6 +15,35 @@ def band_rows(height, world, rank):
     return y0, y0 + base + (1 if rank < rem else 0)
 
 
+def balanced_bands(row_cost, world, min_rows=8):
+    """Contiguous bands [(y0, y1)] * world whose summed `row_cost` (a sequence, one non-negative number per row --
+    e.g. the covered pixels of each row in the previous frame plus a constant for the per-row fixed work) is as equal
+    as a prefix-sum split allows.  Every band gets at least `min_rows` rows.  Same result on every rank."""
+    cost = [float(c) for c in row_cost]
+    height = len(cost)
+    if world <= 1:
+        return [(0, height)]
+    if height < world * min_rows:
+        return [band_rows(height, world, r) for r in range(world)]
+    total = sum(cost)
+    if total <= 0:
+        return [band_rows(height, world, r) for r in range(world)]
+    cuts, acc, y = [0], 0.0, 0
+    for k in range(1, world):
+        target = total * k / world
+        while y < height and acc + cost[y] <= target:
+            acc += cost[y]
+            y += 1
+        lo = cuts[-1] + min_rows                         # leave room for this band and for the bands after it
+        hi = height - (world - k) * min_rows
+        cuts.append(min(max(y, lo), hi))
+        if cuts[-1] != y:                                # clamped: keep the running sum consistent with the cut
+            y = cuts[-1]
+            acc = sum(cost[:y])
+    cuts.append(height)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 def interleaved_bands(height, world, rank, band=64):
     """list of [y0, y1) bands for interleaved assignment (load balance for centred objects)."""
     out = []
@@ -29,25 +58,55 @@ def frames_for_rank(n_frames, world, rank):
     return list(range(rank, n_frames, world))
 
 
-def gather_bands_inplace(frame, height, dist, dst=0):
+def gather_bands_inplace(frame, height, dist, dst=0, bands=None):
     """Copy-free gather for the common case: `frame` is every rank's full (height, width) screen tensor (contiguous),
-    rank r has rendered rows band_rows(height, world, r) of it.  On return rank `dst`'s tensor holds the whole frame:
-    each peer's band is received straight into its place (one NCCL send/recv pair per peer, batched)."""
+    rank r has rendered rows bands[r] of it (default: band_rows(height, world, r)).  On return rank `dst`'s tensor
+    holds the whole frame: each peer's band is received straight into its place (one NCCL send/recv pair per peer,
+    batched)."""
     world, rank = dist.get_world_size(), dist.get_rank()
     if world == 1:
         return frame
+    if bands is None:
+        bands = [band_rows(height, world, r) for r in range(world)]
     ops = []
     if rank == dst:
         for r in range(world):
             if r != dst:
-                y0, y1 = band_rows(height, world, r)
+                y0, y1 = bands[r]
                 ops.append(dist.P2POp(dist.irecv, frame[y0:y1], r))
     else:
-        y0, y1 = band_rows(height, world, rank)
+        y0, y1 = bands[rank]
         ops.append(dist.P2POp(dist.isend, frame[y0:y1], dst))
     for req in dist.batch_isend_irecv(ops):
         req.wait()
     return frame if rank == dst else None
+
+
+def share_screen(renderer, dist, dst=0, device=None):
+    """Peer-memory output: rank `dst` exports its device screen (CUDA IPC handle, broadcast as 64 bytes), every other
+    rank imports it and makes it its colour target, so that its band is written straight into dst's frame by the
+    last kernel of its frame.  Afterwards a frame is complete on dst once every rank's stream has passed a barrier.
+    `renderer` needs export_screen() / import_screen(handle) / set_color_target(ptr) (swegl_b200.Renderer).
+    Returns the pointer the rank now renders into (None on dst: its own screen)."""
+    import torch
+    rank = dist.get_rank()
+    h = torch.zeros(64, dtype=torch.uint8, device=device)
+    if rank == dst:
+        h = torch.tensor(list(renderer.export_screen()), dtype=torch.uint8, device=device)
+    dist.broadcast(h, src=dst)
+    if rank == dst:
+        return None
+    ptr = renderer.import_screen(bytes(h.cpu().tolist()))
+    renderer.set_color_target(ptr)
+    return ptr
+
+
+def frame_barrier(dist, token):
+    """What is left of the gather with share_screen(): every rank's frame kernels (ordered before this call on the
+    current stream) have finished -- and with them their stores into dst's screen -- when the all-reduce of the
+    one-element `token` tensor completes."""
+    dist.all_reduce(token)
+    return token
 
 
 def gather_bands(local_rows, height, width, dist, dst=0):

@@ -211,6 +211,33 @@ def test_pipelined_readback_matches_blocking_render(renderer):
     assert (images[0] == want[0][0]).all()
 
 
+@pytest.mark.parametrize("name", ["truck_1080", "truck_4k_dof"])
+def test_color_target_assembles_bands_in_another_screen(renderer, name):
+    """multi-GPU output path on one GPU: a second context renders its band straight into the first context's screen
+    (set_color_target), as a peer GPU does through a CUDA IPC mapping"""
+    from swegl_b200 import Renderer
+    scene, vps, screen, cfg = configs.build(name)
+    vp = vps[0]
+    want, _, _ = render_gpu(renderer, scene, vps, screen, want_z=False)
+    a, b = Renderer(0), Renderer(0)
+    for r in (a, b):
+        r.upload_scene(scene); r.set_screen(*screen); r.begin_frame(scene)
+    screen_a, _ = a.device_buffers()
+    b.set_color_target(screen_a)
+    cut = vp.h // 3
+    try:
+        vp.band = (0, cut); a.render_device(vp, stats=True)
+        vp.band = (cut, vp.h); b.render_device(vp, stats=True)
+        a.synchronize(); b.synchronize()
+        got = a.read_screen()
+        assert (got == want).all()
+        b.set_color_target(None)                        # back to its own screen: A's frame is not touched any more
+        vp.band = (0, cut); b.render_device(vp, stats=True); b.synchronize()
+        assert (a.read_screen() == want).all() and (b.read_screen()[:cut] == want[:cut]).all()
+    finally:
+        vp.band = (0, 0)
+
+
 def test_band_scissor_equals_full_frame(renderer, oracle):
     """sort-first row bands: rendering [0,h) as 3 uneven bands gives the full frame"""
     scene, vps, screen, cfg = configs.build("truck_1080")

@@ -65,3 +65,17 @@ def test_sun_direction_normalisation(ref):
         sun = ref.set_lights(h, s)
         assert (sun.view(np.uint32) == normalized3(*raw).view(np.uint32)).all()
         ref.lib.ref_scene_free(h)
+
+
+def test_no_undefined_names_in_python_sources():
+    """bench.py and the tools only run on the GPU box: catch NameErrors (no pyflakes in the image) before they cost a run"""
+    import glob
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")]
+    for d in ("swegl_b200", "tools", "tests", "oracle"):
+        files += glob.glob(os.path.join(root, d, "*.py"))
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "check_names.py")] + files, capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout

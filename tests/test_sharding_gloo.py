@@ -32,6 +32,39 @@ def _worker(rank, world, port, out_path):
     inplace = sharding.gather_bands_inplace(mine, vp.h, dist, dst=0)
     if rank == 0:
         assert torch.equal(inplace, frame)
+    # cost-balanced bands from the gathered frame's coverage (rank 0 decides, everyone follows)
+    cuts = torch.zeros(world + 1, dtype=torch.int64)
+    if rank == 0:
+        cov = ((frame >> 24) != 0).sum(dim=1).to(torch.float64) + 0.05 * vp.w
+        b = sharding.balanced_bands(cov.tolist(), world)
+        cuts = torch.tensor([b[0][0]] + [e for _, e in b], dtype=torch.int64)
+    dist.broadcast(cuts, src=0)
+    bands = [(int(cuts[k]), int(cuts[k + 1])) for k in range(world)]
+    vp.band = bands[rank]
+    o2 = Oracle().render(scene, vp, screen_wh=screen)
+    mine2 = torch.zeros((vp.h, vp.w), dtype=torch.int32)
+    mine2[bands[rank][0]:bands[rank][1]] = torch.from_numpy(o2["pixels"][bands[rank][0]:bands[rank][1]].view(np.int32).copy())
+    balanced = sharding.gather_bands_inplace(mine2, vp.h, dist, dst=0, bands=bands)
+    if rank == 0:
+        assert torch.equal(balanced, frame) and bands[0][1] != sharding.band_rows(vp.h, world, 0)[1]
+    # peer-memory output handshake (CUDA IPC in production): the handle reaches every rank, dst keeps its own screen
+    class FakeRenderer:
+        target = None
+
+        def export_screen(self):
+            return bytes(range(64))
+
+        def import_screen(self, handle):
+            assert handle == bytes(range(64))
+            return 0xABC000
+
+        def set_color_target(self, ptr):
+            self.target = ptr
+    fr = FakeRenderer()
+    got = sharding.share_screen(fr, dist, dst=0)
+    assert (got, fr.target) == ((None, None) if rank == 0 else (0xABC000, 0xABC000))
+    tok = sharding.frame_barrier(dist, torch.ones(1))
+    assert float(tok) == world
     frames = sharding.frames_for_rank(7, world, rank)
     counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(counts, torch.tensor([len(frames)], dtype=torch.int64))
@@ -52,6 +85,20 @@ def test_band_partition_covers_every_row_once():
             assert rows == list(range(h))
             inter = sorted(y for r in range(world) for (a, b) in sharding.interleaved_bands(h, world, r) for y in range(a, b))
             assert inter == list(range(h))
+
+
+def test_balanced_bands_split_cost_evenly():
+    from swegl_b200 import sharding
+    h = 2160
+    cost = [max(0.0, 1000.0 - abs(y - 1400) * 2.0) + 10.0 for y in range(h)]         # an off-centre blob
+    for world in (2, 3, 4, 8):
+        b = sharding.balanced_bands(cost, world)
+        assert b[0][0] == 0 and b[-1][1] == h and all(b[k][1] == b[k + 1][0] for k in range(world - 1))
+        assert all(y1 - y0 >= 8 for y0, y1 in b)
+        sums = [sum(cost[y0:y1]) for y0, y1 in b]
+        assert max(sums) <= 1.05 * sum(cost) / world + max(cost)
+    assert sharding.balanced_bands([0.0] * 100, 4) == [sharding.band_rows(100, 4, r) for r in range(4)]
+    assert sharding.balanced_bands([1.0] * 10, 4) == [sharding.band_rows(10, 4, r) for r in range(4)]   # too few rows
 
 
 def test_two_rank_band_render_and_gather(tmp_path, oracle):
