@@ -175,6 +175,8 @@ __global__ void __launch_bounds__(FRAG_TPB) k_fragments(DeviceScene s, const Vie
     __shared__ int32_t s_head[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int band_rows = g.band1 - g.band0;
+    pdl_trigger();
+    pdl_wait();                                                             // k_spans' bins, chunks, fragment stream, tile list
     if ((int)blockIdx.x >= g.n_tiles) {
         // ---- clear CTA ----
         const int t = ((int)blockIdx.x - g.n_tiles) * FRAG_ROWS + warp;
@@ -384,6 +386,8 @@ __global__ void __launch_bounds__(FRAG_TPB) k_fragments_layers(DeviceScene s, co
                                                                float *__restrict__ depth, int count_covered,
                                                                Counters *__restrict__ h_counters_out)
 {
+    pdl_trigger();
+    pdl_wait();
     if (h_counters_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < sizeof(Counters) / 4)
         reinterpret_cast<uint32_t *>(h_counters_out)[threadIdx.x] = reinterpret_cast<const uint32_t *>(pl.counters)[threadIdx.x];
     __shared__ ViewParams vp;
@@ -551,6 +555,7 @@ __global__ void __launch_bounds__(DOF_THREADS) k_dof(const ViewParams *__restric
     const int tid = threadIdx.x;
     const int ox = blockIdx.x * DOF_OW, oy = row0 + blockIdx.y * DOF_OH;
     for (int k = tid; k < (int)(sizeof(ViewParams) / 4); k += DOF_THREADS) reinterpret_cast<uint32_t *>(&vp)[k] = reinterpret_cast<const uint32_t *>(vpp)[k];
+    pdl_wait();                                                             // k_fragments' colour, depth and occupancy map
 
     // ---- k_fragments left one byte per 32-column bin saying whether it drew anything there this frame.  If no bin
     //      under the window [ox-8, ox+72) x [oy-5, oy+36) did, the window is pure background: no loads at all. ----
@@ -711,7 +716,7 @@ static void launch_frag_t(const DeviceScene &s, const ViewParams &vp, const View
     if (n_tiles <= 0) return;
     const FragGeom g = { vp.vx, vp.vy, vp.vw, vp.band0, vp.band1, vp.nbx, vp.ntx, n_tiles };
     const unsigned grid = (unsigned)n_tiles + (unsigned)((n_tiles + FRAG_ROWS - 1) / FRAG_ROWS);
-    k_fragments<LIGHT, TEX><<<grid, FRAG_TPB, 0, st>>>(s, d_vp, d_fp, p, g, color, color_pitch, depth, count_covered ? 1 : 0, h_counters_out);
+    launch_chain(k_fragments<LIGHT, TEX>, grid, FRAG_TPB, st, true, s, d_vp, d_fp, p, g, color, color_pitch, depth, count_covered ? 1 : 0, h_counters_out);
 }
 
 void launch_fragments(const DeviceScene &s, const ViewParams &vp, const ViewParams *d_vp, const FrameParams *d_fp, const Pools &p,
@@ -729,7 +734,7 @@ static void launch_frag_layers_t(const DeviceScene &s, const ViewParams &vp, con
                                  uint32_t *color, int color_pitch, float *depth, bool count_covered, Counters *h_counters_out, cudaStream_t st)
 {
     dim3 grid((vp.nbx + FRAG_STRETCH - 1) / FRAG_STRETCH, (vp.band1 - vp.band0 + FRAG_ROWS - 1) / FRAG_ROWS);
-    k_fragments_layers<LIGHT, TEX><<<grid, FRAG_TPB, 0, st>>>(s, d_vp, d_fp, p, color, color_pitch, depth, count_covered ? 1 : 0, h_counters_out);
+    launch_chain(k_fragments_layers<LIGHT, TEX>, grid, FRAG_TPB, st, true, s, d_vp, d_fp, p, color, color_pitch, depth, count_covered ? 1 : 0, h_counters_out);
 }
 void launch_fragments_layers(const DeviceScene &s, const ViewParams &vp, const ViewParams *d_vp, const FrameParams *d_fp, const Pools &p,
                              uint32_t *color, int color_pitch, float *depth, bool count_covered, Counters *h_counters_out, cudaStream_t st)
@@ -744,7 +749,7 @@ void launch_dof(const ViewParams *d_vp, const uint8_t *bin_used, int nbx, const 
 {
     dim3 grid((w + DOF_OW - 1) / DOF_OW, (row1 - row0 + DOF_OH - 1) / DOF_OH);
     if (grid.x && grid.y)
-        k_dof<<<grid, DOF_THREADS, 0, st>>>(d_vp, bin_used, nbx, src, src_pitch, depth, dst, dst_pitch, w, h, row0, row1);
+        launch_chain(k_dof, grid, DOF_THREADS, st, true, d_vp, bin_used, nbx, src, src_pitch, depth, dst, dst_pitch, w, h, row0, row1);
 }
 
 } // namespace sb

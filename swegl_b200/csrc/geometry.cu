@@ -25,6 +25,7 @@ static constexpr uint32_t SPAN_SEG = 4;      // 32-column bins per span segment 
 template <bool WORLD>
 __global__ void __launch_bounds__(TPB) k_vertex(DeviceScene s, const ViewParams *__restrict__ vpp, Counters *__restrict__ counters)
 {
+    pdl_trigger();
     __shared__ ViewParams vp;
     for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
     if (blockIdx.x == 0 && threadIdx.x < sizeof(Counters) / 4) reinterpret_cast<uint32_t *>(counters)[threadIdx.x] = 0;
@@ -52,9 +53,11 @@ __global__ void __launch_bounds__(TPB) k_vertex(DeviceScene s, const ViewParams 
 // ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB) k_mark(DeviceScene s)
 {
+    pdl_trigger();
     uint32_t t = blockIdx.x * TPB + threadIdx.x;
     if (t >= s.n_tris) return;
-    Tri tr = s.tris[t];
+    Tri tr = s.tris[t];                                                     // static scene data: may be read before the wait
+    pdl_wait();                                                             // k_vertex's v_ndc and yes reset
     V3 a = v3(s.v_ndc[3 * tr.i0], s.v_ndc[3 * tr.i0 + 1], s.v_ndc[3 * tr.i0 + 2]);
     V3 b = v3(s.v_ndc[3 * tr.i1], s.v_ndc[3 * tr.i1 + 1], s.v_ndc[3 * tr.i1 + 2]);
     V3 c = v3(s.v_ndc[3 * tr.i2], s.v_ndc[3 * tr.i2 + 1], s.v_ndc[3 * tr.i2 + 2]);
@@ -247,6 +250,7 @@ SB_DEV void fill_row_slots(const Pools &pl, RowRange rr, uint32_t slot)
 __global__ void __launch_bounds__(128) k_setup(DeviceScene s, const ViewParams *__restrict__ vpp,
                                                const FrameParams *__restrict__ fpp, Pools pl)
 {
+    pdl_trigger();
     __shared__ ViewParams vp;                   // staged once per CTA: used all over the set-up code
     __shared__ FrameParams fp;
     for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += 128) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
@@ -256,8 +260,9 @@ __global__ void __launch_bounds__(128) k_setup(DeviceScene s, const ViewParams *
     RowRange r0 = { 0u, 0u }, r1 = { 0u, 0u };
     Tri tr = { 0u, 0u, 0u, 0u };
     bool go = t < s.n_tris;
+    if (go) tr = s.tris[t];
+    pdl_wait();                                                             // k_mark's yes flags
     if (go) {
-        tr = s.tris[t];
         go = s.yes[tr.i0] && s.yes[tr.i1] && s.yes[tr.i2];                  // renderer.cpp:248-253
     }
     if (go && (vp.band0 > vp.vy || vp.band1 < vp.vy + vp.vh)) {
@@ -428,8 +433,10 @@ __global__ void __launch_bounds__(SPAN_TPB, SPAN_MINB) k_spans(const ViewParams 
 {
     __shared__ SpanCta sh;
     __shared__ ViewParams vp;
+    pdl_trigger();
     for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += SPAN_TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
     __syncthreads();
+    pdl_wait();                                                             // k_setup's records and counters
     if (pl.counters->overflow & 1u) return;      // some rows were never allocated: the host grows the pool and redoes the frame
     const uint32_t n_rows = min(pl.counters->n_rows, pl.rows_cap);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -603,8 +610,10 @@ __global__ void __launch_bounds__(TPB) k_spans_dense(const ViewParams *__restric
 {
     __shared__ SpanCtaDense sh;
     __shared__ ViewParams vp;
+    pdl_trigger();
     for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
     __syncthreads();
+    pdl_wait();                                                             // k_setup's records and counters
     if (pl.counters->overflow & 1u) return;
     const uint32_t n_rows = min(pl.counters->n_rows, pl.rows_cap);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -729,21 +738,22 @@ static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
 void launch_vertex(const DeviceScene &s, const ViewParams *d_vp, Counters *counters, bool with_world, cudaStream_t st)
 {
     const unsigned blocks = max(1u, cdiv(s.n_vertices, TPB));
-    if (with_world) k_vertex<true><<<blocks, TPB, 0, st>>>(s, d_vp, counters);
-    else k_vertex<false><<<blocks, TPB, 0, st>>>(s, d_vp, counters);
+    // first kernel of the frame: it follows the upload of the parameter block (a copy, not a kernel) -> ordinary launch
+    if (with_world) launch_chain(k_vertex<true>, blocks, TPB, st, false, s, d_vp, counters);
+    else launch_chain(k_vertex<false>, blocks, TPB, st, false, s, d_vp, counters);
 }
 void launch_mark(const DeviceScene &s, cudaStream_t st)
 {
-    if (s.n_tris) k_mark<<<cdiv(s.n_tris, TPB), TPB, 0, st>>>(s);
+    if (s.n_tris) launch_chain(k_mark, cdiv(s.n_tris, TPB), TPB, st, true, s);
 }
 void launch_setup(const DeviceScene &s, const ViewParams *d_vp, const FrameParams *d_fp, const Pools &p, cudaStream_t st)
 {
-    if (s.n_tris) k_setup<<<cdiv(s.n_tris, 128), 128, 0, st>>>(s, d_vp, d_fp, p);
+    if (s.n_tris) launch_chain(k_setup, cdiv(s.n_tris, 128), 128, st, true, s, d_vp, d_fp, p);
 }
 void launch_spans(const ViewParams *d_vp, const Pools &p, bool dense, cudaStream_t st)
 {
-    if (dense) k_spans_dense<<<148 * 8, TPB, 0, st>>>(d_vp, p);      // persistent CTAs, 256 scanline records per pass
-    else k_spans<<<148 * 16 * (256 / SPAN_TPB), SPAN_TPB, 0, st>>>(d_vp, p);                 // persistent CTAs, SPAN_ROWS scanline records per pass
+    if (dense) launch_chain(k_spans_dense, 148 * 8, TPB, st, true, d_vp, p);      // persistent CTAs, 256 scanline records per pass
+    else launch_chain(k_spans, 148 * 16 * (256 / SPAN_TPB), SPAN_TPB, st, true, d_vp, p);   // persistent CTAs, SPAN_ROWS scanline records per pass
 }
 
 } // namespace sb
