@@ -252,6 +252,69 @@ def test_band_scissor_equals_full_frame(renderer, oracle):
     assert (px == full).all() and (z.view(np.uint32) == fz[0].view(np.uint32)).all()
 
 
+@pytest.mark.parametrize("rect", [(13, 7, 611, 403), (0, 0, 1003, 701), (500, 299, 503, 402), (37, 41, 33, 31), (37, 41, 5, 3), (1002, 700, 1, 1)])
+@pytest.mark.parametrize("post", [_abi.POST_NULL, _abi.POST_DOF])
+def test_odd_viewport_rectangles(renderer, oracle, rect, post):
+    """rectangles, offsets and a screen pitch that are multiples of nothing: every vector path (128-bit clears, the
+    4-pixel fragment-stream stores, the DoF window loads) has to fall back or peel correctly"""
+    from swegl_b200.scene import Viewport
+    scene, _, _, _ = configs.build("truck_1080")
+    screen = (1003, 701)
+    x, y, w, h = rect
+    vp = Viewport(x, y, w, h, transparency_layers=0, post_mode=post, focal_distance=5.0, focal_depth=5.0)
+    vp.camera.apply(configs.POSE_TEST1 if w < 100 else configs.POSE_CLOSE)
+    gpx, gzs, stats = render_gpu(renderer, scene, [vp], screen)
+    opx, outs = render_oracle(oracle, scene, [vp], screen)
+    check_frame(f"rect {rect}", gpx, gzs, opx, outs, [vp])
+    assert stats[0].n_covered == outs[0]["n_covered"]
+    outside = np.ones((screen[1], screen[0]), bool)
+    outside[y:y + h, x:x + w] = False
+    assert (gpx[outside] == 0).all()                    # nothing is written outside the rectangle
+
+
+def test_odd_rectangle_bands_with_dof(renderer, oracle):
+    from swegl_b200.scene import Viewport
+    scene, _, _, _ = configs.build("truck_1080")
+    screen = (1003, 701)
+    vp = Viewport(13, 7, 611, 403, transparency_layers=0, post_mode=_abi.POST_DOF, focal_distance=5.0, focal_depth=5.0)
+    vp.camera.apply(configs.POSE_CLOSE)
+    full, fz, _ = render_gpu(renderer, scene, [vp], screen)
+    px = np.zeros_like(full)
+    z = np.empty_like(fz[0])
+    for b0, b1 in [(0, 101), (101, 102), (102, 333), (333, 403)]:
+        vp.band = (b0, b1)
+        renderer.render(vp, px, z)
+    vp.band = (0, 0)
+    assert (px == full).all() and (z.view(np.uint32) == fz[0].view(np.uint32)).all()
+
+
+def test_nothing_to_draw(renderer, oracle):
+    """camera turned away from the scene (every triangle culled), and a scene without primitives: cleared frames"""
+    from swegl_b200.scene import Viewport, Scene
+    scene, _, _, _ = configs.build("truck_1080")
+    vp = Viewport(0, 0, 640, 360, transparency_layers=0)
+    vp.camera.apply([("translate", 0, 0, -5), ("rotate_y", 3.14159)])
+    gpx, gzs, stats = render_gpu(renderer, scene, [vp], (640, 360))
+    opx, outs = render_oracle(oracle, scene, [vp], (640, 360))
+    assert outs[0]["n_covered"] == 0 and stats[0].n_covered == 0
+    assert (gpx == 0).all() and (gzs[0].view(np.uint32) == 0x7F7F7F7F).all()
+    empty = Scene()
+    empty.name = "empty"
+    empty.node_scale = np.ones((1, 3), np.float32)
+    empty.node_rotation = np.eye(4, dtype=np.float32)[None]
+    empty.node_translation = np.zeros((1, 3), np.float32)
+    empty.node_parent = np.full(1, -1, np.int32)
+    empty.set_lights(0.3, (1.0, -2.0, -1.0), 0.7, ())
+    gpx, gzs, stats = render_gpu(renderer, empty, [vp], (640, 360))
+    assert stats[0].n_covered == 0 and (gpx == 0).all() and (gzs[0].view(np.uint32) == 0x7F7F7F7F).all()
+    # and the context recovers: the next scene renders normally
+    vp2 = Viewport(0, 0, 640, 360, transparency_layers=0)
+    vp2.camera.apply(configs.POSE_TEST1)
+    gpx, gzs, _ = render_gpu(renderer, scene, [vp2], (640, 360))
+    opx, outs = render_oracle(oracle, scene, [vp2], (640, 360))
+    check_frame("after empty", gpx, gzs, opx, outs, [vp2])
+
+
 def test_errors(renderer):
     from swegl_b200.renderer import SweglB200Error
     scene, vps, screen, cfg = configs.build("box_640")
