@@ -103,6 +103,12 @@ def _lights_synth(s):
     return s.set_lights(0.2, (1.0, -1.0, -1.0), 0.3, POINT_LIGHTS)                     # SURVEY §8c synthetic
 
 
+POSE_PROCEDURAL = [("translate", 1, 2, 6), ("rotate_y", 3.0), ("rotate_x", -0.3)]      # torus / cube / sphere, strips and fans
+# the three stacked (transparent) triangles in front of the cube: 1, 2 and 3 layers deep per pixel
+POSE_LAYERS = [("translate", 1.3, 1.2, -4), ("rotate_y", 0.1), ("rotate_x", -0.1)]
+POSE_LAYERS_CLOSE = [("translate", 1.5, 1, -3)]
+
+
 # name -> (scene, screen (w,h), lights fn, [viewport kwargs + pose], description)
 CONFIGS = {
     "box_640": dict(scene="BoxTextured", screen=(640, 480), lights="test1", views=[dict(rect=(0, 0, 640, 480), pose=POSE_TEST1, layers=3)],
@@ -129,6 +135,12 @@ CONFIGS = {
                                   dict(rect=(0, 540, 960, 540), pose=[("translate", 0, 4, -4), ("rotate_x", -0.7)], layers=0),
                                   dict(rect=(960, 540, 960, 540), pose=[("translate", 3, 1, -3), ("rotate_y", -0.7), ("rotate_x", -0.1)], layers=0)],
                            desc="config 4: 2x2 split screen, 4 cameras (CesiumMilkTruck substituted for the missing BarramundiFish.glb)"),
+    "layers_640": dict(scene="procedural", alpha=100, screen=(640, 480), lights="procedural",
+                       views=[dict(rect=(0, 0, 640, 480), pose=POSE_LAYERS, layers=3)],
+                       desc="SURVEY 8f N1: procedural scene (strips, fans, scaled node), three stacked alpha-100 triangles, 3 transparency layers"),
+    "layers_texalpha_640": dict(scene="procedural", alpha=100, tex_alpha=True, screen=(640, 480), lights="procedural",
+                                views=[dict(rect=(0, 0, 640, 480), pose=POSE_LAYERS_CLOSE, layers=2)],
+                                desc="N1: same scene, texels alternate alpha 255/90 (per-fragment opaque/transparent), 2 layers, close pose"),
     "sphere100_1080": dict(scene="sphere100", screen=(1920, 1080), lights="synth", views=[dict(rect=(0, 0, 1920, 1080), pose=POSE_SPHERE, layers=0)],
                            desc="make_sphere(100) 20 200 triangles, LCG texture, 1920x1080 (survey hash 72b4fc66d972867b)"),
     "sphere1000_8k": dict(scene="sphere1000", screen=(7680, 4320), lights="synth", views=[dict(rect=(0, 0, 7680, 4320), pose=POSE_SPHERE, layers=0)],
@@ -139,8 +151,11 @@ CONFIGS = {
 def build(name, light_mode=_abi.LIGHT_PHONG, tex_mode=_abi.TEX_BILINEAR):
     """-> (scene, [Viewport...], (screen_w, screen_h), config dict)"""
     cfg = CONFIGS[name]
-    s = load_scene(cfg["scene"])
-    {"test1": lambda: _lights_test1(s), "test1+points": lambda: _lights_test1(s, True), "synth": lambda: _lights_synth(s)}[cfg["lights"]]()
+    if cfg["scene"] == "procedural":
+        s = procedural(cfg.get("alpha", 255), cfg.get("tex_alpha", False))      # fresh copy, lights set
+    else:
+        s = load_scene(cfg["scene"])
+        {"test1": lambda: _lights_test1(s), "test1+points": lambda: _lights_test1(s, True), "synth": lambda: _lights_synth(s)}[cfg["lights"]]()
     vps = []
     for v in cfg["views"]:
         x, y, w, h = v["rect"]
@@ -150,12 +165,6 @@ def build(name, light_mode=_abi.LIGHT_PHONG, tex_mode=_abi.TEX_BILINEAR):
         vp.pose = v["pose"]
         vps.append(vp)
     return s, vps, cfg["screen"], cfg
-
-
-POSE_PROCEDURAL = [("translate", 1, 2, 6), ("rotate_y", 3.0), ("rotate_x", -0.3)]      # torus / cube / sphere, strips and fans
-# the three stacked (transparent) triangles in front of the cube: 1, 2 and 3 layers deep per pixel
-POSE_LAYERS = [("translate", 1.3, 1.2, -4), ("rotate_y", 0.1), ("rotate_x", -0.1)]
-POSE_LAYERS_CLOSE = [("translate", 1.5, 1, -3)]
 
 
 def procedural(alpha=255, tex_alpha=False):

@@ -235,7 +235,7 @@ SB_DEV RowRange emit_slot(const DeviceScene &s, const ViewParams &vp, const Fram
 SB_DEV void fill_row_slots(const Pools &pl, RowRange rr, uint32_t slot)
 {
     const int lane = threadIdx.x & 31;
-    const bool big = rr.n > 8;
+    const bool big = rr.n > 48;
     if (!big) for (uint32_t k = 0; k < rr.n; k++) pl.row_slot[rr.base + k] = slot;
     unsigned m = __ballot_sync(0xFFFFFFFFu, big);
     while (m) {
@@ -247,7 +247,10 @@ SB_DEV void fill_row_slots(const Pools &pl, RowRange rr, uint32_t slot)
     }
 }
 
-__global__ void __launch_bounds__(128) k_setup(DeviceScene s, const ViewParams *__restrict__ vpp,
+#ifndef SETUP_MINB
+#define SETUP_MINB 4
+#endif
+__global__ void __launch_bounds__(128, SETUP_MINB) k_setup(DeviceScene s, const ViewParams *__restrict__ vpp,
                                                const FrameParams *__restrict__ fpp, Pools pl)
 {
     pdl_trigger();

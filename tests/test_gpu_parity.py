@@ -50,7 +50,7 @@ def check_frame(name, gpx, gzs, opx, outs, vps):
     return int((gpx != opx).sum())
 
 
-SMALL = ["box_640", "box_640_close", "truck_1080_sun", "truck_1080", "sphere100_1080", "multiview_1080"]
+SMALL = ["box_640", "box_640_close", "truck_1080_sun", "truck_1080", "sphere100_1080", "multiview_1080", "layers_640", "layers_texalpha_640"]
 LARGE = ["brainstem_4k", "truck_4k"]
 
 
