@@ -125,30 +125,45 @@ SB_DEV SV make_clip_vertex(const DeviceScene &s, const ViewParams &vp, const flo
 // fill_triangle_2 up to the row count: y sort, ceil limits, and the records the later stages need
 struct RowRange { uint32_t base, n; };     // scanline records a slot allocated (n == 0: nothing to draw)
 
-SB_DEV RowRange emit_slot(const DeviceScene &s, const ViewParams &vp, const FrameParams &fp, const Pools &pl,
-                          uint32_t slot, uint32_t prim_id, const Prim &pr, SV a, SV b, SV c, bool front_face_visible)
+SB_DEV uint32_t warp_incl_scan(uint32_t v, int lane)
 {
-    const RowRange none = { 0u, 0u };
-    bool inverted = !front_face_visible;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= d) v += t; }
+    return v;
+}
+
+// y sort + the number of scanlines the slot walks inside the band
+struct SlotPlan { int y0, y1, y2, n; };
+
+SB_DEV SlotPlan plan_slot(const ViewParams &vp, SV &a, SV &b, SV &c)
+{
+    SlotPlan p = { 0, 0, 0, 0 };
     if (b.s.y < a.s.y) swap_sv(a, b);                       // renderer.cpp:375-387
     if (c.s.y < b.s.y) swap_sv(b, c);
     if (b.s.y < a.s.y) swap_sv(a, b);
-    int y0 = ceil_i(a.s.y), y1 = ceil_i(b.s.y), y2 = ceil_i(c.s.y);
-    if (y0 == y2) return none;                              // renderer.cpp:394
-
+    p.y0 = ceil_i(a.s.y); p.y1 = ceil_i(b.s.y); p.y2 = ceil_i(c.s.y);
+    if (p.y0 == p.y2) return p;                             // renderer.cpp:394
     // scanlines this slot will walk inside the band (upper half :416-421, lower half :439-444)
     int n = 0;
-    if (y1 >= vp.vy) {
-        int ya = max(max(y0, vp.vy), vp.band0), yb = min(min(y1, vp.vy + vp.vh), vp.band1);
+    if (p.y1 >= vp.vy) {
+        int ya = max(max(p.y0, vp.vy), vp.band0), yb = min(min(p.y1, vp.vy + vp.vh), vp.band1);
         n += max(0, yb - ya);
     }
-    if (y1 < vp.vy + vp.vh) {
-        int ya = max(max(y1, vp.vy), vp.band0), yb = min(min(y2, vp.vy + vp.vh), vp.band1);
+    if (p.y1 < vp.vy + vp.vh) {
+        int ya = max(max(p.y1, vp.vy), vp.band0), yb = min(min(p.y2, vp.vy + vp.vh), vp.band1);
         n += max(0, yb - ya);
     }
-    if (n == 0) return none;
-    uint32_t base = atomicAdd(&pl.counters->n_rows, (uint32_t)n);
-    if (base + (uint32_t)n > pl.rows_cap) { atomicOr(&pl.counters->overflow, 1u); return none; }
+    p.n = n;
+    return p;
+}
+
+// the records of a planned slot whose `plan.n` scanline records start at `base`; a, b, c are y-sorted (plan_slot)
+SB_DEV void finish_slot(const DeviceScene &s, const ViewParams &vp, const FrameParams &fp, const Pools &pl,
+                        uint32_t slot, uint32_t prim_id, const Prim &pr, const SV &a, const SV &b, const SV &c,
+                        bool front_face_visible, const SlotPlan &plan, uint32_t base)
+{
+    const bool inverted = !front_face_visible;
+    const int y0 = plan.y0, y1 = plan.y1, y2 = plan.y2;
 
     // fill_triangle_2's edge set-up (renderer.cpp:396-459): every side's state at the first scanline it is
     // walked on.  k_spans jumps from here to any scanline with radd().
@@ -224,9 +239,21 @@ SB_DEV RowRange emit_slot(const DeviceScene &s, const ViewParams &vp, const Fram
     sh.pad0 = 0;
     sh.color = pr.color; sh.tex_off = pr.tex_off; sh.tw = pr.tw; sh.th = pr.th;
     pl.shades[slot] = sh;
+}
 
+// plan + allocate + finish by one thread (the near clipper's rare second triangle); the common first slot of a
+// triangle goes through the warp-aggregated allocation in k_setup instead
+SB_DEV RowRange emit_slot(const DeviceScene &s, const ViewParams &vp, const FrameParams &fp, const Pools &pl,
+                          uint32_t slot, uint32_t prim_id, const Prim &pr, SV a, SV b, SV c, bool front_face_visible)
+{
+    const RowRange none = { 0u, 0u };
+    const SlotPlan plan = plan_slot(vp, a, b, c);
+    if (plan.n == 0) return none;
+    const uint32_t base = atomicAdd(&pl.counters->n_rows, (uint32_t)plan.n);
+    if (base + (uint32_t)plan.n > pl.rows_cap) { atomicOr(&pl.counters->overflow, 1u); return none; }
+    finish_slot(s, vp, fp, pl, slot, prim_id, pr, a, b, c, front_face_visible, plan, base);
     atomicAdd(&pl.counters->n_slots, 1u);
-    const RowRange rr = { base, (uint32_t)n };
+    const RowRange rr = { base, (uint32_t)plan.n };
     return rr;
 }
 
@@ -280,8 +307,13 @@ __global__ void __launch_bounds__(128, SETUP_MINB) k_setup(DeviceScene s, const 
             if (max(ya, max(yb, yc)) <= vp.band0 || min(ya, min(yb, yc)) >= vp.band1) go = false;
         }
     }
+    // the slot most triangles produce (2t) is planned inside the branches and allocated for the whole warp at once
+    // below; the near clipper's second triangle (2t+1, rare) allocates on its own
+    bool have0 = false, ffv0 = false;
+    SV A, B, C;
+    Prim pr;
     if (go) {
-        Prim pr = s.prims[tr.prim];
+        pr = s.prims[tr.prim];
         SV a = load_sv(s, vp, tr.i0), b = load_sv(s, vp, tr.i1), c = load_sv(s, vp, tr.i2);
 
         bool ffv = cross_n(sub(b.s, a.s), sub(c.s, a.s)).z < 0.0f;          // renderer.cpp:258
@@ -292,7 +324,7 @@ __global__ void __launch_bounds__(128, SETUP_MINB) k_setup(DeviceScene s, const 
 
         const float *m9 = s.node_normal + 9 * pr.node;
         if (c.s.z >= NEAR_Z) {
-            r0 = emit_slot(s, vp, fp, pl, 2 * t, tr.prim, pr, a, b, c, ffv);
+            A = a; B = b; C = c; ffv0 = ffv; have0 = true;
         } else if (b.s.z < NEAR_Z) {
             // only a in front of the camera, renderer.cpp:286-317
             float cut_1 = fdiv(fsub(a.s.z, 0.001f), fsub(a.s.z, b.s.z));
@@ -301,7 +333,7 @@ __global__ void __launch_bounds__(128, SETUP_MINB) k_setup(DeviceScene s, const 
             SV n2 = make_clip_vertex(s, vp, m9, a, c, cut_2);
             ffv = cross_n(sub(n1.s, a.s), sub(n2.s, a.s)).z < 0.0f;
             if (inverted_order) ffv = !ffv;
-            r0 = emit_slot(s, vp, fp, pl, 2 * t, tr.prim, pr, a, n1, n2, ffv);
+            A = a; B = n1; C = n2; ffv0 = ffv; have0 = true;
         } else if (c.s.z < NEAR_Z) {
             // only c behind the camera: two triangles, renderer.cpp:318-356
             float cut_0 = fdiv(fsub(a.s.z, 0.001f), fsub(a.s.z, c.s.z));
@@ -310,10 +342,35 @@ __global__ void __launch_bounds__(128, SETUP_MINB) k_setup(DeviceScene s, const 
             SV n2 = make_clip_vertex(s, vp, m9, b, c, cut_1);
             ffv = cross_n(sub(b.s, a.s), sub(n2.s, a.s)).z < 0.0f;
             if (inverted_order) ffv = !ffv;
-            r0 = emit_slot(s, vp, fp, pl, 2 * t, tr.prim, pr, a, b, n2, ffv);
+            A = a; B = b; C = n2; ffv0 = ffv; have0 = true;
             ffv = cross_n(sub(n2.s, a.s), sub(n1.s, a.s)).z < 0.0f;
             if (inverted_order) ffv = !ffv;
             r1 = emit_slot(s, vp, fp, pl, 2 * t + 1, tr.prim, pr, a, n2, n1, ffv);
+        }
+    }
+    {
+        // one n_rows / n_slots atomic per warp instead of one per triangle
+        const int lane = threadIdx.x & 31;
+        SlotPlan plan = { 0, 0, 0, 0 };
+        if (have0) plan = plan_slot(vp, A, B, C);
+        const uint32_t n = (uint32_t)plan.n;
+        const uint32_t incl = warp_incl_scan(n, lane);
+        const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (tot) {                                                          // warp-uniform
+            uint32_t wbase = 0;
+            if (lane == 31) wbase = atomicAdd(&pl.counters->n_rows, tot);
+            wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
+            const unsigned live = __ballot_sync(0xFFFFFFFFu, n != 0);
+            if (wbase + tot > pl.rows_cap) {
+                if (lane == 0) atomicOr(&pl.counters->overflow, 1u);
+            } else {
+                if (lane == 0) atomicAdd(&pl.counters->n_slots, (uint32_t)__popc(live));
+                if (n) {
+                    const uint32_t base = wbase + incl - n;
+                    finish_slot(s, vp, fp, pl, 2 * t, tr.prim, pr, A, B, C, ffv0, plan, base);
+                    r0.base = base; r0.n = n;
+                }
+            }
         }
     }
     fill_row_slots(pl, r0, 2 * t);
@@ -327,12 +384,6 @@ __global__ void __launch_bounds__(128, SETUP_MINB) k_setup(DeviceScene s, const 
 // interpolator (renderer.cpp:469-480), replays it along x and drops a checkpoint ("chunk") at every
 // 32-column bin the span crosses.
 // ----------------------------------------------------------------------------------------
-SB_DEV uint32_t warp_incl_scan(uint32_t v, int lane)
-{
-    #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= d) v += t; }
-    return v;
-}
 
 // One SEGMENT (up to SPAN_SEG bins = 128 pixels) of a span per thread.
 //  * The thread jumps to its segment's first column with radd() (free for a span's first segment) and replays
