@@ -161,8 +161,11 @@ SB_DEV void clear_tile_row(uint32_t *crow, float *drow, int px_left, int lane)
 //    at the head of the grid instead of wherever the scene happens to sit on the screen); i >= n_busy exits;
 //  * clear CTA j: warp w takes tile j * FRAG_ROWS + w and, unless it was busy, fills it with the clear values
 //    (16 independent 128-bit stores per lane; no bin heads are read for tiles nothing was drawn into).
+#ifndef FRAG_MINB
+#define FRAG_MINB 8         // 32 registers: all 64 warps of an SM resident; measured faster than 48 registers / 40 warps
+#endif
 template <int LIGHT, int TEX>
-__global__ void __launch_bounds__(FRAG_TPB) k_fragments(DeviceScene s, const ViewParams *__restrict__ vpp,
+__global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s, const ViewParams *__restrict__ vpp,
                                                         const FrameParams *__restrict__ fpp, Pools pl, FragGeom g,
                                                         uint32_t *__restrict__ color, int color_pitch,
                                                         float *__restrict__ depth, int count_covered,
