@@ -217,6 +217,19 @@ int  swegl_b200_read_depth(swegl_b200_ctx *ctx, float *zbuffer);
 int  swegl_b200_read_vertices(swegl_b200_ctx *ctx, float *v_world, float *v_viewport,
                               float *normal_world, uint8_t *yes);
 
+/* ---- sort-first band culling (multi-GPU row bands) ----
+ * A banded view (viewport_desc.band_y0/y1) only has to transform, mark and set up what can reach its rows.  The
+ * library keeps a static table of triangle clusters (64 consecutive triangles of the draw order, with the box of
+ * their vertices) and skips, per banded view, the clusters whose projected box misses the band -- dilated over the
+ * "shares a vertex" adjacency so that the `yes` flags of every vertex that is looked at (renderer.cpp:86-185,
+ * 248-253) are exactly the reference's.  The frame is bit-identical with and without it.
+ * policy: -1 automatic (banded views of scenes with >= 16384 triangles), 0 never, 1 every banded view.
+ * Call before upload_scene (the tables are built there); environment override: SWEGL_B200_CULL=0|1. */
+int  swegl_b200_set_band_culling(swegl_b200_ctx *ctx, int policy);
+/* diagnostics of the last view: counts[0..5] = clusters, vertex blocks, live clusters, clusters marked,
+ * vertex blocks transformed, 1 if that view was culled at all (else the three counts equal the totals) */
+int  swegl_b200_cull_counts(swegl_b200_ctx *ctx, uint32_t counts[6]);
+
 #ifdef __cplusplus
 }
 #endif

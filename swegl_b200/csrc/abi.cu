@@ -8,6 +8,7 @@
 // vertex stage with the world transform, later viewports of the same frame upload just their
 // ViewParams.  The launch sequence therefore has no per-frame kernel arguments and is replayed as a
 // CUDA graph (one per viewport configuration, staging slot and with/without frame upload).
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -34,6 +35,11 @@ struct swegl_b200_ctx {
     Tri *d_tris = nullptr; Prim *d_prims = nullptr;
     float *d_v_world = nullptr, *d_v_ndc = nullptr, *d_n_world = nullptr; uint8_t *d_yes = nullptr;
     bool opaque = true;            // every material and texel has alpha 255
+    // band culling (common.cuh): static tables + per-view flags; policy -1 automatic (banded views of big scenes), 0 off, 1 on
+    CullTables cull{};
+    ClusterBox *d_cl_box = nullptr; uint32_t *d_cl_adj_off = nullptr, *d_cl_adj = nullptr, *d_vb_adj_off = nullptr, *d_vb_adj = nullptr;
+    uint8_t *d_cull_flags = nullptr;
+    int cull_policy = -1;
     uint32_t stamp = 0;            // ViewParams::stamp of the last staged view
 
     // the frame block
@@ -72,7 +78,7 @@ struct swegl_b200_ctx {
     uint32_t *color_target = nullptr;   // where finished colour goes instead of d_screen (another context's / GPU's screen)
     std::vector<void *> imported;       // cudaIpcOpenMemHandle mappings to close
 
-    ViewParams last_vp{}; bool have_vp = false;
+    ViewParams last_vp{}; bool have_vp = false; bool last_dof = false;
     ViewParams dof_cache{}; float dof_cache_depth = 0.f; bool dof_cache_valid = false;   // DoF thresholds per focal_depth
     cudaEvent_t ev[8]{};
 
@@ -126,6 +132,106 @@ static int layout_block(swegl_b200_ctx *ctx, uint32_t lights_cap)
     return SWEGL_B200_OK;
 }
 
+// Static tables of the band culling (common.cuh): clusters of CULL_CL consecutive triangles with the object-space box
+// of the vertices they reference, and the two adjacency lists k_cull_need ORs cl_live over:
+//   cl_adj(c) = clusters sharing at least one vertex with c (c included)        -> mark_need
+//   vb_adj(j) = union of cl_adj(c) over the clusters c referencing block j      -> vert_need
+// Lists longer than 32 entries collapse to CULL_ALWAYS (e.g. the hub vertex of a big fan).
+static int build_cull_tables(swegl_b200_ctx *ctx, const std::vector<Tri> &tris, const float *pos, const std::vector<uint32_t> &vert_node, uint32_t nv)
+{
+    const uint32_t nt = (uint32_t)tris.size();
+    const uint32_t ncl = (nt + CULL_CL - 1) / CULL_CL, nvb = (nv + CULL_CL - 1) / CULL_CL;
+    const size_t LIST_CAP = 32;
+    std::vector<ClusterBox> boxes(ncl);
+    std::vector<uint64_t> pairs;                    // vertex << 32 | cluster, one per (cluster, referenced vertex)
+    pairs.reserve((size_t)ncl * (CULL_CL + 2));
+    std::vector<uint32_t> vs;
+    for (uint32_t c = 0; c < ncl; c++) {
+        vs.clear();
+        for (uint32_t t = c * CULL_CL; t < nt && t < (c + 1) * CULL_CL; t++) { vs.push_back(tris[t].i0); vs.push_back(tris[t].i1); vs.push_back(tris[t].i2); }
+        std::sort(vs.begin(), vs.end());
+        vs.erase(std::unique(vs.begin(), vs.end()), vs.end());
+        ClusterBox &b = boxes[c];
+        b.node = (int32_t)vert_node[vs[0]]; b.pad = 0;
+        for (int k = 0; k < 3; k++) { b.lo[k] = pos[3 * (size_t)vs[0] + k]; b.hi[k] = b.lo[k]; }
+        for (uint32_t v : vs) {
+            if ((int32_t)vert_node[v] != b.node) b.node = -1;               // more than one node: one box cannot describe it
+            for (int k = 0; k < 3; k++) {
+                const float x = pos[3 * (size_t)v + k];
+                if (!(x >= b.lo[k])) b.lo[k] = x;                           // (a NaN position ends up in the box and keeps the cluster live)
+                if (!(x <= b.hi[k])) b.hi[k] = x;
+            }
+            pairs.push_back(((uint64_t)v << 32) | c);
+        }
+        if (b.node < 0) b.node = -1;
+    }
+    std::sort(pairs.begin(), pairs.end());
+    std::vector<std::vector<uint32_t>> cl_adj(ncl);
+    std::vector<uint8_t> cl_always(ncl, 0);
+    for (uint32_t c = 0; c < ncl; c++) cl_adj[c].push_back(c);
+    for (size_t a = 0; a < pairs.size();) {
+        size_t b = a;
+        while (b < pairs.size() && (pairs[b] >> 32) == (pairs[a] >> 32)) b++;
+        if (b - a > LIST_CAP) { for (size_t i = a; i < b; i++) cl_always[(uint32_t)pairs[i]] = 1; }
+        else if (b - a > 1)
+            for (size_t i = a; i < b; i++) for (size_t j = a; j < b; j++) if (i != j) cl_adj[(uint32_t)pairs[i]].push_back((uint32_t)pairs[j]);
+        a = b;
+    }
+    for (uint32_t c = 0; c < ncl; c++) {
+        auto &l = cl_adj[c];
+        std::sort(l.begin(), l.end()); l.erase(std::unique(l.begin(), l.end()), l.end());
+        if (l.size() > LIST_CAP) cl_always[c] = 1;
+    }
+    std::vector<uint32_t> cl_off(ncl + 1, 0), cl_list, vb_off(nvb + 1, 0), vb_list;
+    for (uint32_t c = 0; c < ncl; c++) {
+        cl_off[c] = (uint32_t)cl_list.size();
+        if (cl_always[c]) cl_list.push_back(CULL_ALWAYS); else cl_list.insert(cl_list.end(), cl_adj[c].begin(), cl_adj[c].end());
+    }
+    cl_off[ncl] = (uint32_t)cl_list.size();
+    {
+        size_t a = 0;
+        std::vector<uint32_t> l;
+        for (uint32_t j = 0; j < nvb; j++) {
+            vb_off[j] = (uint32_t)vb_list.size();
+            l.clear();
+            bool always = false;
+            uint32_t last_c = 0xFFFFFFFFu;
+            for (; a < pairs.size() && (uint32_t)(pairs[a] >> 32) < (j + 1) * CULL_CL; a++) {
+                const uint32_t c = (uint32_t)pairs[a];
+                if (c == last_c) continue;
+                last_c = c;
+                if (cl_always[c]) always = true; else l.insert(l.end(), cl_adj[c].begin(), cl_adj[c].end());
+            }
+            std::sort(l.begin(), l.end()); l.erase(std::unique(l.begin(), l.end()), l.end());
+            if (always || l.size() > LIST_CAP) vb_list.push_back(CULL_ALWAYS); else vb_list.insert(vb_list.end(), l.begin(), l.end());
+        }
+        vb_off[nvb] = (uint32_t)vb_list.size();
+    }
+    CK(dalloc(ctx->d_cl_box, (size_t)ncl)); CK(dalloc(ctx->d_cl_adj_off, (size_t)ncl + 1)); CK(dalloc(ctx->d_cl_adj, cl_list.size()));
+    CK(dalloc(ctx->d_vb_adj_off, (size_t)nvb + 1)); CK(dalloc(ctx->d_vb_adj, vb_list.size()));
+    CK(dalloc(ctx->d_cull_flags, (size_t)2 * ncl + nvb));
+    CK(cudaMemcpy(ctx->d_cl_box, boxes.data(), (size_t)ncl * sizeof(ClusterBox), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_cl_adj_off, cl_off.data(), ((size_t)ncl + 1) * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_cl_adj, cl_list.data(), cl_list.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_vb_adj_off, vb_off.data(), ((size_t)nvb + 1) * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_vb_adj, vb_list.data(), vb_list.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(ctx->d_cull_flags, 1, (size_t)2 * ncl + nvb));
+    CullTables &ct = ctx->cull;
+    ct.n_clusters = ncl; ct.n_vblocks = nvb; ct.boxes = ctx->d_cl_box;
+    ct.cl_adj_off = ctx->d_cl_adj_off; ct.cl_adj = ctx->d_cl_adj; ct.vb_adj_off = ctx->d_vb_adj_off; ct.vb_adj = ctx->d_vb_adj;
+    ct.cl_live = ctx->d_cull_flags; ct.mark_need = ctx->d_cull_flags + ncl; ct.vert_need = ctx->d_cull_flags + 2 * (size_t)ncl;
+    return SWEGL_B200_OK;
+}
+
+// does this view run the band culling?  (a pure function of the view and the context's policy: graph keys stay valid)
+static bool view_culled(const swegl_b200_ctx *ctx, const ViewParams &vp)
+{
+    if (ctx->cull_policy == 0 || ctx->cull.n_clusters == 0) return false;
+    const bool banded = vp.band0 > vp.vy || vp.band1 < vp.vy + vp.vh;
+    if (!banded) return false;
+    return ctx->cull_policy == 1 || ctx->ds.n_tris >= 16384;
+}
+
 extern "C" {
 
 int swegl_b200_abi_version(void) { return SWEGL_B200_ABI_VERSION; }
@@ -157,6 +263,8 @@ int swegl_b200_create(int device, swegl_b200_ctx **out)
         ctx->span_policy = !strcmp(e, "dense") ? 1 : (!strcmp(e, "coop") ? 0 : -1);
         ctx->dense_spans = ctx->span_policy == 1;
     }
+    if (const char *e = getenv("SWEGL_B200_CULL"))            // "0" / "1" pin band culling off / on, default: automatic
+        ctx->cull_policy = !strcmp(e, "0") ? 0 : (!strcmp(e, "1") ? 1 : -1);
     *out = ctx;
     return SWEGL_B200_OK;
 }
@@ -172,7 +280,7 @@ void swegl_b200_destroy(swegl_b200_ctx *ctx)
                      ctx->pools.edges, ctx->pools.shades, ctx->pools.spans, ctx->pools.span_shades, ctx->pools.frag_u, ctx->pools.row_slot,
                      ctx->pools.chunks, ctx->pools.bin_head, ctx->pools.bin_used, ctx->pools.tile_stamp, ctx->pools.busy_list,
                      ctx->pools.counters, ctx->d_screen, ctx->d_depth,
-                     ctx->d_tmp_color };
+                     ctx->d_tmp_color, ctx->d_cl_box, ctx->d_cl_adj_off, ctx->d_cl_adj, ctx->d_vb_adj_off, ctx->d_vb_adj, ctx->d_cull_flags };
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     for (auto &sl : ctx->slots) {
@@ -412,6 +520,9 @@ int swegl_b200_upload_scene(swegl_b200_ctx *ctx, const swegl_b200_scene_desc *sc
     ds.pos = ctx->d_pos; ds.nrm = ctx->d_nrm; ds.uv = ctx->d_uv; ds.vert_node = ctx->d_vert_node;
     ds.tris = ctx->d_tris; ds.prims = ctx->d_prims; ds.texels = ctx->d_texels;
     ds.v_world = ctx->d_v_world; ds.v_ndc = ctx->d_v_ndc; ds.n_world = ctx->d_n_world; ds.yes = ctx->d_yes;
+    ds.cl_live = ds.mark_need = ds.vert_need = nullptr;
+    ctx->cull = CullTables{};
+    if (nt && ctx->cull_policy != 0) { rc = build_cull_tables(ctx, tris, sc->positions, vert_node, nv); if (rc) return rc; }
     ctx->n_nodes = sc->n_nodes;
     rc = layout_block(ctx, ctx->lights_cap ? ctx->lights_cap : 8);
     if (rc) return rc;
@@ -586,10 +697,15 @@ static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const Vie
     if (timing) cudaEventRecord(ctx->ev[0], st);
     if (with_frame) cudaMemcpyAsync(ctx->d_block, sl.block, ctx->block_bytes, cudaMemcpyHostToDevice, st);
     else cudaMemcpyAsync(ctx->d_block + ctx->off_vp, sl.block + ctx->off_vp, sizeof(ViewParams), cudaMemcpyHostToDevice, st);
-    launch_vertex(ctx->ds, ctx->d_vp(), ctx->pools.counters, with_frame, st); launches++;
-    launch_mark(ctx->ds, st); launches++;
+    DeviceScene ds = ctx->ds;
+    if (view_culled(ctx, vp)) {                             // sort-first band: skip what cannot reach it (common.cuh)
+        ds.cl_live = ctx->cull.cl_live; ds.mark_need = ctx->cull.mark_need; ds.vert_need = ctx->cull.vert_need;
+        launch_cull(ds, ctx->d_vp(), ctx->cull, st); launches += 2;
+    }
+    launch_vertex(ds, ctx->d_vp(), ctx->pools.counters, with_frame, st); launches++;
+    launch_mark(ds, st); launches++;
     if (timing) cudaEventRecord(ctx->ev[1], st);
-    launch_setup(ctx->ds, ctx->d_vp(), ctx->d_fp(), ctx->pools, st); launches++;
+    launch_setup(ds, ctx->d_vp(), ctx->d_fp(), ctx->pools, st); launches++;
     if (timing) cudaEventRecord(ctx->ev[2], st);
     launch_spans(ctx->d_vp(), ctx->pools, ctx->dense_spans, st); launches++;
     if (timing) cudaEventRecord(ctx->ev[3], st);
@@ -691,7 +807,7 @@ static int render_common(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v,
 
     if (!sync && !stats) {                                   // fire and forget
         rc = render_async(ctx, out, dof);
-        if (rc == SWEGL_B200_OK) { ctx->last_vp = out; ctx->have_vp = true; }
+        if (rc == SWEGL_B200_OK) { ctx->last_vp = out; ctx->have_vp = true; ctx->last_dof = dof; }
         return rc;
     }
     // synchronous frame: direct launches, counters checked, pools grown and the frame redone if needed
@@ -727,7 +843,7 @@ static int render_common(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v,
             cudaEventElapsedTime(&stats->ms_total, ctx->ev[0], ctx->ev[5]);
         }
     }
-    ctx->last_vp = out; ctx->have_vp = true;
+    ctx->last_vp = out; ctx->have_vp = true; ctx->last_dof = dof;
     return SWEGL_B200_OK;
 }
 
@@ -881,6 +997,36 @@ int swegl_b200_read_depth(swegl_b200_ctx *ctx, float *zbuffer)
     const ViewParams &vp = ctx->last_vp;
     CK(cudaMemcpyAsync(zbuffer, ctx->d_depth, (size_t)vp.vw * vp.vh * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_set_band_culling(swegl_b200_ctx *ctx, int policy)
+{
+    if (!ctx || policy < -1 || policy > 1) return fail(ctx, SWEGL_B200_ERR_ARG, "set_band_culling: policy must be -1, 0 or 1");
+    if (ctx->have_scene && ctx->cull.n_clusters == 0 && policy != 0)
+        return fail(ctx, SWEGL_B200_ERR_STATE, "set_band_culling: the scene was uploaded with culling off; call before upload_scene");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    drop_graphs(ctx);                                       // the decision is baked into the captured frames
+    ctx->cull_policy = policy;
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_cull_counts(swegl_b200_ctx *ctx, uint32_t counts[6])
+{
+    if (!ctx || !counts) return SWEGL_B200_ERR_ARG;
+    if (!ctx->have_scene || !ctx->have_vp) return fail(ctx, SWEGL_B200_ERR_STATE, "cull_counts before a rendered view");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const CullTables &ct = ctx->cull;
+    counts[0] = ct.n_clusters; counts[1] = ct.n_vblocks; counts[2] = counts[3] = ct.n_clusters; counts[4] = ct.n_vblocks; counts[5] = 0;
+    const bool dof = ctx->last_dof;
+    if (!view_culled(ctx, draw_params(ctx->last_vp, dof))) return SWEGL_B200_OK;
+    std::vector<uint8_t> f((size_t)2 * ct.n_clusters + ct.n_vblocks);
+    CK(cudaMemcpy(f.data(), ctx->d_cull_flags, f.size(), cudaMemcpyDeviceToHost));
+    counts[2] = counts[3] = counts[4] = 0; counts[5] = 1;
+    for (uint32_t c = 0; c < ct.n_clusters; c++) { counts[2] += f[c]; counts[3] += f[ct.n_clusters + c]; }
+    for (uint32_t j = 0; j < ct.n_vblocks; j++) counts[4] += f[(size_t)2 * ct.n_clusters + j];
     return SWEGL_B200_OK;
 }
 

@@ -17,6 +17,78 @@ static constexpr int TPB = 256;
 static constexpr uint32_t SPAN_SEG = 4;      // 32-column bins per span segment (one lane walks one segment)
 
 // ----------------------------------------------------------------------------------------
+// band culling (row-band sharding): which triangle clusters / vertex blocks this view has to look at at all
+// ----------------------------------------------------------------------------------------
+// One thread per cluster.  Every vertex the cluster references lies inside its object-space box, and
+// object -> world -> camera -> (y', z') is affine, so in exact arithmetic y'/z' of any such vertex lies between the
+// extremes over the 8 box corners as long as z' > 0 on all of them.  The fp32 results the vertex stage really
+// produces differ from exact by at most E = 64 ulp-units of the summed magnitudes (12 roundings on the way); the
+// interval below carries 2E (corner + vertex).  A box that comes closer than 0.002 to the camera plane is never
+// culled (the near clipper, renderer.cpp:286-356, then creates vertices of its own).  Rows walked by an unclipped
+// triangle are [ceil(min y), ceil(max y)) of its pixel-space vertices (renderer.cpp:375-394).
+__global__ void __launch_bounds__(128) k_cull_live(DeviceScene s, const ViewParams *__restrict__ vpp, CullTables ct)
+{
+    pdl_trigger();
+    const uint32_t c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= ct.n_clusters) return;
+    const ClusterBox box = ct.boxes[c];
+    bool live = true;
+    if (box.node >= 0) {
+        const float *M = s.node_world + 16 * box.node;
+        const float *V = vpp->view, *P = vpp->proj;
+        double aw[3], ac[3];
+        const double pm[3] = { fmax(fabs((double)box.lo[0]), fabs((double)box.hi[0])), fmax(fabs((double)box.lo[1]), fabs((double)box.hi[1])),
+                               fmax(fabs((double)box.lo[2]), fabs((double)box.hi[2])) };
+        for (int r = 0; r < 3; r++)
+            aw[r] = fabs((double)M[4 * r]) * pm[0] + fabs((double)M[4 * r + 1]) * pm[1] + fabs((double)M[4 * r + 2]) * pm[2] + fabs((double)M[4 * r + 3]);
+        for (int r = 0; r < 3; r++)
+            ac[r] = fabs((double)V[4 * r]) * aw[0] + fabs((double)V[4 * r + 1]) * aw[1] + fabs((double)V[4 * r + 2]) * aw[2] + fabs((double)V[4 * r + 3]);
+        const double ay = fabs((double)P[4]) * ac[0] + fabs((double)P[5]) * ac[1] + fabs((double)P[6]) * ac[2] + fabs((double)P[7]);
+        const double az = fabs((double)P[8]) * ac[0] + fabs((double)P[9]) * ac[1] + fabs((double)P[10]) * ac[2] + fabs((double)P[11]);
+        const double E = 2.0 * 64.0 * 5.9604644775390625e-8;            // 2 x 64 x 2^-24
+        const double Ey = E * ay, Ez = E * az;
+        double rlo = 1e300, rhi = -1e300, zmin = 1e300;
+        for (int k = 0; k < 8; k++) {
+            const V3 p = v3((k & 1) ? box.hi[0] : box.lo[0], (k & 2) ? box.hi[1] : box.lo[1], (k & 4) ? box.hi[2] : box.lo[2]);
+            const V3 q = xform(P, xform(V, xform(M, p)));                   // the vertex stage's own operations
+            const double y = (double)q.y, z = (double)q.z;
+            zmin = fmin(zmin, z);
+            const double zl = z - Ez, zh = z + Ez, yh = y + Ey, yl = y - Ey;
+            rhi = fmax(rhi, yh >= 0.0 ? yh / zl : yh / zh);
+            rlo = fmin(rlo, yl >= 0.0 ? yl / zh : yl / zl);
+        }
+        if (zmin - Ez > 0.002) {
+            const double m11 = (double)vpp->vp_m11, m13 = (double)vpp->vp_m13;
+            const double a = m11 * rlo + m13, b = m11 * rhi + m13;
+            const double ylo = fmin(a, b), yhi = fmax(a, b);
+            const double margin = 1.0 + 1e-5 * (fabs(m11) * fmax(fabs(rlo), fabs(rhi)) + fabs(m13));
+            // NaNs anywhere compare false: the cluster stays live
+            if (yhi + margin < (double)vpp->band0 - 1.0 || ylo - margin > (double)vpp->band1 + 1.0) live = false;
+        }
+    }
+    ct.cl_live[c] = live ? 1 : 0;
+}
+
+// One thread per cluster (mark_need) and per vertex block (vert_need): OR of cl_live over a static adjacency list.
+__global__ void __launch_bounds__(128) k_cull_need(CullTables ct)
+{
+    pdl_trigger();
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    const bool is_cl = i < ct.n_clusters;
+    const uint32_t j = is_cl ? i : i - ct.n_clusters;
+    if (!is_cl && j >= ct.n_vblocks) { pdl_wait(); return; }
+    const uint32_t *off = is_cl ? ct.cl_adj_off : ct.vb_adj_off, *adj = is_cl ? ct.cl_adj : ct.vb_adj;
+    const uint32_t a = off[j], b = off[j + 1];
+    pdl_wait();                                                             // k_cull_live's flags
+    bool need = false;
+    for (uint32_t k = a; k < b && !need; k++) {
+        const uint32_t c = adj[k];
+        need = c == CULL_ALWAYS || ct.cl_live[c] != 0;
+    }
+    (is_cl ? ct.mark_need : ct.vert_need)[j] = need ? 1 : 0;
+}
+
+// ----------------------------------------------------------------------------------------
 // vertex stage
 // ----------------------------------------------------------------------------------------
 // v_world = M_node * v (A1, once per frame) and, per viewport, camera/projection transform, world normal and the
@@ -31,7 +103,9 @@ __global__ void __launch_bounds__(TPB) k_vertex(DeviceScene s, const ViewParams 
     if (blockIdx.x == 0 && threadIdx.x < sizeof(Counters) / 4) reinterpret_cast<uint32_t *>(counters)[threadIdx.x] = 0;
     __syncthreads();
     uint32_t i = blockIdx.x * TPB + threadIdx.x;
+    pdl_wait();                                                             // (culled views only) k_cull_need's flags
     if (i >= s.n_vertices) return;
+    if (s.vert_need && !s.vert_need[i / CULL_CL]) return;                   // no triangle that matters to this band uses it
     const uint32_t node = s.vert_node[i];
     V3 w;
     if (WORLD) {
@@ -55,7 +129,11 @@ __global__ void __launch_bounds__(TPB) k_mark(DeviceScene s)
 {
     pdl_trigger();
     uint32_t t = blockIdx.x * TPB + threadIdx.x;
-    if (t >= s.n_tris) return;
+    if (t >= s.n_tris) { pdl_wait(); return; }                              // (every CTA waits: completion stays transitive along the chain)
+    if (s.mark_need) {
+        pdl_wait();
+        if (!s.mark_need[t / CULL_CL]) return;                              // cannot mark a vertex of a triangle that reaches the band
+    }
     Tri tr = s.tris[t];                                                     // static scene data: may be read before the wait
     pdl_wait();                                                             // k_vertex's v_ndc and yes reset
     V3 a = v3(s.v_ndc[3 * tr.i0], s.v_ndc[3 * tr.i0 + 1], s.v_ndc[3 * tr.i0 + 2]);
@@ -290,6 +368,15 @@ __global__ void __launch_bounds__(128, SETUP_MINB) k_setup(DeviceScene s, const 
     RowRange r0 = { 0u, 0u }, r1 = { 0u, 0u };
     Tri tr = { 0u, 0u, 0u, 0u };
     bool go = t < s.n_tris;
+    if (s.cl_live) {                                                        // band culling: 128 threads = 2 clusters
+        static_assert(128 % CULL_CL == 0, "a warp never straddles two clusters");
+        pdl_wait();
+        const uint32_t c0 = blockIdx.x * (128 / CULL_CL), ncl = (s.n_tris + CULL_CL - 1) / CULL_CL;
+        bool any = false;
+        for (uint32_t c = c0; c < c0 + 128 / CULL_CL && c < ncl; c++) any = any || s.cl_live[c];
+        if (!any) return;                                                   // CTA-uniform
+        go = go && s.cl_live[t / CULL_CL];
+    }
     if (go) tr = s.tris[t];
     pdl_wait();                                                             // k_mark's yes flags
     if (go) {
@@ -789,12 +876,20 @@ __global__ void __launch_bounds__(TPB) k_spans_dense(const ViewParams *__restric
 // ----------------------------------------------------------------------------------------
 static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
+void launch_cull(const DeviceScene &s, const ViewParams *d_vp, const CullTables &ct, cudaStream_t st)
+{
+    // first kernel of the view: it follows the upload of the parameter block (a copy, not a kernel) -> ordinary launch
+    launch_chain(k_cull_live, max(1u, cdiv(ct.n_clusters, 128u)), 128, st, false, s, d_vp, ct);
+    launch_chain(k_cull_need, max(1u, cdiv(ct.n_clusters + ct.n_vblocks, 128u)), 128, st, true, ct);
+}
 void launch_vertex(const DeviceScene &s, const ViewParams *d_vp, Counters *counters, bool with_world, cudaStream_t st)
 {
     const unsigned blocks = max(1u, cdiv(s.n_vertices, TPB));
-    // first kernel of the frame: it follows the upload of the parameter block (a copy, not a kernel) -> ordinary launch
-    if (with_world) launch_chain(k_vertex<true>, blocks, TPB, st, false, s, d_vp, counters);
-    else launch_chain(k_vertex<false>, blocks, TPB, st, false, s, d_vp, counters);
+    // first kernel of the frame unless the view is culled: then it follows the upload of the parameter block (a copy,
+    // not a kernel) -> ordinary launch.  A culled view skips vertices, so it can never rely on an earlier view's v_world.
+    const bool chained = s.vert_need != nullptr;
+    if (with_world || chained) launch_chain(k_vertex<true>, blocks, TPB, st, chained, s, d_vp, counters);
+    else launch_chain(k_vertex<false>, blocks, TPB, st, chained, s, d_vp, counters);
 }
 void launch_mark(const DeviceScene &s, cudaStream_t st)
 {

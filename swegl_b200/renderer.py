@@ -148,6 +148,15 @@ class Renderer:
         self._check(self.lib.swegl_b200_read_vertices(self.ctx, vw.ctypes.data, vv.ctypes.data, nw.ctypes.data, yes.ctypes.data))
         return dict(v_world=vw, v_viewport=vv, normal_world=nw, yes=yes)
 
+    def set_band_culling(self, policy):
+        """-1 automatic, 0 off, 1 on for every banded view; call before upload_scene (include/swegl_b200.h)"""
+        self._check(self.lib.swegl_b200_set_band_culling(self.ctx, int(policy)))
+
+    def cull_counts(self):
+        c = (C.c_uint32 * 6)()
+        self._check(self.lib.swegl_b200_cull_counts(self.ctx, c))
+        return dict(clusters=c[0], vertex_blocks=c[1], live=c[2], marked=c[3], vertex_blocks_needed=c[4], culled=bool(c[5]))
+
     def device_buffers(self):
         s, d = C.c_void_p(), C.c_void_p()
         self._check(self.lib.swegl_b200_device_buffers(self.ctx, C.byref(s), C.byref(d)))

@@ -323,3 +323,76 @@ def test_errors(renderer):
     renderer.begin_frame(scene)
     with pytest.raises(SweglB200Error):
         renderer.render(vps[0], np.zeros((240, 320), np.uint32))      # viewport larger than the screen
+
+
+# ---- sort-first band culling (include/swegl_b200.h: swegl_b200_set_band_culling) ----
+@pytest.fixture(scope="module")
+def culling_renderer():
+    from swegl_b200 import Renderer
+    r = Renderer(0)
+    r.set_band_culling(1)              # every banded view, also of scenes below the automatic threshold
+    yield r
+    r.close()
+
+
+def _bands(h, n):
+    """n uneven bands covering [0, h)"""
+    cuts = sorted({0, h} | {int(h * (k / n) ** 1.3) for k in range(1, n)})
+    return list(zip(cuts[:-1], cuts[1:]))
+
+
+CULL_CASES = [("sphere100_1080", None, 8), ("truck_1080", None, 5), ("brainstem_4k_dof", None, 8), ("truck_4k_dof", None, 3),
+              ("brainstem_4k", None, 16),
+              ("truck_1080", [("translate", 0, 0.5, -0.9), ("rotate_y", 0.4)], 6),          # camera inside the scene: near clipping
+              ("box_640_close", None, 4)]
+
+
+@pytest.mark.parametrize("name,pose,n_bands", CULL_CASES)
+def test_band_culling_is_invisible(culling_renderer, name, pose, n_bands):
+    """a banded view that skips the triangle clusters / vertex blocks that cannot reach it is bit-identical (colour and
+    depth) to the full frame rendered without culling, and something is actually skipped"""
+    r = culling_renderer
+    scene, vps, screen, cfg = configs.build(name)
+    vp = vps[0]
+    if pose is not None:
+        from swegl_b200.scene import Viewport
+        vp = Viewport(vp.x, vp.y, vp.w, vp.h, transparency_layers=0, post_mode=vp.post_mode, focal_distance=vp.focal_distance,
+                      focal_depth=vp.focal_depth)
+        vp.camera.apply(pose)
+    full, fz, _ = render_gpu(r, scene, [vp], screen)
+    assert not r.cull_counts()["culled"]
+    px = np.zeros_like(full)
+    z = np.empty_like(fz[0])
+    skipped = 0
+    for b0, b1 in _bands(vp.h, n_bands):
+        vp.band = (b0, b1)
+        r.render(vp, px, z)
+        c = r.cull_counts()
+        assert c["culled"] and c["live"] <= c["marked"] <= c["clusters"]
+        skipped += c["clusters"] - c["marked"]
+    vp.band = (0, 0)
+    assert (px == full).all() and (z.view(np.uint32) == fz[0].view(np.uint32)).all()
+    if scene.n_triangles() >= 2000 and pose is None:
+        assert skipped > 0, "no cluster was ever skipped"
+
+
+def test_band_culling_async_graph_path(culling_renderer):
+    """the same through the captured-graph path (render_device) with a changing camera: flags are per view, not cached"""
+    r = culling_renderer
+    scene, vps, screen, cfg = configs.build("sphere100_1080")
+    vp = vps[0]
+    r.upload_scene(scene); r.set_screen(*screen)
+    for step in range(3):
+        vp.camera.apply([("rotate_y", 0.15 * step), ("translate", 0.1 * step, 0, 0)])
+        r.begin_frame(scene)
+        full = np.zeros((screen[1], screen[0]), np.uint32)
+        r.render(vp, full)
+        got = np.zeros_like(full)
+        for b0, b1 in _bands(vp.h, 4):
+            vp.band = (b0, b1)
+            r.begin_frame(scene)
+            r.render_device(vp, stats=False)
+            r.synchronize()
+            got[b0:b1] = r.read_screen()[b0:b1]
+        vp.band = (0, 0)
+        assert (got == full).all(), f"step {step}"
