@@ -99,11 +99,17 @@ __global__ void __launch_bounds__(TPB) k_vertex(DeviceScene s, const ViewParams 
 {
     pdl_trigger();
     __shared__ ViewParams vp;
-    for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
     if (blockIdx.x == 0 && threadIdx.x < sizeof(Counters) / 4) reinterpret_cast<uint32_t *>(counters)[threadIdx.x] = 0;
+    if (s.vert_need) {                                                      // culled view: TPB threads = TPB / CULL_CL vertex blocks
+        pdl_wait();                                                         // k_cull_need's flags
+        const uint32_t b0 = blockIdx.x * (TPB / CULL_CL), nvb = (s.n_vertices + CULL_CL - 1) / CULL_CL;
+        bool any = false;
+        for (uint32_t b = b0; b < b0 + TPB / CULL_CL && b < nvb; b++) any = any || s.vert_need[b];
+        if (!any) return;                                                   // CTA-uniform, before anything is staged
+    }
+    for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
     __syncthreads();
     uint32_t i = blockIdx.x * TPB + threadIdx.x;
-    pdl_wait();                                                             // (culled views only) k_cull_need's flags
     if (i >= s.n_vertices) return;
     if (s.vert_need && !s.vert_need[i / CULL_CL]) return;                   // no triangle that matters to this band uses it
     const uint32_t node = s.vert_node[i];
@@ -361,12 +367,7 @@ __global__ void __launch_bounds__(128, SETUP_MINB) k_setup(DeviceScene s, const 
     pdl_trigger();
     __shared__ ViewParams vp;                   // staged once per CTA: used all over the set-up code
     __shared__ FrameParams fp;
-    for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += 128) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
-    for (int w = threadIdx.x; w < (int)(sizeof(FrameParams) / 4); w += 128) reinterpret_cast<uint32_t *>(&fp)[w] = reinterpret_cast<const uint32_t *>(fpp)[w];
-    __syncthreads();
     const uint32_t t = blockIdx.x * 128 + threadIdx.x;
-    RowRange r0 = { 0u, 0u }, r1 = { 0u, 0u };
-    Tri tr = { 0u, 0u, 0u, 0u };
     bool go = t < s.n_tris;
     if (s.cl_live) {                                                        // band culling: 128 threads = 2 clusters
         static_assert(128 % CULL_CL == 0, "a warp never straddles two clusters");
@@ -374,9 +375,14 @@ __global__ void __launch_bounds__(128, SETUP_MINB) k_setup(DeviceScene s, const 
         const uint32_t c0 = blockIdx.x * (128 / CULL_CL), ncl = (s.n_tris + CULL_CL - 1) / CULL_CL;
         bool any = false;
         for (uint32_t c = c0; c < c0 + 128 / CULL_CL && c < ncl; c++) any = any || s.cl_live[c];
-        if (!any) return;                                                   // CTA-uniform
+        if (!any) return;                                                   // CTA-uniform, before anything is staged
         go = go && s.cl_live[t / CULL_CL];
     }
+    for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += 128) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
+    for (int w = threadIdx.x; w < (int)(sizeof(FrameParams) / 4); w += 128) reinterpret_cast<uint32_t *>(&fp)[w] = reinterpret_cast<const uint32_t *>(fpp)[w];
+    __syncthreads();
+    RowRange r0 = { 0u, 0u }, r1 = { 0u, 0u };
+    Tri tr = { 0u, 0u, 0u, 0u };
     if (go) tr = s.tris[t];
     pdl_wait();                                                             // k_mark's yes flags
     if (go) {

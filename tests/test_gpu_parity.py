@@ -396,3 +396,33 @@ def test_band_culling_async_graph_path(culling_renderer):
             got[b0:b1] = r.read_screen()[b0:b1]
         vp.band = (0, 0)
         assert (got == full).all(), f"step {step}"
+
+
+def test_frame_pipeline_renders_the_same_frames(renderer):
+    """swegl_b200.FramePipeline (several contexts, frames round robin, overlapping on the GPU) produces exactly the frames
+    one context renders one at a time -- with a camera that moves from frame to frame"""
+    from swegl_b200.pipeline import FramePipeline
+    scene, vps, screen, cfg = configs.build("truck_1080")
+    vp = vps[0]
+    renderer.upload_scene(scene); renderer.set_screen(*screen)
+    pipe = FramePipeline(0, 3)
+    try:
+        pipe.upload_scene(scene); pipe.set_screen(*screen)
+        pipe.size_pools(scene, vps)
+        want, slots = [], []
+        for i in range(6):
+            vp.camera.apply([("rotate_y", 0.07), ("translate", 0.05, 0, 0)])
+            renderer.begin_frame(scene)
+            px = np.zeros((screen[1], screen[0]), np.uint32)
+            renderer.render(vp, px)
+            want.append(px)
+            slots.append(pipe.submit(scene, [vp.desc()]))
+            if i >= 2:                                  # frame i-2's context is about to be reused: read it first
+                pass
+            if len(slots) == 3:
+                pipe.synchronize()
+                for k, w in zip(slots, want):
+                    assert (pipe.read_screen(k) == w).all()
+                want, slots = [], []
+    finally:
+        pipe.close()
