@@ -15,14 +15,37 @@ namespace sb {
 
 SB_DEV V3 ld3(const float *p) { return v3(p[0], p[1], p[2]); }
 
-// (unsigned char)round(x), colors.cpp:19-25 (round half away from zero), for the common case 0 <= x < 2^23
+// Conversions between small integers and floats without the XU pipe.  I2F / F2I / FRND issue at a quarter of the FP32
+// rate on sm_100 and the bilinear filter alone needs 16 + 8 of them per pixel (ncu: XU pipe 88 % busy in k_fragments
+// before this); for values below 2^22 the same results come out of the FP32 adder:
+//   2^23 + n is exact for an integer 0 <= n < 2^23 and its low mantissa bits ARE n.
+static constexpr float MAGIC23 = 8388608.0f;            // 2^23, bits 0x4B000000
+// (float)byte k of `word`: one PRMT builds the bits of 2^23 + byte, one exact subtraction removes the 2^23
+template <int K> SB_DEV float byte_to_float(uint32_t word)
+{
+    return __fsub_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440u | K)), MAGIC23);
+}
+SB_DEV float small_uint_to_float(uint32_t n)            // n < 2^23
+{
+    return __fsub_rn(__uint_as_float(0x4B000000u | n), MAGIC23);
+}
+// trunc(a) for 0 <= a < 2^22 as the low mantissa bits of RZ(a + 2^23); the caller masks what it needs
+SB_DEV uint32_t trunc_bits_small(float a) { return __float_as_uint(__fadd_rz(a, MAGIC23)); }
+
+// (unsigned char)round(x), colors.cpp:19-25 (round half away from zero), for the common case 0 <= x < 2^22
 // as trunc + exact fraction test; anything else takes roundf
 SB_DEV uint32_t round_to_byte(float a)
 {
-    if (!(a >= 0.0f && a < 8388608.0f)) return (uint32_t)f2i(roundf(a)) & 0xFFu;
-    const int i = __float2int_rz(a);
-    const float fr = fsub(a, (float)i);                                     // exact
-    return (uint32_t)(i + (fr >= 0.5f ? 1 : 0)) & 0xFFu;
+    if (!(a >= 0.0f && a < 4194304.0f)) return (uint32_t)f2i(roundf(a)) & 0xFFu;
+    const float r = __fadd_rz(a, MAGIC23);                                  // 2^23 + trunc(a)
+    const float fr = fsub(a, __fsub_rn(r, MAGIC23));                        // exact
+    return (__float_as_uint(r) + (fr >= 0.5f ? 1u : 0u)) & 0xFFu;
+}
+// floorf(x) for |x| < 2^22: RD(x + 1.5 * 2^23) lies in [2^23, 2^24) where the spacing is 1
+SB_DEV float floor_small(float x)
+{
+    if (fabsf(x) < 4194304.0f) return __fsub_rn(__fadd_rd(x, 12582912.0f), 12582912.0f);
+    return floorf(x);
 }
 // a mod n as the reference computes texel rows/columns, with the negative (UB in the reference) case wrapped
 SB_DEV int wrap_index(int a, int n, int mask)
@@ -49,7 +72,7 @@ SB_DEV uint32_t shade_texture(const SpanShade *ss, const Prim &pr, const uint32_
     // pixel_shader_texture_bilinear::shade, pixel_shaders.cpp:348-384: t.x picks the ROW, t.y the COLUMN
     float v = tx, uq = ty;
     float u1 = fsub(uq, 0.5f), u2 = fadd(uq, 0.5f), v1 = fsub(v, 0.5f), v2 = fadd(v, 0.5f);
-    uq = floorf(u2); v = floorf(v2);
+    uq = floor_small(u2); v = floor_small(v2);
     int tw = pr.tw, th = pr.th;
     int v1m = wrap_index(f2i(v1) + th, th, pr.th_mask);                     // ((int)v1 + theight) % theight; UB guard
     int v2m = v1m + 1; if (v2m == th) v2m = 0;
@@ -61,15 +84,14 @@ SB_DEV uint32_t shade_texture(const SpanShade *ss, const Prim &pr, const uint32_
     float w00 = fmul(fsub(uq, u1), fsub(v, v1)), w10 = fmul(fsub(uq, u1), fsub(v2, v));
     float w01 = fmul(fsub(u2, uq), fsub(v, v1)), w11 = fmul(fsub(u2, uq), fsub(v2, v));
     uint32_t out = 0;
-    #pragma unroll
-    for (int c = 0; c < 4; c++) {
-        int sft = 8 * c;
-        float acc = fmul((float)((p00 >> sft) & 0xFF), w00);                // pixel_colors * float, colors.cpp:27-30
-        acc = fadd(acc, fmul((float)((p10 >> sft) & 0xFF), w10));           // _mm_add_ps, left to right
-        acc = fadd(acc, fmul((float)((p01 >> sft) & 0xFF), w01));
-        acc = fadd(acc, fmul((float)((p11 >> sft) & 0xFF), w11));
-        out |= round_to_byte(acc) << sft;                                   // (unsigned char)round(), colors.cpp:19-25
-    }
+    #define SB_BILINEAR_CHANNEL(C) { \
+        float acc = fmul(byte_to_float<C>(p00), w00);                       /* pixel_colors * float, colors.cpp:27-30 */ \
+        acc = fadd(acc, fmul(byte_to_float<C>(p10), w10));                  /* _mm_add_ps, left to right */ \
+        acc = fadd(acc, fmul(byte_to_float<C>(p01), w01)); \
+        acc = fadd(acc, fmul(byte_to_float<C>(p11), w11)); \
+        out |= round_to_byte(acc) << (8 * C); }                             /* (unsigned char)round(), colors.cpp:19-25 */
+    SB_BILINEAR_CHANNEL(0) SB_BILINEAR_CHANNEL(1) SB_BILINEAR_CHANNEL(2) SB_BILINEAR_CHANNEL(3)
+    #undef SB_BILINEAR_CHANNEL
     return out;
 }
 
@@ -100,15 +122,22 @@ SB_DEV uint32_t shade(const SpanShade *ss, float flat_light, const Prim &pr, con
     float light = fmul(__int2float_rn(li), 1.0f / 65536.0f);               // (float)(li / 65536.0)
     uint32_t b = c & 0xFF, g = (c >> 8) & 0xFF, r = (c >> 16) & 0xFF;
     if (light < 1.0f) {
-        // |light| <= 32768 and c <= 255, so the product is always inside int range: plain truncation
-        b = (uint32_t)__float2int_rz(fmul((float)b, light)) & 0xFF;
-        g = (uint32_t)__float2int_rz(fmul((float)g, light)) & 0xFF;
-        r = (uint32_t)__float2int_rz(fmul((float)r, light)) & 0xFF;
+        if (light >= 0.0f) {
+            // 0 <= c * light < 255: truncation through the adder (see trunc_bits_small), no I2F / F2I
+            b = trunc_bits_small(fmul(small_uint_to_float(b), light)) & 0xFF;
+            g = trunc_bits_small(fmul(small_uint_to_float(g), light)) & 0xFF;
+            r = trunc_bits_small(fmul(small_uint_to_float(r), light)) & 0xFF;
+        } else {
+            // |light| <= 32768 and c <= 255, so the product is always inside int range: plain truncation
+            b = (uint32_t)__float2int_rz(fmul((float)b, light)) & 0xFF;
+            g = (uint32_t)__float2int_rz(fmul((float)g, light)) & 0xFF;
+            r = (uint32_t)__float2int_rz(fmul((float)r, light)) & 0xFF;
+        }
     } else {
-        light = __fsqrt_rn(__fsqrt_rn(light));
-        b = (255u - ((uint32_t)__float2int_rz(fdiv((float)(255 - (int)b), light)) & 0xFF)) & 0xFF;   // light >= 1
-        g = (255u - ((uint32_t)__float2int_rz(fdiv((float)(255 - (int)g), light)) & 0xFF)) & 0xFF;
-        r = (255u - ((uint32_t)__float2int_rz(fdiv((float)(255 - (int)r), light)) & 0xFF)) & 0xFF;
+        light = __fsqrt_rn(__fsqrt_rn(light));                              // light >= 1: 0 <= (255 - c) / light <= 255
+        b = (255u - (trunc_bits_small(fdiv(small_uint_to_float(255u - b), light)) & 0xFF)) & 0xFF;
+        g = (255u - (trunc_bits_small(fdiv(small_uint_to_float(255u - g), light)) & 0xFF)) & 0xFF;
+        r = (255u - (trunc_bits_small(fdiv(small_uint_to_float(255u - r), light)) & 0xFF)) & 0xFF;
     }
     return (c & 0xFF000000u) | (r << 16) | (g << 8) | b;
 }
