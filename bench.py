@@ -398,7 +398,7 @@ def sharded_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
     ms_gather = timed()                                 # bands sent to rank 0 after rendering (NCCL send/recv)
-    ms_peer, peer_ok = None, None
+    ms_peer, peer_ok, ms_sync, sync_ok, sync_info = None, None, None, None, None
     if world > 1:
         # the fused form: every rank's last kernel stores its band into rank 0's screen over NVLink (CUDA IPC mapping)
         checksum = int(full.to(torch.int64).sum().item()) if rank == 0 else 0
@@ -409,19 +409,92 @@ def sharded_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
         ms_peer = timed()
         if rank == 0:
             peer_ok = int(full.to(torch.int64).sum().item()) == checksum        # same frame as the gathered one
-        r.set_color_target(None)
+        # the frame protocol (swegl_b200_set_frame_sync): no collective at all -- rank 0 clears the others' rows locally,
+        # they store only the tiles they drew into and raise a flag in rank 0's memory; bands rebalanced on measured time
         state["peer"] = False
+        state["sync"] = True
+        sharding.arm_frame_sync(r, dist, dst=0)
+
+        def one_sync():
+            r.begin_frame(scene, nodes)
+            r.render_device(state["desc"], stats=False)
+            return full
+        nonlocal_one = one_sync
+
+        def own_time_ms():
+            """this rank's own share of one frame: CUDA events around its chain (rank 0: the device-side stamps, which
+            exclude its wait for the others)"""
+            for _ in range(2):
+                nonlocal_one()
+            r.synchronize(); torch.cuda.synchronize(); dist.barrier()
+            acc = 0.0
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); nonlocal_one(); e1.record()
+                r.synchronize(); torch.cuda.synchronize()
+                acc += (r.frame_sync_status()[1] if rank == 0 else e0.elapsed_time(e1)) / 5
+                dist.barrier()
+            return acc
+        history = []
+        for it in range(4):
+            t_own = torch.tensor([own_time_ms()], device="cuda", dtype=torch.float64)
+            ts = [torch.zeros_like(t_own) for _ in range(world)]
+            dist.all_gather(ts, t_own)
+            ts = [float(t.item()) for t in ts]
+            history.append({"bands": state["bands"], "own_ms": [round(t, 4) for t in ts]})
+            if it == 3:
+                break
+            nb = sharding.rebalance_bands(state["bands"], ts, damping=0.8)
+            set_bands(nb)
+            r.set_frame_sync(-1)                        # pools for the new band are sized outside the protocol
+            r.begin_frame(scene, nodes)
+            r.render_device(state["desc"], stats=True)
+            sharding.arm_frame_sync(r, dist, dst=0)
+        one_saved = one
+
+        def timed_sync():
+            for _ in range(max(warmup, 3)):
+                nonlocal_one()
+            r.synchronize(); torch.cuda.synchronize(); dist.barrier()
+            ms = []
+            for _ in range(steps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); nonlocal_one(); e1.record()
+                r.synchronize(); torch.cuda.synchronize()
+                ms.append(e0.elapsed_time(e1))
+                dist.barrier()                          # host-side, outside the events: frames start together
+            t = torch.tensor([sum(ms) / len(ms)], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        if rank == 0:
+            full.zero_()
+        ms_sync = timed_sync()
+        errs = torch.tensor([r.frame_sync_errors()], device="cuda", dtype=torch.int64)
+        dist.all_reduce(errs)
+        # same frame as the gathered one?  (the bands moved, the frame must not)
+        if rank == 0:
+            sync_ok = int(full.to(torch.int64).sum().item()) == checksum and int(errs.item()) == 0
+        sync_info = {"balance_history": history, "timed_out_waits": int(errs.item())}
+        r.set_frame_sync(-1)
+        r.set_color_target(None)
+        state["sync"] = False
+        dist.barrier()
     st = r.render_device(state["desc"], stats=True)
-    best = ms_gather if ms_peer is None else min(ms_gather, ms_peer)
+    cands = [m for m in (ms_gather, ms_peer, ms_sync) if m is not None]
+    best = min(cands)
     return {"workload": name, "description": cfg["desc"], "ms_per_frame": best, "fps": 1e3 / best,
             "ms_per_frame_nccl_gather": ms_gather if world > 1 else None,
             "ms_per_frame_peer_write": ms_peer, "peer_write_frame_matches_gather": peer_ok,
+            "ms_per_frame_peer_protocol": ms_sync, "peer_protocol_frame_matches_gather": sync_ok, "peer_protocol": sync_info,
             "n_gpus": world,
-            "partition": ("contiguous row bands of the full viewport, balanced on the previous frame's coverage per row; "
-                          "output either sent to rank 0 with NCCL send/recv after rendering, or stored into rank 0's screen "
-                          "by the frame's last kernel over NVLink peer memory + a one-element all-reduce") if world > 1 else "single GPU",
-            "bands": [list(b) for b in state["bands"]],
-            "rank0_band_covered_pixels": int(st.n_covered), "scaling": "strong"}
+            "partition": ("contiguous row bands of the full viewport (sort-first, scene replicated, band culling on). Output: "
+                          "(a) nccl_gather: bands sent to rank 0 with NCCL send/recv after rendering; (b) peer_write: every rank's last "
+                          "kernel stores its band into rank 0's screen over NVLink peer memory, then a one-element all-reduce; "
+                          "(c) peer_protocol: no collective -- rank 0 clears the other bands locally, the others store only the tiles "
+                          "they drew into and raise a flag in rank 0's memory, rank 0's last kernel waits for the flags; bands "
+                          "rebalanced on the ranks' measured times") if world > 1 else "single GPU",
+            "bands": state["bands"], "rank0_band_covered_pixels": int(st.n_covered), "scaling": "strong"}
 
 
 def main():

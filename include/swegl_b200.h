@@ -205,6 +205,23 @@ int  swegl_b200_export_screen(swegl_b200_ctx *ctx, void *handle64);
 int  swegl_b200_import_screen(swegl_b200_ctx *ctx, const void *handle64, void **peer_screen);
 int  swegl_b200_set_color_target(swegl_b200_ctx *ctx, void *device_screen);
 
+/* Frame protocol for the band-sharded single frame, without a collective.  After every rank has selected rank 0's
+ * screen as its colour target, swegl_b200_set_frame_sync(ctx, rank, world) makes the banded, opaque views submitted
+ * through swegl_b200_render_viewport_device(stats == NULL) follow this protocol, entirely on the GPUs:
+ *   rank 0   first kernel: clears the other ranks' rows of its screen (local HBM writes) and publishes "ready(frame)";
+ *            last kernel: waits until every other rank's "done(frame)" flag has arrived -- when the stream reaches the
+ *            end of the view, the whole frame is in rank 0's screen;
+ *   rank r   waits for "ready(frame)" (a load over NVLink) in front of its last kernel, stores ONLY the tiles it drew
+ *            into (the background is already there), then writes "done(frame)" into rank 0's memory.
+ * The flags live behind the pixels of the exported screen, so import_screen is all the set-up it needs.  Every rank
+ * must submit the same sequence of such views; call it on all ranks (rank 0 first, then a host barrier) to (re)start
+ * the sequence, e.g. after a frame reported SWEGL_B200_ERR_CAPACITY.  rank < 0 switches the protocol off.
+ * Waits give up after about 2 s (a lost peer must not hang the GPU); frame_sync_status counts those and, on rank 0,
+ * reports how long rank 0's own share of the last frame took (clear + own band, without the wait for the others:
+ * the input of a time-based band balance).  Either pointer may be null. */
+int  swegl_b200_set_frame_sync(swegl_b200_ctx *ctx, int rank, int world);
+int  swegl_b200_frame_sync_status(swegl_b200_ctx *ctx, uint32_t *timeouts, float *rank0_own_ms);
+
 /* ---- read-back of device state (parity tests, multi-GPU gather) ---- */
 /* device pointers of the screen (screen_w*screen_h words) and of the last viewport's depth */
 int  swegl_b200_device_buffers(swegl_b200_ctx *ctx, void **screen_dev, void **depth_dev);

@@ -91,6 +91,8 @@ SYMBOLS = [
     ("swegl_b200_read_screen", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     ("swegl_b200_read_depth", C.c_int, [C.c_void_p, C.c_void_p]),
     ("swegl_b200_read_vertices", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("swegl_b200_set_frame_sync", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    ("swegl_b200_frame_sync_status", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("swegl_b200_set_band_culling", C.c_int, [C.c_void_p, C.c_int]),
     ("swegl_b200_cull_counts", C.c_int, [C.c_void_p, C.c_void_p]),
 ]

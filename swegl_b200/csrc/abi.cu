@@ -76,6 +76,9 @@ struct swegl_b200_ctx {
     int sw = 0, sh = 0;
     uint32_t *d_screen = nullptr; float *d_depth = nullptr; uint32_t *d_tmp_color = nullptr;
     uint32_t *color_target = nullptr;   // where finished colour goes instead of d_screen (another context's / GPU's screen)
+    // frame protocol of the band-sharded single frame (FrameSync in common.cuh; swegl_b200_set_frame_sync)
+    int sync_rank = -1, sync_world = 0; uint32_t sync_seq = 0;
+    FrameSync *own_sync() const { return reinterpret_cast<FrameSync *>(d_screen + (size_t)sw * sh); }
     std::vector<void *> imported;       // cudaIpcOpenMemHandle mappings to close
 
     ViewParams last_vp{}; bool have_vp = false; bool last_dof = false;
@@ -538,8 +541,9 @@ int swegl_b200_set_screen(swegl_b200_ctx *ctx, int32_t w, int32_t h)
     CK(cudaStreamSynchronize(ctx->stream));
     drop_graphs(ctx);
     size_t n = (size_t)w * h;
-    CK(dalloc(ctx->d_screen, n)); CK(dalloc(ctx->d_depth, n)); CK(dalloc(ctx->d_tmp_color, n));
-    CK(cudaMemset(ctx->d_screen, 0, n * 4));
+    CK(dalloc(ctx->d_screen, n + SYNC_WORDS)); CK(dalloc(ctx->d_depth, n)); CK(dalloc(ctx->d_tmp_color, n));   // + the FrameSync block
+    CK(cudaMemset(ctx->d_screen, 0, (n + SYNC_WORDS) * 4));
+    ctx->sync_rank = -1;
     CK(cudaMemset(ctx->d_depth, 0x7F, n * 4));
     size_t bins = (size_t)((w + 31) / 32 + 1) * h;
     CK(dalloc(ctx->pools.bin_head, bins));
@@ -690,13 +694,19 @@ static ViewParams draw_params(const ViewParams &vp, bool dof)
 // enqueue one viewport's work on the stream (no synchronisation: usable under stream capture): upload of the staging
 // slot (whole block when the frame data is new, else just the ViewParams), then the kernel sequence.
 static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const ViewParams &vp, swegl_b200_ctx::Slot &sl, bool with_frame,
-                           bool dof, bool count_covered, bool timing, bool sync_counters, Counters *counters_out)
+                           bool dof, bool count_covered, bool timing, bool sync_counters, Counters *counters_out, bool synced = false)
 {
     cudaStream_t st = ctx->stream;
     uint32_t launches = 0;
     if (timing) cudaEventRecord(ctx->ev[0], st);
     if (with_frame) cudaMemcpyAsync(ctx->d_block, sl.block, ctx->block_bytes, cudaMemcpyHostToDevice, st);
     else cudaMemcpyAsync(ctx->d_block + ctx->off_vp, sl.block + ctx->off_vp, sizeof(ViewParams), cudaMemcpyHostToDevice, st);
+    // frame protocol (FrameSync): rank 0 clears the other ranks' rows of its screen and announces the frame; the others
+    // wait for that before their first store into it, skip the background, and raise their flag at the end
+    FrameSync *const own_sync = ctx->own_sync();
+    FrameSync *const tgt_sync = ctx->color_target ? reinterpret_cast<FrameSync *>(ctx->color_target + (size_t)ctx->sw * ctx->sh) : own_sync;
+    const bool skip_bg = synced && ctx->sync_rank > 0 && !dof;
+    if (synced && ctx->sync_rank == 0) { launch_sync_clear(out, ctx->d_vp(), ctx->d_screen, ctx->sw, own_sync, !dof, st); launches++; }
     DeviceScene ds = ctx->ds;
     if (view_culled(ctx, vp)) {                             // sort-first band: skip what cannot reach it (common.cuh)
         ds.cl_live = ctx->cull.cl_live; ds.mark_need = ctx->cull.mark_need; ds.vert_need = ctx->cull.vert_need;
@@ -713,16 +723,27 @@ static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const Vie
     uint32_t *color = dof ? ctx->d_tmp_color - ((size_t)vp.vy * vp.vw + vp.vx) : screen_out;
     const int color_pitch = dof ? vp.vw : ctx->sw;
     // asynchronous frames publish their counters from inside k_fragments; synchronous ones copy them at the end
-    (vp.n_layers > 0 ? launch_fragments_layers : launch_fragments)(ctx->ds, vp, ctx->d_vp(), ctx->d_fp(), ctx->pools, color, color_pitch,
-                                                                    ctx->d_depth, count_covered, sync_counters ? nullptr : counters_out, st);
+    if (synced && ctx->sync_rank > 0 && !dof) { launch_sync_wait_ready(ctx->d_vp(), tgt_sync, own_sync, st); launches++; }
+    if (vp.n_layers > 0)
+        launch_fragments_layers(ctx->ds, vp, ctx->d_vp(), ctx->d_fp(), ctx->pools, color, color_pitch, ctx->d_depth, count_covered,
+                                sync_counters ? nullptr : counters_out, st);
+    else
+        launch_fragments(ctx->ds, vp, ctx->d_vp(), ctx->d_fp(), ctx->pools, color, color_pitch, ctx->d_depth, count_covered,
+                         sync_counters ? nullptr : counters_out, skip_bg, st);
     launches++;
     if (timing) cudaEventRecord(ctx->ev[4], st);
     if (dof) {
+        if (synced && ctx->sync_rank > 0) { launch_sync_wait_ready(ctx->d_vp(), tgt_sync, own_sync, st); launches++; }
         launch_dof(ctx->d_vp(), ctx->pools.bin_used, vp.nbx, ctx->d_tmp_color, vp.vw, ctx->d_depth,
                    screen_out + (size_t)vp.vy * ctx->sw + vp.vx, ctx->sw, vp.vw, vp.vh, out.band0 - vp.vy, out.band1 - vp.vy, st);
         launches++;
     }
     if (timing) cudaEventRecord(ctx->ev[5], st);
+    if (synced) {
+        if (ctx->sync_rank > 0) launch_sync_signal(ctx->d_vp(), tgt_sync, ctx->sync_rank, st);
+        else launch_sync_wait_done(ctx->d_vp(), own_sync, ctx->sync_world, st);
+        launches++;
+    }
     if (sync_counters) cudaMemcpyAsync(counters_out, ctx->pools.counters, sizeof(Counters), cudaMemcpyDeviceToHost, st);
     return launches;
 }
@@ -739,6 +760,7 @@ static int stage_view(swegl_b200_ctx *ctx, const ViewParams &vp, int &si, bool &
     // every rendered view gets a stamp no earlier view had (0 = the initial tile_stamp contents, skipped on wrap-around)
     if (++ctx->stamp == 0) ctx->stamp = 1;
     reinterpret_cast<ViewParams *>(sl.block + ctx->off_vp)->stamp = ctx->stamp;
+    reinterpret_cast<ViewParams *>(sl.block + ctx->off_vp)->sync_seq = ctx->sync_seq;
     return SWEGL_B200_OK;
 }
 
@@ -759,16 +781,26 @@ static int render_async(swegl_b200_ctx *ctx, const ViewParams &out, bool dof)
 {
     cudaStream_t st = ctx->stream;
     const ViewParams vp = draw_params(out, dof);
+    // the frame protocol covers banded, opaque views of the asynchronous path (a synchronous frame may be redone when a
+    // pool overflows, which would break the ranks' lock step)
+    const bool banded = out.band0 > out.vy || out.band1 < out.vy + out.vh;
+    const bool synced = ctx->sync_rank >= 0 && banded && out.n_layers == 0;
+    if (synced) {
+        if (ctx->sync_rank > 0 && !ctx->color_target) return fail(ctx, SWEGL_B200_ERR_STATE, "frame sync: rank > 0 needs a colour target (set_color_target)");
+        if (ctx->sync_rank == 0 && ctx->color_target) return fail(ctx, SWEGL_B200_ERR_STATE, "frame sync: rank 0 assembles the frame in its own screen");
+        ctx->sync_seq++;
+    }
     int si; bool with_frame;
     int rc = stage_view(ctx, vp, si, with_frame);
     if (rc) return rc;
     auto &sl = ctx->slots[si];
     if (!ctx->graphs_enabled) {
-        issue_view(ctx, out, vp, sl, with_frame, dof, false, false, false, sl.counters);
+        issue_view(ctx, out, vp, sl, with_frame, dof, false, false, false, sl.counters, synced);
     } else {
         const uint64_t tgt = (uint64_t)reinterpret_cast<uintptr_t>(ctx->color_target);
         const int32_t key[15] = { out.vx, out.vy, out.vw, out.vh, out.band0, out.band1, out.light_mode, out.tex_mode, (dof ? 1 : 0) | (out.n_layers << 1),
-                                  ctx->sw, ctx->sh, with_frame ? 1 : 0, ctx->dense_spans ? 1 : 0, (int32_t)(tgt & 0xFFFFFFFFu), (int32_t)(tgt >> 32) };
+                                  ctx->sw, ctx->sh, (with_frame ? 1 : 0) | (synced ? 2 + 4 * ctx->sync_rank + 256 * ctx->sync_world : 0), ctx->dense_spans ? 1 : 0,
+                                  (int32_t)(tgt & 0xFFFFFFFFu), (int32_t)(tgt >> 32) };
         swegl_b200_ctx::ViewGraph *vg = nullptr;
         for (auto &g : ctx->view_graphs) if (memcmp(g.key, key, sizeof key) == 0) { vg = &g; break; }
         if (!vg) {
@@ -781,7 +813,7 @@ static int render_async(swegl_b200_ctx *ctx, const ViewParams &out, bool dof)
         if (!vg->exec[si]) {
             cudaGraph_t g = nullptr;
             CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-            issue_view(ctx, out, vp, sl, with_frame, dof, false, false, false, sl.counters);
+            issue_view(ctx, out, vp, sl, with_frame, dof, false, false, false, sl.counters, synced);
             CK(cudaStreamEndCapture(st, &g));
             cudaError_t e = cudaGraphInstantiate(&vg->exec[si], g, 0);
             cudaGraphDestroy(g);
@@ -997,6 +1029,31 @@ int swegl_b200_read_depth(swegl_b200_ctx *ctx, float *zbuffer)
     const ViewParams &vp = ctx->last_vp;
     CK(cudaMemcpyAsync(zbuffer, ctx->d_depth, (size_t)vp.vw * vp.vh * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_set_frame_sync(swegl_b200_ctx *ctx, int rank, int world)
+{
+    if (!ctx || !ctx->d_screen) return fail(ctx, SWEGL_B200_ERR_STATE, "set_frame_sync before set_screen");
+    if (rank >= 0 && (world < 1 || world > SYNC_MAX_RANKS || rank >= world)) return fail(ctx, SWEGL_B200_ERR_ARG, "set_frame_sync: bad rank / world");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    drop_graphs(ctx);
+    CK(cudaMemset(ctx->own_sync(), 0, sizeof(FrameSync)));
+    preload_sync_kernels();
+    ctx->sync_rank = rank < 0 ? -1 : rank; ctx->sync_world = rank < 0 ? 0 : world; ctx->sync_seq = 0;
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_frame_sync_status(swegl_b200_ctx *ctx, uint32_t *timeouts, float *rank0_own_ms)
+{
+    if (!ctx || !ctx->d_screen) return fail(ctx, SWEGL_B200_ERR_ARG, "frame_sync_status: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    FrameSync fs;
+    CK(cudaMemcpy(&fs, ctx->own_sync(), sizeof fs, cudaMemcpyDeviceToHost));
+    if (timeouts) *timeouts = fs.error;
+    if (rank0_own_ms) *rank0_own_ms = fs.t_own_end > fs.t_begin ? (float)((double)(fs.t_own_end - fs.t_begin) * 1e-6) : 0.0f;
     return SWEGL_B200_OK;
 }
 

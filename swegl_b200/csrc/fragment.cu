@@ -165,22 +165,22 @@ struct FragWarp {
 //   3. each non-empty bin is resolved with lane = pixel as described at the top of this file.
 // the part of ViewParams that is fixed for a captured frame graph (rectangle, band), passed by value so that the
 // first loads of the kernel do not wait for the parameter block
-struct FragGeom { int32_t vx, vy, vw, band0, band1, nbx, ntx, n_tiles; };
+struct FragGeom { int32_t vx, vy, vw, band0, band1, nbx, ntx, n_tiles, skip_bg; };   // skip_bg: background colour is not stored (FrameSync)
 
 // clear values (viewport.cpp:88-113) for one row of a tile: colour 0, depth 0x7F7F7F7F
-SB_DEV void clear_tile_row(uint32_t *crow, float *drow, int px_left, int lane)
+SB_DEV void clear_tile_row(uint32_t *crow, float *drow, int px_left, int lane, bool with_color)
 {
     const float maxz = __uint_as_float(MAXZ_BITS);
     const bool aligned = ((reinterpret_cast<uintptr_t>(crow) | reinterpret_cast<uintptr_t>(drow)) & 15) == 0;
     #pragma unroll
     for (int px = lane << 2; px < FRAG_STRETCH * 32; px += 128) {
         if (aligned && px + 4 <= px_left) {
-            *reinterpret_cast<uint4 *>(crow + px) = make_uint4(0, 0, 0, 0);
+            if (with_color) *reinterpret_cast<uint4 *>(crow + px) = make_uint4(0, 0, 0, 0);
             *reinterpret_cast<float4 *>(drow + px) = make_float4(maxz, maxz, maxz, maxz);
         } else {
             #pragma unroll 1
             for (int k = 0; k < 4; k++)
-                if (px + k < px_left) { crow[px + k] = 0; drow[px + k] = maxz; }
+                if (px + k < px_left) { if (with_color) crow[px + k] = 0; drow[px + k] = maxz; }
         }
     }
 }
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
         const int px_left = g.vw - (bx0 << 5);
         for (int r = 0; r < rows_here; r++)
             clear_tile_row(color + (size_t)(g.vy + row0 + r) * color_pitch + g.vx + (bx0 << 5),
-                           depth + (size_t)(row0 + r) * g.vw + (bx0 << 5), px_left, lane);
+                           depth + (size_t)(row0 + r) * g.vw + (bx0 << 5), px_left, lane, !g.skip_bg);
         {   // occupancy map for the DoF pass
             const int r = lane / FRAG_STRETCH, b = lane % FRAG_STRETCH;
             if (r < rows_here && bx0 + b < g.nbx) pl.bin_used[(size_t)(row0 + r) * g.nbx + bx0 + b] = 0;
@@ -272,11 +272,11 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
             const int b = i >> 3, px = (b << 5) + ((i & 7) << 2);
             if ((mask >> b) & 1u) continue;
             if (aligned && px + 4 <= px_left) {
-                *reinterpret_cast<uint4 *>(crow + px) = make_uint4(0, 0, 0, 0);
+                if (!g.skip_bg) *reinterpret_cast<uint4 *>(crow + px) = make_uint4(0, 0, 0, 0);
                 *reinterpret_cast<float4 *>(drow + px) = make_float4(maxz, maxz, maxz, maxz);
             } else {
                 for (int k = 0; k < 4; k++)
-                    if (px + k < px_left) { crow[px + k] = 0; drow[px + k] = maxz; }
+                    if (px + k < px_left) { if (!g.skip_bg) crow[px + k] = 0; drow[px + k] = maxz; }
             }
         }
     }
@@ -738,23 +738,152 @@ __global__ void __launch_bounds__(DOF_THREADS) k_dof(const ViewParams *__restric
 }
 
 // ----------------------------------------------------------------------------------------
+// Frame protocol of the band-sharded single frame (FrameSync, common.cuh): the assembling GPU (rank 0) clears the other
+// ranks' rows of its screen itself -- local HBM writes -- and announces the frame; the other ranks then store only the
+// tiles they drew into (their last kernel's ordinary stores, travelling over NVLink) and raise a flag in rank 0's
+// memory; rank 0's stream ends with a kernel that waits for the flags.  No collective, no host round trip, and the
+// NVLink ingress of rank 0 carries the covered pixels instead of the whole frame.
+// ----------------------------------------------------------------------------------------
+static constexpr long long SYNC_TIMEOUT_CYCLES = 4000000000ll;      // ~2 s (first frames include graph instantiation on the peer): a lost peer must not hang the GPU
+
+SB_DEV uint32_t ld_sys(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+SB_DEV unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+SB_DEV void st_sys(uint32_t *p, uint32_t v) { asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// rank 0, first kernel of the frame: clear the viewport's rows outside the own band, then ready = seq (last CTA done)
+__global__ void __launch_bounds__(256) k_sync_clear(const ViewParams *__restrict__ vpp, uint32_t *__restrict__ screen, int pitch,
+                                                    FrameSync *own, int vx, int vy, int vw, int vh, int band0, int band1, int do_clear)
+{
+    pdl_trigger();
+    if (blockIdx.x == 0 && threadIdx.x == 0) own->t_begin = global_ns();
+    if (do_clear) {
+        const int rows_above = band0 - vy, rows_out = vh - (band1 - band0);
+        const bool vec = ((vx | vw | pitch) & 3) == 0 && (reinterpret_cast<uintptr_t>(screen) & 15) == 0;
+        if (vec) {
+            const int w4 = vw >> 2;
+            const long long n = (long long)rows_out * w4;
+            for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+                const int r = (int)(i / w4), c = (int)(i - (long long)r * w4);
+                const int y = r < rows_above ? vy + r : band1 + (r - rows_above);
+                *reinterpret_cast<uint4 *>(screen + (size_t)y * pitch + vx + 4 * c) = make_uint4(0, 0, 0, 0);
+            }
+        } else {
+            const long long n = (long long)rows_out * vw;
+            for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+                const int r = (int)(i / vw), c = (int)(i - (long long)r * vw);
+                const int y = r < rows_above ? vy + r : band1 + (r - rows_above);
+                screen[(size_t)y * pitch + vx + c] = 0;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&own->clear_ctas, 1u) == gridDim.x - 1) {
+            own->clear_ctas = 0;
+            __threadfence_system();
+            st_sys(&own->ready, vpp->sync_seq);
+        }
+    }
+}
+
+// other ranks, in front of the kernel that stores into rank 0's screen
+// (the dependent kernel is released only after the wait: its CTAs would otherwise sit on the SMs, and when the "ranks"
+// are contexts of ONE device -- the in-process test -- rank 0's clear kernel could not be scheduled under them)
+__global__ void k_sync_wait_ready(const ViewParams *__restrict__ vpp, const FrameSync *peer, FrameSync *own)
+{
+    if (threadIdx.x == 0) {
+        const uint32_t seq = vpp->sync_seq;
+        const long long t0 = clock64();
+        while ((int32_t)(ld_sys(&peer->ready) - seq) < 0)
+            if (clock64() - t0 > SYNC_TIMEOUT_CYCLES) { atomicAdd(&own->error, 1u); break; }
+    }
+    __syncwarp();
+    pdl_trigger();
+    pdl_wait();                                                             // keeps completion transitive along the chain
+}
+
+// other ranks, after their last kernel: everything that kernel stored is ordered before the flag
+__global__ void k_sync_signal(const ViewParams *__restrict__ vpp, FrameSync *peer, int rank)
+{
+    pdl_wait();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        st_sys(&peer->done[rank], vpp->sync_seq);
+    }
+}
+
+// rank 0, last kernel of the frame
+__global__ void k_sync_wait_done(const ViewParams *__restrict__ vpp, FrameSync *own, int world)
+{
+    pdl_wait();
+    const int r = threadIdx.x;
+    if (r == 0) own->t_own_end = global_ns();                               // rank 0's own band is finished here
+    if (r >= 1 && r < world) {
+        const uint32_t seq = vpp->sync_seq;
+        const long long t0 = clock64();
+        while ((int32_t)(ld_sys(&own->done[r]) - seq) < 0)
+            if (clock64() - t0 > SYNC_TIMEOUT_CYCLES) { atomicAdd(&own->error, 1u); break; }
+    }
+    __threadfence_system();
+}
+
+// ----------------------------------------------------------------------------------------
 // launchers
 // ----------------------------------------------------------------------------------------
+// With lazy module loading the first use of a kernel may have to synchronise with the device -- which never happens while
+// another context's wait kernel is spinning for this very launch.  Load the protocol's kernels up front.
+void preload_sync_kernels()
+{
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, k_sync_clear); cudaFuncGetAttributes(&a, k_sync_wait_ready);
+    cudaFuncGetAttributes(&a, k_sync_signal); cudaFuncGetAttributes(&a, k_sync_wait_done);
+}
+void launch_sync_clear(const ViewParams &vp, const ViewParams *d_vp, uint32_t *screen, int pitch, FrameSync *own, bool do_clear, cudaStream_t st)
+{
+    const int grid = do_clear ? 148 * 4 : 1;
+    launch_chain(k_sync_clear, grid, 256, st, false, d_vp, screen, pitch, own, (int)vp.vx, (int)vp.vy, (int)vp.vw, (int)vp.vh, (int)vp.band0, (int)vp.band1,
+                 do_clear ? 1 : 0);
+}
+void launch_sync_wait_ready(const ViewParams *d_vp, const FrameSync *peer, FrameSync *own, cudaStream_t st)
+{
+    launch_chain(k_sync_wait_ready, 1, 32, st, true, d_vp, peer, own);
+}
+void launch_sync_signal(const ViewParams *d_vp, FrameSync *peer, int rank, cudaStream_t st)
+{
+    launch_chain(k_sync_signal, 1, 32, st, true, d_vp, peer, rank);
+}
+void launch_sync_wait_done(const ViewParams *d_vp, FrameSync *own, int world, cudaStream_t st)
+{
+    launch_chain(k_sync_wait_done, 1, 32, st, true, d_vp, own, world);
+}
+
 template <int LIGHT, int TEX>
 static void launch_frag_t(const DeviceScene &s, const ViewParams &vp, const ViewParams *d_vp, const FrameParams *d_fp, const Pools &p,
-                          uint32_t *color, int color_pitch, float *depth, bool count_covered, Counters *h_counters_out, cudaStream_t st)
+                          uint32_t *color, int color_pitch, float *depth, bool count_covered, Counters *h_counters_out, bool skip_bg, cudaStream_t st)
 {
     const int nty = (vp.band1 - vp.band0 + FRAG_ROWS - 1) / FRAG_ROWS, n_tiles = vp.ntx * nty;
     if (n_tiles <= 0) return;
-    const FragGeom g = { vp.vx, vp.vy, vp.vw, vp.band0, vp.band1, vp.nbx, vp.ntx, n_tiles };
+    const FragGeom g = { vp.vx, vp.vy, vp.vw, vp.band0, vp.band1, vp.nbx, vp.ntx, n_tiles, skip_bg ? 1 : 0 };
     const unsigned grid = (unsigned)n_tiles + (unsigned)((n_tiles + FRAG_ROWS - 1) / FRAG_ROWS);
     launch_chain(k_fragments<LIGHT, TEX>, grid, FRAG_TPB, st, true, s, d_vp, d_fp, p, g, color, color_pitch, depth, count_covered ? 1 : 0, h_counters_out);
 }
 
 void launch_fragments(const DeviceScene &s, const ViewParams &vp, const ViewParams *d_vp, const FrameParams *d_fp, const Pools &p,
-                      uint32_t *color, int color_pitch, float *depth, bool count_covered, Counters *h_counters_out, cudaStream_t st)
+                      uint32_t *color, int color_pitch, float *depth, bool count_covered, Counters *h_counters_out, bool skip_bg_color,
+                      cudaStream_t st)
 {
-#define SB_CASE(L, T) if (vp.light_mode == L && vp.tex_mode == T) { launch_frag_t<L, T>(s, vp, d_vp, d_fp, p, color, color_pitch, depth, count_covered, h_counters_out, st); return; }
+#define SB_CASE(L, T) if (vp.light_mode == L && vp.tex_mode == T) { launch_frag_t<L, T>(s, vp, d_vp, d_fp, p, color, color_pitch, depth, count_covered, h_counters_out, skip_bg_color, st); return; }
     SB_CASE(0, 0) SB_CASE(0, 1) SB_CASE(0, 2)
     SB_CASE(1, 0) SB_CASE(1, 1) SB_CASE(1, 2)
     SB_CASE(2, 0) SB_CASE(2, 1) SB_CASE(2, 2)

@@ -148,6 +148,19 @@ class Renderer:
         self._check(self.lib.swegl_b200_read_vertices(self.ctx, vw.ctypes.data, vv.ctypes.data, nw.ctypes.data, yes.ctypes.data))
         return dict(v_world=vw, v_viewport=vv, normal_world=nw, yes=yes)
 
+    def set_frame_sync(self, rank, world=0):
+        """frame protocol of the band-sharded single frame over peer memory (include/swegl_b200.h); rank < 0: off"""
+        self._check(self.lib.swegl_b200_set_frame_sync(self.ctx, int(rank), int(world)))
+
+    def frame_sync_status(self):
+        """-> (timed-out waits of this context, rank 0's own share of the last frame in ms)"""
+        n, ms = C.c_uint32(0), C.c_float(0)
+        self._check(self.lib.swegl_b200_frame_sync_status(self.ctx, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
+    def frame_sync_errors(self):
+        return self.frame_sync_status()[0]
+
     def set_band_culling(self, policy):
         """-1 automatic, 0 off, 1 on for every banded view; call before upload_scene (include/swegl_b200.h)"""
         self._check(self.lib.swegl_b200_set_band_culling(self.ctx, int(policy)))

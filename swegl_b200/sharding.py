@@ -44,6 +44,30 @@ def balanced_bands(row_cost, world, min_rows=8):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+def rebalance_bands(bands, times, min_rows=8, damping=1.0):
+    """Feedback step of the band balance: `bands` = the contiguous [(y0, y1)] the ranks just rendered, `times` = what each
+    took (any unit).  Every band's cost is taken as uniform over its rows (time / rows); the new cuts split that
+    piecewise-constant cost profile into equal shares.  Unlike the coverage model this sees everything a rank really
+    pays: triangle-dense rows (the poles of a sphere), the halo of the DoF pass, rank 0's extra duty as the assembling
+    GPU.  `damping` < 1 moves only part of the way (for noisy timings).  Same result on every rank."""
+    world = len(bands)
+    if world <= 1:
+        return list(bands)
+    height = bands[-1][1]
+    cost = []
+    for (y0, y1), t in zip(bands, times):
+        cost += [max(float(t), 1e-9) / max(1, y1 - y0)] * (y1 - y0)
+    new = balanced_bands(cost, world, min_rows)
+    if damping >= 1.0:
+        return new
+    cuts = [0]
+    for k in range(1, world):
+        c = int(round(bands[k][0] + damping * (new[k][0] - bands[k][0])))
+        cuts.append(min(max(c, cuts[-1] + min_rows), height - (world - k) * min_rows))
+    cuts.append(height)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 def interleaved_bands(height, world, rank, band=64):
     """list of [y0, y1) bands for interleaved assignment (load balance for centred objects)."""
     out = []
@@ -99,6 +123,21 @@ def share_screen(renderer, dist, dst=0, device=None):
     ptr = renderer.import_screen(bytes(h.cpu().tolist()))
     renderer.set_color_target(ptr)
     return ptr
+
+
+def arm_frame_sync(renderer, dist, dst=0):
+    """Switch the frame protocol on (after share_screen): from now on a banded view submitted with
+    render_device(..., stats=False) is complete in dst's screen when dst's stream has run past it -- flags over peer
+    memory instead of a collective (include/swegl_b200.h: swegl_b200_set_frame_sync).  dst's flags are reset first."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if dst != 0:
+        raise ValueError("the frame protocol assembles on rank 0")
+    if rank == dst:
+        renderer.set_frame_sync(0, world)
+    dist.barrier()
+    if rank != dst:
+        renderer.set_frame_sync(rank, world)
+    dist.barrier()
 
 
 def frame_barrier(dist, token):

@@ -426,3 +426,42 @@ def test_frame_pipeline_renders_the_same_frames(renderer):
                 want, slots = [], []
     finally:
         pipe.close()
+
+
+@pytest.mark.parametrize("name", ["sphere100_1080", "truck_1080", "truck_4k_dof"])
+def test_frame_sync_protocol_two_contexts(name):
+    """the multi-GPU frame protocol (swegl_b200_set_frame_sync) exercised inside one process: context A is "rank 0" and
+    assembles the frame, context B is "rank 1", renders the lower band with A's screen as its colour target and skips
+    the background.  Flags over (here: same-device) memory only; the camera moves, so stale tiles must disappear."""
+    from swegl_b200 import Renderer
+    scene, vps, screen, cfg = configs.build(name)
+    vp = vps[0]
+    a, b, ref = Renderer(0), Renderer(0), Renderer(0)
+    try:
+        for r in (a, b, ref):
+            r.set_band_culling(1)
+            r.upload_scene(scene); r.set_screen(*screen)
+        cut = int(vp.h * 0.45)
+        for r, band in ((a, (0, cut)), (b, (cut, vp.h))):       # size the pools with ordinary frames first
+            vp.band = band
+            r.begin_frame(scene); r.render_device(vp, stats=True)
+        vp.band = (0, 0)
+        b.set_color_target(a.device_buffers()[0])
+        a.set_frame_sync(0, 2); b.set_frame_sync(1, 2)
+        for step in range(4):
+            vp.camera.apply([("rotate_y", 0.2), ("translate", 0.15, 0.05, 0)])
+            want = np.zeros((screen[1], screen[0]), np.uint32)
+            ref.begin_frame(scene); ref.render(vp, want)
+            first, second = ((b, (cut, vp.h)), (a, (0, cut))) if step % 2 else ((a, (0, cut)), (b, (cut, vp.h)))
+            for r, band in (first, second):                     # either submission order works
+                vp.band = band
+                r.begin_frame(scene); r.render_device(vp, stats=False)
+            vp.band = (0, 0)
+            a.synchronize()                                      # rank 0's stream passing the view = frame complete
+            got = a.read_screen()
+            b.synchronize()
+            assert a.frame_sync_errors() == 0 and b.frame_sync_errors() == 0
+            assert (got == want).all(), f"{name}: step {step}"
+    finally:
+        for r in (a, b, ref):
+            r.close()

@@ -111,3 +111,25 @@ def test_two_rank_band_render_and_gather(tmp_path, oracle):
     full = oracle.render(scene, vps[0], screen_wh=screen)
     got = np.load(out)
     assert (got == full["pixels"]).all()
+
+
+def test_rebalance_bands_equalises_cost():
+    """rebalance_bands: bands whose rows cost different amounts converge to equal per-band time in a few steps"""
+    from swegl_b200 import sharding
+    height, world = 4320, 8
+    # true cost per row: triangle-dense poles + coverage hump in the middle
+    row_cost = [3.0 if (y < 300 or y > 4020) else 1.0 + 2.0 * (1 - abs(y - 2160) / 2160.0) for y in range(height)]
+    bands = [sharding.band_rows(height, world, r) for r in range(world)]
+    def times(b):
+        return [sum(row_cost[y0:y1]) for y0, y1 in b]
+    t0 = times(bands)
+    for _ in range(4):
+        bands = sharding.rebalance_bands(bands, times(bands))
+        assert bands[0][0] == 0 and bands[-1][1] == height and all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+        assert all(y1 - y0 >= 8 for y0, y1 in bands)
+    t = times(bands)
+    assert max(t) / (sum(t) / world) < 1.03 < max(t0) / (sum(t0) / world)
+    # damping moves part of the way; world 1 is the identity
+    half = sharding.rebalance_bands([sharding.band_rows(height, world, r) for r in range(world)], t0, damping=0.5)
+    assert half[0][0] == 0 and half[-1][1] == height
+    assert sharding.rebalance_bands([(0, height)], [1.0]) == [(0, height)]
