@@ -386,6 +386,8 @@ def sharded_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
         ms = []
         for _ in range(steps):
             flush.zero_()
+            if world > 1:
+                dist.all_reduce(start_token)            # stream-ordered, no host wait: the ranks' frames start together on the GPUs
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             one()
@@ -397,6 +399,7 @@ def sharded_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+    start_token = torch.zeros(1, device="cuda")
     ms_gather = timed()                                 # bands sent to rank 0 after rendering (NCCL send/recv)
     ms_peer, peer_ok, ms_sync, sync_ok, sync_info = None, None, None, None, None
     if world > 1:
@@ -459,11 +462,11 @@ def sharded_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
             ms = []
             for _ in range(steps):
                 flush.zero_()
+                dist.all_reduce(start_token)            # stream-ordered, outside the events: the ranks' frames start together
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(); nonlocal_one(); e1.record()
                 r.synchronize(); torch.cuda.synchronize()
                 ms.append(e0.elapsed_time(e1))
-                dist.barrier()                          # host-side, outside the events: frames start together
             t = torch.tensor([sum(ms) / len(ms)], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t.item())
