@@ -328,6 +328,78 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
 
 
+def multiview_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
+    """config 4: ONE split-screen frame, one viewport_t per GPU (viewport v -> rank v mod world, SURVEY §8e / renderer.hpp:
+    20-34), scene replicated.  Output on rank 0 either by an NCCL rectangle gather after rendering or by peer-memory
+    stores of the producing kernels (share_screen) + a one-element all-reduce.  Returns ms per frame, max over ranks."""
+    from swegl_b200 import configs, sharding
+    scene, vps, screen, cfg = configs.build(name)
+    r.upload_scene(scene)
+    r.set_screen(*screen)
+    nodes = scene.node_matrices()
+    mine = sharding.viewports_for_rank(len(vps), world, rank)
+    descs = [vps[v].desc() for v in mine]
+    rects = [(vp.x, vp.y, vp.w, vp.h) for vp in vps]
+    screen_ptr, _ = r.device_buffers()
+    full = torch.as_tensor(_DevArray(screen_ptr, (screen[1], screen[0])), device="cuda")
+    token = torch.zeros(1, device="cuda")
+    start_token = torch.zeros(1, device="cuda")
+    state = {"peer": False}
+
+    def one():
+        r.begin_frame(scene, nodes)
+        for d in descs:
+            r.render_device(d, stats=False)
+        if world > 1:
+            if state["peer"]:
+                sharding.frame_barrier(dist, token)
+            else:
+                sharding.gather_rects_inplace(full, rects, dist, dst=0)
+    r.begin_frame(scene, nodes)
+    for v in mine:
+        r.render_device(vps[v], stats=True)             # sizes the pools
+
+    def timed():
+        for _ in range(max(warmup, 3)):
+            one()
+        r.synchronize(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = []
+        for _ in range(steps):
+            flush.zero_()
+            if world > 1:
+                dist.all_reduce(start_token)            # stream-ordered, outside the events: the ranks start together
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); one(); e1.record()
+            r.synchronize(); torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        t = torch.tensor([sum(ms) / len(ms)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    ms_gather = timed()
+    ms_peer, peer_ok = None, None
+    if world > 1:
+        checksum = int(full.to(torch.int64).sum().item()) if rank == 0 else 0
+        sharding.share_screen(r, dist, dst=0, device="cuda")
+        state["peer"] = True
+        if rank == 0:
+            full.zero_()
+        ms_peer = timed()
+        if rank == 0:
+            peer_ok = int(full.to(torch.int64).sum().item()) == checksum
+        r.set_color_target(None)
+        dist.barrier()
+    best = min(m for m in (ms_gather, ms_peer) if m is not None)
+    return {"workload": name, "description": cfg["desc"], "ms_per_frame": best, "fps": 1e3 / best,
+            "ms_per_frame_nccl_rect_gather": ms_gather if world > 1 else None, "ms_per_frame_peer_write": ms_peer,
+            "peer_write_frame_matches_gather": peer_ok, "n_gpus": world, "active_gpus": min(world, len(vps)),
+            "viewports_per_rank": [len(sharding.viewports_for_rank(len(vps), world, k)) for k in range(world)],
+            "partition": "one viewport_t per GPU (viewport v on rank v mod N), scene replicated" if world > 1 else "single GPU, 4 viewports one after the other",
+            "scaling": "strong"}
+
+
 def sharded_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
     """sort-first: ONE frame split in row bands over the ranks (scene replicated), bands gathered to rank 0 with
     NCCL over NVLink.  Strong scaling of a single frame; returns ms per frame (max over ranks)."""
@@ -511,6 +583,7 @@ def main():
     ap.add_argument("--no-also", action="store_true")
     ap.add_argument("--pipeline-depth", type=int, default=4,
                     help="contexts per GPU that render the independent frames of `value` round robin (1 = one frame at a time)")
+    ap.add_argument("--multiview", default="multiview_4k", help="workload of the viewport-per-GPU split-screen measurement (config 4; '' = skip)")
     ap.add_argument("--sharded", default="sphere1000_8k", help="workload of the band-sharded single-frame measurement ('' = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -568,6 +641,13 @@ def main():
     sharded = None
     if args.sharded and not args.no_also:
         sharded = sharded_frame(r, torch, dist, args.sharded, min(args.steps, 10), args.warmup, flush, world, rank)
+    multiview = None
+    if args.multiview and not args.no_also:
+        rm = Renderer(local_rank, stream=stream.cuda_stream)      # its own context: own screen, own peer mappings
+        try:
+            multiview = multiview_frame(rm, torch, dist, args.multiview, min(args.steps, 20), args.warmup, flush, world, rank)
+        finally:
+            rm.close()
 
     if rank != 0:
         if world > 1:
@@ -637,6 +717,8 @@ def main():
         line["also"] = also
     if sharded:
         line["sharded_frame"] = sharded
+    if multiview:
+        line["multiview_frame"] = multiview
     json_out.write(json.dumps(line) + "\n")
     json_out.flush()
     if world > 1:

@@ -135,6 +135,12 @@ CONFIGS = {
                                   dict(rect=(0, 540, 960, 540), pose=[("translate", 0, 4, -4), ("rotate_x", -0.7)], layers=0),
                                   dict(rect=(960, 540, 960, 540), pose=[("translate", 3, 1, -3), ("rotate_y", -0.7), ("rotate_x", -0.1)], layers=0)],
                            desc="config 4: 2x2 split screen, 4 cameras (CesiumMilkTruck substituted for the missing BarramundiFish.glb)"),
+    "multiview_4k": dict(scene="CesiumMilkTruck", screen=(3840, 2160), lights="test1+points",
+                         views=[dict(rect=(0, 0, 1920, 1080), pose=POSE_TEST1, layers=0),
+                                dict(rect=(1920, 0, 1920, 1080), pose=[("translate", -1, 2, -5), ("rotate_y", 0.2), ("rotate_x", -0.3)], layers=0),
+                                dict(rect=(0, 1080, 1920, 1080), pose=[("translate", 0, 4, -4), ("rotate_x", -0.7)], layers=0),
+                                dict(rect=(1920, 1080, 1920, 1080), pose=[("translate", 3, 1, -3), ("rotate_y", -0.7), ("rotate_x", -0.1)], layers=0)],
+                         desc="config 4 at 4K: 2x2 split screen of 1920x1080 viewports, 4 cameras, sun + 2 point lights (CesiumMilkTruck substituted for the missing BarramundiFish.glb)"),
     "layers_640": dict(scene="procedural", alpha=100, screen=(640, 480), lights="procedural",
                        views=[dict(rect=(0, 0, 640, 480), pose=POSE_LAYERS, layers=3)],
                        desc="SURVEY 8f N1: procedural scene (strips, fans, scaled node), three stacked alpha-100 triangles, 3 transparency layers"),

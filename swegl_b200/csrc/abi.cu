@@ -80,6 +80,7 @@ struct swegl_b200_ctx {
     int sync_rank = -1, sync_world = 0; uint32_t sync_seq = 0;
     FrameSync *own_sync() const { return reinterpret_cast<FrameSync *>(d_screen + (size_t)sw * sh); }
     std::vector<void *> imported;       // cudaIpcOpenMemHandle mappings to close
+    std::vector<cudaIpcMemHandle_t> imported_handles;   // the handle of each mapping (a handle is opened once per context)
 
     ViewParams last_vp{}; bool have_vp = false; bool last_dof = false;
     ViewParams dof_cache{}; float dof_cache_depth = 0.f; bool dof_cache_valid = false;   // DoF thresholds per focal_depth
@@ -996,9 +997,12 @@ int swegl_b200_import_screen(swegl_b200_ctx *ctx, const void *handle64, void **p
     CK(cudaSetDevice(ctx->device));
     cudaIpcMemHandle_t h;
     memcpy(&h, handle64, sizeof h);
+    for (size_t i = 0; i < ctx->imported.size(); i++)
+        if (!memcmp(&ctx->imported_handles[i], &h, sizeof h)) { *peer_screen = ctx->imported[i]; return SWEGL_B200_OK; }
     void *p = nullptr;
     CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     ctx->imported.push_back(p);
+    ctx->imported_handles.push_back(h);
     *peer_screen = p;
     return SWEGL_B200_OK;
 }

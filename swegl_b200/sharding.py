@@ -1,7 +1,8 @@
 """Sort-first multi-GPU partitioning: scene replicated on every rank, each rank renders a band of
 rows of the FULL viewport (a scissor, not a smaller viewport: a sub-viewport would change the projection,
 viewport.cpp:30-35), finished bands are gathered to rank 0 for single-frame output.  Batches of independent
-frames need no collective at all (frame i -> rank i mod world).
+frames need no collective at all (frame i -> rank i mod world).  A multi-viewport frame (config 4) can also be split
+one viewport_t per rank (viewports_for_rank / gather_rects_inplace).
 
 Pure host logic over torch.distributed: works with CUDA tensors over NCCL (NVLink) and with CPU tensors over
 gloo (tests/test_sharding_gloo.py).
@@ -80,6 +81,41 @@ def interleaved_bands(height, world, rank, band=64):
 def frames_for_rank(n_frames, world, rank):
     """frame-parallel batches: frame i -> rank i mod world, no collective."""
     return list(range(rank, n_frames, world))
+
+
+def viewports_for_rank(n_views, world, rank):
+    """config 4 (SURVEY §8e, renderer.hpp:20-34): one viewport_t per GPU.  swegl::render(scene, vp1, vp2, ...) runs
+    original_to_world once and then every viewport independently, so viewport v -> rank v mod world needs no exchange
+    before the output; ranks beyond the viewport count idle."""
+    return list(range(rank, n_views, world))
+
+
+def gather_rects_inplace(frame, rects, dist, dst=0):
+    """Output step of the viewport partition: `frame` is every rank's full (H, W) screen tensor, rank
+    v mod world has rendered rectangle rects[v] = (x, y, w, h) of it.  On return rank `dst` holds every
+    rectangle.  A rectangle is a strided block, so it travels through one contiguous staging tensor per side
+    (send/recv pairs batched in one group).  Peer-memory output (share_screen) needs none of this: the rectangles are
+    stored into dst's screen by the kernels that produce them."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if world == 1:
+        return frame
+    ops, landing = [], []
+    for v, (x, y, w, h) in enumerate(rects):
+        owner = v % world
+        if owner == dst:
+            continue
+        if rank == dst:
+            buf = frame.new_empty((h, w))
+            landing.append((buf, (x, y, w, h)))
+            ops.append(dist.P2POp(dist.irecv, buf, owner, tag=v))
+        elif rank == owner:
+            ops.append(dist.P2POp(dist.isend, frame[y:y + h, x:x + w].contiguous(), dst, tag=v))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for buf, (x, y, w, h) in landing:
+        frame[y:y + h, x:x + w] = buf
+    return frame if rank == dst else None
 
 
 def gather_bands_inplace(frame, height, dist, dst=0, bands=None):

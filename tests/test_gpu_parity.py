@@ -238,6 +238,33 @@ def test_color_target_assembles_bands_in_another_screen(renderer, name):
         vp.band = (0, 0)
 
 
+@pytest.mark.parametrize("name", ["multiview_1080", "multiview_4k"])
+def test_viewport_per_context_assembles_split_screen(renderer, oracle, name):
+    """config 4 on one GPU the way 2 GPUs run it (sharding.viewports_for_rank): context A renders viewports 0 and 2 into
+    its own screen, context B renders 1 and 3 straight into A's screen (set_color_target = the CUDA IPC mapping of a
+    peer).  The assembled split screen equals the one-context frame bit for bit and the oracle within 1 LSB."""
+    from swegl_b200 import Renderer, sharding
+    scene, vps, screen, cfg = configs.build(name)
+    want, _, _ = render_gpu(renderer, scene, vps, screen, want_z=False)
+    a, b = Renderer(0), Renderer(0)
+    for r in (a, b):
+        r.upload_scene(scene); r.set_screen(*screen); r.begin_frame(scene)
+    screen_a, _ = a.device_buffers()
+    b.set_color_target(screen_a)
+    for rank, r in enumerate((a, b)):
+        for v in sharding.viewports_for_rank(len(vps), 2, rank):
+            r.render_device(vps[v], stats=True)
+    a.synchronize(); b.synchronize()
+    got = a.read_screen()
+    assert (got == want).all()
+    if name == "multiview_1080":
+        opx = np.zeros_like(got)
+        for vp in vps:
+            oracle.render(scene, vp, screen_wh=screen, pixels=opx)
+        assert channel_diff(got, opx).max() <= 1
+        assert ((got >> 24) == (opx >> 24)).all()
+
+
 def test_band_scissor_equals_full_frame(renderer, oracle):
     """sort-first row bands: rendering [0,h) as 3 uneven bands gives the full frame"""
     scene, vps, screen, cfg = configs.build("truck_1080")

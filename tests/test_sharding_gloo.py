@@ -133,3 +133,51 @@ def test_rebalance_bands_equalises_cost():
     half = sharding.rebalance_bands([sharding.band_rows(height, world, r) for r in range(world)], t0, damping=0.5)
     assert half[0][0] == 0 and half[-1][1] == height
     assert sharding.rebalance_bands([(0, height)], [1.0]) == [(0, height)]
+
+
+def _viewport_worker(rank, world, port, out_path):
+    """config 4: one viewport_t per rank (viewport v -> rank v mod world), rectangles gathered to rank 0"""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from oracle.binding import Oracle
+    from swegl_b200 import configs, sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    scene, vps, screen, cfg = configs.build("multiview_1080")
+    mine = sharding.viewports_for_rank(len(vps), world, rank)
+    px = np.zeros((screen[1], screen[0]), dtype=np.uint32)
+    o = Oracle()
+    for v in mine:
+        o.render(scene, vps[v], screen_wh=screen, pixels=px)
+    frame = torch.from_numpy(px.view(np.int32))
+    rects = [(vp.x, vp.y, vp.w, vp.h) for vp in vps]
+    got = sharding.gather_rects_inplace(frame, rects, dist, dst=0)
+    if rank == 0:
+        np.save(out_path, got.numpy().view(np.uint32))
+    else:
+        assert got is None
+    dist.destroy_process_group()
+
+
+def test_viewports_for_rank_cover_every_viewport_once():
+    from swegl_b200 import sharding
+    for n in (1, 2, 4, 5):
+        for world in (1, 2, 3, 4, 8):
+            got = sorted(v for r in range(world) for v in sharding.viewports_for_rank(n, world, r))
+            assert got == list(range(n))
+    assert sharding.viewports_for_rank(4, 8, 5) == []           # more GPUs than viewports: the rest idle
+
+
+def test_two_rank_viewport_per_rank_and_rect_gather(tmp_path, oracle):
+    import torch.multiprocessing as mp
+    from swegl_b200 import configs
+    out = str(tmp_path / "frame.npy")
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_viewport_worker, args=(2, port, out), nprocs=2, join=True)
+    scene, vps, screen, cfg = configs.build("multiview_1080")
+    want = np.zeros((screen[1], screen[0]), dtype=np.uint32)
+    for vp in vps:
+        oracle.render(scene, vp, screen_wh=screen, pixels=want)
+    assert (np.load(out) == want).all()
