@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 from . import _abi
-from .scene import Scene, Viewport, f32, identity44, rotate_y, rotate_z, lcg_texture
+from .scene import Scene, Viewport, f32, identity44, rotate_y, rotate_z, lcg_texture, from_quaternion
 
 ASSETS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "assets")
 
@@ -191,3 +191,122 @@ def with_transparency(scene, alpha, tex_alpha=False):
         scene.mat_bgra[0, 3] = 200                  # the textured material itself is not what decides: the texel is
     scene.set_lights(0.2, (1.0, -1.0, -1.0), 0.3, POINT_LIGHTS)
     return scene
+
+
+# ---- seeded random scenes for the parity fuzz tests (tests/test_fuzz_*.py) ----
+POSE_FUZZ = [("translate", 0.3, 0.2, -4.0), ("rotate_y", 0.15), ("rotate_x", -0.1)]
+
+
+def fuzz_scene(seed, n_prims=7, verts_per_prim=36, transparent=False):
+    """A triangle soup that pokes at the branches of the reference's frame a well-behaved model never takes: all
+    three index modes with random (repeated -> degenerate) indices, vertices behind the camera and across the near
+    plane (renderer.cpp:281-356: 1 or 2 vertices clipped), collinear and sub-pixel triangles, screen-filling ones,
+    vertices snapped to a grid (exactly shared edges, exactly equal depths: the z-test tie goes to the earlier draw,
+    renderer.cpp:491), coplanar duplicates under another material, a node chain with non-uniform and mirrored scales
+    (facing flips), unnormalised normals, non-power-of-two textures, 0..3 point lights.  Stays inside the reference's
+    defined behaviour: materials >= 0, texture coordinates well above 0, no exact-zero depths."""
+    rng = np.random.default_rng(seed)
+    u = lambda lo, hi, *shape: rng.uniform(lo, hi, size=shape).astype(np.float32)
+    s = Scene()
+    s.name = f"fuzz{seed}"
+    # nodes: 0 root (identity), 1 child of 0, 2 child of 1 (mirrored), 3 another root
+    nn = 4
+    s.node_parent = np.array([-1, 0, 1, -1], np.int32)
+    s.node_scale = np.ones((nn, 3), np.float32)
+    s.node_rotation = np.stack([identity44() for _ in range(nn)]).astype(np.float32)
+    s.node_translation = np.zeros((nn, 3), np.float32)
+    for i in (1, 2, 3):
+        q = rng.normal(size=4).astype(np.float32)
+        q = (q / np.float32(np.sqrt(np.float32((q * q).sum())))).astype(np.float32)
+        s.node_rotation[i] = from_quaternion(*q)
+        s.node_scale[i] = u(0.5, 1.6, 3)
+        s.node_translation[i] = u(-0.8, 0.8, 3)
+    s.node_scale[2, int(rng.integers(0, 3))] *= np.float32(-1.0)                  # mirrored: winding flips
+    # textures + materials
+    sizes = [(64, 64), (37, 53), (16, 128), (5, 3)]
+    for (tw, th) in sizes:
+        t = rng.integers(0, 1 << 24, size=(th, tw), dtype=np.uint32)
+        a = rng.integers(40, 256, size=(th, tw), dtype=np.uint32) if transparent else np.full((th, tw), 255, np.uint32)
+        s.textures.append((t | (a << 24)).astype(np.uint32))
+    nm = 6
+    s.mat_bgra = rng.integers(0, 256, size=(nm, 4), dtype=np.uint8)
+    s.mat_bgra[:, 3] = rng.integers(60, 256, size=nm, dtype=np.uint8) if transparent else 255
+    s.mat_metal_rough = np.ones((nm, 2), np.float32)
+    s.mat_tex_ds = np.stack([np.array([0, 1, 2, 3, -1, -1], np.int32), rng.integers(0, 2, size=nm).astype(np.int32)], axis=1)
+    pos, nrm, uv, idx = [], [], [], []
+    pn, pm, pmat, pfv, pnv, pfi, pni = [], [], [], [], [], [], []
+    modes = [_abi.MODE_TRIANGLES, _abi.MODE_TRIANGLE_STRIP, _abi.MODE_TRIANGLE_FAN]
+    prim_nodes = sorted(int(k) for k in rng.integers(0, nn, size=n_prims))      # the reference draws node by node (renderer.cpp:86-97)
+    for p in range(n_prims):
+        nv = verts_per_prim
+        v = np.empty((nv, 3), np.float32)
+        v[:, 0] = u(-2.5, 2.5, nv); v[:, 1] = u(-2.0, 2.0, nv)
+        v[:, 2] = u(-6.5, 3.0, nv)                                                # camera at z = -4: some behind it, some across the near plane
+        snap = rng.random(nv) < 0.35
+        v[snap] = (np.round(v[snap] * 2.0) / 2.0).astype(np.float32)              # grid: shared positions, equal depths
+        kind = p % 5
+        if kind == 1:                                                             # a few very large triangles
+            v[:6] *= np.float32(6.0)
+        elif kind == 2:                                                           # a cloud of sub-pixel triangles
+            c = u(-1, 1, 3)
+            v[: nv // 2] = c + u(-0.004, 0.004, nv // 2, 3)
+        elif kind == 3:                                                           # collinear triples
+            d = u(-1, 1, 3)
+            for k in range(0, 9, 3):
+                v[k + 1] = v[k] + d; v[k + 2] = v[k] + np.float32(2.0) * d
+        n = u(-1, 1, nv, 3)
+        n[rng.random(nv) < 0.5] *= np.float32(3.0)                                # not unit length (stored as is, gltf.cpp:192-194)
+        t = u(1.5, 4.0, nv, 2)                                                    # >= 1.5: slivers extrapolate a little, and a negative texel index is UB in the reference
+        mode = modes[p % 3]
+        ni = int(rng.integers(12, 3 * nv)) if mode == _abi.MODE_TRIANGLES else int(rng.integers(5, nv))
+        if mode == _abi.MODE_TRIANGLES:
+            ni -= ni % 3
+        ix = rng.integers(0, nv, size=ni).astype(np.uint32)                       # repeats -> degenerate triangles
+        pfv.append(sum(pnv)); pnv.append(nv); pfi.append(sum(pni)); pni.append(ni)
+        pn.append(prim_nodes[p]); pm.append(mode); pmat.append(int(rng.integers(0, nm)))
+        pos.append(v); nrm.append(n); uv.append(t); idx.append(ix)
+    # coplanar duplicate of the last primitive under another material, drawn after it: every fragment ties in depth
+    pfv.append(sum(pnv)); pnv.append(pnv[-1]); pfi.append(sum(pni)); pni.append(pni[-1])
+    pn.append(pn[-1]); pm.append(pm[-1]); pmat.append((pmat[-1] + 1) % nm)
+    pos.append(pos[-1].copy()); nrm.append(nrm[-1].copy()); uv.append(uv[-1].copy()); idx.append(idx[-1].copy())
+    s.positions = np.concatenate(pos).astype(np.float32)
+    s.normals = np.concatenate(nrm).astype(np.float32)
+    s.texcoords = np.concatenate(uv).astype(np.float32)
+    s.indices = np.concatenate(idx).astype(np.uint32)
+    s.prim_node, s.prim_mode, s.prim_material = (np.array(a, np.int32) for a in (pn, pm, pmat))
+    s.prim_first_vertex, s.prim_n_vertices, s.prim_first_index, s.prim_n_indices = (np.array(a, np.uint32) for a in (pfv, pnv, pfi, pni))
+    nl = int(rng.integers(0, 4))
+    lights = [(float(u(-3, 3)), float(u(-1, 4)), float(u(-4, 2)), float(rng.choice([0.3, 2.0, 40.0, 300.0]))) for _ in range(nl)]
+    s.set_lights(float(u(0.05, 0.5)), (float(u(-1, 1)), float(u(-2, -0.2)), float(u(-1, 1))), float(u(0.2, 0.9)), lights)
+    return s
+
+
+def fuzz_case(seed, screen=(416, 312)):
+    """-> (scene, viewport, screen, pose): shader combination, rectangle, post pass and camera drawn from the seed"""
+    rng = np.random.default_rng(1000 + seed)
+    scene = fuzz_scene(seed)
+    light = int(rng.integers(0, 3)); tex = int(rng.integers(0, 3))
+    if seed % 3 == 0:
+        light, tex = _abi.LIGHT_PHONG, _abi.TEX_BILINEAR
+    x, y = int(rng.integers(0, 24)), int(rng.integers(0, 24))
+    w, h = screen[0] - x - int(rng.integers(0, 24)), screen[1] - y - int(rng.integers(0, 24))
+    post = _abi.POST_DOF if seed % 4 == 1 else _abi.POST_NULL
+    vp = Viewport(x, y, w, h, light_mode=light, tex_mode=tex, transparency_layers=0, post_mode=post,
+                  focal_distance=float(rng.uniform(2, 6)), focal_depth=float(rng.uniform(1.5, 6)))
+    pose = [("translate", float(rng.uniform(-0.8, 0.8)), float(rng.uniform(-0.5, 0.5)), float(rng.uniform(-5.0, -2.5))),
+            ("rotate_y", float(rng.uniform(-0.5, 0.5))), ("rotate_x", float(rng.uniform(-0.4, 0.4))),
+            ("rotate_z", float(rng.uniform(-0.3, 0.3)))]
+    vp.camera.apply(pose)
+    vp.pose = pose
+    return scene, vp, screen, pose
+
+
+def fuzz_layers_case(seed, screen=(416, 312)):
+    """the transparent flavour of fuzz_case: material and texel alpha random, 1..3 transparency layers, viewport at the
+    screen origin (the reference's flatten ignores the viewport offset, viewport.cpp:61,74)"""
+    _, vp0, _, pose = fuzz_case(seed, screen)
+    scene = fuzz_scene(seed, transparent=True)
+    vp = Viewport(0, 0, screen[0], screen[1], light_mode=vp0.light_mode, tex_mode=vp0.tex_mode, transparency_layers=1 + seed % 3)
+    vp.camera.apply(pose)
+    vp.pose = pose
+    return scene, vp, screen, pose
