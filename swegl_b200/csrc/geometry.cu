@@ -231,11 +231,11 @@ SB_DEV SlotPlan plan_slot(const ViewParams &vp, SV &a, SV &b, SV &c)
     int n = 0;
     if (p.y1 >= vp.vy) {
         int ya = max(max(p.y0, vp.vy), vp.band0), yb = min(min(p.y1, vp.vy + vp.vh), vp.band1);
-        n += max(0, yb - ya);
+        if (yb > ya) n += yb - ya;                          // (not max(0, yb - ya): a limit may be INT_MIN, see f2i)
     }
     if (p.y1 < vp.vy + vp.vh) {
         int ya = max(max(p.y1, vp.vy), vp.band0), yb = min(min(p.y2, vp.vy + vp.vh), vp.band1);
-        n += max(0, yb - ya);
+        if (yb > ya) n += yb - ya;                          // y2 = (int)ceil(+huge) is INT_MIN on x86: the reference's loop does not run
     }
     p.n = n;
     return p;
