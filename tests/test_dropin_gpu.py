@@ -54,3 +54,20 @@ def test_four_viewports_one_call(dropin, oracle):
         oracle.render(scene, vp, screen_wh=screen, pixels=opx)
     d = np.abs(px.view(np.uint8).astype(np.int16) - opx.view(np.uint8).astype(np.int16))
     assert d.max() <= 1
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 5, 8, 60])
+def test_fuzz_scene_through_the_dropin(dropin, oracle, seed):
+    """a seeded triangle soup (configs.fuzz_scene: node chain with mirrored scales, all index modes, near-plane clipping)
+    built in the reference's own scene_t and rendered by swegl::render() with the replacement renderer"""
+    scene, vp, screen, pose = configs.fuzz_case(seed)
+    vp.post_mode = _abi.POST_NULL
+    h = dropin.import_scene(scene)
+    scr = dropin.lib.ref_screen_new(*screen)
+    rv = dropin.make_viewport(scr, vp, pose)
+    px, z = dropin.render(h, rv, scr, screen[0], screen[1], vp.w, vp.h)
+    o = oracle.render(scene, vp, screen_wh=screen)
+    assert (z.view(np.uint32) == o["z"].view(np.uint32)).all()
+    d = np.abs(px.view(np.uint8).astype(np.int16) - o["pixels"].view(np.uint8).astype(np.int16))
+    assert d.max() <= 1
+    dropin.lib.ref_viewport_free(rv); dropin.lib.ref_screen_free(scr); dropin.lib.ref_scene_free(h)

@@ -45,9 +45,64 @@ def main():
             bad.append({"flavour": tag, "seed": seed, "depth_words": dz, "alpha_max": da, "channel_max": dc,
                         "pixels_off_by_more_than_1": int((d.max(axis=2) > 1).sum())})
 
+    rc = Renderer(0)
+    rc.set_band_culling(1)                              # culling on every banded view
+
+    def check_paths(seed, scene, vp, screen):
+        """the other ways into the same frame: culled row bands, the captured-graph path (render_device) and the pipelined
+        read-back (render_async/wait) must give the blocking call's frame bit for bit; then a second frame of the same
+        uploaded scene with moved nodes, other lights (more than the light block was laid out for) against the oracle"""
+        nonlocal n
+        rc.upload_scene(scene); rc.set_screen(*screen); rc.begin_frame(scene)
+        full = np.zeros((screen[1], screen[0]), np.uint32)
+        fz = np.empty((vp.h, vp.w), np.float32)
+        rc.render(vp, full, fz)
+        nb = 2 + seed % 5
+        cuts = sorted({0, vp.h} | {int(vp.h * (k / nb) ** 1.3) for k in range(1, nb)})
+        px = np.zeros_like(full); z = np.empty_like(fz)
+        for b0, b1 in zip(cuts, cuts[1:]):
+            vp.band = (b0, b1)
+            rc.render(vp, px, z)
+        vp.band = (0, 0)
+        if not ((px == full).all() and (z.view(np.uint32) == fz.view(np.uint32)).all()):
+            bad.append({"flavour": "culled_bands", "seed": seed, "bands": nb})
+        rc.begin_frame(scene)
+        rc.render_device(vp, stats=False); rc.synchronize()
+        if not (rc.read_screen() == full).all():
+            bad.append({"flavour": "render_device", "seed": seed})
+        host = [rc.alloc_host((screen[1], screen[0]), np.uint32) for _ in range(2)]
+        for h in host:
+            h[:] = 0
+        tickets = []
+        for k in range(2):
+            rc.begin_frame(scene)
+            tickets.append(rc.render_async(vp.desc(), host[k]))
+        for t in tickets:
+            rc.wait(t)
+        if not ((host[0] == full).all() and (host[1] == full).all()):
+            bad.append({"flavour": "render_async", "seed": seed})
+        # frame 2: the app moved things (scene.animate / key handlers, test_1.cpp:288-303,378)
+        rng = np.random.default_rng(5000 + seed)
+        scene.node_translation = (scene.node_translation + rng.uniform(-0.3, 0.3, scene.node_translation.shape)).astype(np.float32)
+        scene.node_scale = (scene.node_scale * rng.uniform(0.8, 1.2, scene.node_scale.shape)).astype(np.float32)
+        lights = [(float(rng.uniform(-3, 3)), float(rng.uniform(-1, 4)), float(rng.uniform(-4, 2)), float(rng.choice([0.5, 5.0, 80.0])))
+                  for _ in range(int(rng.integers(0, 14)))]
+        scene.set_lights(float(rng.uniform(0.05, 0.4)), (float(rng.uniform(-1, 1)), -1.0, float(rng.uniform(-1, 1))), 0.6, lights)
+        rc.begin_frame(scene)
+        px2 = np.zeros_like(full); z2 = np.empty_like(fz)
+        rc.render(vp, px2, z2)
+        ref = o.render(scene, vp, screen_wh=screen)
+        d = np.abs(px2.view(np.uint8).astype(np.int16) - ref["pixels"].view(np.uint8).astype(np.int16))
+        if (z2.view(np.uint32) != ref["z"].view(np.uint32)).any() or d.max() > 1:
+            bad.append({"flavour": "second_frame_moved_nodes_and_lights", "seed": seed, "channel_max": int(d.max()),
+                        "depth_words": int((z2.view(np.uint32) != ref["z"].view(np.uint32)).sum()), "lights": len(lights)})
+        n += 5
+
     for seed in range(a, b):
         scene, vp, screen, pose = configs.fuzz_case(seed)
         check("small", seed, scene, vp, screen)
+        if seed % 2 == 1:
+            check_paths(seed, *configs.fuzz_case(seed)[:3])
         if seed % 4 == 0:
             scene, vp, screen, pose = configs.fuzz_layers_case(seed)
             check("layers", seed, scene, vp, screen)
