@@ -71,11 +71,14 @@ class FramePipeline:
         self.synchronize()
         torch.cuda.synchronize(self.device)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        import time
         e0.record(main)
         for s in self.streams:
             s.wait_event(e0)
+        t0 = time.perf_counter()
         for _ in range(steps):
             self.submit(scene, descs, nodes)
+        self.host_submit_ms = 1e3 * (time.perf_counter() - t0)      # host side of the same frames (enqueue only)
         for s in self.streams:
             done = torch.cuda.Event()
             done.record(s)

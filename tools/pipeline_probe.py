@@ -25,7 +25,7 @@ def main():
     main_stream = torch.cuda.Stream()
     torch.cuda.set_stream(main_stream)
     scene, vps, screen, cfg = configs.build(args.workload)
-    out = {"workload": args.workload, "steps": args.steps, "fps": {}, "ms_per_frame": {}}
+    out = {"workload": args.workload, "steps": args.steps, "fps": {}, "ms_per_frame": {}, "host_submit_ms_per_frame": {}}
     for depth in [int(x) for x in args.depths.split(",")]:
         pipe = FramePipeline(0, depth)
         pipe.upload_scene(scene)
@@ -33,6 +33,7 @@ def main():
         ms = pipe.measure(scene, vps, args.steps, warmup=3 * depth)
         out["fps"][str(depth)] = round(1e3 * args.steps / ms, 1)
         out["ms_per_frame"][str(depth)] = round(ms / args.steps, 5)
+        out["host_submit_ms_per_frame"][str(depth)] = round(pipe.host_submit_ms / args.steps, 5)
         pipe.close()
     print(json.dumps(out))
 
