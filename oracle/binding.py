@@ -115,6 +115,10 @@ class Ref:
             "ref_scene_export": (None, [vp] + [vp] * 19),
             "ref_scene_export_texture": (None, [vp, C.c_int, vp]),
             "ref_scene_animate": (None, [vp, C.c_float]),
+            "ref_scene_animation_counts": (None, [vp, vp]),
+            "ref_scene_export_animations": (None, [vp] + [vp] * 8),
+            "ref_scene_import_animations": (None, [vp, C.c_uint, vp, C.c_uint, vp, vp, vp, vp, vp, vp, vp]),
+            "ref_scene_node_trs": (None, [vp, vp, vp, vp]),
             "ref_scene_node_matrices": (None, [vp, vp, vp]),
             "ref_scene_vertex_state": (None, [vp, vp, vp, vp, vp]),
             "ref_screen_new": (vp, [C.c_int, C.c_int]),
@@ -183,6 +187,12 @@ class Ref:
             t = np.ascontiguousarray(t, dtype=np.uint32)
             self.lib.ref_scene_add_texture(h, t.ctypes.data, t.shape[1], t.shape[0])
         self.set_lights(h, s)
+        if s.n_animations:
+            a = [np.ascontiguousarray(s.anim_end_time, np.float32), np.ascontiguousarray(s.chan_anim, np.int32),
+                 np.ascontiguousarray(s.chan_node, np.int32), np.ascontiguousarray(s.chan_path, np.int32),
+                 np.ascontiguousarray(s.chan_first_step, np.uint32), np.ascontiguousarray(s.chan_n_steps, np.uint32),
+                 np.ascontiguousarray(s.step_time, np.float32), np.ascontiguousarray(s.step_value, np.float32)]
+            self.lib.ref_scene_import_animations(h, len(a[0]), a[0].ctypes.data, len(a[1]), *[x.ctypes.data for x in a[1:]])
         return h
 
     def set_lights(self, h, s: Scene):
@@ -221,7 +231,25 @@ class Ref:
             tex = np.zeros((int(tex_wh[t, 1]), int(tex_wh[t, 0])), np.uint32)
             self.lib.ref_scene_export_texture(h, t, tex.ctypes.data)
             s.textures.append(tex)
+        ac = np.zeros(3, np.uint32)
+        self.lib.ref_scene_animation_counts(h, ac.ctypes.data)
+        na, nc, ns = (int(v) for v in ac)
+        if na:
+            s.anim_end_time = np.zeros(na, np.float32)
+            s.chan_anim, s.chan_node, s.chan_path = (np.zeros(nc, np.int32) for _ in range(3))
+            s.chan_first_step, s.chan_n_steps = (np.zeros(nc, np.uint32) for _ in range(2))
+            s.step_time, s.step_value = np.zeros(ns, np.float32), np.zeros((ns, 4), np.float32)
+            self.lib.ref_scene_export_animations(h, *[getattr(s, n).ctypes.data for n in Scene.ANIM_ARRAYS])
         return s
+
+    def animate(self, h, seconds):
+        """scene_t::animate(seconds) on the reference scene (model.hpp:146-177)"""
+        self.lib.ref_scene_animate(h, float(seconds))
+
+    def node_trs(self, h, n_nodes):
+        sc, ro, tr = np.zeros((n_nodes, 3), np.float32), np.zeros((n_nodes, 4, 4), np.float32), np.zeros((n_nodes, 3), np.float32)
+        self.lib.ref_scene_node_trs(h, sc.ctypes.data, ro.ctypes.data, tr.ctypes.data)
+        return sc, ro, tr
 
     def procedural_scene(self) -> Scene:
         """test_1.cpp's build_scene() flavour from the reference's own mesh builders (src/data/model.cpp):

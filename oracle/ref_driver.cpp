@@ -293,6 +293,72 @@ void ref_scene_export_texture(void * h, int idx, unsigned int * out_bgra)
 	std::memcpy(out_bgra, mm.m_bitmap, sizeof(unsigned int) * (size_t)mm.m_width * mm.m_height);
 }
 
+// scene_t::animations flattened: counts = animations, channels, steps
+void ref_scene_animation_counts(void * h, unsigned * out3)
+{
+	auto & sc = static_cast<ref_scene *>(h)->scene;
+	unsigned nc = 0, ns = 0;
+	for (auto & a : sc.animations)
+		for (auto & c : a.channels) { nc++; ns += (unsigned)c.steps.size(); }
+	out3[0] = (unsigned)sc.animations.size(); out3[1] = nc; out3[2] = ns;
+}
+
+void ref_scene_export_animations(void * h, float * anim_end_time, int * chan_anim, int * chan_node, int * chan_path,
+                                 unsigned * chan_first_step, unsigned * chan_n_steps, float * step_time, float * step_value4)
+{
+	auto & sc = static_cast<ref_scene *>(h)->scene;
+	unsigned c = 0, st = 0;
+	for (size_t a = 0; a < sc.animations.size(); a++)
+	{
+		anim_end_time[a] = sc.animations[a].end_time;
+		for (auto & ch : sc.animations[a].channels)
+		{
+			chan_anim[c] = (int)a; chan_node[c] = ch.node_idx; chan_path[c] = (int)ch.path;
+			chan_first_step[c] = st; chan_n_steps[c] = (unsigned)ch.steps.size();
+			for (auto & step : ch.steps)
+			{
+				step_time[st] = step.time;
+				step_value4[4 * st] = step.value.x(); step_value4[4 * st + 1] = step.value.y();
+				step_value4[4 * st + 2] = step.value.z(); step_value4[4 * st + 3] = step.value.w();
+				st++;
+			}
+			c++;
+		}
+	}
+}
+
+// the inverse, for scenes built with ref_scene_import (replaces any animations the scene had)
+void ref_scene_import_animations(void * h, unsigned n_anims, const float * anim_end_time, unsigned n_channels, const int * chan_anim,
+                                 const int * chan_node, const int * chan_path, const unsigned * chan_first_step,
+                                 const unsigned * chan_n_steps, const float * step_time, const float * step_value4)
+{
+	auto & sc = static_cast<ref_scene *>(h)->scene;
+	sc.animations.clear();
+	sc.animations.resize(n_anims);
+	for (unsigned a = 0; a < n_anims; a++) sc.animations[a].end_time = anim_end_time[a];
+	for (unsigned c = 0; c < n_channels; c++)
+	{
+		auto & ch = sc.animations[chan_anim[c]].channels.emplace_back(
+			swegl::animation_channel_t{chan_node[c], (swegl::animation_channel_t::path_t)chan_path[c], {}});
+		for (unsigned k = chan_first_step[c]; k < chan_first_step[c] + chan_n_steps[c]; k++)
+			ch.steps.emplace_back(swegl::animation_step_t{step_time[k],
+				swegl::vec4f_t(step_value4[4 * k], step_value4[4 * k + 1], step_value4[4 * k + 2], step_value4[4 * k + 3])});
+	}
+}
+
+// node TRS as scene_t::animate left them (rotation 4x4, scale 3, translation 3 per node)
+void ref_scene_node_trs(void * h, float * node_scale, float * node_rotation, float * node_translation)
+{
+	auto & sc = static_cast<ref_scene *>(h)->scene;
+	for (size_t n = 0; n < sc.nodes.size(); n++)
+	{
+		auto & node = sc.nodes[n];
+		node_scale[3 * n] = node.scale.x(); node_scale[3 * n + 1] = node.scale.y(); node_scale[3 * n + 2] = node.scale.z();
+		for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) node_rotation[16 * n + 4 * r + c] = node.rotation[r][c];
+		node_translation[3 * n] = node.translation.x(); node_translation[3 * n + 1] = node.translation.y(); node_translation[3 * n + 2] = node.translation.z();
+	}
+}
+
 void ref_scene_animate(void * h, float seconds) { static_cast<ref_scene *>(h)->scene.animate(seconds); }
 
 // per-frame node state after render(): original_to_world_matrix (16) and scale(rotation, scale) 3x3 (9)

@@ -193,6 +193,10 @@ class Scene:
               "prim_node", "prim_mode", "prim_material", "prim_first_vertex", "prim_n_vertices",
               "prim_first_index", "prim_n_indices", "positions", "normals", "texcoords", "indices",
               "mat_bgra", "mat_metal_rough", "mat_tex_ds"]
+    # scene_t::animations flattened (model.hpp:88-125); optional in a scene pack (packs made before they existed load empty)
+    ANIM_ARRAYS = ["anim_end_time", "chan_anim", "chan_node", "chan_path", "chan_first_step", "chan_n_steps",
+                   "step_time", "step_value"]
+    PATH_SCALE, PATH_ROTATION, PATH_TRANSLATION, PATH_WEIGHTS = 0, 1, 2, 3     # animation_channel_t::path_t
 
     def __init__(self):
         self.node_scale = np.zeros((0, 3), np.float32)
@@ -209,6 +213,13 @@ class Scene:
         self.mat_bgra = np.zeros((0, 4), np.uint8)
         self.mat_metal_rough = np.zeros((0, 2), np.float32)
         self.mat_tex_ds = np.zeros((0, 2), np.int32)
+        self.anim_end_time = np.zeros(0, np.float32)
+        for n in ["chan_anim", "chan_node", "chan_path"]:
+            setattr(self, n, np.zeros(0, np.int32))
+        for n in ["chan_first_step", "chan_n_steps"]:
+            setattr(self, n, np.zeros(0, np.uint32))
+        self.step_time = np.zeros(0, np.float32)
+        self.step_value = np.zeros((0, 4), np.float32)
         self.textures = []                          # list of (h, w) uint32 BGRA arrays
         self.default_material = (255, 255, 255, 255, 1.0, 1.0, -1, 0)   # material_t defaults, model.hpp:80-87
         # lights: test_1.cpp:334-336 defaults
@@ -252,6 +263,49 @@ class Scene:
         return self
 
     # ---- per-frame host math ----
+    def animate(self, elapsed_seconds):
+        """scene_t::animate (swegl/data/model.hpp:146-177): every channel's two key frames around
+        fmod(elapsed, end_time) are blended linearly in fp32 and written to the node's rotation (quaternion
+        normalised, then matrix44_t::from_quaternion), translation or scale.  The app calls it once per frame
+        (src/test_1.cpp:378); node_matrices() / begin_frame pick the new TRS up."""
+        t_in = f32(elapsed_seconds)
+        for c in range(len(self.chan_node)):
+            end = f32(self.anim_end_time[self.chan_anim[c]])
+            rel = f32(math.fmod(float(t_in), float(end)))                   # fmod is exact: float and double agree
+            s0, n = int(self.chan_first_step[c]), int(self.chan_n_steps[c])
+            times = self.step_time[s0:s0 + n]
+            it = int(np.searchsorted(times, rel, side="left"))              # std::lower_bound on step.time < time
+            if it == n:
+                b = a = s0 + n - 1
+            elif it == 0:
+                b = a = s0
+            else:
+                b, a = s0 + it - 1, s0 + it
+            tb, ta = f32(self.step_time[b]), f32(self.step_time[a])
+            vb, va = self.step_value[b].astype(np.float32), self.step_value[a].astype(np.float32)
+            if ta == tb:
+                frame = vb.copy()
+            else:
+                wb = f32(f32(ta - rel) / f32(ta - tb))
+                wa = f32(f32(rel - tb) / f32(ta - tb))
+                frame = ((vb * wb).astype(np.float32) + (va * wa).astype(np.float32)).astype(np.float32)
+            node, path = int(self.chan_node[c]), int(self.chan_path[c])
+            if path == self.PATH_ROTATION:
+                x, y, z, w = (f32(v) for v in frame)
+                ln = f32(math.sqrt(float(f32(f32(f32(f32(x * x) + f32(y * y)) + f32(z * z)) + f32(w * w)))))   # vec2f.hpp:67-77
+                if ln != 0:
+                    x, y, z, w = f32(x / ln), f32(y / ln), f32(z / ln), f32(w / ln)
+                self.node_rotation[node] = from_quaternion(x, y, z, w)
+            elif path == self.PATH_TRANSLATION:
+                self.node_translation[node] = frame[:3]
+            elif path == self.PATH_SCALE:
+                self.node_scale[node] = frame[:3]
+        return self
+
+    @property
+    def n_animations(self):
+        return len(self.anim_end_time)
+
     def node_matrices(self):
         """original_to_world_matrix (n,4,4) and the 3x3 of scale(rotation, scale) (n,3,3) per node."""
         n = self.n_nodes
@@ -348,7 +402,7 @@ class Scene:
             meta = {"format": "swegl_b200.scenepack.v1", "name": self.name,
                     "default_material": list(self.default_material),
                     "textures": []}
-            for name in self.ARRAYS:
+            for name in self.ARRAYS + (self.ANIM_ARRAYS if self.n_animations else []):
                 buf = io.BytesIO()
                 np.save(buf, getattr(self, name))
                 z.writestr(name + ".npy", buf.getvalue())
@@ -376,6 +430,9 @@ class Scene:
             s.default_material = tuple(meta["default_material"])
             for name in cls.ARRAYS:
                 setattr(s, name, np.load(io.BytesIO(z.read(name + ".npy"))))
+            if "anim_end_time.npy" in z.namelist():
+                for name in cls.ANIM_ARRAYS:
+                    setattr(s, name, np.load(io.BytesIO(z.read(name + ".npy"))))
             for i, entry in enumerate(meta["textures"]):
                 if entry["encoding"] == "raw":
                     t = np.load(io.BytesIO(z.read(f"image_{i}.npy")))
