@@ -247,6 +247,13 @@ int  swegl_b200_set_band_culling(swegl_b200_ctx *ctx, int policy);
  * vertex blocks transformed, 1 if that view was culled at all (else the three counts equal the totals) */
 int  swegl_b200_cull_counts(swegl_b200_ctx *ctx, uint32_t counts[6]);
 
+
+/* Self-test of the device's shared-divisor division (csrc/common.cuh div_by: several quotients by one divisor reuse the
+ * refined reciprocal of div.rn.f32's own expansion) against __fdiv_rn over `n_pairs` generated operand pairs.
+ * out[0] = quotients whose bits differ (must be 0), out[1] = pairs that took the fast path.  No reference counterpart:
+ * it guards the bit-exactness of normalize() (points.hpp:71-90) and of the light sums (pixel_shaders.cpp:173-203). */
+int  swegl_b200_selftest_division(swegl_b200_ctx *ctx, uint64_t n_pairs, uint32_t seed, uint64_t out[2]);
+
 #ifdef __cplusplus
 }
 #endif

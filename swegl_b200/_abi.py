@@ -95,6 +95,7 @@ SYMBOLS = [
     ("swegl_b200_frame_sync_status", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("swegl_b200_set_band_culling", C.c_int, [C.c_void_p, C.c_int]),
     ("swegl_b200_cull_counts", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("swegl_b200_selftest_division", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
 ]
 
 _lib = None

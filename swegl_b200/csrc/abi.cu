@@ -1073,6 +1073,22 @@ int swegl_b200_set_band_culling(swegl_b200_ctx *ctx, int policy)
     return SWEGL_B200_OK;
 }
 
+int swegl_b200_selftest_division(swegl_b200_ctx *ctx, uint64_t n_pairs, uint32_t seed, uint64_t out[2])
+{
+    if (!ctx || !out) return fail(ctx, SWEGL_B200_ERR_ARG, "selftest_division: null argument");
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long *d = nullptr;
+    CK(cudaMalloc(&d, 16));
+    CK(cudaMemsetAsync(d, 0, 16, ctx->stream));
+    launch_selftest_division(n_pairs, seed, d, ctx->stream);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, 16, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    CK(e);
+    return SWEGL_B200_OK;
+}
+
 int swegl_b200_cull_counts(swegl_b200_ctx *ctx, uint32_t counts[6])
 {
     if (!ctx || !counts) return SWEGL_B200_ERR_ARG;

@@ -135,9 +135,10 @@ SB_DEV uint32_t shade(const SpanShade *ss, float flat_light, const Prim &pr, con
         }
     } else {
         light = __fsqrt_rn(__fsqrt_rn(light));                              // light >= 1: 0 <= (255 - c) / light <= 255
-        b = (255u - (trunc_bits_small(fdiv(small_uint_to_float(255u - b), light)) & 0xFF)) & 0xFF;
-        g = (255u - (trunc_bits_small(fdiv(small_uint_to_float(255u - g), light)) & 0xFF)) & 0xFF;
-        r = (255u - (trunc_bits_small(fdiv(small_uint_to_float(255u - r), light)) & 0xFF)) & 0xFF;
+        const SharedDivisor dl = shared_divisor(light);
+        b = (255u - (trunc_bits_small(div_by(small_uint_to_float(255u - b), dl)) & 0xFF)) & 0xFF;
+        g = (255u - (trunc_bits_small(div_by(small_uint_to_float(255u - g), dl)) & 0xFF)) & 0xFF;
+        r = (255u - (trunc_bits_small(div_by(small_uint_to_float(255u - r), dl)) & 0xFF)) & 0xFF;
     }
     return (c & 0xFF000000u) | (r << 16) | (g << 8) | b;
 }
@@ -903,6 +904,47 @@ void launch_fragments_layers(const DeviceScene &s, const ViewParams &vp, const V
 #define SB_LCASE(L, T) if (vp.light_mode == L && vp.tex_mode == T) { launch_frag_layers_t<L, T>(s, vp, d_vp, d_fp, p, color, color_pitch, depth, count_covered, h_counters_out, st); return; }
     SB_LCASE(0, 0) SB_LCASE(0, 1) SB_LCASE(0, 2) SB_LCASE(1, 0) SB_LCASE(1, 1) SB_LCASE(1, 2) SB_LCASE(2, 0) SB_LCASE(2, 1) SB_LCASE(2, 2)
 #undef SB_LCASE
+}
+
+// ----------------------------------------------------------------------------------------
+// self-test of div_by() against __fdiv_rn (swegl_b200_selftest_division): every thread draws operand pairs from a
+// counter-based generator -- raw bit patterns, so every exponent, sign, zero, denormal, infinity and NaN occurs, and a
+// share with the exponents pulled into the range shading uses and with extreme significands -- and counts quotients
+// whose bits differ.
+// ----------------------------------------------------------------------------------------
+SB_DEV uint32_t mix32(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__global__ void k_selftest_division(uint64_t n_pairs, uint32_t seed, unsigned long long *mismatches, unsigned long long *fast_path)
+{
+    unsigned long long bad = 0, fast = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t h0 = mix32((uint32_t)i ^ seed), h1 = mix32(h0 + (uint32_t)(i >> 32) + 0x9e3779b9u), h2 = mix32(h1 ^ 0x85ebca6bu);
+        uint32_t ab = h0, bb = h1;
+        const uint32_t mode = h2 & 7u;
+        if (mode >= 2u) {                                   // exponents 127 +- 40: the fast path's territory
+            ab = (ab & 0x807FFFFFu) | ((87u + (h2 >> 8) % 81u) << 23);
+            bb = (bb & 0x807FFFFFu) | ((87u + (h2 >> 16) % 81u) << 23);
+        }
+        if (mode == 3u) bb |= 0x007FFFFFu;                  // significand of all ones (the hard case of reciprocal-based division)
+        if (mode == 4u) bb &= 0xFF800000u;                  // power of two
+        if (mode == 5u) ab = (ab & 0xFFFFFF00u) | (h2 >> 24 & 1u);   // short significands
+        const float a = __uint_as_float(ab), b = __uint_as_float(bb);
+        const SharedDivisor d = shared_divisor(b);
+        const float q = div_by(a, d), want = __fdiv_rn(a, b);
+        const bool same = __float_as_uint(q) == __float_as_uint(want) || (q != q && want != want);
+        bad += same ? 0u : 1u;
+        const float aa = fabsf(a);
+        fast += (d.ok && aa >= 0x1p-70f && aa <= 0x1p70f) ? 1u : 0u;
+    }
+    for (int o = 16; o; o >>= 1) { bad += __shfl_down_sync(0xFFFFFFFFu, bad, o); fast += __shfl_down_sync(0xFFFFFFFFu, fast, o); }
+    if ((threadIdx.x & 31) == 0) { if (bad) atomicAdd(mismatches, bad); atomicAdd(fast_path, fast); }
+}
+void launch_selftest_division(uint64_t n_pairs, uint32_t seed, unsigned long long *d_out2, cudaStream_t st)
+{
+    k_selftest_division<<<148 * 8, 256, 0, st>>>(n_pairs, seed, d_out2, d_out2 + 1);
 }
 
 void launch_dof(const ViewParams *d_vp, const uint8_t *bin_used, int nbx, const uint32_t *src, int src_pitch, const float *depth,

@@ -170,6 +170,12 @@ class Renderer:
         self._check(self.lib.swegl_b200_cull_counts(self.ctx, c))
         return dict(clusters=c[0], vertex_blocks=c[1], live=c[2], marked=c[3], vertex_blocks_needed=c[4], culled=bool(c[5]))
 
+    def selftest_division(self, n_pairs, seed=1):
+        """-> (quotients that differ from __fdiv_rn, pairs that took the shared-reciprocal fast path)"""
+        out = (C.c_uint64 * 2)()
+        self._check(self.lib.swegl_b200_selftest_division(self.ctx, C.c_uint64(int(n_pairs)), C.c_uint32(int(seed)), out))
+        return int(out[0]), int(out[1])
+
     def device_buffers(self):
         s, d = C.c_void_p(), C.c_void_p()
         self._check(self.lib.swegl_b200_device_buffers(self.ctx, C.byref(s), C.byref(d)))

@@ -492,3 +492,12 @@ def test_frame_sync_protocol_two_contexts(name):
     finally:
         for r in (a, b, ref):
             r.close()
+
+
+def test_shared_divisor_division_is_correctly_rounded(renderer):
+    """div_by() (csrc/common.cuh: quotients by one divisor share the refined reciprocal) == __fdiv_rn, bit for bit, over
+    2^30 generated operand pairs: raw bit patterns (every exponent, zeros, denormals, infinities, NaNs), in-range pairs,
+    all-ones and power-of-two divisors, short numerators"""
+    bad, fast = renderer.selftest_division(1 << 30, seed=20261017)
+    assert bad == 0
+    assert fast > (1 << 29)                             # the fast path really is what was compared
