@@ -572,6 +572,30 @@ def sharded_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
             "bands": state["bands"], "rank0_band_covered_pixels": int(st.n_covered), "scaling": "strong"}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's host threads to the CPUs of its GPU's NUMA node BEFORE any page-locked memory is allocated, so
+    that the pinned frame buffers of the end-to-end path land in the memory next to the GPU's PCIe root (with several
+    ranks on one box the default placement sends most D2H copies across the socket link).  Returns the node or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dev = "/sys/bus/pci/devices/" + bus[-12:].lower()                    # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open(dev + "/numa_node").read())
+        cpus = set()
+        for part in open(dev + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus |= set(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node < 0 or not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -599,6 +623,7 @@ def main():
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — swegl_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner) goes to stderr.
     # The original stdout is kept aside for that line.
@@ -694,6 +719,8 @@ def main():
                                       {"parallelism": "single GPU" if world == 1 else
                                        f"frame-parallel x{world}: scene replicated, frame i on GPU i mod N, no collective",
                                        "frames_in_flight_per_gpu": main_res["depth"],
+                                       "host_numa_binding": (f"rank 0 on node {numa_node}, every rank bound to its GPU's node"
+                                                             if numa_node is not None else "none"),
                                        "l2": (f"value: {main_res['depth']} contexts per GPU render the batch of independent frames round robin; "
                                               "their frame buffers and pools (about 140 MB each at 4K) rotate, so the working set exceeds "
                                               "the 126 MB L2 and no flush is inserted; one_frame_at_a_time: 256 MiB memset between timed "
