@@ -248,6 +248,18 @@ int  swegl_b200_set_band_culling(swegl_b200_ctx *ctx, int policy);
 int  swegl_b200_cull_counts(swegl_b200_ctx *ctx, uint32_t counts[6]);
 
 
+/* Host side, no device involved: decode a PNG or JPEG image as embedded in a .glb into the texel layout
+ * the reference's loader produces with libpng / libjpeg -- row-major uint32, bytes b,g,r,a, alpha 255 where the file has
+ * none (src/misc/image.cpp:93-258: read_png_file, read_jpeg_file; called from src/data/gltf.cpp:77-111).  The texels are
+ * the ones libpng / libjpeg(-turbo) produce, bit for bit (JPEG: islow inverse DCT, fancy upsampling, jdcolor tables),
+ * so a texture decoded here and one decoded by the reference sample identically.  PNG: all colour types and bit depths,
+ * tRNS, no Adam7.  JPEG: baseline / extended / progressive Huffman, 8 bit, 1 or 3 components, sampling 1x1 2x1 2x2,
+ * restart intervals.  *texels_bgra is malloc'ed; release it with swegl_b200_image_free.  Errors: SWEGL_B200_ERR_ARG,
+ * SWEGL_B200_ERR_UNSUPPORTED (malformed or unsupported file; swegl_b200_image_error() says which, per thread). */
+int  swegl_b200_decode_image(const void *data, size_t size, uint32_t **texels_bgra, int32_t *width, int32_t *height);
+void swegl_b200_image_free(uint32_t *texels_bgra);
+const char *swegl_b200_image_error(void);
+
 /* Self-test of the device's shared-divisor division (csrc/common.cuh div_by: several quotients by one divisor reuse the
  * refined reciprocal of div.rn.f32's own expansion) against __fdiv_rn over `n_pairs` generated operand pairs.
  * out[0] = quotients whose bits differ (must be 0), out[1] = pairs that took the fast path.  No reference counterpart:

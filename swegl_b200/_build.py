@@ -5,7 +5,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["abi.cu", "geometry.cu", "fragment.cu"]
+SOURCES = ["abi.cu", "geometry.cu", "fragment.cu", "../host/image_decode.cpp"]   # the last one is host-only C++ (PNG / JPEG decode)
 OUT = os.path.join(HERE, "libswegl_b200.so")
 
 NVCC_FLAGS = [
@@ -15,7 +15,9 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-O2,-ffp-contract=off",
     "-Xptxas", "-v",
     "--shared",
+    "-I", os.path.join(HERE, "..", "include"),
 ]
+LIBS = ["-lz"]                              # zlib inflate for PNG (host/image_decode.cpp)
 
 
 def nvcc_path():
@@ -26,14 +28,15 @@ def needs_build():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "swegl_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "swegl_b200.h"),
+                                                               os.path.join(HERE, "host", "image_decode.cpp")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES] + LIBS
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout)

@@ -437,7 +437,7 @@ class Scene:
                 if entry["encoding"] == "raw":
                     t = np.load(io.BytesIO(z.read(f"image_{i}.npy")))
                 else:
-                    t = decode_image_bgra(z.read(f"image_{i}.bin"))
+                    t = decode_image(z.read(f"image_{i}.bin"))
                 if texel_digest(t) != entry["sha256"]:
                     raise ValueError(f"{path}: image {i} decodes to different texels than when the pack was made "
                                      "(image decoder drift); golden frames would not match")
@@ -445,9 +445,26 @@ class Scene:
         return s
 
 
+def decode_image(data):
+    """PNG/JPEG bytes -> (h, w) uint32 texels with bytes b,g,r,a (alpha 255 when absent): the layout and the values the
+    reference's libpng / libjpeg readers produce (src/misc/image.cpp:93-258), decoded by the package's own C++ decoder
+    (swegl_b200_decode_image, host/image_decode.cpp) -- no imaging library involved."""
+    import ctypes as C
+    lib = _abi.load()
+    ptr, w, h = C.POINTER(C.c_uint32)(), C.c_int32(), C.c_int32()
+    data = bytes(data)
+    rc = lib.swegl_b200_decode_image(data, len(data), C.byref(ptr), C.byref(w), C.byref(h))
+    if rc != _abi.OK:
+        raise ValueError(f"swegl_b200_decode_image: status {rc}: {lib.swegl_b200_image_error().decode()}")
+    try:
+        return np.ctypeslib.as_array(ptr, shape=(h.value, w.value)).copy()
+    finally:
+        lib.swegl_b200_image_free(ptr)
+
+
 def decode_image_bgra(data):
-    """PNG/JPEG bytes -> (h, w) uint32 array with bytes b,g,r,a; rows top-down; alpha 255 when absent
-    (the layout src/misc/image.cpp:93-258 produces)."""
+    """The same through PIL (libpng / libjpeg-turbo): used where the scene packs and the image fixtures are MADE
+    (tools/), and as the cross-check of decode_image in tests/test_image_decode.py."""
     from PIL import Image
     im = Image.open(io.BytesIO(data))
     has_alpha = im.mode in ("RGBA", "LA") or "transparency" in im.info
