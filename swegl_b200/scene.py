@@ -17,6 +17,7 @@ All arithmetic is done on numpy float32 scalars so every operation rounds like t
 import io
 import json
 import math
+import os
 import zipfile
 
 import numpy as np
@@ -419,6 +420,11 @@ class Scene:
                 meta["textures"].append(entry)
             z.writestr("meta.json", json.dumps(meta, indent=1))
 
+    @staticmethod
+    def load_glb(path):
+        """see load_glb() below"""
+        return load_glb(path)
+
     @classmethod
     def load_pack(cls, path):
         s = cls()
@@ -443,6 +449,173 @@ class Scene:
                                      "(image decoder drift); golden frames would not match")
                 s.textures.append(t)
         return s
+
+
+def load_glb(path):
+    """A .glb / .gltf file -> Scene, the way the reference's loader reads it (src/data/gltf.cpp:56-436) -- quirks
+    included, because they shape what gets drawn: indices are read as uint16 whatever their
+    component type (:219), TEXCOORD_0 lands swapped (v in tex_coords.x, u in .y, :205-206), baseColorFactor becomes
+    (uchar)(255 * f) in b,g,r,a order (:130-134), a node's glTF quaternion [x,y,z,w] is passed as
+    from_quaternion(q0..q3) (:234-238), `matrix` nodes are decomposed with row lengths but column division (:279-306),
+    a mesh referenced by several nodes is moved into the first one only (:308-309), skins / morph targets / cameras /
+    samplers / scenes are ignored.  Embedded PNG / JPEG images are decoded by
+    decode_image (the package's own decoder).  Returns the same arrays tools/make_scenepacks.py exports from the
+    reference's own loader (tests/test_load_glb.py compares them bit for bit)."""
+    import struct
+    raw = open(path, "rb").read()
+    root = os.path.dirname(os.path.abspath(path))
+    if raw[:4] == b"glTF":
+        chunks, pos = [], 12
+        total = struct.unpack_from("<I", raw, 8)[0]
+        while pos + 8 <= min(total, len(raw)):
+            ln, _ty = struct.unpack_from("<II", raw, pos)
+            chunks.append((pos + 8, ln))
+            pos += 8 + ln
+        j = json.loads(raw[chunks[0][0]:chunks[0][0] + chunks[0][1]])
+        glb_bin = chunks[1] if len(chunks) > 1 else (0, 0)
+    else:
+        j, glb_bin = json.loads(raw), None
+    buffers = []
+    for jb in j.get("buffers", []):
+        if "uri" in jb:
+            buffers.append(open(os.path.join(root, jb["uri"]), "rb").read()[: jb["byteLength"]])
+        else:
+            buffers.append(raw[glb_bin[0]:glb_bin[0] + jb["byteLength"]])
+    views = []
+    for bv in j.get("bufferViews", []):
+        b = buffers[bv["buffer"]]
+        o = bv.get("byteOffset", 0)
+        views.append((b[o:o + bv["byteLength"]], bv.get("byteStride", 0)))
+    comp_size = {5120: 1, 5121: 1, 5122: 2, 5123: 2, 5125: 4, 5126: 4}
+    n_comp = {"SCALAR": 1, "VEC2": 2, "VEC3": 3, "VEC4": 4, "MAT2": 4, "MAT3": 9, "MAT4": 16}
+
+    def accessor(i):                                    # accessor_t, gltf.cpp:13-51 -> (bytes, stride, count)
+        a = j["accessors"][i]
+        data, stride = views[a["bufferView"]]
+        if stride == 0:
+            stride = comp_size[a["componentType"]] * n_comp[a["type"]]
+        o = a.get("byteOffset", 0)
+        return data[o:o + stride * a["count"]], stride, a["count"]
+
+    def floats(acc, n, first=0):                        # n consecutive floats at byte `first` of every element
+        data, stride, count = acc
+        out = np.zeros((count, n), np.float32)
+        for k in range(n):
+            out[:, k] = np.frombuffer(b"".join(data[i * stride + first + 4 * k: i * stride + first + 4 * k + 4] for i in range(count)), "<f4")
+        return out
+    s = Scene()
+    s.name = os.path.splitext(os.path.basename(path))[0]
+    for im in j.get("images", []):
+        if "uri" in im:
+            s.textures.append(decode_image(open(os.path.join(root, im["uri"]), "rb").read()))
+        else:
+            s.textures.append(decode_image(views[im["bufferView"]][0]))
+    mats = j.get("materials", [])
+    s.mat_bgra = np.full((len(mats), 4), 255, np.uint8)
+    s.mat_metal_rough = np.ones((len(mats), 2), np.float32)
+    s.mat_tex_ds = np.zeros((len(mats), 2), np.int32)
+    s.mat_tex_ds[:, 0] = -1
+    for m, mat in enumerate(mats):
+        pbr = mat.get("pbrMetallicRoughness")
+        if pbr is None:
+            continue                                    # material_t{color, metallic, roughness, img_idx}: double_sided stays false (:124-128)
+        s.mat_tex_ds[m, 1] = 1 if mat.get("doubleSided", False) else 0
+        if "baseColorFactor" in pbr:
+            f = [f32(v) for v in pbr["baseColorFactor"]]
+            s.mat_bgra[m] = [int(f32(f32(255) * f[2])) & 255, int(f32(f32(255) * f[1])) & 255, int(f32(f32(255) * f[0])) & 255,
+                             int(f32(f32(255) * f[3])) & 255]
+        if "baseColorTexture" in pbr:
+            s.mat_tex_ds[m, 0] = j["textures"][pbr["baseColorTexture"]["index"]]["source"]
+        s.mat_metal_rough[m] = [f32(pbr.get("metallicFactor", 1.0)), f32(pbr.get("roughnessFactor", 1.0))]
+    meshes = []                                         # temp_meshes: only meshes that have primitives get a slot (:155-161)
+    for mesh in j.get("meshes", []):
+        if "primitives" not in mesh:
+            continue
+        prims = []
+        for pr in mesh["primitives"]:
+            at = pr["attributes"]
+            pos = floats(accessor(at["POSITION"]), 3)
+            nv = len(pos)                               # (the two spare vertices of :175 are the CPU clipper's scratch space: not part of a Scene)
+            P, N, T = np.zeros((nv, 3), np.float32), np.zeros((nv, 3), np.float32), np.zeros((nv, 2), np.float32)
+            P[:len(pos)] = pos
+            if "NORMAL" in at:
+                nr = floats(accessor(at["NORMAL"]), 3)
+                N[:len(nr)] = nr
+            if "TEXCOORD_0" in at:
+                acc = accessor(at["TEXCOORD_0"])
+                T[:acc[2], 0] = floats(acc, 1, first=4)[:, 0]
+                T[:acc[2], 1] = floats(acc, 1, first=0)[:, 0]
+            idx = np.zeros(0, np.uint32)
+            if "indices" in pr:
+                data, stride, count = accessor(pr["indices"])
+                idx = np.array([struct.unpack_from("<H", data, i * stride)[0] for i in range(count)], np.uint32)
+            prims.append(dict(material=pr.get("material", -1), mode=pr.get("mode", 4), P=P, N=N, T=T, idx=idx))
+        meshes.append(prims)
+    nodes = j.get("nodes", [])
+    n = len(nodes)
+    s.node_scale = np.ones((n, 3), np.float32)
+    s.node_rotation = np.stack([identity44() for _ in range(n)]).astype(np.float32) if n else np.zeros((0, 4, 4), np.float32)
+    s.node_translation = np.zeros((n, 3), np.float32)
+    s.node_parent = np.full(n, -1, np.int32)
+    pn, pm, pmat, pfv, pnv, pfi, pni, Ps, Ns, Ts, Is = [], [], [], [], [], [], [], [], [], [], []
+    for i, nd in enumerate(nodes):
+        if "rotation" in nd:
+            s.node_rotation[i] = from_quaternion(*[f32(v) for v in nd["rotation"]])
+        if "translation" in nd:
+            s.node_translation[i] = [f32(v) for v in nd["translation"]]
+        if "scale" in nd:
+            s.node_scale[i] = [f32(v) for v in nd["scale"]]
+        if "matrix" in nd:
+            m = np.array([f32(v) for v in nd["matrix"]], np.float32).reshape(4, 4).T.copy()     # column-major file, row-major swegl
+            s.node_translation[i] = m[:3, 3]
+            sc = [f32(math.sqrt(float(f32(f32(f32(m[r, 0] * m[r, 0]) + f32(m[r, 1] * m[r, 1])) + f32(m[r, 2] * m[r, 2]))))) for r in range(3)]
+            s.node_scale[i] = sc
+            m[:3, 3] = 0
+            for c in range(3):                          # rows measured, COLUMNS divided (:279-306)
+                if sc[c] != 0:
+                    for r in range(3):
+                        m[r, c] = f32(m[r, c] / sc[c])
+            s.node_rotation[i] = m
+        if "mesh" in nd:
+            for pr in meshes[nd["mesh"]]:
+                pn.append(i); pm.append(pr["mode"]); pmat.append(pr["material"])
+                pfv.append(sum(pnv)); pnv.append(len(pr["P"])); pfi.append(sum(pni)); pni.append(len(pr["idx"]))
+                Ps.append(pr["P"]); Ns.append(pr["N"]); Ts.append(pr["T"]); Is.append(pr["idx"])
+            meshes[nd["mesh"]] = []                     # std::move: the next node naming this mesh gets nothing (:308-309)
+        for ch in nd.get("children", []):
+            s.node_parent[ch] = i
+    s.prim_node, s.prim_mode, s.prim_material = (np.array(a, np.int32) for a in (pn, pm, pmat))
+    s.prim_first_vertex, s.prim_n_vertices, s.prim_first_index, s.prim_n_indices = (np.array(a, np.uint32) for a in (pfv, pnv, pfi, pni))
+    s.positions = np.concatenate(Ps).astype(np.float32) if Ps else np.zeros((0, 3), np.float32)
+    s.normals = np.concatenate(Ns).astype(np.float32) if Ns else np.zeros((0, 3), np.float32)
+    s.texcoords = np.concatenate(Ts).astype(np.float32) if Ts else np.zeros((0, 2), np.float32)
+    s.indices = np.concatenate(Is).astype(np.uint32) if Is else np.zeros(0, np.uint32)
+    # animations, gltf.cpp:331-405
+    ends, ca, cn, cp, cf, cc, st, sv = [], [], [], [], [], [], [], []
+    paths = {"scale": Scene.PATH_SCALE, "rotation": Scene.PATH_ROTATION, "translation": Scene.PATH_TRANSLATION, "weights": Scene.PATH_WEIGHTS}
+    for a, an in enumerate(j.get("animations", [])):
+        end = f32(0)
+        for ch in an["channels"]:
+            smp = an["samplers"][ch["sampler"]]
+            path = paths.get(ch["target"]["path"], 3)
+            times = floats(accessor(smp["input"]), 1)[:, 0]
+            vals = np.zeros((len(times), 4), np.float32)
+            vals[:, 3] = 1
+            width = {Scene.PATH_SCALE: 3, Scene.PATH_ROTATION: 4, Scene.PATH_TRANSLATION: 3}.get(path, 0)
+            if width:
+                vals[:, :width] = floats(accessor(smp["output"]), width)[:len(times)]
+            order = np.argsort(times, kind="stable")
+            times, vals = times[order], vals[order]
+            ca.append(a); cn.append(ch["target"]["node"]); cp.append(path); cf.append(len(st)); cc.append(len(times))
+            st += list(times); sv += list(vals)
+            end = max(end, f32(times[-1]))
+        ends.append(end)
+    if ends:
+        s.anim_end_time = np.array(ends, np.float32)
+        s.chan_anim, s.chan_node, s.chan_path = (np.array(a, np.int32) for a in (ca, cn, cp))
+        s.chan_first_step, s.chan_n_steps = np.array(cf, np.uint32), np.array(cc, np.uint32)
+        s.step_time, s.step_value = np.array(st, np.float32), np.array(sv, np.float32).reshape(-1, 4)
+    return s
 
 
 def decode_image(data):
