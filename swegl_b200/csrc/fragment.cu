@@ -55,10 +55,17 @@ SB_DEV int wrap_index(int a, int n, int mask)
     return r;
 }
 
+// The texture part of a pixel in two steps, so that the four texel loads of the bilinear filter can be in flight while
+// the lighting arithmetic (which does not need them) runs: tex_fetch computes the addresses and issues the loads,
+// tex_filter weighs the texels.  (Texels come from DRAM more often than not: a 16 MB texture, no mip maps.)
+struct TexFetch { uint32_t p00, p10, p01, p11; float fu, fv; };     // the four texels + the texture coordinate (column, row) the weights derive from
+
 template <int TEX>
-SB_DEV uint32_t shade_texture(const SpanShade *ss, const Prim &pr, const uint32_t *texels, float u)
+SB_DEV TexFetch tex_fetch(const SpanShade *ss, const Prim &pr, const uint32_t *texels, float u)
 {
-    if (TEX == SWEGL_B200_TEX_PLAIN) return pr.color;                       // pixel_shaders.hpp:28
+    TexFetch f;
+    f.p00 = pr.color; f.p10 = f.p01 = f.p11 = 0u; f.fu = f.fv = 0.f;
+    if (TEX == SWEGL_B200_TEX_PLAIN) return f;                              // pixel_shaders.hpp:28
     // t = t_left + t_dir * progress   (pixel_shaders.cpp:277, 352)
     float tx = fadd(ss->t_left[0], fmul(ss->t_dir[0], u)), ty = fadd(ss->t_left[1], fmul(ss->t_dir[1], u));
     const uint32_t *bm = texels + pr.tex_off;
@@ -67,20 +74,31 @@ SB_DEV uint32_t shade_texture(const SpanShade *ss, const Prim &pr, const uint32_
         unsigned tw = (unsigned)pr.tw, th = (unsigned)pr.th;
         unsigned uu = pr.tw_mask >= 0 ? ((unsigned)f2i(tx) & (unsigned)pr.tw_mask) : (unsigned)f2i(tx) % tw;
         unsigned vv = pr.th_mask >= 0 ? ((unsigned)f2i(ty) & (unsigned)pr.th_mask) : (unsigned)f2i(ty) % th;
-        return __ldg(&bm[vv * tw + uu]);
+        f.p00 = __ldg(&bm[vv * tw + uu]);
+        return f;
     }
     // pixel_shader_texture_bilinear::shade, pixel_shaders.cpp:348-384: t.x picks the ROW, t.y the COLUMN
-    float v = tx, uq = ty;
-    float u1 = fsub(uq, 0.5f), u2 = fadd(uq, 0.5f), v1 = fsub(v, 0.5f), v2 = fadd(v, 0.5f);
-    uq = floor_small(u2); v = floor_small(v2);
+    const float v1 = fsub(tx, 0.5f), u1 = fsub(ty, 0.5f);
     int tw = pr.tw, th = pr.th;
     int v1m = wrap_index(f2i(v1) + th, th, pr.th_mask);                     // ((int)v1 + theight) % theight; UB guard
     int v2m = v1m + 1; if (v2m == th) v2m = 0;
     v1m *= tw; v2m *= tw;
     int u1m = wrap_index(f2i(u1) + tw, tw, pr.tw_mask);
     int u2m = u1m + 1; if (u2m == tw) u2m = 0;
-    uint32_t p00 = __ldg(&bm[v1m + u1m]), p10 = __ldg(&bm[v2m + u1m]);
-    uint32_t p01 = __ldg(&bm[v1m + u2m]), p11 = __ldg(&bm[v2m + u2m]);
+    f.p00 = __ldg(&bm[v1m + u1m]); f.p10 = __ldg(&bm[v2m + u1m]);
+    f.p01 = __ldg(&bm[v1m + u2m]); f.p11 = __ldg(&bm[v2m + u2m]);
+    f.fu = ty; f.fv = tx;                                                   // the filter recomputes its weights from t
+    return f;
+}
+
+template <int TEX>
+SB_DEV uint32_t tex_filter(const TexFetch &f)
+{
+    if (TEX != SWEGL_B200_TEX_BILINEAR) return f.p00;
+    float v = f.fv, uq = f.fu;
+    float u1 = fsub(uq, 0.5f), u2 = fadd(uq, 0.5f), v1 = fsub(v, 0.5f), v2 = fadd(v, 0.5f);
+    uq = floor_small(u2); v = floor_small(v2);
+    const uint32_t p00 = f.p00, p10 = f.p10, p01 = f.p01, p11 = f.p11;
     float w00 = fmul(fsub(uq, u1), fsub(v, v1)), w10 = fmul(fsub(uq, u1), fsub(v2, v));
     float w01 = fmul(fsub(u2, uq), fsub(v, v1)), w11 = fmul(fsub(u2, uq), fsub(v2, v));
     uint32_t out = 0;
@@ -93,6 +111,12 @@ SB_DEV uint32_t shade_texture(const SpanShade *ss, const Prim &pr, const uint32_
     SB_BILINEAR_CHANNEL(0) SB_BILINEAR_CHANNEL(1) SB_BILINEAR_CHANNEL(2) SB_BILINEAR_CHANNEL(3)
     #undef SB_BILINEAR_CHANNEL
     return out;
+}
+
+template <int TEX>
+SB_DEV uint32_t shade_texture(const SpanShade *ss, const Prim &pr, const uint32_t *texels, float u)
+{
+    return tex_filter<TEX>(tex_fetch<TEX>(ss, pr, texels, u));
 }
 
 template <int LIGHT>
@@ -115,10 +139,11 @@ template <int LIGHT, int TEX>
 SB_DEV uint32_t shade(const SpanShade *ss, float flat_light, const Prim &pr, const uint32_t *texels, const ViewParams &vp,
                       const FrameParams &fp, float u)
 {
-    uint32_t c = shade_texture<TEX>(ss, pr, texels, u);
-    if (LIGHT == SWEGL_B200_LIGHT_NONE) return c;
+    const TexFetch tf = tex_fetch<TEX>(ss, pr, texels, u);                  // texel loads issued ...
+    if (LIGHT == SWEGL_B200_LIGHT_NONE) return tex_filter<TEX>(tf);
     // pixel_shader_light_and_texture::shade, pixel_shaders.hpp:159-178
-    int li = shade_light<LIGHT>(ss, flat_light, vp, fp, u);
+    int li = shade_light<LIGHT>(ss, flat_light, vp, fp, u);                 // ... in flight under the lighting arithmetic ...
+    uint32_t c = tex_filter<TEX>(tf);                                       // ... consumed here
     float light = fmul(__int2float_rn(li), 1.0f / 65536.0f);               // (float)(li / 65536.0)
     uint32_t b = c & 0xFF, g = (c >> 8) & 0xFF, r = (c >> 16) & 0xFF;
     if (light < 1.0f) {
