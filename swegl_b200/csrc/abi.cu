@@ -39,6 +39,7 @@ struct swegl_b200_ctx {
     CullTables cull{};
     ClusterBox *d_cl_box = nullptr; uint32_t *d_cl_adj_off = nullptr, *d_cl_adj = nullptr, *d_vb_adj_off = nullptr, *d_vb_adj = nullptr;
     uint8_t *d_cull_flags = nullptr;
+    uint32_t *d_cull_lists = nullptr;   // live_list (ncl) | mark_list (ncl) | vert_list (nvb) | counts (4)
     int cull_policy = -1;
     uint32_t stamp = 0;            // ViewParams::stamp of the last staged view
 
@@ -220,10 +221,15 @@ static int build_cull_tables(swegl_b200_ctx *ctx, const std::vector<Tri> &tris, 
     CK(cudaMemcpy(ctx->d_vb_adj_off, vb_off.data(), ((size_t)nvb + 1) * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_vb_adj, vb_list.data(), vb_list.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemset(ctx->d_cull_flags, 1, (size_t)2 * ncl + nvb));
+    CK(dalloc(ctx->d_cull_lists, (size_t)2 * ncl + nvb + 4));
+    CK(cudaMemset(ctx->d_cull_lists, 0, ((size_t)2 * ncl + nvb + 4) * 4));
     CullTables &ct = ctx->cull;
     ct.n_clusters = ncl; ct.n_vblocks = nvb; ct.boxes = ctx->d_cl_box;
     ct.cl_adj_off = ctx->d_cl_adj_off; ct.cl_adj = ctx->d_cl_adj; ct.vb_adj_off = ctx->d_vb_adj_off; ct.vb_adj = ctx->d_vb_adj;
     ct.cl_live = ctx->d_cull_flags; ct.mark_need = ctx->d_cull_flags + ncl; ct.vert_need = ctx->d_cull_flags + 2 * (size_t)ncl;
+    ct.live_list = ctx->d_cull_lists; ct.mark_list = ctx->d_cull_lists + ncl; ct.vert_list = ctx->d_cull_lists + 2 * (size_t)ncl;
+    ct.counts = ctx->d_cull_lists + 2 * (size_t)ncl + nvb;
+    ctx->pools.cull_counts = ct.counts;
     return SWEGL_B200_OK;
 }
 
@@ -284,7 +290,7 @@ void swegl_b200_destroy(swegl_b200_ctx *ctx)
                      ctx->pools.edges, ctx->pools.shades, ctx->pools.spans, ctx->pools.span_shades, ctx->pools.frag_u, ctx->pools.row_slot,
                      ctx->pools.chunks, ctx->pools.bin_head, ctx->pools.bin_used, ctx->pools.tile_stamp, ctx->pools.busy_list,
                      ctx->pools.counters, ctx->d_screen, ctx->d_depth,
-                     ctx->d_tmp_color, ctx->d_cl_box, ctx->d_cl_adj_off, ctx->d_cl_adj, ctx->d_vb_adj_off, ctx->d_vb_adj, ctx->d_cull_flags };
+                     ctx->d_tmp_color, ctx->d_cl_box, ctx->d_cl_adj_off, ctx->d_cl_adj, ctx->d_vb_adj_off, ctx->d_vb_adj, ctx->d_cull_flags, ctx->d_cull_lists };
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     for (auto &sl : ctx->slots) {
@@ -525,6 +531,7 @@ int swegl_b200_upload_scene(swegl_b200_ctx *ctx, const swegl_b200_scene_desc *sc
     ds.tris = ctx->d_tris; ds.prims = ctx->d_prims; ds.texels = ctx->d_texels;
     ds.v_world = ctx->d_v_world; ds.v_ndc = ctx->d_v_ndc; ds.n_world = ctx->d_n_world; ds.yes = ctx->d_yes;
     ds.cl_live = ds.mark_need = ds.vert_need = nullptr;
+    ds.live_list = ds.mark_list = ds.vert_list = ds.cull_counts = nullptr;
     ctx->cull = CullTables{};
     if (nt && ctx->cull_policy != 0) { rc = build_cull_tables(ctx, tris, sc->positions, vert_node, nv); if (rc) return rc; }
     ctx->n_nodes = sc->n_nodes;
@@ -711,6 +718,8 @@ static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const Vie
     DeviceScene ds = ctx->ds;
     if (view_culled(ctx, vp)) {                             // sort-first band: skip what cannot reach it (common.cuh)
         ds.cl_live = ctx->cull.cl_live; ds.mark_need = ctx->cull.mark_need; ds.vert_need = ctx->cull.vert_need;
+        ds.live_list = ctx->cull.live_list; ds.mark_list = ctx->cull.mark_list; ds.vert_list = ctx->cull.vert_list;
+        ds.cull_counts = ctx->cull.counts;
         launch_cull(ds, ctx->d_vp(), ctx->cull, st); launches += 2;
     }
     launch_vertex(ds, ctx->d_vp(), ctx->pools.counters, with_frame, st); launches++;

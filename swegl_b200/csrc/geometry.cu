@@ -26,14 +26,28 @@ static constexpr uint32_t SPAN_SEG = 4;      // 32-column bins per span segment 
 // interval below carries 2E (corner + vertex).  A box that comes closer than 0.002 to the camera plane is never
 // culled (the near clipper, renderer.cpp:286-356, then creates vertices of its own).  Rows walked by an unclipped
 // triangle are [ceil(min y), ceil(max y)) of its pixel-space vertices (renderer.cpp:375-394).
+// list[atomicAdd(count, #set lanes) + rank among the set lanes] = id, one atomic per warp (every lane of the warp calls it)
+SB_DEV void append_ids(uint32_t *list, uint32_t *count, bool set, uint32_t id)
+{
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, set);
+    if (!m) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (set) list[base + __popc(m & ((1u << lane) - 1u))] = id;
+}
+
 __global__ void __launch_bounds__(128) k_cull_live(DeviceScene s, const ViewParams *__restrict__ vpp, CullTables ct)
 {
     pdl_trigger();
     const uint32_t c = blockIdx.x * 128 + threadIdx.x;
-    if (c >= ct.n_clusters) return;
-    const ClusterBox box = ct.boxes[c];
-    bool live = true;
-    if (box.node >= 0) {
+    const bool valid = c < ct.n_clusters;
+    ClusterBox box;
+    box.node = -1;
+    if (valid) box = ct.boxes[c];
+    bool live = valid;
+    if (valid && box.node >= 0) {
         const float *M = s.node_world + 16 * box.node;
         const float *V = vpp->view, *P = vpp->proj;
         double aw[3], ac[3];
@@ -66,7 +80,8 @@ __global__ void __launch_bounds__(128) k_cull_live(DeviceScene s, const ViewPara
             if (yhi + margin < (double)vpp->band0 - 1.0 || ylo - margin > (double)vpp->band1 + 1.0) live = false;
         }
     }
-    ct.cl_live[c] = live ? 1 : 0;
+    if (valid) ct.cl_live[c] = live ? 1 : 0;
+    append_ids(ct.live_list, &ct.counts[0], live, c);
 }
 
 // One thread per cluster (mark_need) and per vertex block (vert_need): OR of cl_live over a static adjacency list.
@@ -76,16 +91,19 @@ __global__ void __launch_bounds__(128) k_cull_need(CullTables ct)
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
     const bool is_cl = i < ct.n_clusters;
     const uint32_t j = is_cl ? i : i - ct.n_clusters;
-    if (!is_cl && j >= ct.n_vblocks) { pdl_wait(); return; }
+    const bool valid = is_cl || j < ct.n_vblocks;
     const uint32_t *off = is_cl ? ct.cl_adj_off : ct.vb_adj_off, *adj = is_cl ? ct.cl_adj : ct.vb_adj;
-    const uint32_t a = off[j], b = off[j + 1];
+    uint32_t a = 0, b = 0;
+    if (valid) { a = off[j]; b = off[j + 1]; }
     pdl_wait();                                                             // k_cull_live's flags
     bool need = false;
     for (uint32_t k = a; k < b && !need; k++) {
         const uint32_t c = adj[k];
         need = c == CULL_ALWAYS || ct.cl_live[c] != 0;
     }
-    (is_cl ? ct.mark_need : ct.vert_need)[j] = need ? 1 : 0;
+    if (valid) (is_cl ? ct.mark_need : ct.vert_need)[j] = need ? 1 : 0;
+    append_ids(ct.mark_list, &ct.counts[1], need && is_cl, j);              // (a warp may straddle the cluster / block boundary)
+    append_ids(ct.vert_list, &ct.counts[2], need && valid && !is_cl, j);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -95,23 +113,8 @@ __global__ void __launch_bounds__(128) k_cull_need(CullTables ct)
 // yes reset (A2).  WORLD selects whether this launch is the first of the frame and also has to produce v_world.
 // Block 0 clears the frame counters (no memset node in the graph).
 template <bool WORLD>
-__global__ void __launch_bounds__(TPB) k_vertex(DeviceScene s, const ViewParams *__restrict__ vpp, Counters *__restrict__ counters)
+SB_DEV void vertex_one(const DeviceScene &s, const ViewParams &vp, uint32_t i)
 {
-    pdl_trigger();
-    __shared__ ViewParams vp;
-    if (blockIdx.x == 0 && threadIdx.x < sizeof(Counters) / 4) reinterpret_cast<uint32_t *>(counters)[threadIdx.x] = 0;
-    if (s.vert_need) {                                                      // culled view: TPB threads = TPB / CULL_CL vertex blocks
-        pdl_wait();                                                         // k_cull_need's flags
-        const uint32_t b0 = blockIdx.x * (TPB / CULL_CL), nvb = (s.n_vertices + CULL_CL - 1) / CULL_CL;
-        bool any = false;
-        for (uint32_t b = b0; b < b0 + TPB / CULL_CL && b < nvb; b++) any = any || s.vert_need[b];
-        if (!any) return;                                                   // CTA-uniform, before anything is staged
-    }
-    for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
-    __syncthreads();
-    uint32_t i = blockIdx.x * TPB + threadIdx.x;
-    if (i >= s.n_vertices) return;
-    if (s.vert_need && !s.vert_need[i / CULL_CL]) return;                   // no triangle that matters to this band uses it
     const uint32_t node = s.vert_node[i];
     V3 w;
     if (WORLD) {
@@ -127,21 +130,36 @@ __global__ void __launch_bounds__(TPB) k_vertex(DeviceScene s, const ViewParams 
     s.yes[i] = 0;
 }
 
+template <bool WORLD>
+__global__ void __launch_bounds__(TPB, 8) k_vertex(DeviceScene s, const ViewParams *__restrict__ vpp, Counters *__restrict__ counters)
+{
+    pdl_trigger();
+    __shared__ ViewParams vp;
+    if (blockIdx.x == 0 && threadIdx.x < sizeof(Counters) / 4) reinterpret_cast<uint32_t *>(counters)[threadIdx.x] = 0;
+    for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
+    __syncthreads();
+    if (s.vert_list) {
+        // culled view: persistent CTAs walk the list of vertex blocks some triangle that matters to the band uses
+        pdl_wait();                                                         // k_cull_need's list
+        constexpr uint32_t PER = TPB / CULL_CL;                             // vertex blocks per CTA pass
+        const uint32_t n_items = s.cull_counts[2];
+        for (uint32_t it = blockIdx.x * PER + threadIdx.x / CULL_CL; it < n_items; it += gridDim.x * PER) {
+            const uint32_t i = s.vert_list[it] * CULL_CL + threadIdx.x % CULL_CL;
+            if (i < s.n_vertices) vertex_one<WORLD>(s, vp, i);
+        }
+        return;
+    }
+    uint32_t i = blockIdx.x * TPB + threadIdx.x;
+    if (i >= s.n_vertices) return;
+    vertex_one<WORLD>(s, vp, i);
+}
+
 // ----------------------------------------------------------------------------------------
 // mark pass: a triangle that is inside the frustum and front facing (or double sided) marks its
 // three vertices; fill_triangle later draws every triangle whose vertices are all marked.
 // ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) k_mark(DeviceScene s)
+SB_DEV void mark_one(const DeviceScene &s, const Tri &tr)
 {
-    pdl_trigger();
-    uint32_t t = blockIdx.x * TPB + threadIdx.x;
-    if (t >= s.n_tris) { pdl_wait(); return; }                              // (every CTA waits: completion stays transitive along the chain)
-    if (s.mark_need) {
-        pdl_wait();
-        if (!s.mark_need[t / CULL_CL]) return;                              // cannot mark a vertex of a triangle that reaches the band
-    }
-    Tri tr = s.tris[t];                                                     // static scene data: may be read before the wait
-    pdl_wait();                                                             // k_vertex's v_ndc and yes reset
     V3 a = v3(s.v_ndc[3 * tr.i0], s.v_ndc[3 * tr.i0 + 1], s.v_ndc[3 * tr.i0 + 2]);
     V3 b = v3(s.v_ndc[3 * tr.i1], s.v_ndc[3 * tr.i1 + 1], s.v_ndc[3 * tr.i1 + 2]);
     V3 c = v3(s.v_ndc[3 * tr.i2], s.v_ndc[3 * tr.i2 + 1], s.v_ndc[3 * tr.i2 + 2]);
@@ -159,6 +177,27 @@ __global__ void __launch_bounds__(TPB) k_mark(DeviceScene s)
         if (!(cross_n(sub(b, a), sub(c, a)).z > 0.f)) return;
     }
     s.yes[tr.i0] = 1; s.yes[tr.i1] = 1; s.yes[tr.i2] = 1;
+}
+
+__global__ void __launch_bounds__(TPB) k_mark(DeviceScene s)
+{
+    pdl_trigger();
+    if (s.mark_list) {
+        // culled view: only clusters that share a vertex with a cluster reaching the band can mark a vertex that is looked at
+        pdl_wait();                                                         // k_vertex (and, through it, k_cull_need's list)
+        constexpr uint32_t PER = TPB / CULL_CL;
+        const uint32_t n_items = s.cull_counts[1];
+        for (uint32_t it = blockIdx.x * PER + threadIdx.x / CULL_CL; it < n_items; it += gridDim.x * PER) {
+            const uint32_t t = s.mark_list[it] * CULL_CL + threadIdx.x % CULL_CL;
+            if (t < s.n_tris) mark_one(s, s.tris[t]);
+        }
+        return;
+    }
+    uint32_t t = blockIdx.x * TPB + threadIdx.x;
+    if (t >= s.n_tris) { pdl_wait(); return; }                              // (every CTA waits: completion stays transitive along the chain)
+    Tri tr = s.tris[t];                                                     // static scene data: may be read before the wait
+    pdl_wait();                                                             // k_vertex's v_ndc and yes reset
+    mark_one(s, tr);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -361,26 +400,9 @@ SB_DEV void fill_row_slots(const Pools &pl, RowRange rr, uint32_t slot)
 #ifndef SETUP_MINB
 #define SETUP_MINB 4
 #endif
-__global__ void __launch_bounds__(128, SETUP_MINB) k_setup(DeviceScene s, const ViewParams *__restrict__ vpp,
-                                               const FrameParams *__restrict__ fpp, Pools pl)
+// fill_triangle for triangle t (go == false: an idle lane that only takes part in the warp's collectives)
+SB_DEV void setup_one(const DeviceScene &s, const ViewParams &vp, const FrameParams &fp, const Pools &pl, const uint32_t t, bool go)
 {
-    pdl_trigger();
-    __shared__ ViewParams vp;                   // staged once per CTA: used all over the set-up code
-    __shared__ FrameParams fp;
-    const uint32_t t = blockIdx.x * 128 + threadIdx.x;
-    bool go = t < s.n_tris;
-    if (s.cl_live) {                                                        // band culling: 128 threads = 2 clusters
-        static_assert(128 % CULL_CL == 0, "a warp never straddles two clusters");
-        pdl_wait();
-        const uint32_t c0 = blockIdx.x * (128 / CULL_CL), ncl = (s.n_tris + CULL_CL - 1) / CULL_CL;
-        bool any = false;
-        for (uint32_t c = c0; c < c0 + 128 / CULL_CL && c < ncl; c++) any = any || s.cl_live[c];
-        if (!any) return;                                                   // CTA-uniform, before anything is staged
-        go = go && s.cl_live[t / CULL_CL];
-    }
-    for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += 128) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
-    for (int w = threadIdx.x; w < (int)(sizeof(FrameParams) / 4); w += 128) reinterpret_cast<uint32_t *>(&fp)[w] = reinterpret_cast<const uint32_t *>(fpp)[w];
-    __syncthreads();
     RowRange r0 = { 0u, 0u }, r1 = { 0u, 0u };
     Tri tr = { 0u, 0u, 0u, 0u };
     if (go) tr = s.tris[t];
@@ -468,6 +490,34 @@ __global__ void __launch_bounds__(128, SETUP_MINB) k_setup(DeviceScene s, const 
     }
     fill_row_slots(pl, r0, 2 * t);
     if (__any_sync(0xFFFFFFFFu, r1.n != 0)) fill_row_slots(pl, r1, 2 * t + 1);
+}
+
+__global__ void __launch_bounds__(128, SETUP_MINB) k_setup(DeviceScene s, const ViewParams *__restrict__ vpp,
+                                               const FrameParams *__restrict__ fpp, Pools pl)
+{
+    pdl_trigger();
+    __shared__ ViewParams vp;                   // staged once per CTA: used all over the set-up code
+    __shared__ FrameParams fp;
+    for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += 128) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
+    for (int w = threadIdx.x; w < (int)(sizeof(FrameParams) / 4); w += 128) reinterpret_cast<uint32_t *>(&fp)[w] = reinterpret_cast<const uint32_t *>(fpp)[w];
+    __syncthreads();
+    if (s.live_list) {
+        // band culling: persistent CTAs walk the list of clusters that may hold a triangle reaching the band
+        static_assert(128 % CULL_CL == 0, "whole clusters per CTA pass");
+        pdl_wait();                                                         // k_mark (and, through the chain, k_cull_live's list)
+        constexpr uint32_t PER = 128 / CULL_CL;
+        const uint32_t n_items = s.cull_counts[0];
+        for (uint32_t base = blockIdx.x * PER; base < n_items; base += gridDim.x * PER) {      // CTA-uniform trip count (warp collectives inside)
+            const uint32_t it = base + threadIdx.x / CULL_CL;
+            uint32_t t = 0;
+            bool go = false;
+            if (it < n_items) { t = s.live_list[it] * CULL_CL + threadIdx.x % CULL_CL; go = t < s.n_tris; }
+            setup_one(s, vp, fp, pl, t, go);
+        }
+        return;
+    }
+    const uint32_t t = blockIdx.x * 128 + threadIdx.x;
+    setup_one(s, vp, fp, pl, t, t < s.n_tris);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -584,6 +634,7 @@ __global__ void __launch_bounds__(SPAN_TPB, SPAN_MINB) k_spans(const ViewParams 
     for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += SPAN_TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
     __syncthreads();
     pdl_wait();                                                             // k_setup's records and counters
+    if (pl.cull_counts && blockIdx.x == 0 && threadIdx.x < 3) pl.cull_counts[threadIdx.x] = 0;   // the view's cull lists are spent (k_setup was their last reader)
     if (pl.counters->overflow & 1u) return;      // some rows were never allocated: the host grows the pool and redoes the frame
     const uint32_t n_rows = min(pl.counters->n_rows, pl.rows_cap);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -761,6 +812,7 @@ __global__ void __launch_bounds__(TPB) k_spans_dense(const ViewParams *__restric
     for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
     __syncthreads();
     pdl_wait();                                                             // k_setup's records and counters
+    if (pl.cull_counts && blockIdx.x == 0 && threadIdx.x < 3) pl.cull_counts[threadIdx.x] = 0;   // the view's cull lists are spent (k_setup was their last reader)
     if (pl.counters->overflow & 1u) return;
     const uint32_t n_rows = min(pl.counters->n_rows, pl.rows_cap);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -890,7 +942,8 @@ void launch_cull(const DeviceScene &s, const ViewParams *d_vp, const CullTables 
 }
 void launch_vertex(const DeviceScene &s, const ViewParams *d_vp, Counters *counters, bool with_world, cudaStream_t st)
 {
-    const unsigned blocks = max(1u, cdiv(s.n_vertices, TPB));
+    // culled views walk a list with persistent CTAs (k_vertex): one wave is enough
+    const unsigned blocks = s.vert_list ? min(max(1u, cdiv(s.n_vertices, TPB)), 148u * 8u) : max(1u, cdiv(s.n_vertices, TPB));
     // first kernel of the frame unless the view is culled: then it follows the upload of the parameter block (a copy,
     // not a kernel) -> ordinary launch.  A culled view skips vertices, so it can never rely on an earlier view's v_world.
     const bool chained = s.vert_need != nullptr;
@@ -899,11 +952,11 @@ void launch_vertex(const DeviceScene &s, const ViewParams *d_vp, Counters *count
 }
 void launch_mark(const DeviceScene &s, cudaStream_t st)
 {
-    if (s.n_tris) launch_chain(k_mark, cdiv(s.n_tris, TPB), TPB, st, true, s);
+    if (s.n_tris) launch_chain(k_mark, s.mark_list ? min(cdiv(s.n_tris, TPB), 148u * 8u) : cdiv(s.n_tris, TPB), TPB, st, true, s);
 }
 void launch_setup(const DeviceScene &s, const ViewParams *d_vp, const FrameParams *d_fp, const Pools &p, cudaStream_t st)
 {
-    if (s.n_tris) launch_chain(k_setup, cdiv(s.n_tris, 128), 128, st, true, s, d_vp, d_fp, p);
+    if (s.n_tris) launch_chain(k_setup, s.live_list ? min(cdiv(s.n_tris, 128u), 148u * SETUP_MINB * 2u) : cdiv(s.n_tris, 128u), 128, st, true, s, d_vp, d_fp, p);
 }
 void launch_spans(const ViewParams *d_vp, const Pools &p, bool dense, cudaStream_t st)
 {
