@@ -663,6 +663,22 @@ def main():
                 "e2e_fps": args.steps / a["e2e_secs"], "e2e_blocking_call_fps": args.steps / a["e2e_sync_secs"], "shaded_mpix_per_s": al.n_covered * args.steps / a["secs"] / 1e6,
                 "ms_per_stage": ak}
 
+    # the remaining BASELINE.json configs that fit one GPU (config 1 and config 3), device-resident, one frame at a time
+    others = None
+    if not args.no_also and args.workload == DEFAULT_WORKLOAD and world == 1:
+        others = {}
+        for oname in ("box_640", "brainstem_4k_dof"):
+            from swegl_b200 import configs as _cfg
+            osc, ovps, oscreen, ocfg = _cfg.build(oname)
+            r.upload_scene(osc)
+            r.set_screen(*oscreen)
+            osecs, _ = measure_gpu(r, torch, osc, ovps, oscreen, min(args.steps, 30), args.warmup, flush)
+            ok_, ol_ = measure_kernels(r, osc, ovps, 10)
+            n_ = min(args.steps, 30)
+            others[oname] = {"description": ocfg["desc"], "one_frame_at_a_time_fps": n_ / osecs, "ms_per_frame": 1e3 * osecs / n_,
+                             "covered_pixels": int(ol_.n_covered), "shaded_mpix_per_s": ol_.n_covered * n_ / osecs / 1e6,
+                             "ms_per_stage": ok_}
+
     sharded = None
     if args.sharded and not args.no_also:
         sharded = sharded_frame(r, torch, dist, args.sharded, min(args.steps, 10), args.warmup, flush, world, rank)
@@ -708,7 +724,10 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         v, kind, times = cpu_reference_single(args.workload, 3, 1)
-        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
+        from oracle.binding import Oracle                           # the checker, here only to COUNT the CPU path's fragments
+        n_frag_cpu = sum(int(Oracle().render(scene, vp_, screen_wh=screen)["n_fragments"]) for vp_ in vps)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": kind, "fragments_shaded_per_s": n_frag_cpu * v,
+               "fragments_per_frame": n_frag_cpu,
                "sample": f"3 frames of {args.workload} after 1 warm-up, swegl::render as shipped (1 raster thread) "
                          f"via oracle/_ref + DoF-R by the C oracle; {1e3 / v:.1f} ms/frame"}
 
@@ -742,6 +761,8 @@ def main():
             "ms_per_stage": kern, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
     if also:
         line["also"] = also
+    if others:
+        line["other_workloads"] = others
     if sharded:
         line["sharded_frame"] = sharded
     if multiview:

@@ -501,23 +501,24 @@ __global__ void __launch_bounds__(128, SETUP_MINB) k_setup(DeviceScene s, const 
     for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += 128) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
     for (int w = threadIdx.x; w < (int)(sizeof(FrameParams) / 4); w += 128) reinterpret_cast<uint32_t *>(&fp)[w] = reinterpret_cast<const uint32_t *>(fpp)[w];
     __syncthreads();
-    if (s.live_list) {
-        // band culling: persistent CTAs walk the list of clusters that may hold a triangle reaching the band
-        static_assert(128 % CULL_CL == 0, "whole clusters per CTA pass");
+    // One call site for both cases (set-up is a large body: a second inlined copy costs a small frame ~4 us of
+    // instruction fetch): a culled view walks the list of clusters that may hold a triangle reaching the band with
+    // persistent CTAs; otherwise the grid covers every cluster once and the loop runs a single pass.
+    static_assert(128 % CULL_CL == 0, "whole clusters per CTA pass");
+    constexpr uint32_t PER = 128 / CULL_CL;
+    const bool listed = s.live_list != nullptr;
+    uint32_t n_items = (s.n_tris + CULL_CL - 1) / CULL_CL;
+    if (listed) {
         pdl_wait();                                                         // k_mark (and, through the chain, k_cull_live's list)
-        constexpr uint32_t PER = 128 / CULL_CL;
-        const uint32_t n_items = s.cull_counts[0];
-        for (uint32_t base = blockIdx.x * PER; base < n_items; base += gridDim.x * PER) {      // CTA-uniform trip count (warp collectives inside)
-            const uint32_t it = base + threadIdx.x / CULL_CL;
-            uint32_t t = 0;
-            bool go = false;
-            if (it < n_items) { t = s.live_list[it] * CULL_CL + threadIdx.x % CULL_CL; go = t < s.n_tris; }
-            setup_one(s, vp, fp, pl, t, go);
-        }
-        return;
+        n_items = s.cull_counts[0];
     }
-    const uint32_t t = blockIdx.x * 128 + threadIdx.x;
-    setup_one(s, vp, fp, pl, t, t < s.n_tris);
+    for (uint32_t base = blockIdx.x * PER; base < n_items; base += gridDim.x * PER) {          // CTA-uniform trip count (warp collectives inside)
+        const uint32_t it = base + threadIdx.x / CULL_CL;
+        uint32_t t = 0;
+        bool go = false;
+        if (it < n_items) { t = (listed ? s.live_list[it] : it) * CULL_CL + threadIdx.x % CULL_CL; go = t < s.n_tris; }
+        setup_one(s, vp, fp, pl, t, go);
+    }
 }
 
 // ----------------------------------------------------------------------------------------
