@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libswegl_b200.so")
     with open(os.path.join(HERE, "ptxas_info.txt"), "w") as f:
-        f.write(res.stderr)
+        f.write("".join(ln for ln in res.stderr.splitlines(True) if "Compile time" not in ln))   # (timings would change the file on every build)
     return OUT
 
 
