@@ -181,3 +181,39 @@ def test_two_rank_viewport_per_rank_and_rect_gather(tmp_path, oracle):
     for vp in vps:
         oracle.render(scene, vp, screen_wh=screen, pixels=want)
     assert (np.load(out) == want).all()
+
+
+def _protocol_worker(rank, world, port, log_dir):
+    """arm_frame_sync: rank 0 resets its flag block BEFORE any other rank arms (their first frame raises done flags in
+    rank 0's memory); a rank other than 0 cannot be the assembling one"""
+    sys.path.insert(0, ROOT)
+    import time
+    import torch.distributed as dist
+    from swegl_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class FakeRenderer:
+        def set_frame_sync(self, r, w=0):
+            with open(os.path.join(log_dir, f"armed_{r}"), "w") as f:
+                f.write(f"{time.monotonic_ns()} {w}")
+    fr = FakeRenderer()
+    if rank == 1:
+        time.sleep(0.2)                                  # a late rank must not let the others run ahead of rank 0's reset
+    sharding.arm_frame_sync(fr, dist, dst=0)
+    try:
+        sharding.arm_frame_sync(fr, dist, dst=1)
+        raise AssertionError("dst != 0 accepted")
+    except ValueError:
+        pass
+    dist.destroy_process_group()
+
+
+def test_frame_protocol_arms_rank0_first(tmp_path):
+    import torch.multiprocessing as mp
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_protocol_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    t0, w0 = (int(v) for v in open(tmp_path / "armed_0").read().split())
+    t1, w1 = (int(v) for v in open(tmp_path / "armed_1").read().split())
+    assert t0 < t1 and w0 == 2 and w1 == 2
