@@ -57,3 +57,46 @@ def test_fuzz_scene_with_transparency_layers_bit_identical(ref, oracle, seed):
     assert (rpx == o["pixels"]).all()
     a = rpx >> 24
     assert ((a != 0) & (a != 255)).sum() > 500
+
+
+@pytest.mark.parametrize("seed", [0, 8])
+def test_heavy_fuzz_scene_bit_identical(ref, oracle, seed):
+    """30 primitives x 120 vertices on 640x360: deep overdraw (every pixel covered several times), long z-test chains"""
+    from swegl_b200.scene import Viewport
+    _, vp0, _, pose = configs.fuzz_case(seed)
+    scene = configs.fuzz_scene(seed, n_prims=30, verts_per_prim=120)
+    vp = Viewport(0, 0, 640, 360, light_mode=vp0.light_mode, tex_mode=vp0.tex_mode)
+    vp.camera.apply(pose)
+    h = ref.import_scene(scene)
+    scr = ref.lib.ref_screen_new(640, 360)
+    rv = ref.make_viewport(scr, vp, pose)
+    rpx, rz = ref.render(h, rv, scr, 640, 360, 640, 360)
+    ref.lib.ref_viewport_free(rv); ref.lib.ref_screen_free(scr); ref.lib.ref_scene_free(h)
+    o = oracle.render(scene, vp, screen_wh=(640, 360))
+    assert (rz.view(np.uint32) == o["z"].view(np.uint32)).all()
+    assert (rpx == o["pixels"]).all()
+    assert o["n_fragments"] > 3 * o["n_covered"]
+
+
+@pytest.mark.parametrize("seed", [2, 5])
+def test_two_viewports_on_one_surface_bit_identical(ref, oracle, seed):
+    """swegl::render(scene, vp1, vp2) (renderer.hpp:20-34): original_to_world once, then two offset viewports with different
+    shaders and cameras on the same surface"""
+    from swegl_b200.scene import Viewport
+    scene, vpa, _, pose_a = configs.fuzz_case(seed)
+    _, vpb, _, pose_b = configs.fuzz_case(seed + 100)
+    screen = (640, 300)
+    va = Viewport(3, 5, 300, 280, light_mode=vpa.light_mode, tex_mode=vpa.tex_mode)
+    vb = Viewport(320, 11, 311, 260, light_mode=vpb.light_mode, tex_mode=vpb.tex_mode)
+    va.camera.apply(pose_a); vb.camera.apply(pose_b)
+    h = ref.import_scene(scene)
+    scr = ref.lib.ref_screen_new(*screen)
+    ra, rb = ref.make_viewport(scr, va, pose_a), ref.make_viewport(scr, vb, pose_b)
+    ref.lib.ref_render2(h, ra, rb)
+    import ctypes as C
+    rpx = np.ctypeslib.as_array(C.cast(ref.lib.ref_screen_pixels(scr), C.POINTER(C.c_uint32)), shape=(screen[1], screen[0])).copy()
+    ref.lib.ref_viewport_free(ra); ref.lib.ref_viewport_free(rb); ref.lib.ref_screen_free(scr); ref.lib.ref_scene_free(h)
+    opx = np.zeros_like(rpx)
+    oracle.render(scene, va, screen_wh=screen, pixels=opx)
+    oracle.render(scene, vb, screen_wh=screen, pixels=opx)
+    assert (rpx == opx).all()
