@@ -32,7 +32,7 @@ def build(ref=True):
 class OrcDump(C.Structure):
     _fields_ = [("v_world", C.c_void_p), ("v_viewport", C.c_void_p), ("normal_world", C.c_void_p), ("yes", C.c_void_p),
                 ("n_fill_triangle", C.c_uint64), ("n_setup_triangles", C.c_uint64), ("n_spans", C.c_uint64),
-                ("n_fragments", C.c_uint64), ("n_covered", C.c_uint64)]
+                ("n_fragments", C.c_uint64), ("n_covered", C.c_uint64), ("n_texel_guard", C.c_uint64)]
 
 
 class Oracle:
@@ -76,7 +76,7 @@ class Oracle:
         if rc != 0:
             raise RuntimeError(f"orc_render failed: {rc}")
         out.update(pixels=pixels, z=z, n_fill_triangle=dump.n_fill_triangle, n_setup_triangles=dump.n_setup_triangles,
-                   n_spans=dump.n_spans, n_fragments=dump.n_fragments, n_covered=dump.n_covered)
+                   n_spans=dump.n_spans, n_fragments=dump.n_fragments, n_covered=dump.n_covered, n_texel_guard=dump.n_texel_guard)
         return out
 
     def dof_r(self, src, depth, focal_distance=5.0, focal_depth=5.0):

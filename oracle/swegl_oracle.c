@@ -300,7 +300,11 @@ static void ps_prepare_for_scanline(rs_t *s, float pl, float pr)
     }
 }
 
-static int wrap_i(int v, int n) { if (v < 0) { v %= n; if (v < 0) v += n; } return v; }   /* deviation: UB guard */
+/* deviation: a negative texel row / column -- the reference then reads outside the bitmap -- is wrapped.
+ * g_texel_guard counts the fragments where that happened, so that a comparison with the reference can tell "the
+ * reference left its defined behaviour on this frame" from a real difference (orc_dump::n_texel_guard). */
+static uint64_t g_texel_guard;
+static int wrap_i(int v, int n) { if (v < 0) { g_texel_guard++; v %= n; if (v < 0) v += n; } return v; }
 
 static uint32_t shade_texture(const rs_t *s, float progress)
 {
@@ -656,7 +660,8 @@ int orc_render(const swegl_b200_scene_desc *scene, const swegl_b200_frame_desc *
     s.n_layers = vp->transparency_layers > 1 ? vp->transparency_layers : 1;   /* viewport.cpp:37-39 */
     s.band_y0 = vp->y; s.band_y1 = vp->y + vp->h;
     if (vp->band_y0 != 0 || vp->band_y1 != 0) { s.band_y0 = vp->y + vp->band_y0; s.band_y1 = vp->y + vp->band_y1; }
-    if (dump) { dump->n_fill_triangle = dump->n_setup_triangles = dump->n_spans = dump->n_fragments = dump->n_covered = 0; }
+    if (dump) { dump->n_fill_triangle = dump->n_setup_triangles = dump->n_spans = dump->n_fragments = dump->n_covered = dump->n_texel_guard = 0; }
+    g_texel_guard = 0;
     const size_t npx = (size_t)vp->w * vp->h;
 
     /* ---- vertex stage: original_to_world + world_to_camera_or_frustum, vertex_shaders.hpp:16-52 ---- */
@@ -792,6 +797,7 @@ int orc_render(const swegl_b200_scene_desc *scene, const swegl_b200_frame_desc *
         }
         uint32_t mz = 0x7F7F7F7Fu;
         for (size_t i = 0; i < npx; i++) { uint32_t zb; memcpy(&zb, &zbuffer[i], 4); if (zb != mz) dump->n_covered++; }
+        dump->n_texel_guard = g_texel_guard;
     }
     for (int l = 0; l < s.n_layers; l++) { free(s.layer_colors[l]); free(s.layer_z[l]); }
     free(s.layer_colors); free(s.layer_z); free(verts);

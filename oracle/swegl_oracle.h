@@ -40,6 +40,7 @@ typedef struct orc_dump {
     uint64_t n_spans;           /* scanlines with x1 < x2                           */
     uint64_t n_fragments;       /* fragments that passed the z test (were shaded)   */
     uint64_t n_covered;         /* pixels with depth != 0x7F7F7F7F at the end       */
+    uint64_t n_texel_guard;     /* bilinear fetches whose row / column was negative: the reference reads out of bounds there */
 } orc_dump;
 
 /* One swegl::render(scene, viewport) for a single viewport.

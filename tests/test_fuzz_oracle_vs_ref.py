@@ -100,3 +100,39 @@ def test_two_viewports_on_one_surface_bit_identical(ref, oracle, seed):
     oracle.render(scene, va, screen_wh=screen, pixels=opx)
     oracle.render(scene, vb, screen_wh=screen, pixels=opx)
     assert (rpx == opx).all()
+
+
+def test_suite_seeds_stay_inside_the_references_defined_behaviour(oracle):
+    """the oracle counts the bilinear fetches the reference would do outside the bitmap (orc_dump::n_texel_guard,
+    DESIGN.md 7.2): none on the seeds the suite compares bit for bit"""
+    for seed in SEEDS:
+        scene, vp, screen, pose = configs.fuzz_case(seed)
+        vp.post_mode = _abi.POST_NULL
+        assert oracle.render(scene, vp, screen_wh=screen)["n_texel_guard"] == 0, seed
+
+
+@pytest.mark.parametrize("seed", [852, 1860])
+def test_frames_where_the_reference_reads_outside_a_bitmap_are_flagged(ref, oracle, seed):
+    """found by tools/fuzz_cpu.py: a near-plane sliver extrapolates its texture coordinate below zero, the reference
+    indexes the bitmap with a negative row (pixel_shaders.cpp:354-377) and samples whatever lies before it.  Depth and
+    vertex state still agree; colour differs only on such frames, and the oracle says so."""
+    scene, vp, screen, pose = configs.fuzz_case(seed)
+    vp.post_mode = _abi.POST_NULL
+    h = ref.import_scene(scene)
+    scr = ref.lib.ref_screen_new(*screen)
+    rv = ref.make_viewport(scr, vp, pose)
+    rpx, rz = ref.render(h, rv, scr, screen[0], screen[1], vp.w, vp.h)
+    ref.lib.ref_viewport_free(rv); ref.lib.ref_screen_free(scr); ref.lib.ref_scene_free(h)
+    o = oracle.render(scene, vp, screen_wh=screen)
+    assert (rz.view(np.uint32) == o["z"].view(np.uint32)).all()
+    differing = int((rpx != o["pixels"]).sum())
+    assert o["n_texel_guard"] > 0 and differing <= o["n_texel_guard"]
+    # with the coordinates moved far from zero most of the extrapolation stays positive and the frames (nearly) agree again
+    scene.texcoords = (scene.texcoords + np.float32(64.0)).astype(np.float32)
+    h = ref.import_scene(scene)
+    scr = ref.lib.ref_screen_new(*screen)
+    rv = ref.make_viewport(scr, vp, pose)
+    rpx2, _ = ref.render(h, rv, scr, screen[0], screen[1], vp.w, vp.h)
+    ref.lib.ref_viewport_free(rv); ref.lib.ref_screen_free(scr); ref.lib.ref_scene_free(h)
+    o2 = oracle.render(scene, vp, screen_wh=screen)
+    assert int((rpx2 != o2["pixels"]).sum()) <= o2["n_texel_guard"] < o["n_texel_guard"]
