@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SWEGL_B200_ABI_VERSION 1
+#define SWEGL_B200_ABI_VERSION 2
 
 /* ---- status codes (reference has none: void + assert, renderer.cpp:98-100) ---- */
 enum {
@@ -53,6 +53,10 @@ enum {
  * COMBINED = pixel_shader_light_and_texture<L,T> (:121-179): texture colour scaled by light. */
 enum { SWEGL_B200_LIGHT_NONE = 0, SWEGL_B200_LIGHT_FLAT = 1, SWEGL_B200_LIGHT_PHONG = 2 };
 enum { SWEGL_B200_TEX_PLAIN = 0, SWEGL_B200_TEX_NEAREST = 1, SWEGL_B200_TEX_BILINEAR = 2 };
+/* Phong lighting arithmetic (swegl_b200_set_shading).  EXACT reproduces the reference's unfused fp32 / fp64 evaluation
+ * bit for bit; FAST (the default) stays within +-1 LSB per 8-bit colour channel of it (alpha, coverage and depth are
+ * always exact) at about a third of the instructions.  Flat lighting and the texture filters are always exact. */
+enum { SWEGL_B200_SHADING_EXACT = 0, SWEGL_B200_SHADING_FAST = 1 };
 /* post_shader_t (null / copy, post_shaders.hpp:15-48) or post_shader_depth_box (:51-132, as
  * repaired: "DoF-R") */
 enum { SWEGL_B200_POST_NULL = 0, SWEGL_B200_POST_DOF = 1 };
@@ -62,7 +66,10 @@ typedef struct swegl_b200_primitive {
     int32_t  mode;          /* SWEGL_B200_MODE_*                                         */
     int32_t  material_id;   /* primitive_t::material_id, -1 = scene.default_material     */
     uint32_t first_vertex;  /* offset into the SoA vertex arrays                         */
-    uint32_t n_vertices;    /* real vertices (the 2 spare clip slots are NOT uploaded)   */
+    uint32_t n_vertices;    /* vertices of the primitive as the caller counts them; indices must stay below it.
+                               (swegl's loader appends 2 spare slots for the near clipper, gltf.cpp:175: the
+                               adapter uploads them along -- harmless, nothing indexes them; the device clipper
+                               keeps its vertices in registers) */
     uint32_t first_index;   /* offset into indices[]                                     */
     uint32_t n_indices;     /* indices are relative to first_vertex, as in primitive_t   */
 } swegl_b200_primitive;
@@ -120,7 +127,9 @@ typedef struct swegl_b200_viewport_desc {
     int32_t post_mode;             /* SWEGL_B200_POST_*                                    */
     float   focal_distance;        /* post_shader_depth_box::focal_distance                */
     float   focal_depth;           /* post_shader_depth_box::focal_depth                   */
-    int32_t transparency_layers;   /* ctor argument; >0 only supported for opaque scenes   */
+    int32_t transparency_layers;   /* viewport_t ctor argument (viewport.hpp:19-25): up to 8 on the device, and only on a
+                                      viewport at the screen origin; ignored when every material and
+                                      texel has alpha 255 (the layer logic is then the identity)                     */
     int32_t band_y0, band_y1;      /* sort-first scissor, viewport-relative rows
                                       [band_y0, band_y1); (0,0) = whole viewport           */
 } swegl_b200_viewport_desc;
@@ -187,10 +196,37 @@ int  swegl_b200_render_viewport(swegl_b200_ctx *ctx, const swegl_b200_viewport_d
  * At most two frames are in flight (a third submit waits for the oldest), so callers alternate between two
  * host images; these should be page-locked (swegl_b200_alloc_host), otherwise the copy blocks the submit.
  * swegl_b200_wait returns SWEGL_B200_ERR_CAPACITY when that frame ran out of pool space (the pools are then
- * enlarged: submit it again), like swegl_b200_synchronize. */
+ * enlarged: submit it again), like swegl_b200_synchronize.
+ *
+ * Overflow with two frames in flight: by the time wait(ticket i) reports ERR_CAPACITY, frame i+1 has already replaced the
+ * per-frame data on the device (node matrices, lights) and ran with the same undersized pools, so expect its ticket to
+ * fail as well.  Resubmitting frame i therefore means swegl_b200_begin_frame with THAT frame's data again, then
+ * render_viewport_async; render_viewport() (blocking) redoes an overflowed frame itself.
+ *
+ * Partial read-back (default on): outside the bounding box of what was drawn (grown by the blur radius with DoF-R) a frame
+ * is one constant.  The library remembers, per host image (`pixels` pointer), what it last left there, and copies only
+ * the union of the previous and the current box -- the background of a 4K frame does not cross PCIe every frame.  The
+ * image must therefore not be modified by the caller between two frames that go through it; after drawing into it
+ * (an overlay), call swegl_b200_invalidate_host_image (pixels == NULL: all images), or switch the feature off.  The first
+ * frame through an image, a change of viewport / pitch / band / post pass, and views with transparency layers are
+ * copied in full.  render_viewport (blocking, the drop-in's path) always copies the whole rectangle.
+ * Both host-read-back entry points fail with SWEGL_B200_ERR_STATE while a colour target is set (set_color_target): the
+ * finished pixels are then in the target's screen, not in this context's. */
 int  swegl_b200_render_viewport_async(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *vp,
                                       void *pixels, int32_t pitch_bytes, float *zbuffer, uint64_t *ticket);
 int  swegl_b200_wait(swegl_b200_ctx *ctx, uint64_t ticket);
+int  swegl_b200_set_partial_readback(swegl_b200_ctx *ctx, int enabled);
+int  swegl_b200_invalidate_host_image(swegl_b200_ctx *ctx, const void *pixels);
+/* out[0] = bytes copied device->host by render_viewport_async so far, out[1] = frames; reset != 0 zeroes both */
+int  swegl_b200_readback_stats(swegl_b200_ctx *ctx, uint64_t out[2], int reset);
+
+/* SWEGL_B200_SHADING_EXACT / _FAST for the frames submitted from now on (environment override at create:
+ * SWEGL_B200_SHADING=exact|fast).  No reference counterpart: the reference has one arithmetic. */
+int  swegl_b200_set_shading(swegl_b200_ctx *ctx, int mode);
+
+/* FNV-1a-64 over 32-bit words (offset basis 1469598103934665603, prime 1099511628211, one multiply per word): the frame
+ * fingerprint of SURVEY 8c / tests/golden/MANIFEST.json.  Host side, no device involved. */
+uint64_t swegl_b200_frame_hash(const uint32_t *words, size_t n_words);
 
 /* ---- multi-GPU single-frame output over peer memory ----
  * Sort-first sharding gives every GPU a row band of the viewport (viewport_desc.band_y0/y1).  Instead of rendering
@@ -230,7 +266,8 @@ int  swegl_b200_read_screen(swegl_b200_ctx *ctx, int32_t y0, int32_t y1, void *p
 int  swegl_b200_read_depth(swegl_b200_ctx *ctx, float *zbuffer);
 /* post-render vertex state of the last viewport, as the reference leaves it in
  * mesh_vertex_t: any pointer may be null. v_viewport holds pixel coordinates
- * for yes-vertices and NDC for the others (vertex_shaders.hpp:72-84). */
+ * for yes-vertices and NDC for the others (vertex_shaders.hpp:72-84).  After a band-culled view only the vertex
+ * blocks that view needed are current (the others keep older values); render an un-culled view to read them all. */
 int  swegl_b200_read_vertices(swegl_b200_ctx *ctx, float *v_world, float *v_viewport,
                               float *normal_world, uint8_t *yes);
 

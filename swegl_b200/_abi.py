@@ -14,6 +14,8 @@ MODE_TRIANGLES, MODE_TRIANGLE_STRIP, MODE_TRIANGLE_FAN = 4, 5, 6
 LIGHT_NONE, LIGHT_FLAT, LIGHT_PHONG = 0, 1, 2
 TEX_PLAIN, TEX_NEAREST, TEX_BILINEAR = 0, 1, 2
 POST_NULL, POST_DOF = 0, 1
+SHADING_EXACT, SHADING_FAST = 0, 1
+ABI_VERSION = 2
 
 
 class Primitive(C.Structure):
@@ -84,6 +86,11 @@ SYMBOLS = [
     ("swegl_b200_render_viewport_async", C.c_int, [C.c_void_p, C.POINTER(ViewportDesc), C.c_void_p, C.c_int32,
                                                    C.c_void_p, C.POINTER(C.c_uint64)]),
     ("swegl_b200_wait", C.c_int, [C.c_void_p, C.c_uint64]),
+    ("swegl_b200_set_partial_readback", C.c_int, [C.c_void_p, C.c_int]),
+    ("swegl_b200_invalidate_host_image", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("swegl_b200_readback_stats", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    ("swegl_b200_set_shading", C.c_int, [C.c_void_p, C.c_int]),
+    ("swegl_b200_frame_hash", C.c_uint64, [C.c_void_p, C.c_size_t]),
     ("swegl_b200_export_screen", C.c_int, [C.c_void_p, C.c_void_p]),
     ("swegl_b200_import_screen", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     ("swegl_b200_set_color_target", C.c_int, [C.c_void_p, C.c_void_p]),

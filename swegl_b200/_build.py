@@ -33,6 +33,20 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name, extra_flags, verbose=False):
+    """A/B builds for kernel tuning (tools/ab_variants.sh): libswegl_b200_<name>.so with extra -D flags; select it at
+    run time with SWEGL_B200_LIB=<path>.  Not part of the product build."""
+    out = os.path.join(HERE, f"libswegl_b200_{name}.so")
+    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES] + LIBS
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed building variant {name}")
+    return out
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT

@@ -35,6 +35,10 @@ struct swegl_b200_ctx {
     Tri *d_tris = nullptr; Prim *d_prims = nullptr;
     float *d_v_world = nullptr, *d_v_ndc = nullptr, *d_n_world = nullptr; uint8_t *d_yes = nullptr;
     bool opaque = true;            // every material and texel has alpha 255
+    bool fast_shading = true;      // Phong lighting within +-1 LSB (swegl_b200_set_shading); false: bit-exact
+    bool world_complete = false;   // v_world holds this frame's world positions of EVERY vertex (a culled view only fills its blocks)
+    // DoF-R source tensor maps (TMA), valid for (dof_tm_w, dof_tm_h) and the current d_tmp_color / d_depth
+    CUtensorMap dof_tm_color{}, dof_tm_depth{}; int dof_tm_w = 0, dof_tm_h = 0; bool dof_tm_ok = false; int dof_tma_policy = 1;
     // band culling (common.cuh): static tables + per-view flags; policy -1 automatic (banded views of big scenes), 0 off, 1 on
     CullTables cull{};
     ClusterBox *d_cl_box = nullptr; uint32_t *d_cl_adj_off = nullptr, *d_cl_adj = nullptr, *d_vb_adj_off = nullptr, *d_vb_adj = nullptr;
@@ -59,7 +63,21 @@ struct swegl_b200_ctx {
         uint32_t *color = nullptr; float *depth = nullptr; size_t cap = 0;
         cudaEvent_t ready = nullptr, copied = nullptr;
         uint64_t ticket = 0; int slot = 0; bool in_flight = false;
+        // the read-back itself is issued once the frame's bounding box is known on the host (issue_readback)
+        bool d2h_issued = true, partial_ok = false, dof = false;
+        void *pixels = nullptr; int32_t pitch_bytes = 0; float *zbuffer = nullptr; ViewParams vp{};
     } out[2];
+    // partial read-back: what the library last left in each host image (the caller's `pixels`), so that only the
+    // rectangle that differs from it crosses PCIe
+    struct HostImage {
+        void *pixels = nullptr; float *zbuffer = nullptr; int32_t pitch_bytes = 0;
+        int32_t vx = 0, vy = 0, vw = 0, vh = 0, band0 = 0, band1 = 0; uint32_t bg = 0;
+        int32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;     // viewport-relative rectangle outside of which the image holds `bg` (depth: 0x7F7F7F7F)
+        uint64_t age = 0;
+    };
+    std::vector<HostImage> host_images;
+    bool partial_readback = true;
+    uint64_t readback_bytes = 0, readback_frames = 0;
     cudaStream_t copy_stream = nullptr;
     uint64_t ticket_seq = 0;
     struct ViewGraph { int32_t key[15]; cudaGraphExec_t exec[2]; };
@@ -256,6 +274,7 @@ int swegl_b200_create(int device, swegl_b200_ctx **out)
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SWEGL_B200_ERR_CUDA;
     if (prop.major != 10) return SWEGL_B200_ERR_CUDA;          // sm_100a code only, no fallback
     if (cudaSetDevice(device) != cudaSuccess) return SWEGL_B200_ERR_CUDA;
+    configure_kernels();
     swegl_b200_ctx *ctx = new (std::nothrow) swegl_b200_ctx;
     if (!ctx) return SWEGL_B200_ERR_ARG;
     ctx->device = device;
@@ -273,6 +292,10 @@ int swegl_b200_create(int device, swegl_b200_ctx **out)
         ctx->span_policy = !strcmp(e, "dense") ? 1 : (!strcmp(e, "coop") ? 0 : -1);
         ctx->dense_spans = ctx->span_policy == 1;
     }
+    if (const char *e = getenv("SWEGL_B200_SHADING"))         // "exact" pins bit-exact Phong lighting, "fast" the +-1 LSB path (default)
+        ctx->fast_shading = strcmp(e, "exact") != 0;
+    if (const char *e = getenv("SWEGL_B200_DOF_TMA"))         // "0": stage the DoF windows with plain loads instead of TMA
+        ctx->dof_tma_policy = strcmp(e, "0") != 0;
     if (const char *e = getenv("SWEGL_B200_CULL"))            // "0" / "1" pin band culling off / on, default: automatic
         ctx->cull_policy = !strcmp(e, "0") ? 0 : (!strcmp(e, "1") ? 1 : -1);
     *out = ctx;
@@ -288,7 +311,7 @@ void swegl_b200_destroy(swegl_b200_ctx *ctx)
     void *ptrs[] = { ctx->d_pos, ctx->d_nrm, ctx->d_uv, ctx->d_vert_node, ctx->d_texels, ctx->d_tris, ctx->d_prims,
                      ctx->d_v_world, ctx->d_v_ndc, ctx->d_n_world, ctx->d_yes, ctx->d_block,
                      ctx->pools.edges, ctx->pools.shades, ctx->pools.spans, ctx->pools.span_shades, ctx->pools.frag_u, ctx->pools.row_slot,
-                     ctx->pools.chunks, ctx->pools.bin_head, ctx->pools.bin_used, ctx->pools.tile_stamp, ctx->pools.busy_list,
+                     ctx->pools.chunks, ctx->pools.bin_head, ctx->pools.dof_list, ctx->pools.tile_stamp, ctx->pools.busy_list,
                      ctx->pools.counters, ctx->d_screen, ctx->d_depth,
                      ctx->d_tmp_color, ctx->d_cl_box, ctx->d_cl_adj_off, ctx->d_cl_adj, ctx->d_vb_adj_off, ctx->d_vb_adj, ctx->d_cull_flags, ctx->d_cull_lists };
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -458,7 +481,8 @@ int swegl_b200_upload_scene(swegl_b200_ctx *ctx, const swegl_b200_scene_desc *sc
     for (uint32_t m = 0; m < sc->n_materials; m++) {
         texels[n_texels + m] = mat_color(sc->materials[m]);
         if (sc->materials[m].a != 255) opaque = false;
-        if (sc->materials[m].texture_idx >= (int32_t)sc->n_textures) return fail(ctx, SWEGL_B200_ERR_ARG, "upload_scene: texture_idx out of range");
+        if (sc->materials[m].texture_idx >= (int32_t)sc->n_textures || sc->materials[m].texture_idx < -1)
+            return fail(ctx, SWEGL_B200_ERR_ARG, "upload_scene: texture_idx out of range");
     }
     texels[n_texels + sc->n_materials] = mat_color(sc->default_material);
 
@@ -521,8 +545,11 @@ int swegl_b200_upload_scene(swegl_b200_ctx *ctx, const swegl_b200_scene_desc *sc
     // per-slot records: 2 slots per triangle, addressed by slot id (sparse; only live slots are touched)
     ctx->slots_cap = 2 * nt;
     CK(dalloc(ctx->pools.edges, (size_t)ctx->slots_cap)); CK(dalloc(ctx->pools.shades, (size_t)ctx->slots_cap));
-    uint32_t rows0 = nt * 8u < (1u << 20) ? (1u << 20) : nt * 8u;
-    int rc = ensure_pools(ctx, rows0, rows0 * 2, 1u << 24);
+    // initial pool sizes in 64 bit (nt < 2^29 is accepted above), clamped to what the 32-bit record indices can address
+    const uint64_t rows64 = std::max<uint64_t>((uint64_t)nt * 8u, 1u << 20);
+    const uint32_t rows0 = (uint32_t)std::min<uint64_t>(rows64, 0xFFFFFFF0ull);
+    const uint32_t chunks0 = (uint32_t)std::min<uint64_t>(rows64 * 2, 0x7FFFFFF0ull);
+    int rc = ensure_pools(ctx, rows0, chunks0, 1u << 24);
     if (rc) return rc;
 
     DeviceScene &ds = ctx->ds;
@@ -553,11 +580,12 @@ int swegl_b200_set_screen(swegl_b200_ctx *ctx, int32_t w, int32_t h)
     CK(cudaMemset(ctx->d_screen, 0, (n + SYNC_WORDS) * 4));
     ctx->sync_rank = -1;
     CK(cudaMemset(ctx->d_depth, 0x7F, n * 4));
+    CK(cudaMemset(ctx->d_tmp_color, 0, n * 4));
     size_t bins = (size_t)((w + 31) / 32 + 1) * h;
     CK(dalloc(ctx->pools.bin_head, bins));
     CK(cudaMemset(ctx->pools.bin_head, 0xFF, bins * 4));
-    CK(dalloc(ctx->pools.bin_used, bins));
-    CK(cudaMemset(ctx->pools.bin_used, 0, bins));
+    CK(dalloc(ctx->pools.dof_list, bins));              // (a DoF tile is more than one bin)
+    ctx->dof_tm_w = ctx->dof_tm_h = 0;                  // d_tmp_color / d_depth moved: the tensor maps are stale
     CK(dalloc(ctx->pools.tile_stamp, bins));            // (a tile is at least one bin)
     CK(cudaMemset(ctx->pools.tile_stamp, 0, bins * 4));
     CK(dalloc(ctx->pools.busy_list, bins));
@@ -595,6 +623,7 @@ int swegl_b200_begin_frame(swegl_b200_ctx *ctx, const swegl_b200_frame_desc *fr)
     memcpy(sl.block + ctx->off_nn, fr->node_normal, (size_t)36 * ctx->n_nodes);
     if (fr->n_point_lights) memcpy(sl.block + ctx->off_lights, fr->point_lights, (size_t)16 * fr->n_point_lights);
     ctx->frame_slot = si; ctx->frame_dirty = true; ctx->have_frame = true;
+    ctx->world_complete = false;
     return SWEGL_B200_OK;
 }
 
@@ -699,9 +728,21 @@ static ViewParams draw_params(const ViewParams &vp, bool dof)
     return d;
 }
 
+// the DoF pass stages its source windows by TMA: (re)encode the two tensor maps when the viewport size or the buffers changed
+static bool ensure_dof_maps(swegl_b200_ctx *ctx, int vw, int vh)
+{
+    if (!ctx->dof_tma_policy) return false;
+    if (ctx->dof_tm_w != vw || ctx->dof_tm_h != vh) {
+        ctx->dof_tm_ok = make_dof_tensor_maps(ctx->d_tmp_color, ctx->d_depth, vw, vh, &ctx->dof_tm_color, &ctx->dof_tm_depth);
+        ctx->dof_tm_w = vw; ctx->dof_tm_h = vh;
+    }
+    return ctx->dof_tm_ok;
+}
+
 // enqueue one viewport's work on the stream (no synchronisation: usable under stream capture): upload of the staging
 // slot (whole block when the frame data is new, else just the ViewParams), then the kernel sequence.
-static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const ViewParams &vp, swegl_b200_ctx::Slot &sl, bool with_frame,
+// with_world: v_world is not (completely) there yet for this frame -- the vertex stage computes it.
+static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const ViewParams &vp, swegl_b200_ctx::Slot &sl, bool with_frame, bool with_world,
                            bool dof, bool count_covered, bool timing, bool sync_counters, Counters *counters_out, bool synced = false)
 {
     cudaStream_t st = ctx->stream;
@@ -722,7 +763,7 @@ static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const Vie
         ds.cull_counts = ctx->cull.counts;
         launch_cull(ds, ctx->d_vp(), ctx->cull, st); launches += 2;
     }
-    launch_vertex(ds, ctx->d_vp(), ctx->pools.counters, with_frame, st); launches++;
+    launch_vertex(ds, ctx->d_vp(), ctx->pools.counters, with_world, st); launches++;
     launch_mark(ds, st); launches++;
     if (timing) cudaEventRecord(ctx->ev[1], st);
     launch_setup(ds, ctx->d_vp(), ctx->d_fp(), ctx->pools, st); launches++;
@@ -732,20 +773,26 @@ static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const Vie
     uint32_t *screen_out = ctx->color_target ? ctx->color_target : ctx->d_screen;
     uint32_t *color = dof ? ctx->d_tmp_color - ((size_t)vp.vy * vp.vw + vp.vx) : screen_out;
     const int color_pitch = dof ? vp.vw : ctx->sw;
+    uint32_t *post_dst = screen_out + (size_t)vp.vy * ctx->sw + vp.vx;     // the viewport's origin in the destination screen
+    const int out0 = out.band0 - vp.vy, out1 = out.band1 - vp.vy;           // the rows the post pass produces (the band without its halo)
+    // the first kernel that stores into rank 0's screen (with DoF-R, k_fragments already stores the constant tiles)
+    if (synced && ctx->sync_rank > 0) { launch_sync_wait_ready(ctx->d_vp(), tgt_sync, own_sync, st); launches++; }
     // asynchronous frames publish their counters from inside k_fragments; synchronous ones copy them at the end
-    if (synced && ctx->sync_rank > 0 && !dof) { launch_sync_wait_ready(ctx->d_vp(), tgt_sync, own_sync, st); launches++; }
-    if (vp.n_layers > 0)
+    if (vp.n_layers > 0) {
         launch_fragments_layers(ctx->ds, vp, ctx->d_vp(), ctx->d_fp(), ctx->pools, color, color_pitch, ctx->d_depth, count_covered,
                                 sync_counters ? nullptr : counters_out, st);
-    else
+        launches++;
+        if (dof) { launch_dof_classify(vp, ctx->d_vp(), ctx->pools, out0, out1, post_dst, ctx->sw, st); launches++; }
+    } else {
         launch_fragments(ctx->ds, vp, ctx->d_vp(), ctx->d_fp(), ctx->pools, color, color_pitch, ctx->d_depth, count_covered,
-                         sync_counters ? nullptr : counters_out, skip_bg, st);
-    launches++;
+                         sync_counters ? nullptr : counters_out, skip_bg, ctx->fast_shading, dof, out0, out1, post_dst, ctx->sw, st);
+        launches++;
+    }
     if (timing) cudaEventRecord(ctx->ev[4], st);
     if (dof) {
-        if (synced && ctx->sync_rank > 0) { launch_sync_wait_ready(ctx->d_vp(), tgt_sync, own_sync, st); launches++; }
-        launch_dof(ctx->d_vp(), ctx->pools.bin_used, vp.nbx, ctx->d_tmp_color, vp.vw, ctx->d_depth,
-                   screen_out + (size_t)vp.vy * ctx->sw + vp.vx, ctx->sw, vp.vw, vp.vh, out.band0 - vp.vy, out.band1 - vp.vy, st);
+        const bool tma = ensure_dof_maps(ctx, vp.vw, vp.vh);
+        launch_dof(vp, ctx->d_vp(), ctx->pools, &ctx->dof_tm_color, &ctx->dof_tm_depth, tma, ctx->d_tmp_color, vp.vw, ctx->d_depth,
+                   post_dst, ctx->sw, out0, out1, st);
         launches++;
     }
     if (timing) cudaEventRecord(ctx->ev[5], st);
@@ -804,12 +851,18 @@ static int render_async(swegl_b200_ctx *ctx, const ViewParams &out, bool dof)
     int rc = stage_view(ctx, vp, si, with_frame);
     if (rc) return rc;
     auto &sl = ctx->slots[si];
+    // a culled view transforms only the vertex blocks it needs (and always with the world transform); the first view
+    // that covers every vertex completes v_world for the rest of the frame
+    const bool culled = view_culled(ctx, vp);
+    const bool with_world = !ctx->world_complete;
+    const bool tma = dof && ensure_dof_maps(ctx, vp.vw, vp.vh);
     if (!ctx->graphs_enabled) {
-        issue_view(ctx, out, vp, sl, with_frame, dof, false, false, false, sl.counters, synced);
+        issue_view(ctx, out, vp, sl, with_frame, with_world, dof, false, false, false, sl.counters, synced);
     } else {
         const uint64_t tgt = (uint64_t)reinterpret_cast<uintptr_t>(ctx->color_target);
         const int32_t key[15] = { out.vx, out.vy, out.vw, out.vh, out.band0, out.band1, out.light_mode, out.tex_mode, (dof ? 1 : 0) | (out.n_layers << 1),
-                                  ctx->sw, ctx->sh, (with_frame ? 1 : 0) | (synced ? 2 + 4 * ctx->sync_rank + 256 * ctx->sync_world : 0), ctx->dense_spans ? 1 : 0,
+                                  ctx->sw, ctx->sh, (with_frame ? 1 : 0) | (synced ? 2 + 4 * ctx->sync_rank + 256 * ctx->sync_world : 0),
+                                  (ctx->dense_spans ? 1 : 0) | (with_world ? 2 : 0) | (ctx->fast_shading ? 4 : 0) | (tma ? 8 : 0),
                                   (int32_t)(tgt & 0xFFFFFFFFu), (int32_t)(tgt >> 32) };
         swegl_b200_ctx::ViewGraph *vg = nullptr;
         for (auto &g : ctx->view_graphs) if (memcmp(g.key, key, sizeof key) == 0) { vg = &g; break; }
@@ -823,7 +876,7 @@ static int render_async(swegl_b200_ctx *ctx, const ViewParams &out, bool dof)
         if (!vg->exec[si]) {
             cudaGraph_t g = nullptr;
             CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-            issue_view(ctx, out, vp, sl, with_frame, dof, false, false, false, sl.counters, synced);
+            issue_view(ctx, out, vp, sl, with_frame, with_world, dof, false, false, false, sl.counters, synced);
             CK(cudaStreamEndCapture(st, &g));
             cudaError_t e = cudaGraphInstantiate(&vg->exec[si], g, 0);
             cudaGraphDestroy(g);
@@ -832,6 +885,7 @@ static int render_async(swegl_b200_ctx *ctx, const ViewParams &out, bool dof)
         CK(cudaGraphLaunch(vg->exec[si], st));
     }
     CK(cudaGetLastError());
+    if (!culled) ctx->world_complete = true;
     return finish_view(ctx, si);
 }
 
@@ -860,8 +914,9 @@ static int render_common(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v,
         int si; bool with_frame;
         rc = stage_view(ctx, vp, si, with_frame);
         if (rc) return rc;
-        launches = issue_view(ctx, out, vp, ctx->slots[si], with_frame, dof, stats != nullptr, timing, true, ctx->h_counters);
+        launches = issue_view(ctx, out, vp, ctx->slots[si], with_frame, !ctx->world_complete, dof, stats != nullptr, timing, true, ctx->h_counters);
         CK(cudaGetLastError());
+        if (!view_culled(ctx, vp)) ctx->world_complete = true;
         rc = finish_view(ctx, si);
         if (rc) return rc;
         CK(cudaStreamSynchronize(ctx->stream));
@@ -898,6 +953,9 @@ int swegl_b200_render_viewport(swegl_b200_ctx *ctx, const swegl_b200_viewport_de
                                float *zbuffer, swegl_b200_stats *stats)
 {
     if (!pixels || pitch_bytes < 4) return fail(ctx, SWEGL_B200_ERR_ARG, "render_viewport: null pixels");
+    if (ctx && ctx->color_target)
+        return fail(ctx, SWEGL_B200_ERR_STATE, "render_viewport: a colour target is set (the finished pixels are in the target's screen, not here); "
+                                               "use render_viewport_device, or set_color_target(NULL) first");
     // the frame and its read-back are queued back to back; one synchronisation at the end.  If the frame
     // overflowed a pool (first frames of a new scene) it is redone through the synchronous path.
     int rc = render_common(ctx, v, false, stats);
@@ -905,6 +963,7 @@ int swegl_b200_render_viewport(swegl_b200_ctx *ctx, const swegl_b200_viewport_de
     const ViewParams &vp = ctx->last_vp;
     cudaStream_t st = ctx->stream;
     const int rows = vp.band1 - vp.band0;
+    for (auto &hi : ctx->host_images) if (hi.pixels == pixels) hi.pixels = nullptr;     // the whole band is rewritten: forget what was tracked
     for (int attempt = 0; attempt < 2; attempt++) {
         CK(cudaMemcpy2DAsync((char *)pixels + (size_t)vp.band0 * pitch_bytes + (size_t)vp.vx * 4, (size_t)pitch_bytes,
                              ctx->d_screen + (size_t)vp.band0 * ctx->sw + vp.vx, (size_t)ctx->sw * 4,
@@ -921,17 +980,105 @@ int swegl_b200_render_viewport(swegl_b200_ctx *ctx, const swegl_b200_viewport_de
     return rc;
 }
 
+// what DoF-R turns untouched background into (fragment.cu dof_background_value, on the host; same comparisons)
+static uint32_t post_background(const ViewParams &vp, bool dof)
+{
+    if (!dof) return 0u;
+    uint32_t zb = MAXZ_BITS; float z; memcpy(&z, &zb, 4);
+    volatile float d = vp.focal_distance - z;
+    const float t = fabsf(d);
+    uint32_t radius; bool counts;
+    if (vp.dof_const_radius >= 0) { radius = (uint32_t)vp.dof_const_radius; counts = true; }
+    else {
+        radius = (t >= vp.dof_t[0]) + (t >= vp.dof_t[1]) + (t >= vp.dof_t[2]) + (t >= vp.dof_t[3]) + (t >= vp.dof_t[4]);
+        counts = t > vp.dof_on;
+    }
+    return (radius != 0 && counts) ? 0xFF000000u : 0u;
+}
+
+// The device->host copies of an asynchronous frame.  They are issued late -- when the next frame has been queued, or in
+// swegl_b200_wait -- because by then the frame's kernels are done and k_fragments has published the bounding box of what
+// was drawn: outside that box (grown by the blur radius with DoF-R) the frame is one constant, and if the host image
+// already holds that constant there (the library remembers what it last left in each image), only the union of the old
+// and the new box has to cross PCIe.
+static int issue_readback(swegl_b200_ctx *ctx, swegl_b200_ctx::OutBuf &ob)
+{
+    if (ob.d2h_issued) return SWEGL_B200_OK;
+    const ViewParams &vp = ob.vp;
+    CK(cudaEventSynchronize(ob.ready));
+    const int row_a = vp.band0 - vp.vy, row_b = vp.band1 - vp.vy;            // viewport-relative rows of this view
+    int cx0 = 0, cx1 = vp.vw, cy0 = row_a, cy1 = row_b;                       // the rectangle to copy; default: everything
+    const auto &sl = ctx->slots[ob.slot];
+    if (ob.partial_ok && ctx->partial_readback && sl.ticket == ob.ticket && !sl.counters->overflow) {
+        const Counters &c = *sl.counters;
+        int fx0 = 0, fx1 = 0, fy0 = 0, fy1 = 0;                               // this frame's non-constant rectangle (empty: nothing drawn)
+        if (c.bb_x1 > c.bb_x0 && c.bb_y1 > c.bb_y0) {
+            const int grow = ob.dof ? 8 : 0;                                  // blur radius <= 5
+            fx0 = std::max(0, ((int)c.bb_x0 - grow) & ~3); fx1 = std::min(vp.vw, ((int)c.bb_x1 + grow + 3) & ~3);
+            fy0 = std::max(row_a, (int)c.bb_y0 - grow); fy1 = std::min(row_b, (int)c.bb_y1 + grow);
+        }
+        const uint32_t bg = post_background(vp, ob.dof);
+        swegl_b200_ctx::HostImage *hi = nullptr;
+        for (auto &h : ctx->host_images) if (h.pixels == ob.pixels) { hi = &h; break; }
+        const bool known = hi && hi->zbuffer == ob.zbuffer && hi->pitch_bytes == ob.pitch_bytes && hi->vx == vp.vx && hi->vy == vp.vy && hi->vw == vp.vw
+                        && hi->vh == vp.vh && hi->band0 == vp.band0 && hi->band1 == vp.band1 && hi->bg == bg;
+        if (known) {
+            const bool old_empty = hi->x1 <= hi->x0 || hi->y1 <= hi->y0, new_empty = fx1 <= fx0 || fy1 <= fy0;
+            if (old_empty && new_empty) { cx0 = cx1 = cy0 = cy1 = 0; }
+            else if (old_empty) { cx0 = fx0; cx1 = fx1; cy0 = fy0; cy1 = fy1; }
+            else if (new_empty) { cx0 = hi->x0; cx1 = hi->x1; cy0 = hi->y0; cy1 = hi->y1; }
+            else { cx0 = std::min(fx0, hi->x0); cx1 = std::max(fx1, hi->x1); cy0 = std::min(fy0, hi->y0); cy1 = std::max(fy1, hi->y1); }
+        }
+        if (!hi) {
+            if (ctx->host_images.size() >= 8) {                              // forget the least recently used image
+                size_t k = 0;
+                for (size_t i = 1; i < ctx->host_images.size(); i++) if (ctx->host_images[i].age < ctx->host_images[k].age) k = i;
+                ctx->host_images.erase(ctx->host_images.begin() + k);
+            }
+            ctx->host_images.emplace_back();
+            hi = &ctx->host_images.back();
+        }
+        hi->pixels = ob.pixels; hi->zbuffer = ob.zbuffer; hi->pitch_bytes = ob.pitch_bytes;
+        hi->vx = vp.vx; hi->vy = vp.vy; hi->vw = vp.vw; hi->vh = vp.vh; hi->band0 = vp.band0; hi->band1 = vp.band1; hi->bg = bg;
+        hi->x0 = fx0; hi->x1 = fx1; hi->y0 = fy0; hi->y1 = fy1;
+        hi->age = ob.ticket;
+    } else {
+        for (auto &h : ctx->host_images) if (h.pixels == ob.pixels) h.pixels = nullptr;
+    }
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ob.ready, 0));
+    if (cx1 > cx0 && cy1 > cy0) {
+        const size_t w_bytes = (size_t)(cx1 - cx0) * 4, n_rows = (size_t)(cy1 - cy0);
+        CK(cudaMemcpy2DAsync((char *)ob.pixels + (size_t)(vp.vy + cy0) * ob.pitch_bytes + (size_t)(vp.vx + cx0) * 4, (size_t)ob.pitch_bytes,
+                             ob.color + (size_t)(cy0 - row_a) * vp.vw + cx0, (size_t)vp.vw * 4, w_bytes, n_rows, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        ctx->readback_bytes += w_bytes * n_rows;
+        if (ob.zbuffer) {
+            CK(cudaMemcpy2DAsync(ob.zbuffer + (size_t)cy0 * vp.vw + cx0, (size_t)vp.vw * 4, ob.depth + (size_t)(cy0 - row_a) * vp.vw + cx0, (size_t)vp.vw * 4,
+                                 w_bytes, n_rows, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            ctx->readback_bytes += w_bytes * n_rows;
+        }
+    }
+    ctx->readback_frames++;
+    CK(cudaEventRecord(ob.copied, ctx->copy_stream));
+    ob.d2h_issued = true;
+    return SWEGL_B200_OK;
+}
+
 int swegl_b200_render_viewport_async(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v, void *pixels, int32_t pitch_bytes,
                                      float *zbuffer, uint64_t *ticket)
 {
     if (!ctx || !pixels || pitch_bytes < 4 || !ticket) return fail(ctx, SWEGL_B200_ERR_ARG, "render_viewport_async: null argument");
+    if (ctx->color_target)
+        return fail(ctx, SWEGL_B200_ERR_STATE, "render_viewport_async: a colour target is set (the finished pixels are in the target's screen, not here)");
+    auto &ob = ctx->out[ctx->ticket_seq & 1];
+    auto &prev = ctx->out[(ctx->ticket_seq & 1) ^ 1];
+    // this staging image's previous frame (two submits ago) must have its copies queued before it is overwritten
+    if (ob.in_flight && !ob.d2h_issued) { int rc0 = issue_readback(ctx, ob); if (rc0) return rc0; }
     int rc = render_common(ctx, v, false, nullptr);
     if (rc) return rc;
     const ViewParams &vp = ctx->last_vp;
     const int rows = vp.band1 - vp.band0;
     const size_t need = (size_t)vp.vw * rows;
     if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    auto &ob = ctx->out[ctx->ticket_seq & 1];
     if (!ob.ready) { CK(cudaEventCreateWithFlags(&ob.ready, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ob.copied, cudaEventDisableTiming)); }
     if (ob.cap < need) {
         if (ob.in_flight) CK(cudaEventSynchronize(ob.copied));
@@ -946,17 +1093,16 @@ int swegl_b200_render_viewport_async(swegl_b200_ctx *ctx, const swegl_b200_viewp
     if (zbuffer)
         CK(cudaMemcpyAsync(ob.depth, ctx->d_depth + (size_t)(vp.band0 - vp.vy) * vp.vw, need * 4, cudaMemcpyDeviceToDevice, st));
     CK(cudaEventRecord(ob.ready, st));
-    CK(cudaStreamWaitEvent(ctx->copy_stream, ob.ready, 0));
-    CK(cudaMemcpy2DAsync((char *)pixels + (size_t)vp.band0 * pitch_bytes + (size_t)vp.vx * 4, (size_t)pitch_bytes,
-                         ob.color, (size_t)vp.vw * 4, (size_t)vp.vw * 4, (size_t)rows, cudaMemcpyDeviceToHost, ctx->copy_stream));
-    if (zbuffer)
-        CK(cudaMemcpyAsync(zbuffer + (size_t)(vp.band0 - vp.vy) * vp.vw, ob.depth, need * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
-    CK(cudaEventRecord(ob.copied, ctx->copy_stream));
-    ob.in_flight = true;
+    ob.in_flight = true; ob.d2h_issued = false;
+    ob.pixels = pixels; ob.pitch_bytes = pitch_bytes; ob.zbuffer = zbuffer; ob.vp = vp; ob.dof = ctx->last_dof;
+    ob.partial_ok = vp.n_layers == 0;                                    // (the layer kernel does not publish a bounding box)
     ob.slot = ctx->last_slot;
     ob.ticket = ++ctx->ticket_seq;
     ctx->slots[ob.slot].ticket = ob.ticket;
     *ticket = ob.ticket;
+    // the frame before this one: its kernels are done or about to be, and this frame is already queued behind them, so
+    // waiting for it here does not idle the GPU
+    if (prev.in_flight && !prev.d2h_issued) { rc = issue_readback(ctx, prev); if (rc) return rc; }
     return SWEGL_B200_OK;
 }
 
@@ -966,7 +1112,12 @@ int swegl_b200_wait(swegl_b200_ctx *ctx, uint64_t ticket)
     CK(cudaSetDevice(ctx->device));
     auto &ob = ctx->out[(ticket - 1) & 1];
     // a later frame through the same staging image implies this one is done (same stream order)
-    if (ob.in_flight) { CK(cudaEventSynchronize(ob.copied)); ob.in_flight = false; }
+    if (ob.in_flight) {
+        int rc0 = issue_readback(ctx, ob);
+        if (rc0) return rc0;
+        CK(cudaEventSynchronize(ob.copied));
+        ob.in_flight = false;
+    }
     // the frame's kernels are complete.  If its staging slot was not reused since, its pool counters are still
     // unexamined: do that now; if it was, acquire_slot() already did and noted a failure
     if (ob.ticket == ticket && ctx->slots[ob.slot].ticket == ticket) {
@@ -976,10 +1127,49 @@ int swegl_b200_wait(swegl_b200_ctx *ctx, uint64_t ticket)
     for (size_t i = 0; i < ctx->failed_tickets.size(); i++)
         if (ctx->failed_tickets[i] == ticket) {
             ctx->failed_tickets.erase(ctx->failed_tickets.begin() + i);
-            return fail(ctx, SWEGL_B200_ERR_CAPACITY, "the frame overflowed the span/chunk/fragment pools (now enlarged): submit it again");
+            for (auto &h : ctx->host_images) h.pixels = nullptr;        // an incomplete frame went into a host image
+            return fail(ctx, SWEGL_B200_ERR_CAPACITY, "the frame overflowed the span/chunk/fragment pools (now enlarged): submit it again "
+                                                      "(begin_frame with its data, then render_viewport_async)");
         }
     ctx->err.clear();
     return SWEGL_B200_OK;
+}
+
+int swegl_b200_set_partial_readback(swegl_b200_ctx *ctx, int enabled)
+{
+    if (!ctx) return SWEGL_B200_ERR_ARG;
+    ctx->partial_readback = enabled != 0;
+    ctx->host_images.clear();
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_invalidate_host_image(swegl_b200_ctx *ctx, const void *pixels)
+{
+    if (!ctx) return SWEGL_B200_ERR_ARG;
+    for (auto &h : ctx->host_images) if (!pixels || h.pixels == pixels) h.pixels = nullptr;
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_readback_stats(swegl_b200_ctx *ctx, uint64_t out[2], int reset)
+{
+    if (!ctx || !out) return SWEGL_B200_ERR_ARG;
+    out[0] = ctx->readback_bytes; out[1] = ctx->readback_frames;
+    if (reset) ctx->readback_bytes = ctx->readback_frames = 0;
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_set_shading(swegl_b200_ctx *ctx, int mode)
+{
+    if (!ctx || mode < 0 || mode > 1) return fail(ctx, SWEGL_B200_ERR_ARG, "set_shading: mode must be SWEGL_B200_SHADING_EXACT or SWEGL_B200_SHADING_FAST");
+    ctx->fast_shading = mode == SWEGL_B200_SHADING_FAST;        // (part of the graph key: no re-capture needed)
+    return SWEGL_B200_OK;
+}
+
+uint64_t swegl_b200_frame_hash(const uint32_t *words, size_t n_words)
+{
+    uint64_t h = 1469598103934665603ull;                        // FNV-1a 64 over 32-bit words
+    for (size_t i = 0; i < n_words; i++) { h ^= words[i]; h *= 1099511628211ull; }
+    return h;
 }
 
 int swegl_b200_set_color_target(swegl_b200_ctx *ctx, void *device_screen)

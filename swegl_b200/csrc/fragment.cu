@@ -9,6 +9,7 @@
 // (deferred), and the bin is written once as a 128-byte colour segment and a 128-byte depth
 // segment; background pixels get the clear values (viewport.cpp:88-113), so there is no clear pass
 // and no atomics on the framebuffer.
+#include <cstddef>
 #include "common.cuh"
 
 namespace sb {
@@ -135,15 +136,9 @@ SB_DEV int shade_light(const SpanShade *ss, float flat_light, const ViewParams &
     return f2i(fmul(65536.0f, fadd(fadd(fp.ambient, sun), dyn)));
 }
 
-template <int LIGHT, int TEX>
-SB_DEV uint32_t shade(const SpanShade *ss, float flat_light, const Prim &pr, const uint32_t *texels, const ViewParams &vp,
-                      const FrameParams &fp, float u)
+// pixel_shader_light_and_texture::shade, pixel_shaders.hpp:159-178: the texture colour scaled by the light
+SB_DEV uint32_t combine_light(uint32_t c, int li)
 {
-    const TexFetch tf = tex_fetch<TEX>(ss, pr, texels, u);                  // texel loads issued ...
-    if (LIGHT == SWEGL_B200_LIGHT_NONE) return tex_filter<TEX>(tf);
-    // pixel_shader_light_and_texture::shade, pixel_shaders.hpp:159-178
-    int li = shade_light<LIGHT>(ss, flat_light, vp, fp, u);                 // ... in flight under the lighting arithmetic ...
-    uint32_t c = tex_filter<TEX>(tf);                                       // ... consumed here
     float light = fmul(__int2float_rn(li), 1.0f / 65536.0f);               // (float)(li / 65536.0)
     uint32_t b = c & 0xFF, g = (c >> 8) & 0xFF, r = (c >> 16) & 0xFF;
     if (light < 1.0f) {
@@ -168,6 +163,92 @@ SB_DEV uint32_t shade(const SpanShade *ss, float flat_light, const Prim &pr, con
     return (c & 0xFF000000u) | (r << 16) | (g << 8) | b;
 }
 
+template <int LIGHT, int TEX>
+SB_DEV uint32_t shade(const SpanShade *ss, float flat_light, const Prim &pr, const uint32_t *texels, const ViewParams &vp,
+                      const FrameParams &fp, float u)
+{
+    const TexFetch tf = tex_fetch<TEX>(ss, pr, texels, u);                  // texel loads issued ...
+    if (LIGHT == SWEGL_B200_LIGHT_NONE) return tex_filter<TEX>(tf);
+    int li = shade_light<LIGHT>(ss, flat_light, vp, fp, u);                 // ... in flight under the lighting arithmetic ...
+    return combine_light(tex_filter<TEX>(tf), li);                          // ... consumed here
+}
+
+
+// ----------------------------------------------------------------------------------------
+// Phong lighting inside the colour tolerance (+-1 LSB per 8-bit channel, alpha exact; coverage and depth stay
+// bit-exact -- they never pass through here).  The exact path above spends ~650 of its ~1000 instructions per pixel on
+// IEEE-correct divisions, square roots and an fp64 pow in the reference's unfused evaluation order.  This version uses
+// FMA, rsqrt.approx / rcp.approx and five fp32 squarings; its relative error on the light sum is ~1e-6, which moves a
+// truncated colour channel by at most one step -- EXCEPT next to the shader's own discontinuities, where a tiny
+// difference flips a branch with a visible jump (pixel_shaders.cpp:173-203, pixel_shaders.hpp:159-178):
+//   diffuse < 0.05 (the light is dropped),  alignment < 0 (dropped, its specular term with it),  degenerate vectors,
+//   light == 1 (dark branch truncates c*light -> c-1, bright branch gives c+1),  light < 0 or 65536*light beyond int.
+// A pixel within a guard band of any of these reports `false` and is shaded by the exact path instead.  The texture
+// filter is always the exact one (texel selection is discontinuous, and an exact `c` keeps the bound at 1 step).
+// ----------------------------------------------------------------------------------------
+SB_DEV float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+SB_DEV float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+SB_DEV bool phong_light_fast(const SpanShade *ss, const ViewParams &vp, const FrameParams &fp, float u, int &li)
+{
+    const float4 *sq = reinterpret_cast<const float4 *>(ss);
+    const float4 q0 = sq[0];          // v.xyz, vdir.x
+    const float4 q1 = sq[1];        // vdir.yz, n.xy
+    const float4 q2 = sq[2];        // n.z, ndir.xyz
+    const float cx = __fmaf_rn(q0.w, u, q0.x), cy = __fmaf_rn(q1.x, u, q0.y), cz = __fmaf_rn(q1.y, u, q0.z);
+    float nx = __fmaf_rn(q2.y, u, q1.z), ny = __fmaf_rn(q2.z, u, q1.w), nz = __fmaf_rn(q2.w, u, q2.x);
+    const float nn = __fmaf_rn(nx, nx, __fmaf_rn(ny, ny, nz * nz));
+    const float ni = rsqrt_fast(nn);
+    nx *= ni; ny *= ni; nz *= ni;
+    float ex = vp.cam[0] - cx, ey = vp.cam[1] - cy, ez = vp.cam[2] - cz;
+    const float ee = __fmaf_rn(ex, ex, __fmaf_rn(ey, ey, ez * ez));
+    const float ei = rsqrt_fast(ee);
+    ex *= ei; ey *= ei; ez *= ei;
+    bool ok = nn > 1e-30f && ee > 1e-30f;                                   // (NaN compares false)
+    float sun = -__fmaf_rn(nx, fp.sun[0], __fmaf_rn(ny, fp.sun[1], nz * fp.sun[2]));
+    sun = sun < 0.0f ? 0.0f : sun * fp.sun_intensity;
+    float dyn = 0.0f;
+    for (uint32_t i = 0; i < fp.n_lights; i++) {
+        const float4 L = __ldg(&fp.lights[i]);
+        float lx = cx - L.x, ly = cy - L.y, lz = cz - L.z;
+        const float d2 = __fmaf_rn(lx, lx, __fmaf_rn(ly, ly, lz * lz));
+        const float inv = rcp_fast(d2);
+        float diffuse = L.w * inv;
+        ok = ok && d2 > 1e-30f && fabsf(diffuse - 0.05f) > 2e-6f;
+        if (!(diffuse >= 0.05f)) continue;
+        const float il = rsqrt_fast(d2);
+        lx *= il; ly *= il; lz *= il;
+        const float al = -__fmaf_rn(nx, lx, __fmaf_rn(ny, ly, nz * lz));
+        ok = ok && fabsf(al) > 2e-5f;
+        if (!(al > 0.0f)) continue;
+        diffuse *= al;
+        const float a2 = al + al;
+        const float rx = __fmaf_rn(nx, a2, lx), ry = __fmaf_rn(ny, a2, ly), rz = __fmaf_rn(nz, a2, lz);
+        float sp = __fmaf_rn(rx, ex, __fmaf_rn(ry, ey, rz * ez));
+        if (sp > 0.0f) {
+            sp *= sp; sp *= sp; sp *= sp; sp *= sp; sp *= sp;               // ^32
+            dyn += __fmaf_rn(sp * 16.0f, inv, diffuse);
+        } else {
+            dyn += diffuse;
+        }
+    }
+    const float total = fp.ambient + sun + dyn;
+    ok = ok && total >= 0.0f && total < 16384.0f && fabsf(total - 1.0f) > 2e-4f;
+    li = __float2int_rz(65536.0f * total);
+    return ok;
+}
+
+// the exact shader, out of line: the fast kernels call it for the few pixels next to a discontinuity
+template <int LIGHT, int TEX>
+static __device__ __noinline__ uint32_t shade_exact_call(const SpanShade *ss, float flat_light, uint4 bind, const uint32_t *texels,
+                                                         const ViewParams *vp, const FrameParams *fp, float u)
+{
+    Prim pr;
+    pr.color = bind.x; pr.tex_off = bind.y; pr.tw = (int32_t)bind.z; pr.th = (int32_t)bind.w;
+    pr.tw_mask = (pr.tw & (pr.tw - 1)) == 0 ? pr.tw - 1 : -1;
+    pr.th_mask = (pr.th & (pr.th - 1)) == 0 ? pr.th - 1 : -1;
+    return shade<LIGHT, TEX>(ss, flat_light, pr, texels, *vp, *fp, u);
+}
 
 // chunks of a bin whose records are fetched up front, all bins of the stretch at once; longer lists continue serially
 #ifndef FRAG_LIST_CAP_V
@@ -185,13 +266,16 @@ struct FragWarp {
     uint8_t idx[FRAG_STRETCH * 32];     // compacted list of covered pixels
 };
 
-// One warp owns a stretch of FRAG_STRETCH bins (256 pixels) of one scanline:
-//   1. one load fetches the bin heads (and resets them for the next frame),
-//   2. empty bins are cleared in bulk with 128-bit stores (colour 0, depth 0x7F7F7F7F: viewport.cpp:88-113),
-//   3. each non-empty bin is resolved with lane = pixel as described at the top of this file.
 // the part of ViewParams that is fixed for a captured frame graph (rectangle, band), passed by value so that the
 // first loads of the kernel do not wait for the parameter block
-struct FragGeom { int32_t vx, vy, vw, band0, band1, nbx, ntx, n_tiles, skip_bg; };   // skip_bg: background colour is not stored (FrameSync)
+struct FragGeom {
+    int32_t vx, vy, vw, band0, band1, nbx, ntx, nty, n_tiles;
+    int32_t skip_bg;                    // background colour is not stored (FrameSync: rank 0 cleared it already)
+    // when DoF-R follows (k_dof), k_fragments also decides which DoF output tiles are constant, and fills those
+    int32_t dof, ndx, n_dof;            // DoF tiles per row / in total (grid anchored at band0, like the fragment tiles)
+    int32_t out0, out1;                 // viewport-relative rows [out0, out1) the post pass outputs
+    int32_t dof_pitch;                  // pitch of the post pass's destination
+};
 
 // clear values (viewport.cpp:88-113) for one row of a tile: colour 0, depth 0x7F7F7F7F
 SB_DEV void clear_tile_row(uint32_t *crow, float *drow, int px_left, int lane, bool with_color)
@@ -211,192 +295,314 @@ SB_DEV void clear_tile_row(uint32_t *crow, float *drow, int px_left, int lane, b
     }
 }
 
-// Grid: n_tiles "busy" CTAs followed by ceil(n_tiles / FRAG_ROWS) "clear" CTAs.
-//  * busy CTA i works on busy_list[i] (the tiles k_spans put chunks into, so all the expensive tiles start at once
-//    at the head of the grid instead of wherever the scene happens to sit on the screen); i >= n_busy exits;
-//  * clear CTA j: warp w takes tile j * FRAG_ROWS + w and, unless it was busy, fills it with the clear values
-//    (16 independent 128-bit stores per lane; no bin heads are read for tiles nothing was drawn into).
+// ---- DoF-R tile classification (one warp per DoF output tile d) ----
+// The post pass reads, for output tile (i, j), the source window [64i-8, 64i+72) x [32j-5, 32j+36) (rows relative to the
+// first drawn row).  If no fragment tile under that window received a chunk this frame (tile_stamp, written by k_spans),
+// the whole window is background and the output is one constant: it is stored here, at full store rate, and k_dof never
+// sees the tile.  Otherwise the tile goes on k_dof's work list.
+struct DofClass { uint32_t radius; bool counts; };
+SB_DEV DofClass dof_classify(const ViewParams &vp, float z);
+SB_DEV uint32_t dof_background_value(const ViewParams &vp);
+
+SB_DEV void dof_tile_duty(const Pools &pl, const FragGeom &g, uint32_t stamp, uint32_t fill, uint32_t *__restrict__ dof_dst, uint32_t d, int lane)
+{
+    const int j = (int)d / g.ndx, i = (int)d - j * g.ndx;
+    const int c0 = max(0, (i * DOF_OW - 8) >> 7), c1 = min(g.ntx - 1, (i * DOF_OW + DOF_OW + 7) >> 7);       // fragment tile columns under the window
+    constexpr int RPT = DOF_OH / FRAG_ROWS;                                                                  // fragment tile rows per DoF tile row
+    const int r0 = max(0, j * RPT - 1), r1 = min(g.nty - 1, j * RPT + RPT);
+    bool busy = false;
+    {
+        const int rr = r0 + (lane >> 1), cc = c0 + (lane & 1);
+        if (rr <= r1 && cc <= c1) busy = pl.tile_stamp[rr * g.ntx + cc] == stamp;
+    }
+    static_assert(2 * (DOF_OH / FRAG_ROWS + 2) <= 32, "one lane per fragment tile under a DoF window");
+    if (__any_sync(0xFFFFFFFFu, busy)) {
+        if (lane == 0) pl.dof_list[atomicAdd(&pl.counters->n_dof_busy, 1u)] = d;
+        return;
+    }
+    const int anchor = g.band0 - g.vy;
+    const int x0 = i * DOF_OW, wd = min(DOF_OW, g.vw - x0);
+    const int ya = max(anchor + j * DOF_OH, g.out0), yb = min(anchor + (j + 1) * DOF_OH, g.out1);
+    if (yb <= ya) return;
+    const bool vec = (reinterpret_cast<uintptr_t>(dof_dst) & 15) == 0 && (g.dof_pitch & 3) == 0 && wd == DOF_OW;
+    if (vec) {
+        const uint4 v4 = make_uint4(fill, fill, fill, fill);
+        for (int k = lane; k < (yb - ya) * (DOF_OW / 4); k += 32)
+            *reinterpret_cast<uint4 *>(dof_dst + (size_t)(ya + k / (DOF_OW / 4)) * g.dof_pitch + x0 + (k % (DOF_OW / 4)) * 4) = v4;
+    } else {
+        for (int k = lane; k < (yb - ya) * wd; k += 32)
+            dof_dst[(size_t)(ya + k / wd) * g.dof_pitch + x0 + k % wd] = fill;
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// k_fragments: ONE wave of persistent CTAs; every warp pulls work items from a queue (Counters::frag_queue) until it is
+// empty.  Item q bundles up to three independent duties, so that the streaming stores of the first two drain to
+// L2 / HBM underneath the arithmetic of the third:
+//   * clear duty   q < n_tiles        : fragment tile q (8 rows x 128 px), unless k_spans put something into it
+//                                       (tile_stamp), gets the clear values (viewport.cpp:88-113) -- depth always,
+//                                       colour unless the frame protocol cleared it already, or, with DoF-R behind
+//                                       it, only when a DoF window that will really be computed can see the tile;
+//   * DoF duty     q < n_dof          : DoF output tile q is classified (dof_tile_duty) -- constant tiles are stored
+//                                       from here, the others go on k_dof's list;
+//   * busy duty    q < 8 * n_busy     : row (q % 8) of busy tile busy_list[q / 8]: depth resolve, deferred shading of
+//                                       the winners, one 128-byte colour / depth store per bin (see the file header).
+// The unit is a warp, not a CTA: a 4K frame has ~1 500 busy tiles for 1 184 resident CTAs, and a CTA-sized unit
+// leaves the kernel's end to the SMs that drew the heaviest tiles; 12 000 row items balance within a few percent.
+// The next index is fetched while the current item is processed.
+// ----------------------------------------------------------------------------------------
 #ifndef FRAG_MINB
-#define FRAG_MINB 8         // 32 registers: all 64 warps of an SM resident; measured faster than 48 registers / 40 warps
+#define FRAG_MINB 8         // 32 registers: all 64 warps of an SM resident
 #endif
-template <int LIGHT, int TEX>
+#ifndef FRAG_CTAS_PER_SM
+#define FRAG_CTAS_PER_SM FRAG_MINB
+#endif
+template <int LIGHT, int TEX, int FAST>
 __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s, const ViewParams *__restrict__ vpp,
                                                         const FrameParams *__restrict__ fpp, Pools pl, FragGeom g,
                                                         uint32_t *__restrict__ color, int color_pitch,
-                                                        float *__restrict__ depth, int count_covered,
+                                                        float *__restrict__ depth, uint32_t *__restrict__ dof_dst, int count_covered,
                                                         Counters *__restrict__ h_counters_out)
 {
-    static_assert(FRAG_ROWS * FRAG_STRETCH <= 32, "one warp-wide load fetches the bin heads of the whole CTA tile");
-    __shared__ ViewParams vp;                   // per-frame constants, staged only by tiles that shade something
+    static_assert(FAST == 0 || LIGHT == SWEGL_B200_LIGHT_PHONG, "only Phong lighting has a fast variant");
+    __shared__ ViewParams vp;
     __shared__ FrameParams fp;
     __shared__ FragWarp fwarp[FRAG_ROWS];
-    __shared__ int32_t s_head[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int band_rows = g.band1 - g.band0;
+    const int band_rows = g.band1 - g.band0, anchor = g.band0 - g.vy;
     pdl_trigger();
-    pdl_wait();                                                             // k_spans' bins, chunks, fragment stream, tile list
-    if ((int)blockIdx.x >= g.n_tiles) {
-        // ---- clear CTA ----
-        const int t = ((int)blockIdx.x - g.n_tiles) * FRAG_ROWS + warp;
-        if (t >= g.n_tiles) return;
-        if (pl.tile_stamp[t] == vpp->stamp) return;                         // a busy CTA owns this tile
-        const int ty = t / g.ntx, tx = t - ty * g.ntx;
-        const int row0 = (g.band0 - g.vy) + ty * FRAG_ROWS, bx0 = tx * FRAG_STRETCH;
-        const int rows_here = min(FRAG_ROWS, band_rows - ty * FRAG_ROWS);
-        const int px_left = g.vw - (bx0 << 5);
-        for (int r = 0; r < rows_here; r++)
-            clear_tile_row(color + (size_t)(g.vy + row0 + r) * color_pitch + g.vx + (bx0 << 5),
-                           depth + (size_t)(row0 + r) * g.vw + (bx0 << 5), px_left, lane, !g.skip_bg);
-        {   // occupancy map for the DoF pass
-            const int r = lane / FRAG_STRETCH, b = lane % FRAG_STRETCH;
-            if (r < rows_here && bx0 + b < g.nbx) pl.bin_used[(size_t)(row0 + r) * g.nbx + bx0 + b] = 0;
-        }
-        return;
-    }
-    // ---- busy CTA ----
-    // k_setup / k_spans are done: publish their counters (pool demand, overflow flags) to the pinned slot the host
-    // polls, instead of a D2H copy node at the end of the graph.  (n_covered is only final after this kernel; the
-    // synchronous stats path copies the counters itself.)
-    if (h_counters_out && blockIdx.x == 0 && threadIdx.x < sizeof(Counters) / 4)
-        reinterpret_cast<uint32_t *>(h_counters_out)[threadIdx.x] = reinterpret_cast<const uint32_t *>(pl.counters)[threadIdx.x];
-    if (blockIdx.x >= pl.counters->n_busy) return;
-    const int t = (int)pl.busy_list[blockIdx.x];
-    const int ty = t / g.ntx, tx = t - ty * g.ntx;
-    const int row0 = (g.band0 - g.vy) + ty * FRAG_ROWS;                     // viewport-relative first row of the tile
-    const int rows_here = min(FRAG_ROWS, band_rows - ty * FRAG_ROWS);
-    const int bx0 = tx * FRAG_STRETCH;
-    const int nb = min(FRAG_STRETCH, g.nbx - bx0);
-    const int px_left = g.vw - (bx0 << 5);                                  // pixels from the stretch start to the row end
-    const uint64_t KEY_INIT = (uint64_t)MAXZ_BITS << 32;
-    if (warp == 0) {        // lane -> (row, bin) of the tile: fetch and reset the heads, leave the occupancy map for the DoF pass
-        const int r = lane / FRAG_STRETCH, b = lane % FRAG_STRETCH;
-        int32_t h = -1;
-        if (r < rows_here && b < nb) {
-            const size_t bi = (size_t)(row0 + r) * g.nbx + bx0 + b;
-            h = pl.bin_head[bi];
-            if (h >= 0) pl.bin_head[bi] = -1;
-            pl.bin_used[bi] = h >= 0;
-        }
-        s_head[lane] = h;
-    }
+    // the parameter block is written by the copy at the head of the chain, not by a kernel: readable before the wait
     for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += FRAG_TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
     for (int w = threadIdx.x; w < (int)(sizeof(FrameParams) / 4); w += FRAG_TPB) reinterpret_cast<uint32_t *>(&fp)[w] = reinterpret_cast<const uint32_t *>(fpp)[w];
     __syncthreads();
-    if (warp >= rows_here) return;
-    const int row = row0 + warp;
-    const int y = g.vy + row;
-    const int32_t head = lane < FRAG_STRETCH ? s_head[warp * FRAG_STRETCH + lane] : -1;
-    unsigned mask = __ballot_sync(0xFFFFFFFFu, head >= 0);
+    pdl_wait();                                                             // k_spans' bins, chunks, fragment stream, tile list
+    Counters *const cn = pl.counters;
+    const uint32_t n_busy = cn->n_busy;
+    const uint32_t stamp = vp.stamp;
+    // first index of this warp; the queue counter was zeroed by k_vertex at the head of the chain
+    uint32_t q_raw = 0;
+    if (lane == 0) q_raw = atomicAdd(&cn->frag_queue, 1u);
 
-    uint32_t *crow = color + (size_t)y * color_pitch + g.vx + (bx0 << 5);
-    float *drow = depth + (size_t)row * g.vw + (bx0 << 5);
-    const bool aligned = ((reinterpret_cast<uintptr_t>(crow) | reinterpret_cast<uintptr_t>(drow)) & 15) == 0;
-    // ---- empty bins ----
-    if (mask != 0xFFFFFFFFu) {
-        const float maxz = __uint_as_float(MAXZ_BITS);
-        for (int i = lane; i < nb * 8; i += 32) {
-            const int b = i >> 3, px = (b << 5) + ((i & 7) << 2);
-            if ((mask >> b) & 1u) continue;
-            if (aligned && px + 4 <= px_left) {
-                if (!g.skip_bg) *reinterpret_cast<uint4 *>(crow + px) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<float4 *>(drow + px) = make_float4(maxz, maxz, maxz, maxz);
-            } else {
-                for (int k = 0; k < 4; k++)
-                    if (px + k < px_left) { if (!g.skip_bg) crow[px + k] = 0; drow[px + k] = maxz; }
-            }
+    if (blockIdx.x == 0 && warp == 0) {
+        // bounding box of what was drawn (for the host's partial read-back), and k_setup / k_spans' counters (pool demand,
+        // overflow flags) published to the pinned slot the host polls -- instead of a D2H copy node at the end of the graph.
+        // (n_covered is only final after this kernel; the synchronous stats path copies the counters itself.)
+        uint32_t tx0 = 0xFFFFFFFFu, ty0 = 0xFFFFFFFFu, tx1 = 0, ty1 = 0;
+        for (uint32_t i = lane; i < n_busy; i += 32) {
+            const uint32_t t = pl.busy_list[i], ty = t / (uint32_t)g.ntx, tx = t - ty * (uint32_t)g.ntx;
+            tx0 = min(tx0, tx); tx1 = max(tx1, tx + 1); ty0 = min(ty0, ty); ty1 = max(ty1, ty + 1);
+        }
+        #pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            tx0 = min(tx0, __shfl_xor_sync(0xFFFFFFFFu, tx0, o)); ty0 = min(ty0, __shfl_xor_sync(0xFFFFFFFFu, ty0, o));
+            tx1 = max(tx1, __shfl_xor_sync(0xFFFFFFFFu, tx1, o)); ty1 = max(ty1, __shfl_xor_sync(0xFFFFFFFFu, ty1, o));
+        }
+        uint32_t b0 = 0u, b1 = 0u, b2 = 0u, b3 = 0u;
+        if (n_busy) {
+            b0 = tx0 * (FRAG_STRETCH * 32); b1 = (uint32_t)anchor + ty0 * FRAG_ROWS;
+            b2 = min((uint32_t)g.vw, tx1 * (FRAG_STRETCH * 32)); b3 = min((uint32_t)(anchor + band_rows), (uint32_t)anchor + ty1 * FRAG_ROWS);
+        }
+        if (lane == 0) { cn->bb_x0 = b0; cn->bb_y0 = b1; cn->bb_x1 = b2; cn->bb_y1 = b3; }
+        if (h_counters_out && lane < (int)(sizeof(Counters) / 4)) {
+            constexpr int BB = offsetof(Counters, bb_x0) / 4;
+            uint32_t v = reinterpret_cast<const uint32_t *>(cn)[lane];
+            v = lane == BB ? b0 : (lane == BB + 1 ? b1 : (lane == BB + 2 ? b2 : (lane == BB + 3 ? b3 : v)));
+            reinterpret_cast<uint32_t *>(h_counters_out)[lane] = v;
         }
     }
-    // ---- non-empty bins, pass 1: depth resolve.
-    //  a. the first lanes walk one bin list each (FRAG_STRETCH pointer chases side by side instead of one after the
-    //     other) and leave the chunk records in shared memory;
-    //  b. lane = pixel: per bin, the nearest fragment of every pixel is kept in registers.  Depth is written at once,
-    //     and the winners of the whole stretch are queued in shared memory so that shading (pass 2) runs on dense
-    //     batches of 32 covered pixels. ----
-    FragWarp &fw = fwarp[threadIdx.x >> 5];
-    if (lane < FRAG_STRETCH) {
-        int n = 0;
-        int32_t c = head;
-        while (c >= 0 && n < FRAG_LIST_CAP) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(&pl.chunks[c]);
-            const uint4 r0 = src[0], r1 = src[1];
-            fw.rec[2 * (lane * FRAG_LIST_CAP + n)] = r0; fw.rec[2 * (lane * FRAG_LIST_CAP + n) + 1] = r1;
-            n++;
-            c = (int32_t)r1.z;                                                  // Chunk::next
-        }
-        fw.cnt[lane] = n; fw.cursor[lane] = c;
-    }
-    __syncwarp();
+
+    const uint32_t n_items = n_busy * FRAG_ROWS;
+    uint32_t n_total = max(n_items, (uint32_t)g.n_tiles);
+    if (g.dof) n_total = max(n_total, (uint32_t)g.n_dof);
+    const uint32_t dof_fill = g.dof ? dof_background_value(vp) : 0u;
+    const uint64_t KEY_INIT = (uint64_t)MAXZ_BITS << 32;
     const unsigned lt = (1u << lane) - 1u;
-    uint32_t n_hit = 0;
-    const unsigned used = mask;
-    while (mask) {
-        const int b = __ffs(mask) - 1;
-        mask &= mask - 1;
-        uint64_t best = KEY_INIT;
-        float best_u = 0.f;
-        uint32_t best_span = 0xFFFFFFFFu;
-        const int n = fw.cnt[b];
-        const uint4 *rec = &fw.rec[2 * b * FRAG_LIST_CAP];
-        #pragma unroll 2
-        for (int k = 0; k < n; k++) {
-            const uint4 r0 = rec[2 * k];                                        // frag0, xs_xe, v0, v1
-            const unsigned xs = r0.y & 0xFFu, wd = (r0.y >> 8) - xs;
-            if ((unsigned)lane - xs < wd) {
-                const float u = pl.frag_u[r0.x + (uint32_t)lane];               // qpixel.ualpha, replayed by k_spans
-                const float z = fadd(__uint_as_float(r0.z), fmul(__uint_as_float(r0.w), u));   // value(0), renderer.cpp:488
-                if (z >= NEAR_Z) {                                              // renderer.cpp:489-492
-                    const uint2 r1 = *reinterpret_cast<const uint2 *>(&rec[2 * k + 1]);       // slot, span
-                    const uint64_t key = ((uint64_t)__float_as_uint(z) << 32) | r1.x;
-                    if (key < best) { best = key; best_u = u; best_span = r1.y; }
+    FragWarp &fw = fwarp[warp];
+
+    uint32_t q = __shfl_sync(0xFFFFFFFFu, q_raw, 0);
+    while (q < n_total) {
+        if (lane == 0) q_raw = atomicAdd(&cn->frag_queue, 1u);              // the next item's index travels while this one is worked on
+
+        // ---- clear duty ----
+        if (q < (uint32_t)g.n_tiles && pl.tile_stamp[q] != stamp) {
+            const int ty = (int)q / g.ntx, tx = (int)q - ty * g.ntx;
+            bool with_color = !g.skip_bg;
+            if (g.dof) {
+                // tmp colour is only ever read through the window of a DoF tile that is computed, i.e. one with a busy
+                // fragment tile under its window: two tiles under one window are at most 1 column and 5 rows apart
+                constexpr int NDY = DOF_OH / FRAG_ROWS + 1;                  // 5
+                bool near = false;
+                for (int k = lane; k < 3 * (2 * NDY + 1); k += 32) {
+                    const int yy = ty + k / 3 - NDY, xx = tx + k % 3 - 1;
+                    if (yy >= 0 && yy < g.nty && xx >= 0 && xx < g.ntx) near = near || pl.tile_stamp[yy * g.ntx + xx] == stamp;
+                }
+                with_color = __any_sync(0xFFFFFFFFu, near);
+            }
+            const int row0 = anchor + ty * FRAG_ROWS, bx0 = tx * FRAG_STRETCH;
+            const int rows_here = min(FRAG_ROWS, band_rows - ty * FRAG_ROWS);
+            const int px_left = g.vw - (bx0 << 5);
+            for (int r = 0; r < rows_here; r++)
+                clear_tile_row(color + (size_t)(g.vy + row0 + r) * color_pitch + g.vx + (bx0 << 5),
+                               depth + (size_t)(row0 + r) * g.vw + (bx0 << 5), px_left, lane, with_color);
+        }
+        // ---- DoF duty ----
+        if (g.dof && q < (uint32_t)g.n_dof) dof_tile_duty(pl, g, stamp, dof_fill, dof_dst, q, lane);
+
+        // ---- busy duty ----
+        if (q < n_items) do {
+            const int t = (int)pl.busy_list[q / FRAG_ROWS], r = (int)(q % FRAG_ROWS);
+            const int ty = t / g.ntx, tx = t - ty * g.ntx;
+            if (r >= min(FRAG_ROWS, band_rows - ty * FRAG_ROWS)) break;
+            const int row = anchor + ty * FRAG_ROWS + r;                    // viewport-relative
+            const int y = g.vy + row;
+            const int bx0 = tx * FRAG_STRETCH;
+            const int nb = min(FRAG_STRETCH, g.nbx - bx0);
+            const int px_left = g.vw - (bx0 << 5);                          // pixels from the stretch start to the row end
+            int32_t head = -1;
+            if (lane < nb) {                                                // fetch and reset the bin heads of the stretch
+                int32_t *hp = pl.bin_head + (size_t)row * g.nbx + bx0 + lane;
+                head = *hp;
+                if (head >= 0) *hp = -1;
+            }
+            unsigned mask = __ballot_sync(0xFFFFFFFFu, head >= 0);
+            uint32_t *crow = color + (size_t)y * color_pitch + g.vx + (bx0 << 5);
+            float *drow = depth + (size_t)row * g.vw + (bx0 << 5);
+            const bool aligned = ((reinterpret_cast<uintptr_t>(crow) | reinterpret_cast<uintptr_t>(drow)) & 15) == 0;
+            // ---- empty bins ----
+            if (mask != (nb == 32 ? 0xFFFFFFFFu : (1u << nb) - 1u)) {
+                const float maxz = __uint_as_float(MAXZ_BITS);
+                for (int i = lane; i < nb * 8; i += 32) {
+                    const int b = i >> 3, px = (b << 5) + ((i & 7) << 2);
+                    if ((mask >> b) & 1u) continue;
+                    if (aligned && px + 4 <= px_left) {
+                        if (!g.skip_bg) *reinterpret_cast<uint4 *>(crow + px) = make_uint4(0, 0, 0, 0);
+                        *reinterpret_cast<float4 *>(drow + px) = make_float4(maxz, maxz, maxz, maxz);
+                    } else {
+                        for (int k = 0; k < 4; k++)
+                            if (px + k < px_left) { if (!g.skip_bg) crow[px + k] = 0; drow[px + k] = maxz; }
+                    }
                 }
             }
-        }
-        for (int32_t c = fw.cursor[b]; c >= 0;) {                               // a list longer than FRAG_LIST_CAP: the rest, serially
-            const Chunk ch = pl.chunks[c];
-            c = ch.next;
-            const int xs = (int)(ch.xs_xe & 0xFFu), xe = (int)(ch.xs_xe >> 8);
-            if (lane >= xs && lane < xe) {
-                const float u = pl.frag_u[ch.frag0 + (uint32_t)lane];
-                const float z = fadd(ch.v0, fmul(ch.v1, u));
-                if (z >= NEAR_Z) {
-                    const uint64_t key = ((uint64_t)__float_as_uint(z) << 32) | ch.slot;
-                    if (key < best) { best = key; best_u = u; best_span = ch.span; }
+            if (!mask) break;
+            // ---- non-empty bins, pass 1: depth resolve.
+            //  a. the first lanes walk one bin list each (FRAG_STRETCH pointer chases side by side instead of one after the
+            //     other) and leave the chunk records in shared memory;
+            //  b. lane = pixel: per bin, the nearest fragment of every pixel is kept in registers.  Depth is written at once,
+            //     and the winners of the whole stretch are queued in shared memory so that shading (pass 2) runs on dense
+            //     batches of 32 covered pixels. ----
+            if (lane < FRAG_STRETCH) {
+                int n = 0;
+                int32_t c = head;
+                while (c >= 0 && n < FRAG_LIST_CAP) {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(&pl.chunks[c]);
+                    const uint4 r0 = src[0], r1 = src[1];
+                    fw.rec[2 * (lane * FRAG_LIST_CAP + n)] = r0; fw.rec[2 * (lane * FRAG_LIST_CAP + n) + 1] = r1;
+                    n++;
+                    c = (int32_t)r1.z;                                              // Chunk::next
                 }
+                fw.cnt[lane] = n; fw.cursor[lane] = c;
             }
-        }
-        const int px = (b << 5) + lane;
-        const bool inside = px < px_left;
-        const bool hit = best_span != 0xFFFFFFFFu && inside;
-        if (inside) drow[px] = __uint_as_float((uint32_t)(best >> 32));
-        fw.u[px] = best_u; fw.span[px] = hit ? best_span : 0xFFFFFFFFu; fw.slot[px] = (uint32_t)best;
-        const unsigned hm = __ballot_sync(0xFFFFFFFFu, hit);
-        if (hit) fw.idx[n_hit + __popc(hm & lt)] = (uint8_t)px;
-        n_hit += __popc(hm);
+            __syncwarp();
+            uint32_t n_hit = 0;
+            const unsigned used = mask;
+            while (mask) {
+                const int b = __ffs(mask) - 1;
+                mask &= mask - 1;
+                uint64_t best = KEY_INIT;
+                float best_u = 0.f;
+                uint32_t best_span = 0xFFFFFFFFu;
+                const int n = fw.cnt[b];
+                const uint4 *rec = &fw.rec[2 * b * FRAG_LIST_CAP];
+                #pragma unroll 2
+                for (int k = 0; k < n; k++) {
+                    const uint4 r0 = rec[2 * k];                                    // frag0, xs_xe, v0, v1
+                    const unsigned xs = r0.y & 0xFFu, wd = (r0.y >> 8) - xs;
+                    if ((unsigned)lane - xs < wd) {
+                        const float u = pl.frag_u[r0.x + (uint32_t)lane];           // qpixel.ualpha, replayed by k_spans
+                        const float z = fadd(__uint_as_float(r0.z), fmul(__uint_as_float(r0.w), u));   // value(0), renderer.cpp:488
+                        if (z >= NEAR_Z) {                                          // renderer.cpp:489-492
+                            const uint2 r1 = *reinterpret_cast<const uint2 *>(&rec[2 * k + 1]);       // slot, span
+                            const uint64_t key = ((uint64_t)__float_as_uint(z) << 32) | r1.x;
+                            if (key < best) { best = key; best_u = u; best_span = r1.y; }
+                        }
+                    }
+                }
+                for (int32_t c = fw.cursor[b]; c >= 0;) {                           // a list longer than FRAG_LIST_CAP: the rest, serially
+                    const Chunk ch = pl.chunks[c];
+                    c = ch.next;
+                    const int xs = (int)(ch.xs_xe & 0xFFu), xe = (int)(ch.xs_xe >> 8);
+                    if (lane >= xs && lane < xe) {
+                        const float u = pl.frag_u[ch.frag0 + (uint32_t)lane];
+                        const float z = fadd(ch.v0, fmul(ch.v1, u));
+                        if (z >= NEAR_Z) {
+                            const uint64_t key = ((uint64_t)__float_as_uint(z) << 32) | ch.slot;
+                            if (key < best) { best = key; best_u = u; best_span = ch.span; }
+                        }
+                    }
+                }
+                const int px = (b << 5) + lane;
+                const bool inside = px < px_left;
+                const bool hit = best_span != 0xFFFFFFFFu && inside;
+                if (inside) drow[px] = __uint_as_float((uint32_t)(best >> 32));
+                fw.u[px] = best_u; fw.span[px] = hit ? best_span : 0xFFFFFFFFu; fw.slot[px] = (uint32_t)best;
+                const unsigned hm = __ballot_sync(0xFFFFFFFFu, hit);
+                if (hit) fw.idx[n_hit + __popc(hm & lt)] = (uint8_t)px;
+                n_hit += __popc(hm);
+            }
+            __syncwarp();
+            // ---- pass 2: shade the queued winners, 32 at a time (deferred: only the visible fragment of a pixel is shaded) ----
+            for (uint32_t k = lane; k < n_hit; k += 32) {
+                const int px = fw.idx[k];
+                const SpanShade *ss = &pl.span_shades[fw.span[px]];
+                const SlotShade *sh = &pl.shades[fw.slot[px]];
+                const uint4 bind = *reinterpret_cast<const uint4 *>(&sh->color);   // colour, tex_off, tw, th
+                const float u = fw.u[px];
+                uint32_t out;
+                if (FAST) {
+                    Prim pr;
+                    pr.color = bind.x; pr.tex_off = bind.y; pr.tw = (int32_t)bind.z; pr.th = (int32_t)bind.w;
+                    pr.tw_mask = (pr.tw & (pr.tw - 1)) == 0 ? pr.tw - 1 : -1;
+                    pr.th_mask = (pr.th & (pr.th - 1)) == 0 ? pr.th - 1 : -1;
+                    const TexFetch tf = tex_fetch<TEX>(ss, pr, s.texels, u);       // texel loads in flight under the lighting
+                    int li;
+                    if (phong_light_fast(ss, vp, fp, u, li)) out = combine_light(tex_filter<TEX>(tf), li);
+                    else out = shade_exact_call<LIGHT, TEX>(ss, 0.0f, bind, s.texels, &vp, &fp, u);
+                } else {
+                    Prim pr;
+                    pr.color = bind.x; pr.tex_off = bind.y; pr.tw = (int32_t)bind.z; pr.th = (int32_t)bind.w;
+                    pr.tw_mask = (pr.tw & (pr.tw - 1)) == 0 ? pr.tw - 1 : -1;
+                    pr.th_mask = (pr.th & (pr.th - 1)) == 0 ? pr.th - 1 : -1;
+                    out = shade<LIGHT, TEX>(ss, sh->flat_light, pr, s.texels, vp, fp, u);
+                }
+                fw.u[px] = __uint_as_float(out);
+            }
+            __syncwarp();
+            // ---- pass 3: colour write-back, one 128-byte segment per bin (background pixels of a used bin get 0) ----
+            mask = used;
+            while (mask) {
+                const int b = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int px = (b << 5) + lane;
+                if (px < px_left) crow[px] = fw.span[px] != 0xFFFFFFFFu ? __float_as_uint(fw.u[px]) : 0u;
+            }
+            if (count_covered && lane == 0 && n_hit) atomicAdd(&cn->n_covered, n_hit);
+            __syncwarp();                                                   // fw is reused by the next item
+        } while (0);
+
+        q = __shfl_sync(0xFFFFFFFFu, q_raw, 0);
     }
-    __syncwarp();
-    // ---- pass 2: shade the queued winners, 32 at a time (deferred: only the visible fragment of a pixel is shaded) ----
-    for (uint32_t k = lane; k < n_hit; k += 32) {
-        const int px = fw.idx[k];
-        const uint32_t span = fw.span[px];
-        const SlotShade *sh = &pl.shades[fw.slot[px]];
-        const uint4 bind = *reinterpret_cast<const uint4 *>(&sh->color);       // colour, tex_off, tw, th
-        Prim pr;
-        pr.color = bind.x; pr.tex_off = bind.y; pr.tw = (int32_t)bind.z; pr.th = (int32_t)bind.w;
-        pr.tw_mask = (pr.tw & (pr.tw - 1)) == 0 ? pr.tw - 1 : -1;
-        pr.th_mask = (pr.th & (pr.th - 1)) == 0 ? pr.th - 1 : -1;
-        const uint32_t out = shade<LIGHT, TEX>(&pl.span_shades[span], sh->flat_light, pr, s.texels, vp, fp, fw.u[px]);
-        fw.u[px] = __uint_as_float(out);
-    }
-    __syncwarp();
-    // ---- pass 3: colour write-back, one 128-byte segment per bin (background pixels of a used bin get 0) ----
-    mask = used;
-    while (mask) {
-        const int b = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int px = (b << 5) + lane;
-        if (px < px_left) crow[px] = fw.span[px] != 0xFFFFFFFFu ? __float_as_uint(fw.u[px]) : 0u;
-    }
-    if (count_covered && lane == 0 && n_hit) atomicAdd(&pl.counters->n_covered, n_hit);
+}
+
+// DoF tile classification on its own (the transparency-layer kernel has no persistent warps to fold it into)
+__global__ void __launch_bounds__(256) k_dof_classify(const ViewParams *__restrict__ vpp, Pools pl, FragGeom g, uint32_t *__restrict__ dof_dst)
+{
+    pdl_trigger();
+    __shared__ ViewParams vp;
+    for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += 256) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
+    __syncthreads();
+    pdl_wait();
+    const uint32_t d = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (d < (uint32_t)g.n_dof) dof_tile_duty(pl, g, vp.stamp, dof_background_value(vp), dof_dst, d, threadIdx.x & 31);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -467,7 +673,6 @@ __global__ void __launch_bounds__(FRAG_TPB) k_fragments_layers(DeviceScene s, co
     if (lane < nb) {
         head = *headp;
         if (head >= 0) *headp = -1;
-        pl.bin_used[(size_t)row * vp.nbx + bx0 + lane] = head >= 0;
     }
     unsigned mask = __ballot_sync(0xFFFFFFFFu, head >= 0);
     uint32_t *crow = color + (size_t)y * color_pitch + vp.vx + (bx0 << 5);
@@ -550,23 +755,33 @@ __global__ void __launch_bounds__(FRAG_TPB) k_fragments_layers(DeviceScene s, co
 //                                                        to the viewport, whose blur factor is != 0
 // with r = (int)blur(depth(x,y)) in 0..5.  All integer arithmetic -> pixel-identical.
 //
-// One CTA produces a 64x32 tile.  It stages the (64+9)x(32+9) source window in shared memory as
-// packed per-pixel contributions (b | g<<21 | r<<42 in a u64, the tap count in a u32), turns
-// them into a summed-area table with two short serial scans (rows, then columns), and every
-// output pixel is then 4 corner lookups instead of up to 100 taps.  HBM traffic is the
-// algorithmic 12 B/pixel; the halo over-fetch (80x41 staged for 64x32 outputs) is served by L2.
-// The blur radius needs no per-pixel division: r(t) is a monotone step function of
-// t = |focal_distance - z|, so the host finds its 5 step positions by exact bisection over the
-// float bit patterns (abi.cu dof_thresholds) and the kernel just compares.
+// k_dof is a persistent grid over the list of DoF output tiles (64 x 32) that k_fragments found something under
+// (dof_tile_duty; every other tile is a constant k_fragments stored already).  Per tile:
+//   1. the (64+16) x (32+9) source window of colour and depth arrives in shared memory by TMA (two 2-D tensor loads,
+//      cp.async.bulk.tensor; coordinates outside the viewport are zero-filled by the hardware, which replaces all edge
+//      predication: a depth word of 0 means "no such pixel").  The load of the NEXT tile's window is issued as soon as
+//      this tile's window has been consumed, so it lands underneath steps 3-5;
+//   2. lane = consecutive pixel: every staged pixel becomes ONE packed 64-bit contribution
+//          b | g << 15 | r << 30 | 1 << 45          (zero when the pixel's blur factor is 0 or it does not exist)
+//      15 bits hold a box sum of <= 100 bytes, 7 bits its count -- a box of (2r)^2 <= 100 taps; the prefix sums
+//      themselves overflow their fields, but the four-corner difference is exact modulo 2^64;
+//   3. summed-area table: one thread per row, then one thread per column (the conflict-free order for a row stride
+//      of 81 entries);
+//   4. per output pixel 4 corner lookups, exact v / n by a multiply-high; radius-0 / empty boxes copy the source;
+//   5. a window that turns out to hold only background (the tile list is conservative) is a constant fill.
+// The blur radius needs no per-pixel division: r(t) is a monotone step function of t = |focal_distance - z|, so the
+// host finds its 5 step positions by exact bisection over the float bit patterns (abi.cu dof_thresholds).
+// Without TMA (viewport width not a multiple of 4 pixels: the tensor's row pitch must be a multiple of 16 bytes) the
+// window is staged by predicated loads instead; everything downstream is the same.
 // ----------------------------------------------------------------------------------------
-static constexpr int DOF_OW = 64, DOF_OH = 32, DOF_LO = 5, DOF_HI = 4;
+static constexpr int DOF_LO = 5, DOF_HI = 4;
 static constexpr int DOF_SH = DOF_OH + DOF_LO + DOF_HI;      // 41 source rows
 static constexpr int DOF_X0 = 8;                             // the staged window starts 8 columns left of the tile (16-byte aligned)
-static constexpr int DOF_WW = DOF_OW + 16;                   // 80 staged columns = 20 x 128-bit loads per row
-static constexpr int DOF_PW = DOF_WW + 1;                    // SAT row stride in entries (col 0 = zero border; odd -> no bank conflicts)
+static constexpr int DOF_WW = DOF_OW + 16;                   // 80 staged columns
+static constexpr int DOF_PW = DOF_WW + 1;                    // SAT row stride in entries (col 0 = zero border; odd -> rows on different banks)
 static constexpr int DOF_THREADS = 256;
+static constexpr int DOF_NPX = DOF_SH * DOF_WW;              // 3280 staged pixels
 
-struct DofClass { uint32_t radius; bool counts; };
 // blur radius and "this pixel is a tap" for depth z, from the host-derived thresholds (common.cuh ViewParams)
 SB_DEV DofClass dof_classify(const ViewParams &vp, float z)
 {
@@ -577,189 +792,206 @@ SB_DEV DofClass dof_classify(const ViewParams &vp, float z)
     c.counts = t > vp.dof_on;
     return c;
 }
-
-// constant fill of a tile whose whole window is untouched background (colour 0, depth 0x7F7F7F7F)
-SB_DEV void dof_fill_background(const ViewParams &vp, uint32_t *__restrict__ dst, int dst_pitch, int ox, int oy, int w, int h, int row1, int tid)
+// what a window of untouched background (colour 0, depth 0x7F7F7F7F) blurs to:
+// radius 0: copy (0); else every tap counts iff its blur != 0 -> average of zeros with alpha 255, or no taps -> copy
+SB_DEV uint32_t dof_background_value(const ViewParams &vp)
 {
     const DofClass bgc = dof_classify(vp, __uint_as_float(MAXZ_BITS));
-    // radius 0: copy (0); else every tap counts iff its blur != 0 -> average of zeros with alpha 255, or no taps -> copy
-    const uint32_t v = (bgc.radius != 0 && bgc.counts) ? 0xFF000000u : 0u;
-    const bool vst = ((dst_pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ox + DOF_OW <= w;
-    if (vst) {
-        for (int q = tid; q < DOF_OW * DOF_OH / 4; q += DOF_THREADS) {
-            const int ty = q / (DOF_OW / 4), tx = (q % (DOF_OW / 4)) * 4;
-            const int y = oy + ty;
-            if (y < row1 && y < h) *reinterpret_cast<uint4 *>(dst + (size_t)y * dst_pitch + ox + tx) = make_uint4(v, v, v, v);
-        }
-    } else {
-        for (int p = tid; p < DOF_OW * DOF_OH; p += DOF_THREADS) {
-            const int ty = p / DOF_OW, tx = p % DOF_OW;
-            const int x = ox + tx, y = oy + ty;
-            if (y < row1 && y < h && x < w) dst[(size_t)y * dst_pitch + x] = v;
-        }
+    return (bgc.radius != 0 && bgc.counts) ? 0xFF000000u : 0u;
+}
+
+struct DofGeom {
+    int32_t vw, vh;             // the viewport (source arrays are [vh][src_pitch] colour, [vh][vw] depth)
+    int32_t anchor;             // viewport-relative row of the DoF tile grid's origin (= first drawn row)
+    int32_t out0, out1;         // viewport-relative rows [out0, out1) to produce
+    int32_t ndx;                // DoF tiles per row
+    int32_t src_pitch, dst_pitch;
+    int32_t use_tma;
+};
+
+struct __align__(128) DofSmem {
+    uint32_t raw_c[DOF_NPX];                                    // staged colour window (TMA destination: 128-byte aligned)
+    alignas(128) uint32_t raw_z[DOF_NPX];                       // staged depth window (bit patterns)
+    alignas(16) unsigned long long sat[(DOF_SH + 1) * DOF_PW];  // packed contributions -> summed-area table (row 0 / column 0: zero border)
+    uint8_t rad[DOF_OW * DOF_OH];                               // blur radius of the output pixels
+    uint32_t magic[128];                                        // ceil(2^28 / n): exact v / n for v < 2^15, n <= 100
+    ViewParams vp;
+    alignas(8) unsigned long long bar;                          // mbarrier of the window loads
+    uint32_t item[2];                                           // DoF tile of this / the next iteration, 0xFFFFFFFF = none
+};
+
+SB_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// both window loads of DoF tile d, completing on `bar`
+SB_DEV void dof_issue_window(const CUtensorMap *tm_color, const CUtensorMap *tm_depth, DofSmem &sm, const DofGeom &g, uint32_t d)
+{
+    const int j = (int)d / g.ndx, i = (int)d - j * g.ndx;
+    const int x = i * DOF_OW - DOF_X0, y = g.anchor + j * DOF_OH - DOF_LO;
+    const uint32_t bar = smem_u32(&sm.bar);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // earlier generic-proxy accesses to the window are ordered before the refill
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(2 * DOF_NPX * 4) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(sm.raw_c)), "l"(tm_color), "r"(bar), "r"(x), "r"(y) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(sm.raw_z)), "l"(tm_depth), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+SB_DEV void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    const uint32_t a = smem_u32(bar);
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (!ok) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (!ok && clock64() - t0 > 4000000000ll) __trap();                 // ~2 s: a tensor load that never lands must not hang the GPU
     }
 }
 
-__global__ void __launch_bounds__(DOF_THREADS) k_dof(const ViewParams *__restrict__ vpp, const uint8_t *__restrict__ bin_used, int nbx,
-                                                     const uint32_t *__restrict__ src, int src_pitch,
-                                                     const float *__restrict__ depth, uint32_t *__restrict__ dst,
-                                                     int dst_pitch, int w, int h, int row0, int row1)
+__global__ void __launch_bounds__(DOF_THREADS, 4) k_dof(const __grid_constant__ CUtensorMap tm_color, const __grid_constant__ CUtensorMap tm_depth,
+                                                        const ViewParams *__restrict__ vpp, Pools pl, DofGeom g,
+                                                        const uint32_t *__restrict__ src, const float *__restrict__ depth, uint32_t *__restrict__ dst)
 {
-    __shared__ unsigned long long s64[(DOF_SH + 1) * DOF_PW];
-    __shared__ uint32_t s32[(DOF_SH + 1) * DOF_PW];
-    __shared__ uint8_t srad[DOF_SH * DOF_WW];               // blur radius (0..5) of every staged pixel
-    __shared__ uint32_t magic[128];                          // ceil(2^28 / n): exact v / n for v < 2^15, n <= 100
-    __shared__ ViewParams vp;
+    extern __shared__ __align__(128) unsigned char dof_smem_raw[];
+    DofSmem &sm = *reinterpret_cast<DofSmem *>(dof_smem_raw);
     const int tid = threadIdx.x;
-    const int ox = blockIdx.x * DOF_OW, oy = row0 + blockIdx.y * DOF_OH;
-    for (int k = tid; k < (int)(sizeof(ViewParams) / 4); k += DOF_THREADS) reinterpret_cast<uint32_t *>(&vp)[k] = reinterpret_cast<const uint32_t *>(vpp)[k];
-    pdl_wait();                                                             // k_fragments' colour, depth and occupancy map
-
-    // ---- k_fragments left one byte per 32-column bin saying whether it drew anything there this frame.  If no bin
-    //      under the window [ox-8, ox+72) x [oy-5, oy+36) did, the window is pure background: no loads at all. ----
-    {
-        const int b0 = max(0, (ox - DOF_X0) >> 5), b1 = min(nbx - 1, (ox - DOF_X0 + DOF_WW - 1) >> 5);
-        const int nbw = b1 - b0 + 1;                         // <= 4
-        bool used = false;
-        for (int i = tid; i < nbw * DOF_SH; i += DOF_THREADS) {
-            const int sy = i / nbw, gy = oy + sy - DOF_LO;
-            if (gy >= 0 && gy < h) used = used || bin_used[(size_t)gy * nbx + b0 + (i - sy * nbw)];
-        }
-        if (!__syncthreads_or(used)) {                       // (the barrier also makes `vp` visible)
-            dof_fill_background(vp, dst, dst_pitch, ox, oy, w, h, row1, tid);
-            return;
-        }
+    pdl_trigger();
+    // ---- prologue, independent of the predecessor ----
+    for (int k = tid; k < (int)(sizeof(ViewParams) / 4); k += DOF_THREADS) reinterpret_cast<uint32_t *>(&sm.vp)[k] = reinterpret_cast<const uint32_t *>(vpp)[k];
+    if (tid < 128) sm.magic[tid] = tid ? (uint32_t)(((1u << 28) + tid - 1) / tid) : 0u;
+    for (int i = tid; i < DOF_PW; i += DOF_THREADS) sm.sat[i] = 0;                              // zero row 0 ...
+    for (int i = tid; i <= DOF_SH; i += DOF_THREADS) sm.sat[i * DOF_PW] = 0;                    // ... and column 0, for good
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&sm.bar)), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-
-    // ---- stage the source window [ox-8, ox+72) x [oy-5, oy+36): 20 x 41 quads of 4 pixels, 128-bit loads, all of a
-    //      thread's loads issued before any is consumed.  Needs 16-byte aligned rows (w, pitches multiples of 4). ----
-    constexpr int QPR = DOF_WW / 4, NQ = QPR * DOF_SH;       // 20 quads per row, 820 quads
-    constexpr int QPT = (NQ + DOF_THREADS - 1) / DOF_THREADS;   // 4 per thread
-    const bool vec_ok = ((w | src_pitch | dst_pitch) & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(depth)) & 15) == 0;
-    float4 dz[QPT]; uint4 cc[QPT];
-    uint32_t inmask = 0;                                     // 4 bits per quad: which of its pixels exist
-    #pragma unroll
-    for (int k = 0; k < QPT; k++) {
-        const int qi = tid + k * DOF_THREADS;
-        const int sy = qi / QPR, sxq = qi - sy * QPR;
-        const int gy = oy + sy - DOF_LO, gx = ox - DOF_X0 + 4 * sxq;
-        dz[k] = make_float4(0.f, 0.f, 0.f, 0.f); cc[k] = make_uint4(0u, 0u, 0u, 0u);
-        if (qi < NQ && gy >= 0 && gy < h) {
-            if (vec_ok) {
-                if (gx >= 0 && gx < w) {
-                    dz[k] = __ldg(reinterpret_cast<const float4 *>(depth + (size_t)gy * w + gx));
-                    cc[k] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)gy * src_pitch + gx));
-                    inmask |= 0xFu << (4 * k);
+    __syncthreads();
+    pdl_wait();                                                             // k_fragments' colour, depth and tile list
+    const ViewParams &vp = sm.vp;
+    Counters *const cn = pl.counters;
+    const uint32_t n = cn->n_dof_busy;
+    if (tid == 0) {
+        const uint32_t i0 = atomicAdd(&cn->dof_queue, 1u);
+        const uint32_t d0 = i0 < n ? pl.dof_list[i0] : 0xFFFFFFFFu;
+        sm.item[0] = d0;
+        if (d0 != 0xFFFFFFFFu && g.use_tma) dof_issue_window(&tm_color, &tm_depth, sm, g, d0);
+    }
+    __syncthreads();
+    const uint32_t fill = dof_background_value(vp);
+    uint32_t phase = 0;
+    int cur = 0;
+    for (;;) {
+        const uint32_t d = sm.item[cur];
+        if (d == 0xFFFFFFFFu) break;
+        uint32_t nxt_raw = 0;
+        if (tid == 0) nxt_raw = atomicAdd(&cn->dof_queue, 1u);              // the next index travels under the wait for the window
+        const int j = (int)d / g.ndx, i = (int)d - j * g.ndx;
+        const int ox = i * DOF_OW, oy = g.anchor + j * DOF_OH;              // viewport-relative origin of the output tile
+        if (g.use_tma) {
+            mbar_wait(&sm.bar, phase);
+            phase ^= 1u;
+        } else {
+            for (int p = tid; p < DOF_NPX; p += DOF_THREADS) {
+                const int sy = p / DOF_WW, sx = p - sy * DOF_WW;
+                const int gx = ox - DOF_X0 + sx, gy = oy - DOF_LO + sy;
+                uint32_t c = 0u, z = 0u;
+                if (gx >= 0 && gx < g.vw && gy >= 0 && gy < g.vh) {
+                    c = __ldg(&src[(size_t)gy * g.src_pitch + gx]);
+                    z = __float_as_uint(__ldg(&depth[(size_t)gy * g.vw + gx]));
                 }
-            } else {
-                float d4[4] = { 0.f, 0.f, 0.f, 0.f }; uint32_t c4[4] = { 0u, 0u, 0u, 0u };
-                #pragma unroll
-                for (int e = 0; e < 4; e++)
-                    if (gx + e >= 0 && gx + e < w) {
-                        d4[e] = __ldg(&depth[(size_t)gy * w + gx + e]); c4[e] = __ldg(&src[(size_t)gy * src_pitch + gx + e]);
-                        inmask |= 1u << (4 * k + e);
-                    }
-                dz[k] = make_float4(d4[0], d4[1], d4[2], d4[3]); cc[k] = make_uint4(c4[0], c4[1], c4[2], c4[3]);
+                sm.raw_c[p] = c; sm.raw_z[p] = z;
             }
+            __syncthreads();
         }
-    }
-    // a window that only sees untouched background (colour 0, depth 0x7F7F7F7F) blurs to a constant
-    bool all_bg = true;
-    #pragma unroll
-    for (int k = 0; k < QPT; k++) {
-        const uint32_t m = (inmask >> (4 * k)) & 0xFu;
-        const bool bg = (cc[k].x | cc[k].y | cc[k].z | cc[k].w) == 0u
-                     && __float_as_uint(dz[k].x) == MAXZ_BITS && __float_as_uint(dz[k].y) == MAXZ_BITS
-                     && __float_as_uint(dz[k].z) == MAXZ_BITS && __float_as_uint(dz[k].w) == MAXZ_BITS;
-        all_bg = all_bg && (m == 0u || (m == 0xFu && bg));
-    }
-    if (__syncthreads_and(all_bg)) {                         // bins were touched, but only by background-coloured pixels
-        dof_fill_background(vp, dst, dst_pitch, ox, oy, w, h, row1, tid);
-        return;
-    }
-
-    if (tid < 128) magic[tid] = tid ? (uint32_t)(((1u << 28) + tid - 1) / tid) : 0u;
-    for (int i = tid; i < DOF_PW; i += DOF_THREADS) { s64[i] = 0; s32[i] = 0; }                 // zero row 0
-    for (int i = tid; i <= DOF_SH; i += DOF_THREADS) { s64[i * DOF_PW] = 0; s32[i * DOF_PW] = 0; } // zero column 0
-    #pragma unroll
-    for (int k = 0; k < QPT; k++) {
-        const int qi = tid + k * DOF_THREADS;
-        if (qi >= NQ) continue;
-        const int sy = qi / QPR, sx0 = 4 * (qi - sy * QPR);
-        const float d4[4] = { dz[k].x, dz[k].y, dz[k].z, dz[k].w };
-        const uint32_t c4[4] = { cc[k].x, cc[k].y, cc[k].z, cc[k].w };
-        #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            unsigned long long v = 0; uint32_t n = 0, rad = 0;
-            if ((inmask >> (4 * k + e)) & 1u) {
-                const DofClass dc = dof_classify(vp, d4[e]);
-                rad = dc.radius;
+        // ---- staged pixels -> packed contributions (+ the radius of the output pixels); is there anything but background? ----
+        bool bg = true;
+        #pragma unroll 2
+        for (int p = tid; p < DOF_NPX; p += DOF_THREADS) {
+            const int sy = p / DOF_WW, sx = p - sy * DOF_WW;
+            const uint32_t c = sm.raw_c[p], zb = sm.raw_z[p];
+            unsigned long long v = 0;
+            uint32_t radius = 0;
+            if (zb != 0u) {                                                 // the pixel exists (a real depth is >= 0.001 or 0x7F7F7F7F)
+                bg = bg && c == 0u && zb == MAXZ_BITS;
+                const DofClass dc = dof_classify(vp, __uint_as_float(zb));
+                radius = dc.radius;
                 if (dc.counts) {
-                    const uint32_t c = c4[e];
-                    v = (unsigned long long)(c & 0xFF) | ((unsigned long long)((c >> 8) & 0xFF) << 21)
-                      | ((unsigned long long)((c >> 16) & 0xFF) << 42);
-                    n = 1;
+                    const uint32_t b = c & 0xFFu, gg = (c >> 8) & 0xFFu, r = (c >> 16) & 0xFFu;
+                    const uint32_t lo = b | (gg << 15) | (r << 30), hi = (r >> 2) | (1u << 13);
+                    v = ((unsigned long long)hi << 32) | lo;
                 }
             }
-            s64[(sy + 1) * DOF_PW + sx0 + e + 1] = v;
-            s32[(sy + 1) * DOF_PW + sx0 + e + 1] = n;
-            srad[sy * DOF_WW + sx0 + e] = (uint8_t)rad;
+            sm.sat[(sy + 1) * DOF_PW + sx + 1] = v;
+            const int ty = sy - DOF_LO, tx = sx - DOF_X0;
+            if ((unsigned)ty < (unsigned)DOF_OH && (unsigned)tx < (unsigned)DOF_OW) sm.rad[ty * DOF_OW + tx] = (uint8_t)radius;
         }
-    }
-    __syncthreads();
-    if (tid < DOF_SH) {                                      // inclusive scan along each row
-        unsigned long long a = 0; uint32_t n = 0;
-        const int base = (tid + 1) * DOF_PW;
-        #pragma unroll 8
-        for (int sx = 1; sx <= DOF_WW; sx++) {
-            a += s64[base + sx]; n += s32[base + sx];
-            s64[base + sx] = a; s32[base + sx] = n;
+        const bool all_bg = __syncthreads_and(bg);                          // (also: the raw window is consumed, the contributions are visible)
+        if (tid == 0) {
+            const uint32_t dn = nxt_raw < n ? pl.dof_list[nxt_raw] : 0xFFFFFFFFu;
+            sm.item[cur ^ 1] = dn;
+            if (dn != 0xFFFFFFFFu && g.use_tma) dof_issue_window(&tm_color, &tm_depth, sm, g, dn);   // lands under the scans and the outputs
         }
-    }
-    __syncthreads();
-    if (tid < DOF_WW) {                                      // then down each column
-        unsigned long long a = 0; uint32_t n = 0;
-        const int col = tid + 1;
-        #pragma unroll 8
-        for (int sy = 1; sy <= DOF_SH; sy++) {
-            a += s64[sy * DOF_PW + col]; n += s32[sy * DOF_PW + col];
-            s64[sy * DOF_PW + col] = a; s32[sy * DOF_PW + col] = n;
-        }
-    }
-    __syncthreads();
-
-    // ---- outputs: consecutive lanes take consecutive pixels (conflict-free SAT reads, coalesced stores).
-    //      Staged column of output pixel tx is tx + DOF_X0; its SAT column index is that + 1. ----
-    #pragma unroll 2
-    for (int p = tid; p < DOF_OW * DOF_OH; p += DOF_THREADS) {
-        const int ty = p / DOF_OW, tx = p % DOF_OW;
-        const int x = ox + tx, y = oy + ty;
-        if (y >= row1 || y >= h || x >= w) continue;
-        const int radius = srad[(ty + DOF_LO) * DOF_WW + tx + DOF_X0];
-        uint32_t out;
-        bool have = false;
-        if (radius != 0) {
-            // window rows [y-r, y+r) -> SAT rows (ty+5-r, ty+5+r]; columns likewise with the +8 staging offset; the zero
-            // border and the zeros stored for out-of-viewport pixels implement the max(0,..)/min(w|h,..) clipping
-            const int J0 = ty + DOF_LO - radius, J1 = ty + DOF_LO + radius;
-            const int I0 = tx + DOF_X0 - radius, I1 = tx + DOF_X0 + radius;
-            const uint32_t count = (s32[J1 * DOF_PW + I1] + s32[J0 * DOF_PW + I0])
-                                 - (s32[J0 * DOF_PW + I1] + s32[J1 * DOF_PW + I0]);
-            if (count) {
-                const unsigned long long sum = (s64[J1 * DOF_PW + I1] + s64[J0 * DOF_PW + I0])
-                                             - (s64[J0 * DOF_PW + I1] + s64[J1 * DOF_PW + I0]);
-                // exact floor(v / count) for v < 2^15, count <= 100: (v * ceil(2^28 / count)) >> 28, as one IMAD.HI
-                const uint32_t m = magic[count];
-                const uint32_t lo = (uint32_t)sum, hi = (uint32_t)(sum >> 32);
-                const uint32_t b = __umulhi((lo & 0x1FFFFFu) << 4, m);
-                const uint32_t g = __umulhi((((lo >> 21) | (hi << 11)) & 0x1FFFFFu) << 4, m);
-                const uint32_t r = __umulhi(((hi >> 10) & 0x1FFFFFu) << 4, m);
-                out = b | (g << 8) | (r << 16) | 0xFF000000u;
-                have = true;
+        const int ya = max(oy, g.out0), yb = min(min(oy + DOF_OH, g.out1), g.vh);
+        if (all_bg) {
+            // bins were touched nearby, but this window only sees background-coloured pixels: a constant
+            const int wd = min(DOF_OW, g.vw - ox);
+            const bool vec = (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (g.dst_pitch & 3) == 0 && wd == DOF_OW;
+            if (vec) {
+                const uint4 v4 = make_uint4(fill, fill, fill, fill);
+                for (int k = tid; k < (yb - ya) * (DOF_OW / 4); k += DOF_THREADS)
+                    *reinterpret_cast<uint4 *>(dst + (size_t)(ya + k / (DOF_OW / 4)) * g.dst_pitch + ox + (k % (DOF_OW / 4)) * 4) = v4;
+            } else {
+                for (int k = tid; k < (yb - ya) * wd; k += DOF_THREADS)
+                    dst[(size_t)(ya + k / wd) * g.dst_pitch + ox + k % wd] = fill;
+            }
+        } else {
+            if (tid < DOF_SH) {                                             // inclusive scan along each row
+                unsigned long long a = 0;
+                unsigned long long *row = &sm.sat[(tid + 1) * DOF_PW];
+                #pragma unroll 8
+                for (int sx = 1; sx <= DOF_WW; sx++) { a += row[sx]; row[sx] = a; }
+            }
+            __syncthreads();
+            if (tid < DOF_WW) {                                             // then down each column
+                unsigned long long a = 0;
+                unsigned long long *col = &sm.sat[tid + 1];
+                #pragma unroll 8
+                for (int sy = 1; sy <= DOF_SH; sy++) { a += col[sy * DOF_PW]; col[sy * DOF_PW] = a; }
+            }
+            __syncthreads();
+            // ---- outputs: consecutive lanes take consecutive pixels (conflict-free SAT reads, coalesced stores).
+            //      Staged column of output pixel tx is tx + DOF_X0; SAT entry (J, I) = sum over staged rows < J, columns < I. ----
+            #pragma unroll 2
+            for (int p = tid; p < DOF_OW * DOF_OH; p += DOF_THREADS) {
+                const int ty = p / DOF_OW, tx = p % DOF_OW;
+                const int x = ox + tx, y = oy + ty;
+                if (y < ya || y >= yb || x >= g.vw) continue;
+                const int radius = sm.rad[p];
+                uint32_t out;
+                bool have = false;
+                if (radius != 0) {
+                    // window rows [y-r, y+r) -> SAT rows (ty+5-r, ty+5+r]; columns likewise with the +8 staging offset; the zero
+                    // border and the zeros stored for out-of-viewport pixels implement the max(0,..)/min(w|h,..) clipping
+                    const int J0 = ty + DOF_LO - radius, J1 = ty + DOF_LO + radius;
+                    const int I0 = tx + DOF_X0 - radius, I1 = tx + DOF_X0 + radius;
+                    const unsigned long long S = (sm.sat[J1 * DOF_PW + I1] + sm.sat[J0 * DOF_PW + I0])
+                                               - (sm.sat[J0 * DOF_PW + I1] + sm.sat[J1 * DOF_PW + I0]);
+                    const uint32_t lo = (uint32_t)S, hi = (uint32_t)(S >> 32);
+                    const uint32_t count = (hi >> 13) & 0x7Fu;
+                    if (count) {
+                        // exact floor(v / count) for v < 2^15, count <= 100: (v * ceil(2^28 / count)) >> 28, as one IMAD.HI
+                        const uint32_t m = sm.magic[count];
+                        const uint32_t b = __umulhi((lo & 0x7FFFu) << 4, m);
+                        const uint32_t gg = __umulhi(((lo >> 15) & 0x7FFFu) << 4, m);
+                        const uint32_t r = __umulhi((((lo >> 30) | (hi << 2)) & 0x7FFFu) << 4, m);
+                        out = b | (gg << 8) | (r << 16) | 0xFF000000u;
+                        have = true;
+                    }
+                }
+                if (!have) out = __ldg(&src[(size_t)y * g.src_pitch + x]);
+                dst[(size_t)y * g.dst_pitch + x] = out;
             }
         }
-        if (!have) out = __ldg(&src[(size_t)y * src_pitch + x]);
-        dst[(size_t)y * dst_pitch + x] = out;
+        __syncthreads();                                                    // SAT, radii and item[] are reused by the next tile
+        cur ^= 1;
     }
 }
 
@@ -770,6 +1002,7 @@ __global__ void __launch_bounds__(DOF_THREADS) k_dof(const ViewParams *__restric
 // memory; rank 0's stream ends with a kernel that waits for the flags.  No collective, no host round trip, and the
 // NVLink ingress of rank 0 carries the covered pixels instead of the whole frame.
 // ----------------------------------------------------------------------------------------
+static int g_num_sms = 0;                 // of the device the contexts run on (one device per process, or equal devices)
 static constexpr long long SYNC_TIMEOUT_CYCLES = 4000000000ll;      // ~2 s (first frames include graph instantiation on the peer): a lost peer must not hang the GPU
 
 SB_DEV uint32_t ld_sys(const uint32_t *p)
@@ -869,6 +1102,13 @@ __global__ void k_sync_wait_done(const ViewParams *__restrict__ vpp, FrameSync *
 // ----------------------------------------------------------------------------------------
 // With lazy module loading the first use of a kernel may have to synchronise with the device -- which never happens while
 // another context's wait kernel is spinning for this very launch.  Load the protocol's kernels up front.
+// per device, once (swegl_b200_create): k_dof needs more than the default 48 KB of dynamic shared memory
+void configure_kernels()
+{
+    cudaFuncSetAttribute(k_dof, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DofSmem));
+    cudaFuncSetAttribute(k_dof, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    g_num_sms = 0;
+}
 void preload_sync_kernels()
 {
     cudaFuncAttributes a;
@@ -894,26 +1134,57 @@ void launch_sync_wait_done(const ViewParams *d_vp, FrameSync *own, int world, cu
     launch_chain(k_sync_wait_done, 1, 32, st, true, d_vp, own, world);
 }
 
-template <int LIGHT, int TEX>
-static void launch_frag_t(const DeviceScene &s, const ViewParams &vp, const ViewParams *d_vp, const FrameParams *d_fp, const Pools &p,
-                          uint32_t *color, int color_pitch, float *depth, bool count_covered, Counters *h_counters_out, bool skip_bg, cudaStream_t st)
+// geometry shared by k_fragments, k_dof_classify and k_dof: `vp` = the rows that are drawn, [out0, out1) = the rows the post
+// pass produces (the band without its 5-row halo)
+static FragGeom make_geom(const ViewParams &vp, bool skip_bg, bool dof, int out_row0, int out_row1, int dof_pitch)
 {
-    const int nty = (vp.band1 - vp.band0 + FRAG_ROWS - 1) / FRAG_ROWS, n_tiles = vp.ntx * nty;
-    if (n_tiles <= 0) return;
-    const FragGeom g = { vp.vx, vp.vy, vp.vw, vp.band0, vp.band1, vp.nbx, vp.ntx, n_tiles, skip_bg ? 1 : 0 };
-    const unsigned grid = (unsigned)n_tiles + (unsigned)((n_tiles + FRAG_ROWS - 1) / FRAG_ROWS);
-    launch_chain(k_fragments<LIGHT, TEX>, grid, FRAG_TPB, st, true, s, d_vp, d_fp, p, g, color, color_pitch, depth, count_covered ? 1 : 0, h_counters_out);
+    FragGeom g{};
+    g.vx = vp.vx; g.vy = vp.vy; g.vw = vp.vw; g.band0 = vp.band0; g.band1 = vp.band1; g.nbx = vp.nbx; g.ntx = vp.ntx;
+    g.nty = (vp.band1 - vp.band0 + FRAG_ROWS - 1) / FRAG_ROWS;
+    g.n_tiles = g.ntx * g.nty;
+    g.skip_bg = skip_bg ? 1 : 0;
+    g.dof = dof ? 1 : 0;
+    g.ndx = (vp.vw + DOF_OW - 1) / DOF_OW;
+    g.n_dof = dof ? g.ndx * ((vp.band1 - vp.band0 + DOF_OH - 1) / DOF_OH) : 0;
+    g.out0 = out_row0; g.out1 = out_row1; g.dof_pitch = dof_pitch;
+    return g;
+}
+
+static int num_sms()
+{
+    if (!g_num_sms) {
+        int dev = 0, n = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        g_num_sms = n > 0 ? n : 148;
+    }
+    return g_num_sms;
+}
+
+template <int LIGHT, int TEX, int FAST>
+static void launch_frag_t(const DeviceScene &s, const ViewParams *d_vp, const FrameParams *d_fp, const Pools &p, const FragGeom &g,
+                          uint32_t *color, int color_pitch, float *depth, uint32_t *dof_dst, bool count_covered, Counters *h_counters_out, cudaStream_t st)
+{
+    if (g.n_tiles <= 0) return;
+    // one wave of persistent CTAs (fewer when the viewport has fewer row items than that)
+    const unsigned wave = (unsigned)(num_sms() * FRAG_CTAS_PER_SM);
+    const unsigned need = ((unsigned)g.n_tiles * FRAG_ROWS + FRAG_ROWS - 1) / FRAG_ROWS;
+    const unsigned grid = need < wave ? (need ? need : 1u) : wave;
+    launch_chain(k_fragments<LIGHT, TEX, FAST>, grid, FRAG_TPB, st, true, s, d_vp, d_fp, p, g, color, color_pitch, depth, dof_dst, count_covered ? 1 : 0, h_counters_out);
 }
 
 void launch_fragments(const DeviceScene &s, const ViewParams &vp, const ViewParams *d_vp, const FrameParams *d_fp, const Pools &p,
                       uint32_t *color, int color_pitch, float *depth, bool count_covered, Counters *h_counters_out, bool skip_bg_color,
-                      cudaStream_t st)
+                      bool fast, bool dof, int out_row0, int out_row1, uint32_t *dof_dst, int dof_pitch, cudaStream_t st)
 {
-#define SB_CASE(L, T) if (vp.light_mode == L && vp.tex_mode == T) { launch_frag_t<L, T>(s, vp, d_vp, d_fp, p, color, color_pitch, depth, count_covered, h_counters_out, skip_bg_color, st); return; }
+    const FragGeom g = make_geom(vp, skip_bg_color, dof, out_row0, out_row1, dof_pitch);
+#define SB_CASE(L, T) if (vp.light_mode == L && vp.tex_mode == T) { launch_frag_t<L, T, 0>(s, d_vp, d_fp, p, g, color, color_pitch, depth, dof_dst, count_covered, h_counters_out, st); return; }
+#define SB_FAST(T) if (fast && vp.light_mode == SWEGL_B200_LIGHT_PHONG && vp.tex_mode == T) { launch_frag_t<SWEGL_B200_LIGHT_PHONG, T, 1>(s, d_vp, d_fp, p, g, color, color_pitch, depth, dof_dst, count_covered, h_counters_out, st); return; }
+    SB_FAST(0) SB_FAST(1) SB_FAST(2)
     SB_CASE(0, 0) SB_CASE(0, 1) SB_CASE(0, 2)
     SB_CASE(1, 0) SB_CASE(1, 1) SB_CASE(1, 2)
     SB_CASE(2, 0) SB_CASE(2, 1) SB_CASE(2, 2)
 #undef SB_CASE
+#undef SB_FAST
 }
 
 template <int LIGHT, int TEX>
@@ -929,6 +1200,13 @@ void launch_fragments_layers(const DeviceScene &s, const ViewParams &vp, const V
 #define SB_LCASE(L, T) if (vp.light_mode == L && vp.tex_mode == T) { launch_frag_layers_t<L, T>(s, vp, d_vp, d_fp, p, color, color_pitch, depth, count_covered, h_counters_out, st); return; }
     SB_LCASE(0, 0) SB_LCASE(0, 1) SB_LCASE(0, 2) SB_LCASE(1, 0) SB_LCASE(1, 1) SB_LCASE(1, 2) SB_LCASE(2, 0) SB_LCASE(2, 1) SB_LCASE(2, 2)
 #undef SB_LCASE
+}
+
+// the DoF tile classification as a kernel of its own (behind k_fragments_layers; k_fragments does it itself)
+void launch_dof_classify(const ViewParams &vp, const ViewParams *d_vp, const Pools &p, int out_row0, int out_row1, uint32_t *dof_dst, int dof_pitch, cudaStream_t st)
+{
+    const FragGeom g = make_geom(vp, false, true, out_row0, out_row1, dof_pitch);
+    if (g.n_dof > 0) launch_chain(k_dof_classify, (unsigned)(g.n_dof + 7) / 8, 256, st, true, d_vp, p, g, dof_dst);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -972,12 +1250,47 @@ void launch_selftest_division(uint64_t n_pairs, uint32_t seed, unsigned long lon
     k_selftest_division<<<148 * 8, 256, 0, st>>>(n_pairs, seed, d_out2, d_out2 + 1);
 }
 
-void launch_dof(const ViewParams *d_vp, const uint8_t *bin_used, int nbx, const uint32_t *src, int src_pitch, const float *depth,
-                uint32_t *dst, int dst_pitch, int w, int h, int row0, int row1, cudaStream_t st)
+// Tensor maps of the post pass's two sources, both dense [vh][vw] arrays of 32-bit words; box = the 80 x 41 window of one tile.
+// cuTensorMapEncodeTiled comes from the driver through the runtime (no link against libcuda).
+bool make_dof_tensor_maps(const uint32_t *src, const float *depth, int vw, int vh, CUtensorMap *tm_color, CUtensorMap *tm_depth)
 {
-    dim3 grid((w + DOF_OW - 1) / DOF_OW, (row1 - row0 + DOF_OH - 1) / DOF_OH);
-    if (grid.x && grid.y)
-        launch_chain(k_dof, grid, DOF_THREADS, st, true, d_vp, bin_used, nbx, src, src_pitch, depth, dst, dst_pitch, w, h, row0, row1);
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<encode_fn>(fn);
+    }
+    if (!encode || (vw & 3) || ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(depth)) & 15)) return false;
+    const cuuint64_t dims[2] = { (cuuint64_t)vw, (cuuint64_t)vh };
+    const cuuint64_t strides[1] = { (cuuint64_t)vw * 4 };                   // bytes between rows: a multiple of 16
+    const cuuint32_t box[2] = { (cuuint32_t)DOF_WW, (cuuint32_t)DOF_SH };
+    const cuuint32_t estr[2] = { 1, 1 };
+    if (encode(tm_color, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t *>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    // (the depth words are moved as integers: a float tensor could not promise to keep every bit pattern)
+    if (encode(tm_depth, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<float *>(depth), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    return true;
+}
+
+void launch_dof(const ViewParams &vp, const ViewParams *d_vp, const Pools &p, const CUtensorMap *tm_color, const CUtensorMap *tm_depth, bool use_tma,
+                const uint32_t *src, int src_pitch, const float *depth, uint32_t *dst, int dst_pitch, int out_row0, int out_row1, cudaStream_t st)
+{
+    DofGeom g{};
+    g.vw = vp.vw; g.vh = vp.vh; g.anchor = vp.band0 - vp.vy; g.out0 = out_row0; g.out1 = out_row1;
+    g.ndx = (vp.vw + DOF_OW - 1) / DOF_OW;
+    g.src_pitch = src_pitch; g.dst_pitch = dst_pitch; g.use_tma = use_tma ? 1 : 0;
+    const int n_dof = g.ndx * ((vp.band1 - vp.band0 + DOF_OH - 1) / DOF_OH);
+    if (n_dof <= 0) return;
+    const unsigned wave = (unsigned)(num_sms() * 4);
+    const unsigned grid = (unsigned)n_dof < wave ? (unsigned)n_dof : wave;
+    CUtensorMap zero{};
+    launch_chain_smem(k_dof, grid, DOF_THREADS, sizeof(DofSmem), st, true, use_tma ? *tm_color : zero, use_tma ? *tm_depth : zero, d_vp, p, g, src, depth, dst);
 }
 
 } // namespace sb

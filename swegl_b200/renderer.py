@@ -19,10 +19,16 @@ class SweglB200Error(RuntimeError):
         self.status = status
 
 
+def frame_hash(words):
+    """FNV-1a-64 over the 32-bit words of a frame (tests/golden/MANIFEST.json's fingerprint), computed by the library"""
+    a = np.ascontiguousarray(words).view(np.uint32)
+    return int(_abi.load().swegl_b200_frame_hash(a.ctypes.data, a.size))
+
+
 class Renderer:
     def __init__(self, device=0, stream=None):
         self.lib = _abi.load()
-        if self.lib.swegl_b200_abi_version() != 1:
+        if self.lib.swegl_b200_abi_version() != _abi.ABI_VERSION:
             raise SweglB200Error("ABI version mismatch between swegl_b200/_abi.py and libswegl_b200.so")
         self.ctx = C.c_void_p()
         rc = self.lib.swegl_b200_create(int(device), C.byref(self.ctx))
@@ -111,6 +117,23 @@ class Renderer:
         """Blocks until the frame of `ticket` is in host memory.  Raises SweglB200Error(ERR_CAPACITY) if that frame must
         be submitted again (its pools were too small and have been enlarged)."""
         self._check(self.lib.swegl_b200_wait(self.ctx, C.c_uint64(ticket)))
+
+    def set_shading(self, mode):
+        """_abi.SHADING_EXACT (bit-exact Phong lighting) or _abi.SHADING_FAST (within +-1 LSB per colour channel, default)"""
+        self._check(self.lib.swegl_b200_set_shading(self.ctx, int(mode)))
+
+    def set_partial_readback(self, enabled=True):
+        self._check(self.lib.swegl_b200_set_partial_readback(self.ctx, int(bool(enabled))))
+
+    def invalidate_host_image(self, pixels=None):
+        """tell the library that `pixels` (None: every host image) was modified by the caller since the last frame through it"""
+        self._check(self.lib.swegl_b200_invalidate_host_image(self.ctx, C.c_void_p(pixels.ctypes.data) if pixels is not None else None))
+
+    def readback_stats(self, reset=False):
+        """-> (bytes copied device->host by render_async so far, frames)"""
+        out = (C.c_uint64 * 2)()
+        self._check(self.lib.swegl_b200_readback_stats(self.ctx, out, int(bool(reset))))
+        return int(out[0]), int(out[1])
 
     def export_screen(self):
         """64-byte CUDA IPC handle of this context's device screen (ship it to the other ranks)"""
