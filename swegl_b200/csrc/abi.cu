@@ -311,7 +311,7 @@ void swegl_b200_destroy(swegl_b200_ctx *ctx)
     void *ptrs[] = { ctx->d_pos, ctx->d_nrm, ctx->d_uv, ctx->d_vert_node, ctx->d_texels, ctx->d_tris, ctx->d_prims,
                      ctx->d_v_world, ctx->d_v_ndc, ctx->d_n_world, ctx->d_yes, ctx->d_block,
                      ctx->pools.edges, ctx->pools.shades, ctx->pools.spans, ctx->pools.span_shades, ctx->pools.frag_u, ctx->pools.row_slot,
-                     ctx->pools.chunks, ctx->pools.bin_head, ctx->pools.dof_list, ctx->pools.tile_stamp, ctx->pools.busy_list,
+                     ctx->pools.chunks, ctx->pools.bin_head, ctx->pools.bin_cnt, ctx->pools.bin_slots, ctx->pools.dof_list, ctx->pools.tile_stamp, ctx->pools.busy_list,
                      ctx->pools.counters, ctx->d_screen, ctx->d_depth,
                      ctx->d_tmp_color, ctx->d_cl_box, ctx->d_cl_adj_off, ctx->d_cl_adj, ctx->d_vb_adj_off, ctx->d_vb_adj, ctx->d_cull_flags, ctx->d_cull_lists };
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -398,6 +398,7 @@ static int grow_pools_for(swegl_b200_ctx *ctx, const Counters &c)
     // bin lists were consumed by k_fragments except for chunks that never got linked: reset them all
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemsetAsync(ctx->pools.bin_head, 0xFF, ctx->bins_cap * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->pools.bin_cnt, 0, ctx->bins_cap * 4, ctx->stream));
     return ensure_pools(ctx, (uint32_t)want_rows, (uint32_t)want_chunks, (uint32_t)want_frags);
 }
 
@@ -584,6 +585,10 @@ int swegl_b200_set_screen(swegl_b200_ctx *ctx, int32_t w, int32_t h)
     size_t bins = (size_t)((w + 31) / 32 + 1) * h;
     CK(dalloc(ctx->pools.bin_head, bins));
     CK(cudaMemset(ctx->pools.bin_head, 0xFF, bins * 4));
+    CK(dalloc(ctx->pools.bin_cnt, bins));
+    CK(cudaMemset(ctx->pools.bin_cnt, 0, bins * 4));
+    CK(dalloc(ctx->pools.bin_slots, bins * BIN_SLOTS));     // 1 KB per 32-pixel bin: 265 MB at 4K, 1.06 GB at 8K (only the used slots are ever touched)
+
     CK(dalloc(ctx->pools.dof_list, bins));              // (a DoF tile is more than one bin)
     ctx->dof_tm_w = ctx->dof_tm_h = 0;                  // d_tmp_color / d_depth moved: the tensor maps are stale
     CK(dalloc(ctx->pools.tile_stamp, bins));            // (a tile is at least one bin)
@@ -931,6 +936,9 @@ static int render_common(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v,
         const Counters &c = *ctx->h_counters;
         stats->n_setup_triangles = c.n_slots; stats->n_spans = c.n_rows; stats->n_chunks = c.n_chunks;
         stats->n_covered = c.n_covered; stats->n_launches = launches; stats->pool_grows = grows;
+#ifdef FRAG_PROBE_MAXLIST
+        stats->n_launches = c.pad; stats->pool_grows = c.dof_queue;     // probe build: bins with more than FRAG_LIST_CAP / 32 pieces
+#endif
         if (timing) {
             cudaEventElapsedTime(&stats->ms_vertex, ctx->ev[0], ctx->ev[1]);
             cudaEventElapsedTime(&stats->ms_setup, ctx->ev[1], ctx->ev[2]);

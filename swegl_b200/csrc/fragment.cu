@@ -238,6 +238,10 @@ SB_DEV bool phong_light_fast(const SpanShade *ss, const ViewParams &vp, const Fr
     return ok;
 }
 
+// one winner -> its colour
+template <int LIGHT, int TEX, int FAST>
+SB_DEV uint32_t shade_winner(const Pools &pl, const uint32_t *texels, const ViewParams &vp, const FrameParams &fp, uint32_t span, uint32_t slot, float u);
+
 // the exact shader, out of line: the fast kernels call it for the few pixels next to a discontinuity
 template <int LIGHT, int TEX>
 static __device__ __noinline__ uint32_t shade_exact_call(const SpanShade *ss, float flat_light, uint4 bind, const uint32_t *texels,
@@ -250,20 +254,35 @@ static __device__ __noinline__ uint32_t shade_exact_call(const SpanShade *ss, fl
     return shade<LIGHT, TEX>(ss, flat_light, pr, texels, *vp, *fp, u);
 }
 
-// chunks of a bin whose records are fetched up front, all bins of the stretch at once; longer lists continue serially
-#ifndef FRAG_LIST_CAP_V
-#define FRAG_LIST_CAP_V 12
+template <int LIGHT, int TEX, int FAST>
+SB_DEV uint32_t shade_winner(const Pools &pl, const uint32_t *texels, const ViewParams &vp, const FrameParams &fp, uint32_t span, uint32_t slot, float u)
+{
+    const SpanShade *ss = &pl.span_shades[span];
+    const SlotShade *sh = &pl.shades[slot];
+    const uint4 bind = *reinterpret_cast<const uint4 *>(&sh->color);       // colour, tex_off, tw, th
+    Prim pr;
+    pr.color = bind.x; pr.tex_off = bind.y; pr.tw = (int32_t)bind.z; pr.th = (int32_t)bind.w;
+    pr.tw_mask = (pr.tw & (pr.tw - 1)) == 0 ? pr.tw - 1 : -1;
+    pr.th_mask = (pr.th & (pr.th - 1)) == 0 ? pr.th - 1 : -1;
+#ifdef FRAG_PROBE_NOSHADE
+    return 0xFF00FF00u ^ bind.x ^ __float_as_uint(u) ^ __float_as_uint(ss->v[0]);      // timing probe only: what the kernel costs without the shader
+#else
+    if (FAST) {
+        const TexFetch tf = tex_fetch<TEX>(ss, pr, texels, u);             // texel loads in flight under the lighting
+        int li;
+        if (phong_light_fast(ss, vp, fp, u, li)) return combine_light(tex_filter<TEX>(tf), li);
+        return shade_exact_call<LIGHT, TEX>(ss, 0.0f, bind, texels, &vp, &fp, u);
+    }
+    return shade<LIGHT, TEX>(ss, sh->flat_light, pr, texels, vp, fp, u);
 #endif
-static constexpr int FRAG_LIST_CAP = FRAG_LIST_CAP_V;
+}
 
-// per-warp staging: the stretch's chunk records (pass 1) and the queue of winning fragments (pass 1 -> 2 -> 3)
+// chunks of a bin whose records are fetched up front, all bins of the stretch at once; longer lists continue serially
+static constexpr int FRAG_STAGE = 16;           // pieces of a bin staged in shared memory per round
+
+// per-warp staging of the slot records of the current round
 struct FragWarp {
-    float u[FRAG_STRETCH * 32];         // interpolator progress of the winner; overwritten by its colour in pass 2
-    uint32_t span[FRAG_STRETCH * 32];   // winning span, 0xFFFFFFFF = background
-    uint32_t slot[FRAG_STRETCH * 32];   // winning slot (-> SlotShade)
-    uint4 rec[FRAG_STRETCH * FRAG_LIST_CAP * 2];    // Chunk records of bin b at [b * FRAG_LIST_CAP ..], 2 x 16 B each
-    int32_t cnt[FRAG_STRETCH], cursor[FRAG_STRETCH];   // staged list lengths, continuation of longer lists
-    uint8_t idx[FRAG_STRETCH * 32];     // compacted list of covered pixels
+    uint4 rec[FRAG_STAGE * 2];          // Chunk records, 2 x 16 B each
 };
 
 // the part of ViewParams that is fixed for a captured frame graph (rectangle, band), passed by value so that the
@@ -336,24 +355,27 @@ SB_DEV void dof_tile_duty(const Pools &pl, const FragGeom &g, uint32_t stamp, ui
 }
 
 // ----------------------------------------------------------------------------------------
-// k_fragments: ONE wave of persistent CTAs; every warp pulls work items from a queue (Counters::frag_queue) until it is
-// empty.  Item q bundles up to three independent duties, so that the streaming stores of the first two drain to
+// k_fragments: ONE wave of persistent CTAs; every CTA takes item after item from a queue (Counters::frag_queue) until it
+// is empty.  Item p bundles up to three independent duties, so that the streaming stores of the first two drain to
 // L2 / HBM underneath the arithmetic of the third:
-//   * clear duty   q < n_tiles        : fragment tile q (8 rows x 128 px), unless k_spans put something into it
-//                                       (tile_stamp), gets the clear values (viewport.cpp:88-113) -- depth always,
-//                                       colour unless the frame protocol cleared it already, or, with DoF-R behind
-//                                       it, only when a DoF window that will really be computed can see the tile;
-//   * DoF duty     q < n_dof          : DoF output tile q is classified (dof_tile_duty) -- constant tiles are stored
-//                                       from here, the others go on k_dof's list;
-//   * busy duty    q < 8 * n_busy     : row (q % 8) of busy tile busy_list[q / 8]: depth resolve, deferred shading of
-//                                       the winners, one 128-byte colour / depth store per bin (see the file header).
-// The unit is a warp, not a CTA: a 4K frame has ~1 500 busy tiles for 1 184 resident CTAs, and a CTA-sized unit
-// leaves the kernel's end to the SMs that drew the heaviest tiles; 12 000 row items balance within a few percent.
-// The next index is fetched while the current item is processed.
+//   * clear duty   tiles 8p .. 8p+7    : warp w looks at fragment tile 8p+w (8 rows x 128 px); unless k_spans put
+//                                       something into it (tile_stamp) it gets the clear values (viewport.cpp:88-113) --
+//                                       depth always, colour unless the frame protocol cleared it already, or, with
+//                                       DoF-R behind it, only when a DoF window that will really be computed can see it;
+//   * DoF duty     tiles 8p .. 8p+7    : warp w classifies DoF output tile 8p+w (dof_tile_duty) -- constant tiles are
+//                                       stored from here, the others go on k_dof's list;
+//   * busy duty    p < n_busy          : warp w takes row w of busy tile busy_list[p]: depth resolve, deferred shading
+//                                       of the winners, one 128-byte colour / depth store per bin (see the file header).
+// A frame has no more empty CTAs in front of the work (8 100 launches for ~1 500 busy tiles at 4K before), the expensive
+// tiles are spread dynamically, and the background never waits behind them.
 // ----------------------------------------------------------------------------------------
 #ifndef FRAG_MINB
-#define FRAG_MINB 8         // 32 registers: all 64 warps of an SM resident
+#define FRAG_MINB 5         // 48 registers, 40 warps per SM: measured against 6 (40 registers) and 8 (32 registers, spills in the shader)
 #endif
+#ifndef FRAG_RESOLVE_UNROLL
+#define FRAG_RESOLVE_UNROLL 4
+#endif
+static constexpr int RESOLVE_UNROLL = FRAG_RESOLVE_UNROLL;     // chunks of a bin whose fragment-stream loads are in flight together
 #ifndef FRAG_CTAS_PER_SM
 #define FRAG_CTAS_PER_SM FRAG_MINB
 #endif
@@ -368,6 +390,7 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
     __shared__ ViewParams vp;
     __shared__ FrameParams fp;
     __shared__ FragWarp fwarp[FRAG_ROWS];
+    __shared__ uint32_t s_next[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int band_rows = g.band1 - g.band0, anchor = g.band0 - g.vy;
     pdl_trigger();
@@ -379,97 +402,78 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
     Counters *const cn = pl.counters;
     const uint32_t n_busy = cn->n_busy;
     const uint32_t stamp = vp.stamp;
-    // first index of this warp; the queue counter was zeroed by k_vertex at the head of the chain
-    uint32_t q_raw = 0;
-    if (lane == 0) q_raw = atomicAdd(&cn->frag_queue, 1u);
-
-    if (blockIdx.x == 0 && warp == 0) {
-        // bounding box of what was drawn (for the host's partial read-back), and k_setup / k_spans' counters (pool demand,
-        // overflow flags) published to the pinned slot the host polls -- instead of a D2H copy node at the end of the graph.
-        // (n_covered is only final after this kernel; the synchronous stats path copies the counters itself.)
-        uint32_t tx0 = 0xFFFFFFFFu, ty0 = 0xFFFFFFFFu, tx1 = 0, ty1 = 0;
-        for (uint32_t i = lane; i < n_busy; i += 32) {
-            const uint32_t t = pl.busy_list[i], ty = t / (uint32_t)g.ntx, tx = t - ty * (uint32_t)g.ntx;
-            tx0 = min(tx0, tx); tx1 = max(tx1, tx + 1); ty0 = min(ty0, ty); ty1 = max(ty1, ty + 1);
-        }
-        #pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            tx0 = min(tx0, __shfl_xor_sync(0xFFFFFFFFu, tx0, o)); ty0 = min(ty0, __shfl_xor_sync(0xFFFFFFFFu, ty0, o));
-            tx1 = max(tx1, __shfl_xor_sync(0xFFFFFFFFu, tx1, o)); ty1 = max(ty1, __shfl_xor_sync(0xFFFFFFFFu, ty1, o));
-        }
-        uint32_t b0 = 0u, b1 = 0u, b2 = 0u, b3 = 0u;
-        if (n_busy) {
-            b0 = tx0 * (FRAG_STRETCH * 32); b1 = (uint32_t)anchor + ty0 * FRAG_ROWS;
-            b2 = min((uint32_t)g.vw, tx1 * (FRAG_STRETCH * 32)); b3 = min((uint32_t)(anchor + band_rows), (uint32_t)anchor + ty1 * FRAG_ROWS);
-        }
-        if (lane == 0) { cn->bb_x0 = b0; cn->bb_y0 = b1; cn->bb_x1 = b2; cn->bb_y1 = b3; }
-        if (h_counters_out && lane < (int)(sizeof(Counters) / 4)) {
-            constexpr int BB = offsetof(Counters, bb_x0) / 4;
-            uint32_t v = reinterpret_cast<const uint32_t *>(cn)[lane];
-            v = lane == BB ? b0 : (lane == BB + 1 ? b1 : (lane == BB + 2 ? b2 : (lane == BB + 3 ? b3 : v)));
-            reinterpret_cast<uint32_t *>(h_counters_out)[lane] = v;
-        }
-    }
-
-    const uint32_t n_items = n_busy * FRAG_ROWS;
-    uint32_t n_total = max(n_items, (uint32_t)g.n_tiles);
-    if (g.dof) n_total = max(n_total, (uint32_t)g.n_dof);
+    // CTA-level items: [0, n_busy) = the busy tiles, then n_groups streaming groups (8 fragment tiles to clear and 8 DoF tiles
+    // to classify, one of each per warp).  Busy tiles come first: the CTAs whose tile was light finish early and take the
+    // streaming groups, whose stores then drain underneath the arithmetic of the heavy tiles.
+    uint32_t n_groups = (uint32_t)(g.n_tiles + FRAG_ROWS - 1) / FRAG_ROWS;
+    if (g.dof) n_groups = max(n_groups, (uint32_t)(g.n_dof + FRAG_ROWS - 1) / FRAG_ROWS);
+    const uint32_t n_pops = n_busy + n_groups;
     const uint32_t dof_fill = g.dof ? dof_background_value(vp) : 0u;
     const uint64_t KEY_INIT = (uint64_t)MAXZ_BITS << 32;
-    const unsigned lt = (1u << lane) - 1u;
     FragWarp &fw = fwarp[warp];
+    uint32_t my_covered = 0;
+    uint32_t tx0 = 0xFFFFFFFFu, ty0 = 0xFFFFFFFFu, tx1 = 0, ty1 = 0;      // bounding box of the busy tiles this CTA worked on (tile units)
 
-    uint32_t q = __shfl_sync(0xFFFFFFFFu, q_raw, 0);
-    while (q < n_total) {
-        if (lane == 0) q_raw = atomicAdd(&cn->frag_queue, 1u);              // the next item's index travels while this one is worked on
+    // The first item of every CTA is its own index (no atomic: a 4K frame has about as many busy tiles as there are CTAs,
+    // and a thousand CTAs hitting one counter in the same microsecond would queue up behind each other); later ones come
+    // from the queue, one atomic per CTA and item, fetched while the current item is worked on.
+    uint32_t p = blockIdx.x;
+    for (int it = 0; p < n_pops; it ^= 1) {
+        uint32_t next_raw = 0;
+        if (threadIdx.x == 0) next_raw = atomicAdd(&cn->frag_queue, 1u);    // consumed at the end of the iteration: the round trip is free
 
-        // ---- clear duty ----
-        if (q < (uint32_t)g.n_tiles && pl.tile_stamp[q] != stamp) {
-            const int ty = (int)q / g.ntx, tx = (int)q - ty * g.ntx;
-            bool with_color = !g.skip_bg;
-            if (g.dof) {
-                // tmp colour is only ever read through the window of a DoF tile that is computed, i.e. one with a busy
-                // fragment tile under its window: two tiles under one window are at most 1 column and 5 rows apart
-                constexpr int NDY = DOF_OH / FRAG_ROWS + 1;                  // 5
-                bool near = false;
-                for (int k = lane; k < 3 * (2 * NDY + 1); k += 32) {
-                    const int yy = ty + k / 3 - NDY, xx = tx + k % 3 - 1;
-                    if (yy >= 0 && yy < g.nty && xx >= 0 && xx < g.ntx) near = near || pl.tile_stamp[yy * g.ntx + xx] == stamp;
+        if (p >= n_busy) {
+            // ---- a streaming group ----
+            const uint32_t q = (p - n_busy) * FRAG_ROWS + (uint32_t)warp;   // this warp's fragment tile / DoF tile
+#ifndef FRAG_PROBE_NOCLEAR
+            if (q < (uint32_t)g.n_tiles && pl.tile_stamp[q] != stamp) {     // clear duty: nothing was drawn into fragment tile q
+                const int ty = (int)q / g.ntx, tx = (int)q - ty * g.ntx;
+                bool with_color = !g.skip_bg;
+                if (g.dof) {
+                    // tmp colour is only ever read through the window of a DoF tile that is computed, i.e. one with a busy
+                    // fragment tile under its window: two tiles under one window are at most 1 column and 5 rows apart
+                    constexpr int NDY = DOF_OH / FRAG_ROWS + 1;              // 5
+                    bool near = false;
+                    for (int k = lane; k < 3 * (2 * NDY + 1); k += 32) {
+                        const int yy = ty + k / 3 - NDY, xx = tx + k % 3 - 1;
+                        if (yy >= 0 && yy < g.nty && xx >= 0 && xx < g.ntx) near = near || pl.tile_stamp[yy * g.ntx + xx] == stamp;
+                    }
+                    with_color = __any_sync(0xFFFFFFFFu, near);
                 }
-                with_color = __any_sync(0xFFFFFFFFu, near);
+                const int row0 = anchor + ty * FRAG_ROWS, bx0 = tx * FRAG_STRETCH;
+                const int rows_here = min(FRAG_ROWS, band_rows - ty * FRAG_ROWS);
+                const int px_left = g.vw - (bx0 << 5);
+                for (int r = 0; r < rows_here; r++)
+                    clear_tile_row(color + (size_t)(g.vy + row0 + r) * color_pitch + g.vx + (bx0 << 5),
+                                   depth + (size_t)(row0 + r) * g.vw + (bx0 << 5), px_left, lane, with_color);
             }
-            const int row0 = anchor + ty * FRAG_ROWS, bx0 = tx * FRAG_STRETCH;
-            const int rows_here = min(FRAG_ROWS, band_rows - ty * FRAG_ROWS);
-            const int px_left = g.vw - (bx0 << 5);
-            for (int r = 0; r < rows_here; r++)
-                clear_tile_row(color + (size_t)(g.vy + row0 + r) * color_pitch + g.vx + (bx0 << 5),
-                               depth + (size_t)(row0 + r) * g.vw + (bx0 << 5), px_left, lane, with_color);
-        }
-        // ---- DoF duty ----
-        if (g.dof && q < (uint32_t)g.n_dof) dof_tile_duty(pl, g, stamp, dof_fill, dof_dst, q, lane);
-
-        // ---- busy duty ----
-        if (q < n_items) do {
-            const int t = (int)pl.busy_list[q / FRAG_ROWS], r = (int)(q % FRAG_ROWS);
+            if (g.dof && q < (uint32_t)g.n_dof) dof_tile_duty(pl, g, stamp, dof_fill, dof_dst, q, lane);   // DoF duty
+#endif
+        } else do {
+            // ---- a busy tile: the CTA's warps take its rows (their spans, pieces and texels are neighbours in memory) ----
+            const int t = (int)pl.busy_list[p];
             const int ty = t / g.ntx, tx = t - ty * g.ntx;
-            if (r >= min(FRAG_ROWS, band_rows - ty * FRAG_ROWS)) break;
-            const int row = anchor + ty * FRAG_ROWS + r;                    // viewport-relative
+            tx0 = min(tx0, (uint32_t)tx); tx1 = max(tx1, (uint32_t)tx + 1); ty0 = min(ty0, (uint32_t)ty); ty1 = max(ty1, (uint32_t)ty + 1);
+            if (warp >= min(FRAG_ROWS, band_rows - ty * FRAG_ROWS)) break;
+            const int row = anchor + ty * FRAG_ROWS + warp;                 // viewport-relative
             const int y = g.vy + row;
             const int bx0 = tx * FRAG_STRETCH;
             const int nb = min(FRAG_STRETCH, g.nbx - bx0);
             const int px_left = g.vw - (bx0 << 5);                          // pixels from the stretch start to the row end
-            int32_t head = -1;
-            if (lane < nb) {                                                // fetch and reset the bin heads of the stretch
-                int32_t *hp = pl.bin_head + (size_t)row * g.nbx + bx0 + lane;
-                head = *hp;
-                if (head >= 0) *hp = -1;
+            // the bins' piece counts (and overflow lists), fetched and reset for the next frame
+            const size_t bin0 = (size_t)row * g.nbx + bx0;
+            int32_t cnt = 0, over = -1;
+            if (lane < nb) {
+                cnt = pl.bin_cnt[bin0 + lane];
+                if (cnt > 0) pl.bin_cnt[bin0 + lane] = 0;
+                if (cnt > BIN_SLOTS) { over = pl.bin_head[bin0 + lane]; pl.bin_head[bin0 + lane] = -1; }
             }
-            unsigned mask = __ballot_sync(0xFFFFFFFFu, head >= 0);
+            unsigned mask = __ballot_sync(0xFFFFFFFFu, cnt > 0);
             uint32_t *crow = color + (size_t)y * color_pitch + g.vx + (bx0 << 5);
             float *drow = depth + (size_t)row * g.vw + (bx0 << 5);
             const bool aligned = ((reinterpret_cast<uintptr_t>(crow) | reinterpret_cast<uintptr_t>(drow)) & 15) == 0;
             // ---- empty bins ----
-            if (mask != (nb == 32 ? 0xFFFFFFFFu : (1u << nb) - 1u)) {
+            if (mask != (1u << nb) - 1u) {
                 const float maxz = __uint_as_float(MAXZ_BITS);
                 for (int i = lane; i < nb * 8; i += 32) {
                     const int b = i >> 3, px = (b << 5) + ((i & 7) << 2);
@@ -484,50 +488,39 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
                 }
             }
             if (!mask) break;
-            // ---- non-empty bins, pass 1: depth resolve.
-            //  a. the first lanes walk one bin list each (FRAG_STRETCH pointer chases side by side instead of one after the
-            //     other) and leave the chunk records in shared memory;
-            //  b. lane = pixel: per bin, the nearest fragment of every pixel is kept in registers.  Depth is written at once,
-            //     and the winners of the whole stretch are queued in shared memory so that shading (pass 2) runs on dense
-            //     batches of 32 covered pixels. ----
-            if (lane < FRAG_STRETCH) {
-                int n = 0;
-                int32_t c = head;
-                while (c >= 0 && n < FRAG_LIST_CAP) {
-                    const uint4 *src = reinterpret_cast<const uint4 *>(&pl.chunks[c]);
-                    const uint4 r0 = src[0], r1 = src[1];
-                    fw.rec[2 * (lane * FRAG_LIST_CAP + n)] = r0; fw.rec[2 * (lane * FRAG_LIST_CAP + n) + 1] = r1;
-                    n++;
-                    c = (int32_t)r1.z;                                              // Chunk::next
-                }
-                fw.cnt[lane] = n; fw.cursor[lane] = c;
-            }
-            __syncwarp();
-            uint32_t n_hit = 0;
-            const unsigned used = mask;
+            // ---- non-empty bins: depth resolve.  Per bin, rounds of up to FRAG_STAGE pieces: the lanes fetch one slot record
+            //      each (independent loads, one round trip) into shared memory, then lane = pixel and the nearest fragment of
+            //      every pixel is kept in registers ----
             while (mask) {
                 const int b = __ffs(mask) - 1;
                 mask &= mask - 1;
                 uint64_t best = KEY_INIT;
                 float best_u = 0.f;
                 uint32_t best_span = 0xFFFFFFFFu;
-                const int n = fw.cnt[b];
-                const uint4 *rec = &fw.rec[2 * b * FRAG_LIST_CAP];
-                #pragma unroll 2
-                for (int k = 0; k < n; k++) {
-                    const uint4 r0 = rec[2 * k];                                    // frag0, xs_xe, v0, v1
-                    const unsigned xs = r0.y & 0xFFu, wd = (r0.y >> 8) - xs;
-                    if ((unsigned)lane - xs < wd) {
-                        const float u = pl.frag_u[r0.x + (uint32_t)lane];           // qpixel.ualpha, replayed by k_spans
+                const int n = min(__shfl_sync(0xFFFFFFFFu, cnt, b), BIN_SLOTS);
+                const Chunk *slots = pl.bin_slots + (bin0 + b) * BIN_SLOTS;
+                for (int base = 0; base < n; base += FRAG_STAGE) {
+                    const int m = min(FRAG_STAGE, n - base);
+                    __syncwarp();                                                   // the previous round's records are consumed
+                    if (lane < 2 * m) fw.rec[lane] = reinterpret_cast<const uint4 *>(slots + base)[lane];   // lane = half a record
+                    __syncwarp();
+                    // every lane loads for every piece (a lane outside the piece reads entry 0 instead): loads without a branch
+                    // in front of them can be issued RESOLVE_UNROLL at a time
+                    #pragma unroll RESOLVE_UNROLL
+                    for (int k = 0; k < m; k++) {
+                        const uint4 r0 = fw.rec[2 * k];                             // frag0, xs_xe, v0, v1
+                        const unsigned xs = r0.y & 0xFFu, wd = (r0.y >> 8) - xs;
+                        const bool in = (unsigned)lane - xs < wd;
+                        const float u = pl.frag_u[in ? r0.x + (uint32_t)lane : 0u]; // qpixel.ualpha, replayed by k_spans
                         const float z = fadd(__uint_as_float(r0.z), fmul(__uint_as_float(r0.w), u));   // value(0), renderer.cpp:488
-                        if (z >= NEAR_Z) {                                          // renderer.cpp:489-492
-                            const uint2 r1 = *reinterpret_cast<const uint2 *>(&rec[2 * k + 1]);       // slot, span
+                        if (in && z >= NEAR_Z) {                                    // renderer.cpp:489-492
+                            const uint2 r1 = *reinterpret_cast<const uint2 *>(&fw.rec[2 * k + 1]);     // slot, span
                             const uint64_t key = ((uint64_t)__float_as_uint(z) << 32) | r1.x;
                             if (key < best) { best = key; best_u = u; best_span = r1.y; }
                         }
                     }
                 }
-                for (int32_t c = fw.cursor[b]; c >= 0;) {                           // a list longer than FRAG_LIST_CAP: the rest, serially
+                for (int32_t c = __shfl_sync(0xFFFFFFFFu, over, b); c >= 0;) {      // more than BIN_SLOTS pieces: the rest, serially
                     const Chunk ch = pl.chunks[c];
                     c = ch.next;
                     const int xs = (int)(ch.xs_xe & 0xFFu), xe = (int)(ch.xs_xe >> 8);
@@ -543,53 +536,41 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
                 const int px = (b << 5) + lane;
                 const bool inside = px < px_left;
                 const bool hit = best_span != 0xFFFFFFFFu && inside;
+                // depth and colour of the bin at once: lane = pixel, the winner is shaded by its own lane (only the visible
+                // fragment of a pixel is ever shaded).  Resolve and shading alternate bin by bin, so the warps of an SM drift out
+                // of phase -- some wait for loads while others compute -- and nothing but the slot records passes through
+                // shared memory.  (Round 1 queued the winners of the whole 128-pixel stretch and shaded them in dense batches of
+                // 32: 10 % more lanes busy in the shader, paid for with three more passes over shared memory; measured equal.)
                 if (inside) drow[px] = __uint_as_float((uint32_t)(best >> 32));
-                fw.u[px] = best_u; fw.span[px] = hit ? best_span : 0xFFFFFFFFu; fw.slot[px] = (uint32_t)best;
-                const unsigned hm = __ballot_sync(0xFFFFFFFFu, hit);
-                if (hit) fw.idx[n_hit + __popc(hm & lt)] = (uint8_t)px;
-                n_hit += __popc(hm);
+                uint32_t out = 0u;                                                  // background pixels of a used bin get 0
+                if (hit) out = shade_winner<LIGHT, TEX, FAST>(pl, s.texels, vp, fp, best_span, (uint32_t)best, best_u);
+                if (inside) crow[px] = out;
+                my_covered += __popc(__ballot_sync(0xFFFFFFFFu, hit));
             }
-            __syncwarp();
-            // ---- pass 2: shade the queued winners, 32 at a time (deferred: only the visible fragment of a pixel is shaded) ----
-            for (uint32_t k = lane; k < n_hit; k += 32) {
-                const int px = fw.idx[k];
-                const SpanShade *ss = &pl.span_shades[fw.span[px]];
-                const SlotShade *sh = &pl.shades[fw.slot[px]];
-                const uint4 bind = *reinterpret_cast<const uint4 *>(&sh->color);   // colour, tex_off, tw, th
-                const float u = fw.u[px];
-                uint32_t out;
-                if (FAST) {
-                    Prim pr;
-                    pr.color = bind.x; pr.tex_off = bind.y; pr.tw = (int32_t)bind.z; pr.th = (int32_t)bind.w;
-                    pr.tw_mask = (pr.tw & (pr.tw - 1)) == 0 ? pr.tw - 1 : -1;
-                    pr.th_mask = (pr.th & (pr.th - 1)) == 0 ? pr.th - 1 : -1;
-                    const TexFetch tf = tex_fetch<TEX>(ss, pr, s.texels, u);       // texel loads in flight under the lighting
-                    int li;
-                    if (phong_light_fast(ss, vp, fp, u, li)) out = combine_light(tex_filter<TEX>(tf), li);
-                    else out = shade_exact_call<LIGHT, TEX>(ss, 0.0f, bind, s.texels, &vp, &fp, u);
-                } else {
-                    Prim pr;
-                    pr.color = bind.x; pr.tex_off = bind.y; pr.tw = (int32_t)bind.z; pr.th = (int32_t)bind.w;
-                    pr.tw_mask = (pr.tw & (pr.tw - 1)) == 0 ? pr.tw - 1 : -1;
-                    pr.th_mask = (pr.th & (pr.th - 1)) == 0 ? pr.th - 1 : -1;
-                    out = shade<LIGHT, TEX>(ss, sh->flat_light, pr, s.texels, vp, fp, u);
-                }
-                fw.u[px] = __uint_as_float(out);
-            }
-            __syncwarp();
-            // ---- pass 3: colour write-back, one 128-byte segment per bin (background pixels of a used bin get 0) ----
-            mask = used;
-            while (mask) {
-                const int b = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const int px = (b << 5) + lane;
-                if (px < px_left) crow[px] = fw.span[px] != 0xFFFFFFFFu ? __float_as_uint(fw.u[px]) : 0u;
-            }
-            if (count_covered && lane == 0 && n_hit) atomicAdd(&cn->n_covered, n_hit);
             __syncwarp();                                                   // fw is reused by the next item
         } while (0);
 
-        q = __shfl_sync(0xFFFFFFFFu, q_raw, 0);
+        if (threadIdx.x == 0) s_next[it] = gridDim.x + next_raw;
+        __syncthreads();                                                    // every warp is done with item p; the next index is visible
+        p = s_next[it];
+    }
+    if (count_covered && lane == 0 && my_covered) atomicAdd(&cn->n_covered, my_covered);
+    // The frame's bounding box (for the host's partial read-back) is the union over the CTAs; the last CTA to finish
+    // publishes the counters of the frame (pool demand and overflow flags of k_setup / k_spans, covered pixels, the box)
+    // to the pinned slot the host polls -- instead of a D2H copy node at the end of the graph.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (tx1) {
+            atomicMin(&cn->bb_x0, tx0 * (FRAG_STRETCH * 32)); atomicMin(&cn->bb_y0, (uint32_t)anchor + ty0 * FRAG_ROWS);
+            atomicMax(&cn->bb_x1, min((uint32_t)g.vw, tx1 * (FRAG_STRETCH * 32)));
+            atomicMax(&cn->bb_y1, min((uint32_t)(anchor + band_rows), (uint32_t)anchor + ty1 * FRAG_ROWS));
+        }
+        __threadfence();
+        if (atomicAdd(&cn->frag_done, 1u) == gridDim.x - 1 && h_counters_out) {
+            __threadfence();
+            for (int w = 0; w < (int)(sizeof(Counters) / 4); w++)
+                reinterpret_cast<volatile uint32_t *>(h_counters_out)[w] = reinterpret_cast<volatile const uint32_t *>(cn)[w];
+        }
     }
 }
 
@@ -668,13 +649,15 @@ __global__ void __launch_bounds__(FRAG_TPB) k_fragments_layers(DeviceScene s, co
     const int L = vp.n_layers;
     const uint64_t KEY_INIT = (uint64_t)MAXZ_BITS << 32;
 
-    int32_t *headp = pl.bin_head + (size_t)row * vp.nbx + bx0 + lane;
-    int32_t head = -1;
+    // the bins' piece counts and overflow lists (common.cuh BIN_SLOTS), fetched and reset for the next frame
+    const size_t bin0 = (size_t)row * vp.nbx + bx0;
+    int32_t cnt = 0, head = -1;
     if (lane < nb) {
-        head = *headp;
-        if (head >= 0) *headp = -1;
+        cnt = pl.bin_cnt[bin0 + lane];
+        if (cnt > 0) pl.bin_cnt[bin0 + lane] = 0;
+        if (cnt > BIN_SLOTS) { head = pl.bin_head[bin0 + lane]; pl.bin_head[bin0 + lane] = -1; }
     }
-    unsigned mask = __ballot_sync(0xFFFFFFFFu, head >= 0);
+    unsigned mask = __ballot_sync(0xFFFFFFFFu, cnt > 0);
     uint32_t *crow = color + (size_t)y * color_pitch + vp.vx + (bx0 << 5);
     float *drow = depth + (size_t)row * vp.vw + (bx0 << 5);
     const int px_left = vp.vw - (bx0 << 5);
@@ -686,15 +669,17 @@ __global__ void __launch_bounds__(FRAG_TPB) k_fragments_layers(DeviceScene s, co
             continue;
         }
         int32_t c = __shfl_sync(0xFFFFFFFFu, head, b);
+        const int n_in = min(__shfl_sync(0xFFFFFFFFu, cnt, b), BIN_SLOTS);
         uint64_t best = KEY_INIT;                                           // opaque base: z bits << 32 | slot
         float best_u = 0.f;
         uint32_t best_span = 0xFFFFFFFFu;
         // kept transparent fragments, nearest first: key = z bits << 32 | ~slot (a later draw at equal depth is nearer)
         uint64_t tkey[MAX_LAYERS]; float tu[MAX_LAYERS]; uint32_t tspan[MAX_LAYERS];
         int tn = 0;
-        while (c >= 0) {
-            const Chunk ch = pl.chunks[c];
-            c = ch.next;
+        for (int k = 0; k < n_in || c >= 0; k++) {                          // the bin's own slots, then its overflow list
+            Chunk ch;
+            if (k < n_in) ch = pl.bin_slots[(bin0 + b) * BIN_SLOTS + k];
+            else { ch = pl.chunks[c]; c = ch.next; }
             const int xs = (int)(ch.xs_xe & 0xFFu), xe = (int)(ch.xs_xe >> 8);
             if (lane < xs || lane >= xe) continue;
             const float u = pl.frag_u[ch.frag0 + (uint32_t)lane];
@@ -876,6 +861,9 @@ __global__ void __launch_bounds__(DOF_THREADS, 4) k_dof(const __grid_constant__ 
     }
     __syncthreads();
     const uint32_t fill = dof_background_value(vp);
+    // the classification constants live in registers for the whole kernel (13 pixels per thread and tile use them)
+    const float fd = vp.focal_distance, th0 = vp.dof_t[0], th1 = vp.dof_t[1], th2 = vp.dof_t[2], th3 = vp.dof_t[3], th4 = vp.dof_t[4], t_on = vp.dof_on;
+    const int const_radius = vp.dof_const_radius;
     uint32_t phase = 0;
     int cur = 0;
     for (;;) {
@@ -911,9 +899,11 @@ __global__ void __launch_bounds__(DOF_THREADS, 4) k_dof(const __grid_constant__ 
             uint32_t radius = 0;
             if (zb != 0u) {                                                 // the pixel exists (a real depth is >= 0.001 or 0x7F7F7F7F)
                 bg = bg && c == 0u && zb == MAXZ_BITS;
-                const DofClass dc = dof_classify(vp, __uint_as_float(zb));
-                radius = dc.radius;
-                if (dc.counts) {
+                const float t = fabsf(fsub(fd, __uint_as_float(zb)));      // dof_classify with the constants in registers
+                radius = (t >= th0) + (t >= th1) + (t >= th2) + (t >= th3) + (t >= th4);
+                bool counts = t > t_on;
+                if (const_radius >= 0) { radius = (uint32_t)const_radius; counts = true; }
+                if (counts) {
                     const uint32_t b = c & 0xFFu, gg = (c >> 8) & 0xFFu, r = (c >> 16) & 0xFFu;
                     const uint32_t lo = b | (gg << 15) | (r << 30), hi = (r >> 2) | (1u << 13);
                     v = ((unsigned long long)hi << 32) | lo;

@@ -9,6 +9,7 @@
 // The fp32 recurrences (edge x += ratio, topalpha += topstep ...) must see the same additions as the
 // CPU renderer for coverage and depth to be bit-identical; radd() (radd.h) performs k of them in
 // O(1), so there is no serial edge walk: one thread per vertex / triangle / scanline everywhere.
+#include <cstddef>
 #include "common.cuh"
 
 namespace sb {
@@ -135,7 +136,8 @@ __global__ void __launch_bounds__(TPB, 8) k_vertex(DeviceScene s, const ViewPara
 {
     pdl_trigger();
     __shared__ ViewParams vp;
-    if (blockIdx.x == 0 && threadIdx.x < sizeof(Counters) / 4) reinterpret_cast<uint32_t *>(counters)[threadIdx.x] = 0;
+    if (blockIdx.x == 0 && threadIdx.x < sizeof(Counters) / 4)
+        reinterpret_cast<uint32_t *>(counters)[threadIdx.x] = (threadIdx.x == offsetof(Counters, bb_x0) / 4 || threadIdx.x == offsetof(Counters, bb_y0) / 4) ? COUNTERS_BB_MIN_INIT : 0u;
     for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
     __syncthreads();
     if (s.vert_list) {
@@ -549,11 +551,11 @@ SB_DEV void walk_segment(const Pools &pl, const ViewParams &vp, const SH &sh, in
     int x = c0 == 0 ? o_x1 : vp.vx + (b0 << 5);                             // first column of the segment
     const int xend = min(vp.vx + ((b0 + n) << 5), o_x2);                    // one past its last column
     const int row_rel = sh.y[owner] - vp.vy;
-    int32_t *heads = pl.bin_head + (size_t)row_rel * vp.nbx + b0;
+    const size_t bin0 = (size_t)row_rel * vp.nbx + b0;
     const uint32_t cid0 = sh.cbase[owner] + c0;
-    int32_t nxt[SPAN_SEG];
+    int32_t pos[SPAN_SEG];                                                  // arrival order of this piece in its bin
     #pragma unroll
-    for (int j = 0; j < (int)SPAN_SEG; j++) nxt[j] = j < n ? atomicExch(&heads[j], (int32_t)(cid0 + j)) : 0;
+    for (int j = 0; j < (int)SPAN_SEG; j++) pos[j] = j < n ? atomicAdd(&pl.bin_cnt[bin0 + j], 1) : 0;
     const uint32_t steps = (uint32_t)(x - o_x1);
     Interp w;
     w.topstep = sh.topstep[owner]; w.bottomstep = sh.bottomstep[owner];
@@ -584,8 +586,13 @@ SB_DEV void walk_segment(const Pools &pl, const ViewParams &vp, const SH &sh, in
         const int xn = min(binx0 + 32, o_x2);                               // end of this bin's piece of the span
         ch.frag0 = o_fb + (uint32_t)(binx0 - o_x1);                         // wraps for the span's first bin; lanes < xs never read
         ch.xs_xe = (uint32_t)(xc - binx0) | ((uint32_t)(xn - binx0) << 8);
-        ch.next = nxt[j];
-        pl.chunks[cid0 + j] = ch;
+        ch.next = -1;
+        if (pos[j] < BIN_SLOTS) {                                           // the bin's own slots: no list
+            pl.bin_slots[(bin0 + j) * BIN_SLOTS + pos[j]] = ch;
+        } else {                                                            // a crowded bin: the rest is linked
+            ch.next = atomicExch(&pl.bin_head[bin0 + j], (int32_t)(cid0 + j));
+            pl.chunks[cid0 + j] = ch;
+        }
         xc = xn;
     }
     // first chunk of a bin this frame: note the bin's tile once per frame (Pools::busy_list)
@@ -593,7 +600,7 @@ SB_DEV void walk_segment(const Pools &pl, const ViewParams &vp, const SH &sh, in
     #pragma unroll
     for (int j = 0; j < (int)SPAN_SEG; j++) {
         tl[j] = 0xFFFFFFFFu; old[j] = 0;
-        if (j < n && nxt[j] < 0) {
+        if (j < n && pos[j] == 0) {
             const uint32_t t = (uint32_t)((row_rel - (vp.band0 - vp.vy)) / FRAG_ROWS) * (uint32_t)vp.ntx + (uint32_t)((b0 + j) / FRAG_STRETCH);
             bool dup = false;
             #pragma unroll
