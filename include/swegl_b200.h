@@ -264,6 +264,16 @@ int  swegl_b200_device_buffers(swegl_b200_ctx *ctx, void **screen_dev, void **de
 /* copy rows [y0,y1) of the device screen to host */
 int  swegl_b200_read_screen(swegl_b200_ctx *ctx, int32_t y0, int32_t y1, void *pixels, int32_t pitch_bytes);
 int  swegl_b200_read_depth(swegl_b200_ctx *ctx, float *zbuffer);
+/* a rectangle of the device screen into its place in a host surface (`pixels` = the surface's origin), and rows
+ * [row0, row1) of the last viewport's depth into their place in a host depth buffer: what a multi-context host uses to
+ * assemble viewport_t::m_screen / m_zbuffer (swegl_b200/host/swegl_b200_host.hpp) */
+int  swegl_b200_read_rect(swegl_b200_ctx *ctx, int32_t x, int32_t y, int32_t w, int32_t h, void *pixels, int32_t pitch_bytes);
+int  swegl_b200_read_depth_rows(swegl_b200_ctx *ctx, int32_t row0, int32_t row1, float *zbuffer);
+/* Several contexts of ONE process, one per GPU: lets this context's device store into `peer_device`'s memory (NVLink peer
+ * access), so that another context's screen pointer (swegl_b200_device_buffers) can be this one's colour target without the
+ * CUDA IPC detour of export / import_screen.  SWEGL_B200_ERR_UNSUPPORTED when the devices cannot reach each other. */
+int  swegl_b200_enable_peer(swegl_b200_ctx *ctx, int peer_device);
+int  swegl_b200_device_of(const swegl_b200_ctx *ctx);
 /* post-render vertex state of the last viewport, as the reference leaves it in
  * mesh_vertex_t: any pointer may be null. v_viewport holds pixel coordinates
  * for yes-vertices and NDC for the others (vertex_shaders.hpp:72-84).  After a band-culled view only the vertex

@@ -21,6 +21,8 @@ ORACLE_LIB = os.path.join(HERE, "liboracle.so")
 REF_LIB = os.path.join(HERE, "_ref", "libswegl_ref.so")
 # the same driver + unmodified reference sources, with swegl::_render supplied by swegl_b200/host/renderer_b200.cpp
 DROPIN_LIB = os.path.join(HERE, "_ref", "libswegl_dropin.so")
+# the reference with post_shader_depth_box repaired by oracle/dof_r.patch (the pin of the oracle's DoF-R)
+REF_DOFR_LIB = os.path.join(HERE, "_ref", "libswegl_ref_dofr.so")
 
 
 def build(ref=True):
@@ -126,6 +128,7 @@ class Ref:
             "ref_screen_pixels": (vp, [vp]),
             "ref_viewport_new": (vp, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
             "ref_viewport_free": (None, [vp]),
+            "ref_viewport_set_dof": (None, [vp, C.c_float, C.c_float]),
             "ref_viewport_camera": (None, [vp, C.c_int, C.c_float, C.c_float, C.c_float]),
             "ref_viewport_get": (None, [vp, vp, vp, vp, vp]),
             "ref_viewport_zbuffer": (vp, [vp]),
@@ -287,7 +290,7 @@ class Ref:
         return dict(v_world=vw, v_viewport=vv, normal_world=nw, yes=yes)
 
     # ---- viewports ----
-    def make_viewport(self, screen, viewport, camera_ops):
+    def make_viewport(self, screen, viewport, camera_ops, with_dof=False):
         """viewport: swegl_b200.Viewport (rectangle + shader modes); camera_ops replayed on the reference camera."""
         v = self.lib.ref_viewport_new(screen, viewport.x, viewport.y, viewport.w, viewport.h,
                                       viewport.light_mode, viewport.tex_mode, viewport.transparency_layers)
@@ -295,6 +298,8 @@ class Ref:
         for op in camera_ops:
             args = list(op[1:]) + [0.0] * (3 - len(op[1:]))
             self.lib.ref_viewport_camera(v, opcode[op[0]], *args)
+        if with_dof and viewport.post_mode == 1:            # post_shader_depth_box (src/test_1.cpp:355)
+            self.lib.ref_viewport_set_dof(v, float(viewport.focal_distance), float(viewport.focal_depth))
         return v
 
     def viewport_matrices(self, v):

@@ -71,6 +71,7 @@ struct ref_viewport
 	std::shared_ptr<swegl::pixel_shader_t> shader;
 	std::unique_ptr<swegl::viewport_t> vp;
 	swegl::post_shader_t post_null;
+	std::unique_ptr<swegl::post_shader_depth_box> post_dof;     // installed by ref_viewport_set_dof
 };
 
 template <typename L>
@@ -94,6 +95,10 @@ void reserve_clip_slots(swegl::scene_t & scene)
 			primitive.vertices.reserve(primitive.vertices.size() + 2);
 }
 } // namespace
+
+#ifdef SWEGL_B200_DROPIN
+#include "swegl_b200_host.hpp"
+#endif
 
 extern "C"
 {
@@ -423,6 +428,16 @@ void * ref_viewport_new(void * screen, int x, int y, int w, int h, int light_mod
 }
 void ref_viewport_free(void * h) { delete static_cast<ref_viewport *>(h); }
 
+// src/test_1.cpp:355: post_shader_depth_box(focal_distance, focal_depth, viewport).  In libswegl_ref.so this is the
+// reference's DoF as shipped (reads out of bounds: do not call it there); libswegl_ref_dofr.so is built from the header
+// repaired by oracle/dof_r.patch; in libswegl_dropin.so the adapter recognises the type and runs DoF-R on the device.
+void ref_viewport_set_dof(void * h, float focal_distance, float focal_depth)
+{
+	auto * v = static_cast<ref_viewport *>(h);
+	v->post_dof = std::make_unique<swegl::post_shader_depth_box>(focal_distance, focal_depth, *v->vp);
+	v->vp->set_post_shader(*v->post_dof);
+}
+
 // op: 0 translate(a,b,c)  1 rotate_x(a)  2 rotate_y(a)  3 rotate_z(a)   (src/projection/camera.cpp:37-58)
 void ref_viewport_camera(void * h, int op, float a, float b, float c)
 {
@@ -487,5 +502,44 @@ double ref_time_render(void * scene, void * viewport, int warmup, int frames, do
 	}
 	return total;
 }
+
+#ifdef SWEGL_B200_DROPIN
+// Only in libswegl_dropin.so: the multi-context C++ hosts of swegl_b200/host/swegl_b200_host.hpp driven with the
+// reference's own scene_t / viewport_t objects (tests/test_dropin_gpu.py).
+// `frames` frames of one viewport through swegl_b200::pipeline_t (depth contexts, round robin); the camera turns by
+// `dyaw` before every frame; the LAST frame is collected into the viewport's surface
+void ref_render_pipelined(void * scene, void * viewport, int depth, int frames, float dyaw)
+{
+	auto & sc = static_cast<ref_scene *>(scene)->scene;
+	auto & vp = *static_cast<ref_viewport *>(viewport)->vp;
+	swegl_b200::pipeline_t pipe(0, depth);
+	int slot = 0;
+	for (int i = 0; i < frames; i++)
+	{
+		vp.camera().rotate_y(dyaw);
+		slot = pipe.submit(sc, vp);
+	}
+	pipe.collect(slot, vp);
+	pipe.synchronize();
+}
+
+// one frame of one viewport in `n_ctx` row bands (contexts of device 0 standing in for GPUs), `frames` times
+void ref_render_sharded(void * scene, void * viewport, int n_ctx, int frames)
+{
+	auto & sc = static_cast<ref_scene *>(scene)->scene;
+	auto & vp = *static_cast<ref_viewport *>(viewport)->vp;
+	swegl_b200::sharded_renderer_t sh(std::vector<int>((size_t)n_ctx, 0));
+	for (int i = 0; i < frames; i++) sh.render(sc, vp);
+}
+
+// swegl::render(scene, vp1, vp2, vp3, vp4) with one viewport per context
+void ref_render_sharded4(void * scene, void * vp1, void * vp2, void * vp3, void * vp4, int n_ctx)
+{
+	auto & sc = static_cast<ref_scene *>(scene)->scene;
+	swegl_b200::sharded_renderer_t sh(std::vector<int>((size_t)n_ctx, 0));
+	sh.render(sc, *static_cast<ref_viewport *>(vp1)->vp, *static_cast<ref_viewport *>(vp2)->vp,
+	          *static_cast<ref_viewport *>(vp3)->vp, *static_cast<ref_viewport *>(vp4)->vp);
+}
+#endif
 
 } // extern "C"

@@ -97,6 +97,10 @@ SYMBOLS = [
     ("swegl_b200_device_buffers", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     ("swegl_b200_read_screen", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     ("swegl_b200_read_depth", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("swegl_b200_read_rect", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
+    ("swegl_b200_read_depth_rows", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    ("swegl_b200_enable_peer", C.c_int, [C.c_void_p, C.c_int]),
+    ("swegl_b200_device_of", C.c_int, [C.c_void_p]),
     ("swegl_b200_read_vertices", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("swegl_b200_set_frame_sync", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     ("swegl_b200_frame_sync_status", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1233,6 +1233,44 @@ int swegl_b200_read_screen(swegl_b200_ctx *ctx, int32_t y0, int32_t y1, void *pi
     return SWEGL_B200_OK;
 }
 
+int swegl_b200_read_rect(swegl_b200_ctx *ctx, int32_t x, int32_t y, int32_t w, int32_t h, void *pixels, int32_t pitch_bytes)
+{
+    if (!ctx || !pixels || !ctx->d_screen || x < 0 || y < 0 || w <= 0 || h <= 0 || x + w > ctx->sw || y + h > ctx->sh || pitch_bytes < w * 4)
+        return fail(ctx, SWEGL_B200_ERR_ARG, "read_rect: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy2DAsync((char *)pixels + (size_t)y * pitch_bytes + (size_t)x * 4, (size_t)pitch_bytes, ctx->d_screen + (size_t)y * ctx->sw + x,
+                         (size_t)ctx->sw * 4, (size_t)w * 4, (size_t)h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_read_depth_rows(swegl_b200_ctx *ctx, int32_t row0, int32_t row1, float *zbuffer)
+{
+    if (!ctx || !zbuffer || !ctx->have_vp) return fail(ctx, SWEGL_B200_ERR_ARG, "read_depth_rows: nothing rendered");
+    const ViewParams &vp = ctx->last_vp;
+    if (row0 < 0 || row1 > vp.vh || row0 > row1) return fail(ctx, SWEGL_B200_ERR_ARG, "read_depth_rows: bad rows");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(zbuffer + (size_t)row0 * vp.vw, ctx->d_depth + (size_t)row0 * vp.vw, (size_t)(row1 - row0) * vp.vw * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_enable_peer(swegl_b200_ctx *ctx, int peer_device)
+{
+    if (!ctx || peer_device < 0) return fail(ctx, SWEGL_B200_ERR_ARG, "enable_peer: bad device");
+    if (peer_device == ctx->device) return SWEGL_B200_OK;
+    CK(cudaSetDevice(ctx->device));
+    int can = 0;
+    CK(cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
+    if (!can) return fail(ctx, SWEGL_B200_ERR_UNSUPPORTED, "enable_peer: the devices have no peer access (NVLink / PCIe P2P)");
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+    CK(e);
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_device_of(const swegl_b200_ctx *ctx) { return ctx ? ctx->device : -1; }
+
 int swegl_b200_read_depth(swegl_b200_ctx *ctx, float *zbuffer)
 {
     if (!ctx || !zbuffer || !ctx->have_vp) return fail(ctx, SWEGL_B200_ERR_ARG, "read_depth: nothing rendered");

@@ -84,15 +84,19 @@ public:
 		check(swegl_b200_begin_frame(m_ctx, &fd), "begin_frame");
 	}
 
-	// the body of swegl::_render(scene, viewport)
-	void render_viewport(swegl::scene_t &, swegl::viewport_t & vp)
+	// the device screen follows the SDL surface the viewports draw into
+	void ensure_screen(const SDL_Surface * screen)
 	{
-		SDL_Surface * screen = vp.m_screen;
 		if (screen->w != m_screen_w || screen->h != m_screen_h)
 		{
 			check(swegl_b200_set_screen(m_ctx, screen->w, screen->h), "set_screen");
 			m_screen_w = screen->w; m_screen_h = screen->h;
 		}
+	}
+
+	// viewport_t + camera_t + shader selection -> the C ABI's description of one view
+	static swegl_b200_viewport_desc describe(swegl::viewport_t & vp)
+	{
 		swegl_b200_viewport_desc d{};
 		d.x = vp.m_x; d.y = vp.m_y; d.w = vp.m_w; d.h = vp.m_h;
 		for (int r = 0; r < 4; r++)
@@ -114,7 +118,29 @@ public:
 			d.focal_depth = dof->focal_depth;
 		}
 		d.transparency_layers = vp.m_got_transparency ? (int32_t)vp.m_transparency_layers.size() : 0;
+		return d;
+	}
+
+	// the body of swegl::_render(scene, viewport): the frame is in vp.m_screen->pixels / vp.zbuffer() on return
+	void render_viewport(swegl::scene_t &, swegl::viewport_t & vp)
+	{
+		SDL_Surface * screen = vp.m_screen;
+		ensure_screen(screen);
+		const swegl_b200_viewport_desc d = describe(vp);
 		check(swegl_b200_render_viewport(m_ctx, &d, screen->pixels, screen->pitch, vp.zbuffer(), nullptr), "render_viewport");
+	}
+
+	// the same with the result left in HBM (asynchronous when stats == nullptr): the multi-context hosts of
+	// swegl_b200_host.hpp read it back themselves
+	void render_viewport_device(const swegl_b200_viewport_desc & d, swegl_b200_stats * stats = nullptr)
+	{
+		check(swegl_b200_render_viewport_device(m_ctx, &d, stats), "render_viewport_device");
+	}
+
+	void check(int rc, const char * what)
+	{
+		if (rc != SWEGL_B200_OK)
+			throw std::runtime_error(std::string("swegl_b200 ") + what + ": status " + std::to_string(rc) + ": " + swegl_b200_last_error(m_ctx));
 	}
 
 private:
@@ -122,12 +148,6 @@ private:
 	int m_screen_w = 0, m_screen_h = 0;
 	std::string m_signature;
 	std::vector<float> m_node_world, m_node_normal, m_lights;
-
-	void check(int rc, const char * what)
-	{
-		if (rc != SWEGL_B200_OK)
-			throw std::runtime_error(std::string("swegl_b200 ") + what + ": status " + std::to_string(rc) + ": " + swegl_b200_last_error(m_ctx));
-	}
 
 	// node_t::original_to_world_matrix for the whole hierarchy (vertex_shaders.hpp:16-18,26-27), without the
 	// per-vertex loop: the device computes v_world

@@ -5,8 +5,9 @@ For every workload in swegl_b200.configs.CONFIGS:
   2. render it with the C restatement (oracle/swegl_oracle.c),
   3. require bit-identical frames, depth buffers and per-vertex state,
   4. record FNV-1a-64 hashes + counters in tests/golden/MANIFEST.json.
-DoF workloads: the reference's DoF is broken at HEAD, so the pre-DoF frame is pinned against
-the reference and the DoF-R output hash is recorded from the oracle alone ("dof_r_unpinned").
+DoF workloads: the reference's DoF is broken at HEAD, so the pre-DoF frame is pinned against the
+unmodified reference and the DoF-R frame against the reference built with oracle/dof_r.patch
+(oracle/_ref/libswegl_ref_dofr.so, `make -C oracle refdofr`): both must be bit-identical to the oracle's.
 Small full-frame fixtures (compressed) are stored for the 640x480 config so the golden check does not
 depend on hashes only.
 
@@ -22,16 +23,16 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from oracle.binding import Oracle, Ref  # noqa: E402
+from oracle.binding import Oracle, Ref, REF_DOFR_LIB  # noqa: E402
 from swegl_b200 import _abi, configs  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def ref_render_config(ref, scene, vps, screen):
+def ref_render_config(ref, scene, vps, screen, with_dof=False):
     h = ref.import_scene(scene)
     scr = ref.lib.ref_screen_new(*screen)
-    rvs = [ref.make_viewport(scr, vp, vp.pose) for vp in vps]
+    rvs = [ref.make_viewport(scr, vp, vp.pose, with_dof=with_dof) for vp in vps]
     if len(rvs) == 1:
         ref.lib.ref_render(h, rvs[0])
     elif len(rvs) == 4:
@@ -52,7 +53,7 @@ def ref_render_config(ref, scene, vps, screen):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    orc, ref = Oracle(), Ref()
+    orc, ref, ref_dofr = Oracle(), Ref(), Ref(REF_DOFR_LIB)
     manifest = {}
     for name in configs.CONFIGS:
         scene, vps, screen, cfg = configs.build(name)
@@ -80,9 +81,11 @@ def main():
             dpx = np.zeros((screen[1], screen[0]), np.uint32)
             for vp in vps:
                 orc.render(scene, vp, screen_wh=screen, pixels=dpx)
+            rdpx, _, _ = ref_render_config(ref_dofr, scene, vps, screen, with_dof=True)
+            assert (rdpx == dpx).all(), f"{name}: the oracle's DoF-R frame differs from the patched reference"
             entry["pre_dof_frame_fnv1a64"] = entry.pop("frame_fnv1a64")
             entry["frame_fnv1a64"] = "%016x" % orc.fnv(dpx)
-            entry["dof_r_unpinned"] = True
+            entry["dof_r_pinned_against_patched_reference"] = True
         manifest[name] = entry
         print(name, entry["frame_fnv1a64"], entry["covered"])
         if name == "box_640":
