@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--workloads", default="truck_4k_dof,brainstem_4k_dof,truck_1080,sphere1000_8k")
     ap.add_argument("--frames", type=int, default=30)
     ap.add_argument("--pipe", action="store_true")
+    ap.add_argument("--modes", default="exact,fast")
     args = ap.parse_args()
     import torch
     from swegl_b200 import Renderer, configs, _abi
@@ -39,6 +40,8 @@ def main():
         nodes = scene.node_matrices()
         row = {}
         for mode, key in ((_abi.SHADING_EXACT, "exact"), (_abi.SHADING_FAST, "fast")):
+            if key not in args.modes.split(","):
+                continue
             r.set_shading(mode)
             r.begin_frame(scene, nodes)
             for vp in vps:
