@@ -3,12 +3,13 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
 
-A step = one frame of the workload: swegl::render(scene, viewport) = vertex stage + cull/mark + setup +
-scan rasterisation with z test + Phong/bilinear shading + DoF-R.  Default workload = the north-star
+A step = one BATCH of FRAMES_PER_STEP independent frames of the workload (a frame = swegl::render(scene, viewport) =
+vertex stage + cull/mark + setup + scan rasterisation with z test + Phong/bilinear shading + DoF-R; one frame takes
+~0.08 ms, far too short a timed region on its own).  Default workload = the north-star
 target of BASELINE.json (CesiumMilkTruck 3840x2160, Phong + bilinear, sun + 2 point lights, DoF-R);
 the 1080p configs[1] frame is measured in the same run and reported under "also".
 
-  value     : frames/s of a batch of K independent frames with the scene resident in HBM, rendered round robin by
+  value     : frames/s over K batches of independent frames with the scene resident in HBM, rendered round robin by
               --pipeline-depth contexts per GPU (swegl_b200.FramePipeline: the latency-bound head of frame i+1 runs
               under the fragment/DoF kernels of frame i); one pair of CUDA events around the batch; max over ranks.
               one_frame_at_a_time: the same frames on one context, CUDA events around each frame on the launching
@@ -37,6 +38,19 @@ METRIC = "fps"
 UNIT = "frames/s"
 DEFAULT_WORKLOAD = "truck_4k_dof"
 ALSO_WORKLOAD = "truck_1080"
+FRAMES_PER_STEP = 256           # `value`: a step is a batch of this many frames (K = 50 -> ~1 s of timed device work at 4K)
+E2E_FRAMES_PER_STEP = 32        # the end-to-end loops are PCIe / host bound: smaller batches keep the default run within minutes
+SERIAL_FRAMES_MAX = 1000        # one_frame_at_a_time: a 256 MiB L2 flush sits between the frames
+SINGLE_FRAME_STEPS = 50         # timed frames of the single-frame (sharded / multiview) measurements
+
+
+def golden_fnv(name):
+    """FNV-1a-64 of the workload's frame as the unmodified reference renders it (tests/golden/MANIFEST.json, pinned by
+    tools/make_golden.py against oracle/_ref; DoF workloads: against the reference built with oracle/dof_r.patch)"""
+    try:
+        return int(json.load(open(os.path.join(ROOT, "tests", "golden", "MANIFEST.json")))[name]["frame_fnv1a64"], 16)
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def workload_config(name, cfg, scene, screen, extra=None):
@@ -101,6 +115,7 @@ _W = {}
 
 def _ref_worker_init(name):
     """one process = one copy of the single-threaded reference renderer (scene imported once)"""
+    os.environ["SWEGL_B200_IMAGE_DECODER"] = "pil"      # (spawned workers inherit it anyway)
     from oracle.binding import Ref, Oracle, REF_LIB
     from swegl_b200 import configs
     scene, vps, screen, cfg = configs.build(name)
@@ -142,6 +157,9 @@ def run_reference_arm(args, rank, world):
     reference; a step = one frame per process; value = aggregate frames/s (median over steps)."""
     if rank != 0:
         return
+    # the arm runs the unmodified reference and nothing of the product: the scene packs' embedded PNG / JPEG textures are
+    # decoded with PIL here instead of libswegl_b200.so's decoder (same texels, guarded by the packs' digests)
+    os.environ["SWEGL_B200_IMAGE_DECODER"] = "pil"
     import multiprocessing as mp
     from swegl_b200 import configs
     name = args.workload
@@ -271,22 +289,29 @@ def measure_kernels(r, scene, vps, steps):
     return {k: v / max(n, 1) for k, v in acc.items()}, last
 
 
-def measure_pipelined(torch, local_rank, scene, vps, screen, steps, warmup, depth):
-    """`steps` independent frames through swegl_b200.FramePipeline: `depth` contexts on this GPU, frames round robin,
-    device-resident; one pair of CUDA events around the whole batch (fork/join over the context streams).  The contexts'
-    frame buffers and pools rotate, so at 4K the working set (depth x ~140 MB) never fits the 126 MB L2."""
+def measure_pipelined(torch, local_rank, scene, vps, screen, steps, warmup, depth, dist=None):
+    """`steps` batches of FRAMES_PER_STEP independent frames through swegl_b200.FramePipeline: `depth` contexts on this GPU,
+    frames round robin, device-resident; one pair of CUDA events around every batch (fork/join over the context streams).
+    The contexts' frame buffers and pools rotate, so at 4K the working set (depth x ~140 MB) never fits the 126 MB L2.
+    -> [seconds per batch]"""
     from swegl_b200.pipeline import FramePipeline
     pipe = FramePipeline(local_rank, depth)
     try:
         pipe.upload_scene(scene)
         pipe.set_screen(*screen)
-        ms = pipe.measure(scene, vps, steps, warmup=max(warmup, 3) * depth)
+        pipe.measure(scene, vps, 2 * depth, warmup=max(warmup, 3) * depth)         # warm-up: pools sized, graphs captured
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = pipe.measure_batches(scene, vps, steps, FRAMES_PER_STEP, warmup=depth)
     finally:
         pipe.close()
-    return ms / 1e3
+    return [m / 1e3 for m in ms]
 
 
 def gpu_workload(r, torch, name, steps, warmup, flush, world, dist, do_e2e=True, depth=4, local_rank=0):
+    """steps = batches.  -> dict with the per-batch seconds of the pipelined (`value`) measurement, the serial one-frame-at-
+    a-time measurement and the two end-to-end loops, each reduced with MAX over the ranks"""
     from swegl_b200 import configs
     scene, vps, screen, cfg = configs.build(name)
     r.upload_scene(scene)
@@ -294,30 +319,52 @@ def gpu_workload(r, torch, name, steps, warmup, flush, world, dist, do_e2e=True,
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    secs, ms = measure_gpu(r, torch, scene, vps, screen, steps, warmup, flush)
+    serial_frames = min(steps * FRAMES_PER_STEP, SERIAL_FRAMES_MAX)
+    secs, ms = measure_gpu(r, torch, scene, vps, screen, serial_frames, warmup, flush)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    pipe_secs = measure_pipelined(torch, local_rank, scene, vps, screen, steps, warmup, depth) if depth > 1 else secs
+    batch_secs = measure_pipelined(torch, local_rank, scene, vps, screen, steps, warmup, depth, dist if world > 1 else None) if depth > 1 else None
+    if batch_secs is None:                              # --pipeline-depth 1: the serial measurement in batches
+        batch_secs = []
+        for _ in range(steps):
+            bs, _ = measure_gpu(r, torch, scene, vps, screen, FRAMES_PER_STEP, 0, flush)
+            batch_secs.append(bs)
     if world > 1:
-        t = torch.tensor([secs, pipe_secs], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        secs, pipe_secs = float(t[0].item()), float(t[1].item())
+        t = torch.tensor([secs] + batch_secs, device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)        # per batch: the slowest rank
+        secs, batch_secs = float(t[0].item()), [float(x) for x in t[1:].tolist()]
         dist.barrier()
-    out = {"scene": scene, "vps": vps, "screen": screen, "cfg": cfg, "secs": secs, "ms": ms, "pipe_secs": pipe_secs, "depth": depth}
+    out = {"scene": scene, "vps": vps, "screen": screen, "cfg": cfg, "secs": secs, "serial_frames": serial_frames, "ms": ms,
+           "batch_secs": batch_secs, "pipe_secs": sum(batch_secs), "depth": depth}
     if do_e2e:
         images = [r.alloc_host((screen[1], screen[0]), np.uint32) for _ in range(2)]
-        sync_secs = measure_e2e(r, torch, scene, vps, screen, steps, warmup, images[0])
-        e2e_secs = measure_e2e_pipelined(r, torch, scene, vps, screen, steps, warmup, images)
+        n_sync, n_async = max(steps * E2E_FRAMES_PER_STEP // 4, 8), steps * E2E_FRAMES_PER_STEP
+        sync_secs = measure_e2e(r, torch, scene, vps, screen, n_sync, warmup, images[0])
+        r.readback_stats(reset=True)
+        e2e_secs = measure_e2e_pipelined(r, torch, scene, vps, screen, n_async, warmup, images)
+        rb_bytes, rb_frames = r.readback_stats()
         if world > 1:
             t = torch.tensor([e2e_secs, sync_secs], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_secs, sync_secs = float(t[0].item()), float(t[1].item())
-        out["e2e_secs"] = e2e_secs
-        out["e2e_sync_secs"] = sync_secs
+        out.update(e2e_secs=e2e_secs, e2e_frames=n_async, e2e_sync_secs=sync_secs, e2e_sync_frames=n_sync)
         nodes = scene.n_nodes
         out["h2d"] = nodes * (64 + 36) + 16 * len(scene.point_lights)
-        out["d2h"] = sum(vp.w * vp.h * 4 for vp in vps) + 32
+        out["d2h_full"] = sum(vp.w * vp.h * 4 for vp in vps)
+        out["d2h"] = rb_bytes / max(rb_frames, 1) + 64            # what really crossed PCIe per frame (+ the frame's counters)
+        # the partial read-back must leave the same host image as a full copy: check it against the golden frame hash
+        from swegl_b200 import _abi
+        from swegl_b200.renderer import frame_hash
+        want = golden_fnv(name)
+        if want is not None and len(vps) == 1:
+            r.set_shading(_abi.SHADING_EXACT)           # the manifest pins the bit-exact frame; the timed frames use the +-1 LSB shading
+            fd_nodes = scene.node_matrices()
+            for i in range(3):                          # through the pipelined, partial path: both host images
+                r.begin_frame(scene, fd_nodes)
+                r.wait(r.render_async(vps[0].desc(), images[i & 1]))
+            out["frame_fnv_ok"] = frame_hash(images[0]) == want and frame_hash(images[1]) == want
+            r.set_shading(_abi.SHADING_FAST)
     return out
 
 
@@ -326,6 +373,31 @@ class _DevArray:
 
     def __init__(self, ptr, shape):
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
+
+
+def screen_fnv_ok(r, torch, dist, world, rank, name, render_one):
+    """The assembled frame on rank 0 against the golden FNV-1a-64 of the reference's frame (tests/golden/MANIFEST.json).
+    The manifest pins the bit-exact frame, the timed frames use the +-1 LSB shading: every rank renders the frame once
+    more with exact shading through the very same path (`render_one`), rank 0 reads its device screen back and hashes it.
+    -> True / False on rank 0 (None elsewhere, or when the manifest has no entry)"""
+    from swegl_b200 import _abi
+    from swegl_b200.renderer import frame_hash
+    want = golden_fnv(name)
+    if want is None:
+        return None
+    r.set_shading(_abi.SHADING_EXACT)
+    for _ in range(2):
+        render_one()
+    r.synchronize(); torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ok = None
+    if rank == 0:
+        ok = frame_hash(r.read_screen()) == want
+    r.set_shading(_abi.SHADING_FAST)
+    if world > 1:
+        dist.barrier()
+    return ok
 
 
 def multiview_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
@@ -379,22 +451,27 @@ def multiview_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
     ms_gather = timed()
+    if rank == 0:
+        full.zero_()
+    gather_ok = screen_fnv_ok(r, torch, dist, world, rank, name, one)
     ms_peer, peer_ok = None, None
     if world > 1:
-        checksum = int(full.to(torch.int64).sum().item()) if rank == 0 else 0
         sharding.share_screen(r, dist, dst=0, device="cuda")
         state["peer"] = True
         if rank == 0:
             full.zero_()
         ms_peer = timed()
         if rank == 0:
-            peer_ok = int(full.to(torch.int64).sum().item()) == checksum
+            full.zero_()
+        peer_ok = screen_fnv_ok(r, torch, dist, world, rank, name, one)
         r.set_color_target(None)
         dist.barrier()
     best = min(m for m in (ms_gather, ms_peer) if m is not None)
-    return {"workload": name, "description": cfg["desc"], "ms_per_frame": best, "fps": 1e3 / best,
+    checks = [c for c in (gather_ok, peer_ok) if c is not None]
+    return {"workload": name, "description": cfg["desc"], "ms_per_frame": best, "fps": 1e3 / best, "timed_frames": steps,
             "ms_per_frame_nccl_rect_gather": ms_gather if world > 1 else None, "ms_per_frame_peer_write": ms_peer,
-            "peer_write_frame_matches_gather": peer_ok, "n_gpus": world, "active_gpus": min(world, len(vps)),
+            "frame_fnv_ok": (all(checks) if checks else None), "frame_fnv_ok_gather": gather_ok, "frame_fnv_ok_peer_write": peer_ok,
+            "n_gpus": world, "active_gpus": min(world, len(vps)),
             "viewports_per_rank": [len(sharding.viewports_for_rank(len(vps), world, k)) for k in range(world)],
             "partition": "one viewport_t per GPU (viewport v on rank v mod N), scene replicated" if world > 1 else "single GPU, 4 viewports one after the other",
             "scaling": "strong"}
@@ -472,18 +549,45 @@ def sharded_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
     start_token = torch.zeros(1, device="cuda")
+    # one GPU, whole frame: the denominator of the strong-scaling figure, measured by every rank on its own GPU in this very
+    # run (the ranks do not share anything here); rank 0's number is reported
+    ms_1gpu = None
+    if world > 1:
+        saved = (state["bands"], vp.band)
+        vp.band = (0, 0)
+        full_desc = vp.desc()
+        r.begin_frame(scene, nodes)
+        r.render_device(full_desc, stats=True)          # pools for the whole frame
+        for _ in range(max(warmup, 3)):
+            r.begin_frame(scene, nodes); r.render_device(full_desc, stats=False)
+        r.synchronize(); torch.cuda.synchronize()
+        ms1 = []
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r.begin_frame(scene, nodes); r.render_device(full_desc, stats=False); e1.record()
+            r.synchronize(); torch.cuda.synchronize()
+            ms1.append(e0.elapsed_time(e1))
+        ms_1gpu = sum(ms1) / len(ms1)
+        set_bands(saved[0])
+        r.begin_frame(scene, nodes)
+        r.render_device(state["desc"], stats=True)
+        dist.barrier()
     ms_gather = timed()                                 # bands sent to rank 0 after rendering (NCCL send/recv)
+    if rank == 0:
+        full.zero_()
+    gather_ok = screen_fnv_ok(r, torch, dist, world, rank, name, one)
     ms_peer, peer_ok, ms_sync, sync_ok, sync_info = None, None, None, None, None
     if world > 1:
         # the fused form: every rank's last kernel stores its band into rank 0's screen over NVLink (CUDA IPC mapping)
-        checksum = int(full.to(torch.int64).sum().item()) if rank == 0 else 0
         sharding.share_screen(r, dist, dst=0, device="cuda")
         state["peer"] = True
         if rank == 0:
             full.zero_()
         ms_peer = timed()
         if rank == 0:
-            peer_ok = int(full.to(torch.int64).sum().item()) == checksum        # same frame as the gathered one
+            full.zero_()
+        peer_ok = screen_fnv_ok(r, torch, dist, world, rank, name, one)
         # the frame protocol (swegl_b200_set_frame_sync): no collective at all -- rank 0 clears the others' rows locally,
         # they store only the tiles they drew into and raise a flag in rank 0's memory; bands rebalanced on measured time
         state["peer"] = False
@@ -547,9 +651,14 @@ def sharded_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
         ms_sync = timed_sync()
         errs = torch.tensor([r.frame_sync_errors()], device="cuda", dtype=torch.int64)
         dist.all_reduce(errs)
-        # same frame as the gathered one?  (the bands moved, the frame must not)
+        # the reference's frame?  (the bands moved, the frame must not; rank 0 does not clear its own band: zero it first)
         if rank == 0:
-            sync_ok = int(full.to(torch.int64).sum().item()) == checksum and int(errs.item()) == 0
+            r.synchronize(); torch.cuda.synchronize()
+            full.zero_()
+        dist.barrier()
+        sync_ok = screen_fnv_ok(r, torch, dist, world, rank, name, nonlocal_one)
+        if rank == 0:
+            sync_ok = bool(sync_ok) and int(errs.item()) == 0
         sync_info = {"balance_history": history, "timed_out_waits": int(errs.item())}
         r.set_frame_sync(-1)
         r.set_color_target(None)
@@ -558,17 +667,17 @@ def sharded_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
     st = r.render_device(state["desc"], stats=True)
     cands = [m for m in (ms_gather, ms_peer, ms_sync) if m is not None]
     best = min(cands)
-    return {"workload": name, "description": cfg["desc"], "ms_per_frame": best, "fps": 1e3 / best,
+    checks = [c for c in (gather_ok, peer_ok, sync_ok) if c is not None]
+    if ms_1gpu is None:
+        ms_1gpu = best
+    return {"workload": name, "description": cfg["desc"], "ms_per_frame": best, "fps": 1e3 / best, "timed_frames": steps,
+            "ms_per_frame_1gpu_same_run": ms_1gpu, "speedup_vs_1gpu": ms_1gpu / best,
             "ms_per_frame_nccl_gather": ms_gather if world > 1 else None,
-            "ms_per_frame_peer_write": ms_peer, "peer_write_frame_matches_gather": peer_ok,
-            "ms_per_frame_peer_protocol": ms_sync, "peer_protocol_frame_matches_gather": sync_ok, "peer_protocol": sync_info,
+            "ms_per_frame_peer_write": ms_peer, "ms_per_frame_peer_protocol": ms_sync, "peer_protocol": sync_info,
+            "frame_fnv_ok": (all(checks) if checks else None), "frame_fnv_ok_gather": gather_ok, "frame_fnv_ok_peer_write": peer_ok,
+            "frame_fnv_ok_peer_protocol": sync_ok,
             "n_gpus": world,
-            "partition": ("contiguous row bands of the full viewport (sort-first, scene replicated, band culling on). Output: "
-                          "(a) nccl_gather: bands sent to rank 0 with NCCL send/recv after rendering; (b) peer_write: every rank's last "
-                          "kernel stores its band into rank 0's screen over NVLink peer memory, then a one-element all-reduce; "
-                          "(c) peer_protocol: no collective -- rank 0 clears the other bands locally, the others store only the tiles "
-                          "they drew into and raise a flag in rank 0's memory, rank 0's last kernel waits for the flags; bands "
-                          "rebalanced on the ranks' measured times") if world > 1 else "single GPU",
+            "partition": "row bands, sort-first, scene replicated, band culling (DESIGN.md 6: nccl_gather / peer_write / peer_protocol)" if world > 1 else "single GPU",
             "bands": state["bands"], "rank0_band_covered_pixels": int(st.n_covered), "scaling": "strong"}
 
 
@@ -650,18 +759,21 @@ def main():
     scene, vps, screen, cfg = main_res["scene"], main_res["vps"], main_res["screen"], main_res["cfg"]
     kern, last = measure_kernels(r, scene, vps, min(args.steps, 20))
     covered = int(last.n_covered)
-    fps = world * args.steps / main_res["pipe_secs"]
-    serial_fps = world * args.steps / main_res["secs"]
-    e2e_fps = world * args.steps / main_res["e2e_secs"]
+    frames = args.steps * FRAMES_PER_STEP
+    fps = world * frames / main_res["pipe_secs"]
+    batch_fps = sorted(world * FRAMES_PER_STEP / b for b in main_res["batch_secs"])
+    serial_fps = world * main_res["serial_frames"] / main_res["secs"]
+    e2e_fps = world * main_res["e2e_frames"] / main_res["e2e_secs"]
 
     also = None
     if not args.no_also and args.workload == DEFAULT_WORKLOAD and world == 1:
         a = gpu_workload(r, torch, ALSO_WORKLOAD, args.steps, args.warmup, flush, world, dist, depth=args.pipeline_depth, local_rank=local_rank)
         ak, al = measure_kernels(r, a["scene"], a["vps"], min(args.steps, 20))
-        also = {"workload": ALSO_WORKLOAD, "description": a["cfg"]["desc"], "fps": args.steps / a["pipe_secs"],
-                "one_frame_at_a_time_fps": args.steps / a["secs"],
-                "e2e_fps": args.steps / a["e2e_secs"], "e2e_blocking_call_fps": args.steps / a["e2e_sync_secs"], "shaded_mpix_per_s": al.n_covered * args.steps / a["secs"] / 1e6,
-                "ms_per_stage": ak}
+        also = {"workload": ALSO_WORKLOAD, "description": a["cfg"]["desc"], "fps": frames / a["pipe_secs"],
+                "one_frame_at_a_time_fps": a["serial_frames"] / a["secs"],
+                "e2e_fps": a["e2e_frames"] / a["e2e_secs"], "e2e_blocking_call_fps": a["e2e_sync_frames"] / a["e2e_sync_secs"],
+                "e2e_d2h_bytes_per_frame": a["d2h"], "frame_fnv_ok": a.get("frame_fnv_ok"),
+                "shaded_mpix_per_s": al.n_covered * a["serial_frames"] / a["secs"] / 1e6, "ms_per_stage": ak}
 
     # the remaining BASELINE.json configs that fit one GPU (config 1 and config 3), device-resident, one frame at a time
     others = None
@@ -672,21 +784,21 @@ def main():
             osc, ovps, oscreen, ocfg = _cfg.build(oname)
             r.upload_scene(osc)
             r.set_screen(*oscreen)
-            osecs, _ = measure_gpu(r, torch, osc, ovps, oscreen, min(args.steps, 30), args.warmup, flush)
+            n_ = 100
+            osecs, _ = measure_gpu(r, torch, osc, ovps, oscreen, n_, args.warmup, flush)
             ok_, ol_ = measure_kernels(r, osc, ovps, 10)
-            n_ = min(args.steps, 30)
             others[oname] = {"description": ocfg["desc"], "one_frame_at_a_time_fps": n_ / osecs, "ms_per_frame": 1e3 * osecs / n_,
                              "covered_pixels": int(ol_.n_covered), "shaded_mpix_per_s": ol_.n_covered * n_ / osecs / 1e6,
                              "ms_per_stage": ok_}
 
     sharded = None
     if args.sharded and not args.no_also:
-        sharded = sharded_frame(r, torch, dist, args.sharded, min(args.steps, 10), args.warmup, flush, world, rank)
+        sharded = sharded_frame(r, torch, dist, args.sharded, SINGLE_FRAME_STEPS, args.warmup, flush, world, rank)
     multiview = None
     if args.multiview and not args.no_also:
         rm = Renderer(local_rank, stream=stream.cuda_stream)      # its own context: own screen, own peer mappings
         try:
-            multiview = multiview_frame(rm, torch, dist, args.multiview, min(args.steps, 20), args.warmup, flush, world, rank)
+            multiview = multiview_frame(rm, torch, dist, args.multiview, SINGLE_FRAME_STEPS, args.warmup, flush, world, rank)
         finally:
             rm.close()
 
@@ -731,33 +843,45 @@ def main():
                "sample": f"3 frames of {args.workload} after 1 warm-up, swegl::render as shipped (1 raster thread) "
                          f"via oracle/_ref + DoF-R by the C oracle; {1e3 / v:.1f} ms/frame"}
 
+    checks = [c for c in (main_res.get("frame_fnv_ok"), (sharded or {}).get("frame_fnv_ok"), (multiview or {}).get("frame_fnv_ok")) if c is not None]
     line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * main_res["pipe_secs"] / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic" if args.workload.startswith("sphere") else "bundled scene",
             "config": workload_config(args.workload, cfg, scene, screen,
-                                      {"parallelism": "single GPU" if world == 1 else
+                                      {"step": f"one batch of {FRAMES_PER_STEP} independent frames", "frames_per_step": FRAMES_PER_STEP,
+                                       "parallelism": "single GPU" if world == 1 else
                                        f"frame-parallel x{world}: scene replicated, frame i on GPU i mod N, no collective",
                                        "frames_in_flight_per_gpu": main_res["depth"],
                                        "host_numa_binding": (f"rank 0 on node {numa_node}, every rank bound to its GPU's node"
                                                              if numa_node is not None else "none"),
-                                       "l2": (f"value: {main_res['depth']} contexts per GPU render the batch of independent frames round robin; "
+                                       "l2": (f"value: {main_res['depth']} contexts per GPU render the batches of independent frames round robin; "
                                               "their frame buffers and pools (about 140 MB each at 4K) rotate, so the working set exceeds "
                                               "the 126 MB L2 and no flush is inserted; one_frame_at_a_time: 256 MiB memset between timed "
                                               "frames, outside the CUDA events") if main_res["depth"] > 1 else
                                              "256 MiB memset between timed frames, outside the CUDA events"}),
+            "frames_timed": frames * world, "timed_region_s": main_res["pipe_secs"],
+            "batches": {"n": len(batch_fps), "frames_each": FRAMES_PER_STEP, "fps_median": statistics.median(batch_fps),
+                        "fps_min": batch_fps[0], "fps_max": batch_fps[-1]},
+            "ms_per_frame": 1e3 * main_res["pipe_secs"] / frames,
             "shaded_mpix_per_s": covered * fps / 1e6, "viewport_mpix_per_s": sum(v.w * v.h for v in vps) * fps / 1e6,
             "covered_pixels": covered,
-            "one_frame_at_a_time": {"fps": serial_fps, "ms_per_frame": 1e3 * main_res["secs"] / args.steps,
+            "one_frame_at_a_time": {"fps": serial_fps, "ms_per_frame": 1e3 * main_res["secs"] / main_res["serial_frames"], "frames": main_res["serial_frames"],
                                     "how": "one context, frame i+1 starts when frame i is done: per-frame CUDA events on the "
                                            "launching stream, 256 MiB L2 flush between frames outside the events"},
             "frame_stats": {"setup_triangles": int(last.n_setup_triangles), "spans": int(last.n_spans), "chunks": int(last.n_chunks)},
-            "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": main_res["h2d"], "d2h_bytes_per_step": main_res["d2h"],
+            "e2e": {"value": e2e_fps, "unit": UNIT, "frames_per_step": E2E_FRAMES_PER_STEP,
+                    "h2d_bytes_per_step": main_res["h2d"] * E2E_FRAMES_PER_STEP, "d2h_bytes_per_step": int(main_res["d2h"] * E2E_FRAMES_PER_STEP),
+                    "h2d_bytes_per_frame": main_res["h2d"], "d2h_bytes_per_frame": int(main_res["d2h"]), "full_frame_bytes": main_res["d2h_full"],
+                    "timed_region_s": main_res["e2e_secs"],
                     "api": "Renderer.begin_frame + render_async/wait (swegl_b200_render_viewport_async): 2 frames in flight, "
-                           "every frame's node matrices/lights go H2D and its finished image D2H into pinned memory",
-                    "blocking_call_fps": world * args.steps / main_res["e2e_sync_secs"],
+                           "every frame's node matrices/lights go H2D; D2H into pinned memory of the rectangle that differs from "
+                           "what the host image already holds (the frame's bounding box united with the previous frame's; "
+                           "d2h_bytes_* are the bytes the library counted, swegl_b200_readback_stats)",
+                    "blocking_call_fps": world * main_res["e2e_sync_frames"] / main_res["e2e_sync_secs"],
                     "blocking_call_api": "Renderer.begin_frame + render (swegl_b200_render_viewport, what swegl::render maps to): "
-                                         "returns with the frame in host memory"},
-            "gpu_launches": (int(last.n_launches) * len(vps) + 1) * args.steps,
+                                         "returns with the whole frame in host memory (full copy)"},
+            "gpu_launches": (int(last.n_launches) * len(vps) + 1) * frames,
+            "frame_fnv_ok": (all(checks) if checks else None), "frame_fnv_ok_main": main_res.get("frame_fnv_ok"),
             "ms_per_stage": kern, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
     if also:
         line["also"] = also
@@ -767,6 +891,11 @@ def main():
         line["sharded_frame"] = sharded
     if multiview:
         line["multiview_frame"] = multiview
+    # last key, short: what survives in a truncated tail of the line
+    if sharded:
+        line["strong"] = {"workload": sharded["workload"], "n_gpus": world, "ms_1gpu": round(sharded["ms_per_frame_1gpu_same_run"], 4),
+                          "ms": round(sharded["ms_per_frame"], 4), "speedup": round(sharded["speedup_vs_1gpu"], 3),
+                          "frames": sharded["timed_frames"], "fnv_ok": sharded["frame_fnv_ok"]}
     json_out.write(json.dumps(line) + "\n")
     json_out.flush()
     if world > 1:

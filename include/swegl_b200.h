@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SWEGL_B200_ABI_VERSION 2
+#define SWEGL_B200_ABI_VERSION 3
 
 /* ---- status codes (reference has none: void + assert, renderer.cpp:98-100) ---- */
 enum {
@@ -114,6 +114,30 @@ typedef struct swegl_b200_frame_desc {
     const float *point_lights; /* n*4: position xyz, intensity (point_source_light)        */
 } swegl_b200_frame_desc;
 
+/* ---- device-side animation: scene_t::animate, swegl/data/model.hpp:146-177, and the node-hierarchy product of
+ * vertex_shader_t::original_to_world, swegl/render/vertex_shaders.hpp:16-33, evaluated on the device ----
+ * animation_channel_t (model.hpp:94-122) flattened: key frames [first_step, first_step + n_steps) of step_time / step_value */
+typedef struct swegl_b200_anim_channel {
+    int32_t  animation;        /* index of the owning animation_t (its end_time wraps the clock, model.hpp:150)   */
+    int32_t  node;             /* animation_channel_t::node_idx                                                     */
+    int32_t  path;             /* animation_channel_t::path_t: 0 scale, 1 rotation, 2 translation, 3 weights/none   */
+    uint32_t first_step, n_steps;   /* n_steps >= 1                                                                 */
+} swegl_b200_anim_channel;
+typedef struct swegl_b200_animation_desc {
+    uint32_t n_nodes;               /* must equal the uploaded scene's                                               */
+    const int32_t *node_parent;     /* n_nodes: the node whose children_idx holds this node, -1 for scene_t::root_nodes */
+    const float *node_rotation;     /* n_nodes*16: node_t::rotation (matrix44_t) as loaded                           */
+    const float *node_translation;  /* n_nodes*3 : node_t::translation                                               */
+    const float *node_scale;        /* n_nodes*3 : node_t::scale                                                     */
+    uint32_t n_animations;
+    const float *end_time;          /* n_animations: animation_t::end_time                                           */
+    uint32_t n_channels;
+    const swegl_b200_anim_channel *channels;   /* in scene order: animation by animation, channel by channel         */
+    uint32_t n_steps;
+    const float *step_time;         /* n_steps  : animation_step_t::time                                             */
+    const float *step_value;        /* n_steps*4: animation_step_t::value (x, y, z, w)                               */
+} swegl_b200_animation_desc;
+
 /* viewport_t + camera_t + shader selection, swegl/render/viewport.hpp:27-62 */
 typedef struct swegl_b200_viewport_desc {
     int32_t x, y, w, h;            /* m_x, m_y, m_w, m_h                                   */
@@ -176,6 +200,20 @@ int  swegl_b200_set_screen(swegl_b200_ctx *ctx, int32_t screen_w, int32_t screen
 /* replaces vertex_shader_t::original_to_world's per-vertex loop (vertex_shaders.hpp:20-24):
  * uploads node matrices + lights and computes v_world for every vertex. Once per frame. */
 int  swegl_b200_begin_frame(swegl_b200_ctx *ctx, const swegl_b200_frame_desc *frame);
+
+/* Device-side animation.  set_animation uploads the key frames, the nodes' TRS as loaded and the hierarchy once (after
+ * upload_scene; a new upload_scene drops them).  begin_frame_animated(t, frame) then replaces the application's
+ *     scene.animate(t);  (test_1.cpp:378)   +   the node loop of original_to_world (vertex_shaders.hpp:16-33)
+ * for that frame: `frame` supplies the lights only (node_world / node_normal are ignored and may be NULL), 4 bytes of time
+ * stamp travel instead of 100 bytes per node, and the first kernel of the frame computes node_t::rotation / translation /
+ * scale from the key frames and from them the world matrices, with the reference's fp32 operations in the reference's
+ * order -- bit-identical to animate() + original_to_world on the host.  The state is a function of t alone (every call of
+ * animate() rewrites the same node paths), so frames may be submitted in any order of t.  Plain begin_frame and
+ * begin_frame_animated can be mixed freely.  read_node_matrices returns the matrices the device holds after the last
+ * rendered frame (either pointer may be NULL). */
+int  swegl_b200_set_animation(swegl_b200_ctx *ctx, const swegl_b200_animation_desc *animation);
+int  swegl_b200_begin_frame_animated(swegl_b200_ctx *ctx, float elapsed_seconds, const swegl_b200_frame_desc *frame);
+int  swegl_b200_read_node_matrices(swegl_b200_ctx *ctx, float *node_world, float *node_normal);
 
 /* replaces swegl::_render(scene, viewport) (renderer.cpp:77-235), result left in HBM.  Asynchronous when
  * stats == NULL (see swegl_b200_synchronize for the pool-overflow contract); with stats it synchronises,
@@ -274,6 +312,9 @@ int  swegl_b200_read_depth_rows(swegl_b200_ctx *ctx, int32_t row0, int32_t row1,
  * CUDA IPC detour of export / import_screen.  SWEGL_B200_ERR_UNSUPPORTED when the devices cannot reach each other. */
 int  swegl_b200_enable_peer(swegl_b200_ctx *ctx, int peer_device);
 int  swegl_b200_device_of(const swegl_b200_ctx *ctx);
+/* 1 when every material and texel of the uploaded scene has alpha 255 (viewport_desc.transparency_layers is then ignored:
+ * the layer logic of renderer.cpp:500-550 is the identity), 0 when not, -1 before upload_scene */
+int  swegl_b200_scene_opaque(const swegl_b200_ctx *ctx);
 /* post-render vertex state of the last viewport, as the reference leaves it in
  * mesh_vertex_t: any pointer may be null. v_viewport holds pixel coordinates
  * for yes-vertices and NDC for the others (vertex_shaders.hpp:72-84).  After a band-culled view only the vertex

@@ -137,9 +137,22 @@ class Ref:
             "ref_render4": (None, [vp, vp, vp, vp, vp]),
             "ref_time_render": (C.c_double, [vp, vp, C.c_int, C.c_int, vp]),
         }
+        # only in libswegl_dropin.so: the C++ multi-context hosts and the device-side animation (ref_driver.cpp, SWEGL_B200_DROPIN)
+        dropin_only = {
+            "ref_render_pipelined": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_float]),
+            "ref_render_sharded": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+            "ref_render_sharded4": (C.c_int, [vp, vp, vp, vp, vp, C.c_int]),
+            "ref_render_animated": (C.c_int, [vp, vp, C.c_float]),
+            "ref_dropin_last_error": (C.c_char_p, []),
+        }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
+        self.is_dropin = hasattr(L, "ref_render_pipelined")
+        if self.is_dropin:
+            for name, (res, args) in dropin_only.items():
+                fn = getattr(L, name)
+                fn.restype, fn.argtypes = res, args
         del fp, ip, up
         self.encoded_images = []     # filled by the decode callback: the original bytes of each image
         self._cb = _DECODE_CB(self._decode)
@@ -163,6 +176,11 @@ class Ref:
             C.memmove(out, t.ctypes.data, t.nbytes)
             self.encoded_images.append(self._decoded[key][1])
         return 0
+
+    def host(self, name, *args):
+        """call one of the C++-host entry points of libswegl_dropin.so; a C++ exception becomes a RuntimeError"""
+        if getattr(self.lib, name)(*args) != 0:
+            raise RuntimeError(f"{name}: {self.lib.ref_dropin_last_error().decode()}")
 
     # ---- scenes ----
     def load(self, path):

@@ -504,41 +504,56 @@ double ref_time_render(void * scene, void * viewport, int warmup, int frames, do
 }
 
 #ifdef SWEGL_B200_DROPIN
+static std::string g_dropin_error;
+const char * ref_dropin_last_error() { return g_dropin_error.c_str(); }
+// every entry point below returns 0, or 1 with the exception's text in ref_dropin_last_error() (a C++ exception must not
+// cross the C boundary into ctypes)
+#define DROPIN_GUARD(body) try { body; g_dropin_error.clear(); return 0; } catch (const std::exception & e) { g_dropin_error = e.what(); return 1; }
 // Only in libswegl_dropin.so: the multi-context C++ hosts of swegl_b200/host/swegl_b200_host.hpp driven with the
 // reference's own scene_t / viewport_t objects (tests/test_dropin_gpu.py).
 // `frames` frames of one viewport through swegl_b200::pipeline_t (depth contexts, round robin); the camera turns by
 // `dyaw` before every frame; the LAST frame is collected into the viewport's surface
-void ref_render_pipelined(void * scene, void * viewport, int depth, int frames, float dyaw)
+int ref_render_pipelined(void * scene, void * viewport, int depth, int frames, float dyaw)
 {
 	auto & sc = static_cast<ref_scene *>(scene)->scene;
 	auto & vp = *static_cast<ref_viewport *>(viewport)->vp;
-	swegl_b200::pipeline_t pipe(0, depth);
-	int slot = 0;
-	for (int i = 0; i < frames; i++)
-	{
-		vp.camera().rotate_y(dyaw);
-		slot = pipe.submit(sc, vp);
-	}
-	pipe.collect(slot, vp);
-	pipe.synchronize();
+	DROPIN_GUARD(
+		swegl_b200::pipeline_t pipe(0, depth);
+		int slot = 0;
+		for (int i = 0; i < frames; i++)
+		{
+			vp.camera().rotate_y(dyaw);
+			slot = pipe.submit(sc, vp);
+		}
+		pipe.collect(slot, vp);
+		pipe.synchronize())
 }
 
 // one frame of one viewport in `n_ctx` row bands (contexts of device 0 standing in for GPUs), `frames` times
-void ref_render_sharded(void * scene, void * viewport, int n_ctx, int frames)
+int ref_render_sharded(void * scene, void * viewport, int n_ctx, int frames)
 {
 	auto & sc = static_cast<ref_scene *>(scene)->scene;
 	auto & vp = *static_cast<ref_viewport *>(viewport)->vp;
-	swegl_b200::sharded_renderer_t sh(std::vector<int>((size_t)n_ctx, 0));
-	for (int i = 0; i < frames; i++) sh.render(sc, vp);
+	DROPIN_GUARD(
+		swegl_b200::sharded_renderer_t sh(std::vector<int>((size_t)n_ctx, 0));
+		for (int i = 0; i < frames; i++) sh.render(sc, vp))
+}
+
+// the application's pair  scene.animate(t); swegl::render(scene, viewport)  (src/test_1.cpp:374-378) with the animation and
+// the node-hierarchy product evaluated on the device (swegl_b200::render_animated): the host scene_t is not touched
+int ref_render_animated(void * scene, void * viewport, float elapsed_seconds)
+{
+	DROPIN_GUARD(swegl_b200::render_animated(static_cast<ref_scene *>(scene)->scene, elapsed_seconds, *static_cast<ref_viewport *>(viewport)->vp))
 }
 
 // swegl::render(scene, vp1, vp2, vp3, vp4) with one viewport per context
-void ref_render_sharded4(void * scene, void * vp1, void * vp2, void * vp3, void * vp4, int n_ctx)
+int ref_render_sharded4(void * scene, void * vp1, void * vp2, void * vp3, void * vp4, int n_ctx)
 {
 	auto & sc = static_cast<ref_scene *>(scene)->scene;
-	swegl_b200::sharded_renderer_t sh(std::vector<int>((size_t)n_ctx, 0));
-	sh.render(sc, *static_cast<ref_viewport *>(vp1)->vp, *static_cast<ref_viewport *>(vp2)->vp,
-	          *static_cast<ref_viewport *>(vp3)->vp, *static_cast<ref_viewport *>(vp4)->vp);
+	DROPIN_GUARD(
+		swegl_b200::sharded_renderer_t sh(std::vector<int>((size_t)n_ctx, 0));
+		sh.render(sc, *static_cast<ref_viewport *>(vp1)->vp, *static_cast<ref_viewport *>(vp2)->vp,
+		          *static_cast<ref_viewport *>(vp3)->vp, *static_cast<ref_viewport *>(vp4)->vp))
 }
 #endif
 

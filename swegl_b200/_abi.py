@@ -15,7 +15,7 @@ LIGHT_NONE, LIGHT_FLAT, LIGHT_PHONG = 0, 1, 2
 TEX_PLAIN, TEX_NEAREST, TEX_BILINEAR = 0, 1, 2
 POST_NULL, POST_DOF = 0, 1
 SHADING_EXACT, SHADING_FAST = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Primitive(C.Structure):
@@ -50,6 +50,18 @@ class FrameDesc(C.Structure):
                 ("n_point_lights", C.c_uint32), ("point_lights", C.POINTER(C.c_float))]
 
 
+class AnimChannel(C.Structure):
+    _fields_ = [("animation", C.c_int32), ("node", C.c_int32), ("path", C.c_int32), ("first_step", C.c_uint32), ("n_steps", C.c_uint32)]
+
+
+class AnimationDesc(C.Structure):
+    _fields_ = [("n_nodes", C.c_uint32), ("node_parent", C.POINTER(C.c_int32)), ("node_rotation", C.POINTER(C.c_float)),
+                ("node_translation", C.POINTER(C.c_float)), ("node_scale", C.POINTER(C.c_float)),
+                ("n_animations", C.c_uint32), ("end_time", C.POINTER(C.c_float)),
+                ("n_channels", C.c_uint32), ("channels", C.POINTER(AnimChannel)),
+                ("n_steps", C.c_uint32), ("step_time", C.POINTER(C.c_float)), ("step_value", C.POINTER(C.c_float))]
+
+
 class ViewportDesc(C.Structure):
     _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("w", C.c_int32), ("h", C.c_int32),
                 ("view", C.c_float * 16), ("proj", C.c_float * 16), ("cam_pos", C.c_float * 3),
@@ -80,6 +92,9 @@ SYMBOLS = [
     ("swegl_b200_upload_scene", C.c_int, [C.c_void_p, C.POINTER(SceneDesc)]),
     ("swegl_b200_set_screen", C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     ("swegl_b200_begin_frame", C.c_int, [C.c_void_p, C.POINTER(FrameDesc)]),
+    ("swegl_b200_set_animation", C.c_int, [C.c_void_p, C.POINTER(AnimationDesc)]),
+    ("swegl_b200_begin_frame_animated", C.c_int, [C.c_void_p, C.c_float, C.POINTER(FrameDesc)]),
+    ("swegl_b200_read_node_matrices", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("swegl_b200_render_viewport_device", C.c_int, [C.c_void_p, C.POINTER(ViewportDesc), C.POINTER(Stats)]),
     ("swegl_b200_render_viewport", C.c_int, [C.c_void_p, C.POINTER(ViewportDesc), C.c_void_p, C.c_int32,
                                              C.c_void_p, C.POINTER(Stats)]),
@@ -101,6 +116,7 @@ SYMBOLS = [
     ("swegl_b200_read_depth_rows", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     ("swegl_b200_enable_peer", C.c_int, [C.c_void_p, C.c_int]),
     ("swegl_b200_device_of", C.c_int, [C.c_void_p]),
+    ("swegl_b200_scene_opaque", C.c_int, [C.c_void_p]),
     ("swegl_b200_read_vertices", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("swegl_b200_set_frame_sync", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     ("swegl_b200_frame_sync_status", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

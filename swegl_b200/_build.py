@@ -5,7 +5,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["abi.cu", "geometry.cu", "fragment.cu", "../host/image_decode.cpp"]   # the last one is host-only C++ (PNG / JPEG decode)
+SOURCES = ["abi.cu", "geometry.cu", "fragment.cu", "animate.cu", "../host/image_decode.cpp"]   # the last one is host-only C++ (PNG / JPEG decode)
 OUT = os.path.join(HERE, "libswegl_b200.so")
 
 NVCC_FLAGS = [

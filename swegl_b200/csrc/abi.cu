@@ -36,6 +36,9 @@ struct swegl_b200_ctx {
     float *d_v_world = nullptr, *d_v_ndc = nullptr, *d_n_world = nullptr; uint8_t *d_yes = nullptr;
     bool opaque = true;            // every material and texel has alpha 255
     bool fast_shading = true;      // Phong lighting within +-1 LSB (swegl_b200_set_shading); false: bit-exact
+    // device-side scene_t::animate (animate.cu): one allocation holding every static table + the scratch matrices
+    AnimTables anim{}; uint8_t *d_anim = nullptr; bool have_anim = false;
+    bool frame_animated = false;   // the staged frame's node matrices come from k_animate (begin_frame_animated), not from the host
     bool world_complete = false;   // v_world holds this frame's world positions of EVERY vertex (a culled view only fills its blocks)
     // DoF-R source tensor maps (TMA), valid for (dof_tm_w, dof_tm_h) and the current d_tmp_color / d_depth
     CUtensorMap dof_tm_color{}, dof_tm_depth{}; int dof_tm_w = 0, dof_tm_h = 0; bool dof_tm_ok = false; int dof_tma_policy = 1;
@@ -313,7 +316,7 @@ void swegl_b200_destroy(swegl_b200_ctx *ctx)
                      ctx->pools.edges, ctx->pools.shades, ctx->pools.spans, ctx->pools.span_shades, ctx->pools.frag_u, ctx->pools.row_slot,
                      ctx->pools.chunks, ctx->pools.bin_head, ctx->pools.bin_cnt, ctx->pools.bin_slots, ctx->pools.dof_list, ctx->pools.tile_stamp, ctx->pools.busy_list,
                      ctx->pools.counters, ctx->d_screen, ctx->d_depth,
-                     ctx->d_tmp_color, ctx->d_cl_box, ctx->d_cl_adj_off, ctx->d_cl_adj, ctx->d_vb_adj_off, ctx->d_vb_adj, ctx->d_cull_flags, ctx->d_cull_lists };
+                     ctx->d_tmp_color, ctx->d_cl_box, ctx->d_cl_adj_off, ctx->d_cl_adj, ctx->d_vb_adj_off, ctx->d_vb_adj, ctx->d_cull_flags, ctx->d_cull_lists, ctx->d_anim };
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     for (auto &sl : ctx->slots) {
@@ -563,6 +566,7 @@ int swegl_b200_upload_scene(swegl_b200_ctx *ctx, const swegl_b200_scene_desc *sc
     ctx->cull = CullTables{};
     if (nt && ctx->cull_policy != 0) { rc = build_cull_tables(ctx, tris, sc->positions, vert_node, nv); if (rc) return rc; }
     ctx->n_nodes = sc->n_nodes;
+    ctx->have_anim = false; ctx->frame_animated = false;    // the animation tables belong to the previous scene's nodes
     rc = layout_block(ctx, ctx->lights_cap ? ctx->lights_cap : 8);
     if (rc) return rc;
     ctx->opaque = opaque;
@@ -600,11 +604,11 @@ int swegl_b200_set_screen(swegl_b200_ctx *ctx, int32_t w, int32_t h)
     return SWEGL_B200_OK;
 }
 
-int swegl_b200_begin_frame(swegl_b200_ctx *ctx, const swegl_b200_frame_desc *fr)
+// stage one frame's data in a pinned slot: lights always; node matrices from the caller, or (animated) only the time stamp
+static int stage_frame(swegl_b200_ctx *ctx, const swegl_b200_frame_desc *fr, bool animated, float elapsed_seconds)
 {
-    if (!ctx || !fr) return SWEGL_B200_ERR_ARG;
     if (!ctx->have_scene) return fail(ctx, SWEGL_B200_ERR_STATE, "begin_frame before upload_scene");
-    if ((ctx->n_nodes && (!fr->node_world || !fr->node_normal)) || (fr->n_point_lights && !fr->point_lights))
+    if ((!animated && ctx->n_nodes && (!fr->node_world || !fr->node_normal)) || (fr->n_point_lights && !fr->point_lights))
         return fail(ctx, SWEGL_B200_ERR_ARG, "begin_frame: null array");
     CK(cudaSetDevice(ctx->device));
     if (fr->n_point_lights > ctx->lights_cap) {
@@ -623,12 +627,123 @@ int swegl_b200_begin_frame(swegl_b200_ctx *ctx, const swegl_b200_frame_desc *fr)
     fp.sun_intensity = fr->sun_intensity;
     fp.n_lights = fr->n_point_lights;
     fp.lights = reinterpret_cast<const float4 *>(ctx->d_block + ctx->off_lights);
+    fp.anim_time = elapsed_seconds;
     memcpy(sl.block, &fp, sizeof fp);
-    memcpy(sl.block + ctx->off_nw, fr->node_world, (size_t)64 * ctx->n_nodes);
-    memcpy(sl.block + ctx->off_nn, fr->node_normal, (size_t)36 * ctx->n_nodes);
+    if (!animated) {
+        memcpy(sl.block + ctx->off_nw, fr->node_world, (size_t)64 * ctx->n_nodes);
+        memcpy(sl.block + ctx->off_nn, fr->node_normal, (size_t)36 * ctx->n_nodes);
+    }
     if (fr->n_point_lights) memcpy(sl.block + ctx->off_lights, fr->point_lights, (size_t)16 * fr->n_point_lights);
     ctx->frame_slot = si; ctx->frame_dirty = true; ctx->have_frame = true;
+    ctx->frame_animated = animated;
     ctx->world_complete = false;
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_begin_frame(swegl_b200_ctx *ctx, const swegl_b200_frame_desc *fr)
+{
+    if (!ctx || !fr) return SWEGL_B200_ERR_ARG;
+    return stage_frame(ctx, fr, false, 0.0f);
+}
+
+int swegl_b200_begin_frame_animated(swegl_b200_ctx *ctx, float elapsed_seconds, const swegl_b200_frame_desc *fr)
+{
+    if (!ctx || !fr) return SWEGL_B200_ERR_ARG;
+    if (!ctx->have_anim) return fail(ctx, SWEGL_B200_ERR_STATE, "begin_frame_animated before set_animation");
+    return stage_frame(ctx, fr, true, elapsed_seconds);
+}
+
+// Upload what scene_t::animate and the hierarchy product need (animate.cu).  Everything is validated here so that the
+// kernel can index without checks.
+int swegl_b200_set_animation(swegl_b200_ctx *ctx, const swegl_b200_animation_desc *an)
+{
+    if (!ctx || !an) return SWEGL_B200_ERR_ARG;
+    if (!ctx->have_scene) return fail(ctx, SWEGL_B200_ERR_STATE, "set_animation before upload_scene");
+    const uint32_t n = ctx->n_nodes;
+    if (an->n_nodes != n) return fail(ctx, SWEGL_B200_ERR_ARG, "set_animation: n_nodes differs from the uploaded scene's");
+    if (n && (!an->node_parent || !an->node_rotation || !an->node_translation || !an->node_scale))
+        return fail(ctx, SWEGL_B200_ERR_ARG, "set_animation: null node array");
+    if ((an->n_channels && (!an->channels || !an->n_animations)) || (an->n_animations && !an->end_time) || (an->n_steps && (!an->step_time || !an->step_value)))
+        return fail(ctx, SWEGL_B200_ERR_ARG, "set_animation: null animation array");
+    // hierarchy levels (vertex_shaders.hpp:16-33 recurses from the roots; a node's matrix needs its parent's)
+    std::vector<int32_t> level(n, -1);
+    uint32_t n_levels = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t depth = 0; int32_t j = (int32_t)i;
+        while (j >= 0 && level[j] < 0) {
+            if ((uint32_t)j >= n || an->node_parent[j] >= (int32_t)n || ++depth > n) return fail(ctx, SWEGL_B200_ERR_ARG, "set_animation: bad node_parent (index or cycle)");
+            j = an->node_parent[j];
+        }
+        // walk down again assigning levels
+        int32_t base = j < 0 ? -1 : level[j];
+        std::vector<int32_t> chain;
+        for (int32_t k = (int32_t)i; k >= 0 && level[k] < 0; k = an->node_parent[k]) chain.push_back(k);
+        for (size_t c = chain.size(); c-- > 0;) level[chain[c]] = ++base;
+    }
+    for (uint32_t i = 0; i < n; i++) n_levels = std::max(n_levels, (uint32_t)level[i] + 1);
+    std::vector<uint32_t> level_off(n_levels + 1, 0), order(n);
+    for (uint32_t i = 0; i < n; i++) level_off[level[i] + 1]++;
+    for (uint32_t l = 0; l < n_levels; l++) level_off[l + 1] += level_off[l];
+    { std::vector<uint32_t> fill(level_off.begin(), level_off.end() - 1); for (uint32_t i = 0; i < n; i++) order[fill[level[i]]++] = i; }
+    // channels, grouped by node in scene order (animation by animation, channel by channel: model.hpp:148-153)
+    std::vector<uint32_t> chan_off(n + 1, 0);
+    for (uint32_t c = 0; c < an->n_channels; c++) {
+        const auto &ch = an->channels[c];
+        if (ch.node < 0 || (uint32_t)ch.node >= n || ch.animation < 0 || (uint32_t)ch.animation >= an->n_animations || ch.n_steps == 0
+            || (uint64_t)ch.first_step + ch.n_steps > an->n_steps)
+            return fail(ctx, SWEGL_B200_ERR_ARG, "set_animation: channel out of range (node, animation or key frames; a channel needs at least one key frame)");
+        chan_off[ch.node + 1]++;
+    }
+    for (uint32_t i = 0; i < n; i++) chan_off[i + 1] += chan_off[i];
+    std::vector<AnimChannel> chans(an->n_channels);
+    { std::vector<uint32_t> fill(chan_off.begin(), chan_off.end() - 1);
+      for (uint32_t c = 0; c < an->n_channels; c++) {
+          const auto &ch = an->channels[c];
+          chans[fill[ch.node]++] = AnimChannel{ ch.path, ch.first_step, ch.n_steps, an->end_time[ch.animation] };
+      } }
+    // one device allocation, 16-byte aligned pieces
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    drop_graphs(ctx);
+    size_t off = 0;
+    auto piece = [&](size_t bytes) { const size_t o = off; off = align16(off + bytes); return o; };
+    const size_t o_rot = piece((size_t)64 * n), o_tr = piece((size_t)12 * n), o_sc = piece((size_t)12 * n), o_par = piece((size_t)4 * n),
+                 o_ord = piece((size_t)4 * n), o_lvl = piece((size_t)4 * (n_levels + 1)), o_cho = piece((size_t)4 * (n + 1)),
+                 o_ch = piece(sizeof(AnimChannel) * chans.size()), o_st = piece((size_t)4 * an->n_steps), o_sv = piece((size_t)16 * an->n_steps),
+                 o_loc = piece((size_t)64 * n);
+    std::vector<uint8_t> host(off, 0);
+    if (n) {
+        memcpy(&host[o_rot], an->node_rotation, (size_t)64 * n); memcpy(&host[o_tr], an->node_translation, (size_t)12 * n);
+        memcpy(&host[o_sc], an->node_scale, (size_t)12 * n); memcpy(&host[o_par], an->node_parent, (size_t)4 * n);
+        memcpy(&host[o_ord], order.data(), (size_t)4 * n);
+    }
+    memcpy(&host[o_lvl], level_off.data(), 4 * level_off.size());
+    memcpy(&host[o_cho], chan_off.data(), 4 * chan_off.size());
+    if (!chans.empty()) memcpy(&host[o_ch], chans.data(), sizeof(AnimChannel) * chans.size());
+    if (an->n_steps) { memcpy(&host[o_st], an->step_time, (size_t)4 * an->n_steps); memcpy(&host[o_sv], an->step_value, (size_t)16 * an->n_steps); }
+    CK(dalloc(ctx->d_anim, off));
+    CK(cudaMemcpy(ctx->d_anim, host.data(), off, cudaMemcpyHostToDevice));
+    AnimTables &a = ctx->anim;
+    a.n_nodes = n; a.n_levels = n_levels;
+    a.base_rotation = reinterpret_cast<const float *>(ctx->d_anim + o_rot); a.base_translation = reinterpret_cast<const float *>(ctx->d_anim + o_tr);
+    a.base_scale = reinterpret_cast<const float *>(ctx->d_anim + o_sc); a.parent = reinterpret_cast<const int32_t *>(ctx->d_anim + o_par);
+    a.order = reinterpret_cast<const uint32_t *>(ctx->d_anim + o_ord); a.level_off = reinterpret_cast<const uint32_t *>(ctx->d_anim + o_lvl);
+    a.node_chan_off = reinterpret_cast<const uint32_t *>(ctx->d_anim + o_cho); a.channels = reinterpret_cast<const AnimChannel *>(ctx->d_anim + o_ch);
+    a.step_time = reinterpret_cast<const float *>(ctx->d_anim + o_st); a.step_value = reinterpret_cast<const float4 *>(ctx->d_anim + o_sv);
+    a.local = reinterpret_cast<float *>(ctx->d_anim + o_loc);
+    ctx->have_anim = true;
+    return SWEGL_B200_OK;
+}
+
+// the node matrices the device currently holds (after an animated frame: k_animate's), for parity checks
+int swegl_b200_read_node_matrices(swegl_b200_ctx *ctx, float *node_world, float *node_normal)
+{
+    if (!ctx) return SWEGL_B200_ERR_ARG;
+    if (!ctx->have_scene || !ctx->d_block) return fail(ctx, SWEGL_B200_ERR_STATE, "read_node_matrices before upload_scene");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (node_world) CK(cudaMemcpy(node_world, ctx->d_block + ctx->off_nw, (size_t)64 * ctx->n_nodes, cudaMemcpyDeviceToHost));
+    if (node_normal) CK(cudaMemcpy(node_normal, ctx->d_block + ctx->off_nn, (size_t)36 * ctx->n_nodes, cudaMemcpyDeviceToHost));
     return SWEGL_B200_OK;
 }
 
@@ -753,7 +868,16 @@ static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const Vie
     cudaStream_t st = ctx->stream;
     uint32_t launches = 0;
     if (timing) cudaEventRecord(ctx->ev[0], st);
-    if (with_frame) cudaMemcpyAsync(ctx->d_block, sl.block, ctx->block_bytes, cudaMemcpyHostToDevice, st);
+    if (with_frame && ctx->frame_animated) {
+        // animated frame: the slot carries FrameParams (with the time stamp), ViewParams and the lights; the node matrices
+        // in between are produced on the device by k_animate (scene_t::animate + hierarchy product), ahead of the vertex stage
+        cudaMemcpyAsync(ctx->d_block, sl.block, ctx->off_nw, cudaMemcpyHostToDevice, st);
+        if (ctx->block_bytes > ctx->off_lights)
+            cudaMemcpyAsync(ctx->d_block + ctx->off_lights, sl.block + ctx->off_lights, ctx->block_bytes - ctx->off_lights, cudaMemcpyHostToDevice, st);
+        launch_animate(ctx->anim, ctx->d_fp(), reinterpret_cast<float *>(ctx->d_block + ctx->off_nw), reinterpret_cast<float *>(ctx->d_block + ctx->off_nn), st);
+        launches++;
+    }
+    else if (with_frame) cudaMemcpyAsync(ctx->d_block, sl.block, ctx->block_bytes, cudaMemcpyHostToDevice, st);
     else cudaMemcpyAsync(ctx->d_block + ctx->off_vp, sl.block + ctx->off_vp, sizeof(ViewParams), cudaMemcpyHostToDevice, st);
     // frame protocol (FrameSync): rank 0 clears the other ranks' rows of its screen and announces the frame; the others
     // wait for that before their first store into it, skip the background, and raise their flag at the end
@@ -867,7 +991,7 @@ static int render_async(swegl_b200_ctx *ctx, const ViewParams &out, bool dof)
         const uint64_t tgt = (uint64_t)reinterpret_cast<uintptr_t>(ctx->color_target);
         const int32_t key[15] = { out.vx, out.vy, out.vw, out.vh, out.band0, out.band1, out.light_mode, out.tex_mode, (dof ? 1 : 0) | (out.n_layers << 1),
                                   ctx->sw, ctx->sh, (with_frame ? 1 : 0) | (synced ? 2 + 4 * ctx->sync_rank + 256 * ctx->sync_world : 0),
-                                  (ctx->dense_spans ? 1 : 0) | (with_world ? 2 : 0) | (ctx->fast_shading ? 4 : 0) | (tma ? 8 : 0),
+                                  (ctx->dense_spans ? 1 : 0) | (with_world ? 2 : 0) | (ctx->fast_shading ? 4 : 0) | (tma ? 8 : 0) | (with_frame && ctx->frame_animated ? 16 : 0),
                                   (int32_t)(tgt & 0xFFFFFFFFu), (int32_t)(tgt >> 32) };
         swegl_b200_ctx::ViewGraph *vg = nullptr;
         for (auto &g : ctx->view_graphs) if (memcmp(g.key, key, sizeof key) == 0) { vg = &g; break; }
@@ -1270,6 +1394,7 @@ int swegl_b200_enable_peer(swegl_b200_ctx *ctx, int peer_device)
 }
 
 int swegl_b200_device_of(const swegl_b200_ctx *ctx) { return ctx ? ctx->device : -1; }
+int swegl_b200_scene_opaque(const swegl_b200_ctx *ctx) { return (ctx && ctx->have_scene) ? (ctx->opaque ? 1 : 0) : -1; }
 
 int swegl_b200_read_depth(swegl_b200_ctx *ctx, float *zbuffer)
 {

@@ -84,6 +84,77 @@ public:
 		check(swegl_b200_begin_frame(m_ctx, &fd), "begin_frame");
 	}
 
+	// Device-side animation.  set_animation flattens scene.animations, the nodes' TRS as they are now and
+	// the hierarchy (children_idx) into swegl_b200_animation_desc; begin_frame_animated(scene, t) then stands for
+	//     scene.animate(t);                                   test_1.cpp:378, model.hpp:146-177
+	//     vertex_shader_t::original_to_world(scene);          vertex_shaders.hpp:16-33
+	// of one frame: the key-frame blend, the TRS -> matrix step and the hierarchy product run on the device, only the time
+	// stamp and the lights travel.  The host scene_t is NOT touched (its node_t::rotation / original_to_world_matrix keep
+	// their values); mix with begin_frame() at will.
+	void set_animation(const swegl::scene_t & scene)
+	{
+		upload_static_if_changed(scene);
+		const size_t n = scene.nodes.size();
+		std::vector<int32_t> parent(n, -1);
+		std::vector<float> rot(16 * n), tr(3 * n), sc(3 * n), end_time, step_time, step_value;
+		for (size_t i = 0; i < n; i++)
+		{
+			const auto & node = scene.nodes[i];
+			for (auto child : node.children_idx)
+				if (child >= 0 && (size_t)child < n) parent[(size_t)child] = (int32_t)i;
+			for (int r = 0; r < 4; r++)
+				for (int c = 0; c < 4; c++)
+					rot[16 * i + 4 * r + c] = node.rotation[r][c];
+			tr[3 * i] = node.translation.x(); tr[3 * i + 1] = node.translation.y(); tr[3 * i + 2] = node.translation.z();
+			sc[3 * i] = node.scale.x(); sc[3 * i + 1] = node.scale.y(); sc[3 * i + 2] = node.scale.z();
+		}
+		std::vector<swegl_b200_anim_channel> chans;
+		for (size_t a = 0; a < scene.animations.size(); a++)
+		{
+			end_time.push_back(scene.animations[a].end_time);
+			for (const auto & ch : scene.animations[a].channels)
+			{
+				swegl_b200_anim_channel c{};
+				c.animation = (int32_t)a; c.node = ch.node_idx; c.path = (int32_t)ch.path;
+				c.first_step = (uint32_t)step_time.size(); c.n_steps = (uint32_t)ch.steps.size();
+				for (const auto & st : ch.steps)
+				{
+					step_time.push_back(st.time);
+					step_value.push_back(st.value.x()); step_value.push_back(st.value.y());
+					step_value.push_back(st.value.z()); step_value.push_back(st.value.w());
+				}
+				chans.push_back(c);
+			}
+		}
+		swegl_b200_animation_desc ad{};
+		ad.n_nodes = (uint32_t)n;
+		ad.node_parent = parent.data(); ad.node_rotation = rot.data(); ad.node_translation = tr.data(); ad.node_scale = sc.data();
+		ad.n_animations = (uint32_t)end_time.size(); ad.end_time = end_time.data();
+		ad.n_channels = (uint32_t)chans.size(); ad.channels = chans.data();
+		ad.n_steps = (uint32_t)step_time.size(); ad.step_time = step_time.data(); ad.step_value = step_value.data();
+		check(swegl_b200_set_animation(m_ctx, &ad), "set_animation");
+		m_anim_uploaded = true;
+	}
+
+	void begin_frame_animated(const swegl::scene_t & scene, float elapsed_seconds)
+	{
+		upload_static_if_changed(scene);                // (a re-upload drops the device's animation tables)
+		if ( ! m_anim_uploaded) set_animation(scene);
+		m_lights.clear();
+		for (const auto & psl : scene.point_source_lights)
+		{
+			m_lights.push_back(psl.position.x()); m_lights.push_back(psl.position.y());
+			m_lights.push_back(psl.position.z()); m_lights.push_back(psl.intensity);
+		}
+		swegl_b200_frame_desc fd{};
+		fd.ambient = scene.ambient_light_intensity;
+		fd.sun_dir[0] = scene.sun_direction.x(); fd.sun_dir[1] = scene.sun_direction.y(); fd.sun_dir[2] = scene.sun_direction.z();
+		fd.sun_intensity = scene.sun_intensity;
+		fd.n_point_lights = (uint32_t)scene.point_source_lights.size();
+		fd.point_lights = m_lights.data();
+		check(swegl_b200_begin_frame_animated(m_ctx, elapsed_seconds, &fd), "begin_frame_animated");
+	}
+
 	// the device screen follows the SDL surface the viewports draw into
 	void ensure_screen(const SDL_Surface * screen)
 	{
@@ -147,6 +218,7 @@ private:
 	swegl_b200_ctx * m_ctx = nullptr;
 	int m_screen_w = 0, m_screen_h = 0;
 	std::string m_signature;
+	bool m_anim_uploaded = false;
 	std::vector<float> m_node_world, m_node_normal, m_lights;
 
 	// node_t::original_to_world_matrix for the whole hierarchy (vertex_shaders.hpp:16-18,26-27), without the
@@ -246,6 +318,7 @@ private:
 		sd.textures = texs.data();
 		check(swegl_b200_upload_scene(m_ctx, &sd), "upload_scene");
 		m_signature = sig;
+		m_anim_uploaded = false;
 	}
 };
 
@@ -262,6 +335,16 @@ void render(swegl::scene_t & scene, T &... viewports)
 {
 	engine_t & e = default_engine();
 	e.begin_frame(scene, false);
+	(e.render_viewport(scene, viewports), ...);
+}
+
+// drop-in for the application's pair  scene.animate(t); swegl::render(scene, viewports...)  (test_1.cpp:374-378) with the
+// animation evaluated on the device
+template <typename... T>
+void render_animated(swegl::scene_t & scene, float elapsed_seconds, T &... viewports)
+{
+	engine_t & e = default_engine();
+	e.begin_frame_animated(scene, elapsed_seconds);
 	(e.render_viewport(scene, viewports), ...);
 }
 

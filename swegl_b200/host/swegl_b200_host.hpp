@@ -106,7 +106,7 @@ public:
 		const int n = world();
 		prepare(scene, vp.m_screen);
 		swegl_b200_viewport_desc base = engine_t::describe(vp);
-		if (base.transparency_layers > 0 && n > 1)
+		if (base.transparency_layers > 0 && n > 1 && swegl_b200_scene_opaque(m_engines[0]->ctx()) != 1)     // (opaque scenes: the layers are the identity)
 			throw std::runtime_error("swegl_b200: transparency layers are not sharded (render the viewport on one context)");
 		if (m_bands.size() != (size_t)n + 1 || m_bands_h != vp.m_h) even_bands(vp.m_h);
 		std::vector<swegl_b200_viewport_desc> d(n, base);

@@ -88,5 +88,36 @@ class FramePipeline:
         torch.cuda.synchronize(self.device)
         return e0.elapsed_time(e1)
 
+    def measure_batches(self, scene, viewports, batches, frames_per_batch, warmup=6):
+        """-> [milliseconds of each of `batches` batches of `frames_per_batch` frames]: every batch is bracketed by its own
+        pair of CUDA events on the current torch stream (fork to the context streams before its first frame, join after
+        its last), the batches follow each other without a host synchronisation"""
+        torch = self.torch
+        main = torch.cuda.current_stream(self.device)
+        descs = [vp.desc() for vp in viewports]
+        nodes = scene.node_matrices()
+        self.size_pools(scene, viewports)
+        for _ in range(warmup):
+            self.submit(scene, descs, nodes)
+        self.synchronize()
+        torch.cuda.synchronize(self.device)
+        ev = []
+        for _ in range(batches):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(main)
+            for s in self.streams:
+                s.wait_event(e0)
+            for _ in range(frames_per_batch):
+                self.submit(scene, descs, nodes)
+            for s in self.streams:
+                done = torch.cuda.Event()
+                done.record(s)
+                main.wait_event(done)
+            e1.record(main)
+            ev.append((e0, e1))
+        self.synchronize()
+        torch.cuda.synchronize(self.device)
+        return [a.elapsed_time(b) for a, b in ev]
+
     def read_screen(self, k):
         return self.renderers[k].read_screen()

@@ -87,6 +87,26 @@ class Renderer:
         fd = scene.frame_desc(*(node_mats or (None, None)))
         self._check(self.lib.swegl_b200_begin_frame(self.ctx, C.byref(fd)))
 
+    def set_animation(self, scene=None):
+        """upload the scene's key frames, base TRS and hierarchy (swegl_b200_set_animation); call after upload_scene and
+        BEFORE the first Scene.animate() on `scene` (the base TRS is the scene as loaded)"""
+        scene = scene or self.scene
+        ad = scene.animation_desc()
+        self._check(self.lib.swegl_b200_set_animation(self.ctx, C.byref(ad)))
+
+    def begin_frame_animated(self, elapsed_seconds, scene=None):
+        """scene_t::animate(t) + the node-hierarchy product on the device: only the time stamp and the lights travel"""
+        scene = scene or self.scene
+        fd = scene.frame_desc(lights_only=True)
+        self._check(self.lib.swegl_b200_begin_frame_animated(self.ctx, C.c_float(elapsed_seconds), C.byref(fd)))
+
+    def read_node_matrices(self):
+        """-> (node_world (n,4,4), node_normal (n,3,3)) as the device holds them after the last rendered frame"""
+        n = self.scene.n_nodes
+        w, nn = np.zeros((n, 4, 4), np.float32), np.zeros((n, 3, 3), np.float32)
+        self._check(self.lib.swegl_b200_read_node_matrices(self.ctx, w.ctypes.data, nn.ctypes.data))
+        return w, nn
+
     def render_device(self, viewport, stats=True):
         """_render() with the result left in HBM."""
         vd = viewport.desc() if not isinstance(viewport, _abi.ViewportDesc) else viewport

@@ -379,21 +379,52 @@ class Scene:
         self._keep = keep
         return d
 
-    def frame_desc(self, node_world=None, node_normal=None):
+    def frame_desc(self, node_world=None, node_normal=None, lights_only=False):
         import ctypes as C
-        if node_world is None:
-            node_world, node_normal = self.node_matrices()
         d = _abi.FrameDesc()
-        self._nw = np.ascontiguousarray(node_world, dtype=np.float32).reshape(-1)
-        self._nn = np.ascontiguousarray(node_normal, dtype=np.float32).reshape(-1)
+        if not lights_only:
+            if node_world is None:
+                node_world, node_normal = self.node_matrices()
+            self._nw = np.ascontiguousarray(node_world, dtype=np.float32).reshape(-1)
+            self._nn = np.ascontiguousarray(node_normal, dtype=np.float32).reshape(-1)
+            d.node_world = self._nw.ctypes.data_as(C.POINTER(C.c_float))
+            d.node_normal = self._nn.ctypes.data_as(C.POINTER(C.c_float))
         self._pl = np.ascontiguousarray(self.point_lights, dtype=np.float32).reshape(-1)
-        d.node_world = self._nw.ctypes.data_as(C.POINTER(C.c_float))
-        d.node_normal = self._nn.ctypes.data_as(C.POINTER(C.c_float))
         d.ambient = float(f32(self.ambient))
         d.sun_dir[:] = [float(v) for v in self.sun_dir]
         d.sun_intensity = float(f32(self.sun_intensity))
         d.n_point_lights = len(self.point_lights)
         d.point_lights = self._pl.ctypes.data_as(C.POINTER(C.c_float))
+        return d
+
+    def animation_desc(self):
+        """swegl_b200_animation_desc of the scene AS IT IS NOW (take it before the first animate(): the device evaluates
+        scene_t::animate from the base TRS, model.hpp:146-177)"""
+        import ctypes as C
+        d = _abi.AnimationDesc()
+        n, nc = self.n_nodes, len(self.chan_node)
+        keep = [np.ascontiguousarray(self.node_parent, dtype=np.int32), np.ascontiguousarray(self.node_rotation, dtype=np.float32),
+                np.ascontiguousarray(self.node_translation, dtype=np.float32), np.ascontiguousarray(self.node_scale, dtype=np.float32),
+                np.ascontiguousarray(self.anim_end_time, dtype=np.float32), np.ascontiguousarray(self.step_time, dtype=np.float32),
+                np.ascontiguousarray(self.step_value, dtype=np.float32)]
+        chans = (_abi.AnimChannel * max(1, nc))()
+        for c in range(nc):
+            chans[c] = _abi.AnimChannel(int(self.chan_anim[c]), int(self.chan_node[c]), int(self.chan_path[c]),
+                                        int(self.chan_first_step[c]), int(self.chan_n_steps[c]))
+        d.n_nodes = n
+        d.node_parent = keep[0].ctypes.data_as(C.POINTER(C.c_int32))
+        d.node_rotation = keep[1].ctypes.data_as(C.POINTER(C.c_float))
+        d.node_translation = keep[2].ctypes.data_as(C.POINTER(C.c_float))
+        d.node_scale = keep[3].ctypes.data_as(C.POINTER(C.c_float))
+        d.n_animations = len(self.anim_end_time)
+        d.end_time = keep[4].ctypes.data_as(C.POINTER(C.c_float))
+        d.n_channels = nc
+        d.channels = chans
+        d.n_steps = len(self.step_time)
+        d.step_time = keep[5].ctypes.data_as(C.POINTER(C.c_float))
+        d.step_value = keep[6].ctypes.data_as(C.POINTER(C.c_float))
+        assert keep[6].size == 4 * len(self.step_time)
+        self._keep_anim = keep + [chans]
         return d
 
     # ---- scene packs (assets/*.scenepack): npz-style zip of the arrays + encoded images ----
@@ -623,6 +654,10 @@ def decode_image(data):
     reference's libpng / libjpeg readers produce (src/misc/image.cpp:93-258), decoded by the package's own C++ decoder
     (swegl_b200_decode_image, host/image_decode.cpp) -- no imaging library involved."""
     import ctypes as C
+    if os.environ.get("SWEGL_B200_IMAGE_DECODER") == "pil":
+        # bench.py --impl reference: the reference arm must not load the product library at all; the scene packs' texel
+        # digests (texel_digest) make sure both decoders give the same texels
+        return decode_image_bgra(data)
     lib = _abi.load()
     ptr, w, h = C.POINTER(C.c_uint32)(), C.c_int32(), C.c_int32()
     data = bytes(data)

@@ -127,3 +127,100 @@ def test_animated_sequence_through_the_dropin(oracle):
         d = np.abs(px.view(np.uint8).astype(np.int16) - o["pixels"].view(np.uint8).astype(np.int16))
         assert d.max() <= 1, t
     dropin.lib.ref_viewport_free(rv); dropin.lib.ref_screen_free(scr); dropin.lib.ref_scene_free(h)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ANIMATED)
+def test_device_side_animate_matrices_bit_exact(renderer, name):
+    """swegl_b200_set_animation + begin_frame_animated(t): k_animate's node_world / node_normal == Scene.animate(t) +
+    node_matrices() bit for bit (which test_animate_matches_reference pins against the unmodified reference), at every
+    probe time, in shuffled order (the device state is a function of t alone), interleaved with host-side frames"""
+    scene = fresh(name)
+    scene.set_lights(0.3, (1, -2, -1), 0.7, configs.POINT_LIGHTS)
+    vp = Viewport(0, 0, 64, 48)
+    vp.camera.apply(configs.POSE_TEST1)
+    renderer.upload_scene(scene)
+    renderer.set_screen(64, 48)
+    renderer.set_animation(scene)                    # base TRS = the scene as loaded
+    host = fresh(name)
+    order = TIMES[::2] + TIMES[1::2][::-1]
+    for k, t in enumerate(order):
+        renderer.begin_frame_animated(t, scene)
+        renderer.render_device(vp, stats=(k % 2 == 0))          # direct launches and the captured-graph path
+        w, n = renderer.read_node_matrices()
+        host.animate(t)
+        hw, hn = host.node_matrices()
+        assert (w.view(np.uint32) == hw.view(np.uint32)).all(), (t, "node_world")
+        assert (n.view(np.uint32) == hn.view(np.uint32)).all(), (t, "node_normal")
+        if k == 3:                                   # a host-side frame in between does not disturb the device tables
+            renderer.begin_frame(scene)
+            renderer.render_device(vp, stats=True)
+            w0, _ = renderer.read_node_matrices()
+            assert (w0.view(np.uint32) == scene.node_matrices()[0].view(np.uint32)).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,res", [("CesiumMilkTruck", (960, 540)), ("BrainStem", (640, 360)), ("BoxAnimated", (320, 240))])
+def test_device_side_animated_frames_match_the_oracle(renderer, oracle, name, res):
+    """whole frames: begin_frame_animated(t) + render (blocking, and pipelined through render_async) == oracle on the scene
+    after Scene.animate(t)"""
+    scene = fresh(name)
+    scene.set_lights(0.3, (1, -2, -1), 0.7, configs.POINT_LIGHTS)
+    vp = Viewport(0, 0, *res)
+    vp.camera.apply(configs.POSE_TEST1)
+    renderer.upload_scene(scene)
+    renderer.set_screen(*res)
+    renderer.set_animation(scene)
+    host = fresh(name)
+    host.set_lights(0.3, (1, -2, -1), 0.7, configs.POINT_LIGHTS)
+    images = [renderer.alloc_host((res[1], res[0]), np.uint32) for _ in range(2)]
+    depths = [renderer.alloc_host((res[1], res[0]), np.float32) for _ in range(2)]
+    times = (0.0, 0.21, 0.7, 1.9, 40.0)
+    want = []
+    for t in times:
+        host.animate(t)
+        want.append(oracle.render(host, vp, screen_wh=res))
+    for t, o in zip(times, want):                    # blocking
+        renderer.begin_frame_animated(t, scene)
+        px = np.zeros((res[1], res[0]), np.uint32)
+        z = np.empty((res[1], res[0]), np.float32)
+        renderer.render(vp, px, z)
+        assert (z.view(np.uint32) == o["z"].view(np.uint32)).all(), t
+        assert np.abs(px.view(np.uint8).astype(np.int16) - o["pixels"].view(np.uint8).astype(np.int16)).max() <= 1, t
+    tickets = []
+    for k, t in enumerate(times):                    # two frames in flight
+        if k >= 2:
+            renderer.wait(tickets[k - 2])
+            o = want[k - 2]
+            assert (depths[k & 1].view(np.uint32) == o["z"].view(np.uint32)).all(), times[k - 2]
+            assert np.abs(images[k & 1].view(np.uint8).astype(np.int16) - o["pixels"].view(np.uint8).astype(np.int16)).max() <= 1
+        renderer.begin_frame_animated(t, scene)
+        tickets.append(renderer.render_async(vp, images[k & 1], depths[k & 1]))
+    for k in (len(times) - 2, len(times) - 1):
+        renderer.wait(tickets[k])
+        o = want[k]
+        assert (depths[k & 1].view(np.uint32) == o["z"].view(np.uint32)).all()
+        assert np.abs(images[k & 1].view(np.uint8).astype(np.int16) - o["pixels"].view(np.uint8).astype(np.int16)).max() <= 1
+
+
+@pytest.mark.gpu
+def test_device_side_animation_argument_checks(renderer):
+    from swegl_b200.renderer import SweglB200Error
+    scene = fresh("BoxAnimated")
+    renderer.upload_scene(scene)
+    renderer.set_screen(32, 32)
+    with pytest.raises(SweglB200Error) as e:          # begin_frame_animated before set_animation (upload_scene dropped the tables)
+        renderer.begin_frame_animated(0.5, scene)
+    assert e.value.status == _abi.ERR_STATE
+    bad = fresh("BoxAnimated")
+    bad.node_parent = bad.node_parent.copy()
+    bad.node_parent[0] = 0                            # a node that is its own parent
+    with pytest.raises(SweglB200Error) as e:
+        renderer.set_animation(bad)
+    assert e.value.status == _abi.ERR_ARG
+    bad = fresh("BoxAnimated")
+    bad.chan_n_steps = bad.chan_n_steps.copy()
+    bad.chan_n_steps[0] = len(bad.step_time) + 5      # key frames beyond the arrays
+    with pytest.raises(SweglB200Error) as e:
+        renderer.set_animation(bad)
+    assert e.value.status == _abi.ERR_ARG

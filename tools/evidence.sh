@@ -7,7 +7,7 @@ tag=${1:-run}
 out=gpurun_out
 mkdir -p $out
 python -m pytest tests -m gpu -q 2>&1 | tail -3 > $out/${tag}_tests.log
-python bench.py --steps 100 --warmup 10 > $out/${tag}_bench.json 2> $out/${tag}_bench.err
+python bench.py --gpus 1 --steps 20 --warmup 5 > $out/${tag}_bench.json 2> $out/${tag}_bench.err
 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_ref.json 2> $out/${tag}_ref.err
 B="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-also --pipeline-depth 1"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv $B > /dev/null 2>&1
