@@ -353,6 +353,11 @@ const char *swegl_b200_image_error(void);
  * out[0] = quotients whose bits differ (must be 0), out[1] = pairs that took the fast path.  No reference counterpart:
  * it guards the bit-exactness of normalize() (points.hpp:71-90) and of the light sums (pixel_shaders.cpp:173-203). */
 int  swegl_b200_selftest_division(swegl_b200_ctx *ctx, uint64_t n_pairs, uint32_t seed, uint64_t out[2]);
+/* Self-test of the FAST kernels' bilinear filter (same arithmetic as pixel_shader_texture_bilinear::shade,
+ * pixel_shaders.cpp:348-384, without the per-operation range checks; csrc/fragment.cu tex_filter_bilinear_fast) against the
+ * exact kernels' filter over `n_samples` generated (texels, texture coordinate) samples below the 2^21 guard.
+ * out[0] = samples whose filtered colour or texel index differs (must be 0). */
+int  swegl_b200_selftest_filter(swegl_b200_ctx *ctx, uint64_t n_samples, uint32_t seed, uint64_t out[1]);
 
 #ifdef __cplusplus
 }

@@ -123,6 +123,7 @@ SYMBOLS = [
     ("swegl_b200_set_band_culling", C.c_int, [C.c_void_p, C.c_int]),
     ("swegl_b200_cull_counts", C.c_int, [C.c_void_p, C.c_void_p]),
     ("swegl_b200_selftest_division", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
+    ("swegl_b200_selftest_filter", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
     ("swegl_b200_decode_image", C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("swegl_b200_image_free", None, [C.POINTER(C.c_uint32)]),
     ("swegl_b200_image_error", C.c_char_p, []),

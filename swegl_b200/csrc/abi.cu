@@ -1459,6 +1459,22 @@ int swegl_b200_selftest_division(swegl_b200_ctx *ctx, uint64_t n_pairs, uint32_t
     return SWEGL_B200_OK;
 }
 
+int swegl_b200_selftest_filter(swegl_b200_ctx *ctx, uint64_t n_samples, uint32_t seed, uint64_t out[1])
+{
+    if (!ctx || !out) return fail(ctx, SWEGL_B200_ERR_ARG, "selftest_filter: null argument");
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long *d = nullptr;
+    CK(cudaMalloc(&d, 8));
+    CK(cudaMemsetAsync(d, 0, 8, ctx->stream));
+    launch_selftest_filter(n_samples, seed, d, ctx->stream);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    CK(e);
+    return SWEGL_B200_OK;
+}
+
 int swegl_b200_cull_counts(swegl_b200_ctx *ctx, uint32_t counts[6])
 {
     if (!ctx || !counts) return SWEGL_B200_ERR_ARG;

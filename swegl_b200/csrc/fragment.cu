@@ -238,9 +238,62 @@ SB_DEV bool phong_light_fast(const SpanShade *ss, const ViewParams &vp, const Fr
     return ok;
 }
 
+// ----------------------------------------------------------------------------------------
+// The bilinear filter of the fast kernels: the SAME arithmetic as tex_fetch / tex_filter above (bit-identical texels, weights,
+// products, sums and rounding), minus the per-operation range checks.  The caller guarantees |t| < 2^21 for both texture
+// coordinates (a pixel outside takes the exact shader), and then
+//   * (int)(t - 0.5) is a plain truncation (no cvttss2si overflow case), floor(t + 0.5) is RD(x + 1.5 * 2^23) - 1.5 * 2^23;
+//   * the four weights are >= 0 (rounding is monotone: floor(RN(t + 0.5)) >= RN(t - 0.5)) and sum to 1 +- 2^-2, so every
+//     channel sum lies in [0, 2^10): (unsigned char)round(acc) = trunc(RZ(acc + 0.5)) -- RZ, not RN, so that
+//     0.5 - 2^-25 + 0.5 does not round up to 1 -- read off the low mantissa bits of RZ(. + 2^23);
+//   * below |t| < 2^12 the weights sum to 1 +- 2^-11, so four texels of alpha 255 give 255 +- 0.13 -> 255 without computing it.
+// ----------------------------------------------------------------------------------------
+template <int K> SB_DEV float byte_to_float_r(uint32_t word, uint32_t k4b)
+{
+    return __fsub_rn(__uint_as_float(__byte_perm(word, k4b, 0x7440u | K)), MAGIC23);
+}
+SB_DEV uint32_t round_bits_small(float acc)     // 0x4B0000bb with bb = (unsigned char)round(acc), for 0 <= acc < 2^22
+{
+    return __float_as_uint(__fadd_rz(__fadd_rz(acc, 0.5f), MAGIC23));
+}
+SB_DEV TexFetch tex_fetch_bilinear_fast(float tx, float ty, const Prim &pr, const uint32_t *texels)
+{
+    TexFetch f;
+    const uint32_t *bm = texels + pr.tex_off;
+    const float v1 = fsub(tx, 0.5f), u1 = fsub(ty, 0.5f);
+    const int tw = pr.tw, th = pr.th;
+    int v1m = wrap_index(__float2int_rz(v1) + th, th, pr.th_mask);
+    int v2m = v1m + 1; if (v2m == th) v2m = 0;
+    v1m *= tw; v2m *= tw;
+    const int u1m = wrap_index(__float2int_rz(u1) + tw, tw, pr.tw_mask);
+    int u2m = u1m + 1; if (u2m == tw) u2m = 0;
+    f.p00 = __ldg(&bm[v1m + u1m]); f.p10 = __ldg(&bm[v2m + u1m]);
+    f.p01 = __ldg(&bm[v1m + u2m]); f.p11 = __ldg(&bm[v2m + u2m]);
+    f.fu = ty; f.fv = tx;
+    return f;
+}
+// k4b = 0x4B000000 handed in as a RUN-TIME value (FragGeom::k4b, a kernel parameter): as a literal, ptxas makes it PRMT's
+// immediate and spends an instruction per conversion on materialising the selector in a register instead
+SB_DEV uint32_t tex_filter_bilinear_fast(const TexFetch &f, const uint32_t k4b)
+{
+    const float u1 = fsub(f.fu, 0.5f), u2 = fadd(f.fu, 0.5f), v1 = fsub(f.fv, 0.5f), v2 = fadd(f.fv, 0.5f);
+    const float uq = __fsub_rn(__fadd_rd(u2, 12582912.0f), 12582912.0f), v = __fsub_rn(__fadd_rd(v2, 12582912.0f), 12582912.0f);
+    const uint32_t p00 = f.p00, p10 = f.p10, p01 = f.p01, p11 = f.p11;
+    const float w00 = fmul(fsub(uq, u1), fsub(v, v1)), w10 = fmul(fsub(uq, u1), fsub(v2, v));
+    const float w01 = fmul(fsub(u2, uq), fsub(v, v1)), w11 = fmul(fsub(u2, uq), fsub(v2, v));
+    #define SB_FAST_CHANNEL(C) round_bits_small(fadd(fadd(fadd(fmul(byte_to_float_r<C>(p00, k4b), w00), fmul(byte_to_float_r<C>(p10, k4b), w10)), \
+                                                          fmul(byte_to_float_r<C>(p01, k4b), w01)), fmul(byte_to_float_r<C>(p11, k4b), w11)))
+    const uint32_t b = SB_FAST_CHANNEL(0), g = SB_FAST_CHANNEL(1), r = SB_FAST_CHANNEL(2);
+    uint32_t a = 0xFFu;
+    if ((p00 & p10 & p01 & p11) < 0xFF000000u || !(fabsf(f.fu) < 4096.0f && fabsf(f.fv) < 4096.0f)) a = SB_FAST_CHANNEL(3);
+    #undef SB_FAST_CHANNEL
+    // low bytes of b, g, r, a -> one word
+    return __byte_perm(__byte_perm(b, g, 0x0040u), __byte_perm(r, a, 0x0040u), 0x5410u);
+}
+
 // one winner -> its colour
 template <int LIGHT, int TEX, int FAST>
-SB_DEV uint32_t shade_winner(const Pools &pl, const uint32_t *texels, const ViewParams &vp, const FrameParams &fp, uint32_t span, uint32_t slot, float u);
+SB_DEV uint32_t shade_winner(const Pools &pl, const uint32_t *texels, const ViewParams &vp, const FrameParams &fp, uint32_t span, uint32_t slot, float u, uint32_t k4b);
 
 // the exact shader, out of line: the fast kernels call it for the few pixels next to a discontinuity
 template <int LIGHT, int TEX>
@@ -255,7 +308,7 @@ static __device__ __noinline__ uint32_t shade_exact_call(const SpanShade *ss, fl
 }
 
 template <int LIGHT, int TEX, int FAST>
-SB_DEV uint32_t shade_winner(const Pools &pl, const uint32_t *texels, const ViewParams &vp, const FrameParams &fp, uint32_t span, uint32_t slot, float u)
+SB_DEV uint32_t shade_winner(const Pools &pl, const uint32_t *texels, const ViewParams &vp, const FrameParams &fp, uint32_t span, uint32_t slot, float u, uint32_t k4b)
 {
     const SpanShade *ss = &pl.span_shades[span];
     const SlotShade *sh = &pl.shades[slot];
@@ -267,6 +320,16 @@ SB_DEV uint32_t shade_winner(const Pools &pl, const uint32_t *texels, const View
 #ifdef FRAG_PROBE_NOSHADE
     return 0xFF00FF00u ^ bind.x ^ __float_as_uint(u) ^ __float_as_uint(ss->v[0]);      // timing probe only: what the kernel costs without the shader
 #else
+    if (FAST && TEX == SWEGL_B200_TEX_BILINEAR) {
+        // t = t_left + t_dir * progress (pixel_shaders.cpp:352); a coordinate beyond 2^21 (or NaN) takes the exact shader
+        const float tx = fadd(ss->t_left[0], fmul(ss->t_dir[0], u)), ty = fadd(ss->t_left[1], fmul(ss->t_dir[1], u));
+        int li;
+        if (fabsf(tx) < 2097152.0f && fabsf(ty) < 2097152.0f) {
+            const TexFetch tf = tex_fetch_bilinear_fast(tx, ty, pr, texels);   // texel loads in flight under the lighting
+            if (phong_light_fast(ss, vp, fp, u, li)) return combine_light(tex_filter_bilinear_fast(tf, k4b), li);
+        }
+        return shade_exact_call<LIGHT, TEX>(ss, 0.0f, bind, texels, &vp, &fp, u);
+    }
     if (FAST) {
         const TexFetch tf = tex_fetch<TEX>(ss, pr, texels, u);             // texel loads in flight under the lighting
         int li;
@@ -282,8 +345,11 @@ static constexpr int FRAG_STAGE = 16;           // pieces of a bin staged in sha
 
 // per-warp staging of the slot records of the current round
 struct FragWarp {
-    uint4 rec[FRAG_STAGE * 2];          // Chunk records, 2 x 16 B each
+    uint4 rec[FRAG_STRETCH][FRAG_STAGE * 2];    // Chunk records (2 x 16 B each) of the row's bins: the first FRAG_STAGE of every bin are staged together
 };
+// a load hint: bring the line into L1 / L2 without a destination register (the resolve and shading loads that follow
+// find it there instead of paying a round trip to L2 / HBM each)
+SB_DEV void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 
 // the part of ViewParams that is fixed for a captured frame graph (rectangle, band), passed by value so that the
 // first loads of the kernel do not wait for the parameter block
@@ -294,6 +360,7 @@ struct FragGeom {
     int32_t dof, ndx, n_dof;            // DoF tiles per row / in total (grid anchored at band0, like the fragment tiles)
     int32_t out0, out1;                 // viewport-relative rows [out0, out1) the post pass outputs
     int32_t dof_pitch;                  // pitch of the post pass's destination
+    uint32_t k4b;                       // 0x4B000000 (the bits of 2^23), see tex_filter_bilinear_fast
 };
 
 // clear values (viewport.cpp:88-113) for one row of a tile: colour 0, depth 0x7F7F7F7F
@@ -345,9 +412,12 @@ SB_DEV void dof_tile_duty(const Pools &pl, const FragGeom &g, uint32_t stamp, ui
     if (yb <= ya) return;
     const bool vec = (reinterpret_cast<uintptr_t>(dof_dst) & 15) == 0 && (g.dof_pitch & 3) == 0 && wd == DOF_OW;
     if (vec) {
+        // 16 lanes cover a 64-pixel row with 128-bit stores: the warp does two rows per step
+        static_assert(DOF_OW / 4 == 16, "two rows of a DoF tile per warp step");
         const uint4 v4 = make_uint4(fill, fill, fill, fill);
-        for (int k = lane; k < (yb - ya) * (DOF_OW / 4); k += 32)
-            *reinterpret_cast<uint4 *>(dof_dst + (size_t)(ya + k / (DOF_OW / 4)) * g.dof_pitch + x0 + (k % (DOF_OW / 4)) * 4) = v4;
+        uint4 *q = reinterpret_cast<uint4 *>(dof_dst + (size_t)(ya + (lane >> 4)) * g.dof_pitch + x0) + (lane & 15);
+        const size_t step = (size_t)(g.dof_pitch >> 1);                     // two rows, in 16-byte units
+        for (int y = ya + (lane >> 4); y < yb; y += 2, q += step) *q = v4;
     } else {
         for (int k = lane; k < (yb - ya) * wd; k += 32)
             dof_dst[(size_t)(ya + k / wd) * g.dof_pitch + x0 + k % wd] = fill;
@@ -379,6 +449,16 @@ static constexpr int RESOLVE_UNROLL = FRAG_RESOLVE_UNROLL;     // chunks of a bi
 #ifndef FRAG_CTAS_PER_SM
 #define FRAG_CTAS_PER_SM FRAG_MINB
 #endif
+SB_DEV unsigned long long global_ns();
+#ifdef FRAG_PROBE_TIMELINE
+// probe build only: per CTA, the %globaltimer at kernel entry, after the dependency wait, and at the end of every item
+__device__ unsigned long long g_frag_timeline[2048 * 16];
+#define FRAG_TL(slot, v) do { if (threadIdx.x == 0 && blockIdx.x < 2048 && (slot) < 16) g_frag_timeline[blockIdx.x * 16 + (slot)] = (v); } while (0)
+#define FRAG_PH(slot) do { if (tl_first) FRAG_TL(slot, global_ns()); } while (0)
+#else
+#define FRAG_PH(slot) do { } while (0)
+#define FRAG_TL(slot, v) do { } while (0)
+#endif
 template <int LIGHT, int TEX, int FAST>
 __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s, const ViewParams *__restrict__ vpp,
                                                         const FrameParams *__restrict__ fpp, Pools pl, FragGeom g,
@@ -394,6 +474,7 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int band_rows = g.band1 - g.band0, anchor = g.band0 - g.vy;
     pdl_trigger();
+    FRAG_TL(0, global_ns());
     // the parameter block is written by the copy at the head of the chain, not by a kernel: readable before the wait
     for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += FRAG_TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
     for (int w = threadIdx.x; w < (int)(sizeof(FrameParams) / 4); w += FRAG_TPB) reinterpret_cast<uint32_t *>(&fp)[w] = reinterpret_cast<const uint32_t *>(fpp)[w];
@@ -402,6 +483,10 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
     Counters *const cn = pl.counters;
     const uint32_t n_busy = cn->n_busy;
     const uint32_t stamp = vp.stamp;
+    FRAG_TL(1, global_ns());
+#ifdef FRAG_PROBE_TIMELINE
+    int tl_slot = 2;
+#endif
     // CTA-level items: [0, n_busy) = the busy tiles, then n_groups streaming groups (8 fragment tiles to clear and 8 DoF tiles
     // to classify, one of each per warp).  Busy tiles come first: the CTAs whose tile was light finish early and take the
     // streaming groups, whose stores then drain underneath the arithmetic of the heavy tiles.
@@ -443,16 +528,39 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
                 const int row0 = anchor + ty * FRAG_ROWS, bx0 = tx * FRAG_STRETCH;
                 const int rows_here = min(FRAG_ROWS, band_rows - ty * FRAG_ROWS);
                 const int px_left = g.vw - (bx0 << 5);
-                for (int r = 0; r < rows_here; r++)
-                    clear_tile_row(color + (size_t)(g.vy + row0 + r) * color_pitch + g.vx + (bx0 << 5),
-                                   depth + (size_t)(row0 + r) * g.vw + (bx0 << 5), px_left, lane, with_color);
+                uint32_t *c0 = color + (size_t)(g.vy + row0) * color_pitch + g.vx + (bx0 << 5);
+                float *d0 = depth + (size_t)row0 * g.vw + (bx0 << 5);
+                if (px_left >= FRAG_STRETCH * 32 && ((color_pitch | g.vw) & 3) == 0
+                    && ((reinterpret_cast<uintptr_t>(c0) | reinterpret_cast<uintptr_t>(d0)) & 15) == 0) {
+                    // the common case, a whole tile of 16-byte aligned rows: lane = 4 pixels, one 128-bit store per row and plane
+                    const float maxz = __uint_as_float(MAXZ_BITS);
+                    uint4 *cq = reinterpret_cast<uint4 *>(c0) + lane;
+                    float4 *dq = reinterpret_cast<float4 *>(d0) + lane;
+                    const int cstep = color_pitch >> 2, dstep = g.vw >> 2;
+                    #pragma unroll
+                    for (int r = 0; r < FRAG_ROWS; r++) {
+                        if (r < rows_here) {
+                            if (with_color) cq[(size_t)r * cstep] = make_uint4(0, 0, 0, 0);
+                            dq[(size_t)r * dstep] = make_float4(maxz, maxz, maxz, maxz);
+                        }
+                    }
+                } else {
+                    for (int r = 0; r < rows_here; r++)
+                        clear_tile_row(c0 + (size_t)r * color_pitch, d0 + (size_t)r * g.vw, px_left, lane, with_color);
+                }
             }
             if (g.dof && q < (uint32_t)g.n_dof) dof_tile_duty(pl, g, stamp, dof_fill, dof_dst, q, lane);   // DoF duty
 #endif
         } else do {
             // ---- a busy tile: the CTA's warps take its rows (their spans, pieces and texels are neighbours in memory) ----
-            const int t = (int)pl.busy_list[p];
-            const int ty = t / g.ntx, tx = t - ty * g.ntx;
+#ifdef FRAG_PROBE_TIMELINE
+            const bool tl_first = tl_slot == 2;
+#endif
+            FRAG_PH(8);
+            const uint32_t t = pl.busy_list[p];                             // tile row << 16 | tile column (k_spans)
+            const int ty = (int)(t >> 16), tx = (int)(t & 0xFFFFu);
+            if (t == 0xFFFFFFFEu) break;                                    // (never: makes the stamp below wait for the load)
+            FRAG_PH(9);
             tx0 = min(tx0, (uint32_t)tx); tx1 = max(tx1, (uint32_t)tx + 1); ty0 = min(ty0, (uint32_t)ty); ty1 = max(ty1, (uint32_t)ty + 1);
             if (warp >= min(FRAG_ROWS, band_rows - ty * FRAG_ROWS)) break;
             const int row = anchor + ty * FRAG_ROWS + warp;                 // viewport-relative
@@ -469,6 +577,7 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
                 if (cnt > BIN_SLOTS) { over = pl.bin_head[bin0 + lane]; pl.bin_head[bin0 + lane] = -1; }
             }
             unsigned mask = __ballot_sync(0xFFFFFFFFu, cnt > 0);
+            FRAG_PH(10);
             uint32_t *crow = color + (size_t)y * color_pitch + g.vx + (bx0 << 5);
             float *drow = depth + (size_t)row * g.vw + (bx0 << 5);
             const bool aligned = ((reinterpret_cast<uintptr_t>(crow) | reinterpret_cast<uintptr_t>(drow)) & 15) == 0;
@@ -488,9 +597,33 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
                 }
             }
             if (!mask) break;
-            // ---- non-empty bins: depth resolve.  Per bin, rounds of up to FRAG_STAGE pieces: the lanes fetch one slot record
-            //      each (independent loads, one round trip) into shared memory, then lane = pixel and the nearest fragment of
-            //      every pixel is kept in registers ----
+            // ---- non-empty bins.  The first FRAG_STAGE slot records of EVERY bin of the row are fetched at once (lane = half a
+            //      record, up to four independent 128-bit loads per lane), and every record's fragment-stream segment, span
+            //      constants and colour binding are prefetched into L1 right away: the row pays these round trips once, side by
+            //      side, instead of one after the other in front of every bin ----
+            __syncwarp();                                                   // fw of the previous item is consumed
+            #pragma unroll
+            for (int b = 0; b < FRAG_STRETCH; b++) {
+                const int nk = min(__shfl_sync(0xFFFFFFFFu, cnt, b), FRAG_STAGE);
+                if (lane < 2 * nk) fw.rec[b][lane] = reinterpret_cast<const uint4 *>(pl.bin_slots + (bin0 + b) * BIN_SLOTS)[lane];
+            }
+            __syncwarp();
+            FRAG_PH(11);
+#ifndef FRAG_NO_PREFETCH
+            #pragma unroll
+            for (int h = 0; h < FRAG_STAGE / 8; h++) {
+                const int b = lane >> 3, k = (lane & 7) + 8 * h;           // FRAG_STRETCH * 8 == 32 lanes
+                if (k < min(__shfl_sync(0xFFFFFFFFu, cnt, b), FRAG_STAGE)) {
+                    const uint4 r0 = fw.rec[b][2 * k];
+                    const uint2 r1 = *reinterpret_cast<const uint2 *>(&fw.rec[b][2 * k + 1]);
+                    prefetch_l1(&pl.frag_u[r0.x + (r0.y & 0xFFu)]);
+                    prefetch_l1(&pl.frag_u[r0.x + (r0.y >> 8) - 1u]);
+                    prefetch_l1(&pl.span_shades[r1.y]);
+                    prefetch_l1(&pl.shades[r1.x].color);
+                }
+            }
+#endif
+            // ---- depth resolve, bin by bin: lane = pixel, the nearest fragment of every pixel is kept in registers ----
             while (mask) {
                 const int b = __ffs(mask) - 1;
                 mask &= mask - 1;
@@ -499,24 +632,37 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
                 uint32_t best_span = 0xFFFFFFFFu;
                 const int n = min(__shfl_sync(0xFFFFFFFFu, cnt, b), BIN_SLOTS);
                 const Chunk *slots = pl.bin_slots + (bin0 + b) * BIN_SLOTS;
+                const uint4 *rec = fw.rec[b];
                 for (int base = 0; base < n; base += FRAG_STAGE) {
                     const int m = min(FRAG_STAGE, n - base);
-                    __syncwarp();                                                   // the previous round's records are consumed
-                    if (lane < 2 * m) fw.rec[lane] = reinterpret_cast<const uint4 *>(slots + base)[lane];   // lane = half a record
-                    __syncwarp();
-                    // every lane loads for every piece (a lane outside the piece reads entry 0 instead): loads without a branch
-                    // in front of them can be issued RESOLVE_UNROLL at a time
-                    #pragma unroll RESOLVE_UNROLL
-                    for (int k = 0; k < m; k++) {
-                        const uint4 r0 = fw.rec[2 * k];                             // frag0, xs_xe, v0, v1
-                        const unsigned xs = r0.y & 0xFFu, wd = (r0.y >> 8) - xs;
-                        const bool in = (unsigned)lane - xs < wd;
-                        const float u = pl.frag_u[in ? r0.x + (uint32_t)lane : 0u]; // qpixel.ualpha, replayed by k_spans
-                        const float z = fadd(__uint_as_float(r0.z), fmul(__uint_as_float(r0.w), u));   // value(0), renderer.cpp:488
-                        if (in && z >= NEAR_Z) {                                    // renderer.cpp:489-492
-                            const uint2 r1 = *reinterpret_cast<const uint2 *>(&fw.rec[2 * k + 1]);     // slot, span
-                            const uint64_t key = ((uint64_t)__float_as_uint(z) << 32) | r1.x;
-                            if (key < best) { best = key; best_u = u; best_span = r1.y; }
+                    if (base) {                                                     // a bin with more than FRAG_STAGE pieces: the next round
+                        __syncwarp();
+                        if (lane < 2 * m) fw.rec[b][lane] = reinterpret_cast<const uint4 *>(slots + base)[lane];
+                        __syncwarp();
+                    }
+                    // groups of RESOLVE_UNROLL pieces whose fragment-stream loads are issued back to back, WITHOUT a remainder
+                    // loop: a bin holds ~3 pieces on average, and pieces taken one by one pay one L2 round trip each.  Every lane
+                    // loads for every piece of the group (a lane outside the piece, or a piece beyond the bin's last, reads
+                    // entry 0 instead), so no branch separates the loads.
+                    for (int k0 = 0; k0 < m; k0 += RESOLVE_UNROLL) {
+                        uint4 r0[RESOLVE_UNROLL]; float u[RESOLVE_UNROLL]; bool in[RESOLVE_UNROLL];
+                        #pragma unroll
+                        for (int j = 0; j < RESOLVE_UNROLL; j++) {
+                            r0[j] = rec[2 * min(k0 + j, m - 1)];                    // frag0, xs_xe, v0, v1
+                            const unsigned xs = r0[j].y & 0xFFu, wd = (r0[j].y >> 8) - xs;
+                            in[j] = (unsigned)lane - xs < wd && k0 + j < m;
+                        }
+                        #pragma unroll
+                        for (int j = 0; j < RESOLVE_UNROLL; j++)
+                            u[j] = pl.frag_u[in[j] ? r0[j].x + (uint32_t)lane : 0u];   // qpixel.ualpha, replayed by k_spans
+                        #pragma unroll
+                        for (int j = 0; j < RESOLVE_UNROLL; j++) {
+                            const float z = fadd(__uint_as_float(r0[j].z), fmul(__uint_as_float(r0[j].w), u[j]));   // value(0), renderer.cpp:488
+                            if (in[j] && z >= NEAR_Z) {                             // renderer.cpp:489-492
+                                const uint2 r1 = *reinterpret_cast<const uint2 *>(&rec[2 * (k0 + j) + 1]);         // slot, span
+                                const uint64_t key = ((uint64_t)__float_as_uint(z) << 32) | r1.x;
+                                if (key < best) { best = key; best_u = u[j]; best_span = r1.y; }
+                            }
                         }
                     }
                 }
@@ -536,15 +682,22 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
                 const int px = (b << 5) + lane;
                 const bool inside = px < px_left;
                 const bool hit = best_span != 0xFFFFFFFFu && inside;
+#ifdef FRAG_PROBE_TIMELINE
+                if (tl_first && __any_sync(0xFFFFFFFFu, best != KEY_INIT || true)) FRAG_TL(12 + (b & 1) * 2, global_ns());
+#endif
+                if (inside) drow[px] = __uint_as_float((uint32_t)(best >> 32));
                 // depth and colour of the bin at once: lane = pixel, the winner is shaded by its own lane (only the visible
                 // fragment of a pixel is ever shaded).  Resolve and shading alternate bin by bin, so the warps of an SM drift out
-                // of phase -- some wait for loads while others compute -- and nothing but the slot records passes through
-                // shared memory.  (Round 1 queued the winners of the whole 128-pixel stretch and shaded them in dense batches of
-                // 32: 10 % more lanes busy in the shader, paid for with three more passes over shared memory; measured equal.)
-                if (inside) drow[px] = __uint_as_float((uint32_t)(best >> 32));
+                // of phase -- some wait for loads while others compute.  (Measured alternatives: winners of the whole 128-pixel
+                // stretch queued and shaded in dense batches of 32 -- equal; all bins of the row resolved first, their winners
+                // parked in shared memory and the texels prefetched before any shading -- 10 % slower on the truck, 2x on
+                // BrainStem: 12 KB more shared memory per CTA takes it from the L1 the texels live in.)
                 uint32_t out = 0u;                                                  // background pixels of a used bin get 0
-                if (hit) out = shade_winner<LIGHT, TEX, FAST>(pl, s.texels, vp, fp, best_span, (uint32_t)best, best_u);
+                if (hit) out = shade_winner<LIGHT, TEX, FAST>(pl, s.texels, vp, fp, best_span, (uint32_t)best, best_u, g.k4b);
                 if (inside) crow[px] = out;
+#ifdef FRAG_PROBE_TIMELINE
+                if (tl_first && __any_sync(0xFFFFFFFFu, out != 0x12345u)) FRAG_TL(13 + (b & 1) * 2, global_ns());
+#endif
                 my_covered += __popc(__ballot_sync(0xFFFFFFFFu, hit));
             }
             __syncwarp();                                                   // fw is reused by the next item
@@ -552,6 +705,9 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
 
         if (threadIdx.x == 0) s_next[it] = gridDim.x + next_raw;
         __syncthreads();                                                    // every warp is done with item p; the next index is visible
+#ifdef FRAG_PROBE_TIMELINE
+        FRAG_TL(tl_slot, (global_ns() << 1) | (p >= n_busy ? 1ull : 0ull)); tl_slot++;
+#endif
         p = s_next[it];
     }
     if (count_covered && lane == 0 && my_covered) atomicAdd(&cn->n_covered, my_covered);
@@ -1137,6 +1293,7 @@ static FragGeom make_geom(const ViewParams &vp, bool skip_bg, bool dof, int out_
     g.ndx = (vp.vw + DOF_OW - 1) / DOF_OW;
     g.n_dof = dof ? g.ndx * ((vp.band1 - vp.band0 + DOF_OH - 1) / DOF_OH) : 0;
     g.out0 = out_row0; g.out1 = out_row1; g.dof_pitch = dof_pitch;
+    g.k4b = 0x4B000000u;
     return g;
 }
 
@@ -1235,6 +1392,55 @@ __global__ void k_selftest_division(uint64_t n_pairs, uint32_t seed, unsigned lo
     for (int o = 16; o; o >>= 1) { bad += __shfl_down_sync(0xFFFFFFFFu, bad, o); fast += __shfl_down_sync(0xFFFFFFFFu, fast, o); }
     if ((threadIdx.x & 31) == 0) { if (bad) atomicAdd(mismatches, bad); atomicAdd(fast_path, fast); }
 }
+// self-test of the fast kernels' bilinear filter against the exact one (swegl_b200_selftest_filter): random texels, texture
+// coordinates drawn over every binade below 2^21 with extra weight on integers, halves and their float neighbours
+__global__ void k_selftest_filter(uint64_t n, uint32_t seed, unsigned long long *mismatches, uint32_t k4b)
+{
+    unsigned long long bad = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t h0 = mix32((uint32_t)i ^ seed), h1 = mix32(h0 + (uint32_t)(i >> 32) + 0x9e3779b9u), h2 = mix32(h1 ^ 0x85ebca6bu), h3 = mix32(h2 + 0xc2b2ae35u);
+        TexFetch f;
+        f.p00 = mix32(h3 ^ 1u); f.p10 = mix32(h3 ^ 2u); f.p01 = mix32(h3 ^ 3u); f.p11 = mix32(h3 ^ 4u);
+        if (h3 & 1u) { f.p00 |= 0xFF000000u; f.p10 |= 0xFF000000u; f.p01 |= 0xFF000000u; f.p11 |= 0xFF000000u; }    // opaque texels: the alpha shortcut
+        if ((h3 & 6u) == 2u) f.p00 = f.p10 = f.p01 = f.p11 = 0xFFFFFFFFu;                                           // saturated channels
+        float c[2];
+        for (int k = 0; k < 2; k++) {
+            const uint32_t h = k ? h1 : h0, mode = (h2 >> (4 * k)) & 15u;
+            const int e = (int)(h >> 8) % 23 - 2;                            // binade 2^-2 .. 2^20
+            float t = ldexpf(1.0f + (float)(h & 0x7FFFFFu) * (1.0f / 8388608.0f), e);
+            if (mode == 1u) t = floorf(t);
+            if (mode == 2u) t = floorf(t) + 0.5f;
+            if (mode == 3u) t = __uint_as_float(__float_as_uint(floorf(t) + 0.5f) - 1u);
+            if (mode == 4u) t = __uint_as_float(__float_as_uint(floorf(t) + 0.5f) + 1u);
+            if (mode == 5u) t = __uint_as_float(__float_as_uint(floorf(t)) - 1u);
+            if (mode == 6u) t = (float)(h & 0xFFFu) * (1.0f / 4096.0f);      // [0, 1)
+            if (mode == 7u) t = -t;
+            if (mode == 8u) t = 0.0f;
+            c[k] = t;
+        }
+        f.fu = c[0]; f.fv = c[1];
+        if (!(fabsf(f.fu) < 2097152.0f && fabsf(f.fv) < 2097152.0f)) continue;
+        bad += tex_filter<SWEGL_B200_TEX_BILINEAR>(f) != tex_filter_bilinear_fast(f, k4b) ? 1u : 0u;
+        // the index arithmetic of the fetch: plain truncation == the guarded f2i inside the range
+        bad += (__float2int_rz(fsub(f.fu, 0.5f)) != f2i(fsub(f.fu, 0.5f)) || __float2int_rz(fsub(f.fv, 0.5f)) != f2i(fsub(f.fv, 0.5f))) ? 1u : 0u;
+    }
+    for (int o = 16; o; o >>= 1) bad += __shfl_down_sync(0xFFFFFFFFu, bad, o);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, bad);
+}
+#ifdef FRAG_PROBE_TIMELINE
+extern "C" int swegl_b200_probe_timeline(unsigned long long *out, int clear)
+{
+    cudaDeviceSynchronize();
+    if (out) cudaMemcpyFromSymbol(out, g_frag_timeline, sizeof(g_frag_timeline));
+    if (clear) { static unsigned long long z[2048 * 16]; cudaMemcpyToSymbol(g_frag_timeline, z, sizeof(z)); }
+    return 0;
+}
+#endif
+void launch_selftest_filter(uint64_t n, uint32_t seed, unsigned long long *d_out, cudaStream_t st)
+{
+    k_selftest_filter<<<148 * 8, 256, 0, st>>>(n, seed, d_out, 0x4B000000u);
+}
+
 void launch_selftest_division(uint64_t n_pairs, uint32_t seed, unsigned long long *d_out2, cudaStream_t st)
 {
     k_selftest_division<<<148 * 8, 256, 0, st>>>(n_pairs, seed, d_out2, d_out2 + 1);

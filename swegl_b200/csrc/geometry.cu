@@ -608,9 +608,12 @@ SB_DEV void walk_segment(const Pools &pl, const ViewParams &vp, const SH &sh, in
             if (!dup) { tl[j] = t; old[j] = atomicExch(&pl.tile_stamp[t], vp.stamp); }
         }
     }
+    // (the list entry is the tile's row and column, tile row << 16 | tile column: its consumer, one warp per tile row, would
+    // otherwise divide by the tiles-per-row count)
     #pragma unroll
     for (int j = 0; j < (int)SPAN_SEG; j++)
-        if (tl[j] != 0xFFFFFFFFu && old[j] != vp.stamp) pl.busy_list[atomicAdd(&pl.counters->n_busy, 1u)] = tl[j];
+        if (tl[j] != 0xFFFFFFFFu && old[j] != vp.stamp)
+            pl.busy_list[atomicAdd(&pl.counters->n_busy, 1u)] = ((uint32_t)((row_rel - (vp.band0 - vp.vy)) / FRAG_ROWS) << 16) | (uint32_t)((b0 + j) / FRAG_STRETCH);
 }
 
 // shared state of one CTA pass over SPAN_ROWS scanline records

@@ -219,6 +219,12 @@ class Renderer:
         self._check(self.lib.swegl_b200_selftest_division(self.ctx, C.c_uint64(int(n_pairs)), C.c_uint32(int(seed)), out))
         return int(out[0]), int(out[1])
 
+    def selftest_filter(self, n_samples, seed=1):
+        """-> samples on which the fast kernels' bilinear filter differs from the exact one (must be 0)"""
+        out = (C.c_uint64 * 1)()
+        self._check(self.lib.swegl_b200_selftest_filter(self.ctx, C.c_uint64(int(n_samples)), C.c_uint32(int(seed)), out))
+        return int(out[0])
+
     def device_buffers(self):
         s, d = C.c_void_p(), C.c_void_p()
         self._check(self.lib.swegl_b200_device_buffers(self.ctx, C.byref(s), C.byref(d)))

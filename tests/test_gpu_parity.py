@@ -568,6 +568,12 @@ def test_shared_divisor_division_is_correctly_rounded(renderer):
     assert fast > (1 << 29)                             # the fast path really is what was compared
 
 
+def test_fast_bilinear_filter_equals_the_exact_one(renderer):
+    """tex_filter_bilinear_fast (the fast kernels' filter: no per-operation range checks, rounding through the adder, alpha
+    shortcut) == tex_filter<BILINEAR>, bit for bit, over 2^28 generated samples below the 2^21 coordinate guard"""
+    assert renderer.selftest_filter(1 << 28, seed=20261018) == 0
+
+
 # ---- partial read-back of asynchronous frames (include/swegl_b200.h: swegl_b200_render_viewport_async) ----
 @pytest.mark.parametrize("name", ["truck_1080", "truck_4k_dof"])
 def test_partial_readback_equals_full_copy(renderer, name):
