@@ -375,6 +375,46 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
 
 
+def nvlink_kib(local_rank):
+    """(tx, rx) payload KiB this GPU has moved over all its NVLinks so far (NVML field values
+    NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX / _RX, summed over the links), or None where NVML does not report them"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        out = []
+        for fid in (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX):
+            total, seen = 0, False
+            vals = pynvml.nvmlDeviceGetFieldValues(h, [(fid, 0xFFFFFFFF)])        # scope UINT_MAX: all links
+            v = vals[0]
+            if v.nvmlReturn == pynvml.NVML_SUCCESS:
+                total, seen = int(v.value.ullVal), True
+            else:
+                for link in range(18):
+                    v = pynvml.nvmlDeviceGetFieldValues(h, [(fid, link)])[0]
+                    if v.nvmlReturn == pynvml.NVML_SUCCESS:
+                        total += int(v.value.ullVal); seen = True
+            if not seen:
+                return None
+            out.append(total)
+        return tuple(out)
+    except Exception:
+        return None
+
+
+def nvlink_delta(torch, dist, world, local_rank, before, frames):
+    """per-frame NVLink payload of every rank between `before` (nvlink_kib) and now: {"tx_kib_per_frame": [...], "rx_...": [...]}"""
+    after = nvlink_kib(local_rank)
+    ok = before is not None and after is not None
+    t = torch.tensor([(after[0] - before[0]) / frames if ok else -1.0, (after[1] - before[1]) / frames if ok else -1.0], device="cuda", dtype=torch.float64)
+    allt = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allt, t)
+    if any(float(a[0]) < 0 for a in allt):
+        return None
+    return {"tx_kib_per_frame": [round(float(a[0]), 1) for a in allt], "rx_kib_per_frame": [round(float(a[1]), 1) for a in allt],
+            "source": "NVML NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX/RX, all links, sampled around warm-up + timed frames"}
+
+
 def screen_fnv_ok(r, torch, dist, world, rank, name, render_one):
     """The assembled frame on rank 0 against the golden FNV-1a-64 of the reference's frame (tests/golden/MANIFEST.json).
     The manifest pins the bit-exact frame, the timed frames use the +-1 LSB shading: every rank renders the frame once
@@ -573,18 +613,25 @@ def sharded_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
         r.begin_frame(scene, nodes)
         r.render_device(state["desc"], stats=True)
         dist.barrier()
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_timed = max(warmup, 3) + steps
+    nv0 = nvlink_kib(local_rank) if world > 1 else None
     ms_gather = timed()                                 # bands sent to rank 0 after rendering (NCCL send/recv)
+    nvl_gather = nvlink_delta(torch, dist, world, local_rank, nv0, n_timed) if world > 1 else None
     if rank == 0:
         full.zero_()
     gather_ok = screen_fnv_ok(r, torch, dist, world, rank, name, one)
     ms_peer, peer_ok, ms_sync, sync_ok, sync_info = None, None, None, None, None
+    nvl_peer, nvl_sync = None, None
     if world > 1:
         # the fused form: every rank's last kernel stores its band into rank 0's screen over NVLink (CUDA IPC mapping)
         sharding.share_screen(r, dist, dst=0, device="cuda")
         state["peer"] = True
         if rank == 0:
             full.zero_()
+        nv0 = nvlink_kib(local_rank)
         ms_peer = timed()
+        nvl_peer = nvlink_delta(torch, dist, world, local_rank, nv0, n_timed)
         if rank == 0:
             full.zero_()
         peer_ok = screen_fnv_ok(r, torch, dist, world, rank, name, one)
@@ -648,7 +695,9 @@ def sharded_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
             return float(t.item())
         if rank == 0:
             full.zero_()
+        nv0 = nvlink_kib(local_rank)
         ms_sync = timed_sync()
+        nvl_sync = nvlink_delta(torch, dist, world, local_rank, nv0, n_timed)
         errs = torch.tensor([r.frame_sync_errors()], device="cuda", dtype=torch.int64)
         dist.all_reduce(errs)
         # the reference's frame?  (the bands moved, the frame must not; rank 0 does not clear its own band: zero it first)
@@ -676,6 +725,7 @@ def sharded_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
             "ms_per_frame_peer_write": ms_peer, "ms_per_frame_peer_protocol": ms_sync, "peer_protocol": sync_info,
             "frame_fnv_ok": (all(checks) if checks else None), "frame_fnv_ok_gather": gather_ok, "frame_fnv_ok_peer_write": peer_ok,
             "frame_fnv_ok_peer_protocol": sync_ok,
+            "nvlink": ({"nccl_gather": nvl_gather, "peer_write": nvl_peer, "peer_protocol": nvl_sync} if world > 1 else None),
             "n_gpus": world,
             "partition": "row bands, sort-first, scene replicated, band culling (DESIGN.md 6: nccl_gather / peer_write / peer_protocol)" if world > 1 else "single GPU",
             "bands": state["bands"], "rank0_band_covered_pixels": int(st.n_covered), "scaling": "strong"}

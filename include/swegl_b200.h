@@ -341,7 +341,7 @@ int  swegl_b200_cull_counts(swegl_b200_ctx *ctx, uint32_t counts[6]);
  * none (src/misc/image.cpp:93-258: read_png_file, read_jpeg_file; called from src/data/gltf.cpp:77-111).  The texels are
  * the ones libpng / libjpeg(-turbo) produce, bit for bit (JPEG: islow inverse DCT, fancy upsampling, jdcolor tables),
  * so a texture decoded here and one decoded by the reference sample identically.  PNG: all colour types and bit depths,
- * tRNS, no Adam7.  JPEG: baseline / extended / progressive Huffman, 8 bit, 1 or 3 components, sampling 1x1 2x1 2x2,
+ * tRNS, Adam7 interlacing.  JPEG: baseline / extended / progressive Huffman, 8 bit, 1 or 3 components, sampling 1x1 2x1 2x2,
  * restart intervals.  *texels_bgra is malloc'ed; release it with swegl_b200_image_free.  Errors: SWEGL_B200_ERR_ARG,
  * SWEGL_B200_ERR_UNSUPPORTED (malformed or unsupported file; swegl_b200_image_error() says which, per thread). */
 int  swegl_b200_decode_image(const void *data, size_t size, uint32_t **texels_bgra, int32_t *width, int32_t *height);

@@ -63,68 +63,89 @@ void decode_png(const uint8_t *d, size_t n, std::vector<uint32_t> &out, int &w, 
         pos += 12 + (size_t)len;
     }
     if (!have_ihdr || w <= 0 || h <= 0 || w > 32768 || h > 32768) fail("png: no usable IHDR");
-    if (interlace) fail("png: Adam7 interlacing is not supported");
+    if (interlace > 1) fail("png: unknown interlace method");
     const int channels = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
     if (!channels || !(depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)) fail("png: bad colour type / bit depth");
     if ((ctype == 2 || ctype == 4 || ctype == 6) && depth < 8) fail("png: bad bit depth for colour type");
     if (ctype == 3 && (depth == 16 || plte.empty())) fail("png: bad palette image");
     const int bpp_bits = channels * depth, bpp = (bpp_bits + 7) / 8;       // filter unit in bytes
-    const size_t stride = ((size_t)w * bpp_bits + 7) / 8;
-    std::vector<uint8_t> raw((stride + 1) * (size_t)h);
+    // the image as one pass, or as the seven reduced images of Adam7 (PNG spec 8.2; libpng's png_read_image de-interlaces
+    // them transparently, src/misc/image.cpp:93-170): pass = every dx-th column from x0 of every dy-th row from y0
+    struct Pass { int x0, y0, dx, dy, pw, ph; size_t stride, offset; };
+    static const int A7[7][4] = { {0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2} };
+    std::vector<Pass> passes;
+    size_t raw_size = 0;
+    for (int k = 0; k < (interlace ? 7 : 1); k++) {
+        Pass ps;
+        ps.x0 = interlace ? A7[k][0] : 0; ps.y0 = interlace ? A7[k][1] : 0; ps.dx = interlace ? A7[k][2] : 1; ps.dy = interlace ? A7[k][3] : 1;
+        ps.pw = (w - ps.x0 + ps.dx - 1) / ps.dx; ps.ph = (h - ps.y0 + ps.dy - 1) / ps.dy;
+        if (ps.pw <= 0 || ps.ph <= 0) continue;                             // an empty pass has no bytes at all, not even filter bytes
+        ps.stride = ((size_t)ps.pw * bpp_bits + 7) / 8;
+        ps.offset = raw_size;
+        raw_size += (ps.stride + 1) * (size_t)ps.ph;
+        passes.push_back(ps);
+    }
+    // deflate cannot expand by more than ~1032:1: an IHDR that promises more than the IDAT bytes can hold is refused before
+    // anything is allocated (a few-byte file must not make the decoder allocate gigabytes)
+    if (raw_size > (size_t)1040 * idat.size() + 65536) fail("png: image data too short for the declared size");
+    std::vector<uint8_t> raw(raw_size);
     uLongf raw_len = (uLongf)raw.size();
     if (uncompress(raw.data(), &raw_len, idat.data(), (uLong)idat.size()) != Z_OK || raw_len != raw.size()) fail("png: inflate failed");
-    // unfilter in place (PNG spec 9.2), prior row = zeros for the first row
-    std::vector<uint8_t> zero(stride, 0);
-    for (int y = 0; y < h; y++) {
-        uint8_t *row = raw.data() + (stride + 1) * (size_t)y + 1;
-        const uint8_t *up = y ? row - (stride + 1) : zero.data();
-        const int f = row[-1];
-        for (size_t i = 0; i < stride; i++) {
-            const int a = i >= (size_t)bpp ? row[i - bpp] : 0, b = up[i], c = i >= (size_t)bpp ? up[i - bpp] : 0;
-            int add;
-            switch (f) {
-                case 0: add = 0; break;
-                case 1: add = a; break;
-                case 2: add = b; break;
-                case 3: add = (a + b) >> 1; break;
-                case 4: add = paeth(a, b, c); break;
-                default: fail("png: bad filter type");
-            }
-            row[i] = (uint8_t)(row[i] + add);
-        }
-    }
     out.resize((size_t)w * h);
     // tRNS for gray / RGB: one colour key (16-bit samples in the chunk), compared BEFORE 16 -> 8 stripping as libpng does
     int key[3] = { -1, -1, -1 };
     if (have_trns && ctype == 0 && trns.size() >= 2) key[0] = (int)be16(trns.data());
     if (have_trns && ctype == 2 && trns.size() >= 6) for (int c = 0; c < 3; c++) key[c] = (int)be16(trns.data() + 2 * c);
-    for (int y = 0; y < h; y++) {
-        const uint8_t *row = raw.data() + (stride + 1) * (size_t)y + 1;
-        for (int x = 0; x < w; x++) {
-            int s[4] = { 0, 0, 0, 0 }, s8[4];
-            for (int c = 0; c < channels; c++) {
-                if (depth == 8) s[c] = row[(size_t)x * channels + c];
-                else if (depth == 16) s[c] = (int)be16(row + 2 * ((size_t)x * channels + c));
-                else { const size_t bit = (size_t)x * depth; s[c] = (row[bit >> 3] >> (8 - depth - (bit & 7))) & ((1 << depth) - 1); }
+    for (const Pass &ps : passes) {
+        const size_t stride = ps.stride;
+        // unfilter in place (PNG spec 9.2), prior row = zeros for the first row of the pass
+        std::vector<uint8_t> zero(stride, 0);
+        for (int y = 0; y < ps.ph; y++) {
+            uint8_t *row = raw.data() + ps.offset + (stride + 1) * (size_t)y + 1;
+            const uint8_t *up = y ? row - (stride + 1) : zero.data();
+            const int f = row[-1];
+            for (size_t i = 0; i < stride; i++) {
+                const int a = i >= (size_t)bpp ? row[i - bpp] : 0, b = up[i], c = i >= (size_t)bpp ? up[i - bpp] : 0;
+                int add;
+                switch (f) {
+                    case 0: add = 0; break;
+                    case 1: add = a; break;
+                    case 2: add = b; break;
+                    case 3: add = (a + b) >> 1; break;
+                    case 4: add = paeth(a, b, c); break;
+                    default: fail("png: bad filter type");
+                }
+                row[i] = (uint8_t)(row[i] + add);
             }
-            for (int c = 0; c < channels; c++)
-                s8[c] = depth == 16 ? s[c] >> 8 : depth == 8 ? s[c] : s[c] * (255 / ((1 << depth) - 1));   // strip_16 / expand 1,2,4
-            int r, g, b, a = 255;
-            if (ctype == 3) {
-                const size_t i = (size_t)s[0];
-                if (3 * i + 2 >= plte.size()) fail("png: palette index out of range");
-                r = plte[3 * i]; g = plte[3 * i + 1]; b = plte[3 * i + 2];
-                if (have_trns && i < trns.size()) a = trns[i];
-            } else if (ctype == 0 || ctype == 4) {
-                r = g = b = s8[0];
-                if (ctype == 4) a = s8[1];
-                else if (have_trns && s[0] == key[0]) a = 0;
-            } else {
-                r = s8[0]; g = s8[1]; b = s8[2];
-                if (ctype == 6) a = s8[3];
-                else if (have_trns && s[0] == key[0] && s[1] == key[1] && s[2] == key[2]) a = 0;
+        }
+        for (int y = 0; y < ps.ph; y++) {
+            const uint8_t *row = raw.data() + ps.offset + (stride + 1) * (size_t)y + 1;
+            for (int x = 0; x < ps.pw; x++) {
+                int s[4] = { 0, 0, 0, 0 }, s8[4];
+                for (int c = 0; c < channels; c++) {
+                    if (depth == 8) s[c] = row[(size_t)x * channels + c];
+                    else if (depth == 16) s[c] = (int)be16(row + 2 * ((size_t)x * channels + c));
+                    else { const size_t bit = (size_t)x * depth; s[c] = (row[bit >> 3] >> (8 - depth - (bit & 7))) & ((1 << depth) - 1); }
+                }
+                for (int c = 0; c < channels; c++)
+                    s8[c] = depth == 16 ? s[c] >> 8 : depth == 8 ? s[c] : s[c] * (255 / ((1 << depth) - 1));   // strip_16 / expand 1,2,4
+                int r, g, b, a = 255;
+                if (ctype == 3) {
+                    const size_t i = (size_t)s[0];
+                    if (3 * i + 2 >= plte.size()) fail("png: palette index out of range");
+                    r = plte[3 * i]; g = plte[3 * i + 1]; b = plte[3 * i + 2];
+                    if (have_trns && i < trns.size()) a = trns[i];
+                } else if (ctype == 0 || ctype == 4) {
+                    r = g = b = s8[0];
+                    if (ctype == 4) a = s8[1];
+                    else if (have_trns && s[0] == key[0]) a = 0;
+                } else {
+                    r = s8[0]; g = s8[1]; b = s8[2];
+                    if (ctype == 6) a = s8[3];
+                    else if (have_trns && s[0] == key[0] && s[1] == key[1] && s[2] == key[2]) a = 0;
+                }
+                out[(size_t)(ps.y0 + y * ps.dy) * w + (ps.x0 + x * ps.dx)] = pack_bgra(r, g, b, a);
             }
-            out[(size_t)y * w + x] = pack_bgra(r, g, b, a);
         }
     }
 }

@@ -83,3 +83,70 @@ def test_truncated_files_do_not_crash():
                 decode_image(data[:cut])
             except ValueError:
                 pass
+
+
+def _png(w, h, ctype, depth, samples, interlace, plte=None):
+    """a PNG file from `samples` (h, w, channels) written by hand (filter type 0 everywhere), one pass or Adam7 -- PIL cannot
+    write interlaced files"""
+    import struct
+    import zlib
+
+    def chunk(ty, body):
+        return struct.pack(">I", len(body)) + ty + body + struct.pack(">I", zlib.crc32(ty + body) & 0xFFFFFFFF)
+
+    def pack_row(row):                       # row: (pw, channels) integer samples
+        flat = row.reshape(-1)
+        if depth == 8:
+            return bytes(flat.astype(np.uint8))
+        if depth == 16:
+            return flat.astype(">u2").tobytes()
+        bits = "".join(format(int(v), f"0{depth}b") for v in flat)
+        bits += "0" * (-len(bits) % 8)
+        return bytes(int(bits[i:i + 8], 2) for i in range(0, len(bits), 8))
+
+    passes = [(0, 0, 1, 1)] if not interlace else [(0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)]
+    raw = b""
+    for x0, y0, dx, dy in passes:
+        sub = samples[y0::dy, x0::dx]
+        if sub.shape[0] == 0 or sub.shape[1] == 0:
+            continue
+        for row in sub:
+            raw += b"\0" + pack_row(row)
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 1 if interlace else 0))
+    if plte is not None:
+        out += chunk(b"PLTE", bytes(plte))
+    return out + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (2, 3), (5, 3), (8, 8), (9, 7), (37, 21), (64, 33)])
+@pytest.mark.parametrize("ctype,depth", [(6, 8), (2, 8), (2, 16), (0, 1), (0, 4), (4, 8), (3, 2), (3, 8)])
+def test_adam7_interlaced_png(w, h, ctype, depth):
+    """Adam7 (PNG spec 8.2): the seven reduced images, each with its own scanlines and filter bytes, decode to the same
+    texels as the one-pass file of the same samples (libpng's png_read_image de-interlaces transparently, image.cpp:93-170);
+    sizes below 8 leave some passes empty"""
+    rng = np.random.default_rng(w * 1000 + h * 10 + ctype + depth)
+    channels = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}[ctype]
+    plte = list(rng.integers(0, 256, 3 * (1 << min(depth, 8)))) if ctype == 3 else None
+    samples = rng.integers(0, 1 << depth, (h, w, channels))
+    a = decode_image(_png(w, h, ctype, depth, samples, False, plte))
+    b = decode_image(_png(w, h, ctype, depth, samples, True, plte))
+    assert a.shape == (h, w) and (a == b).all()
+    pil = pytest.importorskip("PIL.Image")
+    if depth != 16:                                   # (PIL's 16 -> 8 conversion is not libpng's strip_16)
+        from swegl_b200.scene import decode_image_bgra
+        assert (b == decode_image_bgra(_png(w, h, ctype, depth, samples, True, plte))).all()
+
+
+def test_png_header_that_promises_more_than_the_data_holds_is_refused_early():
+    """a few-byte file with a 32768 x 32768 RGBA16 header must fail before the decoder allocates the 8.6 GB it asks for"""
+    import resource
+    import struct
+    import zlib
+
+    def chunk(ty, body):
+        return struct.pack(">I", len(body)) + ty + body + struct.pack(">I", zlib.crc32(ty + body) & 0xFFFFFFFF)
+    data = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 32768, 32768, 16, 6, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(b"\0" * 64)) + chunk(b"IEND", b"")
+    before = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss
+    with pytest.raises(ValueError):
+        decode_image(data)
+    assert resource.getrusage(resource.RUSAGE_SELF).ru_maxrss - before < 512 * 1024      # KiB: nowhere near the declared size
