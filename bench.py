@@ -395,10 +395,12 @@ def nvlink_kib(local_rank):
                     if v.nvmlReturn == pynvml.NVML_SUCCESS:
                         total += int(v.value.ullVal); seen = True
             if not seen:
+                print(f"[bench] NVLink counters: field {fid} not reported (nvmlReturn {vals[0].nvmlReturn})", file=sys.stderr)
                 return None
             out.append(total)
         return tuple(out)
-    except Exception:
+    except Exception as e:
+        print(f"[bench] NVLink counters unavailable: {type(e).__name__}: {e}", file=sys.stderr)
         return None
 
 
@@ -714,6 +716,19 @@ def sharded_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
         state["sync"] = False
         dist.barrier()
     st = r.render_device(state["desc"], stats=True)
+    # what the peer-memory variants put on NVLink by construction (rank 0's own band stays local): peer_write stores every
+    # row of a band, background included; under the protocol only the colour of the tiles something was drawn into travels
+    peer_bytes = None
+    if world > 1:
+        t = torch.tensor([int(st.n_busy_tiles)], device="cuda", dtype=torch.int64)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        busy = [int(a.item()) for a in allt]
+        bands_now = state["bands"]
+        peer_bytes = {"busy_tiles_per_rank": busy,
+                      "peer_write_into_rank0": sum((b[1] - b[0]) * vp.w * 4 for b in bands_now[1:]),
+                      "peer_protocol_into_rank0": sum(n * 8 * 128 * 4 for n in busy[1:]),
+                      "how": "algorithmic: rows x width x 4 B of the other ranks' bands / 4 KiB of colour per busy tile of theirs"}
     cands = [m for m in (ms_gather, ms_peer, ms_sync) if m is not None]
     best = min(cands)
     checks = [c for c in (gather_ok, peer_ok, sync_ok) if c is not None]
@@ -725,7 +740,9 @@ def sharded_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
             "ms_per_frame_peer_write": ms_peer, "ms_per_frame_peer_protocol": ms_sync, "peer_protocol": sync_info,
             "frame_fnv_ok": (all(checks) if checks else None), "frame_fnv_ok_gather": gather_ok, "frame_fnv_ok_peer_write": peer_ok,
             "frame_fnv_ok_peer_protocol": sync_ok,
-            "nvlink": ({"nccl_gather": nvl_gather, "peer_write": nvl_peer, "peer_protocol": nvl_sync} if world > 1 else None),
+            "nvlink": ({"nccl_gather": nvl_gather, "peer_write": nvl_peer, "peer_protocol": nvl_sync,
+                        "note": "hardware counters (NVML NVLINK_THROUGHPUT_DATA_TX/RX, nvidia-smi nvlink -gt d); None = not exposed on this box"} if world > 1 else None),
+            "peer_bytes_per_frame": peer_bytes,
             "n_gpus": world,
             "partition": "row bands, sort-first, scene replicated, band culling (DESIGN.md 6: nccl_gather / peer_write / peer_protocol)" if world > 1 else "single GPU",
             "bands": state["bands"], "rank0_band_covered_pixels": int(st.n_covered), "scaling": "strong"}

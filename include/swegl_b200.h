@@ -168,6 +168,9 @@ typedef struct swegl_b200_stats {
     uint32_t pool_grows;           /* times the span/chunk pools had to be enlarged        */
     float    ms_vertex, ms_setup, ms_raster, ms_fragment, ms_post, ms_total;
                                    /* CUDA-event times, only when timing is enabled        */
+    uint32_t n_busy_tiles;         /* screen tiles of 8 rows x 128 pixels something was drawn into: with a colour target
+                                      (multi-GPU output over peer memory) and the frame protocol, 4 KiB of finished
+                                      colour per busy tile is what crosses NVLink                                      */
 } swegl_b200_stats;
 
 typedef struct swegl_b200_ctx swegl_b200_ctx;

@@ -75,7 +75,7 @@ class Stats(C.Structure):
     _fields_ = [("n_setup_triangles", C.c_uint32), ("n_spans", C.c_uint32), ("n_chunks", C.c_uint32),
                 ("n_covered", C.c_uint32), ("n_launches", C.c_uint32), ("pool_grows", C.c_uint32),
                 ("ms_vertex", C.c_float), ("ms_setup", C.c_float), ("ms_raster", C.c_float),
-                ("ms_fragment", C.c_float), ("ms_post", C.c_float), ("ms_total", C.c_float)]
+                ("ms_fragment", C.c_float), ("ms_post", C.c_float), ("ms_total", C.c_float), ("n_busy_tiles", C.c_uint32)]
 
 
 # every symbol include/swegl_b200.h declares: (name, restype, argtypes)

@@ -1060,6 +1060,7 @@ static int render_common(swegl_b200_ctx *ctx, const swegl_b200_viewport_desc *v,
         const Counters &c = *ctx->h_counters;
         stats->n_setup_triangles = c.n_slots; stats->n_spans = c.n_rows; stats->n_chunks = c.n_chunks;
         stats->n_covered = c.n_covered; stats->n_launches = launches; stats->pool_grows = grows;
+        stats->n_busy_tiles = c.n_busy;
 #ifdef FRAG_PROBE_MAXLIST
         stats->n_launches = c.pad; stats->pool_grows = c.dof_queue;     // probe build: bins with more than FRAG_LIST_CAP / 32 pieces
 #endif
