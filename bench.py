@@ -53,14 +53,22 @@ def golden_fnv(name):
         return None
 
 
-def workload_config(name, cfg, scene, screen, extra=None):
-    c = {"workload": name, "description": cfg["desc"], "resolution": f"{screen[0]}x{screen[1]}",
-         "triangles": scene.n_triangles(), "vertices": scene.n_vertices,
-         "shader": "phong+bilinear", "data": "bundled glTF scene pack" if not name.startswith("sphere") else "synthetic make_sphere + seeded LCG texture",
-         "l2": "256 MiB memset between timed frames, outside the CUDA events"}
-    if extra:
-        c.update(extra)
-    return c
+def workload_config(name, cfg, scene, screen, n_gpus=1, depth=4):
+    """`config` of the JSON line: the workload and how the swegl_b200 arm measures `value` on it.  BOTH arms print exactly
+    this dict for the same command line (the driver compares them); what is specific to an arm's own run -- the reference
+    arm's processes, the host's NUMA binding -- lives in top-level keys of its line."""
+    return {"workload": name, "description": cfg["desc"], "resolution": f"{screen[0]}x{screen[1]}",
+            "triangles": scene.n_triangles(), "vertices": scene.n_vertices,
+            "shader": "phong+bilinear", "data": "bundled glTF scene pack" if not name.startswith("sphere") else "synthetic make_sphere + seeded LCG texture",
+            "step": f"one batch of {FRAMES_PER_STEP} independent frames", "frames_per_step": FRAMES_PER_STEP,
+            "parallelism": "single GPU" if n_gpus == 1 else
+                           f"frame-parallel x{n_gpus}: scene replicated, frame i on GPU i mod N, no collective",
+            "frames_in_flight_per_gpu": depth,
+            "l2": (f"value: {depth} contexts per GPU render the batches of independent frames round robin; "
+                   "their frame buffers and pools (about 140 MB each at 4K) rotate, so the working set exceeds "
+                   "the 126 MB L2 and no flush is inserted; one_frame_at_a_time: 256 MiB memset between timed "
+                   "frames, outside the CUDA events") if depth > 1 else
+                  "256 MiB memset between timed frames, outside the CUDA events"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -184,7 +192,9 @@ def run_reference_arm(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
             "warmup": args.warmup, "ms_per_step": 1e3 * procs / value, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic" if name.startswith("sphere") else "bundled scene",
-            "config": workload_config(name, cfg, scene, screen),
+            "config": workload_config(name, cfg, scene, screen, n_gpus=max(1, args.gpus), depth=args.pipeline_depth),
+            "arm": "the unmodified reference on the host cores (config.step / parallelism / l2 describe the swegl_b200 arm of the same command; "
+                   "here a step is one frame per renderer process, no GPU involved)",
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind,
                              "sample": f"{procs} independent single-threaded renderer processes, 1 frame each per step, "
                                        f"{len(vals)} steps (swegl has one raster thread, so frame-parallel processes are all the "
@@ -914,18 +924,8 @@ def main():
     line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * main_res["pipe_secs"] / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic" if args.workload.startswith("sphere") else "bundled scene",
-            "config": workload_config(args.workload, cfg, scene, screen,
-                                      {"step": f"one batch of {FRAMES_PER_STEP} independent frames", "frames_per_step": FRAMES_PER_STEP,
-                                       "parallelism": "single GPU" if world == 1 else
-                                       f"frame-parallel x{world}: scene replicated, frame i on GPU i mod N, no collective",
-                                       "frames_in_flight_per_gpu": main_res["depth"],
-                                       "host_numa_binding": (f"rank 0 on node {numa_node}, every rank bound to its GPU's node"
-                                                             if numa_node is not None else "none"),
-                                       "l2": (f"value: {main_res['depth']} contexts per GPU render the batches of independent frames round robin; "
-                                              "their frame buffers and pools (about 140 MB each at 4K) rotate, so the working set exceeds "
-                                              "the 126 MB L2 and no flush is inserted; one_frame_at_a_time: 256 MiB memset between timed "
-                                              "frames, outside the CUDA events") if main_res["depth"] > 1 else
-                                             "256 MiB memset between timed frames, outside the CUDA events"}),
+            "config": workload_config(args.workload, cfg, scene, screen, n_gpus=world, depth=main_res["depth"]),
+            "host_numa_binding": (f"rank 0 on node {numa_node}, every rank bound to its GPU's node" if numa_node is not None else "none"),
             "frames_timed": frames * world, "timed_region_s": main_res["pipe_secs"],
             "batches": {"n": len(batch_fps), "frames_each": FRAMES_PER_STEP, "fps_median": statistics.median(batch_fps),
                         "fps_min": batch_fps[0], "fps_max": batch_fps[-1]},
