@@ -374,6 +374,9 @@ static int ensure_pools(swegl_b200_ctx *ctx, uint32_t rows_cap, uint32_t chunks_
     }
     if (frags_cap > ctx->pools.frags_cap) {
         CK(dalloc(ctx->pools.frag_u, (size_t)frags_cap));
+        // entry 0 is what k_fragments' lanes OUTSIDE a piece load (and ignore) instead of branching around the load; the
+        // stream's alignment rule may leave it unwritten (compute-sanitizer initcheck)
+        CK(cudaMemset(ctx->pools.frag_u, 0, 64));
         ctx->pools.frags_cap = frags_cap;
     }
     if (rows_cap > ctx->pools.rows_cap) {

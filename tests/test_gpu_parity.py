@@ -278,6 +278,59 @@ def test_pipelined_readback_matches_blocking_render(renderer):
     assert (images[0] == want[0][0]).all()
 
 
+def test_async_pool_overflow_with_two_frames_in_flight():
+    """The overflow contract of render_viewport_async (include/swegl_b200.h): a fresh context's fragment pool holds 2^24
+    entries; a frame that fills a 6400x3600 screen needs 23 M.  With two frames in flight the frame after the overflowing
+    one has already run with the same pools: BOTH tickets report ERR_CAPACITY, the pools are enlarged, and resubmitting
+    means begin_frame with THAT frame's node matrices again -- the device block holds the later frame's by then."""
+    from swegl_b200 import Renderer
+    from swegl_b200.renderer import SweglB200Error
+    from swegl_b200.scene import Viewport
+    scene, _, _, _ = configs.build("sphere100_1080")
+    screen = (6400, 3600)
+    r = Renderer(0)
+    try:
+        r.upload_scene(scene)
+        r.set_screen(*screen)
+        far, near = Viewport(0, 0, *screen, transparency_layers=0), Viewport(0, 0, *screen, transparency_layers=0)
+        far.camera.apply([("translate", 0, 0, -40.0)])          # a dot: fits any pool
+        near.camera.apply([("translate", 0, 0, -3.0)])          # the sphere fills the screen: 23 M fragments
+        w0, n0 = scene.node_matrices()
+        mats = []
+        for k in range(3):                                      # every frame has node matrices of its own (the sphere turns)
+            w = w0.copy()
+            c, s_ = np.float32(np.cos(0.3 * k)), np.float32(np.sin(0.3 * k))
+            rot = np.array([[c, 0, s_, 0], [0, 1, 0, 0], [-s_, 0, c, 0], [0, 0, 0, 1]], np.float32)
+            w[0] = (rot @ w0[0]).astype(np.float32)
+            mats.append((w, n0))
+        images = [r.alloc_host((screen[1], screen[0]), np.uint32) for _ in range(2)]
+        r.begin_frame(scene, mats[0]); t_a = r.render_async(far, images[0])
+        r.begin_frame(scene, mats[1]); t_b = r.render_async(near, images[1])
+        r.wait(t_a)                                             # the small frame is fine
+        r.begin_frame(scene, mats[2]); t_c = r.render_async(near, images[0])
+        failed = []
+        for t in (t_b, t_c):
+            try:
+                r.wait(t)
+            except SweglB200Error as e:
+                assert e.status == _abi.ERR_CAPACITY
+                failed.append(t)
+        assert failed == [t_b, t_c]
+        # resubmission: begin_frame with frame b's data, then the view again; now it fits
+        r.begin_frame(scene, mats[1]); t_b2 = r.render_async(near, images[1])
+        r.wait(t_b2)
+        r.begin_frame(scene, mats[2]); t_c2 = r.render_async(near, images[0])
+        r.wait(t_c2)
+        want = np.zeros((screen[1], screen[0]), np.uint32)
+        for k, img in ((1, images[1]), (2, images[0])):
+            r.begin_frame(scene, mats[k]); st = r.render(near, want)
+            assert st.n_covered == screen[0] * screen[1]
+            assert (img == want).all(), f"resubmitted frame {k}"
+        assert (images[0] != images[1]).any()                   # the two frames really differ (different node matrices)
+    finally:
+        r.close()
+
+
 @pytest.mark.parametrize("name", ["truck_1080", "truck_4k_dof"])
 def test_color_target_assembles_bands_in_another_screen(renderer, name):
     """multi-GPU output path on one GPU: a second context renders its band straight into the first context's screen
