@@ -214,6 +214,17 @@ def algorithmic_bytes(scene, vp, covered):
     return {"fragment": 8 * wh + t_unique, "dof": 12 * wh}
 
 
+def stage_fracs(scene, vp, covered, ms_per_stage):
+    """k_fragments / k_dof of a workload against the measured HBM bandwidth: algorithmic bytes / stage time / peak"""
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    ab = algorithmic_bytes(scene, vp, covered)
+    out = {"k_fragments": ab["fragment"] / (ms_per_stage["ms_fragment"] * 1e-3) / 1e9 / peak if ms_per_stage["ms_fragment"] > 0 else None}
+    if ms_per_stage.get("ms_post", 0) > 0.005:              # (a null post pass is a 2.7 us copy-less stage, not k_dof)
+        out["k_dof"] = ab["dof"] / (ms_per_stage["ms_post"] * 1e-3) / 1e9 / peak
+    return out
+
+
 def measure_gpu(r, torch, scene, vps, screen, steps, warmup, flush):
     """-> (seconds for `steps` frames measured with per-frame CUDA events, stats of the last frame)"""
     for w in range(warmup):
@@ -739,6 +750,10 @@ def sharded_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
                       "peer_write_into_rank0": sum((b[1] - b[0]) * vp.w * 4 for b in bands_now[1:]),
                       "peer_protocol_into_rank0": sum(n * 8 * 128 * 4 for n in busy[1:]),
                       "how": "algorithmic: rows x width x 4 B of the other ranks' bands / 4 KiB of colour per busy tile of theirs"}
+    stage_ms, stage_frac = None, None
+    if world == 1:                                      # the whole frame on one GPU: its stages against the roofline as well
+        stage_ms, last_ = measure_kernels(r, scene, [vp], 5)
+        stage_frac = stage_fracs(scene, vp, int(last_.n_covered), stage_ms)
     cands = [m for m in (ms_gather, ms_peer, ms_sync) if m is not None]
     best = min(cands)
     checks = [c for c in (gather_ok, peer_ok, sync_ok) if c is not None]
@@ -752,7 +767,7 @@ def sharded_frame(r, torch, dist, name, steps, warmup, flush, world, rank):
             "frame_fnv_ok_peer_protocol": sync_ok,
             "nvlink": ({"nccl_gather": nvl_gather, "peer_write": nvl_peer, "peer_protocol": nvl_sync,
                         "note": "hardware counters (NVML NVLINK_THROUGHPUT_DATA_TX/RX, nvidia-smi nvlink -gt d); None = not exposed on this box"} if world > 1 else None),
-            "peer_bytes_per_frame": peer_bytes,
+            "peer_bytes_per_frame": peer_bytes, "ms_per_stage": stage_ms, "roofline_frac": stage_frac,
             "n_gpus": world,
             "partition": "row bands, sort-first, scene replicated, band culling (DESIGN.md 6: nccl_gather / peer_write / peer_protocol)" if world > 1 else "single GPU",
             "bands": state["bands"], "rank0_band_covered_pixels": int(st.n_covered), "scaling": "strong"}
@@ -850,7 +865,8 @@ def main():
                 "one_frame_at_a_time_fps": a["serial_frames"] / a["secs"],
                 "e2e_fps": a["e2e_frames"] / a["e2e_secs"], "e2e_blocking_call_fps": a["e2e_sync_frames"] / a["e2e_sync_secs"],
                 "e2e_d2h_bytes_per_frame": a["d2h"], "frame_fnv_ok": a.get("frame_fnv_ok"),
-                "shaded_mpix_per_s": al.n_covered * a["serial_frames"] / a["secs"] / 1e6, "ms_per_stage": ak}
+                "shaded_mpix_per_s": al.n_covered * a["serial_frames"] / a["secs"] / 1e6, "ms_per_stage": ak,
+                "roofline_frac": stage_fracs(a["scene"], a["vps"][0], int(al.n_covered), ak)}
 
     # the remaining BASELINE.json configs that fit one GPU (config 1 and config 3), device-resident, one frame at a time
     others = None
@@ -866,7 +882,7 @@ def main():
             ok_, ol_ = measure_kernels(r, osc, ovps, 10)
             others[oname] = {"description": ocfg["desc"], "one_frame_at_a_time_fps": n_ / osecs, "ms_per_frame": 1e3 * osecs / n_,
                              "covered_pixels": int(ol_.n_covered), "shaded_mpix_per_s": ol_.n_covered * n_ / osecs / 1e6,
-                             "ms_per_stage": ok_}
+                             "ms_per_stage": ok_, "roofline_frac": stage_fracs(osc, ovps[0], int(ol_.n_covered), ok_)}
 
     sharded = None
     if args.sharded and not args.no_also:
