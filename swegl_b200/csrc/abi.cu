@@ -671,10 +671,12 @@ int swegl_b200_set_animation(swegl_b200_ctx *ctx, const swegl_b200_animation_des
     // hierarchy levels (vertex_shaders.hpp:16-33 recurses from the roots; a node's matrix needs its parent's)
     std::vector<int32_t> level(n, -1);
     uint32_t n_levels = 0;
+    for (uint32_t i = 0; i < n; i++)
+        if (an->node_parent[i] < -1 || an->node_parent[i] >= (int32_t)n) return fail(ctx, SWEGL_B200_ERR_ARG, "set_animation: node_parent out of range");
     for (uint32_t i = 0; i < n; i++) {
         uint32_t depth = 0; int32_t j = (int32_t)i;
         while (j >= 0 && level[j] < 0) {
-            if ((uint32_t)j >= n || an->node_parent[j] >= (int32_t)n || ++depth > n) return fail(ctx, SWEGL_B200_ERR_ARG, "set_animation: bad node_parent (index or cycle)");
+            if (++depth > n) return fail(ctx, SWEGL_B200_ERR_ARG, "set_animation: node_parent forms a cycle");
             j = an->node_parent[j];
         }
         // walk down again assigning levels

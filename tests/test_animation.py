@@ -219,6 +219,12 @@ def test_device_side_animation_argument_checks(renderer):
         renderer.set_animation(bad)
     assert e.value.status == _abi.ERR_ARG
     bad = fresh("BoxAnimated")
+    bad.node_parent = bad.node_parent.copy()
+    bad.node_parent[0] = 10 ** 6                      # a parent index beyond the node array
+    with pytest.raises(SweglB200Error) as e:
+        renderer.set_animation(bad)
+    assert e.value.status == _abi.ERR_ARG
+    bad = fresh("BoxAnimated")
     bad.chan_n_steps = bad.chan_n_steps.copy()
     bad.chan_n_steps[0] = len(bad.step_time) + 5      # key frames beyond the arrays
     with pytest.raises(SweglB200Error) as e:
