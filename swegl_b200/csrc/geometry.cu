@@ -15,7 +15,10 @@
 namespace sb {
 
 static constexpr int TPB = 256;
-static constexpr uint32_t SPAN_SEG = 4;      // 32-column bins per span segment (one lane walks one segment)
+#ifndef SPAN_SEG_V
+#define SPAN_SEG_V 4
+#endif
+static constexpr uint32_t SPAN_SEG = SPAN_SEG_V;      // 32-column bins per span segment (one lane walks one segment; 2 and 1 measured: see profiles/README.md)
 
 // ----------------------------------------------------------------------------------------
 // band culling (row-band sharding): which triangle clusters / vertex blocks this view has to look at at all
