@@ -16,9 +16,9 @@ namespace sb {
 
 static constexpr int TPB = 256;
 #ifndef SPAN_SEG_V
-#define SPAN_SEG_V 4
+#define SPAN_SEG_V 2
 #endif
-static constexpr uint32_t SPAN_SEG = SPAN_SEG_V;      // 32-column bins per span segment (one lane walks one segment; 2 and 1 measured: see profiles/README.md)
+static constexpr uint32_t SPAN_SEG = SPAN_SEG_V;      // 32-column bins per span segment (one lane walks one segment).  Measured 1 / 2 / 4 / 8: truck 4K spans 29.7 / 29.6 / 32.6 / 39.4 us, BrainStem 71.0 / 67.8 / 67.4 / 71.7, 8K sphere 252 / 250 / 250 / 309
 
 // ----------------------------------------------------------------------------------------
 // band culling (row-band sharding): which triangle clusters / vertex blocks this view has to look at at all
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(128, SETUP_MINB) k_setup(DeviceScene s, const 
 // 32-column bin the span crosses.
 // ----------------------------------------------------------------------------------------
 
-// One SEGMENT (up to SPAN_SEG bins = 128 pixels) of a span per thread.
+// One SEGMENT (up to SPAN_SEG bins = 64 pixels) of a span per thread.
 //  * The thread jumps to its segment's first column with radd() (free for a span's first segment) and replays
 //    qpixel.Step() pixel by pixel (renderer.cpp:486); the recurrence is serial in x.  It writes ualpha = topalpha /
 //    bottomalpha (progress(), interpolator.hpp:98) of every pixel to the fragment stream, four pixels per 128-bit
@@ -786,7 +786,7 @@ __global__ void __launch_bounds__(SPAN_TPB, SPAN_MINB) k_spans(const ViewParams 
             sh.seg_incl[tid] += before;
         }
         if (SPAN_ROWS > 32) __syncthreads();
-        // ---- phase C: thread = SEGMENT (SPAN_SEG bins = 128 pixels) of the group's spans, so a screen-wide span
+        // ---- phase C: thread = SEGMENT (SPAN_SEG bins = 64 pixels) of the group's spans, so a screen-wide span
         //      is walked by many threads (walk_segment) ----
         const uint32_t total = sh.seg_incl[SPAN_ROWS - 1];
         for (uint32_t t = tid; t < total; t += SPAN_TPB) {
