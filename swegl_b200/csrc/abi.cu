@@ -919,7 +919,7 @@ static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const Vie
         if (dof) { launch_dof_classify(vp, ctx->d_vp(), ctx->pools, out0, out1, post_dst, ctx->sw, st); launches++; }
     } else {
         launch_fragments(ctx->ds, vp, ctx->d_vp(), ctx->d_fp(), ctx->pools, color, color_pitch, ctx->d_depth, count_covered,
-                         sync_counters ? nullptr : counters_out, skip_bg, ctx->fast_shading, dof, out0, out1, post_dst, ctx->sw, st);
+                         sync_counters ? nullptr : counters_out, skip_bg, ctx->fast_shading, dof, out0, out1, post_dst, ctx->sw, ctx->dense_spans, st);
         launches++;
     }
     if (timing) cudaEventRecord(ctx->ev[4], st);

@@ -442,6 +442,9 @@ SB_DEV void dof_tile_duty(const Pools &pl, const FragGeom &g, uint32_t stamp, ui
 #ifndef FRAG_MINB
 #define FRAG_MINB 5         // 48 registers, 40 warps per SM: measured against 6 (40 registers) and 8 (32 registers, spills in the shader)
 #endif
+#ifndef FRAG_COVER_MIN
+#define FRAG_COVER_MIN 3    // k_fragments<.., CROWD = 1>: staged rounds of at least this many pieces are resolved per covered lane
+#endif
 #ifndef FRAG_RESOLVE_UNROLL
 #define FRAG_RESOLVE_UNROLL 4
 #endif
@@ -459,7 +462,7 @@ __device__ unsigned long long g_frag_timeline[2048 * 16];
 #define FRAG_PH(slot) do { } while (0)
 #define FRAG_TL(slot, v) do { } while (0)
 #endif
-template <int LIGHT, int TEX, int FAST>
+template <int LIGHT, int TEX, int FAST, int CROWD>
 __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s, const ViewParams *__restrict__ vpp,
                                                         const FrameParams *__restrict__ fpp, Pools pl, FragGeom g,
                                                         uint32_t *__restrict__ color, int color_pitch,
@@ -639,6 +642,45 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
                         __syncwarp();
                         if (lane < 2 * m) fw.rec[b][lane] = reinterpret_cast<const uint4 *>(slots + base)[lane];
                         __syncwarp();
+                    }
+                    if (CROWD && m >= FRAG_COVER_MIN) {
+                        // A crowded round (a dense mesh: many pieces of a few pixels each; CROWD is chosen per frame, like
+                        // the span kernel, from the previous frame's scanline count -- the mere presence of this path costs
+                        // the lean kernel a microsecond on a frame of few, wide pieces).  Taking the pieces one after the
+                        // other costs the whole warp a pass per piece although each touches a few lanes; instead every lane
+                        // first notes WHICH of the staged pieces cover it (one bit per piece, from the broadcast xs | xe words),
+                        // then walks only its own pieces -- the warp makes as many turns as its most overdrawn pixel has
+                        // pieces, two pieces per turn so that their stream loads go out together.  Same keys, same minimum.
+                        uint32_t cover = 0;
+                        #pragma unroll 4
+                        for (int k = 0; k < m; k++) {
+                            const uint32_t xx = reinterpret_cast<const uint32_t *>(&rec[2 * k])[1];
+                            const unsigned xs = xx & 0xFFu, wd = (xx >> 8) - xs;
+                            cover |= ((unsigned)lane - xs < wd ? 1u : 0u) << k;
+                        }
+                        while (__any_sync(0xFFFFFFFFu, cover != 0u)) {
+                            const bool in0 = cover != 0u;
+                            const int p0 = in0 ? __ffs(cover) - 1 : 0;
+                            cover &= cover - 1u;
+                            const bool in1 = cover != 0u;
+                            const int p1 = in1 ? __ffs(cover) - 1 : 0;
+                            cover &= cover - 1u;
+                            const uint4 a0 = rec[2 * p0], b0 = rec[2 * p1];
+                            const float ua = pl.frag_u[in0 ? a0.x + (uint32_t)lane : 0u], ub = pl.frag_u[in1 ? b0.x + (uint32_t)lane : 0u];
+                            const float za = fadd(__uint_as_float(a0.z), fmul(__uint_as_float(a0.w), ua));     // value(0), renderer.cpp:488
+                            const float zb = fadd(__uint_as_float(b0.z), fmul(__uint_as_float(b0.w), ub));
+                            if (in0 && za >= NEAR_Z) {                              // renderer.cpp:489-492
+                                const uint2 r1 = *reinterpret_cast<const uint2 *>(&rec[2 * p0 + 1]);
+                                const uint64_t key = ((uint64_t)__float_as_uint(za) << 32) | r1.x;
+                                if (key < best) { best = key; best_u = ua; best_span = r1.y; }
+                            }
+                            if (in1 && zb >= NEAR_Z) {
+                                const uint2 r1 = *reinterpret_cast<const uint2 *>(&rec[2 * p1 + 1]);
+                                const uint64_t key = ((uint64_t)__float_as_uint(zb) << 32) | r1.x;
+                                if (key < best) { best = key; best_u = ub; best_span = r1.y; }
+                            }
+                        }
+                        continue;
                     }
                     // groups of RESOLVE_UNROLL pieces whose fragment-stream loads are issued back to back, WITHOUT a remainder
                     // loop: a bin holds ~3 pieces on average, and pieces taken one by one pay one L2 round trip each.  Every lane
@@ -1313,23 +1355,24 @@ static int num_sms()
 
 template <int LIGHT, int TEX, int FAST>
 static void launch_frag_t(const DeviceScene &s, const ViewParams *d_vp, const FrameParams *d_fp, const Pools &p, const FragGeom &g,
-                          uint32_t *color, int color_pitch, float *depth, uint32_t *dof_dst, bool count_covered, Counters *h_counters_out, cudaStream_t st)
+                          uint32_t *color, int color_pitch, float *depth, uint32_t *dof_dst, bool count_covered, Counters *h_counters_out, bool crowded, cudaStream_t st)
 {
     if (g.n_tiles <= 0) return;
     // one wave of persistent CTAs (fewer when the viewport has fewer row items than that)
     const unsigned wave = (unsigned)(num_sms() * FRAG_CTAS_PER_SM);
     const unsigned need = ((unsigned)g.n_tiles * FRAG_ROWS + FRAG_ROWS - 1) / FRAG_ROWS;
     const unsigned grid = need < wave ? (need ? need : 1u) : wave;
-    launch_chain(k_fragments<LIGHT, TEX, FAST>, grid, FRAG_TPB, st, true, s, d_vp, d_fp, p, g, color, color_pitch, depth, dof_dst, count_covered ? 1 : 0, h_counters_out);
+    if (crowded) launch_chain(k_fragments<LIGHT, TEX, FAST, 1>, grid, FRAG_TPB, st, true, s, d_vp, d_fp, p, g, color, color_pitch, depth, dof_dst, count_covered ? 1 : 0, h_counters_out);
+    else launch_chain(k_fragments<LIGHT, TEX, FAST, 0>, grid, FRAG_TPB, st, true, s, d_vp, d_fp, p, g, color, color_pitch, depth, dof_dst, count_covered ? 1 : 0, h_counters_out);
 }
 
 void launch_fragments(const DeviceScene &s, const ViewParams &vp, const ViewParams *d_vp, const FrameParams *d_fp, const Pools &p,
                       uint32_t *color, int color_pitch, float *depth, bool count_covered, Counters *h_counters_out, bool skip_bg_color,
-                      bool fast, bool dof, int out_row0, int out_row1, uint32_t *dof_dst, int dof_pitch, cudaStream_t st)
+                      bool fast, bool dof, int out_row0, int out_row1, uint32_t *dof_dst, int dof_pitch, bool crowded, cudaStream_t st)
 {
     const FragGeom g = make_geom(vp, skip_bg_color, dof, out_row0, out_row1, dof_pitch);
-#define SB_CASE(L, T) if (vp.light_mode == L && vp.tex_mode == T) { launch_frag_t<L, T, 0>(s, d_vp, d_fp, p, g, color, color_pitch, depth, dof_dst, count_covered, h_counters_out, st); return; }
-#define SB_FAST(T) if (fast && vp.light_mode == SWEGL_B200_LIGHT_PHONG && vp.tex_mode == T) { launch_frag_t<SWEGL_B200_LIGHT_PHONG, T, 1>(s, d_vp, d_fp, p, g, color, color_pitch, depth, dof_dst, count_covered, h_counters_out, st); return; }
+#define SB_CASE(L, T) if (vp.light_mode == L && vp.tex_mode == T) { launch_frag_t<L, T, 0>(s, d_vp, d_fp, p, g, color, color_pitch, depth, dof_dst, count_covered, h_counters_out, crowded, st); return; }
+#define SB_FAST(T) if (fast && vp.light_mode == SWEGL_B200_LIGHT_PHONG && vp.tex_mode == T) { launch_frag_t<SWEGL_B200_LIGHT_PHONG, T, 1>(s, d_vp, d_fp, p, g, color, color_pitch, depth, dof_dst, count_covered, h_counters_out, crowded, st); return; }
     SB_FAST(0) SB_FAST(1) SB_FAST(2)
     SB_CASE(0, 0) SB_CASE(0, 1) SB_CASE(0, 2)
     SB_CASE(1, 0) SB_CASE(1, 1) SB_CASE(1, 2)
