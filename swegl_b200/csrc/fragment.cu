@@ -445,6 +445,9 @@ SB_DEV void dof_tile_duty(const Pools &pl, const FragGeom &g, uint32_t stamp, ui
 #ifndef FRAG_COVER_MIN
 #define FRAG_COVER_MIN 3    // k_fragments<.., CROWD = 1>: staged rounds of at least this many pieces are resolved per covered lane
 #endif
+#ifndef FRAG_TURN
+#define FRAG_TURN 2         // pieces per lane and turn of the CROWD resolve (their stream loads go out together); 1 / 2 / 3 / 4 measured: BrainStem 88.5 / 81.0 / 79.9 / 81.9 us, 8K sphere 336 / 341 / 348 / 356 us
+#endif
 #ifndef FRAG_RESOLVE_UNROLL
 #define FRAG_RESOLVE_UNROLL 4
 #endif
@@ -650,7 +653,7 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
                         // other costs the whole warp a pass per piece although each touches a few lanes; instead every lane
                         // first notes WHICH of the staged pieces cover it (one bit per piece, from the broadcast xs | xe words),
                         // then walks only its own pieces -- the warp makes as many turns as its most overdrawn pixel has
-                        // pieces, two pieces per turn so that their stream loads go out together.  Same keys, same minimum.
+                        // pieces, FRAG_TURN pieces per turn so that their stream loads go out together.  Same keys, same minimum.
                         uint32_t cover = 0;
                         #pragma unroll 4
                         for (int k = 0; k < m; k++) {
@@ -659,25 +662,24 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
                             cover |= ((unsigned)lane - xs < wd ? 1u : 0u) << k;
                         }
                         while (__any_sync(0xFFFFFFFFu, cover != 0u)) {
-                            const bool in0 = cover != 0u;
-                            const int p0 = in0 ? __ffs(cover) - 1 : 0;
-                            cover &= cover - 1u;
-                            const bool in1 = cover != 0u;
-                            const int p1 = in1 ? __ffs(cover) - 1 : 0;
-                            cover &= cover - 1u;
-                            const uint4 a0 = rec[2 * p0], b0 = rec[2 * p1];
-                            const float ua = pl.frag_u[in0 ? a0.x + (uint32_t)lane : 0u], ub = pl.frag_u[in1 ? b0.x + (uint32_t)lane : 0u];
-                            const float za = fadd(__uint_as_float(a0.z), fmul(__uint_as_float(a0.w), ua));     // value(0), renderer.cpp:488
-                            const float zb = fadd(__uint_as_float(b0.z), fmul(__uint_as_float(b0.w), ub));
-                            if (in0 && za >= NEAR_Z) {                              // renderer.cpp:489-492
-                                const uint2 r1 = *reinterpret_cast<const uint2 *>(&rec[2 * p0 + 1]);
-                                const uint64_t key = ((uint64_t)__float_as_uint(za) << 32) | r1.x;
-                                if (key < best) { best = key; best_u = ua; best_span = r1.y; }
+                            bool in[FRAG_TURN]; int pc[FRAG_TURN]; uint4 r0[FRAG_TURN]; float u[FRAG_TURN];
+                            #pragma unroll
+                            for (int j = 0; j < FRAG_TURN; j++) {
+                                in[j] = cover != 0u;
+                                pc[j] = in[j] ? __ffs(cover) - 1 : 0;
+                                cover &= cover - 1u;
+                                r0[j] = rec[2 * pc[j]];
                             }
-                            if (in1 && zb >= NEAR_Z) {
-                                const uint2 r1 = *reinterpret_cast<const uint2 *>(&rec[2 * p1 + 1]);
-                                const uint64_t key = ((uint64_t)__float_as_uint(zb) << 32) | r1.x;
-                                if (key < best) { best = key; best_u = ub; best_span = r1.y; }
+                            #pragma unroll
+                            for (int j = 0; j < FRAG_TURN; j++) u[j] = pl.frag_u[in[j] ? r0[j].x + (uint32_t)lane : 0u];
+                            #pragma unroll
+                            for (int j = 0; j < FRAG_TURN; j++) {
+                                const float z = fadd(__uint_as_float(r0[j].z), fmul(__uint_as_float(r0[j].w), u[j]));   // value(0), renderer.cpp:488
+                                if (in[j] && z >= NEAR_Z) {                         // renderer.cpp:489-492
+                                    const uint2 r1 = *reinterpret_cast<const uint2 *>(&rec[2 * pc[j] + 1]);
+                                    const uint64_t key = ((uint64_t)__float_as_uint(z) << 32) | r1.x;
+                                    if (key < best) { best = key; best_u = u[j]; best_span = r1.y; }
+                                }
                             }
                         }
                         continue;
