@@ -453,7 +453,9 @@ SB_DEV void dof_tile_duty(const Pools &pl, const FragGeom &g, uint32_t stamp, ui
 #endif
 static constexpr int RESOLVE_UNROLL = FRAG_RESOLVE_UNROLL;     // chunks of a bin whose fragment-stream loads are in flight together
 #ifndef FRAG_CTAS_PER_SM
+#ifndef FRAG_CTAS_PER_SM
 #define FRAG_CTAS_PER_SM FRAG_MINB
+#endif
 #endif
 SB_DEV unsigned long long global_ns();
 #ifdef FRAG_PROBE_TIMELINE
@@ -969,6 +971,9 @@ static constexpr int DOF_X0 = 8;                             // the staged windo
 static constexpr int DOF_WW = DOF_OW + 16;                   // 80 staged columns
 static constexpr int DOF_PW = DOF_WW + 1;                    // SAT row stride in entries (col 0 = zero border; odd -> rows on different banks)
 static constexpr int DOF_THREADS = 256;
+#ifndef DOF_CTAS_PER_SM
+#define DOF_CTAS_PER_SM 4         // persistent CTAs per SM (64 registers, 45 KB of shared memory each)
+#endif
 static constexpr int DOF_NPX = DOF_SH * DOF_WW;              // 3280 staged pixels
 
 // blur radius and "this pixel is a tap" for depth z, from the host-derived thresholds (common.cuh ViewParams)
@@ -1532,7 +1537,7 @@ void launch_dof(const ViewParams &vp, const ViewParams *d_vp, const Pools &p, co
     g.src_pitch = src_pitch; g.dst_pitch = dst_pitch; g.use_tma = use_tma ? 1 : 0;
     const int n_dof = g.ndx * ((vp.band1 - vp.band0 + DOF_OH - 1) / DOF_OH);
     if (n_dof <= 0) return;
-    const unsigned wave = (unsigned)(num_sms() * 4);
+    const unsigned wave = (unsigned)(num_sms() * DOF_CTAS_PER_SM);
     const unsigned grid = (unsigned)n_dof < wave ? (unsigned)n_dof : wave;
     CUtensorMap zero{};
     launch_chain_smem(k_dof, grid, DOF_THREADS, sizeof(DofSmem), st, true, use_tma ? *tm_color : zero, use_tma ? *tm_depth : zero, d_vp, p, g, src, depth, dst);
