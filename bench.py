@@ -14,7 +14,7 @@ the 1080p configs[1] frame is measured in the same run and reported under "also"
               under the fragment/DoF kernels of frame i); one pair of CUDA events around the batch; max over ranks.
               one_frame_at_a_time: the same frames on one context, CUDA events around each frame on the launching
               stream, a 256 MiB L2 flush between frames (outside the events).
-  e2e       : the same frames through the public host API (Renderer.begin_frame + render_async/wait, two frames in
+  e2e       : the same frames through the public host API (Renderer.begin_frame + render_async/wait, three frames in
               flight): node matrices/lights H2D and the finished frame D2H into pinned memory every step;
               e2e.blocking_call_fps is the same through the blocking Renderer.render.
   roofline  : the dominant kernel's algorithmic bytes / its CUDA-event duration.
@@ -40,6 +40,7 @@ DEFAULT_WORKLOAD = "truck_4k_dof"
 ALSO_WORKLOAD = "truck_1080"
 FRAMES_PER_STEP = 256           # `value`: a step is a batch of this many frames (K = 50 -> ~1 s of timed device work at 4K)
 E2E_FRAMES_PER_STEP = 32        # the end-to-end loops are PCIe / host bound: smaller batches keep the default run within minutes
+E2E_IN_FLIGHT = 3               # frames submitted before the oldest is waited for (the library keeps three staging images)
 SERIAL_FRAMES_MAX = 1000        # one_frame_at_a_time: a 256 MiB L2 flush sits between the frames
 SINGLE_FRAME_STEPS = 50         # timed frames of the single-frame (sharded / multiview) measurements
 
@@ -268,7 +269,8 @@ def measure_e2e(r, torch, scene, vps, screen, steps, warmup, pixels):
 
 def measure_e2e_pipelined(r, torch, scene, vps, screen, steps, warmup, images):
     """the same per-frame host work (begin_frame: node matrices + lights H2D; finished frame D2H into pinned memory)
-    through render_async/wait: frame i+1 is submitted before frame i is waited for, two host images alternate"""
+    through render_async/wait: frames i+1 and i+2 are submitted before frame i is waited for (the library keeps three
+    staging images), three host images take turns"""
     fd_nodes = scene.node_matrices()
     descs = [vp.desc() for vp in vps]
 
@@ -276,8 +278,8 @@ def measure_e2e_pipelined(r, torch, scene, vps, screen, steps, warmup, images):
         pending = []
         for i in range(n):
             r.begin_frame(scene, fd_nodes)
-            pending.append([r.render_async(d, images[i & 1]) for d in descs])
-            if len(pending) > 1:
+            pending.append([r.render_async(d, images[i % len(images)]) for d in descs])
+            if len(pending) > len(images) - 1:
                 for t in pending.pop(0):
                     r.wait(t)
         for fr in pending:
@@ -359,7 +361,7 @@ def gpu_workload(r, torch, name, steps, warmup, flush, world, dist, do_e2e=True,
     out = {"scene": scene, "vps": vps, "screen": screen, "cfg": cfg, "secs": secs, "serial_frames": serial_frames, "ms": ms,
            "batch_secs": batch_secs, "pipe_secs": sum(batch_secs), "depth": depth}
     if do_e2e:
-        images = [r.alloc_host((screen[1], screen[0]), np.uint32) for _ in range(2)]
+        images = [r.alloc_host((screen[1], screen[0]), np.uint32) for _ in range(E2E_IN_FLIGHT)]
         n_sync, n_async = max(steps * E2E_FRAMES_PER_STEP // 4, 8), steps * E2E_FRAMES_PER_STEP
         sync_secs = measure_e2e(r, torch, scene, vps, screen, n_sync, warmup, images[0])
         r.readback_stats(reset=True)
@@ -381,10 +383,10 @@ def gpu_workload(r, torch, name, steps, warmup, flush, world, dist, do_e2e=True,
         if want is not None and len(vps) == 1:
             r.set_shading(_abi.SHADING_EXACT)           # the manifest pins the bit-exact frame; the timed frames use the +-1 LSB shading
             fd_nodes = scene.node_matrices()
-            for i in range(3):                          # through the pipelined, partial path: both host images
+            for i in range(2 * len(images)):            # through the pipelined, partial path: every host image (and staging image) twice
                 r.begin_frame(scene, fd_nodes)
-                r.wait(r.render_async(vps[0].desc(), images[i & 1]))
-            out["frame_fnv_ok"] = frame_hash(images[0]) == want and frame_hash(images[1]) == want
+                r.wait(r.render_async(vps[0].desc(), images[i % len(images)]))
+            out["frame_fnv_ok"] = all(frame_hash(im) == want for im in images)
             r.set_shading(_abi.SHADING_FAST)
     return out
 
@@ -956,7 +958,7 @@ def main():
                     "h2d_bytes_per_step": main_res["h2d"] * E2E_FRAMES_PER_STEP, "d2h_bytes_per_step": int(main_res["d2h"] * E2E_FRAMES_PER_STEP),
                     "h2d_bytes_per_frame": main_res["h2d"], "d2h_bytes_per_frame": int(main_res["d2h"]), "full_frame_bytes": main_res["d2h_full"],
                     "timed_region_s": main_res["e2e_secs"],
-                    "api": "Renderer.begin_frame + render_async/wait (swegl_b200_render_viewport_async): 2 frames in flight, "
+                    "api": "Renderer.begin_frame + render_async/wait (swegl_b200_render_viewport_async): 3 frames in flight, "
                            "every frame's node matrices/lights go H2D; D2H into pinned memory of the rectangle that differs from "
                            "what the host image already holds (the frame's bounding box united with the previous frame's; "
                            "d2h_bytes_* are the bytes the library counted, swegl_b200_readback_stats)",

@@ -231,15 +231,17 @@ int  swegl_b200_render_viewport(swegl_b200_ctx *ctx, const swegl_b200_viewport_d
                                 swegl_b200_stats *stats);
 
 /* Pipelined variant of render_viewport ("async readback / double-buffered frames"): queues the
- * frame, a device-side copy of the finished rectangle into one of two staging images, and the copy of that
- * image to host `pixels` / `zbuffer` on a second stream -- then returns.  The next frame renders while this one
- * crosses PCIe.  `*ticket` identifies the frame; its host data is complete after swegl_b200_wait(ticket).
- * At most two frames are in flight (a third submit waits for the oldest), so callers alternate between two
- * host images; these should be page-locked (swegl_b200_alloc_host), otherwise the copy blocks the submit.
+ * frame, a device-side copy of the finished rectangle into one of three staging images (only the part that differs
+ * from the frame the staging image already holds), and the copy of that image to host `pixels` / `zbuffer` on a
+ * second stream -- then returns.  The next frames render while this one crosses PCIe.  `*ticket` identifies the
+ * frame; its host data is complete after swegl_b200_wait(ticket).
+ * At most three frames are in flight (a fourth submit waits, on the device, for the oldest one's copy), so callers
+ * rotate over two or three host images and wait for a frame before reusing its image; the images should be
+ * page-locked (swegl_b200_alloc_host), otherwise the copy blocks the submit.
  * swegl_b200_wait returns SWEGL_B200_ERR_CAPACITY when that frame ran out of pool space (the pools are then
  * enlarged: submit it again), like swegl_b200_synchronize.
  *
- * Overflow with two frames in flight: by the time wait(ticket i) reports ERR_CAPACITY, frame i+1 has already replaced the
+ * Overflow with several frames in flight: by the time wait(ticket i) reports ERR_CAPACITY, frame i+1 has already replaced the
  * per-frame data on the device (node matrices, lights) and ran with the same undersized pools, so expect its ticket to
  * fail as well.  Resubmitting frame i therefore means swegl_b200_begin_frame with THAT frame's data again, then
  * render_viewport_async; render_viewport() (blocking) redoes an overflowed frame itself.

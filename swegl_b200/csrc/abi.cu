@@ -61,7 +61,11 @@ struct swegl_b200_ctx {
     std::vector<uint64_t> failed_tickets;                           // async frames found to have overflowed a pool
     int next_slot = 0, frame_slot = 0; bool frame_dirty = false;
     int last_slot = 0;                  // staging slot of the most recently issued view
-    // pipelined read-back (render_viewport_async): two device staging images, filled on `stream`, drained on `copy_stream`
+    // pipelined read-back (render_viewport_async): N_OUT device staging images, filled on `stream`, drained on `copy_stream`.
+    // Three, not two: the host learns a frame's bounding box (and so can queue its copy) only when that frame's kernels are
+    // done, and the copy of a 4K frame's box takes about as long as the next frame's kernels -- with two images the submit
+    // of frame i+2 has to wait for that copy and reaches the GPU just after frame i+1 has ended.
+    static constexpr int N_OUT = 3;
     struct OutBuf {
         uint32_t *color = nullptr; float *depth = nullptr; size_t cap = 0;
         cudaEvent_t ready = nullptr, copied = nullptr;
@@ -69,7 +73,9 @@ struct swegl_b200_ctx {
         // the read-back itself is issued once the frame's bounding box is known on the host (issue_readback)
         bool d2h_issued = true, partial_ok = false, dof = false;
         void *pixels = nullptr; int32_t pitch_bytes = 0; float *zbuffer = nullptr; ViewParams vp{};
-    } out[2];
+        // what the staging image holds (k_stage_rect): a complete frame of view `vp` over background `stage_bg`, its box in rec[rec_par]
+        StageRect *rec = nullptr; int rec_par = 0; bool stage_valid = false; uint32_t stage_bg = 0;
+    } out[N_OUT];
     // partial read-back: what the library last left in each host image (the caller's `pixels`), so that only the
     // rectangle that differs from it crosses PCIe
     struct HostImage {
@@ -329,6 +335,7 @@ void swegl_b200_destroy(swegl_b200_ctx *ctx)
     for (auto &ob : ctx->out) {
         if (ob.color) cudaFree(ob.color);
         if (ob.depth) cudaFree(ob.depth);
+        if (ob.rec) cudaFree(ob.rec);
         if (ob.ready) cudaEventDestroy(ob.ready);
         if (ob.copied) cudaEventDestroy(ob.copied);
     }
@@ -1207,9 +1214,10 @@ int swegl_b200_render_viewport_async(swegl_b200_ctx *ctx, const swegl_b200_viewp
     if (!ctx || !pixels || pitch_bytes < 4 || !ticket) return fail(ctx, SWEGL_B200_ERR_ARG, "render_viewport_async: null argument");
     if (ctx->color_target)
         return fail(ctx, SWEGL_B200_ERR_STATE, "render_viewport_async: a colour target is set (the finished pixels are in the target's screen, not here)");
-    auto &ob = ctx->out[ctx->ticket_seq & 1];
-    auto &prev = ctx->out[(ctx->ticket_seq & 1) ^ 1];
-    // this staging image's previous frame (two submits ago) must have its copies queued before it is overwritten
+    constexpr int N_OUT = swegl_b200_ctx::N_OUT;
+    auto &ob = ctx->out[ctx->ticket_seq % N_OUT];
+    auto &prev = ctx->out[(ctx->ticket_seq + N_OUT - 1) % N_OUT];
+    // this staging image's previous frame (N_OUT submits ago) must have its copies queued before it is overwritten
     if (ob.in_flight && !ob.d2h_issued) { int rc0 = issue_readback(ctx, ob); if (rc0) return rc0; }
     int rc = render_common(ctx, v, false, nullptr);
     if (rc) return rc;
@@ -1222,12 +1230,24 @@ int swegl_b200_render_viewport_async(swegl_b200_ctx *ctx, const swegl_b200_viewp
         if (ob.in_flight) CK(cudaEventSynchronize(ob.copied));
         CK(cudaStreamSynchronize(ctx->stream));
         CK(dalloc(ob.color, need)); CK(dalloc(ob.depth, need));
-        ob.cap = need;
+        ob.cap = need; ob.stage_valid = false;
     }
+    if (!ob.rec) { CK(cudaMalloc((void **)&ob.rec, 2 * sizeof(StageRect))); ob.stage_valid = false; }
     cudaStream_t st = ctx->stream;
-    if (ob.in_flight) CK(cudaStreamWaitEvent(st, ob.copied, 0));        // the frame before last has left this image
-    CK(cudaMemcpy2DAsync(ob.color, (size_t)vp.vw * 4, ctx->d_screen + (size_t)vp.band0 * ctx->sw + vp.vx, (size_t)ctx->sw * 4,
-                         (size_t)vp.vw * 4, (size_t)rows, cudaMemcpyDeviceToDevice, st));
+    if (ob.in_flight) CK(cudaStreamWaitEvent(st, ob.copied, 0));        // the frame N_OUT submits ago has left this image
+    {
+        // only the part of the view that differs from what the staging image already holds is copied (k_stage_rect): the image
+        // must hold a complete frame of the same view geometry over the same background, and the view must publish its box
+        const bool dof = ctx->last_dof;
+        const uint32_t bg = post_background(vp, dof);
+        const ViewParams &o = ob.vp;
+        const bool same = ob.stage_valid && vp.n_layers == 0 && o.vx == vp.vx && o.vy == vp.vy && o.vw == vp.vw && o.vh == vp.vh
+                       && o.band0 == vp.band0 && o.band1 == vp.band1 && ob.stage_bg == bg;
+        launch_stage_rect(ob.color, ctx->d_screen + (size_t)vp.band0 * ctx->sw + vp.vx, ctx->sw, vp.vw, vp.band0 - vp.vy, vp.band1 - vp.vy,
+                          dof ? 8 : 0, ctx->pools.counters, ob.rec, ob.rec_par, !same, st);
+        CK(cudaGetLastError());
+        ob.rec_par ^= 1; ob.stage_valid = vp.n_layers == 0; ob.stage_bg = bg;
+    }
     if (zbuffer)
         CK(cudaMemcpyAsync(ob.depth, ctx->d_depth + (size_t)(vp.band0 - vp.vy) * vp.vw, need * 4, cudaMemcpyDeviceToDevice, st));
     CK(cudaEventRecord(ob.ready, st));
@@ -1248,7 +1268,7 @@ int swegl_b200_wait(swegl_b200_ctx *ctx, uint64_t ticket)
 {
     if (!ctx || ticket == 0 || ticket > ctx->ticket_seq) return fail(ctx, SWEGL_B200_ERR_ARG, "wait: unknown ticket");
     CK(cudaSetDevice(ctx->device));
-    auto &ob = ctx->out[(ticket - 1) & 1];
+    auto &ob = ctx->out[(ticket - 1) % swegl_b200_ctx::N_OUT];
     // a later frame through the same staging image implies this one is done (same stream order)
     if (ob.in_flight) {
         int rc0 = issue_readback(ctx, ob);

@@ -1195,6 +1195,61 @@ __global__ void __launch_bounds__(DOF_THREADS, 4) k_dof(const __grid_constant__ 
 }
 
 // ----------------------------------------------------------------------------------------
+// Staging of a finished view for the pipelined read-back (swegl_b200_render_viewport_async): the view's rows of the screen
+// go into a staging image the next frames do not touch.  Outside the bounding box of what was drawn (grown by the blur
+// radius under DoF-R) a frame is one constant, so an image that already holds a complete earlier frame of the same view
+// and background only needs the union of that frame's box and this one's -- 7 MB instead of 33 MB on the 4K truck
+// frame.  The boxes never leave the device: this frame's comes from the counters k_fragments left, the image's previous
+// one from a two-entry record (read entry `par`, write entry `par ^ 1`: no CTA can see the new box too early).
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_stage_rect(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, int src_pitch, int vw,
+                                                     int row_a, int row_b, int grow, const Counters *__restrict__ cn, StageRect *rec, int par, int full)
+{
+    int fx0 = 0, fx1 = 0, fy0 = 0, fy1 = 0;                                 // this frame's box, as the host derives it (abi.cu issue_readback)
+    const uint32_t bx0 = cn->bb_x0, bx1 = cn->bb_x1, by0 = cn->bb_y0, by1 = cn->bb_y1;
+    if (bx1 > bx0 && by1 > by0) {
+        fx0 = max(0, ((int)bx0 - grow) & ~3); fx1 = min(vw, ((int)bx1 + grow + 3) & ~3);
+        fy0 = max(row_a, (int)by0 - grow); fy1 = min(row_b, (int)by1 + grow);
+    }
+    if (cn->overflow) { full = 1; fx0 = 0; fx1 = vw; fy0 = row_a; fy1 = row_b; }   // an incomplete frame: nothing is known about it
+    int cx0 = 0, cx1 = vw, cy0 = row_a, cy1 = row_b;
+    if (!full) {
+        const StageRect o = rec[par];
+        const bool old_empty = o.x1 <= o.x0 || o.y1 <= o.y0, new_empty = fx1 <= fx0 || fy1 <= fy0;
+        if (old_empty && new_empty) { cx0 = cx1 = cy0 = cy1 = 0; }
+        else if (old_empty) { cx0 = fx0; cx1 = fx1; cy0 = fy0; cy1 = fy1; }
+        else if (new_empty) { cx0 = o.x0; cx1 = o.x1; cy0 = o.y0; cy1 = o.y1; }
+        else { cx0 = min(fx0, o.x0); cx1 = max(fx1, o.x1); cy0 = min(fy0, o.y0); cy1 = max(fy1, o.y1); }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { StageRect n; n.x0 = fx0; n.y0 = fy0; n.x1 = fx1; n.y1 = fy1; rec[par ^ 1] = n; }
+    const int w = cx1 - cx0, h = cy1 - cy0;
+    if (w <= 0 || h <= 0) return;
+    const uint32_t *s0 = src + (size_t)(cy0 - row_a) * src_pitch + cx0;
+    uint32_t *d0 = dst + (size_t)(cy0 - row_a) * vw + cx0;
+    if (((src_pitch | vw | cx0 | w) & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+        // item = 128 uint4 (2 KB) of one row, one warp per item, four independent 128-bit copies per lane
+        const int w4 = w >> 2, segs = (w4 + 127) >> 7, n_items = h * segs;
+        const int lane = threadIdx.x & 31, n_warps = (int)(gridDim.x * blockDim.x) >> 5;
+        for (int it = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); it < n_items; it += n_warps) {
+            const int r = it / segs, c = ((it - r * segs) << 7) + lane;
+            const uint4 *sp = reinterpret_cast<const uint4 *>(s0 + (size_t)r * src_pitch);
+            uint4 *dp = reinterpret_cast<uint4 *>(d0 + (size_t)r * vw);
+            uint4 v[4];
+            #pragma unroll
+            for (int k = 0; k < 4; k++) if (c + 32 * k < w4) v[k] = sp[c + 32 * k];
+            #pragma unroll
+            for (int k = 0; k < 4; k++) if (c + 32 * k < w4) dp[c + 32 * k] = v[k];
+        }
+    } else {
+        const size_t n = (size_t)w * h;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+            const int r = (int)(i / w), c = (int)(i - (size_t)r * w);
+            d0[(size_t)r * vw + c] = s0[(size_t)r * src_pitch + c];
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
 // Frame protocol of the band-sharded single frame (FrameSync, common.cuh): the assembling GPU (rank 0) clears the other
 // ranks' rows of its screen itself -- local HBM writes -- and announces the frame; the other ranks then store only the
 // tiles they drew into (their last kernel's ordinary stores, travelling over NVLink) and raise a flag in rank 0's
@@ -1313,6 +1368,12 @@ void preload_sync_kernels()
     cudaFuncAttributes a;
     cudaFuncGetAttributes(&a, k_sync_clear); cudaFuncGetAttributes(&a, k_sync_wait_ready);
     cudaFuncGetAttributes(&a, k_sync_signal); cudaFuncGetAttributes(&a, k_sync_wait_done);
+}
+static int num_sms();
+void launch_stage_rect(uint32_t *dst, const uint32_t *src, int src_pitch, int vw, int row_a, int row_b, int grow, const Counters *counters,
+                       StageRect *rec, int par, bool full, cudaStream_t st)
+{
+    launch_chain(k_stage_rect, num_sms() * 4, 256, st, false, dst, src, src_pitch, vw, row_a, row_b, grow, counters, rec, par, full ? 1 : 0);
 }
 void launch_sync_clear(const ViewParams &vp, const ViewParams *d_vp, uint32_t *screen, int pitch, FrameSync *own, bool do_clear, cudaStream_t st)
 {

@@ -125,7 +125,8 @@ class Renderer:
 
     def render_async(self, viewport, pixels, zbuffer=None):
         """Pipelined render(): queues the frame and its copy into `pixels` (page-locked: alloc_host) and returns a
-        ticket; the image is complete after wait(ticket).  Alternate between two host images."""
+        ticket; the image is complete after wait(ticket).  Up to three frames may be in flight: rotate over two or three
+        host images and wait for a frame before its image is used again."""
         vd = viewport.desc() if not isinstance(viewport, _abi.ViewportDesc) else viewport
         zptr = zbuffer.ctypes.data if zbuffer is not None else None
         ticket = C.c_uint64(0)

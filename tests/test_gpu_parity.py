@@ -692,6 +692,67 @@ def test_partial_readback_equals_full_copy(renderer, name):
         renderer.set_partial_readback(True)
 
 
+@pytest.mark.parametrize("partial", [False, True])
+@pytest.mark.parametrize("name", ["truck_1080", "truck_4k_dof"])
+def test_three_frames_in_flight_staged_boxes(renderer, name, partial):
+    """render_async keeps three device staging images and copies into one only the union of the box of the frame it holds
+    and the new frame's (k_stage_rect): with three frames in flight over a moving camera -- the object wanders, leaves the
+    screen, comes back, so every staging image sees growing, shrinking and empty boxes -- every host image equals the
+    blocking render()'s.  With partial read-back off the WHOLE staging image crosses PCIe, which checks that it stayed a
+    complete frame."""
+    from swegl_b200.scene import Viewport
+    scene, vps, screen, cfg = configs.build(name)
+    base = vps[0]
+    renderer.upload_scene(scene)
+    renderer.set_screen(*screen)
+    poses = [configs.POSE_TEST1,
+             [("translate", 2.5, 2, -5), ("rotate_y", -0.2), ("rotate_x", -0.3)],
+             [("translate", -1.5, 3, -6), ("rotate_y", 0.3), ("rotate_x", -0.4)],
+             [("translate", 0, 0, -5), ("rotate_y", 3.14159)],                     # looks away: nothing drawn
+             configs.POSE_CLOSE,
+             [("translate", 0, 0, -5), ("rotate_y", 3.14159)],
+             [("translate", 0, 0, -5), ("rotate_y", 3.14159)],
+             [("translate", 1, 2, -9), ("rotate_y", -0.2), ("rotate_x", -0.3)],
+             [("translate", -2.5, 1, -7), ("rotate_y", 0.25)],
+             configs.POSE_TEST1, configs.POSE_CLOSE]
+    views = []
+    for pose in poses:
+        v = Viewport(0, 0, screen[0], screen[1], transparency_layers=0, post_mode=base.post_mode, focal_distance=base.focal_distance,
+                     focal_depth=base.focal_depth)
+        v.camera.apply(pose)
+        views.append(v)
+    want = []
+    for v in views:
+        px = np.zeros((screen[1], screen[0]), np.uint32)
+        renderer.begin_frame(scene); renderer.render(v, px)
+        want.append(px)
+    images = [renderer.alloc_host((screen[1], screen[0]), np.uint32) for _ in range(3)]
+    for im in images:
+        im[:] = 0xDEADBEEF
+    renderer.set_partial_readback(partial)
+    try:
+        renderer.readback_stats(reset=True)
+        tickets = []
+        for i, v in enumerate(views):
+            renderer.begin_frame(scene)
+            tickets.append(renderer.render_async(v, images[i % 3]))
+            if i >= 2:
+                renderer.wait(tickets[i - 2])
+                assert (images[(i - 2) % 3] == want[i - 2]).all(), f"frame {i - 2}"
+                if not partial:
+                    images[(i - 2) % 3][:] = 0xDEADBEEF         # every frame has to arrive whole
+        for i in (len(views) - 2, len(views) - 1):
+            renderer.wait(tickets[i])
+            assert (images[i % 3] == want[i]).all(), f"frame {i}"
+        nbytes, nframes = renderer.readback_stats()
+        full = screen[0] * screen[1] * 4 * len(views)
+        assert nframes == len(views)
+        assert nbytes < 0.7 * full if partial else nbytes == full
+    finally:
+        renderer.set_partial_readback(True)
+        renderer.invalidate_host_image(None)
+
+
 def test_host_readback_refused_while_a_colour_target_is_set(renderer):
     from swegl_b200 import Renderer
     from swegl_b200.renderer import SweglB200Error
