@@ -320,7 +320,7 @@ void swegl_b200_destroy(swegl_b200_ctx *ctx)
     void *ptrs[] = { ctx->d_pos, ctx->d_nrm, ctx->d_uv, ctx->d_vert_node, ctx->d_texels, ctx->d_tris, ctx->d_prims,
                      ctx->d_v_world, ctx->d_v_ndc, ctx->d_n_world, ctx->d_yes, ctx->d_block,
                      ctx->pools.edges, ctx->pools.shades, ctx->pools.spans, ctx->pools.span_shades, ctx->pools.frag_u, ctx->pools.row_slot,
-                     ctx->pools.chunks, ctx->pools.bin_head, ctx->pools.bin_cnt, ctx->pools.bin_slots, ctx->pools.dof_list, ctx->pools.tile_stamp, ctx->pools.busy_list,
+                     ctx->pools.chunks, ctx->pools.bin_head, ctx->pools.bin_cnt, ctx->pools.bin_slots, ctx->pools.dof_list, ctx->pools.tile_stamp, ctx->pools.busy_list, ctx->pools.tile_cost,
                      ctx->pools.counters, ctx->d_screen, ctx->d_depth,
                      ctx->d_tmp_color, ctx->d_cl_box, ctx->d_cl_adj_off, ctx->d_cl_adj, ctx->d_vb_adj_off, ctx->d_vb_adj, ctx->d_cull_flags, ctx->d_cull_lists, ctx->d_anim };
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -607,7 +607,11 @@ int swegl_b200_set_screen(swegl_b200_ctx *ctx, int32_t w, int32_t h)
     ctx->dof_tm_w = ctx->dof_tm_h = 0;                  // d_tmp_color / d_depth moved: the tensor maps are stale
     CK(dalloc(ctx->pools.tile_stamp, bins));            // (a tile is at least one bin)
     CK(cudaMemset(ctx->pools.tile_stamp, 0, bins * 4));
-    CK(dalloc(ctx->pools.busy_list, bins));
+    CK(dalloc(ctx->pools.busy_list, 4 * bins));         // four cost classes, each able to hold every tile
+    ctx->pools.busy_stride = (uint32_t)bins;
+    CK(dalloc(ctx->pools.tile_cost, bins + 2));         // + the running sum and the last frame's mean
+    CK(cudaMemset(ctx->pools.tile_cost, 0, (bins + 2) * 4));
+    ctx->pools.cost_acc = ctx->pools.tile_cost + bins;
     ctx->bins_cap = bins;
     ctx->sw = w; ctx->sh = h;
     ctx->color_target = nullptr;

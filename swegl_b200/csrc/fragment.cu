@@ -479,6 +479,7 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
     __shared__ FrameParams fp;
     __shared__ FragWarp fwarp[FRAG_ROWS];
     __shared__ uint32_t s_next[2];
+    __shared__ uint32_t s_nb[4], s_cost[2];                                 // entries of the busy list's cost classes; start clock and tile of the current item
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int band_rows = g.band1 - g.band0, anchor = g.band0 - g.vy;
     pdl_trigger();
@@ -491,6 +492,8 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
     Counters *const cn = pl.counters;
     const uint32_t n_busy = cn->n_busy;
     const uint32_t stamp = vp.stamp;
+    if (threadIdx.x < 4) s_nb[threadIdx.x] = cn->n_busy_b[threadIdx.x];
+    __syncthreads();
     FRAG_TL(1, global_ns());
 #ifdef FRAG_PROBE_TIMELINE
     int tl_slot = 2;
@@ -565,9 +568,13 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
             const bool tl_first = tl_slot == 2;
 #endif
             FRAG_PH(8);
-            const uint32_t t = pl.busy_list[p];                             // tile row << 16 | tile column (k_spans)
+            uint32_t q = p, cls = 0;                                        // item p of the heaviest-first order: entry q of cost class cls
+            #pragma unroll
+            for (uint32_t k = 0; k < 3; k++) { const uint32_t nk = s_nb[k]; if (cls == k && q >= nk) { q -= nk; cls = k + 1; } }
+            const uint32_t t = pl.busy_list[cls * pl.busy_stride + q];      // tile row << 16 | tile column (k_spans)
             const int ty = (int)(t >> 16), tx = (int)(t & 0xFFFFu);
             if (t == 0xFFFFFFFEu) break;                                    // (never: makes the stamp below wait for the load)
+            if (threadIdx.x == 0) { s_cost[0] = (uint32_t)clock(); s_cost[1] = (uint32_t)(ty * g.ntx + tx); }
             FRAG_PH(9);
             tx0 = min(tx0, (uint32_t)tx); tx1 = max(tx1, (uint32_t)tx + 1); ty0 = min(ty0, (uint32_t)ty); ty1 = max(ty1, (uint32_t)ty + 1);
             if (warp >= min(FRAG_ROWS, band_rows - ty * FRAG_ROWS)) break;
@@ -758,6 +765,11 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
 #ifdef FRAG_PROBE_TIMELINE
         FRAG_TL(tl_slot, (global_ns() << 1) | (p >= n_busy ? 1ull : 0ull)); tl_slot++;
 #endif
+        if (threadIdx.x == 0 && p < n_busy) {                               // what this tile cost: the next frame's hint for the order
+            const uint32_t cost = ((uint32_t)clock() - s_cost[0]) >> 6;
+            pl.tile_cost[s_cost[1]] = cost;
+            atomicAdd(&pl.cost_acc[0], cost);
+        }
         p = s_next[it];
     }
     if (count_covered && lane == 0 && my_covered) atomicAdd(&cn->n_covered, my_covered);
@@ -772,10 +784,12 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
             atomicMax(&cn->bb_y1, min((uint32_t)(anchor + band_rows), (uint32_t)anchor + ty1 * FRAG_ROWS));
         }
         __threadfence();
-        if (atomicAdd(&cn->frag_done, 1u) == gridDim.x - 1 && h_counters_out) {
+        if (atomicAdd(&cn->frag_done, 1u) == gridDim.x - 1) {
             __threadfence();
-            for (int w = 0; w < (int)(sizeof(Counters) / 4); w++)
-                reinterpret_cast<volatile uint32_t *>(h_counters_out)[w] = reinterpret_cast<volatile const uint32_t *>(cn)[w];
+            if (n_busy) pl.cost_acc[1] = atomicExch(&pl.cost_acc[0], 0u) / n_busy;     // mean tile cost of this frame
+            if (h_counters_out)
+                for (int w = 0; w < (int)(sizeof(Counters) / 4); w++)
+                    reinterpret_cast<volatile uint32_t *>(h_counters_out)[w] = reinterpret_cast<volatile const uint32_t *>(cn)[w];
         }
     }
 }

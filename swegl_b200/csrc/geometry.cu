@@ -615,8 +615,17 @@ SB_DEV void walk_segment(const Pools &pl, const ViewParams &vp, const SH &sh, in
     // otherwise divide by the tiles-per-row count)
     #pragma unroll
     for (int j = 0; j < (int)SPAN_SEG; j++)
-        if (tl[j] != 0xFFFFFFFFu && old[j] != vp.stamp)
-            pl.busy_list[atomicAdd(&pl.counters->n_busy, 1u)] = ((uint32_t)((row_rel - (vp.band0 - vp.vy)) / FRAG_ROWS) << 16) | (uint32_t)((b0 + j) / FRAG_STRETCH);
+        if (tl[j] != 0xFFFFFFFFu && old[j] != vp.stamp) {
+            const uint32_t c = pl.tile_cost[tl[j]], m = pl.cost_acc[1];      // last measured cost of this tile, mean of that frame
+#ifdef FRAG_NO_COST_ORDER       // A/B: one class, first-touch order
+            const uint32_t cls = c + m == 0xFFFFFFFFu ? 1u : 0u;
+#else
+            const uint32_t cls = c * 2u >= m * 3u ? 0u : (c >= m ? 1u : (c * 2u >= m ? 2u : 3u));
+#endif
+            pl.busy_list[cls * pl.busy_stride + atomicAdd(&pl.counters->n_busy_b[cls], 1u)] =
+                ((uint32_t)((row_rel - (vp.band0 - vp.vy)) / FRAG_ROWS) << 16) | (uint32_t)((b0 + j) / FRAG_STRETCH);
+            atomicAdd(&pl.counters->n_busy, 1u);
+        }
 }
 
 // shared state of one CTA pass over SPAN_ROWS scanline records
