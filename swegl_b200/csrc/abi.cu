@@ -901,7 +901,12 @@ static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const Vie
     FrameSync *const tgt_sync = ctx->color_target ? reinterpret_cast<FrameSync *>(ctx->color_target + (size_t)ctx->sw * ctx->sh) : own_sync;
     const bool skip_bg = synced && ctx->sync_rank > 0 && !dof;
     if (synced && ctx->sync_rank == 0) { launch_sync_clear(out, ctx->d_vp(), ctx->d_screen, ctx->sw, own_sync, !dof, st); launches++; }
+    // a band of a sharded frame is a latency chain on an otherwise idle GPU: its kernels release their successors early
+    // (common.cuh pdl_trigger); whole views, which share the GPU with other contexts' frames, do not
+    const uint32_t early = (vp.band0 > vp.vy || vp.band1 < vp.vy + vp.vh) ? 1u : 0u;
+    ctx->pools.early_trigger = early; ctx->cull.early_trigger = early;
     DeviceScene ds = ctx->ds;
+    ds.early_trigger = early;
     if (view_culled(ctx, vp)) {                             // sort-first band: skip what cannot reach it (common.cuh)
         ds.cl_live = ctx->cull.cl_live; ds.mark_need = ctx->cull.mark_need; ds.vert_need = ctx->cull.vert_need;
         ds.live_list = ctx->cull.live_list; ds.mark_list = ctx->cull.mark_list; ds.vert_list = ctx->cull.vert_list;

@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
     __shared__ uint32_t s_nb[4], s_cost[2];                                 // entries of the busy list's cost classes; start clock and tile of the current item
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int band_rows = g.band1 - g.band0, anchor = g.band0 - g.vy;
-    pdl_trigger();
+    pdl_trigger(pl.early_trigger);
     FRAG_TL(0, global_ns());
     // the parameter block is written by the copy at the head of the chain, not by a kernel: readable before the wait
     for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += FRAG_TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
@@ -797,7 +797,7 @@ __global__ void __launch_bounds__(FRAG_TPB, FRAG_MINB) k_fragments(DeviceScene s
 // DoF tile classification on its own (the transparency-layer kernel has no persistent warps to fold it into)
 __global__ void __launch_bounds__(256) k_dof_classify(const ViewParams *__restrict__ vpp, Pools pl, FragGeom g, uint32_t *__restrict__ dof_dst)
 {
-    pdl_trigger();
+    pdl_trigger(pl.early_trigger);
     __shared__ ViewParams vp;
     for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += 256) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
     __syncthreads();
@@ -851,7 +851,7 @@ __global__ void __launch_bounds__(FRAG_TPB) k_fragments_layers(DeviceScene s, co
                                                                float *__restrict__ depth, int count_covered,
                                                                Counters *__restrict__ h_counters_out)
 {
-    pdl_trigger();
+    pdl_trigger(pl.early_trigger);
     pdl_wait();
     if (h_counters_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < sizeof(Counters) / 4)
         reinterpret_cast<uint32_t *>(h_counters_out)[threadIdx.x] = reinterpret_cast<const uint32_t *>(pl.counters)[threadIdx.x];
@@ -1061,7 +1061,7 @@ __global__ void __launch_bounds__(DOF_THREADS, 4) k_dof(const __grid_constant__ 
     extern __shared__ __align__(128) unsigned char dof_smem_raw[];
     DofSmem &sm = *reinterpret_cast<DofSmem *>(dof_smem_raw);
     const int tid = threadIdx.x;
-    pdl_trigger();
+    pdl_trigger(pl.early_trigger);
     // ---- prologue, independent of the predecessor ----
     for (int k = tid; k < (int)(sizeof(ViewParams) / 4); k += DOF_THREADS) reinterpret_cast<uint32_t *>(&sm.vp)[k] = reinterpret_cast<const uint32_t *>(vpp)[k];
     if (tid < 128) sm.magic[tid] = tid ? (uint32_t)(((1u << 28) + tid - 1) / tid) : 0u;
@@ -1291,7 +1291,7 @@ SB_DEV void st_sys(uint32_t *p, uint32_t v) { asm volatile("st.relaxed.sys.globa
 __global__ void __launch_bounds__(256) k_sync_clear(const ViewParams *__restrict__ vpp, uint32_t *__restrict__ screen, int pitch,
                                                     FrameSync *own, int vx, int vy, int vw, int vh, int band0, int band1, int do_clear)
 {
-    pdl_trigger();
+    pdl_trigger(1u);
     if (blockIdx.x == 0 && threadIdx.x == 0) own->t_begin = global_ns();
     if (do_clear) {
         const int rows_above = band0 - vy, rows_out = vh - (band1 - band0);
@@ -1336,7 +1336,7 @@ __global__ void k_sync_wait_ready(const ViewParams *__restrict__ vpp, const Fram
             if (clock64() - t0 > SYNC_TIMEOUT_CYCLES) { atomicAdd(&own->error, 1u); break; }
     }
     __syncwarp();
-    pdl_trigger();
+    pdl_trigger(1u);
     pdl_wait();                                                             // keeps completion transitive along the chain
 }
 

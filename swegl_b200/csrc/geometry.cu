@@ -44,7 +44,7 @@ SB_DEV void append_ids(uint32_t *list, uint32_t *count, bool set, uint32_t id)
 
 __global__ void __launch_bounds__(128) k_cull_live(DeviceScene s, const ViewParams *__restrict__ vpp, CullTables ct)
 {
-    pdl_trigger();
+    pdl_trigger(s.early_trigger);
     const uint32_t c = blockIdx.x * 128 + threadIdx.x;
     const bool valid = c < ct.n_clusters;
     ClusterBox box;
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(128) k_cull_live(DeviceScene s, const ViewPara
 // One thread per cluster (mark_need) and per vertex block (vert_need): OR of cl_live over a static adjacency list.
 __global__ void __launch_bounds__(128) k_cull_need(CullTables ct)
 {
-    pdl_trigger();
+    pdl_trigger(ct.early_trigger);
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
     const bool is_cl = i < ct.n_clusters;
     const uint32_t j = is_cl ? i : i - ct.n_clusters;
@@ -137,7 +137,7 @@ SB_DEV void vertex_one(const DeviceScene &s, const ViewParams &vp, uint32_t i)
 template <bool WORLD>
 __global__ void __launch_bounds__(TPB, 8) k_vertex(DeviceScene s, const ViewParams *__restrict__ vpp, Counters *__restrict__ counters)
 {
-    pdl_trigger();
+    pdl_trigger(s.early_trigger);
     __shared__ ViewParams vp;
     if (blockIdx.x == 0 && threadIdx.x < sizeof(Counters) / 4)
         reinterpret_cast<uint32_t *>(counters)[threadIdx.x] = (threadIdx.x == offsetof(Counters, bb_x0) / 4 || threadIdx.x == offsetof(Counters, bb_y0) / 4) ? COUNTERS_BB_MIN_INIT : 0u;
@@ -186,7 +186,7 @@ SB_DEV void mark_one(const DeviceScene &s, const Tri &tr)
 
 __global__ void __launch_bounds__(TPB) k_mark(DeviceScene s)
 {
-    pdl_trigger();
+    pdl_trigger(s.early_trigger);
     if (s.mark_list) {
         // culled view: only clusters that share a vertex with a cluster reaching the band can mark a vertex that is looked at
         pdl_wait();                                                         // k_vertex (and, through it, k_cull_need's list)
@@ -500,7 +500,7 @@ SB_DEV void setup_one(const DeviceScene &s, const ViewParams &vp, const FramePar
 __global__ void __launch_bounds__(128, SETUP_MINB) k_setup(DeviceScene s, const ViewParams *__restrict__ vpp,
                                                const FrameParams *__restrict__ fpp, Pools pl)
 {
-    pdl_trigger();
+    pdl_trigger(s.early_trigger);
     __shared__ ViewParams vp;                   // staged once per CTA: used all over the set-up code
     __shared__ FrameParams fp;
     for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += 128) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
@@ -653,7 +653,7 @@ __global__ void __launch_bounds__(SPAN_TPB, SPAN_MINB) k_spans(const ViewParams 
 {
     __shared__ SpanCta sh;
     __shared__ ViewParams vp;
-    pdl_trigger();
+    pdl_trigger(pl.early_trigger);
     for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += SPAN_TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
     __syncthreads();
     pdl_wait();                                                             // k_setup's records and counters
@@ -831,7 +831,7 @@ __global__ void __launch_bounds__(TPB) k_spans_dense(const ViewParams *__restric
 {
     __shared__ SpanCtaDense sh;
     __shared__ ViewParams vp;
-    pdl_trigger();
+    pdl_trigger(pl.early_trigger);
     for (int w = threadIdx.x; w < (int)(sizeof(ViewParams) / 4); w += TPB) reinterpret_cast<uint32_t *>(&vp)[w] = reinterpret_cast<const uint32_t *>(vpp)[w];
     __syncthreads();
     pdl_wait();                                                             // k_setup's records and counters
