@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SWEGL_B200_ABI_VERSION 3
+#define SWEGL_B200_ABI_VERSION 4
 
 /* ---- status codes (reference has none: void + assert, renderer.cpp:98-100) ---- */
 enum {
@@ -266,6 +266,14 @@ int  swegl_b200_readback_stats(swegl_b200_ctx *ctx, uint64_t out[2], int reset);
 /* SWEGL_B200_SHADING_EXACT / _FAST for the frames submitted from now on (environment override at create:
  * SWEGL_B200_SHADING=exact|fast).  No reference counterpart: the reference has one arithmetic. */
 int  swegl_b200_set_shading(swegl_b200_ctx *ctx, int mode);
+
+/* shared != 0: other contexts render on this context's GPU at the same time (several frames in flight, one context each:
+ * swegl_b200::pipeline_t, swegl_b200/pipeline.py).  The context then prefers kernel shapes that hold fewer SM resources
+ * while they wait over the ones with the shortest critical path (today: the span kernel at 128 instead of 256 threads
+ * per 32 scanlines -- a single frame takes ~5 us longer, four contexts together render ~6 % more frames per second).
+ * Same pixels either way.  Default off (environment override at create: SWEGL_B200_SHARED_GPU=0|1).  No reference
+ * counterpart. */
+int  swegl_b200_set_shared_gpu(swegl_b200_ctx *ctx, int shared);
 
 /* FNV-1a-64 over 32-bit words (offset basis 1469598103934665603, prime 1099511628211, one multiply per word): the frame
  * fingerprint of SURVEY 8c / tests/golden/MANIFEST.json.  Host side, no device involved. */

@@ -15,7 +15,7 @@ LIGHT_NONE, LIGHT_FLAT, LIGHT_PHONG = 0, 1, 2
 TEX_PLAIN, TEX_NEAREST, TEX_BILINEAR = 0, 1, 2
 POST_NULL, POST_DOF = 0, 1
 SHADING_EXACT, SHADING_FAST = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class Primitive(C.Structure):
@@ -105,6 +105,7 @@ SYMBOLS = [
     ("swegl_b200_invalidate_host_image", C.c_int, [C.c_void_p, C.c_void_p]),
     ("swegl_b200_readback_stats", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     ("swegl_b200_set_shading", C.c_int, [C.c_void_p, C.c_int]),
+    ("swegl_b200_set_shared_gpu", C.c_int, [C.c_void_p, C.c_int]),
     ("swegl_b200_frame_hash", C.c_uint64, [C.c_void_p, C.c_size_t]),
     ("swegl_b200_export_screen", C.c_int, [C.c_void_p, C.c_void_p]),
     ("swegl_b200_import_screen", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),

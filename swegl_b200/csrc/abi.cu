@@ -36,6 +36,7 @@ struct swegl_b200_ctx {
     float *d_v_world = nullptr, *d_v_ndc = nullptr, *d_n_world = nullptr; uint8_t *d_yes = nullptr;
     bool opaque = true;            // every material and texel has alpha 255
     bool fast_shading = true;      // Phong lighting within +-1 LSB (swegl_b200_set_shading); false: bit-exact
+    bool shared_gpu = false;       // other contexts render on this GPU at the same time (swegl_b200_set_shared_gpu): kernels that hold fewer SM resources
     // device-side scene_t::animate (animate.cu): one allocation holding every static table + the scratch matrices
     AnimTables anim{}; uint8_t *d_anim = nullptr; bool have_anim = false;
     bool frame_animated = false;   // the staged frame's node matrices come from k_animate (begin_frame_animated), not from the host
@@ -301,6 +302,8 @@ int swegl_b200_create(int device, swegl_b200_ctx **out)
         ctx->span_policy = !strcmp(e, "dense") ? 1 : (!strcmp(e, "coop") ? 0 : -1);
         ctx->dense_spans = ctx->span_policy == 1;
     }
+    if (const char *e = getenv("SWEGL_B200_SHARED_GPU"))      // "1" / "0": the default of swegl_b200_set_shared_gpu
+        ctx->shared_gpu = atoi(e) != 0;
     if (const char *e = getenv("SWEGL_B200_SHADING"))         // "exact" pins bit-exact Phong lighting, "fast" the +-1 LSB path (default)
         ctx->fast_shading = strcmp(e, "exact") != 0;
     if (const char *e = getenv("SWEGL_B200_DOF_TMA"))         // "0": stage the DoF windows with plain loads instead of TMA
@@ -918,7 +921,7 @@ static uint32_t issue_view(swegl_b200_ctx *ctx, const ViewParams &out, const Vie
     if (timing) cudaEventRecord(ctx->ev[1], st);
     launch_setup(ds, ctx->d_vp(), ctx->d_fp(), ctx->pools, st); launches++;
     if (timing) cudaEventRecord(ctx->ev[2], st);
-    launch_spans(ctx->d_vp(), ctx->pools, ctx->dense_spans, st); launches++;
+    launch_spans(ctx->d_vp(), ctx->pools, ctx->dense_spans, ctx->shared_gpu && !early, st); launches++;
     if (timing) cudaEventRecord(ctx->ev[3], st);
     uint32_t *screen_out = ctx->color_target ? ctx->color_target : ctx->d_screen;
     uint32_t *color = dof ? ctx->d_tmp_color - ((size_t)vp.vy * vp.vw + vp.vx) : screen_out;
@@ -1012,7 +1015,7 @@ static int render_async(swegl_b200_ctx *ctx, const ViewParams &out, bool dof)
         const uint64_t tgt = (uint64_t)reinterpret_cast<uintptr_t>(ctx->color_target);
         const int32_t key[15] = { out.vx, out.vy, out.vw, out.vh, out.band0, out.band1, out.light_mode, out.tex_mode, (dof ? 1 : 0) | (out.n_layers << 1),
                                   ctx->sw, ctx->sh, (with_frame ? 1 : 0) | (synced ? 2 + 4 * ctx->sync_rank + 256 * ctx->sync_world : 0),
-                                  (ctx->dense_spans ? 1 : 0) | (with_world ? 2 : 0) | (ctx->fast_shading ? 4 : 0) | (tma ? 8 : 0) | (with_frame && ctx->frame_animated ? 16 : 0),
+                                  (ctx->dense_spans ? 1 : 0) | (with_world ? 2 : 0) | (ctx->fast_shading ? 4 : 0) | (tma ? 8 : 0) | (with_frame && ctx->frame_animated ? 16 : 0) | (ctx->shared_gpu ? 32 : 0),
                                   (int32_t)(tgt & 0xFFFFFFFFu), (int32_t)(tgt >> 32) };
         swegl_b200_ctx::ViewGraph *vg = nullptr;
         for (auto &g : ctx->view_graphs) if (memcmp(g.key, key, sizeof key) == 0) { vg = &g; break; }
@@ -1329,6 +1332,13 @@ int swegl_b200_set_shading(swegl_b200_ctx *ctx, int mode)
 {
     if (!ctx || mode < 0 || mode > 1) return fail(ctx, SWEGL_B200_ERR_ARG, "set_shading: mode must be SWEGL_B200_SHADING_EXACT or SWEGL_B200_SHADING_FAST");
     ctx->fast_shading = mode == SWEGL_B200_SHADING_FAST;        // (part of the graph key: no re-capture needed)
+    return SWEGL_B200_OK;
+}
+
+int swegl_b200_set_shared_gpu(swegl_b200_ctx *ctx, int shared)
+{
+    if (!ctx) return SWEGL_B200_ERR_ARG;
+    ctx->shared_gpu = shared != 0;                              // (part of the graph key: no re-capture needed)
     return SWEGL_B200_OK;
 }
 

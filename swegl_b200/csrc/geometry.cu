@@ -648,8 +648,19 @@ struct SpanCta {
 #ifndef SPAN_TPB_V
 #define SPAN_TPB_V 256
 #endif
-static constexpr int SPAN_TPB = SPAN_TPB_V;
-__global__ void __launch_bounds__(SPAN_TPB, SPAN_MINB) k_spans(const ViewParams *__restrict__ vpp, Pools pl)
+// Two widths of the same kernel.  256 threads per 32 scanline records give the shortest critical path (phase A is one
+// round, phase C one round) -- but phase B occupies one warp of the eight and phase C a quarter of the threads, and the
+// idle ones hold registers and warp slots.  A context that shares its GPU with other contexts' frames
+// (swegl_b200_set_shared_gpu) takes the 128-thread width: alone the kernel is slower (truck 4K 31 -> 36 us), four contexts
+// together render 6 % more frames per second (profiles/README.md).
+#ifndef SPAN_NARROW_TPB
+#define SPAN_NARROW_TPB 128
+#endif
+#ifndef SPAN_NARROW_MINB
+#define SPAN_NARROW_MINB 10
+#endif
+template <int SPAN_TPB, int MINB>
+__global__ void __launch_bounds__(SPAN_TPB, MINB) k_spans(const ViewParams *__restrict__ vpp, Pools pl)
 {
     __shared__ SpanCta sh;
     __shared__ ViewParams vp;
@@ -981,10 +992,11 @@ void launch_setup(const DeviceScene &s, const ViewParams *d_vp, const FrameParam
 {
     if (s.n_tris) launch_chain(k_setup, s.live_list ? min(cdiv(s.n_tris, 128u), 148u * SETUP_MINB * 2u) : cdiv(s.n_tris, 128u), 128, st, true, s, d_vp, d_fp, p);
 }
-void launch_spans(const ViewParams *d_vp, const Pools &p, bool dense, cudaStream_t st)
+void launch_spans(const ViewParams *d_vp, const Pools &p, bool dense, bool narrow, cudaStream_t st)
 {
     if (dense) launch_chain(k_spans_dense, 148 * 8, TPB, st, true, d_vp, p);      // persistent CTAs, 256 scanline records per pass
-    else launch_chain(k_spans, 148 * 16 * (256 / SPAN_TPB), SPAN_TPB, st, true, d_vp, p);   // persistent CTAs, SPAN_ROWS scanline records per pass
+    else if (narrow) launch_chain(k_spans<SPAN_NARROW_TPB, SPAN_NARROW_MINB>, 148 * 16 * (256 / SPAN_NARROW_TPB), SPAN_NARROW_TPB, st, true, d_vp, p);
+    else launch_chain(k_spans<SPAN_TPB_V, SPAN_MINB>, 148 * 16 * (256 / SPAN_TPB_V), SPAN_TPB_V, st, true, d_vp, p);   // persistent CTAs, SPAN_ROWS scanline records per pass
 }
 
 } // namespace sb

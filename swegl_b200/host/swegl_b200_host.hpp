@@ -35,6 +35,8 @@ public:
 	pipeline_t(int device, int depth)
 	{
 		for (int i = 0; i < std::max(1, depth); i++) m_engines.push_back(std::make_unique<engine_t>(device));
+		if (m_engines.size() > 1)           // the contexts' frames overlap on the GPU: kernels that hold fewer SM resources
+			for (auto & e : m_engines) e->check(swegl_b200_set_shared_gpu(e->ctx(), 1), "set_shared_gpu");
 	}
 
 	int depth() const { return (int)m_engines.size(); }

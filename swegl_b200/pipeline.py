@@ -21,6 +21,9 @@ class FramePipeline:
         self.depth = int(depth)
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.depth)]
         self.renderers = [Renderer(self.device, stream=s.cuda_stream) for s in self.streams]
+        if self.depth > 1:
+            for r in self.renderers:
+                r.set_shared_gpu(True)          # the contexts' frames overlap on the GPU
         self.next = 0
 
     def close(self):

@@ -143,6 +143,10 @@ class Renderer:
         """_abi.SHADING_EXACT (bit-exact Phong lighting) or _abi.SHADING_FAST (within +-1 LSB per colour channel, default)"""
         self._check(self.lib.swegl_b200_set_shading(self.ctx, int(mode)))
 
+    def set_shared_gpu(self, shared=True):
+        """other contexts render on this GPU at the same time (FramePipeline): prefer kernels that hold fewer SM resources"""
+        self._check(self.lib.swegl_b200_set_shared_gpu(self.ctx, int(bool(shared))))
+
     def set_partial_readback(self, enabled=True):
         self._check(self.lib.swegl_b200_set_partial_readback(self.ctx, int(bool(enabled))))
 

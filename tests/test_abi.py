@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/swegl_b200.h but not exported"
     bound = {n for n, _, _ in _abi.SYMBOLS}
     assert set(names) == bound, f"ctypes bindings and header differ: {set(names) ^ bound}"
-    assert lib.swegl_b200_abi_version() == _abi.ABI_VERSION == 3
+    assert lib.swegl_b200_abi_version() == _abi.ABI_VERSION == 4
 
 
 def test_struct_layouts_match_the_header():

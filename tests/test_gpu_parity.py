@@ -753,6 +753,28 @@ def test_three_frames_in_flight_staged_boxes(renderer, name, partial):
         renderer.invalidate_host_image(None)
 
 
+@pytest.mark.parametrize("name", ["truck_1080", "box_640"])
+def test_shared_gpu_mode_renders_the_same_frame(renderer, name):
+    """swegl_b200_set_shared_gpu selects kernel shapes (the 128-thread span kernel), not results: colour and depth of a
+    frame are identical with and without it"""
+    scene, vps, screen, cfg = configs.build(name)
+    renderer.upload_scene(scene)
+    renderer.set_screen(*screen)
+    got = []
+    try:
+        for shared in (False, True, False):
+            renderer.set_shared_gpu(shared)
+            px = np.zeros((screen[1], screen[0]), np.uint32); z = np.empty((vps[0].h, vps[0].w), np.float32)
+            renderer.begin_frame(scene)
+            st = renderer.render(vps[0], px, z)
+            got.append((px, z, st.n_covered))
+    finally:
+        renderer.set_shared_gpu(False)
+    assert got[0][2] > 0
+    for px, z, n in got[1:]:
+        assert n == got[0][2] and (px == got[0][0]).all() and (z.view(np.uint32) == got[0][1].view(np.uint32)).all()
+
+
 def test_host_readback_refused_while_a_colour_target_is_set(renderer):
     from swegl_b200 import Renderer
     from swegl_b200.renderer import SweglB200Error
