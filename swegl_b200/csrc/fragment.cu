@@ -1054,7 +1054,7 @@ SB_DEV void mbar_wait(unsigned long long *bar, uint32_t parity)
     }
 }
 
-__global__ void __launch_bounds__(DOF_THREADS, 4) k_dof(const __grid_constant__ CUtensorMap tm_color, const __grid_constant__ CUtensorMap tm_depth,
+__global__ void __launch_bounds__(DOF_THREADS, DOF_CTAS_PER_SM) k_dof(const __grid_constant__ CUtensorMap tm_color, const __grid_constant__ CUtensorMap tm_depth,
                                                         const ViewParams *__restrict__ vpp, Pools pl, DofGeom g,
                                                         const uint32_t *__restrict__ src, const float *__restrict__ depth, uint32_t *__restrict__ dst)
 {
